@@ -1,0 +1,111 @@
+/* roger_b200.h -- C ABI of the B200-native RoGeR SVAT / SAS compute backend.
+ *
+ * The reference (Hydrology-IFH/roger) has no FFI: its plug-in boundary is Python-level
+ * (roger/backend.py:3 BACKENDS, roger/core/operators.py:148-186, roger/routines.py:239-383,
+ * roger/roger.py:355-489 RogerSetup.step).  This header is what a `cuda` backend branch of
+ * those files binds through ctypes.  Plain pointers and sizes only,
+ * no torch / CUDA types in any signature; all device memory is owned by the handle or by
+ * the caller (raw device addresses passed as uint64_t).
+ *
+ * Return value of every int function: 0 on success, negative errno-style code on failure
+ * (-ROGER_EINVAL bad argument, -ROGER_ECUDA CUDA runtime error, -ROGER_ENODEV no CUDA device).
+ * roger_last_error() returns a human readable message for the calling thread.
+ */
+#ifndef ROGER_B200_H
+#define ROGER_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include "roger_b200_fields.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROGER_EINVAL 22
+#define ROGER_ENODEV 19
+#define ROGER_ECUDA 5
+#define ROGER_SLOTS_PER_DAY 144 /* 10-minute forcing slots, roger/models/svat/svat.py:150-174 */
+
+/* Model switches and physical constants read by the step (roger/settings.py:18-136). */
+typedef struct roger_svat_settings {
+    double ta_fm;               /* settings.ta_fm   freeze/melt threshold (degC)            */
+    double hpi;                 /* settings.hpi     heavy-rain threshold (mm/10 min)        */
+    double end_event;           /* settings.end_event (s)                                   */
+    double sf;                  /* settings.sf      degree-day factor                       */
+    double rmax;                /* settings.rmax    liquid water retention of snow (%)      */
+    double r_mp;                /* settings.r_mp    macropore radius (mm)                   */
+    double l_sc;                /* settings.l_sc    shrinkage crack length (mm/m2)          */
+    double pi;                  /* settings.pi                                              */
+    double transp_water_stress; /* settings.transp_water_stress                             */
+    double dx;                  /* settings.dx      (lateral flow only)                     */
+    double atol, rtol;          /* settings.atol/rtol used by numerics.sanity_check         */
+    int32_t enable_lateral_flow;                       /* oneD model                        */
+    int32_t enable_macropore_lower_boundary_condition; /* infiltration.py:1013              */
+    int32_t clamp_small_negative_storage; /* after_timestep clamp of S_fp/S_lp in (-1e-6,0),
+                                             models/svat/svat.py:333-352 (SVAT yes, oneD no) */
+    int32_t forcing_uniform;    /* 1: prec/ta/pet day blocks are 144 values shared by all cells
+                                   (benchmarks/SVAT_benchmark.py:162-170); 0: (C,144) per cell   */
+} roger_svat_settings;
+
+/* Global (grid-wide) scalars of the adaptive time stepping, roger/variables.py:198-460.
+ * event_id[0] = [taum1], event_id[1] = [tau]. */
+typedef struct roger_svat_scalars {
+    int64_t time;             /* vs.time (s)            */
+    int64_t itt;              /* vs.itt                 */
+    int64_t dt_secs;          /* vs.dt_secs             */
+    int64_t itt_day;          /* vs.itt_day             */
+    int64_t event_id[2];      /* vs.event_id            */
+    int64_t event_id_counter; /* vs.event_id_counter    */
+    int64_t time_event0;      /* vs.time_event0         */
+    int64_t month;            /* vs.month[tau] (1..12)  */
+    int64_t sanity_ok;        /* result of numerics.sanity_check for the last step (1/0) */
+    double dt;                /* vs.dt (h)              */
+} roger_svat_scalars;
+
+typedef struct roger_svat roger_svat; /* opaque handle */
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int roger_svat_create(roger_svat **out, int64_t n_cells, const roger_svat_settings *settings, int device);
+void roger_svat_destroy(roger_svat *h);
+const char *roger_last_error(void);
+int roger_svat_field_count(void);
+const char *roger_svat_field_name(int field);
+int roger_svat_field_kind(int field);
+
+/* ---- host <-> device mirrors of named planes (replaces RogerVariables.__setattr__/__getattr__
+ *      for the fields the step owns, roger/state.py:213-251).  `host` holds n_cells doubles. */
+int roger_svat_upload(roger_svat *h, int field, const double *host);
+int roger_svat_download(roger_svat *h, int field, double *host);
+/* raw device address of a plane (for zero-copy use from torch / other kernels) */
+uint64_t roger_svat_plane_ptr(roger_svat *h, int field);
+
+int roger_svat_set_scalars(roger_svat *h, const roger_svat_scalars *s);
+int roger_svat_get_scalars(roger_svat *h, roger_svat_scalars *s);
+
+/* ---- forcing: the day block that RogerSetup.set_forcing writes into vs.prec_day/ta_day/pet_day
+ *      at midnight (roger/models/svat/svat.py:150-174).  Host pointers; 144 doubles each when
+ *      settings.forcing_uniform, else n_cells*144 in the reference's (cell, slot) order.
+ *      The copy is asynchronous on the handle's stream from the caller's (ideally pinned) buffer. */
+int roger_svat_set_forcing_day(roger_svat *h, const double *prec_day, const double *ta_day,
+                               const double *pet_day);
+/* same, from buffers already resident on the device (raw addresses) */
+int roger_svat_set_forcing_day_device(roger_svat *h, uint64_t prec_day, uint64_t ta_day, uint64_t pet_day);
+
+/* ---- the hot path: ONE adaptive time step = adaptive_time_stepping + interception + ET + snow +
+ *      infiltration + percolation (+ lateral) + capillary rise + storages + numerical error +
+ *      after_timestep roll (roger/roger.py:389-485).  Updates scalars (time, itt, dt, ...).
+ *      write_fluxes != 0 additionally stores every F-kind plane (parity / diagnostics mode). */
+int roger_svat_step(roger_svat *h, int write_fluxes);
+/* run adaptive steps until vs.time reaches the next midnight (at most 144 steps); returns the
+ * number of steps taken through *n_steps. */
+int roger_svat_run_day(roger_svat *h, int write_fluxes, int *n_steps);
+int roger_svat_synchronize(roger_svat *h);
+/* CUDA-event time (ms) spent in kernels of the most recent roger_svat_step / run_day call and the
+ * number of kernel launches it made (bench.py roofline / gpu_launches). */
+int roger_svat_last_timing(roger_svat *h, double *kernel_ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROGER_B200_H */

@@ -1,0 +1,67 @@
+"""ctypes wrapper of the CPU oracle (oracle/svat_oracle.c).  TEST INFRASTRUCTURE: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libroger_oracle.so")
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or any(
+        os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(LIB) for f in ("svat_oracle.c", "sas_oracle.c")
+    ):
+        subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+class OracleSvatEngine:
+    """Same engine interface as roger_b200.engine.CudaSvatEngine, computed by the C oracle."""
+
+    def __init__(self, n_cells, settings):
+        from roger_b200 import abi
+
+        self.abi = abi
+        self.n = int(n_cells)
+        self.settings = settings
+        self.planes = np.zeros((abi.N_FIELDS, self.n), dtype=np.float64)
+        self.scalars = abi.initial_scalars()
+        self.forcing = None
+        self._fn = lib().svat_oracle_step
+        self._fn.restype = None
+
+    def upload(self, name, arr):
+        self.planes[self.abi.FIELD_ID[name]] = np.asarray(arr, dtype=np.float64).reshape(-1)
+
+    def download(self, name):
+        return self.planes[self.abi.FIELD_ID[name]].copy()
+
+    def set_scalars(self, s):
+        self.scalars = s
+
+    def get_scalars(self):
+        return self.scalars
+
+    def set_forcing_day(self, prec, ta, pet):
+        self.forcing = [np.ascontiguousarray(a, dtype=np.float64) for a in (prec, ta, pet)]
+
+    def step(self, write_fluxes=True):
+        p, t, e = self.forcing
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        self._fn(C.c_int64(self.n), dp(self.planes), dp(p), dp(t), dp(e), C.byref(self.scalars), C.byref(self.settings))
+
+    def synchronize(self):
+        pass

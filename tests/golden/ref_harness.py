@@ -1,0 +1,243 @@
+"""Runs the UNMODIFIED reference (read-only at /root/reference) in this container.
+
+TEST INFRASTRUCTURE ONLY -- used by the ``make_*_golden.py`` scripts to produce the
+committed fixtures under ``tests/golden/``.  Nothing on the GPU box imports this file
+(`/root/reference` does not exist there).
+
+The reference's NumPy backend is imported as-is; the only shims are empty stand-ins
+for the three IO packages that are absent offline (h5netcdf, h5py, cftime) -- they are
+never called because forcing is fed from memory and ``diskless_mode`` is on
+(roger/diagnostics/base.py:85, roger/restart.py:134).
+"""
+import sys
+import types
+import numpy as onp
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def import_reference(float_type="float64"):
+    for name in ("h5netcdf", "h5py", "cftime"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.File = None
+            m.date2num = None
+            sys.modules[name] = m
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import roger  # noqa
+
+    if not getattr(import_reference, "_done", False):
+        roger.runtime_settings.update(
+            backend="numpy",
+            float_type=float_type,
+            int_type="int64" if float_type == "float64" else "int32",
+            diskless_mode=True,
+            loglevel="error",
+        )
+        import_reference._done = True
+    return roger
+
+
+def make_svat_setup(case):
+    """Build a RogerSetup subclass mirroring benchmarks/SVAT_benchmark.py but with in-memory,
+    optionally per-cell forcing and heterogeneous parameters.
+
+    case: dict with nx, ny, ndays, PREC/TA/PET (1-D 10-min series), YEAR/MONTH/DOY, params dict of
+    (nx, ny) arrays, optional prec_weight/ta_offset/pet_weight (nx, ny), lateral (bool -> oneD).
+    """
+    roger = import_reference()
+    from roger import RogerSetup, roger_routine, roger_kernel, KernelOutput
+    from roger.variables import allocate
+    from roger.core.operators import numpy as npx, update, at
+    from roger.core.surface import calc_parameters_surface_kernel
+    import roger.lookuptables as lut
+
+    nx, ny, ndays = case["nx"], case["ny"], case["ndays"]
+    P = case["params"]
+    lateral = bool(case.get("lateral", False))
+
+    copy_tau = [
+        "ta", "z_root", "ground_cover", "S_sur", "S_int_top", "S_int_ground", "S_dep", "S_snow", "swe",
+        "S_rz", "S_ss", "S_s", "S", "z_sat", "z_wf", "z_wf_t0", "z_wf_t1", "y_mp", "y_sc", "theta_rz",
+        "theta_ss", "theta", "k_rz", "k_ss", "k", "h_rz", "h_ss", "h", "z0", "prec",
+    ]
+
+    class GoldenSetup(RogerSetup):
+        @roger_routine
+        def set_settings(self, state):
+            s = state.settings
+            s.identifier = "GOLDEN"
+            s.nx, s.ny = nx, ny
+            s.runlen = 24 * 60 * 60 * ndays
+            s.nitt_forc = len(case["PREC"])
+            s.dx = 1
+            s.dy = 1
+            s.x_origin = 0.0
+            s.y_origin = 0.0
+            s.time_origin = "2017-12-31 00:00:00"
+            s.enable_groundwater_boundary = False
+            s.enable_adaptive_time_stepping = True
+            if lateral:
+                s.enable_lateral_flow = True
+
+        @roger_routine
+        def read_data(self, state):
+            pass
+
+        @roger_routine(dist_safe=False, local_variables=["x", "y"])
+        def set_grid(self, state):
+            vs = state.variables
+            dx = allocate(state.dimensions, ("x"))
+            dx = update(dx, at[:], 1)
+            dy = allocate(state.dimensions, ("y"))
+            dy = update(dy, at[:], 1)
+            vs.x = update(vs.x, at[3:-2], npx.cumsum(dx[3:-2]))
+            vs.y = update(vs.y, at[3:-2], npx.cumsum(dy[3:-2]))
+
+        @roger_routine
+        def set_look_up_tables(self, state):
+            vs = state.variables
+            vs.lut_ilu = update(vs.lut_ilu, at[:, :], lut.ARR_ILU)
+            vs.lut_gc = update(vs.lut_gc, at[:, :], lut.ARR_GC)
+            vs.lut_gcm = update(vs.lut_gcm, at[:, :], lut.ARR_GCM)
+            vs.lut_is = update(vs.lut_is, at[:, :], lut.ARR_IS)
+            vs.lut_rdlu = update(vs.lut_rdlu, at[:, :], lut.ARR_RDLU)
+            if lateral:
+                vs.lut_mlms = update(vs.lut_mlms, at[:, :], lut.ARR_MLMS)
+
+        @roger_routine
+        def set_topography(self, state):
+            pass
+
+        @roger_routine
+        def set_parameters_setup(self, state):
+            vs = state.variables
+            for name, arr in P.items():
+                cur = getattr(vs, name)
+                setattr(vs, name, update(cur, at[2:-2, 2:-2], onp.asarray(arr).astype(cur.dtype)))
+            if lateral:
+                vs.slope_per = update(vs.slope_per, at[2:-2, 2:-2], vs.slope[2:-2, 2:-2] * 100)
+
+        @roger_routine
+        def set_parameters(self, state):
+            vs = state.variables
+            if (vs.month[vs.tau] != vs.month[vs.taum1]) & (vs.itt > 1):
+                vs.update(calc_parameters_surface_kernel(state))
+
+        @roger_routine
+        def set_initial_conditions_setup(self, state):
+            pass
+
+        @roger_routine
+        def set_initial_conditions(self, state):
+            vs = state.variables
+            th_rz = onp.asarray(case["theta_rz0"])[:, :, None]
+            th_ss = onp.asarray(case["theta_ss0"])[:, :, None]
+            vs.theta_rz = update(vs.theta_rz, at[2:-2, 2:-2, : vs.taup1], th_rz)
+            vs.theta_ss = update(vs.theta_ss, at[2:-2, 2:-2, : vs.taup1], th_ss)
+
+        @roger_routine
+        def set_boundary_conditions_setup(self, state):
+            pass
+
+        @roger_routine
+        def set_boundary_conditions(self, state):
+            pass
+
+        @roger_routine(dist_safe=False, local_variables=["PREC", "TA", "PET", "YEAR", "MONTH", "DOY"])
+        def set_forcing_setup(self, state):
+            vs = state.variables
+            vs.PREC = update(vs.PREC, at[:], case["PREC"])
+            vs.TA = update(vs.TA, at[:], case["TA"])
+            vs.PET = update(vs.PET, at[:], case["PET"])
+            vs.YEAR = update(vs.YEAR, at[:], case["YEAR"])
+            vs.MONTH = update(vs.MONTH, at[:], case["MONTH"])
+            vs.DOY = update(vs.DOY, at[:], case["DOY"])
+
+        @roger_routine
+        def set_forcing(self, state):
+            vs = state.variables
+            condt = vs.time % (24 * 60 * 60) == 0
+            if condt:
+                vs.itt_day = 0
+                vs.year = update(vs.year, at[1], vs.YEAR[vs.itt_forc])
+                vs.month = update(vs.month, at[1], vs.MONTH[vs.itt_forc])
+                vs.doy = update(vs.doy, at[1], vs.DOY[vs.itt_forc])
+                sl = slice(int(vs.itt_forc), int(vs.itt_forc) + 6 * 24)
+                pw = case.get("prec_weight")
+                to = case.get("ta_offset")
+                ew = case.get("pet_weight")
+                prec = vs.PREC[npx.newaxis, npx.newaxis, sl]
+                ta = vs.TA[npx.newaxis, npx.newaxis, sl]
+                pet = vs.PET[npx.newaxis, npx.newaxis, sl]
+                if pw is not None:
+                    # Eberbaechle pattern (examples/catchment_scale/eberbaechle/svat_distributed/svat.py:258-297)
+                    prec = prec * onp.asarray(pw)[:, :, None]
+                    ta = ta + onp.asarray(to)[:, :, None]
+                    pet = pet * onp.asarray(ew)[:, :, None]
+                    vs.prec_day = update(vs.prec_day, at[2:-2, 2:-2, :], prec)
+                    vs.ta_day = update(vs.ta_day, at[2:-2, 2:-2, :], ta)
+                    vs.pet_day = update(vs.pet_day, at[2:-2, 2:-2, :], pet)
+                else:
+                    vs.prec_day = update(vs.prec_day, at[:, :, :], prec)
+                    vs.ta_day = update(vs.ta_day, at[:, :, :], ta)
+                    vs.pet_day = update(vs.pet_day, at[:, :, :], pet)
+                vs.itt_forc = vs.itt_forc + 6 * 24
+
+        @roger_routine
+        def set_diagnostics(self, state):
+            pass
+
+        @roger_routine
+        def after_timestep(self, state):
+            vs = state.variables
+            vs.update(after_timestep_kernel(state))
+
+    @roger_kernel
+    def after_timestep_kernel(state):
+        # same variable list as benchmarks/SVAT_benchmark.py:183-418
+        vs = state.variables
+        out = {}
+        for name in copy_tau:
+            arr = getattr(vs, name)
+            arr = update(arr, at[2:-2, 2:-2, vs.taum1], arr[2:-2, 2:-2, vs.tau])
+            setattr(vs, name, arr)
+            out[name] = arr
+        if not lateral:
+            for name in ("S_fp_rz", "S_lp_rz", "S_fp_ss", "S_lp_ss"):
+                arr = getattr(vs, name)
+                arr = update(arr, at[2:-2, 2:-2], npx.where((arr > -1e-6) & (arr < 0), 0, arr)[2:-2, 2:-2])
+                setattr(vs, name, arr)
+                out[name] = arr
+        for name in ("event_id", "year", "month", "doy"):
+            arr = getattr(vs, name)
+            arr = update(arr, at[vs.taum1], arr[vs.tau])
+            setattr(vs, name, arr)
+            out[name] = arr
+        return KernelOutput(**out)
+
+    return GoldenSetup
+
+
+def snapshot(state, names=None):
+    """Interior view of every active (x, y[, t]) float/int variable plus the 0-d scalars."""
+    vs = state.variables
+    out = {}
+    for name, meta in state.var_meta.items():
+        if not meta.active:
+            continue
+        if names is not None and name not in names:
+            continue
+        dims = meta.dims
+        arr = onp.asarray(getattr(vs, name))
+        if dims is None or len(dims) == 0:
+            out[name] = arr.copy()
+        elif tuple(dims[:2]) == ("x", "y"):
+            if len(dims) == 2:
+                out[name] = arr[2:-2, 2:-2].copy()
+            elif len(dims) == 3 and dims[2] == "timesteps":
+                out[name] = arr[2:-2, 2:-2, :2].copy()
+        elif tuple(dims) == ("timesteps",):
+            out[name] = arr.copy()
+    return out

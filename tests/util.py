@@ -1,0 +1,88 @@
+"""Shared helpers of the parity tests: fixture loading and replay through an engine."""
+import os
+
+import numpy as np
+
+from roger_b200 import abi
+from roger_b200.svat import SvatModel
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+SVAT_CASES = ["svat_rain", "svat_heavyrain", "svat_snowrain", "svat_snow", "svat_mixed_dist"]
+ONED_CASES = ["oned_rain", "oned_mixed"]
+
+
+def load_case(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as d:
+        return {k: d[k] for k in d.files}
+
+
+def model_from_fixture(fx, engine_cls, from_reference_setup=True, engine_kwargs=None):
+    """Build a SvatModel on the fixture's inputs.  from_reference_setup=True starts every plane from
+    the reference's own post-setup values (isolates the step); False uses roger_b200.params."""
+    shape = (int(fx["nx"]), int(fx["ny"]))
+    forcing = {k: fx[k] for k in ("PREC", "TA", "PET", "YEAR", "MONTH", "DOY")}
+    primary = {k[len("param_"):]: fx[k] for k in fx if k.startswith("param_")}
+    weights = None
+    if "prec_weight" in fx:
+        weights = {k: fx[k] for k in ("prec_weight", "ta_offset", "pet_weight")}
+    m = SvatModel(engine_cls, shape, forcing, primary, fx["theta_rz0"], fx["theta_ss0"], lateral=bool(fx["lateral"]),
+                  weights=weights, engine_kwargs=engine_kwargs)
+    over = None
+    if from_reference_setup:
+        names = [str(n) for n in fx["field_names"]]
+        over = {}
+        for n, row in zip(names, fx["init_fields"]):
+            if n in abi.FIELD_ID and not np.isnan(row).all():
+                over[n] = row
+    m.setup(override_planes=over)
+    return m
+
+
+def normalised_max_error(a, b):
+    """The reference's own parity idiom (test/restart_test.py:7-17): max |a-b| / max|a|."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    if (np.isnan(a) != np.isnan(b)).any():
+        return np.inf
+    a = np.where(both_nan, 0, a)
+    b = np.where(both_nan, 0, b)
+    scale = np.max(np.abs(a))
+    if scale == 0:
+        return float(np.max(np.abs(b)))
+    return float(np.max(np.abs(a - b)) / scale)
+
+
+def replay_and_compare(fx, model, tol, kinds=("S", "F"), skip=(), write_fluxes=True, collect=None):
+    names = [str(n) for n in fx["field_names"]]
+    kinds_of = {str(n): str(k) for n, k in zip(fx["field_names"], fx["field_kinds"])}
+    rec_steps = [int(s) for s in fx["rec_steps"]]
+    rec = {s: i for i, s in enumerate(rec_steps)}
+    scal_keys = [str(k) for k in fx["scal_keys"]]
+    worst = {}
+    nsteps = int(rec_steps[-1])
+    for step in range(1, nsteps + 1):
+        sc = model.step(write_fluxes)
+        ref_sc = dict(zip(scal_keys, fx["all_scalars"][step - 1]))
+        got = dict(time=sc.time, itt=sc.itt, dt_secs=sc.dt_secs, itt_day=sc.itt_day, event_id_counter=sc.event_id_counter,
+                   time_event0=sc.time_event0, dt=sc.dt, event_id0=sc.event_id[0], event_id1=sc.event_id[1], month=sc.month)
+        for k, v in ref_sc.items():
+            assert float(got[k]) == float(v), f"step {step}: scalar {k}: got {got[k]} ref {v}"
+        if step in rec:
+            ref = fx["rec_fields"][rec[step]]
+            for n, row in zip(names, ref):
+                if kinds_of[n] not in kinds or n in skip or np.isnan(row).all():
+                    continue
+                if n.endswith("_num_error"):
+                    # closure residuals are O(1e-14) rounding noise: compared absolutely (mm)
+                    err = float(np.nanmax(np.abs(row - model.get(n)))) * 1e-1
+                else:
+                    err = normalised_max_error(row, model.get(n))
+                if err > worst.get(n, (0, 0))[0]:
+                    worst[n] = (err, step)
+    bad = {n: v for n, v in worst.items() if v[0] > tol}
+    if collect is not None:
+        collect.update(worst)
+    assert not bad, "fields above tolerance %g: %s" % (tol, sorted(bad.items(), key=lambda kv: -kv[1][0])[:12])
+    return worst
