@@ -1,0 +1,613 @@
+// svat_api.cu -- kernels, host-side adaptive-time-stepping scheduler and the C ABI of the SVAT / oneD
+// hot path (include/roger_b200.h).  sm_100a only; there is no CPU fallback: every entry point
+// fails with -ROGER_ENODEV / -ROGER_ECUDA if no usable CUDA device is present.
+//
+// Data layout in HBM: structure of arrays, one plane of C doubles per field
+// (include/roger_b200_fields.h), cell index fastest, so a warp's 32 threads read/write 256
+// contiguous bytes per field.  Parameter (P) and state (S) planes live in one allocation; flux (F)
+// planes are allocated lazily, only when a caller asks for diagnostics.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "svat_device.cuh"
+
+namespace roger {
+
+// ------------------------------------------------------------------------------------------------
+// field tables
+#define ROGER_NAME(kind, name) #name,
+static const char* const kFieldName[RF_COUNT] = {ROGER_SVAT_FIELDS(ROGER_NAME)};
+#undef ROGER_NAME
+#define ROGER_KIND(kind, name) ROGER_KIND_##kind,
+static const int kFieldKind[RF_COUNT] = {ROGER_SVAT_FIELDS(ROGER_KIND)};
+#undef ROGER_KIND
+
+__host__ __device__ constexpr bool kind_is_F(int id) { return id >= RF_pet_res; }  // enum order is P.., S.., F..
+constexpr int kNumPS = RF_pet_res;
+static_assert(RF_prec > RF_v_mp_layer_8 && RF_pet_res > RF_S, "field enum must be ordered P.., S.., F..");
+constexpr int kNumF = RF_COUNT - RF_pet_res;
+
+__host__ __device__ constexpr bool lat_only(int id) {
+    return (id >= RF_dmph && id <= RF_v_mp_layer_8) || (id >= RF_q_sub_mat_pot && id <= RF_z_sat_layer_8);
+}
+
+enum : unsigned {
+    FLAG_SWE_GT0 = 1u, FLAG_SWE_NOT_LE0 = 2u, FLAG_SWETOP_GT0 = 4u, FLAG_SWETOP_NOT_LE0 = 8u, FLAG_INSANE = 16u,
+    // forcing day flags
+    DAY_NOT_PREC_LE0 = 1u << 8, DAY_NOT_TA_GT = 1u << 9, DAY_SNOWFALL = 1u << 10, DAY_NOT_DRY_COLD = 1u << 11,
+    DAY_HPI = 1u << 12, DAY_PREC = 1u << 13, DAY_TA_GT = 1u << 14, DAY_NOT_LE_HPI = 1u << 15,
+    // per-step event flags (adaptive_time_stepping.py:191-201)
+    EV_RAIN_WARM = 1u << 16, EV_SNOW_WARM = 1u << 17, EV_NOT_PREC_LE0 = 1u << 18, EV_NOT_SNOWING = 1u << 19,
+};
+
+// ------------------------------------------------------------------------------------------------
+// numpy-order sums of a 144-slot forcing row (np.add.reduce pairwise summation, 8 lanes, halves of 72)
+template <typename F>
+__host__ __device__ inline double pairwise144(F at) {
+    double half[2];
+    for (int h = 0; h < 2; h++) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = at(h * 72 + j);
+        for (int i = 8; i < 72; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] += at(h * 72 + i + j);
+        }
+        half[h] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    }
+    return 0.0 + (half[0] + half[1]);
+}
+
+struct RowAgg {  // aggregates of one forcing row for the three time-step classes
+    __host__ __device__ static double day_sum(const double* row) {
+        return pairwise144([&](int k) { return row[k]; });
+    }
+    __host__ __device__ static double day_nanmean(const double* row) {
+        int cnt = 0;
+        for (int k = 0; k < 144; k++) cnt += (row[k] == row[k]) ? 1 : 0;
+        double tot = pairwise144([&](int k) { double v = row[k]; return (v == v) ? v : 0.0; });
+        return tot / (double)cnt;
+    }
+    __host__ __device__ static double win_sum(const double* row, int itt_day) {
+        return pairwise144([&](int k) { return (k >= itt_day && k < itt_day + 6) ? row[k] : 0.0; });
+    }
+    __host__ __device__ static double win_nanmean(const double* row, int itt_day) {
+        int cnt = 0;
+        for (int k = itt_day; k < itt_day + 6 && k < 144; k++) cnt += (row[k] == row[k]) ? 1 : 0;
+        double tot = pairwise144([&](int k) {
+            double v = (k >= itt_day && k < itt_day + 6) ? row[k] : 0.0;
+            return (v == v) ? v : 0.0;
+        });
+        return tot / (double)cnt;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct Planes {
+    double* ps;  // kNumPS planes
+    double* fl;  // kNumF planes (may be null)
+    int64_t C;
+    __host__ __device__ double* at(int id) const { return kind_is_F(id) ? fl + (size_t)(id - kNumPS) * C : ps + (size_t)id * C; }
+};
+
+__device__ __forceinline__ void warp_or(unsigned* flags, unsigned bits) {
+    unsigned all = __reduce_or_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0 && all) atomicOr(flags, all);
+}
+
+// snow flags of the current state (used before the first step and after a host upload of swe / swe_top)
+__global__ void k_snow_flags(Planes pl, unsigned* flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bits = 0;
+    if (i < pl.C) {
+        double swe = pl.at(RF_swe)[i], st = pl.at(RF_swe_top)[i];
+        bits |= (swe > 0) ? FLAG_SWE_GT0 : 0;
+        bits |= !(swe <= 0) ? FLAG_SWE_NOT_LE0 : 0;
+        bits |= (st > 0) ? FLAG_SWETOP_GT0 : 0;
+        bits |= !(st <= 0) ? FLAG_SWETOP_NOT_LE0 : 0;
+    }
+    warp_or(flags, bits);
+}
+
+// grid-wide conditions on the day's forcing block (adaptive_time_stepping.py:38-80), distributed forcing
+__global__ void k_day_flags(const double* __restrict__ prec_day, const double* __restrict__ ta_day, int64_t n,
+                            double ta_fm, double hpi, unsigned* flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bits = 0;
+    for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double p = prec_day[i], t = ta_day[i];
+        bits |= !(p <= 0) ? DAY_NOT_PREC_LE0 : 0;
+        bits |= !(t > ta_fm) ? DAY_NOT_TA_GT : 0;
+        bits |= ((p > 0) && (t <= ta_fm)) ? DAY_SNOWFALL : 0;
+        bits |= !((p <= 0) && (t <= ta_fm)) ? DAY_NOT_DRY_COLD : 0;
+        bits |= (p > hpi) ? DAY_HPI : 0;
+        bits |= (p > 0) ? DAY_PREC : 0;
+        bits |= (t > ta_fm) ? DAY_TA_GT : 0;
+        bits |= !(p <= hpi) ? DAY_NOT_LE_HPI : 0;
+    }
+    warp_or(flags, bits);
+}
+
+// first block of adaptive_time_stepping (:130-189) for per-cell forcing: prec/ta[tau] for the chosen class,
+// old prec kept as prec[taum1]; plus the event start/end conditions (:191-201)
+__global__ void k_aggregate_a(Planes pl, double* __restrict__ prec_m1, const double* __restrict__ prec_day,
+                              const double* __restrict__ ta_day, int class_a, int itt_day, double ta_fm, unsigned* flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bits = 0;
+    if (i < pl.C) {
+        double* prec = pl.at(RF_prec);
+        double* ta = pl.at(RF_ta);
+        double p = prec[i], t = ta[i];
+        prec_m1[i] = p;
+        const double* pr = prec_day + (size_t)i * 144;
+        const double* tr = ta_day + (size_t)i * 144;
+        if (class_a == 1) { p = RowAgg::day_sum(pr); t = RowAgg::day_nanmean(tr); }
+        else if (class_a == 2) { p = RowAgg::win_sum(pr, itt_day); t = RowAgg::win_nanmean(tr, itt_day); }
+        else if (class_a == 3) { p = pr[itt_day]; t = tr[itt_day]; }
+        if (class_a) { prec[i] = p; ta[i] = t; }
+        double swe = pl.at(RF_swe)[i], st = pl.at(RF_swe_top)[i];
+        bits |= ((p > 0) && (t > ta_fm)) ? EV_RAIN_WARM : 0;
+        bits |= (((swe > 0) || (st > 0)) && (t > ta_fm)) ? EV_SNOW_WARM : 0;
+        bits |= !(p <= 0) ? EV_NOT_PREC_LE0 : 0;
+        bits |= !((p > 0) && (t <= ta_fm)) ? EV_NOT_SNOWING : 0;
+    }
+    warp_or(flags, bits);
+}
+
+// The fused step.  One thread = one soil column; all parameters and state in registers.
+template <bool LAT, bool FLUX>
+__global__ void __launch_bounds__(128)
+k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* __restrict__ ta_day,
+            const double* __restrict__ pet_day, StepPlan p, unsigned* flags) {
+    const int64_t C = pl.C;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bits = 0;
+    if (i < C) {
+        Cell c;
+#define ROGER_LOAD_P(name) c.name = (LAT || !lat_only(RF_##name)) ? __ldg(pl.ps + (size_t)RF_##name * C + i) : 0.0;
+#define ROGER_LOAD_S(name) c.name = pl.ps[(size_t)RF_##name * C + i];
+#define ROGER_LOAD_F(name) c.name = 0.0;
+#define ROGER_LOAD(kind, name) ROGER_LOAD_##kind(name)
+        ROGER_SVAT_FIELDS(ROGER_LOAD)
+#undef ROGER_LOAD
+        c.m = c.maskCatch;
+        // ---- adaptive_time_stepping.py:130-189 / :256-360: forcing for this cell ----
+        if (p.uniform) {
+            c.prec_m1 = c.prec;
+            if (p.class_a) { c.prec = p.u_prec; c.ta = p.u_ta_a; }
+            if (p.class_b) { c.pet = p.u_pet; c.ta = p.u_ta_b; }
+        } else {
+            c.prec_m1 = prec_m1_plane[i];  // prec / ta already hold the class-A aggregates (k_aggregate_a)
+            const double* tr = ta_day + (size_t)i * 144;
+            const double* er = pet_day + (size_t)i * 144;
+            if (p.class_b == 1) { c.pet = er[p.itt_day]; c.ta = tr[p.itt_day]; }
+            else if (p.class_b == 2) { c.pet = RowAgg::win_sum(er, p.itt_day); c.ta = RowAgg::win_nanmean(tr, p.itt_day); }
+            else if (p.class_b == 3) { c.pet = RowAgg::day_sum(er); c.ta = RowAgg::day_nanmean(tr); }
+        }
+        c.z_wf_m1 = c.z_wf; c.z_wf_t0_m1 = c.z_wf_t0; c.z_wf_t1_m1 = c.z_wf_t1;
+        c.y_mp_m1 = c.y_mp; c.y_sc_m1 = c.y_sc;
+        c.S_m1 = c.S; c.S_rz_m1 = c.S_rz; c.S_ss_m1 = c.S_ss; c.S_s_m1 = c.S_s;
+
+        const bool ok = (c.m == 1.0) ? cell_step<LAT, true>(c, p) : cell_step<LAT, false>(c, p);
+
+#define ROGER_STORE_P(name)
+#define ROGER_STORE_S(name) pl.ps[(size_t)RF_##name * C + i] = c.name;
+#define ROGER_STORE_F(name) \
+    if (FLUX && (LAT || !lat_only(RF_##name))) pl.fl[(size_t)(RF_##name - kNumPS) * C + i] = c.name;
+#define ROGER_STORE(kind, name) ROGER_STORE_##kind(name)
+        ROGER_SVAT_FIELDS(ROGER_STORE)
+#undef ROGER_STORE
+        bits |= (c.swe > 0) ? FLAG_SWE_GT0 : 0;
+        bits |= !(c.swe <= 0) ? FLAG_SWE_NOT_LE0 : 0;
+        bits |= (c.swe_top > 0) ? FLAG_SWETOP_GT0 : 0;
+        bits |= !(c.swe_top <= 0) ? FLAG_SWETOP_NOT_LE0 : 0;
+        bits |= ok ? 0 : FLAG_INSANE;
+    }
+    warp_or(flags, bits);
+}
+
+}  // namespace roger
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace roger;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return -code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ROGER_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+struct roger_svat {
+    int64_t C = 0;
+    int device = 0;
+    roger_svat_settings st{};
+    roger_svat_scalars sc{};
+    double* d_ps = nullptr;
+    double* d_fl = nullptr;
+    double* d_prec_m1 = nullptr;
+    double* d_forc[3] = {nullptr, nullptr, nullptr};  // prec_day, ta_day, pet_day (owned copies)
+    const double* forc[3] = {nullptr, nullptr, nullptr};
+    double h_forc[3][144];  // uniform forcing (host copy for the scheduler)
+    unsigned* d_flags = nullptr;  // [0] snow/sanity flags, [1] day flags, [2] event flags
+    unsigned* h_flags = nullptr;  // pinned
+    unsigned snow_flags = 0;
+    unsigned day_flags = 0;
+    bool snow_flags_valid = false;
+    bool ks_ss_synced = false;
+    bool have_forcing = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_kernel_ms = 0;
+    int64_t last_launches = 0;
+    Planes planes() const { return Planes{d_ps, d_fl, C}; }
+};
+
+static int ensure_flux_planes(roger_svat* h) {
+    if (h->d_fl) return 0;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMalloc(&h->d_fl, sizeof(double) * (size_t)kNumF * (size_t)h->C));
+    CU(cudaMemsetAsync(h->d_fl, 0, sizeof(double) * (size_t)kNumF * (size_t)h->C, h->stream));
+    return 0;
+}
+
+extern "C" {
+
+const char* roger_last_error(void) { return g_err.c_str(); }
+int roger_svat_field_count(void) { return RF_COUNT; }
+const char* roger_svat_field_name(int f) { return (f >= 0 && f < RF_COUNT) ? kFieldName[f] : nullptr; }
+int roger_svat_field_kind(int f) { return (f >= 0 && f < RF_COUNT) ? kFieldKind[f] : -1; }
+
+int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settings* settings, int device) {
+    if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_svat_create: bad argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ROGER_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                      " (this backend has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(ROGER_EINVAL, "roger_svat_create: bad device index");
+    CU(cudaSetDevice(device));
+    roger_svat* h = new roger_svat();
+    h->C = n_cells;
+    h->device = device;
+    h->st = *settings;
+    h->sc.dt = 1.0;
+    h->sc.dt_secs = 3600;
+    h->sc.event_id_counter = 1;
+    h->sc.sanity_ok = 1;
+    h->sc.month = 1;
+    const size_t plane = sizeof(double) * (size_t)n_cells;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&h->d_ps, plane * kNumPS));
+    CU(cudaMemsetAsync(h->d_ps, 0, plane * kNumPS, h->stream));
+    CU(cudaMalloc(&h->d_prec_m1, plane));
+    CU(cudaMalloc(&h->d_flags, 4 * sizeof(unsigned)));
+    CU(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(unsigned), h->stream));
+    CU(cudaHostAlloc(&h->h_flags, 4 * sizeof(unsigned), cudaHostAllocDefault));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    *out = h;
+    return 0;
+}
+
+void roger_svat_destroy(roger_svat* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_ps);
+    cudaFree(h->d_fl);
+    cudaFree(h->d_prec_m1);
+    for (auto p : h->d_forc) cudaFree(p);
+    cudaFree(h->d_flags);
+    cudaFreeHost(h->h_flags);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int roger_svat_upload(roger_svat* h, int field, const double* host) {
+    if (!h || !host || field < 0 || field >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_upload: bad argument");
+    CU(cudaSetDevice(h->device));
+    if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
+    CU(cudaMemcpyAsync(h->planes().at(field), host, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (field == RF_swe || field == RF_swe_top) h->snow_flags_valid = false;
+    if (field == RF_ks_ss) h->ks_ss_synced = (h->sc.itt > 0) ? false : h->ks_ss_synced;
+    return 0;
+}
+
+int roger_svat_download(roger_svat* h, int field, double* host) {
+    if (!h || !host || field < 0 || field >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_download: bad argument");
+    CU(cudaSetDevice(h->device));
+    if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
+    CU(cudaMemcpyAsync(host, h->planes().at(field), sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+uint64_t roger_svat_plane_ptr(roger_svat* h, int field) {
+    if (!h || field < 0 || field >= RF_COUNT) return 0;
+    if (kind_is_F(field) && ensure_flux_planes(h)) return 0;
+    return (uint64_t)(uintptr_t)h->planes().at(field);
+}
+
+int roger_svat_set_scalars(roger_svat* h, const roger_svat_scalars* s) {
+    if (!h || !s) return fail(ROGER_EINVAL, "roger_svat_set_scalars: bad argument");
+    h->sc = *s;
+    return 0;
+}
+int roger_svat_get_scalars(roger_svat* h, roger_svat_scalars* s) {
+    if (!h || !s) return fail(ROGER_EINVAL, "roger_svat_get_scalars: bad argument");
+    *s = h->sc;
+    return 0;
+}
+
+static unsigned day_flags_host(const double* pr, const double* tr, int n, double ta_fm, double hpi) {
+    unsigned bits = 0;
+    for (int k = 0; k < n; k++) {
+        double p = pr[k], t = tr[k];
+        bits |= !(p <= 0) ? DAY_NOT_PREC_LE0 : 0;
+        bits |= !(t > ta_fm) ? DAY_NOT_TA_GT : 0;
+        bits |= ((p > 0) && (t <= ta_fm)) ? DAY_SNOWFALL : 0;
+        bits |= !((p <= 0) && (t <= ta_fm)) ? DAY_NOT_DRY_COLD : 0;
+        bits |= (p > hpi) ? DAY_HPI : 0;
+        bits |= (p > 0) ? DAY_PREC : 0;
+        bits |= (t > ta_fm) ? DAY_TA_GT : 0;
+        bits |= !(p <= hpi) ? DAY_NOT_LE_HPI : 0;
+    }
+    return bits;
+}
+
+static int after_forcing(roger_svat* h) {
+    if (h->st.forcing_uniform) {
+        h->day_flags = day_flags_host(h->h_forc[0], h->h_forc[1], 144, h->st.ta_fm, h->st.hpi);
+    } else {
+        CU(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(unsigned), h->stream));
+        int64_t n = h->C * 144;
+        int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+        k_day_flags<<<blocks, 256, 0, h->stream>>>(h->forc[0], h->forc[1], n, h->st.ta_fm, h->st.hpi, h->d_flags + 1);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h->h_flags + 1, h->d_flags + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->day_flags = h->h_flags[1];
+    }
+    h->have_forcing = true;
+    return 0;
+}
+
+int roger_svat_set_forcing_day(roger_svat* h, const double* prec_day, const double* ta_day, const double* pet_day) {
+    if (!h || !prec_day || !ta_day || !pet_day) return fail(ROGER_EINVAL, "roger_svat_set_forcing_day: bad argument");
+    CU(cudaSetDevice(h->device));
+    const double* src[3] = {prec_day, ta_day, pet_day};
+    if (h->st.forcing_uniform) {
+        for (int v = 0; v < 3; v++) memcpy(h->h_forc[v], src[v], sizeof(double) * 144);
+    } else {
+        const size_t bytes = sizeof(double) * 144 * (size_t)h->C;
+        for (int v = 0; v < 3; v++) {
+            if (!h->d_forc[v]) CU(cudaMalloc(&h->d_forc[v], bytes));
+            CU(cudaMemcpyAsync(h->d_forc[v], src[v], bytes, cudaMemcpyHostToDevice, h->stream));
+            h->forc[v] = h->d_forc[v];
+        }
+    }
+    return after_forcing(h);
+}
+
+int roger_svat_set_forcing_day_device(roger_svat* h, uint64_t prec_day, uint64_t ta_day, uint64_t pet_day) {
+    if (!h || !prec_day || !ta_day || !pet_day) return fail(ROGER_EINVAL, "roger_svat_set_forcing_day_device: bad argument");
+    CU(cudaSetDevice(h->device));
+    const double* src[3] = {(const double*)(uintptr_t)prec_day, (const double*)(uintptr_t)ta_day, (const double*)(uintptr_t)pet_day};
+    if (h->st.forcing_uniform) {
+        for (int v = 0; v < 3; v++)
+            CU(cudaMemcpyAsync(h->h_forc[v], src[v], sizeof(double) * 144, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } else {
+        for (int v = 0; v < 3; v++) h->forc[v] = src[v];
+    }
+    return after_forcing(h);
+}
+
+// One adaptive time step.  Host side = the grid-wide part of adaptive_time_stepping_kernel
+// (adaptive_time_stepping.py:34-381) evaluated on reduction flags; device side = everything per cell.
+static int step_impl(roger_svat* h, int write_fluxes) {
+    if (!h->have_forcing) return fail(ROGER_EINVAL, "roger_svat_step: no forcing day set");
+    CU(cudaSetDevice(h->device));
+    if (write_fluxes) { int r = ensure_flux_planes(h); if (r) return r; }
+    const roger_svat_settings& st = h->st;
+    roger_svat_scalars& sc = h->sc;
+    const int threads = 128;
+    const int blocks = (int)((h->C + threads - 1) / threads);
+    int64_t launches = 0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+
+    if (!h->snow_flags_valid) {
+        CU(cudaMemsetAsync(h->d_flags, 0, sizeof(unsigned), h->stream));
+        k_snow_flags<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(h->planes(), h->d_flags);
+        CU(cudaGetLastError());
+        launches++;
+        CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->snow_flags = h->h_flags[0];
+        h->snow_flags_valid = true;
+    }
+    const unsigned sf = h->snow_flags, df = h->day_flags;
+    const bool all_prec_le0 = !(df & DAY_NOT_PREC_LE0), all_ta_gt = !(df & DAY_NOT_TA_GT);
+    const bool any_snowfall = df & DAY_SNOWFALL, all_dry_cold = !(df & DAY_NOT_DRY_COLD);
+    const bool any_hpi = df & DAY_HPI, any_prec = df & DAY_PREC, any_ta_gt = df & DAY_TA_GT, all_le_hpi = !(df & DAY_NOT_LE_HPI);
+    const bool any_swe = sf & FLAG_SWE_GT0, any_swetop = sf & FLAG_SWETOP_GT0;
+    const bool all_swe_le0 = !(sf & FLAG_SWE_NOT_LE0), all_swetop_le0 = !(sf & FLAG_SWETOP_NOT_LE0);
+    const bool cond0 = all_prec_le0 && all_swe_le0 && all_swetop_le0 && all_ta_gt;
+    const bool cond00 = any_snowfall || all_dry_cold;
+    const bool cond1 = any_hpi && any_prec && any_ta_gt;
+    const bool cond2 = all_le_hpi && any_prec && any_ta_gt;
+    const bool snow_warm = (any_swe || any_swetop) && any_ta_gt;
+    const bool cond3 = any_hpi && any_prec && snow_warm;
+    const bool cond4 = all_le_hpi && any_prec && snow_warm;
+    const bool cond5 = all_prec_le0 && snow_warm;
+    const bool daily = cond0 || cond00;
+    const bool hourly = (cond2 || cond4 || cond5) && !cond1 && !cond3;
+    const bool tenmin = (cond1 || cond3) && !cond2 && !cond4 && !cond5;
+    const int itt_day = (int)sc.itt_day;
+    if (itt_day < 0 || itt_day > 143) return fail(ROGER_EINVAL, "roger_svat_step: itt_day outside the forcing day (set_forcing_day not called at midnight?)");
+
+    StepPlan p{};
+    p.class_a = tenmin ? 3 : (hourly ? 2 : (daily ? 1 : 0));
+    sc.dt_secs = (sc.time % 86400 == 0) ? 86400 : 3600;
+    if (hourly) sc.dt_secs = 3600;
+    if (tenmin) sc.dt_secs = 600;
+
+    unsigned ev = 0;
+    if (st.forcing_uniform) {
+        // event conditions need prec/ta[tau]; with class "keep" they are the stored planes' (uniform) values:
+        // the scheduler keeps the last uniform aggregates on the host.
+        static_assert(sizeof(double) == 8, "");
+        double pa, ta_a;
+        const double* pr = h->h_forc[0];
+        const double* tr = h->h_forc[1];
+        if (p.class_a == 1) { pa = RowAgg::day_sum(pr); ta_a = RowAgg::day_nanmean(tr); }
+        else if (p.class_a == 2) { pa = RowAgg::win_sum(pr, itt_day); ta_a = RowAgg::win_nanmean(tr, itt_day); }
+        else if (p.class_a == 3) { pa = pr[itt_day]; ta_a = tr[itt_day]; }
+        else {
+            // keep: read one cell's current value (uniform planes) -- rare path
+            CU(cudaMemcpyAsync(&pa, h->planes().at(RF_prec), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(&ta_a, h->planes().at(RF_ta), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
+        p.u_prec = pa;
+        p.u_ta_a = ta_a;
+        ev |= ((pa > 0) && (ta_a > st.ta_fm)) ? EV_RAIN_WARM : 0;
+        ev |= ((any_swe || any_swetop) && (ta_a > st.ta_fm)) ? EV_SNOW_WARM : 0;
+        ev |= !(pa <= 0) ? EV_NOT_PREC_LE0 : 0;
+        ev |= !((pa > 0) && (ta_a <= st.ta_fm)) ? EV_NOT_SNOWING : 0;
+    } else {
+        CU(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(unsigned), h->stream));
+        k_aggregate_a<<<blocks, threads, 0, h->stream>>>(h->planes(), h->d_prec_m1, h->forc[0], h->forc[1], p.class_a, itt_day,
+                                                          st.ta_fm, h->d_flags + 2);
+        CU(cudaGetLastError());
+        launches++;
+        CU(cudaMemcpyAsync(h->h_flags + 2, h->d_flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        ev = h->h_flags[2];
+    }
+    const bool cond_event1 = (ev & EV_RAIN_WARM) || (ev & EV_SNOW_WARM);
+    // swe[taum1] == swe[tau] at this point (after_timestep copied it): any(swe_m1 > 0) & all(swe <= 0)
+    const bool cond_event2 = !(ev & EV_NOT_PREC_LE0) || !(ev & EV_NOT_SNOWING) || (any_swe && all_swe_le0);
+    if (cond_event1) sc.time_event0 = 0;
+    if (cond_event2) sc.time_event0 = sc.time_event0 + sc.dt_secs;
+
+    const int64_t end_event = (int64_t)st.end_event;
+    const bool c6 = (sc.time_event0 <= end_event) && (sc.dt_secs == 600);
+    const bool c7 = (sc.time_event0 <= end_event) && (sc.dt_secs == 3600);
+    const bool c8 = (sc.time_event0 <= end_event) && (sc.dt_secs == 86400);
+    const bool c9 = (sc.time_event0 > end_event) && (sc.time % 3600 != 0) && (sc.dt_secs == 600);
+    const bool c10 = (sc.time_event0 > end_event) && (sc.time % 3600 == 0) && ((sc.dt_secs == 600) || (sc.dt_secs == 3600));
+    const bool c11 = (sc.time_event0 > end_event) && (sc.time % 86400 == 0) && (sc.dt_secs == 86400);
+    if (c6) { sc.event_id[1] = sc.event_id_counter; sc.dt = 1.0 / 6; sc.itt_day += 1; p.class_b = 1; }
+    if (c7) { sc.event_id[1] = sc.event_id_counter; sc.dt = 1; sc.itt_day += 6; p.class_b = 2; }
+    if (c8) { sc.dt = 24; sc.itt_day = 0; p.class_b = 3; }
+    if (c9) { sc.event_id[1] = 0; sc.dt = 1.0 / 6; sc.dt_secs = 600; sc.itt_day += 1; p.class_b = 1; }
+    if (c10) { sc.event_id[1] = 0; sc.dt = 1; sc.dt_secs = 3600; sc.itt_day += 6; p.class_b = 2; }
+    if (c11) { sc.event_id[1] = 0; sc.dt = 24; sc.dt_secs = 86400; sc.itt_day = 0; p.class_b = 3; }
+    if ((sc.event_id[0] > 0) && (sc.event_id[1] == 0)) sc.event_id_counter += 1;
+
+    if (st.forcing_uniform) {
+        const double* tr = h->h_forc[1];
+        const double* er = h->h_forc[2];
+        if (p.class_b == 1) { p.u_pet = er[itt_day]; p.u_ta_b = tr[itt_day]; }
+        else if (p.class_b == 2) { p.u_pet = RowAgg::win_sum(er, itt_day); p.u_ta_b = RowAgg::win_nanmean(tr, itt_day); }
+        else if (p.class_b == 3) { p.u_pet = RowAgg::day_sum(er); p.u_ta_b = RowAgg::day_nanmean(tr); }
+    }
+    p.dt = sc.dt;
+    p.ta_fm = st.ta_fm; p.sf = st.sf; p.retention = (10000. / (100 - st.rmax) / 100.);
+    p.r_mp = st.r_mp; p.r_mp2 = st.r_mp * st.r_mp; p.r_mp3_6 = std::pow(st.r_mp, 3.0) / 6.0;
+    p.l_sc = st.l_sc; p.pi = st.pi; p.transp_water_stress = st.transp_water_stress; p.dx = st.dx;
+    p.atol = st.atol; p.rtol = st.rtol;
+    p.sqrt6x2 = std::pow(6.0, 0.5) * 2;
+    p.itt_day = itt_day;
+    p.substeps = (int)std::nearbyint(sc.dt / (1.0 / 5));
+    p.cond1 = (sc.event_id[0] == 0) && (sc.event_id[1] >= 1);
+    p.cond2s = (sc.event_id[0] >= 1);
+    p.cond3s = (sc.event_id[0] == sc.event_id[1]);
+    p.cond4 = (sc.event_id[0] >= 1) && (sc.event_id[1] == 0);
+    p.cond5 = (sc.event_id[1] >= 1);
+    p.irrigation_month = (sc.month >= 4 && sc.month <= 9);
+    p.uniform = st.forcing_uniform;
+    p.lbc = st.enable_macropore_lower_boundary_condition;
+    p.clamp = st.clamp_small_negative_storage;
+
+    CU(cudaMemsetAsync(h->d_flags, 0, sizeof(unsigned), h->stream));
+    const Planes pl = h->planes();
+#define LAUNCH(LAT, FLUX) \
+    k_svat_step<LAT, FLUX><<<blocks, threads, 0, h->stream>>>(pl, h->d_prec_m1, h->forc[1], h->forc[2], p, h->d_flags)
+    if (st.enable_lateral_flow) { if (write_fluxes) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (write_fluxes) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+    CU(cudaGetLastError());
+    launches++;
+    if (!h->ks_ss_synced) {  // subsoil.calc_ks (subsoil.py:6-20): ks_ss = ks from the end of the first step on
+        CU(cudaMemcpyAsync(pl.at(RF_ks_ss), pl.at(RF_ks), sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToDevice, h->stream));
+        h->ks_ss_synced = true;
+    }
+    CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->snow_flags = h->h_flags[0];
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_kernel_ms += ms;
+    h->last_launches += launches;
+
+    sc.itt += 1;
+    sc.time += sc.dt_secs;
+    sc.sanity_ok = (h->snow_flags & FLAG_INSANE) ? 0 : 1;
+    sc.event_id[0] = sc.event_id[1];  // after_timestep
+    return 0;
+}
+
+int roger_svat_step(roger_svat* h, int write_fluxes) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_step: null handle");
+    h->last_kernel_ms = 0;
+    h->last_launches = 0;
+    return step_impl(h, write_fluxes);
+}
+
+int roger_svat_run_day(roger_svat* h, int write_fluxes, int* n_steps) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_run_day: null handle");
+    h->last_kernel_ms = 0;
+    h->last_launches = 0;
+    int n = 0;
+    do {
+        int r = step_impl(h, write_fluxes);
+        if (r) return r;
+        n++;
+    } while (h->sc.time % 86400 != 0 && n < 144);
+    if (n_steps) *n_steps = n;
+    return 0;
+}
+
+int roger_svat_synchronize(roger_svat* h) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_synchronize: null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int roger_svat_last_timing(roger_svat* h, double* kernel_ms, int64_t* launches) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_last_timing: null handle");
+    if (kernel_ms) *kernel_ms = h->last_kernel_ms;
+    if (launches) *launches = h->last_launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1063 @@
+// svat_device.cuh -- fused per-cell SVAT / oneD time step for sm_100a (device code).
+//
+// One thread owns one soil column for the whole step: every parameter and state value of the
+// cell is loaded once into registers, the complete process chain of RogerSetup.step
+// (roger/roger.py:389-447: interception -> evapotranspiration -> snow -> infiltration ->
+// percolation / lateral flow -> capillary rise -> storages -> balance check -> after_timestep)
+// runs on registers, and the state is stored once.  The reference executes the same chain as
+// ~60 whole-array NumPy kernels with several hundred full-array copies per step.
+//
+// Template switches:
+//   LAT    oneD model (settings.enable_lateral_flow, roger/core/subsurface_runoff.py:1455-1466)
+//   MASK1  the cell's maskCatch is exactly 1.0: every `* maskCatch` of the reference is the
+//          identity (x * 1.0 == x for all x incl. NaN/Inf/-0) and is elided at compile time.
+//
+// The arithmetic keeps the reference's operation order, its where()-chains (including the
+// order in which masks are captured), its operator-precedence slips and its NaN behaviour
+// (comparisons with NaN are false; no fmin/fmax shortcuts) -- see SURVEY.md section 7
+// "Reference quirks".  Built with -fmad=false so that a*b+c rounds twice as NumPy does.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/roger_b200.h"
+
+namespace roger {
+
+// Everything a step needs besides the cell's own planes (kernel parameter, lives in the constant bank).
+struct StepPlan {
+    double dt;            // vs.dt (h) chosen by the adaptive time stepping for this step
+    double ta_fm, sf, retention, r_mp, r_mp2, r_mp3_6, l_sc, pi, transp_water_stress, dx;
+    double atol, rtol;
+    double sqrt6x2;       // 6**0.5 * 2 (infiltration.py:628)
+    double u_prec, u_ta_a, u_pet, u_ta_b;  // uniform forcing: aggregates computed by the scheduler
+    int class_a;          // prec/ta[tau] first block: 0 keep, 1 daily, 2 hourly, 3 ten-minute
+    int class_b;          // pet/ta second block (cond6..cond11): 0 keep, 1 ten-minute, 2 hourly, 3 daily
+    int itt_day;          // vs.itt_day at entry of adaptive_time_stepping
+    int substeps;         // int32(round(dt / (1/5)))  (infiltration.py:513)
+    int cond1, cond2s, cond3s, cond4, cond5;  // event gates (infiltration.py:2155-2167)
+    int irrigation_month; // month in 4..9 (root_zone.py:155)
+    int uniform;          // forcing shared by all cells
+    int lbc;              // settings.enable_macropore_lower_boundary_condition
+    int clamp;            // after_timestep clamp of tiny negative storages (SVAT setups)
+};
+
+#define RD __device__ __forceinline__
+
+struct Cell {
+#define ROGER_DECL(kind, name) double name;
+    ROGER_SVAT_FIELDS(ROGER_DECL)
+#undef ROGER_DECL
+    double m;  // maskCatch
+    // [taum1] companions (the reference copies [tau] -> [taum1] after every step)
+    double prec_m1, z_wf_m1, z_wf_t0_m1, z_wf_t1_m1, y_mp_m1, y_sc_m1, S_m1, S_rz_m1, S_ss_m1, S_s_m1;
+};
+
+template <bool MASK1>
+RD double mk(const Cell& c, double x) { return MASK1 ? x : x * c.m; }
+#define M(x) mk<MASK1>(c, (x))
+
+// ---- interception.py:6-343 ------------------------------------------------------------------
+template <bool MASK1>
+RD void interception(Cell& c, const StepPlan& p) {
+    const double ta_fm = p.ta_fm;
+    const bool warm = c.ta > ta_fm;
+    const double tf_top = 1. - c.throughfall_coeff_top;
+    const double tf_gr = 1. - c.throughfall_coeff_ground;
+    // rain, upper storage (:6-71)
+    c.rain_top = M(warm ? c.prec : 0.0);
+    {
+        double wtmx = p.retention * c.swe_top;
+        double tot = M((c.S_int_top_tot < wtmx) ? wtmx : c.S_int_top_tot);
+        double free_ = M((c.S_int_top < tot) ? tot - c.S_int_top : 0.0);
+        double want = c.prec * tf_top;
+        bool m1 = (free_ >= want) && warm && (free_ > 0);
+        bool m2 = (free_ < want) && warm && (free_ > 0);
+        double v = 0.0 + M((c.prec * tf_top) * (m1 ? 1.0 : 0.0));
+        c.int_rain_top = M(m2 ? free_ : v);
+        c.S_int_top += M(c.int_rain_top);
+    }
+    // rain, lower storage (:74-151)
+    {
+        double rain = M((c.prec - c.int_rain_top) * (warm ? 1.0 : 0.0));
+        double free_ = M(((c.S_int_ground < c.S_int_ground_tot) && (c.S_snow <= 0)) ? c.S_int_ground_tot - c.S_int_ground : 0.0);
+        double want = rain * tf_gr;
+        bool m1 = (free_ >= want) && warm && (free_ > 0);
+        bool m2 = (free_ < want) && warm && (free_ > 0);
+        double v = 0.0 + M((rain * tf_gr) * (m1 ? 1.0 : 0.0));
+        v = M(m2 ? free_ : v);
+        c.int_rain_ground = M((c.lu_id == 599) ? 0.0 : v);
+        c.S_int_ground += M(c.int_rain_ground);
+        c.rain_ground = M(c.rain_top - c.int_rain_top - c.int_rain_ground);
+        double add = M((c.S_snow > 0) ? 0.0 : c.rain_ground);
+        c.z0 += add;
+        c.prec_event_csum += add;
+    }
+    // snow, upper storage (:154-245)
+    const bool cold = c.ta <= ta_fm;
+    c.snow_top = M(cold ? c.prec : 0.0);
+    {
+        const double ta = c.ta, lu = c.lu_id;
+        double s = c.swe_top_tot;
+        s = M(((ta > -1) && (lu == 10)) ? 9.0 : s);
+        s = M(((ta > -1) && (lu == 11)) ? 15.0 : s);
+        s = M(((ta > -1) && (lu == 12)) ? 25.0 : s);
+        const bool mid = (ta >= -3) && (ta <= -1);
+        s = M((mid && (lu == 10)) ? 2.5 + 0.5 * ta * 9 : s);
+        s = M((mid && (lu == 11)) ? 2.5 + 0.5 * ta * 15 : s);
+        s = M((mid && (lu == 12)) ? 2.5 + 0.5 * ta * 25 : s);
+        s = M(((ta < -3) && (lu == 10)) ? 18.0 : s);
+        s = M(((ta < -3) && (lu == 11)) ? 30.0 : s);
+        s = M(((ta < -3) && (lu == 12)) ? 50.0 : s);
+        c.swe_top_tot = s;
+        double free_ = M((c.swe_top >= s) ? 0.0 : s - c.swe_top);
+        double want = c.prec * tf_top;
+        bool m1 = (free_ >= want) && cold && (free_ > 0);
+        bool m2 = (free_ < want) && cold && (free_ > 0);
+        double v = 0.0 + M((c.prec * tf_top) * (m1 ? 1.0 : 0.0));
+        c.int_snow_top = M(m2 ? free_ : v);
+        c.S_int_top += M(c.int_snow_top);
+        c.swe_top += M(c.int_snow_top);
+    }
+    // snow, lower storage (:248-318)
+    {
+        double snow = M((c.prec - c.int_snow_top) * (cold ? 1.0 : 0.0));
+        double free_ = M((c.S_int_ground >= c.S_int_ground_tot) ? 0.0 : c.S_int_ground_tot - c.S_int_ground);
+        double want = snow * tf_gr;
+        bool m1 = (free_ >= want) && cold && (free_ > 0);
+        bool m2 = (free_ < want) && cold && (free_ > 0);
+        double v = 0.0 + M((snow * tf_gr) * (m1 ? 1.0 : 0.0));
+        v = M(m2 ? free_ : v);
+        c.int_snow_ground = M((c.lu_id == 599) ? 0.0 : v);
+        c.S_int_ground += M(c.int_snow_ground);
+        c.swe_ground += M(c.int_snow_ground);
+        c.snow_ground = M(c.snow_top - c.int_snow_top - c.int_snow_ground);
+        c.prec_event_csum += M(c.snow_ground);
+    }
+    // :321-343
+    c.int_top = M(c.int_rain_top + c.int_snow_top);
+    c.int_ground = M(c.int_rain_ground + c.int_snow_ground);
+    c.int_prec = M(c.int_rain_top + c.int_rain_ground + c.int_snow_top + c.int_snow_ground);
+}
+
+// ---- evapotranspiration.py:9-599 -----------------------------------------------------------
+RD bool lu_is_crop(double lu) { return (lu >= 500) && (lu < 600) && (lu == floor(lu)); }
+RD bool lu_is_tree(double lu) { return lu == 10 || lu == 11 || lu == 12 || lu == 15 || lu == 16 || lu == 17; }
+
+template <bool MASK1>
+RD void evapotranspiration(Cell& c, const StepPlan& p) {
+    const bool dry = c.prec <= 0;
+    // upper interception storage (:9-66)
+    {
+        bool ok = (c.S_int_top <= c.S_int_top_tot) && (c.S_int_top_tot > 0) && (c.S_int_top > 0);
+        bool m1 = ok && (c.pet_res <= c.S_int_top);
+        bool m2 = ok && (c.pet_res > c.S_int_top);
+        double e = 0.0 + M(c.pet_res * (m1 ? 1.0 : 0.0));
+        c.pet_res = M(m1 ? 0.0 : c.pet_res);
+        e += M(c.S_int_top * (m2 ? 1.0 : 0.0));
+        c.pet_res += M(-c.S_int_top * (m2 ? 1.0 : 0.0));
+        c.evap_int_top = e;
+        c.S_int_top += M(-e);
+    }
+    // lower interception storage (:69-134)
+    {
+        bool ok = (c.S_int_ground <= c.S_int_ground_tot) && (c.S_int_ground_tot > 0) && (c.S_int_ground > 0);
+        bool m1 = ok && (c.pet_res <= c.S_int_ground);
+        bool m2 = ok && (c.pet_res > c.S_int_ground);
+        double e = 0.0 + M(c.pet_res * (m1 ? 1.0 : 0.0));
+        c.pet_res = M(m1 ? 0.0 : c.pet_res);
+        e += M(c.S_int_ground * (m2 ? 1.0 : 0.0));
+        c.pet_res += M(-c.S_int_ground * (m2 ? 1.0 : 0.0));
+        c.evap_int_ground = e;
+        c.S_int_ground += M(-e);
+        c.evap_int = c.evap_int_ground + M(c.evap_int_top);  // :129, mask binds to the last term
+    }
+    // depression storage (:137-194)
+    {
+        bool ok = (c.S_dep > 0) && (c.pet_res > 0) && dry;
+        bool m1 = ok && (c.S_dep <= c.pet_res);
+        bool m2 = ok && (c.S_dep > c.pet_res);
+        double e = 0.0 + M(c.S_dep * (m1 ? 1.0 : 0.0));
+        c.pet_res += M(-c.S_dep * (m1 ? 1.0 : 0.0));
+        e += M(c.pet_res * (m2 ? 1.0 : 0.0));
+        c.pet_res = M(m2 ? 0.0 : c.pet_res);
+        c.evap_dep = e;
+        bool m3 = (c.S_dep > 0) && (e > 0);
+        c.S_dep += M(-e * (m3 ? 1.0 : 0.0));
+    }
+    c.evap_sur = c.evap_int_top + c.evap_int_ground + M(c.evap_dep);  // :197-212
+    // soil evaporation (:215-345)
+    {
+        bool m3 = c.de <= c.rew;
+        bool m4 = (c.de > c.rew) && (c.de <= c.tew);
+        bool m5 = c.de > c.tew;
+        double k = M(m3 ? 1.0 : c.k_stress_evap);
+        k = M(m4 ? (c.tew - c.de) / (c.tew - c.rew) : k);
+        k = M(m5 ? 0.0 : k);
+        c.k_stress_evap = k;
+        c.evap_coeff = M(c.basal_evap_coeff * k);
+        double pe = M(c.pet_res * c.evap_coeff);
+        c.pevap_soil = pe;
+        bool ok = (c.S_fp_rz > 0) && (pe > 0) && (c.swe <= 0) && dry;
+        bool m1 = ok && (pe <= c.S_fp_rz);
+        bool m2 = ok && (pe > c.S_fp_rz);
+        double e = 0.0 + M(pe * (m1 ? 1.0 : 0.0));
+        c.pet_res += M(-pe * (m1 ? 1.0 : 0.0));
+        c.pet_res = M((c.pet_res < 0) ? 0.0 : c.pet_res);
+        e += M(c.S_fp_rz * (m2 ? 1.0 : 0.0));
+        c.pet_res += M(-c.S_fp_rz * (m2 ? 1.0 : 0.0));
+        c.pet_res = M((c.pet_res < 0) ? 0.0 : c.pet_res);
+        c.evap_soil = M(e);
+        c.S_fp_rz += M(-c.evap_soil);
+    }
+    // transpiration (:348-543)
+    {
+        double tws = p.transp_water_stress * c.theta_ufc + M(c.theta_pwp);  // :360
+        double ks = lu_is_crop(c.lu_id) ? c.k_stress_transp : ((c.theta_rz - c.theta_pwp) / (tws - c.theta_pwp));
+        ks = M(ks);
+        ks = (ks > 1) ? 1.0 : ks;
+        c.k_stress_transp = ks;
+        double tc = M(c.basal_transp_coeff * ks);
+        bool anoxia = (c.lu_id > 500) && (c.lu_id < 599) && (c.theta_rz >= 0.8 * c.theta_sat);
+        if (anoxia) {
+            double r = c.S_lp_rz / c.S_ac_rz;
+            tc = ((r >= 0) && (r <= 1)) ? 1 - pow(r, 1.5) : 1.0;
+        }
+        tc = M(tc);
+        c.transp_coeff = tc;
+        double pt_ = M((c.pevap_soil < c.pet) ? c.pet - c.pevap_soil : 0.0);
+        double ptr_ = M((c.evap_soil < c.pet) ? c.pet - c.evap_soil : 0.0);
+        c.pt = M(pt_ * c.basal_transp_coeff);
+        double ptransp = M(ptr_ * tc);
+        ptransp = M(lu_is_tree(c.lu_id) ? c.pet * tc : ptransp);
+        c.ptransp = ptransp;
+        double res = M(ptransp);
+        double t_lp = 0.0, t_fp = 0.0;
+        const bool act = (ptransp > 0) && dry;
+        bool m1 = (c.S_lp_rz > 0) && (res <= c.S_lp_rz) && act;
+        t_lp += M(m1 ? res : 0.0);
+        res = M(m1 ? 0.0 : res);
+        bool m2 = (c.S_lp_rz > 0) && (res > c.S_lp_rz) && act;
+        t_lp += M(m2 ? c.S_lp_rz : 0.0);
+        res += M(m2 ? -c.S_lp_rz : 0.0);
+        bool m3 = (c.S_fp_rz > 0) && (res <= c.S_fp_rz) && (c.S_lp_rz <= 0) && act;
+        t_fp += M(m3 ? res : 0.0);
+        res = M(m3 ? 0.0 : res);
+        bool m4 = (c.S_fp_rz > 0) && (res > c.S_fp_rz) && (c.S_lp_rz <= 0) && act;
+        t_fp += M(m4 ? c.S_fp_rz : 0.0);
+        res += M(m4 ? -c.S_fp_rz : 0.0);
+        res = M((res < 0) ? 0.0 : res);
+        c.ptransp_res = res;
+        c.S_lp_rz += M(-t_lp);
+        c.S_fp_rz += M(-t_fp);
+        c.transp = M(t_fp + t_lp);
+    }
+    // :546-599
+    c.de += c.evap_soil + M(c.transp * (c.z_evap / c.z_root));  // :557
+    c.aet_soil = M(c.evap_soil + c.transp);
+    c.aet = M(c.evap_int_top + c.evap_int_ground + c.evap_dep + c.evap_soil + c.transp);
+}
+
+// ---- snow.py:6-290 ---------------------------------------------------------------------------
+template <bool MASK1>
+RD void snow(Cell& c, const StepPlan& p) {
+    const double ta_fm = p.ta_fm;
+    const bool cold = c.ta <= ta_fm;
+    double add = M(c.snow_ground * (cold ? 1.0 : 0.0));  // :6-26
+    c.S_snow += add;
+    c.swe += add;
+    c.S_snow += M(c.rain_ground * (((c.swe > 0) && (c.ta > ta_fm)) ? 1.0 : 0.0));  // :29-44
+    const double pot = M(p.sf * (c.ta - ta_fm) * p.dt);
+    // upper interception storage (:47-133)
+    {
+        bool has = (pot > 0) && (c.swe_top > 0);
+        double melt = 0.0;
+        melt = M((has && (pot <= c.swe_top)) ? pot : melt);
+        melt = M((has && (pot > c.swe_top)) ? c.swe_top : melt);
+        c.snow_melt_top = melt;
+        bool m4 = (melt > 0) && (melt <= c.swe_top);
+        bool m5 = (melt > 0) && (melt > c.swe_top);
+        c.pet_res += M(-melt * (m4 ? 1.0 : 0.0));
+        c.swe_top += M(-melt * (m4 ? 1.0 : 0.0));
+        c.pet_res += M(-c.swe_top * (m5 ? 1.0 : 0.0));
+        c.swe_top += M(m5 ? 0.0 : -c.swe_top);  // :98-101
+        c.pet_res = M((c.pet_res < 0) ? 0.0 : c.pet_res);
+        double wtmx = p.retention * c.swe_top;
+        double q_ret = M((c.S_int_top > c.S_int_top_tot) ? c.S_int_top - c.swe_top : 0.0);
+        bool over = c.S_int_top_tot < c.S_int_top;
+        double drip = (q_ret > wtmx) ? q_ret - wtmx : (((wtmx <= 0) && over) ? c.S_int_top - c.S_int_top_tot : 0.0);
+        drip = M(drip);
+        c.snow_melt_drip = drip;
+        c.S_snow += M(over ? drip : 0.0);
+        c.S_int_top += M(over ? -drip : 0.0);
+    }
+    // lower interception storage (:136-193)
+    {
+        bool has = (pot > 0) && (c.swe_ground > 0);
+        double melt = 0.0;
+        melt = M((has && (pot <= c.swe_ground)) ? pot : melt);
+        melt = M((has && (pot > c.swe_ground)) ? c.swe_ground : melt);
+        c.snow_melt_ground = melt;
+        bool m4 = (melt > 0) && (melt <= c.swe_ground);
+        bool m5 = (melt > 0) && (melt > c.swe_ground);
+        c.pet_res += M(-melt * (m4 ? 1.0 : 0.0));
+        c.swe_ground += M(-melt * (m4 ? 1.0 : 0.0));
+        c.pet_res += M(-c.swe_ground * (m5 ? 1.0 : 0.0));
+        c.swe_ground += M(m5 ? 0.0 : -c.swe_ground);
+    }
+    // snow cover (:196-290)
+    {
+        bool has = (pot > 0) && (c.swe > 0);
+        double melt = 0.0;
+        melt = M((has && (pot <= c.swe)) ? pot : melt);
+        melt = M((has && (pot > c.swe)) ? c.swe : melt);
+        c.snow_melt = melt;
+        bool m5 = (melt > 0) && (melt <= c.swe);
+        bool m6 = (melt > 0) && (melt > c.swe);
+        c.pet_res += M(-melt * (m5 ? 1.0 : 0.0));
+        c.swe += M(-melt * (m5 ? 1.0 : 0.0));
+        c.pet_res += M(-c.swe * (m6 ? 1.0 : 0.0));
+        c.swe = M(m6 ? 0.0 : c.swe);
+        c.pet_res = M((c.pet_res < 0) ? 0.0 : c.pet_res);
+        double wtmx = p.retention * c.swe;
+        double q_ret = M((c.S_snow > 0) ? c.S_snow - c.swe : 0.0);
+        double q = (q_ret > wtmx) ? q_ret - wtmx : ((wtmx <= 0) ? c.S_snow : 0.0);
+        q = M(q);
+        c.q_snow = q;
+        c.S_snow += M(-q);
+        c.z0 += M(q);
+        c.prec_event_csum += M(q);
+    }
+}
+
+// ---- infiltration.py ---------------------------------------------------------------------------
+template <bool MASK1>
+RD double theta_deficit(const Cell& c) {  // :1563-1594
+    double t = 0.0;
+    t = M((c.z_root > 0) ? (c.theta_sat - c.theta_rz) * (1 - c.sealing / 1) : t);
+    t = M((c.z_soil <= 0) ? 0.01 : t);
+    t = M((t <= 0) ? 0.01 : t);
+    return t;
+}
+template <bool MASK1>
+RD double theta_deficit_rel(const Cell& c) {  // :1597-1632
+    double t = 0.0;
+    t = M((c.z_root > 0) ? ((c.theta_sat - c.theta_rz) / (c.theta_sat - c.theta_pwp)) * (1 - c.sealing / 1) : t);
+    t = M((c.z_soil <= 0) ? 0.01 : t);
+    t = M((t <= 0) ? 0.01 : t);
+    return t;
+}
+template <bool MASK1>
+RD double theta_deficit_fp(const Cell& c) {  // :1635-1666
+    double t = 0.0;
+    t = M((c.z_soil > 0) ? (c.theta_fc - c.theta_rz) * (1 - c.sealing / 1) : t);
+    t = M((c.z_soil <= 0) ? 0.01 : t);
+    t = M((t <= 0) ? 0.01 : t);
+    return t;
+}
+
+template <bool MASK1>
+RD void event_bookkeeping_start(Cell& c, const StepPlan& p) {
+    if (p.cond1) {
+        // calc_depth_shrinkage_cracks :1767-1826
+        const double th = c.theta_rz;
+        double z = (th < c.theta_4) ? c.z_sc_max
+                                    : (((th >= c.theta_4) && (th < c.theta_27)) ? (th - c.theta_4) / (c.theta_27 - c.theta_4) : 0.0) * c.z_sc_max;
+        z = M(z);
+        z = M((th < c.theta_4) ? c.z_sc_max : z);
+        z = M((th > c.theta_27) ? 0.0 : z);
+        z = M((1 - c.sealing / 1) * z);
+        z = M((z > c.z_root) ? c.z_root : z);
+        z = M((c.lu_id == 13) ? 0.0 : z);
+        c.z_sc = z;
+        // set_event_vars :1829-1976
+        c.no_wf = 1;
+        c.z_wf = 0; c.z_wf_m1 = 0;
+        c.z_wf_t0 = 0; c.z_wf_t0_m1 = 0;
+        c.z_wf_t1 = 0; c.z_wf_t1_m1 = 0;
+        c.z_wf_fc = 0;
+        c.inf_mat_event_csum = 0;
+        c.inf_mat_pot_event_csum = 0;
+        c.inf_mp_event_csum = 0;
+        c.y_mp = 0; c.y_mp_m1 = 0;
+        c.inf_sc_event_csum = 0;
+        c.y_sc = 0; c.y_sc_m1 = 0;
+        double td = theta_deficit<MASK1>(c);
+        double tdr = theta_deficit_rel<MASK1>(c);
+        c.theta_d = M(td);
+        c.theta_d_rel = M(tdr);
+        c.theta_d_t0 = M(td);
+        c.theta_d_rel_t0 = M(tdr);
+        c.theta_d_fp = M(theta_deficit_fp<MASK1>(c));
+        c.prec_event_csum = 0;
+        c.t_event_csum = 0;
+        c.de = 0;
+    }
+    // cond2 / cond3 are `scalar & grid.any()` gates whose kernels re-apply the per-cell mask
+    // (infiltration.py:1987, :2005): a cell acts iff the scalar part holds and its own mask is true.
+    if (p.cond2s) {  // set_event_vars_start_rainfall_pause :1979-1995 (+ calc_z_wf_fc :1535-1560)
+        double z = M((c.theta_d_fp > 0) ? c.inf_mat_event_csum / c.theta_d_fp : c.z_wf);
+        z = M((z > c.z_soil) ? c.z_soil : z);
+        bool mk_ = (c.prec == 0) && (c.prec_m1 != 0);
+        c.z_wf_fc = M(mk_ ? z : c.z_wf_fc);
+    }
+    if (p.cond3s) {  // set_event_vars_end_rainfall_pause :1998-2053
+        bool mk_ = (c.prec != 0) && (c.prec_m1 == 0);
+        c.no_wf = mk_ ? 2.0 : c.no_wf;
+        double td = theta_deficit<MASK1>(c);
+        c.theta_d = M(mk_ ? td : c.theta_d);
+        double tdr = theta_deficit_rel<MASK1>(c);
+        c.theta_d_rel = M(mk_ ? tdr : c.theta_d_rel);
+        if (mk_) { c.z_wf_t1 = 0; c.z_wf_t1_m1 = 0; }
+        c.prec_event_csum = mk_ ? 0.0 : c.prec_event_csum;
+        c.t_event_csum = mk_ ? 0.0 : c.t_event_csum;
+    }
+    if (p.cond5) c.t_event_csum += p.dt;  // :2175-2180
+}
+
+template <bool MASK1>
+RD void green_ampt_and_matrix(Cell& c, const StepPlan& p) {
+    const double dt = p.dt;
+    // calc_green_ampt_params :7-48 with calc_pi_gr/pi_m/sat_time/Fs :1669-1764
+    const double ktw = c.ks * c.theta_d * c.wfs;
+    c.pi_gr = M(c.ks * (((c.theta_d * c.wfs) / (c.prec_event_csum + 1)) + 1));
+    const double pi_m = M(ktw);
+    c.pi_m = M(pi_m);
+    {
+        bool le = c.pi_m <= c.prec_event_csum, z = (c.t_sat == 0);
+        bool m1 = le && (c.pi_m > c.pi_gr) && z;
+        bool m2 = ((c.prec * (1 / dt) - c.ks) * c.prec_event_csum > ktw) && le && (c.pi_m <= c.pi_gr) && z;
+        double t = m1 ? c.t_event_csum - dt : c.t_sat;
+        t = m2 ? c.t_event_csum + (ktw / (c.pi_m * (c.pi_m * -c.ks))) - (dt / c.pi_m) * c.prec_event_csum : t;
+        c.t_sat = M(t);
+    }
+    {
+        double Fs = M(ktw / (pi_m - c.ks));
+        Fs = M((pi_m <= c.ks) ? pi_m : Fs);
+        c.Fs = M(Fs);
+    }
+    // calc_inf_mat :51-427   (vs.Fs_t0 and vs.theta_d_t1 are never written by the reference: 0)
+    const bool mask1 = (c.pi_m <= c.prec_event_csum) && (c.t_event_csum > c.t_sat) && (c.t_sat > 0);
+    const bool mask2 = (c.pi_m > c.prec_event_csum) && (c.t_event_csum > c.t_sat) && (c.t_sat > 0);
+    const bool mask3 = (c.t_sat > c.t_event_csum - dt) && (c.t_sat < c.t_event_csum);
+    const bool mask4 = (c.pi_m > c.prec_event_csum) && (c.t_sat <= 0);
+    const double ksdt = c.ks * dt;
+    const double seal = ((1 - c.sealing) / 1);
+    double pot = ksdt;
+    double rec = 0.0;
+    if (mask1 || mask3) {
+        double a = M(c.ks * (c.t_event_csum - c.t_sat));
+        double b = c.Fs + M(2 * c.theta_d * c.wfs);  // :77
+        rec = (ksdt / 2) * (1 + (1 + 2 * b / a) / sqrt(1 + (4 * b / a) + (4 * (0.0 * 0.0) / (a * a))));
+    }
+    pot = M(mask1 ? rec * seal : pot);
+    if (mask2) {
+        double num = ksdt * c.wfs * c.theta_d;
+        double l1 = M((c.z0 > ksdt) ? num / (c.z0 - ksdt) : num / ksdt);
+        pot = ksdt * (1 + ((c.wfs * c.theta_d) / l1)) * seal;
+    }
+    pot = M(pot);
+    {
+        double rec3 = M(mask3 ? rec : 0.0);
+        double sat3 = M(mask3 ? c.z0 * (c.t_sat - (c.t_event_csum - dt)) : 0.0);
+        pot = M(mask3 ? sat3 + rec3 * seal : pot);
+    }
+    pot = M(mask4 ? c.pi_gr * seal : pot);
+    c.inf_mat_pot = pot;
+    double inf = c.inf_mat;  // previous value survives only if z0 / pot is NaN
+    inf = M((c.z0 < pot) ? c.z0 : inf);
+    inf = M((c.z0 >= pot) ? pot : inf);
+    {
+        double cap = (c.S_ac_rz + c.S_ufc_rz) - (c.S_lp_rz + c.S_fp_rz);
+        inf = M((inf > cap) ? cap : inf);
+        inf = M((inf < 0) ? 0.0 : inf);
+    }
+    c.inf_mat = inf;
+    c.inf_mat_event_csum += M(inf);
+    c.inf_mat_pot_event_csum += M(pot);
+    // wetting fronts
+    const bool wf1 = (c.no_wf == 1), wf2 = (c.no_wf == 2);
+    double dz = 0.0;
+    dz = M(wf1 ? (inf / c.theta_d_t0) : dz);
+    dz = M(wf2 ? inf / c.theta_d : dz);
+    dz = M(isfinite(dz) ? dz : 0.0);
+    c.z_wf_t0 += dz;
+    c.z_wf_t1 += dz;
+    c.z_wf_t0 = M((c.z_wf_t0 > c.z_soil) ? c.z_soil : c.z_wf_t0);
+    c.z_wf_t1 = M((c.z_wf_t1 > c.z_soil) ? c.z_soil : c.z_wf_t1);
+    c.z0 += M(-inf);
+    c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
+    const bool pause = (c.z_wf_fc > 0) && (c.rain_ground <= 0);
+    {
+        double d0 = M((pause && wf1) ? pot / c.theta_d_t0 : 0.0);
+        c.z_wf_t0 += M(isfinite(d0) ? d0 : 0.0);
+        c.z_wf_t0 = M(((c.z_wf_t0 > c.z_wf_fc) && (c.z_wf_fc > 0)) ? c.z_wf_fc : c.z_wf_t0);
+        c.z_wf_t0 = M((c.z_wf_t0 > c.z_soil) ? c.z_soil : c.z_wf_t0);
+        double d1 = M((pause && wf2) ? pot / c.theta_d : 0.0);
+        c.z_wf_t1 += M(isfinite(d1) ? d1 : 0.0);
+        c.z_wf_t1 = M(((c.z_wf_t1 > c.z_wf_fc) && (c.z_wf_fc > 0)) ? c.z_wf_fc : c.z_wf_t1);
+        c.z_wf_t1 = M((c.z_wf_t1 > c.z_soil) ? c.z_soil : c.z_wf_t1);
+    }
+    const bool m14 = (c.z_wf_t0 >= c.z_wf_t1) && (c.z_wf_t1 <= 0);
+    const bool m15 = (c.z_wf_t0 > c.z_wf_t1) && (c.z_wf_t1 > 0);
+    const bool m20 = (c.z_wf_t0 <= c.z_wf_t1) && (c.z_wf_t1 > 0);
+    c.z_wf = M(m14 ? c.z_wf_t0 : c.z_wf);
+    c.theta_d = M(m14 ? c.theta_d_t0 : c.theta_d);
+    c.theta_d_rel = M(m14 ? c.theta_d_rel_t0 : c.theta_d_rel);
+    c.z_wf_m1 = M(m15 ? 0.0 : c.z_wf_m1);
+    c.z_wf = M(m15 ? c.z_wf_t1 : c.z_wf);
+    c.no_wf = m20 ? 1.0 : c.no_wf;
+    c.z_wf = M(m20 ? c.z_wf_t0 : c.z_wf);
+    c.theta_d = M(m20 ? c.theta_d_t0 : c.theta_d);
+    c.theta_d_rel = M(m20 ? c.theta_d_rel_t0 : c.theta_d_rel);
+    c.z_wf = M((c.z_wf > c.z_soil) ? c.z_soil : c.z_wf);
+    c.theta_d = M(c.theta_d_t0);  // :411-416 (theta_d_t1 <= 0 always holds)
+}
+
+// Vertical macropores: radial wetting front y(t) advanced in `substeps` explicit sub-steps
+// (infiltration.py:430-1077, loop body :582-777).
+//
+// Exact early exit.  One pass of the loop body is a pure function G of the carried triple
+// (ym1, t, inf_mp_event_csum) plus loop-invariant inputs; the accumulator inf_mp only receives
+// `+= inf_mp_di`.  If a pass returns the triple bit-identical to its input and added
+// inf_mp_di == 0, every later pass repeats it verbatim, so the remaining passes are skipped
+// without changing a single bit of the result.  This is what happens on dry steps (z0 == 0):
+// the front stops after the second pass and the reference's other 118 of 120 daily sub-steps
+// recompute the same numbers.  If inf_mp turns NaN it stays NaN (NaN + x) and so does
+// inf_mp_event_csum and y; the reference then stores y_mp = inf_mp = 0 (:808-824), so the loop
+// can stop at the first NaN as well.
+template <bool MASK1>
+RD void macropores(Cell& c, const StepPlan& p) {
+    const double dt = p.dt, r_mp = p.r_mp, pi = p.pi;
+    const int substeps = p.substeps;
+    // the reference's second `update(z_wf, ...)` discards the first (:443-462)
+    const double z_wf = M((c.no_wf == 2) ? 0.0 : c.z_wf_t1);
+    const double z_wf_m1 = M((c.no_wf == 2) ? 0.0 : c.z_wf_t1_m1);
+    double nonsat = c.lmpv - M(z_wf);  // :468
+    nonsat = M((nonsat < 0) ? 0.0 : nonsat);
+    double dz = z_wf - M(z_wf_m1);  // :480
+    dz = M((z_wf >= c.lmpv) ? nonsat : dz);
+    dz = M((nonsat <= 0) ? 0.0 : dz);
+    dz = M((dz <= 0) ? 0.0 : dz);
+    nonsat = c.lmpv - M(c.z_wf);  // :503
+    nonsat = M((nonsat < 0) ? 0.0 : nonsat);
+    nonsat = M((substeps == 1) ? nonsat + dz / 1.39 : nonsat);
+    c.lmpv_non_sat = nonsat;
+
+    const double a = M(c.theta_d * p.r_mp2);
+    double ym1 = M(c.y_mp_m1);
+    double y = ym1;
+    double csum = M(c.inf_mp_event_csum);
+    double t = 0.0, inf_mp = 0.0;
+    const double z0_di = M(c.z0 * (c.mp_drain_area / substeps));
+    const double dts = M(dt / substeps);
+    const double ksw = c.ks * c.wfs;
+    const double rtd2 = r_mp * (c.theta_d * c.theta_d);
+    const double dmtd = c.dmpv * c.theta_d;
+    const double tfac = c.theta_d / (ksw * r_mp);
+    for (int i = 0; i < substeps; i++) {
+        const double ym1_in = ym1, t_in = t, csum_in = csum;
+        t += dts;
+        double cc = M(ksw * t);
+        cc = M(isnan(cc) ? 0.0 : cc);
+        double b1 = M(p.sqrt6x2 * sqrt(cc * (6 * cc - a)));
+        b1 = M(isnan(b1) ? 0.0 : b1);
+        double b2 = M(rtd2 * (12 * cc - a + b1));
+        b2 = M(isnan(b2) ? 0.0 : b2);
+        b2 = M((b2 <= 0) ? 0.0 : b2);
+        const double cb = pow(b2, 1.0 / 3);
+        double y1 = M((cb / c.theta_d) * 0.5);
+        double y2 = M((a / cb) * 0.5);
+        y = M(y1 + y2 + ym1);
+        y = M((y < r_mp) ? r_mp : y);
+        y = M((y < ym1) ? ym1 : y);
+        double pot_di = M(pi * (y * y - ym1 * ym1) * nonsat * c.theta_d * c.dmpv * 1e-06);
+        double di = M((pot_di > z0_di) ? z0_di : pot_di);
+        di = M((nonsat == 0) ? 0.0 : di);
+        inf_mp += M(di);
+        csum += M(di);
+        y = r_mp + M(sqrt((csum / dmtd) / pi));  // :728-730
+        y = M((y < r_mp) ? r_mp : y);
+        t = M(tfac * (pow(y, 3.0) / 3.0 - (y * y) * r_mp / 2.0 + p.r_mp3_6));
+        inf_mp = M((inf_mp < 0) ? 0.0 : inf_mp);
+        ym1 = M(y);
+        if (isnan(inf_mp)) break;
+        if (di == 0.0 && ym1 == ym1_in && t == t_in && csum == csum_in) break;
+    }
+    y = M(y);
+    c.y_mp = M(isnan(y) ? 0.0 : y);
+    inf_mp = M(inf_mp);
+    inf_mp = M(isnan(inf_mp) ? 0.0 : inf_mp);
+
+    double share = M((nonsat > 0) ? 1.0 - (c.lmpv - c.z_root) / nonsat : 0.0);
+    share = M((c.lmpv <= c.z_root) ? 1.0 : share);
+    share = M((z_wf >= c.z_root) ? 0.0 : share);
+    share = M((share < 0) ? 0.0 : share);
+    share = M((share > 1) ? 1.0 : share);
+    double mp_rz = M(inf_mp * share);
+    {   // :880-913; vs.inf_mat_rz still holds the PREVIOUS step's value here
+        double free_rz = (c.S_ac_rz + c.S_ufc_rz) - (c.inf_mat_rz + c.S_lp_rz + c.S_fp_rz);
+        mp_rz = M(((mp_rz > free_rz) && (free_rz >= 0)) ? free_rz : mp_rz);
+        mp_rz = M((free_rz < 0) ? 0.0 : mp_rz);
+    }
+    c.inf_mp_rz = mp_rz;
+    double mp_ss = M(inf_mp * (1 - share));
+    {
+        double free_ss = (c.S_ac_ss + c.S_ufc_ss) - (c.S_lp_ss + c.S_fp_ss);
+        mp_ss = M(((mp_ss > free_ss) && (free_ss > 0)) ? free_ss : mp_ss);
+    }
+    c.inf_ss = M(mp_ss);
+    c.S_fp_ss += M(c.inf_ss);
+    bool ex = c.S_fp_ss > c.S_ufc_ss;
+    c.S_lp_ss += M(ex ? (c.S_fp_ss - c.S_ufc_ss) : 0.0);
+    c.S_fp_ss = M(ex ? c.S_ufc_ss : c.S_fp_ss);
+    ex = c.S_lp_ss > c.S_ac_ss;
+    mp_ss += M(ex ? -(c.S_lp_ss - c.S_ac_ss) : 0.0);
+    mp_ss = M((mp_ss < 0) ? 0.0 : mp_ss);
+    c.inf_mp_ss = mp_ss;
+    c.S_lp_ss = M(ex ? c.S_ac_ss : c.S_lp_ss);
+    c.inf_mp = c.inf_mp_rz + M(c.inf_mp_ss);  // :990
+    c.inf_mp_event_csum += M(c.inf_mp);
+    c.z0 += M(-c.inf_mp);
+    c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
+    if (p.lbc) {  // :1013-1065
+        bool lbc = c.z_wf > c.lmpv;
+        double lim = c.ks * dt * c.mp_drain_area;
+        double add = lbc ? ((c.z0 > lim) ? lim : c.z0) : 0.0;
+        c.inf_mp += M(add);
+        double room = c.S_ac_ss - c.S_lp_ss;
+        c.inf_mp = M(((c.z_wf > c.z_root) && (c.inf_mp > room) && (room > 0)) ? room : c.inf_mp);
+        double sub = lbc ? ((c.z0 > lim) ? lim : c.z0) : 0.0;
+        c.z0 += M(-sub);
+        c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
+    }
+}
+
+// Shrinkage cracks (infiltration.py:1080-1318).  In the reference the loop's `inf_sc` carry is
+// never updated (always 0) and `inf_sc_di` is doubled (:1248-1252); only y_sc and z_sc_non_sat
+// evolve.  Same exact early exit as for the macropores: the pass is a pure function of the
+// carried triple (ym1, t, inf_sc_event_csum).
+template <bool MASK1>
+RD void shrinkage_cracks(Cell& c, const StepPlan& p) {
+    const double dt = p.dt, l_sc = p.l_sc;
+    const int substeps = p.substeps;
+    const double z_wf = M((c.no_wf == 2) ? 0.0 : c.z_wf_t1);
+    const double z_wf_m1 = M((c.no_wf == 2) ? 0.0 : c.z_wf_t1_m1);
+    double nonsat = c.z_sc - M(z_wf);
+    nonsat = M((nonsat < 0) ? 0.0 : nonsat);
+    double dz = z_wf - M(z_wf_m1);
+    dz = M((z_wf >= c.z_sc) ? nonsat : dz);
+    dz = M((nonsat <= 0) ? 0.0 : dz);
+    dz = M((dz <= 0) ? 0.0 : dz);
+    nonsat = c.z_sc - M(c.z_wf);
+    nonsat = M((nonsat < 0) ? 0.0 : nonsat);
+    nonsat = M((substeps == 1) ? nonsat + dz / 1.39 : nonsat);
+    c.z_sc_non_sat = nonsat;
+
+    double ym1 = M(c.y_sc_m1), y = ym1;
+    double csum = M(c.inf_sc_event_csum);
+    double t = 0.0;
+    const double z0_di = M(c.z0 / substeps);
+    const double dts = M(dt / substeps);
+    const double ksw = c.ks * c.wfs;
+    const double geo = nonsat * c.theta_d * l_sc;
+    for (int i = 0; i < substeps; i++) {
+        const double ym1_in = ym1, t_in = t, csum_in = csum;
+        t += dts;
+        y = M(sqrt((ksw * t * 2) / c.theta_d));
+        double pot_di = M(geo * (y - ym1) * 1e-06);
+        pot_di = M((pot_di <= 0) ? 0.0 : pot_di);
+        double di = M((pot_di > z0_di) ? z0_di : pot_di);
+        di = M((nonsat <= 0) ? 0.0 : di);
+        di += M(di);
+        csum += M(di);
+        y = M(csum / l_sc / 2);
+        t = M(((ym1 * ym1) * c.theta_d) / (ksw * 2));
+        ym1 = M(y);
+        if (isnan(csum)) break;  // y = csum / l_sc / 2 stays NaN in every later pass
+        if (ym1 == ym1_in && t == t_in && csum == csum_in) break;
+    }
+    c.y_sc = M(y);
+    c.inf_sc = 0.0;
+    c.inf_sc_event_csum += M(c.inf_sc);
+    c.z0 += M(-c.inf_sc);
+    c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
+}
+
+template <bool MASK1>
+RD void infiltration_tail(Cell& c, const StepPlan& p) {
+    // calc_inf_rz :1321-1417
+    c.inf_mat_rz = M(c.inf_mat);
+    c.inf_sc_rz = M(c.inf_sc);
+    c.inf_rz = M(c.inf_mat_rz + c.inf_mp_rz + c.inf_sc_rz);
+    c.S_fp_rz += M(c.inf_rz);
+    bool ex = c.S_fp_rz > c.S_ufc_rz;
+    c.S_lp_rz += M(ex ? (c.S_fp_rz - c.S_ufc_rz) : 0.0);
+    c.S_fp_rz = M(ex ? c.S_ufc_rz : c.S_fp_rz);
+    ex = c.S_lp_rz > c.S_ac_rz;
+    c.inf_mp_rz += M(ex ? -(c.S_lp_rz - c.S_ac_rz) : 0.0);
+    c.inf_mp_rz = M((c.inf_mp_rz < 0) ? 0.0 : c.inf_mp_rz);
+    c.z0 += M(ex ? c.S_lp_rz - c.S_ac_rz : 0.0);
+    c.S_lp_rz = M(ex ? c.S_ac_rz : c.S_lp_rz);
+    c.inf_mp = c.inf_mp_rz + M(c.inf_mp_ss);  // :1399
+    c.inf_rz = M(c.inf_mat_rz + c.inf_mp_rz + c.inf_sc_rz);
+    c.inf = M(c.inf_rz + c.inf_ss);  // :1519-1532
+    // calc_hof_and_sof :1420-1476
+    double hof = M(c.z0);
+    hof = M((hof < 0) ? 0.0 : hof);
+    c.q_hof = hof;
+    bool sat = ((c.S_lp_rz + c.S_fp_rz) > (c.S_ac_rz + c.S_ufc_rz)) && ((c.S_lp_ss + c.S_fp_ss) >= (c.S_ac_ss + c.S_ufc_ss));
+    c.q_sof = M(sat ? (c.S_lp_rz + c.S_fp_rz) - (c.S_ac_rz + c.S_ufc_rz) : 0.0);
+    bool so = c.q_sof > 0;
+    c.S_fp_rz = M(so ? c.S_ufc_rz : c.S_fp_rz);
+    c.S_lp_rz = M(so ? c.S_ac_rz : c.S_lp_rz);
+    // calc_surface_runoff :1479-1516
+    c.z0 += M(-hof);
+    c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
+    c.q_sur = 0.0 + M(c.q_hof + c.q_sof);
+    c.q_sur += (c.maskRiverLake != 0) ? c.prec : 0.0;
+    if (p.cond4) {  // reset_event_vars :2056-2144
+        c.z_wf = 0; c.z_wf_t0 = 0; c.z_wf_t1 = 0;
+        c.y_mp = 0;
+        c.y_sc = 0;
+        double td = theta_deficit<MASK1>(c);
+        c.theta_d = M(td);
+        c.theta_d_t0 = M(td);
+        c.pi_gr = 0; c.pi_m = 0; c.t_sat = 0; c.Fs = 0; c.z_sc = 0;
+    }
+}
+
+// ---- subsurface_runoff.py / capillary_rise.py -------------------------------------------------
+// Salvucci-type flux between two depths: ((z/(-ha*10.2))^-n - (h/ha)^-n) / (1 + (h/ha)^-n + (n-1)(z/(-ha*10.2))^-n)
+RD double salvucci(double pa, double pb, double n_salv) { return (pa - pb) / (1 + pb + (n_salv - 1) * pa); }
+
+template <bool LAT, bool MASK1>
+RD void subsurface(Cell& c, const StepPlan& p) {
+    const double dt = p.dt;
+    const double zsub = c.z_soil - c.z_root;
+    // calc_rise_of_saturation_water_table :693-765
+    {
+        double lmpv_ss = c.lmpv - M(c.z_root);  // :705
+        lmpv_ss = M((c.lmpv < c.z_root) ? 0.0 : lmpv_ss);
+        const double lp_ss_ac = c.S_lp_ss / c.theta_ac;
+        double top = M((c.S_lp_ss < c.theta_ac) ? lp_ss_ac : c.S_lp_rz + lp_ss_ac);
+        double nomp = zsub - lmpv_ss - M(c.z_sat);  // :733
+        nomp = (nomp < 0) ? 0.0 : nomp;
+        double v = lp_ss_ac;
+        if (top > nomp) {
+            if ((c.S_fp_ss >= c.S_ufc_ss) && (((c.S_lp_ss + 1e-6) / c.theta_ac) < zsub)) v = lp_ss_ac;
+            else if ((c.S_fp_rz >= c.S_ufc_rz) && (c.S_lp_ss + 1e-6 >= c.S_ac_ss)) v = c.S_lp_rz / c.theta_ac + lp_ss_ac;
+        }
+        c.z_sat = M(v);
+    }
+    // calc_S_zsat :7-48
+    c.S_zsat = M((c.z_sat <= c.z_soil) ? c.z_sat * c.theta_ac : c.z_soil * c.theta_ac);
+    c.S_zsat_ss = M((c.z_sat <= zsub) ? c.S_zsat : zsub * c.theta_ac);
+    c.S_zsat_rz = M((c.z_sat > zsub) ? (c.z_sat - zsub) * c.theta_ac : 0.0);
+    if (LAT) {  // calc_z_sat_layer :52-245
+#define ROGER_LAYER(k, name, clamp_top)                                  \
+    {                                                                    \
+        double z = (k == 0) ? M(c.z_sat) : c.z_sat - M(200.0 * k);       \
+        if (clamp_top) z = M((z > 200) ? 200.0 : z);                     \
+        z = M((z <= 0) ? 0.0 : z);                                       \
+        c.name = z;                                                      \
+    }
+        ROGER_LAYER(0, z_sat_layer_1, true) ROGER_LAYER(1, z_sat_layer_2, true) ROGER_LAYER(2, z_sat_layer_3, true)
+        ROGER_LAYER(3, z_sat_layer_4, true) ROGER_LAYER(4, z_sat_layer_5, true) ROGER_LAYER(5, z_sat_layer_6, true)
+        ROGER_LAYER(6, z_sat_layer_7, true) ROGER_LAYER(7, z_sat_layer_8, false)
+#undef ROGER_LAYER
+    }
+    const double mn = -c.n_salv;
+    const double haz = -c.ha * 10.2;
+    double pb_rz = 0.0;  // (h_rz/ha)^-n, shared by root-zone percolation and capillary rise (h_rz is unchanged in between)
+    bool have_pb_rz = false;
+    // calc_potential_percolation_rz :768-888
+    {
+        bool m1 = (c.z_wf < c.z_root) && (c.z_sat <= 0);
+        bool m2 = (c.z_wf >= c.z_root) && (c.z_sat <= 0);
+        bool m3 = (c.z_sat > 0) && (c.z_root < c.z_soil - c.z_sat);
+        double perc = M(m1 ? c.k_rz * dt : 0.0);
+        perc = M(m2 ? c.k_rz * dt : perc);
+        if (m3) {
+            double z = zsub - c.z_sat;
+            double pa = pow(z / haz, mn);
+            pb_rz = pow(-c.h_rz / -c.ha, mn);
+            have_pb_rz = true;
+            perc = salvucci(pa, pb_rz, c.n_salv) * dt * c.ks * (-1);
+        }
+        perc = M(perc);
+        perc = M((perc < 0) ? 0.0 : perc);
+        const double lim = c.z_soil - c.z_sat;
+        const bool gate = c.z_root < lim;  // z_root[taum1] == z_root[tau]
+        const double avail = c.S_lp_rz + c.S_fp_rz;
+        bool m4 = (perc > 0) && (avail >= perc) && gate;
+        bool m5 = (perc > 0) && (avail < perc) && gate;
+        double q = 0.0;
+        q = M(m4 ? perc : q);
+        q = M(m5 ? c.S_fp_rz + c.S_lp_rz : q);
+        double room = (c.S_ac_ss + c.S_ufc_ss) - (c.S_lp_ss + c.S_fp_ss);
+        bool m6 = (q > 0) && (room > 0) && (q > room) && gate;
+        q = M(m6 ? room : q);
+        bool m7 = (c.S_lp_ss >= c.S_ac_ss - 1e-6) && (c.S_fp_ss >= c.S_ufc_ss - 1e-6);
+        q = M(m7 ? 0.0 : q);
+        q = M((c.z_root >= lim) ? 0.0 : q);
+        c.q_pot_rz = q;
+    }
+    // calc_percolation_rz :891-968
+    {
+        bool below = c.z_sat < zsub;
+        bool m1 = (c.S_lp_rz < c.q_pot_rz) && below;
+        bool m2 = (c.S_lp_rz >= c.q_pot_rz) && below;
+        double q = M(c.q_pot_rz);
+        q = M((c.z_sat >= zsub) ? 0.0 : q);
+        c.S_fp_rz += M(m1 ? -(q - c.S_lp_rz) : 0.0);
+        c.S_lp_rz = M(m1 ? 0.0 : c.S_lp_rz);
+        c.S_lp_rz += M(m2 ? -q : 0.0);
+        c.S_fp_ss += M(q);
+        bool ex = c.S_fp_ss > c.S_ufc_ss;
+        c.S_lp_ss += M(ex ? c.S_fp_ss - c.S_ufc_ss : 0.0);
+        c.S_fp_ss = M(ex ? c.S_ufc_ss : c.S_fp_ss);
+        ex = c.S_lp_ss > c.S_ac_ss;
+        q += M(ex ? -(c.S_lp_ss - c.S_ac_ss) : 0.0);
+        c.S_lp_rz += M(ex ? c.S_lp_ss - c.S_ac_ss : 0.0);
+        c.S_lp_ss = M(ex ? c.S_ac_ss : c.S_lp_ss);
+        c.q_rz = q;
+    }
+    if (LAT) {
+        // calc_potential_lateral_subsurface_runoff :249-362
+        const double geom = (1 / (p.dx * (c.z_soil / 1000)));
+        double mat = M((c.ks * c.slope * c.z_sat * p.dx * 1000 * dt) * 1e-6 * geom);
+        mat = M((c.z_sat <= 0) ? 0.0 : mat);
+        const double mpf = p.r_mp2;
+#define ROGER_TERM(n) (c.z_sat_layer_##n * c.v_mp_layer_##n * dt * p.dx * 1000 * c.dmph * 1e-6 * mpf * p.pi * 1e-6)
+        double sum = ROGER_TERM(1);
+        sum = sum + ROGER_TERM(2);
+        sum = sum + ROGER_TERM(3);
+        sum = sum + ROGER_TERM(4);
+        sum = sum + ROGER_TERM(5);
+        sum = sum + ROGER_TERM(6);
+        sum = sum + ROGER_TERM(7);
+        sum = sum + ROGER_TERM(8);
+#undef ROGER_TERM
+        double mp = M(sum * geom);
+        mp = M((mp < 0) ? 0.0 : mp);
+        mp = M((c.z_sat <= 0) ? 0.0 : mp);
+        double pot = M(mp + mat);
+        double sh_mat = M(mat / pot);
+        sh_mat = M((pot == 0) ? 0.0 : sh_mat);
+        double sh_mp = M(mp / pot);
+        sh_mp = M((pot == 0) ? 0.0 : sh_mp);
+        c.q_sub_mat_share = sh_mat;
+        c.q_sub_mp_share = sh_mp;
+        pot = M((pot > c.S_lp_rz + c.S_lp_ss) ? c.S_lp_rz + c.S_lp_ss : pot);
+        c.q_sub_pot = pot;
+        c.q_sub_mat_pot = M(pot * sh_mat);
+        c.q_sub_mp_pot = M(pot * sh_mp);
+        // calc_lateral_subsurface_runoff_rz :365-457
+        double rz_share = M((c.z_sat > 0) ? ((c.z_sat - zsub) / c.z_sat) : 0.0);
+        bool off = (c.z_sat <= zsub) || (c.S_lp_rz <= 0);
+        rz_share = M(off ? 0.0 : rz_share);
+        rz_share = M(isnan(rz_share) ? 0.0 : rz_share);
+        c.S_zsat_rz = M((c.z_sat * rz_share) * c.theta_ac);
+        double want = c.q_sub_pot * rz_share;
+        c.q_sub_rz = M((want < c.S_zsat_rz) ? want : c.S_zsat_rz);
+        c.q_sub_mat_rz = M(c.q_sub_rz * sh_mat);
+        c.q_sub_mp_rz = M(c.q_sub_rz * sh_mp);
+        c.q_sub_mp_pot_rz = M(c.q_sub_mp_pot * rz_share);
+        c.z_sat += M(-c.q_sub_rz / c.theta_ac);
+        c.S_lp_rz += M(-c.q_sub_rz);
+        // calc_potential_lateral_subsurface_runoff_ss :461-517
+        double ss_share = M(zsub / c.z_sat);
+        bool one = (c.z_sat <= zsub) || (c.S_lp_rz <= 0);
+        bool zero = c.z_sat <= 0;
+        bool nan_ = isnan(ss_share);
+        ss_share = M(one ? 1.0 : ss_share);
+        ss_share = M(zero ? 0.0 : ss_share);
+        ss_share = M(nan_ ? 0.0 : ss_share);
+        c.q_sub_mat_pot_ss = M(c.q_sub_mat_pot * ss_share);
+        c.q_sub_mp_pot_ss = M(c.q_sub_mp_pot * ss_share);
+        c.q_sub_pot_ss = M(c.q_sub_mat_pot_ss + c.q_sub_mp_pot_ss);
+    }
+    // calc_potential_percolation_ss :971-1099 (the z_gw <= 10 assignment overwrites the z_gw > 10 one)
+    {
+        const double zgw = c.z_gw * 1000;
+        double z = (zgw - c.z_soil) + M(zsub / 2);
+        double pa = pow(z / haz, mn);
+        double pb = pow(-c.h_ss / -c.ha, mn);
+        const double kfdt = c.kf * dt;
+        double sal = salvucci(pa, pb, c.n_salv);
+        double perc;
+        if ((c.z_gw <= 10) && (zgw > c.z_soil) && (c.z_sat > 0)) perc = fmin(fmin(kfdt, c.ks_ss * dt), c.k_ss * dt);
+        else perc = fmin(kfdt, sal * dt * c.ks_ss * (-1));
+        perc = M(perc);
+        const bool above = c.z_soil < zgw;
+        const double avail = c.S_fp_ss + c.S_lp_ss;
+        bool m1 = (perc > 0) && above && (perc <= avail);
+        bool m2 = (perc > 0) && above && (perc > avail);
+        double q = 0.0;
+        q = M(m1 ? perc : q);
+        q = M(m2 ? avail : q);
+        double cpr = M(sal * dt * c.ks_ss);
+        cpr = M(((perc > 0) && above) ? 0.0 : cpr);
+        cpr = M((zgw - c.z_soil > 10000) ? 0.0 : cpr);
+        q = M((cpr > 0) ? 0.0 : q);
+        c.q_pot_ss = q;
+    }
+    if (!LAT) {  // calc_percolation_ss :1102-1154
+        c.q_ss = M(c.q_pot_ss);
+        c.z_sat += M((c.z_sat > 0) ? -c.q_ss / c.theta_ac : 0.0);
+        c.z_sat = M((c.z_sat < 0) ? 0.0 : c.z_sat);
+        c.S_zsat_ss = M(c.z_sat * c.theta_ac);
+        bool m1 = c.S_lp_ss < c.q_pot_ss;
+        bool m2 = c.S_lp_ss >= c.q_pot_ss;
+        c.S_fp_ss += M(m1 ? -(c.q_ss - c.S_lp_ss) : 0.0);
+        c.S_lp_ss = M(m1 ? 0.0 : c.S_lp_ss);
+        c.S_lp_ss += M(m2 ? -c.q_ss : 0.0);
+    } else {  // calc_lateral_subsurface_runoff_ss :521-662, calc_lateral_subsurface_runoff :666-690
+        double q = M((c.z_sat <= 0) ? c.q_pot_ss : 0.0);
+        double tot = c.q_pot_ss + c.q_sub_pot_ss;
+        double fv = M((tot > 0) ? c.q_pot_ss / tot : 0.0);
+        double fl = M((tot > 0) ? c.q_sub_pot_ss / tot : 0.0);
+        bool fits = tot <= c.S_zsat_ss;
+        double q_sat = M(fits ? tot * fv : c.S_zsat_ss * fv);
+        q = (c.z_sat > 0) ? q_sat : q;
+        c.q_ss = q;
+        c.q_sub_ss = M(fits ? tot * fl : c.S_zsat_ss * fl);
+        c.q_sub_mat_ss = M(c.q_sub_ss * c.q_sub_mat_share);
+        c.q_sub_mp_ss = M(c.q_sub_ss * c.q_sub_mp_share);
+        bool m1 = c.S_lp_ss < q;
+        bool m2 = c.S_lp_ss >= q;
+        c.S_fp_ss += M(m1 ? -(q - c.S_lp_ss) : 0.0);
+        c.S_lp_ss = M(m1 ? 0.0 : c.S_lp_ss);
+        c.S_lp_ss += M(m2 ? -q : 0.0);
+        c.S_lp_ss += M((c.z_sat > 0) ? -c.q_sub_ss : 0.0);
+        c.z_sat += M(-((c.q_sub_ss + q) / c.theta_ac));
+        c.z_sat = M((c.z_sat < 0) ? 0.0 : c.z_sat);
+        c.S_zsat = M(c.z_sat * c.theta_ac);
+        c.q_sub_mat = M(c.q_sub_mat_rz + c.q_sub_mat_ss);
+        c.q_sub_mp = M(c.q_sub_mp_rz + c.q_sub_mp_ss);
+        c.q_sub = M(c.q_sub_rz + c.q_sub_ss);
+    }
+    // calc_cpr_rz capillary_rise.py:7-173
+    {
+        double z = M((c.z_root + zsub / 2) - c.z_root / 2);
+        double pa = pow(z / haz, mn);
+        double pb = have_pb_rz ? pb_rz : pow(-c.h_rz / -c.ha, mn);
+        double cpr = M(salvucci(pa, pb, c.n_salv) * dt * c.ks);
+        cpr = M((cpr < 0) ? 0.0 : cpr);
+        cpr = M(isnan(cpr) ? 0.0 : cpr);
+        cpr = M((c.S_lp_rz > 0) ? 0.0 : cpr);
+        cpr = M((c.h_rz > c.h_ss) ? 0.0 : cpr);
+        double avail = c.S_fp_ss + c.S_lp_ss;
+        cpr = M((cpr > avail) ? avail : cpr);
+        double room = c.S_ufc_rz - c.S_fp_rz;
+        cpr = M(((cpr > room) && (room > 0)) ? room : cpr);
+        c.cpr_rz = cpr;
+        bool gate = (c.z_wf < c.z_root) || (c.z_sat < zsub);
+        bool m1 = (cpr > 0) && (c.S_lp_ss <= 0) && gate;
+        bool m2 = (cpr > 0) && (c.S_lp_ss > 0) && (cpr <= c.S_lp_ss) && gate;
+        bool m3 = (cpr > 0) && (c.S_lp_ss > 0) && (cpr > c.S_lp_ss) && gate;
+        c.S_fp_rz += M(m1 ? cpr : 0.0);
+        c.S_fp_ss += M(m1 ? -cpr : 0.0);
+        c.S_fp_rz += M(m2 ? cpr : 0.0);
+        c.S_lp_ss += M(m2 ? -cpr : 0.0);
+        c.S_fp_rz += M(m3 ? cpr : 0.0);
+        c.S_fp_ss += M(m3 ? -(cpr - c.S_lp_ss) : 0.0);
+        c.S_lp_ss = M(m3 ? 0.0 : c.S_lp_ss);
+        bool ex = c.S_fp_rz > c.S_ufc_rz;
+        c.S_lp_rz += M(ex ? (c.S_fp_rz - c.S_ufc_rz) : 0.0);
+        c.S_fp_rz = M(ex ? c.S_ufc_rz : c.S_fp_rz);
+    }
+}
+
+// ---- storages (surface.py:8-28, root_zone.py:36-163, subsoil.py:6-130, soil.py:9-140, numerics.py:125-152)
+template <bool MASK1>
+RD void storages(Cell& c, const StepPlan& p) {
+    c.S_sur = M(c.S_int_top + c.S_int_ground + c.S_dep + c.S_snow + c.z0);
+    const double inv_lambda = 1 / c.lambda_bc;
+    const double mm = -c.m_bc;
+    c.S_rz = M(c.S_pwp_rz + c.S_fp_rz + c.S_lp_rz);
+    c.dS_rz = M(c.S_rz - c.S_rz_m1);
+    c.theta_rz = M((c.S_fp_rz + c.S_lp_rz) / c.z_root + c.theta_pwp);
+    if (p.irrigation_month) {  // root_zone.py:7-33 with vs.theta_irr == 0 in the SVAT / oneD setups
+        double d = 0.0 - c.theta_rz;
+        d = (d <= 0) ? 0.0 : d;
+        c.irr_demand = d * c.z_root;
+    } else {
+        c.irr_demand = 0.0;
+    }
+    double r = c.theta_rz / c.theta_sat;
+    c.k_rz = M(c.ks / (1 + pow(r, mm)));
+    c.h_rz = M(c.ha / pow(r, inv_lambda));
+    c.S_ss = M(c.S_pwp_ss + c.S_fp_ss + c.S_lp_ss);
+    c.dS_ss = M(c.S_ss - c.S_ss_m1);
+    c.theta_ss = M((c.S_fp_ss + c.S_lp_ss) / (c.z_soil - c.z_root) + c.theta_pwp);
+    r = c.theta_ss / c.theta_sat;
+    c.k_ss = M(c.ks / (1 + pow(r, mm)));
+    c.h_ss = M(c.ha / pow(r, inv_lambda));
+    c.S_fp_s = M(c.S_fp_rz + c.S_fp_ss);
+    c.S_lp_s = M(c.S_lp_rz + c.S_lp_ss);
+    c.S_s = M(c.S_pwp_s + c.S_fp_s + c.S_lp_s);
+    c.dS_s = M(c.S_s - c.S_s_m1);
+    c.theta = M((c.S_fp_s + c.S_lp_s) / c.z_soil + c.theta_pwp);
+    r = c.theta / c.theta_sat;
+    c.k = M(c.ks / (1 + pow(r, mm)));
+    c.h = M(c.ha / pow(r, inv_lambda));
+    c.S = c.S_sur + M(c.S_s);       // numerics.py:134
+    c.dS = c.S - M(c.S_m1);         // numerics.py:147
+}
+
+// numerics.py:217-346 calc_dS_num_error and :742-800 / :978-1016 sanity_check; returns the cell's verdict
+template <bool LAT>
+RD bool balance_check(Cell& c, const StepPlan& p) {
+    const double lhs = c.S - c.S_m1;
+    double rhs;
+    if (LAT) {
+        rhs = c.prec - c.q_sur - c.aet - c.q_ss - c.q_sub;
+        c.dS_num_error = fabs(lhs - rhs);
+    } else {
+        rhs = c.prec - c.q_sur - c.aet - c.q_ss;
+        c.dS_num_error = fabs(lhs - rhs);
+        c.dS_rz_num_error = fabs((c.S_rz - c.S_rz_m1) -
+                                 (c.inf_mat_rz + c.inf_mp_rz + c.inf_sc_rz + c.cpr_rz - c.transp - c.evap_soil - c.q_rz));
+        c.dS_ss_num_error = fabs((c.S_ss - c.S_ss_m1) - (c.inf_mp_ss + c.q_rz - c.q_ss - c.cpr_rz));
+    }
+    bool ok = true;
+    if (c.m != 0) {
+        bool close = fabs(lhs - rhs) <= (p.atol + p.rtol * fabs(rhs));  // npx.isclose
+        if (!(isfinite(lhs) && isfinite(rhs))) close = (lhs == rhs);
+        ok = close;
+    }
+    auto nz = [](double x) { return isnan(x) ? 0.0 : x; };
+    const double a = p.atol;
+    ok = ok && (nz(c.S_fp_rz) > -a) && (nz(c.S_lp_rz) > -a) && (nz(c.S_fp_ss) > -a) && (nz(c.S_lp_ss) > -a);
+    ok = ok && (nz(c.S_fp_rz) - a <= nz(c.S_ufc_rz)) && (nz(c.S_lp_rz) - a <= nz(c.S_ac_rz)) &&
+         (nz(c.S_fp_ss) - a <= nz(c.S_ufc_ss)) && (nz(c.S_lp_ss) - a <= nz(c.S_ac_ss));
+    return ok;
+}
+
+template <bool LAT, bool MASK1>
+RD bool cell_step(Cell& c, const StepPlan& p) {
+    c.pet_res = c.pet;  // adaptive_time_stepping.py:367-368
+    interception<MASK1>(c, p);
+    evapotranspiration<MASK1>(c, p);
+    snow<MASK1>(c, p);
+    event_bookkeeping_start<MASK1>(c, p);
+    green_ampt_and_matrix<MASK1>(c, p);
+    macropores<MASK1>(c, p);
+    shrinkage_cracks<MASK1>(c, p);
+    infiltration_tail<MASK1>(c, p);
+    subsurface<LAT, MASK1>(c, p);
+    storages<MASK1>(c, p);
+    bool ok = balance_check<LAT>(c, p);
+    if (p.clamp) {  // models/svat/svat.py:333-352
+        c.S_fp_rz = ((c.S_fp_rz > -1e-6) && (c.S_fp_rz < 0)) ? 0.0 : c.S_fp_rz;
+        c.S_lp_rz = ((c.S_lp_rz > -1e-6) && (c.S_lp_rz < 0)) ? 0.0 : c.S_lp_rz;
+        c.S_fp_ss = ((c.S_fp_ss > -1e-6) && (c.S_fp_ss < 0)) ? 0.0 : c.S_fp_ss;
+        c.S_lp_ss = ((c.S_lp_ss > -1e-6) && (c.S_lp_ss < 0)) ? 0.0 : c.S_lp_ss;
+    }
+    return ok;
+}
+
+#undef M
+}  // namespace roger

@@ -1,0 +1,146 @@
+"""ctypes binding of libroger_b200.so (include/roger_b200.h): the `cuda` engine of the SVAT / oneD path.
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is usable,
+construction raises.  PyTorch is not needed by this binding; when the caller passes torch tensors
+they are used only as host/device buffers.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .build import LIB
+
+_lib = None
+
+
+class RogerCudaError(RuntimeError):
+    pass
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        raise RogerCudaError(
+            f"{LIB} not found: the CUDA extension has not been built (run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "roger_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB)
+    dp = C.POINTER(C.c_double)
+    hp = C.c_void_p
+    lib.roger_last_error.restype = C.c_char_p
+    lib.roger_svat_create.argtypes = [C.POINTER(hp), C.c_int64, C.POINTER(abi.SvatSettings), C.c_int]
+    lib.roger_svat_destroy.argtypes = [hp]
+    lib.roger_svat_destroy.restype = None
+    lib.roger_svat_field_count.restype = C.c_int
+    lib.roger_svat_field_name.argtypes = [C.c_int]
+    lib.roger_svat_field_name.restype = C.c_char_p
+    lib.roger_svat_field_kind.argtypes = [C.c_int]
+    lib.roger_svat_upload.argtypes = [hp, C.c_int, dp]
+    lib.roger_svat_download.argtypes = [hp, C.c_int, dp]
+    lib.roger_svat_plane_ptr.argtypes = [hp, C.c_int]
+    lib.roger_svat_plane_ptr.restype = C.c_uint64
+    lib.roger_svat_set_scalars.argtypes = [hp, C.POINTER(abi.SvatScalars)]
+    lib.roger_svat_get_scalars.argtypes = [hp, C.POINTER(abi.SvatScalars)]
+    lib.roger_svat_set_forcing_day.argtypes = [hp, dp, dp, dp]
+    lib.roger_svat_set_forcing_day_device.argtypes = [hp, C.c_uint64, C.c_uint64, C.c_uint64]
+    lib.roger_svat_step.argtypes = [hp, C.c_int]
+    lib.roger_svat_run_day.argtypes = [hp, C.c_int, C.POINTER(C.c_int)]
+    lib.roger_svat_synchronize.argtypes = [hp]
+    lib.roger_svat_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
+    # the field table compiled into the library must be the one this package parsed from the header
+    n = lib.roger_svat_field_count()
+    names = [lib.roger_svat_field_name(i).decode() for i in range(n)]
+    if names != abi.FIELD_NAMES:
+        raise RogerCudaError("libroger_b200.so was built from a different include/roger_b200_fields.h; rebuild")
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise RogerCudaError(f"roger_b200 error {rc}: {lib.roger_last_error().decode()}")
+
+
+class CudaSvatEngine:
+    def __init__(self, n_cells, settings, device=0):
+        self.lib = load_library()
+        self.n = int(n_cells)
+        self.settings = settings
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.roger_svat_create(C.byref(self.h), self.n, C.byref(settings), int(device)))
+        self._keep = None
+        self.kernel_ms = 0.0
+        self.launches = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.roger_svat_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _dp(a):
+        return a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def upload(self, name, arr):
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64).reshape(-1))
+        if a.size != self.n:
+            raise ValueError(f"upload({name}): expected {self.n} values, got {a.size}")
+        _check(self.lib, self.lib.roger_svat_upload(self.h, abi.FIELD_ID[name], self._dp(a)))
+
+    def download(self, name):
+        out = np.empty(self.n, dtype=np.float64)
+        _check(self.lib, self.lib.roger_svat_download(self.h, abi.FIELD_ID[name], self._dp(out)))
+        return out
+
+    def plane_ptr(self, name):
+        return int(self.lib.roger_svat_plane_ptr(self.h, abi.FIELD_ID[name]))
+
+    def set_scalars(self, s):
+        _check(self.lib, self.lib.roger_svat_set_scalars(self.h, C.byref(s)))
+
+    def get_scalars(self):
+        s = abi.SvatScalars()
+        _check(self.lib, self.lib.roger_svat_get_scalars(self.h, C.byref(s)))
+        return s
+
+    def set_forcing_day(self, prec, ta, pet):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (prec, ta, pet)]
+        want = abi.SLOTS_PER_DAY * (1 if self.settings.forcing_uniform else self.n)
+        for a in arrs:
+            if a.size != want:
+                raise ValueError(f"forcing day block: expected {want} values, got {a.size}")
+        self._keep = arrs  # the copy is asynchronous for per-cell forcing
+        _check(self.lib, self.lib.roger_svat_set_forcing_day(self.h, *[self._dp(a) for a in arrs]))
+
+    def set_forcing_day_device(self, prec_ptr, ta_ptr, pet_ptr):
+        _check(self.lib, self.lib.roger_svat_set_forcing_day_device(self.h, int(prec_ptr), int(ta_ptr), int(pet_ptr)))
+
+    def _timing(self):
+        ms = C.c_double()
+        n = C.c_int64()
+        self.lib.roger_svat_last_timing(self.h, C.byref(ms), C.byref(n))
+        self.kernel_ms += ms.value
+        self.launches += n.value
+
+    def step(self, write_fluxes=False):
+        _check(self.lib, self.lib.roger_svat_step(self.h, int(bool(write_fluxes))))
+        self._timing()
+
+    def run_day(self, write_fluxes=False):
+        n = C.c_int()
+        _check(self.lib, self.lib.roger_svat_run_day(self.h, int(bool(write_fluxes)), C.byref(n)))
+        self._timing()
+        return n.value
+
+    def synchronize(self):
+        _check(self.lib, self.lib.roger_svat_synchronize(self.h))
