@@ -92,6 +92,14 @@ int roger_svat_set_forcing_day(roger_svat *h, const double *prec_day, const doub
 /* same, from buffers already resident on the device (raw addresses) */
 int roger_svat_set_forcing_day_device(roger_svat *h, uint64_t prec_day, uint64_t ta_day, uint64_t pet_day);
 
+/* ---- multi-GPU: the grid-wide any()/all() of adaptive_time_stepping.py:38-81/:191-201 and the global_and of
+ *      numerics.sanity_check are evaluated on per-rank flag words; with the grid partitioned over several
+ *      processes the caller supplies a collective that ORs `n` flag words in place across all ranks
+ *      (replaces roger/distributed.py global_and/global_or; NCCL or gloo from torch.distributed).
+ *      Every rank calls it the same number of times per step. */
+typedef void (*roger_flag_reduce_fn)(uint32_t *flags, int n, void *user);
+int roger_svat_set_flag_reducer(roger_svat *h, roger_flag_reduce_fn fn, void *user);
+
 /* ---- the hot path: ONE adaptive time step = adaptive_time_stepping + interception + ET + snow +
  *      infiltration + percolation (+ lateral) + capillary rise + storages + numerical error +
  *      after_timestep roll (roger/roger.py:389-485).  Updates scalars (time, itt, dt, ...).

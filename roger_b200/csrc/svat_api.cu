@@ -251,6 +251,12 @@ struct roger_svat {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_kernel_ms = 0;
     int64_t last_launches = 0;
+    roger_flag_reduce_fn reduce_fn = nullptr;
+    void* reduce_user = nullptr;
+    unsigned reduce(unsigned v) const {
+        if (reduce_fn) { uint32_t w = v; reduce_fn(&w, 1, reduce_user); return w; }
+        return v;
+    }
     Planes planes() const { return Planes{d_ps, d_fl, C}; }
 };
 
@@ -383,6 +389,7 @@ static int after_forcing(roger_svat* h) {
         CU(cudaStreamSynchronize(h->stream));
         h->day_flags = h->h_flags[1];
     }
+    h->day_flags = h->reduce(h->day_flags);
     h->have_forcing = true;
     return 0;
 }
@@ -438,7 +445,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
         launches++;
         CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        h->snow_flags = h->h_flags[0];
+        h->snow_flags = h->reduce(h->h_flags[0]);
         h->snow_flags_valid = true;
     }
     const unsigned sf = h->snow_flags, df = h->day_flags;
@@ -498,7 +505,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
         launches++;
         CU(cudaMemcpyAsync(h->h_flags + 2, h->d_flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        ev = h->h_flags[2];
+        ev = h->reduce(h->h_flags[2]);
     }
     const bool cond_event1 = (ev & EV_RAIN_WARM) || (ev & EV_SNOW_WARM);
     // swe[taum1] == swe[tau] at this point (after_timestep copied it): any(swe_m1 > 0) & all(swe <= 0)
@@ -562,7 +569,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
     CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    h->snow_flags = h->h_flags[0];
+    h->snow_flags = h->reduce(h->h_flags[0]);
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_kernel_ms += ms;
@@ -593,6 +600,13 @@ int roger_svat_run_day(roger_svat* h, int write_fluxes, int* n_steps) {
         n++;
     } while (h->sc.time % 86400 != 0 && n < 144);
     if (n_steps) *n_steps = n;
+    return 0;
+}
+
+int roger_svat_set_flag_reducer(roger_svat* h, roger_flag_reduce_fn fn, void* user) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_set_flag_reducer: null handle");
+    h->reduce_fn = fn;
+    h->reduce_user = user;
     return 0;
 }
 

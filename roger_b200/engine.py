@@ -13,6 +13,7 @@ from . import abi
 from .build import LIB
 
 _lib = None
+FLAG_REDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_uint32), C.c_int, C.c_void_p)
 
 
 class RogerCudaError(RuntimeError):
@@ -51,6 +52,7 @@ def load_library():
     lib.roger_svat_run_day.argtypes = [hp, C.c_int, C.POINTER(C.c_int)]
     lib.roger_svat_synchronize.argtypes = [hp]
     lib.roger_svat_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
+    lib.roger_svat_set_flag_reducer.argtypes = [hp, FLAG_REDUCE_FN, C.c_void_p]
     # the field table compiled into the library must be the one this package parsed from the header
     n = lib.roger_svat_field_count()
     names = [lib.roger_svat_field_name(i).decode() for i in range(n)]
@@ -66,12 +68,22 @@ def _check(lib, rc):
 
 
 class CudaSvatEngine:
-    def __init__(self, n_cells, settings, device=0):
+    def __init__(self, n_cells, settings, device=0, flag_reducer=None):
         self.lib = load_library()
         self.n = int(n_cells)
         self.settings = settings
         self.h = C.c_void_p()
         _check(self.lib, self.lib.roger_svat_create(C.byref(self.h), self.n, C.byref(settings), int(device)))
+        self._reducer = None
+        if flag_reducer is not None:
+            # flag_reducer(list_of_uint32) -> list_of_uint32 OR-ed over all ranks (roger_b200.parallel)
+            def _cb(ptr, n, _user):
+                vals = flag_reducer([int(ptr[i]) for i in range(n)])
+                for i in range(n):
+                    ptr[i] = vals[i]
+
+            self._reducer = FLAG_REDUCE_FN(_cb)
+            _check(self.lib, self.lib.roger_svat_set_flag_reducer(self.h, self._reducer, None))
         self._keep = None
         self.kernel_ms = 0.0
         self.launches = 0
