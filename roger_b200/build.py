@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libroger_b200.so")
+LIB = os.environ.get("ROGER_B200_LIB") or os.path.join(LIBDIR, "libroger_b200.so")
 SOURCES = ["svat_api.cu", "sas_api.cu"]
 HEADERS = ["svat_device.cuh", os.path.join("..", "..", "include", "roger_b200.h"),
            os.path.join("..", "..", "include", "roger_b200_fields.h"), os.path.join("..", "..", "include", "roger_b200_sas.h")]
@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    extra = os.environ.get("ROGER_NVCC_EXTRA", "").split()
+    flags = [f for f in NVCC_FLAGS if not (f == "-fmad=false" and "-fmad=true" in extra)]
+    cmd = [_nvcc()] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
     subprocess.check_call(cmd)
     return LIB

@@ -159,8 +159,11 @@ __global__ void k_aggregate_a(Planes pl, double* __restrict__ prec_m1, const dou
 }
 
 // The fused step.  One thread = one soil column; all parameters and state in registers.
+#ifndef ROGER_MIN_BLOCKS
+#define ROGER_MIN_BLOCKS 1
+#endif
 template <bool LAT, bool FLUX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, ROGER_MIN_BLOCKS)
 k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* __restrict__ ta_day,
             const double* __restrict__ pet_day, StepPlan p, unsigned* flags) {
     const int64_t C = pl.C;

@@ -44,6 +44,53 @@ struct StepPlan {
 
 #define RD __device__ __forceinline__
 
+// ---- arithmetic helpers ---------------------------------------------------------------------
+// ROGER_FAST_MATH (default): transcendental powers are evaluated as exp(y*log(x)) with the logarithm shared
+// between powers of the same base, the cube root / cube of the macropore front use cbrt() / y*y*y, and
+// divisions with a zero operand skip the IEEE slow path.  Results stay within a few ulp of libm's pow
+// (far inside the 1e-10 parity tolerance); build with -DROGER_FAST_MATH=0 for pow() everywhere.
+#ifndef ROGER_FAST_MATH
+#define ROGER_FAST_MATH 1
+#endif
+
+// IEEE-identical a / b.  nvcc's inline double division branches to a ~60-instruction slow path whenever an
+// operand's exponent field is 0 (i.e. also for an exact zero); on dry steps most numerators of the
+// reference's formulas are exactly 0, so those cases are answered directly.
+RD double dv(double a, double b) {
+    if (a == 0.0 || b == 0.0) {
+        if (a != a || b != b) return a + b;
+        const unsigned long long sign = (__double_as_longlong(a) ^ __double_as_longlong(b)) & 0x8000000000000000ULL;
+        if (a == 0.0) {
+            if (b == 0.0) return __longlong_as_double(0x7ff8000000000000ULL);
+            return __longlong_as_double(sign);
+        }
+        return __longlong_as_double(sign | 0x7ff0000000000000ULL);
+    }
+    return a / b;
+}
+
+RD double powr(double x, double y) {  // x ** y (numpy power on float64)
+#if ROGER_FAST_MATH
+    return exp(y * log(x));
+#else
+    return pow(x, y);
+#endif
+}
+RD double cube_root(double x) {  // x ** (1 / 3)
+#if ROGER_FAST_MATH
+    return cbrt(x);
+#else
+    return pow(x, 1.0 / 3);
+#endif
+}
+RD double cube(double x) {  // x ** 3
+#if ROGER_FAST_MATH
+    return x * x * x;
+#else
+    return pow(x, 3.0);
+#endif
+}
+
 struct Cell {
 #define ROGER_DECL(kind, name) double name;
     ROGER_SVAT_FIELDS(ROGER_DECL)
@@ -396,7 +443,7 @@ RD void event_bookkeeping_start(Cell& c, const StepPlan& p) {
     // cond2 / cond3 are `scalar & grid.any()` gates whose kernels re-apply the per-cell mask
     // (infiltration.py:1987, :2005): a cell acts iff the scalar part holds and its own mask is true.
     if (p.cond2s) {  // set_event_vars_start_rainfall_pause :1979-1995 (+ calc_z_wf_fc :1535-1560)
-        double z = M((c.theta_d_fp > 0) ? c.inf_mat_event_csum / c.theta_d_fp : c.z_wf);
+        double z = M((c.theta_d_fp > 0) ? dv(c.inf_mat_event_csum, c.theta_d_fp) : c.z_wf);
         z = M((z > c.z_soil) ? c.z_soil : z);
         bool mk_ = (c.prec == 0) && (c.prec_m1 != 0);
         c.z_wf_fc = M(mk_ ? z : c.z_wf_fc);
@@ -478,8 +525,8 @@ RD void green_ampt_and_matrix(Cell& c, const StepPlan& p) {
     // wetting fronts
     const bool wf1 = (c.no_wf == 1), wf2 = (c.no_wf == 2);
     double dz = 0.0;
-    dz = M(wf1 ? (inf / c.theta_d_t0) : dz);
-    dz = M(wf2 ? inf / c.theta_d : dz);
+    dz = M(wf1 ? dv(inf, c.theta_d_t0) : dz);
+    dz = M(wf2 ? dv(inf, c.theta_d) : dz);
     dz = M(isfinite(dz) ? dz : 0.0);
     c.z_wf_t0 += dz;
     c.z_wf_t1 += dz;
@@ -489,11 +536,11 @@ RD void green_ampt_and_matrix(Cell& c, const StepPlan& p) {
     c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
     const bool pause = (c.z_wf_fc > 0) && (c.rain_ground <= 0);
     {
-        double d0 = M((pause && wf1) ? pot / c.theta_d_t0 : 0.0);
+        double d0 = M((pause && wf1) ? dv(pot, c.theta_d_t0) : 0.0);
         c.z_wf_t0 += M(isfinite(d0) ? d0 : 0.0);
         c.z_wf_t0 = M(((c.z_wf_t0 > c.z_wf_fc) && (c.z_wf_fc > 0)) ? c.z_wf_fc : c.z_wf_t0);
         c.z_wf_t0 = M((c.z_wf_t0 > c.z_soil) ? c.z_soil : c.z_wf_t0);
-        double d1 = M((pause && wf2) ? pot / c.theta_d : 0.0);
+        double d1 = M((pause && wf2) ? dv(pot, c.theta_d) : 0.0);
         c.z_wf_t1 += M(isfinite(d1) ? d1 : 0.0);
         c.z_wf_t1 = M(((c.z_wf_t1 > c.z_wf_fc) && (c.z_wf_fc > 0)) ? c.z_wf_fc : c.z_wf_t1);
         c.z_wf_t1 = M((c.z_wf_t1 > c.z_soil) ? c.z_soil : c.z_wf_t1);
@@ -541,7 +588,7 @@ RD void macropores(Cell& c, const StepPlan& p) {
     dz = M((dz <= 0) ? 0.0 : dz);
     nonsat = c.lmpv - M(c.z_wf);  // :503
     nonsat = M((nonsat < 0) ? 0.0 : nonsat);
-    nonsat = M((substeps == 1) ? nonsat + dz / 1.39 : nonsat);
+    nonsat = M((substeps == 1) ? nonsat + dv(dz, 1.39) : nonsat);
     c.lmpv_non_sat = nonsat;
 
     const double a = M(c.theta_d * p.r_mp2);
@@ -565,9 +612,9 @@ RD void macropores(Cell& c, const StepPlan& p) {
         double b2 = M(rtd2 * (12 * cc - a + b1));
         b2 = M(isnan(b2) ? 0.0 : b2);
         b2 = M((b2 <= 0) ? 0.0 : b2);
-        const double cb = pow(b2, 1.0 / 3);
-        double y1 = M((cb / c.theta_d) * 0.5);
-        double y2 = M((a / cb) * 0.5);
+        const double cb = cube_root(b2);
+        double y1 = M(dv(cb, c.theta_d) * 0.5);
+        double y2 = M(dv(a, cb) * 0.5);
         y = M(y1 + y2 + ym1);
         y = M((y < r_mp) ? r_mp : y);
         y = M((y < ym1) ? ym1 : y);
@@ -576,9 +623,9 @@ RD void macropores(Cell& c, const StepPlan& p) {
         di = M((nonsat == 0) ? 0.0 : di);
         inf_mp += M(di);
         csum += M(di);
-        y = r_mp + M(sqrt((csum / dmtd) / pi));  // :728-730
+        y = r_mp + M(sqrt(dv(dv(csum, dmtd), pi)));  // :728-730
         y = M((y < r_mp) ? r_mp : y);
-        t = M(tfac * (pow(y, 3.0) / 3.0 - (y * y) * r_mp / 2.0 + p.r_mp3_6));
+        t = M(tfac * (cube(y) / 3.0 - (y * y) * r_mp / 2.0 + p.r_mp3_6));
         inf_mp = M((inf_mp < 0) ? 0.0 : inf_mp);
         ym1 = M(y);
         if (isnan(inf_mp)) break;
@@ -589,7 +636,7 @@ RD void macropores(Cell& c, const StepPlan& p) {
     inf_mp = M(inf_mp);
     inf_mp = M(isnan(inf_mp) ? 0.0 : inf_mp);
 
-    double share = M((nonsat > 0) ? 1.0 - (c.lmpv - c.z_root) / nonsat : 0.0);
+    double share = M((nonsat > 0) ? 1.0 - dv(c.lmpv - c.z_root, nonsat) : 0.0);
     share = M((c.lmpv <= c.z_root) ? 1.0 : share);
     share = M((z_wf >= c.z_root) ? 0.0 : share);
     share = M((share < 0) ? 0.0 : share);
@@ -651,13 +698,13 @@ RD void shrinkage_cracks(Cell& c, const StepPlan& p) {
     dz = M((dz <= 0) ? 0.0 : dz);
     nonsat = c.z_sc - M(c.z_wf);
     nonsat = M((nonsat < 0) ? 0.0 : nonsat);
-    nonsat = M((substeps == 1) ? nonsat + dz / 1.39 : nonsat);
+    nonsat = M((substeps == 1) ? nonsat + dv(dz, 1.39) : nonsat);
     c.z_sc_non_sat = nonsat;
 
     double ym1 = M(c.y_sc_m1), y = ym1;
     double csum = M(c.inf_sc_event_csum);
     double t = 0.0;
-    const double z0_di = M(c.z0 / substeps);
+    const double z0_di = M(dv(c.z0, (double)substeps));
     const double dts = M(dt / substeps);
     const double ksw = c.ks * c.wfs;
     const double geo = nonsat * c.theta_d * l_sc;
@@ -671,8 +718,8 @@ RD void shrinkage_cracks(Cell& c, const StepPlan& p) {
         di = M((nonsat <= 0) ? 0.0 : di);
         di += M(di);
         csum += M(di);
-        y = M(csum / l_sc / 2);
-        t = M(((ym1 * ym1) * c.theta_d) / (ksw * 2));
+        y = M(dv(csum, l_sc) / 2);
+        t = M(dv((ym1 * ym1) * c.theta_d, ksw * 2));
         ym1 = M(y);
         if (isnan(csum)) break;  // y = csum / l_sc / 2 stays NaN in every later pass
         if (ym1 == ym1_in && t == t_in && csum == csum_in) break;
@@ -739,14 +786,14 @@ RD void subsurface(Cell& c, const StepPlan& p) {
     {
         double lmpv_ss = c.lmpv - M(c.z_root);  // :705
         lmpv_ss = M((c.lmpv < c.z_root) ? 0.0 : lmpv_ss);
-        const double lp_ss_ac = c.S_lp_ss / c.theta_ac;
+        const double lp_ss_ac = dv(c.S_lp_ss, c.theta_ac);
         double top = M((c.S_lp_ss < c.theta_ac) ? lp_ss_ac : c.S_lp_rz + lp_ss_ac);
         double nomp = zsub - lmpv_ss - M(c.z_sat);  // :733
         nomp = (nomp < 0) ? 0.0 : nomp;
         double v = lp_ss_ac;
         if (top > nomp) {
             if ((c.S_fp_ss >= c.S_ufc_ss) && (((c.S_lp_ss + 1e-6) / c.theta_ac) < zsub)) v = lp_ss_ac;
-            else if ((c.S_fp_rz >= c.S_ufc_rz) && (c.S_lp_ss + 1e-6 >= c.S_ac_ss)) v = c.S_lp_rz / c.theta_ac + lp_ss_ac;
+            else if ((c.S_fp_rz >= c.S_ufc_rz) && (c.S_lp_ss + 1e-6 >= c.S_ac_ss)) v = dv(c.S_lp_rz, c.theta_ac) + lp_ss_ac;
         }
         c.z_sat = M(v);
     }
@@ -780,8 +827,8 @@ RD void subsurface(Cell& c, const StepPlan& p) {
         perc = M(m2 ? c.k_rz * dt : perc);
         if (m3) {
             double z = zsub - c.z_sat;
-            double pa = pow(z / haz, mn);
-            pb_rz = pow(-c.h_rz / -c.ha, mn);
+            double pa = powr(z / haz, mn);
+            pb_rz = powr(-c.h_rz / -c.ha, mn);
             have_pb_rz = true;
             perc = salvucci(pa, pb_rz, c.n_salv) * dt * c.ks * (-1);
         }
@@ -843,9 +890,9 @@ RD void subsurface(Cell& c, const StepPlan& p) {
         mp = M((mp < 0) ? 0.0 : mp);
         mp = M((c.z_sat <= 0) ? 0.0 : mp);
         double pot = M(mp + mat);
-        double sh_mat = M(mat / pot);
+        double sh_mat = M(dv(mat, pot));
         sh_mat = M((pot == 0) ? 0.0 : sh_mat);
-        double sh_mp = M(mp / pot);
+        double sh_mp = M(dv(mp, pot));
         sh_mp = M((pot == 0) ? 0.0 : sh_mp);
         c.q_sub_mat_share = sh_mat;
         c.q_sub_mp_share = sh_mp;
@@ -864,10 +911,10 @@ RD void subsurface(Cell& c, const StepPlan& p) {
         c.q_sub_mat_rz = M(c.q_sub_rz * sh_mat);
         c.q_sub_mp_rz = M(c.q_sub_rz * sh_mp);
         c.q_sub_mp_pot_rz = M(c.q_sub_mp_pot * rz_share);
-        c.z_sat += M(-c.q_sub_rz / c.theta_ac);
+        c.z_sat += M(dv(-c.q_sub_rz, c.theta_ac));
         c.S_lp_rz += M(-c.q_sub_rz);
         // calc_potential_lateral_subsurface_runoff_ss :461-517
-        double ss_share = M(zsub / c.z_sat);
+        double ss_share = M(dv(zsub, c.z_sat));
         bool one = (c.z_sat <= zsub) || (c.S_lp_rz <= 0);
         bool zero = c.z_sat <= 0;
         bool nan_ = isnan(ss_share);
@@ -882,8 +929,8 @@ RD void subsurface(Cell& c, const StepPlan& p) {
     {
         const double zgw = c.z_gw * 1000;
         double z = (zgw - c.z_soil) + M(zsub / 2);
-        double pa = pow(z / haz, mn);
-        double pb = pow(-c.h_ss / -c.ha, mn);
+        double pa = powr(z / haz, mn);
+        double pb = powr(-c.h_ss / -c.ha, mn);
         const double kfdt = c.kf * dt;
         double sal = salvucci(pa, pb, c.n_salv);
         double perc;
@@ -905,7 +952,7 @@ RD void subsurface(Cell& c, const StepPlan& p) {
     }
     if (!LAT) {  // calc_percolation_ss :1102-1154
         c.q_ss = M(c.q_pot_ss);
-        c.z_sat += M((c.z_sat > 0) ? -c.q_ss / c.theta_ac : 0.0);
+        c.z_sat += M((c.z_sat > 0) ? dv(-c.q_ss, c.theta_ac) : 0.0);
         c.z_sat = M((c.z_sat < 0) ? 0.0 : c.z_sat);
         c.S_zsat_ss = M(c.z_sat * c.theta_ac);
         bool m1 = c.S_lp_ss < c.q_pot_ss;
@@ -916,8 +963,8 @@ RD void subsurface(Cell& c, const StepPlan& p) {
     } else {  // calc_lateral_subsurface_runoff_ss :521-662, calc_lateral_subsurface_runoff :666-690
         double q = M((c.z_sat <= 0) ? c.q_pot_ss : 0.0);
         double tot = c.q_pot_ss + c.q_sub_pot_ss;
-        double fv = M((tot > 0) ? c.q_pot_ss / tot : 0.0);
-        double fl = M((tot > 0) ? c.q_sub_pot_ss / tot : 0.0);
+        double fv = M((tot > 0) ? dv(c.q_pot_ss, tot) : 0.0);
+        double fl = M((tot > 0) ? dv(c.q_sub_pot_ss, tot) : 0.0);
         bool fits = tot <= c.S_zsat_ss;
         double q_sat = M(fits ? tot * fv : c.S_zsat_ss * fv);
         q = (c.z_sat > 0) ? q_sat : q;
@@ -931,7 +978,7 @@ RD void subsurface(Cell& c, const StepPlan& p) {
         c.S_lp_ss = M(m1 ? 0.0 : c.S_lp_ss);
         c.S_lp_ss += M(m2 ? -q : 0.0);
         c.S_lp_ss += M((c.z_sat > 0) ? -c.q_sub_ss : 0.0);
-        c.z_sat += M(-((c.q_sub_ss + q) / c.theta_ac));
+        c.z_sat += M(-dv(c.q_sub_ss + q, c.theta_ac));
         c.z_sat = M((c.z_sat < 0) ? 0.0 : c.z_sat);
         c.S_zsat = M(c.z_sat * c.theta_ac);
         c.q_sub_mat = M(c.q_sub_mat_rz + c.q_sub_mat_ss);
@@ -941,8 +988,8 @@ RD void subsurface(Cell& c, const StepPlan& p) {
     // calc_cpr_rz capillary_rise.py:7-173
     {
         double z = M((c.z_root + zsub / 2) - c.z_root / 2);
-        double pa = pow(z / haz, mn);
-        double pb = have_pb_rz ? pb_rz : pow(-c.h_rz / -c.ha, mn);
+        double pa = powr(z / haz, mn);
+        double pb = have_pb_rz ? pb_rz : powr(-c.h_rz / -c.ha, mn);
         double cpr = M(salvucci(pa, pb, c.n_salv) * dt * c.ks);
         cpr = M((cpr < 0) ? 0.0 : cpr);
         cpr = M(isnan(cpr) ? 0.0 : cpr);
@@ -970,6 +1017,21 @@ RD void subsurface(Cell& c, const StepPlan& p) {
     }
 }
 
+// Brooks-Corey conductivity and matric potential of one layer (root_zone.py:36-60, subsoil.py:22-48,
+// soil.py:9-42): k = ks / (1 + r**-m), h = ha / r**(1/lambda) with r = theta / theta_sat.
+template <bool MASK1>
+RD void brooks_corey(const Cell& c, double theta, double mm, double inv_lambda, double& k, double& h) {
+    const double r = theta / c.theta_sat;
+#if ROGER_FAST_MATH
+    const double lr = log(r);  // one logarithm for both powers
+    k = M(c.ks / (1 + exp(mm * lr)));
+    h = M(c.ha / exp(inv_lambda * lr));
+#else
+    k = M(c.ks / (1 + pow(r, mm)));
+    h = M(c.ha / pow(r, inv_lambda));
+#endif
+}
+
 // ---- storages (surface.py:8-28, root_zone.py:36-163, subsoil.py:6-130, soil.py:9-140, numerics.py:125-152)
 template <bool MASK1>
 RD void storages(Cell& c, const StepPlan& p) {
@@ -986,23 +1048,17 @@ RD void storages(Cell& c, const StepPlan& p) {
     } else {
         c.irr_demand = 0.0;
     }
-    double r = c.theta_rz / c.theta_sat;
-    c.k_rz = M(c.ks / (1 + pow(r, mm)));
-    c.h_rz = M(c.ha / pow(r, inv_lambda));
+    brooks_corey<MASK1>(c, c.theta_rz, mm, inv_lambda, c.k_rz, c.h_rz);
     c.S_ss = M(c.S_pwp_ss + c.S_fp_ss + c.S_lp_ss);
     c.dS_ss = M(c.S_ss - c.S_ss_m1);
     c.theta_ss = M((c.S_fp_ss + c.S_lp_ss) / (c.z_soil - c.z_root) + c.theta_pwp);
-    r = c.theta_ss / c.theta_sat;
-    c.k_ss = M(c.ks / (1 + pow(r, mm)));
-    c.h_ss = M(c.ha / pow(r, inv_lambda));
+    brooks_corey<MASK1>(c, c.theta_ss, mm, inv_lambda, c.k_ss, c.h_ss);
     c.S_fp_s = M(c.S_fp_rz + c.S_fp_ss);
     c.S_lp_s = M(c.S_lp_rz + c.S_lp_ss);
     c.S_s = M(c.S_pwp_s + c.S_fp_s + c.S_lp_s);
     c.dS_s = M(c.S_s - c.S_s_m1);
     c.theta = M((c.S_fp_s + c.S_lp_s) / c.z_soil + c.theta_pwp);
-    r = c.theta / c.theta_sat;
-    c.k = M(c.ks / (1 + pow(r, mm)));
-    c.h = M(c.ha / pow(r, inv_lambda));
+    brooks_corey<MASK1>(c, c.theta, mm, inv_lambda, c.k, c.h);
     c.S = c.S_sur + M(c.S_s);       // numerics.py:134
     c.dS = c.S - M(c.S_m1);         // numerics.py:147
 }
