@@ -160,7 +160,7 @@ __global__ void k_aggregate_a(Planes pl, double* __restrict__ prec_m1, const dou
 
 // The fused step.  One thread = one soil column; all parameters and state in registers.
 #ifndef ROGER_MIN_BLOCKS
-#define ROGER_MIN_BLOCKS 1
+#define ROGER_MIN_BLOCKS 4
 #endif
 template <bool LAT, bool FLUX>
 __global__ void __launch_bounds__(128, ROGER_MIN_BLOCKS)
@@ -171,14 +171,17 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
     unsigned bits = 0;
     if (i < C) {
         Cell c;
-#define ROGER_LOAD_P(name) c.name = (LAT || !lat_only(RF_##name)) ? __ldg(pl.ps + (size_t)RF_##name * C + i) : 0.0;
-#define ROGER_LOAD_S(name) c.name = pl.ps[(size_t)RF_##name * C + i];
-#define ROGER_LOAD_F(name) c.name = 0.0;
-#define ROGER_LOAD(kind, name) ROGER_LOAD_##kind(name)
-        ROGER_SVAT_FIELDS(ROGER_LOAD)
-#undef ROGER_LOAD
+#ifdef ROGER_DEBUG_NAN_INIT  // use-before-load detector for the lazy loads (tests only)
+        {
+            double* raw = reinterpret_cast<double*>(&c);
+            for (unsigned k = 0; k < sizeof(Cell) / sizeof(double); k++) raw[k] = __longlong_as_double(0x7ff8000000000000ULL);
+        }
+#endif
+        const Io io{pl.ps, pl.fl, C, i};
+        c.maskCatch = io.ldp(RF_maskCatch);
         c.m = c.maskCatch;
         // ---- adaptive_time_stepping.py:130-189 / :256-360: forcing for this cell ----
+        c.prec = io.lds(RF_prec); c.ta = io.lds(RF_ta); c.pet = io.lds(RF_pet);
         if (p.uniform) {
             c.prec_m1 = c.prec;
             if (p.class_a) { c.prec = p.u_prec; c.ta = p.u_ta_a; }
@@ -191,19 +194,10 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
             else if (p.class_b == 2) { c.pet = RowAgg::win_sum(er, p.itt_day); c.ta = RowAgg::win_nanmean(tr, p.itt_day); }
             else if (p.class_b == 3) { c.pet = RowAgg::day_sum(er); c.ta = RowAgg::day_nanmean(tr); }
         }
-        c.z_wf_m1 = c.z_wf; c.z_wf_t0_m1 = c.z_wf_t0; c.z_wf_t1_m1 = c.z_wf_t1;
-        c.y_mp_m1 = c.y_mp; c.y_sc_m1 = c.y_sc;
-        c.S_m1 = c.S; c.S_rz_m1 = c.S_rz; c.S_ss_m1 = c.S_ss; c.S_s_m1 = c.S_s;
+        io.sts(RF_prec, c.prec); io.sts(RF_ta, c.ta); io.sts(RF_pet, c.pet);
 
-        const bool ok = (c.m == 1.0) ? cell_step<LAT, true>(c, p) : cell_step<LAT, false>(c, p);
+        const bool ok = (c.m == 1.0) ? cell_step<LAT, FLUX, true>(c, p, io) : cell_step<LAT, FLUX, false>(c, p, io);
 
-#define ROGER_STORE_P(name)
-#define ROGER_STORE_S(name) pl.ps[(size_t)RF_##name * C + i] = c.name;
-#define ROGER_STORE_F(name) \
-    if (FLUX && (LAT || !lat_only(RF_##name))) pl.fl[(size_t)(RF_##name - kNumPS) * C + i] = c.name;
-#define ROGER_STORE(kind, name) ROGER_STORE_##kind(name)
-        ROGER_SVAT_FIELDS(ROGER_STORE)
-#undef ROGER_STORE
         bits |= (c.swe > 0) ? FLAG_SWE_GT0 : 0;
         bits |= !(c.swe <= 0) ? FLAG_SWE_NOT_LE0 : 0;
         bits |= (c.swe_top > 0) ? FLAG_SWETOP_GT0 : 0;

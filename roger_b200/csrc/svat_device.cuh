@@ -104,9 +104,33 @@ template <bool MASK1>
 RD double mk(const Cell& c, double x) { return MASK1 ? x : x * c.m; }
 #define M(x) mk<MASK1>(c, (x))
 
+// Plane access of one thread.  Loads are issued where a field is first needed and stores as soon as a
+// field is final, so that only the values a process actually works on are alive in registers
+// (load everything up front costs 250+ registers and two resident blocks per SM).
+constexpr int kFirstFlux = RF_pet_res;  // the enum is ordered P.., S.., F..
+struct Io {
+    double* __restrict__ ps;  // parameter + state planes
+    double* __restrict__ fl;  // flux planes (FLUX kernels only)
+    int64_t C, i;
+    RD double ldp(int id) const { return __ldg(ps + (size_t)id * C + i); }
+    RD double lds(int id) const { return ps[(size_t)id * C + i]; }
+    RD void sts(int id, double v) const { ps[(size_t)id * C + i] = v; }
+    template <bool FLUX>
+    RD void stf(int id, double v) const {
+        if (FLUX) fl[(size_t)(id - kFirstFlux) * C + i] = v;
+    }
+};
+#define LDP(name) c.name = io.ldp(RF_##name)
+#define LDS(name) c.name = io.lds(RF_##name)
+#define STS(name) io.sts(RF_##name, c.name)
+#define STF(name) io.template stf<FLUX>(RF_##name, c.name)
+
 // ---- interception.py:6-343 ------------------------------------------------------------------
-template <bool MASK1>
-RD void interception(Cell& c, const StepPlan& p) {
+template <bool FLUX, bool MASK1>
+RD void interception(Cell& c, const StepPlan& p, const Io& io) {
+    LDP(throughfall_coeff_top); LDP(throughfall_coeff_ground); LDP(S_int_top_tot); LDP(S_int_ground_tot); LDP(lu_id);
+    LDS(swe_top); LDS(S_int_top); LDS(S_int_ground); LDS(S_snow); LDS(z0); LDS(prec_event_csum); LDS(swe_top_tot);
+    LDS(swe_ground);
     const double ta_fm = p.ta_fm;
     const bool warm = c.ta > ta_fm;
     const double tf_top = 1. - c.throughfall_coeff_top;
@@ -185,14 +209,20 @@ RD void interception(Cell& c, const StepPlan& p) {
     c.int_top = M(c.int_rain_top + c.int_snow_top);
     c.int_ground = M(c.int_rain_ground + c.int_snow_ground);
     c.int_prec = M(c.int_rain_top + c.int_rain_ground + c.int_snow_top + c.int_snow_ground);
+    STS(swe_top_tot);
+    STF(rain_top); STF(int_rain_top); STF(rain_ground); STF(int_rain_ground); STF(snow_top); STF(int_snow_top);
+    STF(snow_ground); STF(int_snow_ground); STF(int_top); STF(int_ground); STF(int_prec);
 }
 
 // ---- evapotranspiration.py:9-599 -----------------------------------------------------------
 RD bool lu_is_crop(double lu) { return (lu >= 500) && (lu < 600) && (lu == floor(lu)); }
 RD bool lu_is_tree(double lu) { return lu == 10 || lu == 11 || lu == 12 || lu == 15 || lu == 16 || lu == 17; }
 
-template <bool MASK1>
-RD void evapotranspiration(Cell& c, const StepPlan& p) {
+template <bool FLUX, bool MASK1>
+RD void evapotranspiration(Cell& c, const StepPlan& p, const Io& io) {
+    LDS(S_dep); LDS(de); LDP(rew); LDP(tew); LDP(basal_evap_coeff); LDS(S_fp_rz); LDS(swe); LDS(theta_rz);
+    LDP(basal_transp_coeff); LDS(S_lp_rz); LDP(z_evap);
+    c.k_stress_evap = 0.0;  // fully rewritten below (de <= rew | rew < de <= tew | de > tew) unless de is NaN
     const bool dry = c.prec <= 0;
     // upper interception storage (:9-66)
     {
@@ -260,7 +290,9 @@ RD void evapotranspiration(Cell& c, const StepPlan& p) {
     // transpiration (:348-543)
     {
         double tws = p.transp_water_stress * c.theta_ufc + M(c.theta_pwp);  // :360
-        double ks = lu_is_crop(c.lu_id) ? c.k_stress_transp : ((c.theta_rz - c.theta_pwp) / (tws - c.theta_pwp));
+        double ks;
+        if (lu_is_crop(c.lu_id)) { LDS(k_stress_transp); ks = c.k_stress_transp; }
+        else ks = ((c.theta_rz - c.theta_pwp) / (tws - c.theta_pwp));
         ks = M(ks);
         ks = (ks > 1) ? 1.0 : ks;
         c.k_stress_transp = ks;
@@ -303,11 +335,15 @@ RD void evapotranspiration(Cell& c, const StepPlan& p) {
     c.de += c.evap_soil + M(c.transp * (c.z_evap / c.z_root));  // :557
     c.aet_soil = M(c.evap_soil + c.transp);
     c.aet = M(c.evap_int_top + c.evap_int_ground + c.evap_dep + c.evap_soil + c.transp);
+    STS(S_dep); STS(k_stress_evap); STS(k_stress_transp); STS(S_int_ground);
+    STF(evap_int_top); STF(evap_int_ground); STF(evap_int); STF(evap_dep); STF(evap_sur); STF(evap_coeff);
+    STF(pevap_soil); STF(evap_soil); STF(transp_coeff); STF(pt); STF(ptransp); STF(ptransp_res); STF(transp);
+    STF(aet_soil); STF(aet);
 }
 
 // ---- snow.py:6-290 ---------------------------------------------------------------------------
-template <bool MASK1>
-RD void snow(Cell& c, const StepPlan& p) {
+template <bool FLUX, bool MASK1>
+RD void snow(Cell& c, const StepPlan& p, const Io& io) {
     const double ta_fm = p.ta_fm;
     const bool cold = c.ta <= ta_fm;
     double add = M(c.snow_ground * (cold ? 1.0 : 0.0));  // :6-26
@@ -375,6 +411,10 @@ RD void snow(Cell& c, const StepPlan& p) {
         c.z0 += M(q);
         c.prec_event_csum += M(q);
     }
+    STS(S_int_top); STS(swe_top); STS(swe_ground); STS(swe); STS(S_snow);
+    STF(pet_res); STF(snow_melt_top); STF(snow_melt_drip); STF(snow_melt_ground); STF(snow_melt); STF(q_snow);
+    // S_sur = (S_int_top + S_int_ground + S_dep + S_snow + z0) * maskCatch (surface.py:8-28): the first four are final
+    c.S_sur = c.S_int_top + c.S_int_ground + c.S_dep + c.S_snow;
 }
 
 // ---- infiltration.py ---------------------------------------------------------------------------
@@ -403,9 +443,18 @@ RD double theta_deficit_fp(const Cell& c) {  // :1635-1666
     return t;
 }
 
-template <bool MASK1>
-RD void event_bookkeeping_start(Cell& c, const StepPlan& p) {
+template <bool FLUX, bool MASK1>
+RD void event_bookkeeping_start(Cell& c, const StepPlan& p, const Io& io) {
+    LDP(sealing);
+    if (!p.cond1) {  // (cond1 overwrites every one of these)
+        LDS(no_wf); LDS(z_wf); LDS(z_wf_t0); LDS(z_wf_t1); LDS(z_wf_fc); LDS(inf_mat_event_csum);
+        LDS(inf_mat_pot_event_csum); LDS(inf_mp_event_csum); LDS(y_mp); LDS(inf_sc_event_csum); LDS(y_sc);
+        LDS(theta_d); LDS(theta_d_rel); LDS(theta_d_t0); LDS(theta_d_rel_t0); LDS(theta_d_fp); LDS(t_event_csum);
+        LDS(z_sc);
+        c.z_wf_m1 = c.z_wf; c.z_wf_t1_m1 = c.z_wf_t1; c.y_mp_m1 = c.y_mp; c.y_sc_m1 = c.y_sc;
+    }
     if (p.cond1) {
+        LDP(theta_4); LDP(theta_27); LDP(z_sc_max);
         // calc_depth_shrinkage_cracks :1767-1826
         const double th = c.theta_rz;
         double z = (th < c.theta_4) ? c.z_sc_max
@@ -460,10 +509,13 @@ RD void event_bookkeeping_start(Cell& c, const StepPlan& p) {
         c.t_event_csum = mk_ ? 0.0 : c.t_event_csum;
     }
     if (p.cond5) c.t_event_csum += p.dt;  // :2175-2180
+    STS(theta_d_fp); STS(theta_d_rel_t0); STS(de); STS(z_wf_fc); STS(prec_event_csum); STS(t_event_csum);
 }
 
-template <bool MASK1>
-RD void green_ampt_and_matrix(Cell& c, const StepPlan& p) {
+template <bool FLUX, bool MASK1>
+RD void green_ampt_and_matrix(Cell& c, const StepPlan& p, const Io& io) {
+    LDP(ks); LDP(wfs); LDS(t_sat);
+    c.inf_mat = 0.0;  // mask7 | mask8 rewrite it unless z0 / inf_mat_pot is NaN
     const double dt = p.dt;
     // calc_green_ampt_params :7-48 with calc_pi_gr/pi_m/sat_time/Fs :1669-1764
     const double ktw = c.ks * c.theta_d * c.wfs;
@@ -559,6 +611,15 @@ RD void green_ampt_and_matrix(Cell& c, const StepPlan& p) {
     c.theta_d_rel = M(m20 ? c.theta_d_rel_t0 : c.theta_d_rel);
     c.z_wf = M((c.z_wf > c.z_soil) ? c.z_soil : c.z_wf);
     c.theta_d = M(c.theta_d_t0);  // :411-416 (theta_d_t1 <= 0 always holds)
+    STF(pi_gr); STF(pi_m); STF(Fs); STF(inf_mat_pot); STF(inf_mat);
+    STS(inf_mat_event_csum); STS(inf_mat_pot_event_csum); STS(theta_d_rel); STS(no_wf);
+    // reset_event_vars (cond4, :2056-2144) zeroes these after the infiltration kernels; nothing reads them in between
+    if (p.cond4) {
+        io.sts(RF_t_sat, 0.0); io.sts(RF_z_wf_t0, 0.0);
+        if (FLUX) { c.pi_gr = 0; c.pi_m = 0; c.Fs = 0; STF(pi_gr); STF(pi_m); STF(Fs); }
+    } else {
+        STS(t_sat); STS(z_wf_t0);
+    }
 }
 
 // Vertical macropores: radial wetting front y(t) advanced in `substeps` explicit sub-steps
@@ -573,8 +634,9 @@ RD void green_ampt_and_matrix(Cell& c, const StepPlan& p) {
 // recompute the same numbers.  If inf_mp turns NaN it stays NaN (NaN + x) and so does
 // inf_mp_event_csum and y; the reference then stores y_mp = inf_mp = 0 (:808-824), so the loop
 // can stop at the first NaN as well.
-template <bool MASK1>
-RD void macropores(Cell& c, const StepPlan& p) {
+template <bool FLUX, bool MASK1>
+RD void macropores(Cell& c, const StepPlan& p, const Io& io) {
+    LDP(lmpv); LDP(dmpv); LDP(mp_drain_area); LDS(inf_mat_rz); LDS(S_lp_ss); LDS(S_fp_ss);
     const double dt = p.dt, r_mp = p.r_mp, pi = p.pi;
     const int substeps = p.substeps;
     // the reference's second `update(z_wf, ...)` discards the first (:443-462)
@@ -678,14 +740,16 @@ RD void macropores(Cell& c, const StepPlan& p) {
         c.z0 += M(-sub);
         c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
     }
+    STS(inf_mp_event_csum); STF(lmpv_non_sat); STF(inf_ss);
+    if (p.cond4) io.sts(RF_y_mp, 0.0); else STS(y_mp);
 }
 
 // Shrinkage cracks (infiltration.py:1080-1318).  In the reference the loop's `inf_sc` carry is
 // never updated (always 0) and `inf_sc_di` is doubled (:1248-1252); only y_sc and z_sc_non_sat
 // evolve.  Same exact early exit as for the macropores: the pass is a pure function of the
 // carried triple (ym1, t, inf_sc_event_csum).
-template <bool MASK1>
-RD void shrinkage_cracks(Cell& c, const StepPlan& p) {
+template <bool FLUX, bool MASK1>
+RD void shrinkage_cracks(Cell& c, const StepPlan& p, const Io& io) {
     const double dt = p.dt, l_sc = p.l_sc;
     const int substeps = p.substeps;
     const double z_wf = M((c.no_wf == 2) ? 0.0 : c.z_wf_t1);
@@ -729,10 +793,20 @@ RD void shrinkage_cracks(Cell& c, const StepPlan& p) {
     c.inf_sc_event_csum += M(c.inf_sc);
     c.z0 += M(-c.inf_sc);
     c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
+    STS(inf_sc_event_csum); STF(z_sc_non_sat); STF(inf_sc);
+    if (p.cond4) {  // reset_event_vars :2056-2144
+        io.sts(RF_y_sc, 0.0); io.sts(RF_z_sc, 0.0); io.sts(RF_z_wf_t1, 0.0);
+        const double td = theta_deficit<MASK1>(c);
+        io.sts(RF_theta_d, M(td)); io.sts(RF_theta_d_t0, M(td));
+        c.z_wf = 0;
+    } else {
+        STS(y_sc); STS(z_sc); STS(z_wf_t1); STS(theta_d); STS(theta_d_t0);
+    }
 }
 
-template <bool MASK1>
-RD void infiltration_tail(Cell& c, const StepPlan& p) {
+template <bool FLUX, bool MASK1>
+RD void infiltration_tail(Cell& c, const StepPlan& p, const Io& io) {
+    LDP(maskRiverLake);
     // calc_inf_rz :1321-1417
     c.inf_mat_rz = M(c.inf_mat);
     c.inf_sc_rz = M(c.inf_sc);
@@ -763,23 +837,23 @@ RD void infiltration_tail(Cell& c, const StepPlan& p) {
     c.z0 = M((c.z0 < 0) ? 0.0 : c.z0);
     c.q_sur = 0.0 + M(c.q_hof + c.q_sof);
     c.q_sur += (c.maskRiverLake != 0) ? c.prec : 0.0;
-    if (p.cond4) {  // reset_event_vars :2056-2144
-        c.z_wf = 0; c.z_wf_t0 = 0; c.z_wf_t1 = 0;
-        c.y_mp = 0;
-        c.y_sc = 0;
-        double td = theta_deficit<MASK1>(c);
-        c.theta_d = M(td);
-        c.theta_d_t0 = M(td);
-        c.pi_gr = 0; c.pi_m = 0; c.t_sat = 0; c.Fs = 0; c.z_sc = 0;
-    }
+    STS(inf_mat_rz); STS(z0); STS(z_wf);
+    STF(inf_mp); STF(inf_mp_rz); STF(inf_mp_ss); STF(inf_sc_rz); STF(inf_rz); STF(inf); STF(q_hof); STF(q_sof); STF(q_sur);
+    c.S_sur = M(c.S_sur + c.z0);
+    STS(S_sur);
 }
 
 // ---- subsurface_runoff.py / capillary_rise.py -------------------------------------------------
 // Salvucci-type flux between two depths: ((z/(-ha*10.2))^-n - (h/ha)^-n) / (1 + (h/ha)^-n + (n-1)(z/(-ha*10.2))^-n)
 RD double salvucci(double pa, double pb, double n_salv) { return (pa - pb) / (1 + pb + (n_salv - 1) * pa); }
 
-template <bool LAT, bool MASK1>
-RD void subsurface(Cell& c, const StepPlan& p) {
+template <bool LAT, bool FLUX, bool MASK1>
+RD void subsurface(Cell& c, const StepPlan& p, const Io& io) {
+    LDS(z_sat); LDS(k_rz); LDS(h_rz); LDS(h_ss); LDP(n_salv); LDP(ha); LDP(z_gw); LDP(kf); LDP(ks_ss);
+    if (LAT) {
+        LDP(dmph); LDP(slope); LDP(v_mp_layer_1); LDP(v_mp_layer_2); LDP(v_mp_layer_3); LDP(v_mp_layer_4);
+        LDP(v_mp_layer_5); LDP(v_mp_layer_6); LDP(v_mp_layer_7); LDP(v_mp_layer_8);
+    }
     const double dt = p.dt;
     const double zsub = c.z_soil - c.z_root;
     // calc_rise_of_saturation_water_table :693-765
@@ -934,7 +1008,7 @@ RD void subsurface(Cell& c, const StepPlan& p) {
         const double kfdt = c.kf * dt;
         double sal = salvucci(pa, pb, c.n_salv);
         double perc;
-        if ((c.z_gw <= 10) && (zgw > c.z_soil) && (c.z_sat > 0)) perc = fmin(fmin(kfdt, c.ks_ss * dt), c.k_ss * dt);
+        if ((c.z_gw <= 10) && (zgw > c.z_soil) && (c.z_sat > 0)) { LDS(k_ss); perc = fmin(fmin(kfdt, c.ks_ss * dt), c.k_ss * dt); }
         else perc = fmin(kfdt, sal * dt * c.ks_ss * (-1));
         perc = M(perc);
         const bool above = c.z_soil < zgw;
@@ -1015,6 +1089,15 @@ RD void subsurface(Cell& c, const StepPlan& p) {
         c.S_lp_rz += M(ex ? (c.S_fp_rz - c.S_ufc_rz) : 0.0);
         c.S_fp_rz = M(ex ? c.S_ufc_rz : c.S_fp_rz);
     }
+    STS(z_sat);
+    STF(S_zsat); STF(S_zsat_rz); STF(S_zsat_ss); STF(q_pot_rz); STF(q_rz); STF(q_pot_ss); STF(q_ss); STF(cpr_rz);
+    if (LAT) {
+        STF(q_sub_mat_pot); STF(q_sub_mp_pot); STF(q_sub_pot); STF(q_sub_mat_share); STF(q_sub_mp_share); STF(q_sub_rz);
+        STF(q_sub_mat_rz); STF(q_sub_mp_rz); STF(q_sub_mp_pot_rz); STF(q_sub_mat_pot_ss); STF(q_sub_mp_pot_ss);
+        STF(q_sub_pot_ss); STF(q_sub_ss); STF(q_sub_mat_ss); STF(q_sub_mp_ss); STF(q_sub_mat); STF(q_sub_mp); STF(q_sub);
+        STF(z_sat_layer_1); STF(z_sat_layer_2); STF(z_sat_layer_3); STF(z_sat_layer_4); STF(z_sat_layer_5);
+        STF(z_sat_layer_6); STF(z_sat_layer_7); STF(z_sat_layer_8);
+    }
 }
 
 // Brooks-Corey conductivity and matric potential of one layer (root_zone.py:36-60, subsoil.py:22-48,
@@ -1033,9 +1116,12 @@ RD void brooks_corey(const Cell& c, double theta, double mm, double inv_lambda, 
 }
 
 // ---- storages (surface.py:8-28, root_zone.py:36-163, subsoil.py:6-130, soil.py:9-140, numerics.py:125-152)
-template <bool MASK1>
-RD void storages(Cell& c, const StepPlan& p) {
-    c.S_sur = M(c.S_int_top + c.S_int_ground + c.S_dep + c.S_snow + c.z0);
+template <bool FLUX, bool MASK1>
+RD void storages(Cell& c, const StepPlan& p, const Io& io) {
+    LDP(lambda_bc); LDP(m_bc); LDS(S);
+    c.S_m1 = c.S;
+    if (FLUX) { c.S_rz_m1 = io.lds(RF_S_rz); c.S_ss_m1 = io.lds(RF_S_ss); c.S_s_m1 = io.lds(RF_S_s); }
+    else { c.S_rz_m1 = 0; c.S_ss_m1 = 0; c.S_s_m1 = 0; }
     const double inv_lambda = 1 / c.lambda_bc;
     const double mm = -c.m_bc;
     c.S_rz = M(c.S_pwp_rz + c.S_fp_rz + c.S_lp_rz);
@@ -1061,11 +1147,14 @@ RD void storages(Cell& c, const StepPlan& p) {
     brooks_corey<MASK1>(c, c.theta, mm, inv_lambda, c.k, c.h);
     c.S = c.S_sur + M(c.S_s);       // numerics.py:134
     c.dS = c.S - M(c.S_m1);         // numerics.py:147
+    STS(S_rz); STS(theta_rz); STS(k_rz); STS(h_rz); STS(S_ss); STS(theta_ss); STS(k_ss); STS(h_ss);
+    STS(S_s); STS(theta); STS(k); STS(h); STS(S);
+    STF(S_fp_s); STF(S_lp_s); STF(dS_rz); STF(dS_ss); STF(dS_s); STF(dS); STF(irr_demand);
 }
 
 // numerics.py:217-346 calc_dS_num_error and :742-800 / :978-1016 sanity_check; returns the cell's verdict
-template <bool LAT>
-RD bool balance_check(Cell& c, const StepPlan& p) {
+template <bool LAT, bool FLUX>
+RD bool balance_check(Cell& c, const StepPlan& p, const Io& io) {
     const double lhs = c.S - c.S_m1;
     double rhs;
     if (LAT) {
@@ -1089,29 +1178,50 @@ RD bool balance_check(Cell& c, const StepPlan& p) {
     ok = ok && (nz(c.S_fp_rz) > -a) && (nz(c.S_lp_rz) > -a) && (nz(c.S_fp_ss) > -a) && (nz(c.S_lp_ss) > -a);
     ok = ok && (nz(c.S_fp_rz) - a <= nz(c.S_ufc_rz)) && (nz(c.S_lp_rz) - a <= nz(c.S_ac_rz)) &&
          (nz(c.S_fp_ss) - a <= nz(c.S_ufc_ss)) && (nz(c.S_lp_ss) - a <= nz(c.S_ac_ss));
+    STF(dS_num_error);
+    if (!LAT) { STF(dS_rz_num_error); STF(dS_ss_num_error); }
     return ok;
 }
 
-template <bool LAT, bool MASK1>
-RD bool cell_step(Cell& c, const StepPlan& p) {
+// Parameters the reference derives once at setup from the primary ones (soil.py:143-560); two flops each, so
+// they are recomputed instead of read (80 B per cell-step less HBM traffic).  Same expressions, same rounding.
+template <bool MASK1>
+RD void derived_parameters(Cell& c, const Io& io) {
+    LDP(theta_ac); LDP(theta_ufc); LDP(theta_pwp); LDP(z_root); LDP(z_soil);
+    c.theta_sat = M(c.theta_ac + c.theta_ufc + c.theta_pwp);
+    c.theta_fc = M(c.theta_ufc + c.theta_pwp);
+    c.S_ac_rz = M(c.theta_ac * c.z_root);
+    c.S_ufc_rz = M(c.theta_ufc * c.z_root);
+    c.S_pwp_rz = M(c.theta_pwp * c.z_root);
+    const double zsub = c.z_soil - c.z_root;
+    c.S_ac_ss = M(c.theta_ac * zsub);
+    c.S_ufc_ss = M(c.theta_ufc * zsub);
+    c.S_pwp_ss = M(c.theta_pwp * zsub);
+    c.S_pwp_s = M(c.z_soil * c.theta_pwp);
+}
+
+template <bool LAT, bool FLUX, bool MASK1>
+RD bool cell_step(Cell& c, const StepPlan& p, const Io& io) {
+    derived_parameters<MASK1>(c, io);
     c.pet_res = c.pet;  // adaptive_time_stepping.py:367-368
-    interception<MASK1>(c, p);
-    evapotranspiration<MASK1>(c, p);
-    snow<MASK1>(c, p);
-    event_bookkeeping_start<MASK1>(c, p);
-    green_ampt_and_matrix<MASK1>(c, p);
-    macropores<MASK1>(c, p);
-    shrinkage_cracks<MASK1>(c, p);
-    infiltration_tail<MASK1>(c, p);
-    subsurface<LAT, MASK1>(c, p);
-    storages<MASK1>(c, p);
-    bool ok = balance_check<LAT>(c, p);
+    interception<FLUX, MASK1>(c, p, io);
+    evapotranspiration<FLUX, MASK1>(c, p, io);
+    snow<FLUX, MASK1>(c, p, io);
+    event_bookkeeping_start<FLUX, MASK1>(c, p, io);
+    green_ampt_and_matrix<FLUX, MASK1>(c, p, io);
+    macropores<FLUX, MASK1>(c, p, io);
+    shrinkage_cracks<FLUX, MASK1>(c, p, io);
+    infiltration_tail<FLUX, MASK1>(c, p, io);
+    subsurface<LAT, FLUX, MASK1>(c, p, io);
+    storages<FLUX, MASK1>(c, p, io);
+    bool ok = balance_check<LAT, FLUX>(c, p, io);
     if (p.clamp) {  // models/svat/svat.py:333-352
         c.S_fp_rz = ((c.S_fp_rz > -1e-6) && (c.S_fp_rz < 0)) ? 0.0 : c.S_fp_rz;
         c.S_lp_rz = ((c.S_lp_rz > -1e-6) && (c.S_lp_rz < 0)) ? 0.0 : c.S_lp_rz;
         c.S_fp_ss = ((c.S_fp_ss > -1e-6) && (c.S_fp_ss < 0)) ? 0.0 : c.S_fp_ss;
         c.S_lp_ss = ((c.S_lp_ss > -1e-6) && (c.S_lp_ss < 0)) ? 0.0 : c.S_lp_ss;
     }
+    STS(S_fp_rz); STS(S_lp_rz); STS(S_fp_ss); STS(S_lp_ss);
     return ok;
 }
 
