@@ -162,8 +162,11 @@ __global__ void k_aggregate_a(Planes pl, double* __restrict__ prec_m1, const dou
 #ifndef ROGER_MIN_BLOCKS
 #define ROGER_MIN_BLOCKS 4
 #endif
+#ifndef ROGER_BLOCK
+#define ROGER_BLOCK 128
+#endif
 template <bool LAT, bool FLUX>
-__global__ void __launch_bounds__(128, ROGER_MIN_BLOCKS)
+__global__ void __launch_bounds__(ROGER_BLOCK, ROGER_MIN_BLOCKS)
 k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* __restrict__ ta_day,
             const double* __restrict__ pet_day, StepPlan p, unsigned* flags) {
     const int64_t C = pl.C;
@@ -430,7 +433,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
     if (write_fluxes) { int r = ensure_flux_planes(h); if (r) return r; }
     const roger_svat_settings& st = h->st;
     roger_svat_scalars& sc = h->sc;
-    const int threads = 128;
+    const int threads = ROGER_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
     int64_t launches = 0;
     CU(cudaEventRecord(h->ev0, h->stream));

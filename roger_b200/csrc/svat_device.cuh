@@ -107,6 +107,9 @@ RD double mk(const Cell& c, double x) { return MASK1 ? x : x * c.m; }
 // Plane access of one thread.  Loads are issued where a field is first needed and stores as soon as a
 // field is final, so that only the values a process actually works on are alive in registers
 // (load everything up front costs 250+ registers and two resident blocks per SM).
+#ifndef ROGER_L2_PREFETCH
+#define ROGER_L2_PREFETCH 0
+#endif
 constexpr int kFirstFlux = RF_pet_res;  // the enum is ordered P.., S.., F..
 struct Io {
     double* __restrict__ ps;  // parameter + state planes
@@ -119,6 +122,13 @@ struct Io {
     RD void stf(int id, double v) const {
         if (FLUX) fl[(size_t)(id - kFirstFlux) * C + i] = v;
     }
+    RD void pf(int id) const {
+#if ROGER_L2_PREFETCH == 2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ps + (size_t)id * C + i));
+#else
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (size_t)id * C + i));
+#endif
+    }
 };
 #define LDP(name) c.name = io.ldp(RF_##name)
 #define LDS(name) c.name = io.lds(RF_##name)
@@ -128,9 +138,6 @@ struct Io {
 // ---- interception.py:6-343 ------------------------------------------------------------------
 template <bool FLUX, bool MASK1>
 RD void interception(Cell& c, const StepPlan& p, const Io& io) {
-    LDP(throughfall_coeff_top); LDP(throughfall_coeff_ground); LDP(S_int_top_tot); LDP(S_int_ground_tot); LDP(lu_id);
-    LDS(swe_top); LDS(S_int_top); LDS(S_int_ground); LDS(S_snow); LDS(z0); LDS(prec_event_csum); LDS(swe_top_tot);
-    LDS(swe_ground);
     const double ta_fm = p.ta_fm;
     const bool warm = c.ta > ta_fm;
     const double tf_top = 1. - c.throughfall_coeff_top;
@@ -220,8 +227,6 @@ RD bool lu_is_tree(double lu) { return lu == 10 || lu == 11 || lu == 12 || lu ==
 
 template <bool FLUX, bool MASK1>
 RD void evapotranspiration(Cell& c, const StepPlan& p, const Io& io) {
-    LDS(S_dep); LDS(de); LDP(rew); LDP(tew); LDP(basal_evap_coeff); LDS(S_fp_rz); LDS(swe); LDS(theta_rz);
-    LDP(basal_transp_coeff); LDS(S_lp_rz); LDP(z_evap);
     c.k_stress_evap = 0.0;  // fully rewritten below (de <= rew | rew < de <= tew | de > tew) unless de is NaN
     const bool dry = c.prec <= 0;
     // upper interception storage (:9-66)
@@ -445,16 +450,8 @@ RD double theta_deficit_fp(const Cell& c) {  // :1635-1666
 
 template <bool FLUX, bool MASK1>
 RD void event_bookkeeping_start(Cell& c, const StepPlan& p, const Io& io) {
-    LDP(sealing);
-    if (!p.cond1) {  // (cond1 overwrites every one of these)
-        LDS(no_wf); LDS(z_wf); LDS(z_wf_t0); LDS(z_wf_t1); LDS(z_wf_fc); LDS(inf_mat_event_csum);
-        LDS(inf_mat_pot_event_csum); LDS(inf_mp_event_csum); LDS(y_mp); LDS(inf_sc_event_csum); LDS(y_sc);
-        LDS(theta_d); LDS(theta_d_rel); LDS(theta_d_t0); LDS(theta_d_rel_t0); LDS(theta_d_fp); LDS(t_event_csum);
-        LDS(z_sc);
-        c.z_wf_m1 = c.z_wf; c.z_wf_t1_m1 = c.z_wf_t1; c.y_mp_m1 = c.y_mp; c.y_sc_m1 = c.y_sc;
-    }
+    if (!p.cond1) { c.z_wf_m1 = c.z_wf; c.z_wf_t1_m1 = c.z_wf_t1; c.y_mp_m1 = c.y_mp; c.y_sc_m1 = c.y_sc; }
     if (p.cond1) {
-        LDP(theta_4); LDP(theta_27); LDP(z_sc_max);
         // calc_depth_shrinkage_cracks :1767-1826
         const double th = c.theta_rz;
         double z = (th < c.theta_4) ? c.z_sc_max
@@ -514,7 +511,6 @@ RD void event_bookkeeping_start(Cell& c, const StepPlan& p, const Io& io) {
 
 template <bool FLUX, bool MASK1>
 RD void green_ampt_and_matrix(Cell& c, const StepPlan& p, const Io& io) {
-    LDP(ks); LDP(wfs); LDS(t_sat);
     c.inf_mat = 0.0;  // mask7 | mask8 rewrite it unless z0 / inf_mat_pot is NaN
     const double dt = p.dt;
     // calc_green_ampt_params :7-48 with calc_pi_gr/pi_m/sat_time/Fs :1669-1764
@@ -636,7 +632,6 @@ RD void green_ampt_and_matrix(Cell& c, const StepPlan& p, const Io& io) {
 // can stop at the first NaN as well.
 template <bool FLUX, bool MASK1>
 RD void macropores(Cell& c, const StepPlan& p, const Io& io) {
-    LDP(lmpv); LDP(dmpv); LDP(mp_drain_area); LDS(inf_mat_rz); LDS(S_lp_ss); LDS(S_fp_ss);
     const double dt = p.dt, r_mp = p.r_mp, pi = p.pi;
     const int substeps = p.substeps;
     // the reference's second `update(z_wf, ...)` discards the first (:443-462)
@@ -806,7 +801,6 @@ RD void shrinkage_cracks(Cell& c, const StepPlan& p, const Io& io) {
 
 template <bool FLUX, bool MASK1>
 RD void infiltration_tail(Cell& c, const StepPlan& p, const Io& io) {
-    LDP(maskRiverLake);
     // calc_inf_rz :1321-1417
     c.inf_mat_rz = M(c.inf_mat);
     c.inf_sc_rz = M(c.inf_sc);
@@ -849,11 +843,6 @@ RD double salvucci(double pa, double pb, double n_salv) { return (pa - pb) / (1 
 
 template <bool LAT, bool FLUX, bool MASK1>
 RD void subsurface(Cell& c, const StepPlan& p, const Io& io) {
-    LDS(z_sat); LDS(k_rz); LDS(h_rz); LDS(h_ss); LDP(n_salv); LDP(ha); LDP(z_gw); LDP(kf); LDP(ks_ss);
-    if (LAT) {
-        LDP(dmph); LDP(slope); LDP(v_mp_layer_1); LDP(v_mp_layer_2); LDP(v_mp_layer_3); LDP(v_mp_layer_4);
-        LDP(v_mp_layer_5); LDP(v_mp_layer_6); LDP(v_mp_layer_7); LDP(v_mp_layer_8);
-    }
     const double dt = p.dt;
     const double zsub = c.z_soil - c.z_root;
     // calc_rise_of_saturation_water_table :693-765
@@ -1118,10 +1107,6 @@ RD void brooks_corey(const Cell& c, double theta, double mm, double inv_lambda, 
 // ---- storages (surface.py:8-28, root_zone.py:36-163, subsoil.py:6-130, soil.py:9-140, numerics.py:125-152)
 template <bool FLUX, bool MASK1>
 RD void storages(Cell& c, const StepPlan& p, const Io& io) {
-    LDP(lambda_bc); LDP(m_bc); LDS(S);
-    c.S_m1 = c.S;
-    if (FLUX) { c.S_rz_m1 = io.lds(RF_S_rz); c.S_ss_m1 = io.lds(RF_S_ss); c.S_s_m1 = io.lds(RF_S_s); }
-    else { c.S_rz_m1 = 0; c.S_ss_m1 = 0; c.S_s_m1 = 0; }
     const double inv_lambda = 1 / c.lambda_bc;
     const double mm = -c.m_bc;
     c.S_rz = M(c.S_pwp_rz + c.S_fp_rz + c.S_lp_rz);
@@ -1200,19 +1185,99 @@ RD void derived_parameters(Cell& c, const Io& io) {
     c.S_pwp_s = M(c.z_soil * c.theta_pwp);
 }
 
+// ---- plane loads, grouped by the process that first needs them.  cell_step issues each group one process
+// ahead of its use (software prefetch): with 16 resident warps per SM the ~600-cycle HBM latency of a group
+// is then covered by the arithmetic of the process running in between.
+RD void load_interception(Cell& c, const Io& io) {
+    LDP(throughfall_coeff_top); LDP(throughfall_coeff_ground); LDP(S_int_top_tot); LDP(S_int_ground_tot); LDP(lu_id);
+    LDS(swe_top); LDS(S_int_top); LDS(S_int_ground); LDS(S_snow); LDS(z0); LDS(prec_event_csum); LDS(swe_top_tot);
+    LDS(swe_ground);
+}
+RD void load_evapotranspiration(Cell& c, const Io& io) {
+    LDS(S_dep); LDS(de); LDP(rew); LDP(tew); LDP(basal_evap_coeff); LDS(S_fp_rz); LDS(swe); LDS(theta_rz);
+    LDP(basal_transp_coeff); LDS(S_lp_rz); LDP(z_evap);
+}
+RD void load_event_state(Cell& c, const StepPlan& p, const Io& io) {
+    LDP(sealing);
+    if (!p.cond1) {  // (set_event_vars overwrites every one of these)
+        LDS(no_wf); LDS(z_wf); LDS(z_wf_t0); LDS(z_wf_t1); LDS(z_wf_fc); LDS(inf_mat_event_csum);
+        LDS(inf_mat_pot_event_csum); LDS(inf_mp_event_csum); LDS(y_mp); LDS(inf_sc_event_csum); LDS(y_sc);
+        LDS(theta_d); LDS(theta_d_rel); LDS(theta_d_t0); LDS(theta_d_rel_t0); LDS(theta_d_fp); LDS(t_event_csum);
+        LDS(z_sc);
+    } else {
+        LDP(theta_4); LDP(theta_27); LDP(z_sc_max);
+    }
+}
+RD void load_infiltration(Cell& c, const Io& io) {
+    LDP(ks); LDP(wfs); LDS(t_sat);
+    LDP(lmpv); LDP(dmpv); LDP(mp_drain_area); LDS(inf_mat_rz); LDS(S_lp_ss); LDS(S_fp_ss);
+    LDP(maskRiverLake);
+}
+template <bool LAT>
+RD void load_subsurface(Cell& c, const Io& io) {
+    LDS(z_sat); LDS(k_rz); LDS(h_rz); LDS(h_ss); LDP(n_salv); LDP(ha); LDP(z_gw); LDP(kf); LDP(ks_ss);
+    if (LAT) {
+        LDP(dmph); LDP(slope); LDP(v_mp_layer_1); LDP(v_mp_layer_2); LDP(v_mp_layer_3); LDP(v_mp_layer_4);
+        LDP(v_mp_layer_5); LDP(v_mp_layer_6); LDP(v_mp_layer_7); LDP(v_mp_layer_8);
+    }
+}
+template <bool FLUX>
+RD void load_storages(Cell& c, const Io& io) {
+    LDP(lambda_bc); LDP(m_bc); LDS(S);
+    c.S_m1 = c.S;
+    if (FLUX) { c.S_rz_m1 = io.lds(RF_S_rz); c.S_ss_m1 = io.lds(RF_S_ss); c.S_s_m1 = io.lds(RF_S_s); }
+    else { c.S_rz_m1 = 0; c.S_ss_m1 = 0; c.S_s_m1 = 0; }
+}
+
+#ifndef ROGER_PREFETCH
+#define ROGER_PREFETCH 0
+#endif
+// Register-free alternative: ask the memory system to pull the planes of the later processes into L2 (or L1)
+// while the first processes compute.
+template <bool LAT>
+RD void prefetch_later_groups(const StepPlan& p, const Io& io) {
+#define PF(name) io.pf(RF_##name)
+    PF(sealing);
+    if (!p.cond1) {
+        PF(no_wf); PF(z_wf); PF(z_wf_t0); PF(z_wf_t1); PF(z_wf_fc); PF(inf_mat_event_csum); PF(inf_mat_pot_event_csum);
+        PF(inf_mp_event_csum); PF(y_mp); PF(inf_sc_event_csum); PF(y_sc); PF(theta_d); PF(theta_d_rel); PF(theta_d_t0);
+        PF(theta_d_rel_t0); PF(theta_d_fp); PF(t_event_csum); PF(z_sc);
+    }
+    PF(ks); PF(wfs); PF(t_sat); PF(lmpv); PF(dmpv); PF(mp_drain_area); PF(inf_mat_rz); PF(S_lp_ss); PF(S_fp_ss); PF(maskRiverLake);
+    PF(z_sat); PF(k_rz); PF(h_rz); PF(h_ss); PF(n_salv); PF(ha); PF(z_gw); PF(kf); PF(ks_ss);
+    if (LAT) {
+        PF(dmph); PF(slope); PF(v_mp_layer_1); PF(v_mp_layer_2); PF(v_mp_layer_3); PF(v_mp_layer_4); PF(v_mp_layer_5);
+        PF(v_mp_layer_6); PF(v_mp_layer_7); PF(v_mp_layer_8);
+    }
+    PF(lambda_bc); PF(m_bc); PF(S);
+#undef PF
+}
+
 template <bool LAT, bool FLUX, bool MASK1>
 RD bool cell_step(Cell& c, const StepPlan& p, const Io& io) {
     derived_parameters<MASK1>(c, io);
     c.pet_res = c.pet;  // adaptive_time_stepping.py:367-368
+    load_interception(c, io);
+    if (ROGER_PREFETCH) load_evapotranspiration(c, io);
+    if (ROGER_L2_PREFETCH) prefetch_later_groups<LAT>(p, io);
     interception<FLUX, MASK1>(c, p, io);
+    if (!ROGER_PREFETCH) load_evapotranspiration(c, io);
+    if (ROGER_PREFETCH) load_event_state(c, p, io);
     evapotranspiration<FLUX, MASK1>(c, p, io);
     snow<FLUX, MASK1>(c, p, io);
+    if (!ROGER_PREFETCH) load_event_state(c, p, io);
+    if (ROGER_PREFETCH) load_infiltration(c, io);
     event_bookkeeping_start<FLUX, MASK1>(c, p, io);
+    if (!ROGER_PREFETCH) load_infiltration(c, io);
     green_ampt_and_matrix<FLUX, MASK1>(c, p, io);
+    if (ROGER_PREFETCH) load_subsurface<LAT>(c, io);
     macropores<FLUX, MASK1>(c, p, io);
     shrinkage_cracks<FLUX, MASK1>(c, p, io);
     infiltration_tail<FLUX, MASK1>(c, p, io);
+    if (!ROGER_PREFETCH) load_subsurface<LAT>(c, io);
+    if (ROGER_PREFETCH) load_storages<FLUX>(c, io);
     subsurface<LAT, FLUX, MASK1>(c, p, io);
+    if (!ROGER_PREFETCH) load_storages<FLUX>(c, io);
     storages<FLUX, MASK1>(c, p, io);
     bool ok = balance_check<LAT, FLUX>(c, p, io);
     if (p.clamp) {  // models/svat/svat.py:333-352
