@@ -1,0 +1,74 @@
+/* roger_b200_sas.h -- C ABI of the offline StorAge-selection (SAS) oxygen-18 transport step.
+ *
+ * Replaces, for the deterministic solver, the body of transport.svat_transport_model_deterministic
+ * (roger/core/transport.py:948-991): infiltration into the root zone, soil evaporation, transpiration,
+ * root-zone percolation, infiltration into the subsoil, subsoil percolation, capillary rise
+ * (each: cumulative StorAge -> SAS function -> backward travel-time distribution -> isotope mixing),
+ * storage concentrations, ageing.  One call = one daily time step for every cell.
+ *
+ * Age-ranked arrays are (cell, age) with the age axis contiguous, exactly the interior of the reference's
+ * `vs.sa_rz[2:-2, 2:-2, tau, :]` (roger/variables.py:2500-2525).
+ */
+#ifndef ROGER_B200_SAS_H
+#define ROGER_B200_SAS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-cell daily forcing planes (roger/models/svat_oxygen18 set_forcing; benchmarks/SVATOXYGEN18_benchmark.py:385-398) */
+enum roger_sas_forcing {
+    RSF_inf_mat_rz = 0, RSF_inf_pf_rz, RSF_inf_pf_ss, RSF_evap_soil, RSF_transp, RSF_q_rz, RSF_q_ss, RSF_cpr_rz,
+    RSF_C_in, /* isotope concentration of the input (after the snow-pack mixing of set_forcing) */
+    RSF_COUNT
+};
+
+/* the five SAS-controlled fluxes, index into the sas_params block: (process, cell, 8) */
+enum roger_sas_process { RSP_evap_soil = 0, RSP_transp, RSP_q_rz, RSP_q_ss, RSP_cpr_rz, RSP_COUNT };
+
+/* per-cell scalar results of a step */
+enum roger_sas_output {
+    RSO_C_inf_mat_rz = 0, RSO_C_inf_pf_rz, RSO_C_inf_pf_ss, RSO_C_evap_soil, RSO_C_transp, RSO_C_q_rz, RSO_C_q_ss, RSO_C_cpr_rz,
+    RSO_C_iso_inf_mat_rz, RSO_C_iso_inf_pf_rz, RSO_C_iso_inf_pf_ss, RSO_C_iso_evap_soil, RSO_C_iso_transp, RSO_C_iso_q_rz,
+    RSO_C_iso_q_ss, RSO_C_iso_cpr_rz,
+    RSO_C_rz, RSO_C_ss, RSO_C_s, RSO_C_iso_rz, RSO_C_iso_ss, RSO_C_iso_s,
+    RSO_COUNT
+};
+
+typedef struct roger_sas_settings {
+    int32_t ages;          /* settings.ages (number of age bins)                       */
+    int32_t substeps;      /* settings.sas_solver_substeps                              */
+    double VSMOW_conc18O;  /* settings.VSMOW_conc18O                                    */
+    double d18O_min;       /* settings.d18O_min                                         */
+    double d18O_max;       /* settings.d18O_max                                         */
+    int32_t store_tt;      /* keep the five travel-time distributions tt_* (diagnostics) */
+    int32_t reserved;
+} roger_sas_settings;
+
+typedef struct roger_sas roger_sas; /* opaque handle */
+
+int roger_sas_create(roger_sas **out, int64_t n_cells, const roger_sas_settings *settings, int device);
+void roger_sas_destroy(roger_sas *h);
+/* age-ranked state: which = 0 sa_rz, 1 sa_ss, 2 msa_rz, 3 msa_ss; host buffers of n_cells*ages doubles */
+int roger_sas_upload_state(roger_sas *h, int which, const double *host);
+int roger_sas_download_state(roger_sas *h, int which, double *host);
+uint64_t roger_sas_state_ptr(roger_sas *h, int which);
+/* maskCatch (n_cells) and SAS parameters (RSP_COUNT * n_cells * 8), roger/variables.py:4275 */
+int roger_sas_set_parameters(roger_sas *h, const double *mask_catch, const double *sas_params);
+/* one daily step.  forcing: RSF_COUNT planes of n_cells doubles (host memory). */
+int roger_sas_step(roger_sas *h, const double *forcing);
+/* same with forcing already on the device (raw address of RSF_COUNT * n_cells doubles) */
+int roger_sas_step_device(roger_sas *h, uint64_t forcing);
+/* per-cell scalar results of the last step: RSO_COUNT planes of n_cells doubles */
+int roger_sas_download_outputs(roger_sas *h, double *host);
+/* travel-time distribution of process p from the last step (needs settings.store_tt): n_cells*ages doubles */
+int roger_sas_download_tt(roger_sas *h, int process, double *host);
+int roger_sas_synchronize(roger_sas *h);
+int roger_sas_last_timing(roger_sas *h, double *kernel_ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROGER_B200_SAS_H */

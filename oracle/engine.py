@@ -65,3 +65,46 @@ class OracleSvatEngine:
 
     def synchronize(self):
         pass
+
+
+class OracleSasEngine:
+    """Same interface as roger_b200.sas_engine.CudaSasEngine, computed by oracle/sas_oracle.c."""
+
+    def __init__(self, n_cells, settings):
+        from roger_b200 import sas
+
+        self.sas = sas
+        self.n = int(n_cells)
+        self.settings = settings
+        self.A = int(settings.ages)
+        self.state = {k: np.zeros((self.n, self.A)) for k in sas.STATE}
+        self.out = np.zeros((len(sas.OUTPUTS), self.n))
+        self.ttbuf = np.zeros((len(sas.PROCESSES), self.n, self.A)) if settings.store_tt else None
+        self._fn = lib().sas_oracle_day
+        self._fn.restype = None
+
+    def set_parameters(self, mask, sas_params):
+        self.mask = np.ascontiguousarray(mask, dtype=np.float64)
+        self.params = np.ascontiguousarray(sas_params, dtype=np.float64)
+
+    def upload_state(self, name, arr):
+        self.state[name] = np.ascontiguousarray(np.asarray(arr, dtype=np.float64).reshape(self.n, self.A)).copy()
+
+    def download_state(self, name):
+        return self.state[name].copy()
+
+    def step(self, forcing):
+        f = np.ascontiguousarray(forcing, dtype=np.float64)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        s = self.state
+        self._fn(C.c_int64(self.n), C.byref(self.settings), dp(s["sa_rz"]), dp(s["sa_ss"]), dp(s["msa_rz"]), dp(s["msa_ss"]),
+                 dp(f), dp(self.mask), dp(self.params), dp(self.out), dp(self.ttbuf) if self.ttbuf is not None else None)
+
+    def download_outputs(self):
+        return self.out.copy()
+
+    def download_tt(self, process):
+        return self.ttbuf[self.sas.PROCESSES.index(process)].copy()
+
+    def synchronize(self):
+        pass

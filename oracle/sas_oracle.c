@@ -1,1 +1,355 @@
-/* placeholder until the SAS oracle lands */
+/* sas_oracle.c -- CPU restatement of the reference's deterministic oxygen-18 StorAge-selection transport
+ * step (roger/core/transport.py:948-991 and the *_transport_iso_kernel of every process module).
+ *
+ * TEST INFRASTRUCTURE (see svat_oracle.c): only tests/, __graft_entry__.smoke() and bench.py's CPU legs use it.
+ * Parity status: PINNED against outputs of the reference's own NumPy backend (tests/golden/sas_*.npz produced
+ * by tests/golden/make_sas_golden.py).  SAS families restated: uniform (1), dirac (2), Kumaraswamy (3, 31-37),
+ * exponential (51, 52), power (6, 61, 62); the gamma family (4, scipy.special.gammainc) is not restated and
+ * is not used by any benchmark configuration.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/roger_b200_sas.h"
+
+/* numpy add.reduce over a contiguous axis (pairwise, 8 lanes, blocks of 128) */
+static double pw_sum(const double *a, int n)
+{
+    if (n < 8) {
+        double res = 0.;
+        for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        double r[8];
+        int i;
+        for (int j = 0; j < 8; j++) r[j] = a[j];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; j++) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return pw_sum(a, n2) + pw_sum(a + n2, n - n2);
+    }
+}
+static double np_sum(const double *a, int n) { return 0.0 + pw_sum(a, n); }
+static double np_max(const double *a, int n)
+{ /* npx.max propagates NaN */
+    double mx = a[0];
+    for (int i = 1; i < n; i++) {
+        if (isnan(a[i])) return a[i];
+        if (a[i] > mx) mx = a[i];
+    }
+    return mx;
+}
+
+typedef struct {
+    int A, substeps;
+    double vsmow, dmin, dmax;
+} sas_ctx;
+
+/* transport.py:328-340 */
+static double conc_to_delta(const sas_ctx *c, double conc)
+{
+    double d = 1000. * (conc / (c->vsmow * (1. - conc)) - 1.);
+    return ((d < c->dmin) || (d > c->dmax)) ? NAN : d;
+}
+
+/* ---- SAS functions (roger/core/sas.py), Omega over nages = A + 1 points ---- */
+static void sas_uniform(const sas_ctx *c, const double *SA, const double *sp, double m, double *Om)
+{ /* sas.py:5-35 */
+    const int N = c->A + 1;
+    double mask = (sp[0] == 1) ? 1.0 : 0.0;
+    double S = np_max(SA, N) * mask * m;
+    double lam = 1 / S * mask * m;
+    for (int j = 0; j < N; j++) Om[j] = ((SA[j] < S) ? ((SA[j] > 0) ? lam * SA[j] : 0.) : 1.) * mask * m;
+    Om[N - 1] = ((mask != 0) ? 1 : Om[N - 1]) * m;
+    for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
+}
+static void sas_dirac(const sas_ctx *c, const double *SA, const double *sp, double m, double *Om)
+{ /* sas.py:243-264 */
+    const int N = c->A + 1;
+    int mask2 = (sp[0] == 2);
+    double S = np_max(SA, N) * m;
+    for (int j = 0; j < N; j++) Om[j] = ((mask2 && ((double)j <= sp[1])) ? 0 : 1) * m;
+    for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * (mask2 ? 1.0 : 0.0) * m;
+}
+static double s_rel(double S, const double *sp, double m)
+{
+    double r = (S - sp[5]) / (sp[6] - sp[5]) * m;
+    r = (r < 0) ? 0 : r;
+    r = (r > 1) ? 1 : r;
+    return r;
+}
+static void sas_kumaraswami(const sas_ctx *c, const double *SA, double *sp, double m, double *Om)
+{ /* sas.py:38-134 (modifies sp[1], sp[2] for the storage-dependent variants) */
+    const int N = c->A + 1;
+    double id = sp[0];
+    int mask3 = (id == 3 || id == 31 || id == 32 || id == 33 || id == 34 || id == 35 || id == 36 || id == 37);
+    double S = np_max(SA, N) * m;
+    double r = s_rel(S, sp, m);
+    if (id == 31) { sp[1] = 1; sp[2] = sp[3] + (r * sp[4]); }
+    if (id == 32) { sp[1] = sp[3] + ((1 - r) * sp[4]); sp[2] = 1; }
+    if (id == 33) { sp[1] = 1; sp[2] = sp[3] + ((1 - r) * sp[4]); }
+    if (id == 34) { sp[1] = sp[3] + (r * sp[4]); sp[2] = 1; }
+    if (id == 35) { sp[1] = sp[3] + ((1 - r) * sp[4]); sp[2] = sp[3] + (r * sp[4]); }
+    if (id == 36) { sp[1] = sp[3] + ((1 - r) * sp[4]); }
+    if (id == 37) { sp[2] = sp[3] + (r * sp[4]); }
+    for (int j = 0; j < N; j++) {
+        double f = 1 - pow(1 - pow(SA[j] / S, sp[1]), sp[2]);
+        double v;
+        if (S >= 0) v = (SA[j] > 0) ? ((SA[j] < S) ? f : 1.) : 0.;
+        else v = (SA[j] > 0) ? f : 0.;
+        Om[j] = v * (mask3 ? 1.0 : 0.0) * m;
+    }
+    for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
+}
+static void sas_exponential(const sas_ctx *c, const double *SA, const double *sp, double m, double *Om)
+{ /* sas.py:163-191 */
+    const int N = c->A + 1;
+    int m51 = (sp[0] == 51), m52 = (sp[0] == 52);
+    double S = np_max(SA, N) * m;
+    double *tmp = (double *)malloc(sizeof(double) * N);
+    for (int j = 0; j < N; j++) tmp[j] = (SA[j] > 0) ? ((SA[j] < S) ? 1 - exp(sp[1] * (-1) * (SA[j] / S)) : 1.) : 0.;
+    for (int j = 0; j < N; j++) Om[j] = (m51 ? tmp[j] : 0.0) * m;
+    for (int j = 0; j < N; j++) Om[j] = (m52 ? tmp[N - 1 - j] : Om[j]) * m;
+    for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
+    free(tmp);
+}
+static void sas_power(const sas_ctx *c, const double *SA, double *sp, double m, double *Om)
+{ /* sas.py:194-240 */
+    const int N = c->A + 1;
+    double id = sp[0];
+    int mask6 = (id == 6 || id == 61 || id == 62);
+    double S = np_max(SA, N) * m;
+    double r = s_rel(S, sp, m);
+    if (id == 61) sp[1] = sp[3] + ((1 - r) * sp[4]);
+    if (id == 62) sp[1] = sp[3] + (r * sp[4]);
+    for (int j = 0; j < N; j++)
+        Om[j] = ((SA[j] > 0) ? ((SA[j] <= S) ? pow(SA[j] / S, sp[1]) : 1.) : 0.) * (mask6 ? 1.0 : 0.0) * m;
+    for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
+}
+
+/* transport.py:343-359 */
+static void calc_SA(int A, const double *sa, double *SA)
+{
+    SA[0] = 0;
+    double acc = 0;
+    for (int j = 0; j < A; j++) { acc += sa[j]; SA[j + 1] = acc; }
+    SA[0] = 0;
+}
+
+/* transport.py:362-509 backward travel-time distribution of one flux */
+static void calc_tt(const sas_ctx *c, const double *SA_in, const double *sa, double flux, const double *sas_params, double m,
+                    double *tt, double *work)
+{
+    const int A = c->A, N = A + 1;
+    double *SAn = work, *san = SAn + N, *TTn = san + A, *TTi = TTn + N, *tti = TTi + N, *ttqi = tti + A, *Om = ttqi + A;
+    double sp[8];
+    memcpy(sp, sas_params, sizeof(sp));
+    memcpy(SAn, SA_in, sizeof(double) * N);
+    memcpy(san, sa, sizeof(double) * A);
+    memset(TTn, 0, sizeof(double) * N);
+    const double h = 1.0 / c->substeps;
+    for (int s = 0; s < c->substeps; s++) {
+        for (int j = 0; j < N; j++) TTi[j] = 0;
+        sas_uniform(c, SAn, sp, m, Om);
+        for (int j = 0; j < N; j++) TTi[j] += Om[j];
+        sas_dirac(c, SAn, sp, m, Om);
+        for (int j = 0; j < N; j++) TTi[j] += Om[j];
+        sas_kumaraswami(c, SAn, sp, m, Om);
+        for (int j = 0; j < N; j++) TTi[j] += Om[j];
+        /* gamma family (id 4) not restated: contributes 0 for every other id */
+        sas_exponential(c, SAn, sp, m, Om);
+        for (int j = 0; j < N; j++) TTi[j] += Om[j];
+        sas_power(c, SAn, sp, m, Om);
+        for (int j = 0; j < N; j++) TTi[j] += Om[j];
+        for (int j = 0; j < A; j++) {
+            double d = TTi[j + 1] - TTi[j];
+            tti[j] = (d >= 0) ? d : 0;
+        }
+        for (int j = 0; j < A; j++) {
+            double q = flux * tti[j] * h;
+            ttqi[j] = (q > san[j]) ? san[j] : q;
+        }
+        for (int j = 0; j < A; j++) tti[j] = (flux * h > 0) ? ttqi[j] / (flux * h) : 0;
+        for (int j = 0; j < A; j++) san[j] += -tti[j] * flux * h;
+        {
+            double acc = 0;
+            for (int j = 0; j < A; j++) { acc += san[j]; SAn[j + 1] = acc; }
+        }
+        {
+            double acc = 0;
+            for (int j = 0; j < A; j++) { acc += tti[j]; TTn[j + 1] += acc; }
+        }
+    }
+    /* aggregate :480-496 */
+    double prev = TTn[0] / c->substeps;
+    for (int j = 0; j < A; j++) {
+        double cur = TTn[j + 1] / c->substeps;
+        tt[j] = cur - prev;
+        prev = cur;
+    }
+    for (int j = 0; j < A; j++) {
+        double q = flux * tt[j];
+        double ttq = (q > sa[j]) ? sa[j] : q;
+        tt[j] = (flux > 0) ? ttq / flux : 0;
+    }
+}
+
+/* flux concentration transport.py:512-535 with calc_mtt :565-580 (isotope branch) */
+static double flux_conc(const sas_ctx *c, const double *msa, const double *tt, double m, double *mtt, double *tmp)
+{
+    const int A = c->A;
+    for (int j = 0; j < A; j++) mtt[j] = ((tt[j] > 0) ? msa[j] : 0) * m;
+    for (int j = 0; j < A; j++) tmp[j] = mtt[j] * tt[j];
+    double st = np_sum(tt, A);
+    double conc = (st > 0) ? np_sum(tmp, A) / st : NAN;
+    conc = (conc != 0) ? conc : NAN;
+    return conc;
+}
+
+/* update_sa transport.py:599-619 */
+static void update_sa(int A, double *sa, const double *tt, double flux, double m)
+{
+    for (int j = 0; j < A; j++) {
+        double v = sa[j] + -flux * tt[j];
+        v = ((v > -1e-5) && (v < 0)) ? 0 : v;
+        sa[j] = v * m;
+    }
+}
+
+/* a SAS-controlled withdrawal from one layer, optionally received by the other layer
+ * (evapotranspiration.py:653-716, :831-895; subsurface_runoff.py:1531-1625, :1753-1815; capillary_rise.py:404-500) */
+static void withdrawal(const sas_ctx *c, double *sa_src, double *msa_src, double *sa_dst, double *msa_dst, double flux,
+                       const double *sp, double m, double *C_flux, double *C_iso_flux, double *tt_out, double *work)
+{
+    const int A = c->A, N = A + 1;
+    double *SA = work, *tt = SA + N, *mtt = tt + A, *tmp = mtt + A, *w2 = tmp + A;
+    calc_SA(A, sa_src, SA);
+    for (int j = 0; j < N; j++) SA[j] = SA[j] * m;
+    calc_tt(c, SA, sa_src, flux, sp, m, tt, w2);
+    for (int j = 0; j < A; j++) tt[j] = tt[j] * m;
+    double conc = flux_conc(c, msa_src, tt, m, mtt, tmp);
+    *C_flux = conc * m;
+    *C_iso_flux = conc_to_delta(c, *C_flux) * m;
+    if (sa_dst) { /* isotope mixing into the receiving layer, bin by bin */
+        for (int j = 0; j < A; j++) {
+            double in = tt[j] * flux;
+            double tot = in + sa_dst[j];
+            double v = (tot > 0) ? msa_dst[j] * (sa_dst[j] / tot) + mtt[j] * (in / tot) : msa_dst[j];
+            msa_dst[j] = v * m;
+        }
+    }
+    update_sa(A, sa_src, tt, flux, m);
+    if (sa_dst)
+        for (int j = 0; j < A; j++) sa_dst[j] += tt[j] * flux * m;
+    for (int j = 0; j < A; j++) msa_src[j] = ((sa_src[j] <= 0) ? 0 : msa_src[j]) * m;
+    if (tt_out) memcpy(tt_out, tt, sizeof(double) * A);
+}
+
+/* infiltration of `inf` with concentration C_in into bin 0 (infiltration.py:2218-2345, :2441-2500) */
+static void inflow(const sas_ctx *c, double *sa, double *msa, double inf, double C_in, double m, double *C_out, double *C_iso_out)
+{
+    const int A = c->A;
+    *C_out = ((inf > 0) ? C_in : 0) * m;
+    *C_iso_out = conc_to_delta(c, *C_out) * m;
+    double tt0 = ((inf > 0) ? 1 : 0) * m;
+    double mtt0 = ((inf > 0) ? C_in : 0) * m;
+    for (int j = 0; j < A; j++) {
+        double ttj = (j == 0) ? tt0 : 0.0, mttj = (j == 0) ? mtt0 : 0.0;
+        double v;
+        if (inf * ttj + sa[j] > 0)
+            v = msa[j] * (sa[j] / (ttj * inf + sa[j])) + mttj * ((ttj * inf) / (inf * ttj + sa[j]));
+        else
+            v = msa[j];
+        msa[j] = v * m;
+    }
+    sa[0] += inf * m;
+}
+
+/* storage concentration transport.py:538-562 */
+static double storage_conc(const sas_ctx *c, const double *sa, const double *msa, double *tmp)
+{
+    const int A = c->A;
+    for (int j = 0; j < A; j++) tmp[j] = msa[j] * sa[j];
+    double s = np_sum(sa, A);
+    return (s > 0) ? np_sum(tmp, A) / s : 0;
+}
+
+/* ageing transport.py:682-739 */
+static void ageing(int A, double *sa, double *msa)
+{
+    double sam1_last = sa[A - 1], msam1_last = msa[A - 1];
+    for (int j = A - 1; j >= 1; j--) sa[j] = sa[j - 1];
+    for (int j = A - 1; j >= 1; j--) msa[j] = msa[j - 1];
+    msa[0] = 0;
+    double tot = sa[A - 1] + sam1_last;
+    double v = (tot > 0) ? msam1_last * (sam1_last / tot) + msa[A - 1] * (sa[A - 1] / tot) : 0;
+    msa[A - 1] = isnan(v) ? 0 : v;
+    sa[0] = 0;
+    sa[A - 1] += sam1_last;
+    sa[A - 1] = (sa[A - 1] < 1e-8) ? 0 : sa[A - 1];
+    msa[A - 1] = (sa[A - 1] <= 0) ? NAN : msa[A - 1];
+}
+
+void sas_oracle_day(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
+                    const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out)
+{
+    sas_ctx ctx = {st->ages, st->substeps, st->VSMOW_conc18O, st->d18O_min, st->d18O_max};
+    const int A = ctx.A;
+#pragma omp parallel
+    {
+        double *work = (double *)malloc(sizeof(double) * (size_t)(16 * (A + 2)));
+        double *tmp = (double *)malloc(sizeof(double) * (size_t)(4 * (A + 2)));
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < C; i++) {
+            const double m = mask[i];
+            double *s_rz = sa_rz + (size_t)i * A, *s_ss = sa_ss + (size_t)i * A;
+            double *ms_rz = msa_rz + (size_t)i * A, *ms_ss = msa_ss + (size_t)i * A;
+#define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
+#define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
+#define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)
+#define TT(p) (tt_out ? tt_out + ((size_t)(p) * (size_t)C + (size_t)i) * A : NULL)
+            const double C_in = F(RSF_C_in);
+            /* infiltration into the root zone: matrix, then preferential flow */
+            inflow(&ctx, s_rz, ms_rz, F(RSF_inf_mat_rz), C_in, m, &O(RSO_C_inf_mat_rz), &O(RSO_C_iso_inf_mat_rz));
+            inflow(&ctx, s_rz, ms_rz, F(RSF_inf_pf_rz), C_in, m, &O(RSO_C_inf_pf_rz), &O(RSO_C_iso_inf_pf_rz));
+            withdrawal(&ctx, s_rz, ms_rz, NULL, NULL, F(RSF_evap_soil), SP(RSP_evap_soil), m, &O(RSO_C_evap_soil), &O(RSO_C_iso_evap_soil), TT(RSP_evap_soil), work);
+            withdrawal(&ctx, s_rz, ms_rz, NULL, NULL, F(RSF_transp), SP(RSP_transp), m, &O(RSO_C_transp), &O(RSO_C_iso_transp), TT(RSP_transp), work);
+            withdrawal(&ctx, s_rz, ms_rz, s_ss, ms_ss, F(RSF_q_rz), SP(RSP_q_rz), m, &O(RSO_C_q_rz), &O(RSO_C_iso_q_rz), TT(RSP_q_rz), work);
+            inflow(&ctx, s_ss, ms_ss, F(RSF_inf_pf_ss), C_in, m, &O(RSO_C_inf_pf_ss), &O(RSO_C_iso_inf_pf_ss));
+            withdrawal(&ctx, s_ss, ms_ss, NULL, NULL, F(RSF_q_ss), SP(RSP_q_ss), m, &O(RSO_C_q_ss), &O(RSO_C_iso_q_ss), TT(RSP_q_ss), work);
+            withdrawal(&ctx, s_ss, ms_ss, s_rz, ms_rz, F(RSF_cpr_rz), SP(RSP_cpr_rz), m, &O(RSO_C_cpr_rz), &O(RSO_C_iso_cpr_rz), TT(RSP_cpr_rz), work);
+            /* storage kernels root_zone.py:189-215, subsoil.py:153-180, soil.py:1036-1092 */
+            for (int j = 0; j < A; j++) s_rz[j] = (s_rz[j] < 1e-8) ? 0 : s_rz[j];
+            O(RSO_C_rz) = storage_conc(&ctx, s_rz, ms_rz, tmp) * m;
+            O(RSO_C_iso_rz) = conc_to_delta(&ctx, O(RSO_C_rz)) * m;
+            for (int j = 0; j < A; j++) s_ss[j] = (s_ss[j] < 1e-8) ? 0 : s_ss[j];
+            O(RSO_C_ss) = storage_conc(&ctx, s_ss, ms_ss, tmp) * m;
+            O(RSO_C_iso_ss) = conc_to_delta(&ctx, O(RSO_C_ss)) * m;
+            {
+                double *sa_s = tmp + (A + 2), *msa_s = sa_s + (A + 2);
+                for (int j = 0; j < A; j++) {
+                    sa_s[j] = s_rz[j] + s_ss[j] * m;
+                    double tot = s_rz[j] + s_ss[j];
+                    double v = (tot > 0) ? ms_rz[j] * (s_rz[j] / tot) + ms_ss[j] * (s_ss[j] / tot) : 0;
+                    msa_s[j] = isnan(v) ? 0 : v;
+                }
+                O(RSO_C_s) = storage_conc(&ctx, sa_s, msa_s, tmp) * m;
+                O(RSO_C_iso_s) = conc_to_delta(&ctx, O(RSO_C_s)) * m;
+            }
+            ageing(A, s_rz, ms_rz);
+            ageing(A, s_ss, ms_ss);
+#undef F
+#undef O
+#undef SP
+#undef TT
+        }
+        free(work);
+        free(tmp);
+    }
+}

@@ -1,0 +1,135 @@
+"""Host-side driver of the offline oxygen-18 StorAge-selection transport: the parts of the reference's
+SVATOXYGEN18 setup that surround the per-cell transport step (benchmarks/SVATOXYGEN18_benchmark.py:150-444,
+roger/models/svat_oxygen18): initial age distributions, daily forcing hand-over with the snow-pack isotope
+mixing of `set_forcing`.  The step itself is delegated to an engine (CUDA in the product, the CPU oracle in tests).
+"""
+import ctypes as C
+
+import numpy as np
+
+FORCING = ["inf_mat_rz", "inf_pf_rz", "inf_pf_ss", "evap_soil", "transp", "q_rz", "q_ss", "cpr_rz", "C_in"]
+PROCESSES = ["evap_soil", "transp", "q_rz", "q_ss", "cpr_rz"]
+OUTPUTS = [
+    "C_inf_mat_rz", "C_inf_pf_rz", "C_inf_pf_ss", "C_evap_soil", "C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz",
+    "C_iso_inf_mat_rz", "C_iso_inf_pf_rz", "C_iso_inf_pf_ss", "C_iso_evap_soil", "C_iso_transp", "C_iso_q_rz", "C_iso_q_ss",
+    "C_iso_cpr_rz", "C_rz", "C_ss", "C_s", "C_iso_rz", "C_iso_ss", "C_iso_s",
+]
+STATE = ["sa_rz", "sa_ss", "msa_rz", "msa_ss"]
+VSMOW_conc18O = 2005.2e-6  # roger/settings.py
+D18O_MIN, D18O_MAX = -20.0, 0.0
+
+
+class SasSettings(C.Structure):
+    _fields_ = [("ages", C.c_int32), ("substeps", C.c_int32), ("VSMOW_conc18O", C.c_double), ("d18O_min", C.c_double),
+                ("d18O_max", C.c_double), ("store_tt", C.c_int32), ("reserved", C.c_int32)]
+
+
+def default_settings(ages, substeps=6, store_tt=False):
+    return SasSettings(int(ages), int(substeps), VSMOW_conc18O, D18O_MIN, D18O_MAX, int(store_tt), 0)
+
+
+def delta_to_conc(delta):
+    """roger/core/transport.py:315-325"""
+    delta = np.asarray(delta, dtype=np.float64)
+    return VSMOW_conc18O * (delta / 1000.0 + 1.0) / (1.0 + (delta / 1000.0 + 1.0) * VSMOW_conc18O)
+
+
+def conc_to_delta(conc):
+    """roger/core/transport.py:328-340"""
+    conc = np.asarray(conc, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        d = 1000.0 * (conc / (VSMOW_conc18O * (1.0 - conc)) - 1.0)
+        return np.where((d < D18O_MIN) | (d > D18O_MAX), np.nan, d)
+
+
+def sas_parameter_block(n_cells, spec):
+    """spec: process -> tuple (id, p1, p2, ...) or (n_cells, 8) array.  Returns (5, n_cells, 8)."""
+    out = np.zeros((len(PROCESSES), n_cells, 8))
+    for k, proc in enumerate(PROCESSES):
+        v = spec[proc]
+        a = np.asarray(v, dtype=np.float64)
+        if a.ndim == 1:
+            out[k, :, : a.size] = a[None, :]
+        else:
+            out[k] = a.reshape(n_cells, 8)
+    return out
+
+
+def initial_age_distribution(S, ages):
+    """benchmarks/SVATOXYGEN18_benchmark.py:172-190: sa[1:] = diff(linspace(0, S, ages)), sa[0] = 0."""
+    S = np.asarray(S, dtype=np.float64).reshape(-1)
+    lin = np.linspace(np.zeros_like(S), S, ages, axis=-1)
+    sa = np.zeros((S.size, ages))
+    sa[:, 1:] = np.diff(lin, axis=-1)
+    return sa
+
+
+class SasModel:
+    def __init__(self, engine_cls, n_cells, ages, daily, sas_spec, d18O_soil=-10.0, mask=None, substeps=6, store_tt=False,
+                 engine_kwargs=None):
+        """daily: dict of (n_cells, ndays + 1) arrays PREC, INF_MAT_RZ, INF_PF_RZ, INF_PF_SS, TRANSP, EVAP_SOIL, CPR_RZ,
+        Q_RZ, Q_SS, S_RZ, S_SS, S_SNOW, C_ISO_IN (index 0 = initial state, as in the reference's SVAT.nc)."""
+        self.C = int(n_cells)
+        self.ages = int(ages)
+        self.daily = {k: np.asarray(v, dtype=np.float64) for k, v in daily.items()}
+        self.settings = default_settings(ages, substeps, store_tt)
+        self.engine = engine_cls(self.C, self.settings, **(engine_kwargs or {}))
+        self.mask = np.ones(self.C) if mask is None else np.asarray(mask, dtype=np.float64)
+        self.sas_params = sas_parameter_block(self.C, sas_spec)
+        self.d18O_soil = d18O_soil
+        self.itt = 0
+        self.C_IN = delta_to_conc(self.daily["C_ISO_IN"])
+        self.C_snow = np.full((self.C, 2), 0.0)  # vs.C_snow[taum1, tau], initial 0 (roger/variables.py)
+        self.S_snow_m1 = self.daily["S_SNOW"][:, 0].copy()
+        self.prec_m1 = np.zeros(self.C)
+        self.C_in = np.zeros(self.C)
+
+    def setup(self):
+        d = self.daily
+        sa_rz = initial_age_distribution(d["S_RZ"][:, 0], self.ages)
+        sa_ss = initial_age_distribution(d["S_SS"][:, 0], self.ages)
+        c0 = float(delta_to_conc(self.d18O_soil))
+        msa = np.full((self.C, self.ages), c0)
+        msa[:, 0] = 0
+        self.engine.set_parameters(self.mask, self.sas_params)
+        self.engine.upload_state("sa_rz", sa_rz)
+        self.engine.upload_state("sa_ss", sa_ss)
+        self.engine.upload_state("msa_rz", msa)
+        self.engine.upload_state("msa_ss", msa.copy())
+
+    def _set_forcing(self):
+        """benchmarks/SVATOXYGEN18_benchmark.py:385-444 (per-cell vectors)."""
+        d, t = self.daily, self.itt
+        prec, S_snow = d["PREC"][:, t], d["S_SNOW"][:, t]
+        C_in = self.C_IN[:, t].copy()
+        cs_m1, cs = self.C_snow[:, 0], self.C_snow[:, 1]
+        with np.errstate(all="ignore"):
+            mixed = (prec / (prec + S_snow)) * C_in + (S_snow / (prec + S_snow)) * cs_m1
+            new = np.where(S_snow > 0, np.where(np.isnan(cs), C_in, mixed), np.nan)
+            new = np.where(S_snow <= 0, np.nan, new)
+        self.C_snow[:, 1] = new
+        C_in = np.where(np.isfinite(cs_m1), cs_m1, np.where(prec > 0, self.C_IN[:, t], 0))
+        self.C_in = C_in
+        f = np.empty((len(FORCING), self.C))
+        f[0], f[1], f[2] = d["INF_MAT_RZ"][:, t], d["INF_PF_RZ"][:, t], d["INF_PF_SS"][:, t]
+        f[3], f[4], f[5], f[6], f[7] = d["EVAP_SOIL"][:, t], d["TRANSP"][:, t], d["Q_RZ"][:, t], d["Q_SS"][:, t], d["CPR_RZ"][:, t]
+        f[8] = C_in
+        return f
+
+    def step(self):
+        """RogerSetup.step, offline-transport branch (roger/roger.py:467-485)."""
+        self.itt += 1
+        f = self._set_forcing()
+        self.engine.step(f)
+        self.C_snow[:, 0] = self.C_snow[:, 1]  # after_timestep
+        return self.itt
+
+    def outputs(self):
+        o = self.engine.download_outputs()
+        return {n: o[k] for k, n in enumerate(OUTPUTS)}
+
+    def state(self, name):
+        return self.engine.download_state(name)
+
+    def tt(self, process):
+        return self.engine.download_tt(process)

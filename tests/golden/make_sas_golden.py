@@ -1,0 +1,115 @@
+"""Generates tests/golden/sas_*.npz: the reference's deterministic oxygen-18 StorAge-selection transport
+(roger/core/transport.py:948-991) run by the UNMODIFIED NumPy backend on seeded synthetic inputs.
+Daily hydrologic forcing comes from an online SVAT run of the (already pinned) CPU oracle.
+
+    python tests/golden/make_sas_golden.py [case ...]
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_harness as rh  # noqa: E402
+from oracle.engine import OracleSvatEngine  # noqa: E402
+from roger_b200 import sas_inputs, synth  # noqa: E402
+from roger_b200.svat import SvatModel  # noqa: E402
+
+CASES = {
+    # power-law SAS of benchmarks/SVATOXYGEN18_benchmark.py:129-138
+    "sas_power": dict(shape=(2, 3), ndays=30, ages=60, doy=100, sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
+    # winter start: snow storage, isotope mixing in the snow pack
+    "sas_power_snow": dict(shape=(2, 2), ndays=25, ages=50, doy=20, sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5)), var_input=True),
+    # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
+    "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
+                         sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
+}
+
+
+def build(name):
+    c = CASES[name]
+    nx, ny = c["shape"]
+    ndays, ages = c["ndays"], c["ages"]
+    forcing = synth.mixed_forcing(ndays + 2, seed=7, start_doy=c["doy"])
+    prim, th_rz, th_ss = synth.heterogeneous_parameters((nx, ny), seed=5, lu_choices=(5, 6, 8, 9, 10))
+    svat = SvatModel(OracleSvatEngine, (nx, ny), forcing, prim, th_rz, th_ss)
+    svat.setup()
+    daily = sas_inputs.daily_fluxes_from_svat(svat, ndays)
+    case = dict(nx=nx, ny=ny, ndays=ndays, ages=ages)
+    for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES):
+        case[k] = daily[k].reshape(nx, ny, ndays + 1)
+    for k in ("S_pwp_rz", "S_pwp_ss"):
+        case[k] = daily[k].reshape(nx, ny)
+    case["S_sat_rz"] = svat.get("S_pwp_rz").reshape(nx, ny) * 0 + 1e4
+    case["S_sat_ss"] = svat.get("S_pwp_ss").reshape(nx, ny) * 0 + 1e4
+    rng = np.random.default_rng(11)
+    ciso = np.full((nx, ny, ndays + 1), -7.0)
+    if c.get("var_input"):
+        ciso = rng.uniform(-12, -5, (nx, ny, ndays + 1))
+    ciso[:, :, 0] = np.nan
+    case["C_ISO_IN"] = ciso
+    sas = {}
+    for proc, tup in c["sas"].items():
+        arr = np.zeros((nx, ny, 8))
+        for j, v in enumerate(tup):
+            arr[:, :, j] = v
+        sas[proc] = arr
+    case["sas"] = sas
+    return case
+
+
+def run(name):
+    case = build(name)
+    Setup = rh.make_o18_setup(case)
+    model = Setup()
+    model.setup()
+    model.warmup()
+    state = model.state
+    vs = state.variables
+    nx, ny, ages = case["nx"], case["ny"], case["ages"]
+    C = nx * ny
+    age_vars = ["sa_rz", "sa_ss", "msa_rz", "msa_ss", "sa_s", "msa_s"]
+    tt_vars = ["tt_evap_soil", "tt_transp", "tt_q_rz", "tt_q_ss", "tt_cpr_rz"]
+    scal_vars = ["C_evap_soil", "C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz", "C_iso_evap_soil", "C_iso_transp", "C_iso_q_rz", "C_iso_q_ss",
+                 "C_iso_cpr_rz", "C_inf_mat_rz", "C_inf_pf_rz", "C_inf_pf_ss", "C_in"]
+    lvl_vars = ["C_rz", "C_ss", "C_s", "C_iso_rz", "C_iso_ss", "C_iso_s", "C_snow"]
+
+    def grab():
+        d = {}
+        for v in age_vars:
+            d[v] = np.asarray(getattr(vs, v))[2:-2, 2:-2, 1, :].reshape(C, -1).copy()
+        for v in tt_vars:
+            d[v] = np.asarray(getattr(vs, v))[2:-2, 2:-2, :].reshape(C, -1).copy()
+        for v in scal_vars:
+            d[v] = np.asarray(getattr(vs, v))[2:-2, 2:-2].reshape(C).copy()
+        for v in lvl_vars:
+            d[v] = np.asarray(getattr(vs, v))[2:-2, 2:-2, 1].reshape(C).copy()
+        return d
+
+    init = grab()
+    recs = []
+    for day in range(case["ndays"]):
+        model.step(state)
+        recs.append(grab())
+    out = dict(nx=nx, ny=ny, ndays=case["ndays"], ages=ages, substeps=6)
+    for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES) + ["C_ISO_IN"]:
+        out["in_" + k] = case[k].reshape(C, -1)
+    for proc, arr in case["sas"].items():
+        out["sas_" + proc] = arr.reshape(C, 8)
+    for k, v in init.items():
+        out["init_" + k] = v
+    for k in recs[0]:
+        out["rec_" + k] = np.stack([r[k] for r in recs])
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "days", case["ndays"], "size %.1f KB" % (os.path.getsize(path) / 1024),
+          "sum sa_rz", float(np.nansum(recs[-1]["sa_rz"])), "C_iso_q_ss", recs[-1]["C_iso_q_ss"][:3])
+
+
+if __name__ == "__main__":
+    for n in sys.argv[1:] or list(CASES):
+        run(n)

@@ -241,3 +241,198 @@ def snapshot(state, names=None):
         elif tuple(dims) == ("timesteps",):
             out[name] = arr.copy()
     return out
+
+
+def make_o18_setup(case):
+    """Offline oxygen-18 StorAge-selection transport, restating benchmarks/SVATOXYGEN18_benchmark.py
+    (the multi-cell variant of roger/models/svat_oxygen18) with in-memory daily forcing.
+
+    case: nx, ny, ndays, ages, daily arrays of shape (nx, ny, ndays + 1): PREC, INF_MAT_RZ, INF_PF_RZ,
+    INF_PF_SS, TRANSP, EVAP_SOIL, CPR_RZ, Q_RZ, Q_SS, S_RZ, S_SS, S_SNOW, C_ISO_IN;
+    (nx, ny) arrays S_pwp_rz, S_pwp_ss, S_sat_rz, S_sat_ss; sas: dict process -> (nx, ny, 8) parameter array.
+    """
+    import_reference()
+    from roger import RogerSetup, roger_routine, roger_kernel, KernelOutput
+    from roger.variables import allocate
+    from roger.core.operators import numpy as npx, update, at
+    from roger.core.transport import delta_to_conc, conc_to_delta
+
+    nx, ny, ndays, ages = case["nx"], case["ny"], case["ndays"], case["ages"]
+
+    class O18Setup(RogerSetup):
+        @roger_routine
+        def set_settings(self, state):
+            s = state.settings
+            s.identifier = "GOLDEN_O18"
+            s.sas_solver = "deterministic"
+            s.sas_solver_substeps = case.get("substeps", 6)
+            s.nx, s.ny = nx, ny
+            s.runlen = 24 * 60 * 60 * ndays
+            s.runlen_warmup = 0
+            s.nitt = ndays + 1
+            s.ages = ages
+            s.nages = ages + 1
+            s.dx = 1
+            s.dy = 1
+            s.x_origin = 0.0
+            s.y_origin = 0.0
+            s.time_origin = "01-01-2022"
+            s.enable_offline_transport = True
+            s.enable_oxygen18 = True
+            s.tm_structure = "power"
+            s.enable_age_statistics = bool(case.get("age_statistics", False))
+
+        @roger_routine
+        def read_data(self, state):
+            pass
+
+        @roger_routine
+        def set_grid(self, state):
+            vs = state.variables
+            settings = state.settings
+            vs.dt_secs = 60 * 60 * 24
+            vs.dt = 60 * 60 * 24 / (60 * 60)
+            vs.ages = update(vs.ages, at[:], npx.arange(1, settings.nages))
+            vs.nages = update(vs.nages, at[:], npx.arange(settings.nages))
+            dx = allocate(state.dimensions, ("x"))
+            dx = update(dx, at[:], settings.dx)
+            dy = allocate(state.dimensions, ("y"))
+            dy = update(dy, at[:], settings.dy)
+            vs.x = update(vs.x, at[3:-2], settings.x_origin + npx.cumsum(dx[3:-2]))
+            vs.y = update(vs.y, at[3:-2], settings.y_origin + npx.cumsum(dy[3:-2]))
+
+        @roger_routine
+        def set_look_up_tables(self, state):
+            pass
+
+        @roger_routine
+        def set_topography(self, state):
+            pass
+
+        @roger_routine
+        def set_parameters_setup(self, state):
+            vs = state.variables
+            for k in ("S_pwp_rz", "S_pwp_ss", "S_sat_rz", "S_sat_ss"):
+                setattr(vs, k, update(getattr(vs, k), at[2:-2, 2:-2], case[k]))
+            for proc, arr in case["sas"].items():
+                name = "sas_params_" + proc
+                setattr(vs, name, update(getattr(vs, name), at[2:-2, 2:-2, :], arr))
+
+        @roger_routine
+        def set_parameters(self, state):
+            pass
+
+        @roger_routine
+        def set_initial_conditions_setup(self, state):
+            vs = state.variables
+            vs.S_snow = update(vs.S_snow, at[2:-2, 2:-2, : vs.taup1], case["S_SNOW"][:, :, 0, None])
+            vs.S_rz = update(vs.S_rz, at[2:-2, 2:-2, : vs.taup1], case["S_RZ"][:, :, 0, None])
+            vs.S_ss = update(vs.S_ss, at[2:-2, 2:-2, : vs.taup1], case["S_SS"][:, :, 0, None])
+            vs.S_s = update(vs.S_s, at[2:-2, 2:-2, : vs.taup1], vs.S_rz[2:-2, 2:-2, : vs.taup1] + vs.S_ss[2:-2, 2:-2, : vs.taup1])
+            vs.S_rz_init = update(vs.S_rz_init, at[2:-2, 2:-2], vs.S_rz[2:-2, 2:-2, 0])
+            vs.S_ss_init = update(vs.S_ss_init, at[2:-2, 2:-2], vs.S_ss[2:-2, 2:-2, 0])
+
+        @roger_routine
+        def set_initial_conditions(self, state):
+            # benchmarks/SVATOXYGEN18_benchmark.py:172-310
+            vs = state.variables
+            settings = state.settings
+            arr0 = allocate(state.dimensions, ("x", "y"))
+            vs.sa_rz = update(vs.sa_rz, at[2:-2, 2:-2, : vs.taup1, 1:],
+                              npx.diff(npx.linspace(arr0[2:-2, 2:-2], vs.S_rz[2:-2, 2:-2, vs.tau], settings.ages, axis=-1), axis=-1)[:, :, npx.newaxis, :])
+            vs.sa_ss = update(vs.sa_ss, at[2:-2, 2:-2, : vs.taup1, 1:],
+                              npx.diff(npx.linspace(arr0[2:-2, 2:-2], vs.S_ss[2:-2, 2:-2, vs.tau], settings.ages, axis=-1), axis=-1)[:, :, npx.newaxis, :])
+            vs.SA_rz = update(vs.SA_rz, at[2:-2, 2:-2, :, 1:], npx.cumsum(vs.sa_rz[2:-2, 2:-2, :, :], axis=-1))
+            vs.SA_ss = update(vs.SA_ss, at[2:-2, 2:-2, :, 1:], npx.cumsum(vs.sa_rz[2:-2, 2:-2, :, :], axis=-1))
+            vs.sa_s = update(vs.sa_s, at[2:-2, 2:-2, :, :], vs.sa_rz[2:-2, 2:-2, :, :] + vs.sa_ss[2:-2, 2:-2, :, :])
+            vs.SA_s = update(vs.SA_s, at[2:-2, 2:-2, :, 1:], npx.cumsum(vs.sa_s[2:-2, 2:-2, :, :], axis=-1))
+            vs.C_iso_snow = update(vs.C_iso_snow, at[2:-2, 2:-2, : vs.taup1], npx.nan)
+            vs.C_iso_rz = update(vs.C_iso_rz, at[2:-2, 2:-2, : vs.taup1], case.get("d18O_soil", -10))
+            vs.C_iso_ss = update(vs.C_iso_ss, at[2:-2, 2:-2, : vs.taup1], case.get("d18O_soil", -10))
+            vs.C_rz = update(vs.C_rz, at[2:-2, 2:-2, : vs.taup1], delta_to_conc(state, vs.C_iso_rz[2:-2, 2:-2, vs.tau, npx.newaxis]))
+            vs.msa_rz = update(vs.msa_rz, at[2:-2, 2:-2, : vs.taup1, :], vs.C_rz[2:-2, 2:-2, : vs.taup1, npx.newaxis])
+            vs.msa_rz = update(vs.msa_rz, at[2:-2, 2:-2, : vs.taup1, 0], 0)
+            vs.C_ss = update(vs.C_ss, at[2:-2, 2:-2, : vs.taup1], delta_to_conc(state, vs.C_iso_ss[2:-2, 2:-2, vs.tau, npx.newaxis]))
+            vs.msa_ss = update(vs.msa_ss, at[2:-2, 2:-2, : vs.taup1, :], vs.C_ss[2:-2, 2:-2, : vs.taup1, npx.newaxis])
+            vs.msa_ss = update(vs.msa_ss, at[2:-2, 2:-2, : vs.taup1, 0], 0)
+
+        @roger_routine
+        def set_boundary_conditions_setup(self, state):
+            pass
+
+        @roger_routine
+        def set_boundary_conditions(self, state):
+            pass
+
+        @roger_routine
+        def set_forcing_setup(self, state):
+            vs = state.variables
+            for big, key in (("PREC_DIST_DAILY", "PREC"), ("INF_MAT_RZ", "INF_MAT_RZ"), ("INF_PF_RZ", "INF_PF_RZ"),
+                             ("INF_PF_SS", "INF_PF_SS"), ("TRANSP", "TRANSP"), ("EVAP_SOIL", "EVAP_SOIL"), ("CPR_RZ", "CPR_RZ"),
+                             ("Q_RZ", "Q_RZ"), ("Q_SS", "Q_SS"), ("S_RZ", "S_RZ"), ("S_SS", "S_SS"), ("S_SNOW", "S_SNOW"),
+                             ("C_ISO_IN", "C_ISO_IN")):
+                setattr(vs, big, update(getattr(vs, big), at[2:-2, 2:-2, :], case[key]))
+            vs.S_S = update(vs.S_S, at[2:-2, 2:-2, :], vs.S_RZ[2:-2, 2:-2, :] + vs.S_SS[2:-2, 2:-2, :])
+            vs.C_IN = update(vs.C_IN, at[2:-2, 2:-2, :], delta_to_conc(state, vs.C_ISO_IN)[2:-2, 2:-2, :])
+
+        @roger_routine
+        def set_forcing(self, state):
+            # benchmarks/SVATOXYGEN18_benchmark.py:385-444
+            vs = state.variables
+            vs.prec = update(vs.prec, at[2:-2, 2:-2, vs.tau], vs.PREC_DIST_DAILY[2:-2, 2:-2, vs.itt])
+            vs.inf_mat_rz = update(vs.inf_mat_rz, at[2:-2, 2:-2], vs.INF_MAT_RZ[2:-2, 2:-2, vs.itt])
+            vs.inf_pf_rz = update(vs.inf_pf_rz, at[2:-2, 2:-2], vs.INF_PF_RZ[2:-2, 2:-2, vs.itt])
+            vs.inf_pf_ss = update(vs.inf_pf_ss, at[2:-2, 2:-2], vs.INF_PF_SS[2:-2, 2:-2, vs.itt])
+            vs.transp = update(vs.transp, at[2:-2, 2:-2], vs.TRANSP[2:-2, 2:-2, vs.itt])
+            vs.evap_soil = update(vs.evap_soil, at[2:-2, 2:-2], vs.EVAP_SOIL[2:-2, 2:-2, vs.itt])
+            vs.cpr_rz = update(vs.cpr_rz, at[2:-2, 2:-2], vs.CPR_RZ[2:-2, 2:-2, vs.itt])
+            vs.q_rz = update(vs.q_rz, at[2:-2, 2:-2], vs.Q_RZ[2:-2, 2:-2, vs.itt])
+            vs.q_ss = update(vs.q_ss, at[2:-2, 2:-2], vs.Q_SS[2:-2, 2:-2, vs.itt])
+            vs.S_rz = update(vs.S_rz, at[2:-2, 2:-2, vs.tau], vs.S_RZ[2:-2, 2:-2, vs.itt])
+            vs.S_ss = update(vs.S_ss, at[2:-2, 2:-2, vs.tau], vs.S_SS[2:-2, 2:-2, vs.itt])
+            vs.S_s = update(vs.S_s, at[2:-2, 2:-2, vs.tau], vs.S_rz[2:-2, 2:-2, vs.tau] + vs.S_ss[2:-2, 2:-2, vs.tau])
+            vs.S_snow = update(vs.S_snow, at[2:-2, 2:-2, vs.tau], vs.S_SNOW[2:-2, 2:-2, vs.itt])
+            vs.C_in = update(vs.C_in, at[2:-2, 2:-2], vs.C_IN[2:-2, 2:-2, vs.itt])
+            vs.C_snow = update(
+                vs.C_snow, at[2:-2, 2:-2, vs.tau],
+                npx.where(
+                    vs.S_snow[2:-2, 2:-2, vs.tau] > 0,
+                    npx.where(
+                        npx.isnan(vs.C_snow[2:-2, 2:-2, vs.tau]),
+                        vs.C_in[2:-2, 2:-2],
+                        (vs.prec[2:-2, 2:-2, vs.tau] / (vs.prec[2:-2, 2:-2, vs.tau] + vs.S_snow[2:-2, 2:-2, vs.tau])) * vs.C_in[2:-2, 2:-2]
+                        + (vs.S_snow[2:-2, 2:-2, vs.tau] / (vs.prec[2:-2, 2:-2, vs.tau] + vs.S_snow[2:-2, 2:-2, vs.tau])) * vs.C_snow[2:-2, 2:-2, vs.taum1],
+                    ),
+                    npx.nan,
+                ),
+            )
+            vs.C_snow = update(vs.C_snow, at[2:-2, 2:-2, vs.tau], npx.where(vs.S_snow[2:-2, 2:-2, vs.tau] <= 0, npx.nan, vs.C_snow[2:-2, 2:-2, vs.tau]))
+            vs.C_iso_snow = update(vs.C_iso_snow, at[2:-2, 2:-2, vs.tau], conc_to_delta(state, vs.C_snow[2:-2, 2:-2, vs.tau]))
+            vs.C_in = update(
+                vs.C_in, at[2:-2, 2:-2],
+                npx.where(npx.isfinite(vs.C_snow[2:-2, 2:-2, vs.taum1]), vs.C_snow[2:-2, 2:-2, vs.taum1],
+                          npx.where(vs.prec[2:-2, 2:-2, vs.tau] > 0, vs.C_IN[2:-2, 2:-2, vs.itt], 0)),
+            )
+            vs.C_iso_in = update(vs.C_iso_in, at[2:-2, 2:-2], conc_to_delta(state, vs.C_in[2:-2, 2:-2]))
+
+        @roger_routine
+        def set_diagnostics(self, state):
+            pass
+
+        @roger_routine
+        def after_timestep(self, state):
+            vs = state.variables
+            vs.update(after_timestep_kernel(state))
+
+    @roger_kernel
+    def after_timestep_kernel(state):
+        vs = state.variables
+        out = {}
+        for name in ("S_snow", "C_snow", "prec"):  # benchmarks/SVATOXYGEN18_benchmark.py:453-480
+            arr = getattr(vs, name)
+            arr = update(arr, at[2:-2, 2:-2, vs.taum1], arr[2:-2, 2:-2, vs.tau])
+            setattr(vs, name, arr)
+            out[name] = arr
+        return KernelOutput(**out)
+
+    return O18Setup
