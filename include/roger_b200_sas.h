@@ -49,12 +49,21 @@ typedef struct roger_sas_settings {
 
 typedef struct roger_sas roger_sas; /* opaque handle */
 
+#define ROGER_ENOTSUP 95 /* a SAS function id this backend does not implement (gamma = 4, reversed exponential = 52) */
+
 int roger_sas_create(roger_sas **out, int64_t n_cells, const roger_sas_settings *settings, int device);
 void roger_sas_destroy(roger_sas *h);
 /* age-ranked state: which = 0 sa_rz, 1 sa_ss, 2 msa_rz, 3 msa_ss; host buffers of n_cells*ages doubles */
 int roger_sas_upload_state(roger_sas *h, int which, const double *host);
 int roger_sas_download_state(roger_sas *h, int which, double *host);
+/* raw device address of the age-major array (A planes of n_cells doubles; age bin j is plane (base + j) mod A,
+ * base = roger_sas_age_base()) */
 uint64_t roger_sas_state_ptr(roger_sas *h, int which);
+int roger_sas_age_base(roger_sas *h);
+/* initial condition of the benchmark / model setups computed on the device (benchmarks/SVATOXYGEN18_benchmark.py:172-218,
+ * roger/models/svat_oxygen18 set_initial_conditions): sa[1:] = diff(linspace(0, S, ages)), sa[0] = 0, msa = conc0, msa[0] = 0.
+ * S_rz, S_ss: n_cells doubles (host). */
+int roger_sas_init_linear(roger_sas *h, const double *S_rz, const double *S_ss, double conc0);
 /* maskCatch (n_cells) and SAS parameters (RSP_COUNT * n_cells * 8), roger/variables.py:4275 */
 int roger_sas_set_parameters(roger_sas *h, const double *mask_catch, const double *sas_params);
 /* one daily step.  forcing: RSF_COUNT planes of n_cells doubles (host memory). */
@@ -65,6 +74,10 @@ int roger_sas_step_device(roger_sas *h, uint64_t forcing);
 int roger_sas_download_outputs(roger_sas *h, double *host);
 /* travel-time distribution of process p from the last step (needs settings.store_tt): n_cells*ages doubles */
 int roger_sas_download_tt(roger_sas *h, int process, double *host);
+/* out[i] = roger_pow(x[i], y[i]) -- or roger_exp(x[i]) when y is NULL -- evaluated by the device build of
+ * roger_b200/csrc/roger_pow.h (host pointers, n doubles each): the parity tests use it to prove that the device and
+ * the host evaluate the shared power function to identical bits. */
+int roger_pow_device(const double *x, const double *y, double *out, int64_t n, int device);
 int roger_sas_synchronize(roger_sas *h);
 int roger_sas_last_timing(roger_sas *h, double *kernel_ms, int64_t *launches);
 

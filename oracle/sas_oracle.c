@@ -12,6 +12,31 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../include/roger_b200_sas.h"
+#include "../roger_b200/csrc/roger_pow.h"
+
+/* Which pow the SAS functions call.  0: the C library's pow -- what NumPy's float64 `power` loop calls when its
+ * AVX512 SVML dispatch is off; the mode the oracle is PINNED in against the reference fixtures.  1: roger_pow()
+ * (roger_b200/csrc/roger_pow.h), the fixed IEEE operation sequence the CUDA kernels also evaluate, so that GPU
+ * results can be compared with this oracle bit for bit (the two modes differ by at most 1 ulp per call). */
+ROGER_POW_DEFINE_HOST_TABLES(static const)
+static int g_pow_mode = 0;
+void sas_oracle_set_pow(int mode) { g_pow_mode = mode; }
+double roger_pow_host(double x, double y)
+{
+    const roger_pow_tables t = {roger_pow_log_tab_h, roger_pow_exp_tab_h};
+    return roger_pow(x, y, t);
+}
+void roger_pow_host_array(const double *x, const double *y, double *out, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = roger_pow_host(x[i], y[i]);
+}
+static double sas_pow(double x, double y) { return g_pow_mode ? roger_pow_host(x, y) : pow(x, y); }
+double roger_exp_host(double x)
+{
+    const roger_pow_tables t = {roger_pow_log_tab_h, roger_pow_exp_tab_h};
+    return roger_exp(x, t);
+}
+static double sas_exp(double x) { return g_pow_mode ? roger_exp_host(x) : exp(x); }
 
 /* numpy add.reduce over a contiguous axis (pairwise, 8 lanes, blocks of 128) */
 static double pw_sum(const double *a, int n)
@@ -99,7 +124,7 @@ static void sas_kumaraswami(const sas_ctx *c, const double *SA, double *sp, doub
     if (id == 36) { sp[1] = sp[3] + ((1 - r) * sp[4]); }
     if (id == 37) { sp[2] = sp[3] + (r * sp[4]); }
     for (int j = 0; j < N; j++) {
-        double f = 1 - pow(1 - pow(SA[j] / S, sp[1]), sp[2]);
+        double f = 1 - sas_pow(1 - sas_pow(SA[j] / S, sp[1]), sp[2]);
         double v;
         if (S >= 0) v = (SA[j] > 0) ? ((SA[j] < S) ? f : 1.) : 0.;
         else v = (SA[j] > 0) ? f : 0.;
@@ -113,7 +138,7 @@ static void sas_exponential(const sas_ctx *c, const double *SA, const double *sp
     int m51 = (sp[0] == 51), m52 = (sp[0] == 52);
     double S = np_max(SA, N) * m;
     double *tmp = (double *)malloc(sizeof(double) * N);
-    for (int j = 0; j < N; j++) tmp[j] = (SA[j] > 0) ? ((SA[j] < S) ? 1 - exp(sp[1] * (-1) * (SA[j] / S)) : 1.) : 0.;
+    for (int j = 0; j < N; j++) tmp[j] = (SA[j] > 0) ? ((SA[j] < S) ? 1 - sas_exp(sp[1] * (-1) * (SA[j] / S)) : 1.) : 0.;
     for (int j = 0; j < N; j++) Om[j] = (m51 ? tmp[j] : 0.0) * m;
     for (int j = 0; j < N; j++) Om[j] = (m52 ? tmp[N - 1 - j] : Om[j]) * m;
     for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
@@ -129,7 +154,7 @@ static void sas_power(const sas_ctx *c, const double *SA, double *sp, double m, 
     if (id == 61) sp[1] = sp[3] + ((1 - r) * sp[4]);
     if (id == 62) sp[1] = sp[3] + (r * sp[4]);
     for (int j = 0; j < N; j++)
-        Om[j] = ((SA[j] > 0) ? ((SA[j] <= S) ? pow(SA[j] / S, sp[1]) : 1.) : 0.) * (mask6 ? 1.0 : 0.0) * m;
+        Om[j] = ((SA[j] > 0) ? ((SA[j] <= S) ? sas_pow(SA[j] / S, sp[1]) : 1.) : 0.) * (mask6 ? 1.0 : 0.0) * m;
     for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
 }
 

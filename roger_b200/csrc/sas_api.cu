@@ -1,0 +1,428 @@
+// sas_api.cu -- kernels and C ABI of the offline oxygen-18 StorAge-selection transport step
+// (include/roger_b200_sas.h).  sm_100a only, no CPU fallback.
+//
+// HBM layout: every age-ranked array (sa_rz, sa_ss, msa_rz, msa_ss, and the two scratch arrays of the sub-step
+// solver) is AGE-MAJOR: A planes of C doubles, cell index fastest; age bin j of the state arrays lives in plane
+// (base + j) mod A so that the daily ageing shift is a decrement of `base` (sas_device.cuh).  The C ABI speaks
+// the reference's (cell, age) order; upload / download transpose through a bounded staging buffer.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "sas_device.cuh"
+
+using namespace rsas;
+
+#define ROGER_EINVAL 22
+#define ROGER_ENODEV 19
+#define ROGER_ECUDA 5
+#define ROGER_ENOTSUP 95
+
+extern "C" const char* roger_last_error(void);
+namespace roger { int set_last_error(int code, const std::string& msg); }
+static int fail(int code, const std::string& msg) { return roger::set_last_error(code, msg); }
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ROGER_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+__device__ const roger_pow_log_entry d_pow_log_tab[ROGER_POW_N] = {ROGER_POW_LOG_TABLE};
+__device__ const roger_pow_exp_entry d_pow_exp_tab[ROGER_POW_N] = {ROGER_POW_EXP_TABLE};
+
+#ifndef ROGER_SAS_BLOCK
+#define ROGER_SAS_BLOCK 128
+#endif
+
+// One daily transport step of every cell (transport.py:948-991), one thread per cell.
+__global__ void __launch_bounds__(ROGER_SAS_BLOCK)
+k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
+          const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out) {
+    __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
+    __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
+    for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
+        s_log[k] = d_pow_log_tab[k];
+        s_exp[k] = d_pow_exp_tab[k];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t C = P.C;
+    if (i >= C) return;
+    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    const double m = mask[i];
+#define F(k) forcing[(int64_t)(k) * C + i]
+#define O(k) out[(int64_t)(k) * C + i]
+#define SP(p) (sas_params + (int64_t)(p) * 8 * C + i)
+    const double C_in = F(RSF_C_in);
+    double a, b;
+    inflow(cx, 0, F(RSF_inf_mat_rz), C_in, m, &a, &b);
+    O(RSO_C_inf_mat_rz) = a; O(RSO_C_iso_inf_mat_rz) = b;
+    inflow(cx, 0, F(RSF_inf_pf_rz), C_in, m, &a, &b);
+    O(RSO_C_inf_pf_rz) = a; O(RSO_C_iso_inf_pf_rz) = b;
+    withdrawal(cx, 0, -1, F(RSF_evap_soil), SP(RSP_evap_soil), C, m, &a, &b, RSP_evap_soil);
+    O(RSO_C_evap_soil) = a; O(RSO_C_iso_evap_soil) = b;
+    withdrawal(cx, 0, -1, F(RSF_transp), SP(RSP_transp), C, m, &a, &b, RSP_transp);
+    O(RSO_C_transp) = a; O(RSO_C_iso_transp) = b;
+    withdrawal(cx, 0, 1, F(RSF_q_rz), SP(RSP_q_rz), C, m, &a, &b, RSP_q_rz);
+    O(RSO_C_q_rz) = a; O(RSO_C_iso_q_rz) = b;
+    inflow(cx, 1, F(RSF_inf_pf_ss), C_in, m, &a, &b);
+    O(RSO_C_inf_pf_ss) = a; O(RSO_C_iso_inf_pf_ss) = b;
+    withdrawal(cx, 1, -1, F(RSF_q_ss), SP(RSP_q_ss), C, m, &a, &b, RSP_q_ss);
+    O(RSO_C_q_ss) = a; O(RSO_C_iso_q_ss) = b;
+    withdrawal(cx, 1, 0, F(RSF_cpr_rz), SP(RSP_cpr_rz), C, m, &a, &b, RSP_cpr_rz);
+    O(RSO_C_cpr_rz) = a; O(RSO_C_iso_cpr_rz) = b;
+    storage_and_ageing(cx, m, out, C);
+#undef F
+#undef O
+#undef SP
+}
+
+// (cells, A) row-major staging block <-> age-major planes, 32 x 32 tiles through shared memory
+__global__ void k_stage_to_planes(const double* __restrict__ stage, double* __restrict__ planes, int64_t C, int A, int base,
+                                  int64_t cell0, int ncell) {
+    __shared__ double tile[32][33];
+    const int jt = blockIdx.x * 32, ct = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = ct + r, j = jt + threadIdx.x;
+        if (c < ncell && j < A) tile[r][threadIdx.x] = stage[(int64_t)c * A + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = jt + r, c = ct + threadIdx.x;
+        if (c < ncell && j < A) {
+            int p = base + j;
+            if (p >= A) p -= A;
+            planes[(int64_t)p * C + cell0 + c] = tile[threadIdx.x][r];
+        }
+    }
+}
+__global__ void k_planes_to_stage(double* __restrict__ stage, const double* __restrict__ planes, int64_t C, int A, int base,
+                                  int64_t cell0, int ncell) {
+    __shared__ double tile[32][33];
+    const int jt = blockIdx.x * 32, ct = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = jt + r, c = ct + threadIdx.x;
+        if (c < ncell && j < A) {
+            int p = base + j;
+            if (p >= A) p -= A;
+            tile[r][threadIdx.x] = planes[(int64_t)p * C + cell0 + c];
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = ct + r, j = jt + threadIdx.x;
+        if (c < ncell && j < A) stage[(int64_t)c * A + j] = tile[threadIdx.x][r];
+    }
+}
+
+// benchmarks/SVATOXYGEN18_benchmark.py:172-218: sa[1:] = diff(linspace(0, S, ages)), sa[0] = 0; msa = c0, msa[0] = 0
+__global__ void k_init_linear(Planes pl, SasParams P, const double* __restrict__ S_rz, const double* __restrict__ S_ss, double c0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.C) return;
+    const int A = P.A;
+    for (int L = 0; L < 2; L++) {
+        const double S = (L == 0) ? S_rz[i] : S_ss[i];
+        const double step = (S - 0.0) / (double)(A - 1);  // numpy.linspace: step = delta / div
+        Cursor c(P, i);
+        double prev = 0.0;
+        for (int j = 0; j < A; j++, c.next()) {
+            double y = (double)j * step + 0.0;
+            if (j == A - 1) y = S;  // endpoint is set exactly
+            pl.sa[L][c.off] = (j == 0) ? 0.0 : y - prev;
+            pl.msa[L][c.off] = (j == 0) ? 0.0 : c0;
+            prev = y;
+        }
+    }
+}
+
+__global__ void k_pow_array(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out, int64_t n, int use_exp) {
+    __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
+    __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
+    for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
+        s_log[k] = d_pow_log_tab[k];
+        s_exp[k] = d_pow_exp_tab[k];
+    }
+    __syncthreads();
+    const roger_pow_tables tabs{s_log, s_exp};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = use_exp ? roger_exp(x[i], tabs) : roger_pow(x[i], y[i], tabs);
+}
+
+// ================================================================================================
+struct roger_sas {
+    int64_t C = 0;
+    int device = 0;
+    roger_sas_settings st{};
+    int base = 0;
+    double* d_state[4] = {nullptr, nullptr, nullptr, nullptr};  // sa_rz, sa_ss, msa_rz, msa_ss
+    double* d_san = nullptr;
+    double* d_TTn = nullptr;
+    double* d_tt = nullptr;
+    double* d_forcing = nullptr;
+    double* d_out = nullptr;
+    double* d_mask = nullptr;
+    double* d_params = nullptr;
+    double* d_stage = nullptr;
+    int64_t stage_cells = 0;
+    PwPlan* d_plan = nullptr;
+    bool have_params = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_kernel_ms = 0;
+    int64_t last_launches = 0;
+
+    SasParams params() const {
+        SasParams P;
+        P.A = st.ages; P.substeps = st.substeps; P.store_tt = st.store_tt; P.base = base;
+        P.vsmow = st.VSMOW_conc18O; P.dmin = st.d18O_min; P.dmax = st.d18O_max; P.C = C;
+        return P;
+    }
+    Planes planes() const {
+        Planes pl;
+        pl.sa[0] = d_state[0]; pl.sa[1] = d_state[1]; pl.msa[0] = d_state[2]; pl.msa[1] = d_state[3];
+        pl.san = d_san; pl.TTn = d_TTn; pl.tt = d_tt;
+        return pl;
+    }
+};
+
+static void plan_rec(int n, std::vector<int>& len, std::vector<int>& merges) {
+    if (n <= 128) {  // numpy PW_BLOCKSIZE
+        len.push_back(n);
+        merges.push_back(0);
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    plan_rec(n2, len, merges);
+    plan_rec(n - n2, len, merges);
+    merges.back() += 1;
+}
+
+static int transfer_state(roger_sas* h, double* planes, int base, double* host, bool upload) {
+    const int A = h->st.ages;
+    dim3 tb(32, 8);
+    for (int64_t c0 = 0; c0 < h->C; c0 += h->stage_cells) {
+        const int n = (int)std::min<int64_t>(h->stage_cells, h->C - c0);
+        dim3 grid((A + 31) / 32, (n + 31) / 32);
+        const size_t bytes = sizeof(double) * (size_t)n * (size_t)A;
+        if (upload) {
+            CU(cudaMemcpyAsync(h->d_stage, host + (size_t)c0 * A, bytes, cudaMemcpyHostToDevice, h->stream));
+            k_stage_to_planes<<<grid, tb, 0, h->stream>>>(h->d_stage, planes, h->C, A, base, c0, n);
+        } else {
+            k_planes_to_stage<<<grid, tb, 0, h->stream>>>(h->d_stage, planes, h->C, A, base, c0, n);
+            CU(cudaMemcpyAsync(host + (size_t)c0 * A, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+extern "C" {
+
+int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings* settings, int device) {
+    if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_sas_create: bad argument");
+    if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ROGER_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this backend has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(ROGER_EINVAL, "roger_sas_create: bad device index");
+    CU(cudaSetDevice(device));
+    std::vector<int> len, merges;
+    plan_rec(settings->ages, len, merges);
+    if ((int)len.size() > kMaxLeaves) return fail(ROGER_EINVAL, "roger_sas_create: too many age bins for the summation plan");
+    roger_sas* h = new roger_sas();
+    h->C = n_cells;
+    h->device = device;
+    h->st = *settings;
+    const size_t arr = sizeof(double) * (size_t)n_cells * (size_t)settings->ages;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; k++) {
+        CU(cudaMalloc(&h->d_state[k], arr));
+        CU(cudaMemsetAsync(h->d_state[k], 0, arr, h->stream));
+    }
+    CU(cudaMalloc(&h->d_san, arr));
+    CU(cudaMalloc(&h->d_TTn, arr));
+    if (settings->store_tt) {
+        CU(cudaMalloc(&h->d_tt, arr * RSP_COUNT));
+        CU(cudaMemsetAsync(h->d_tt, 0, arr * RSP_COUNT, h->stream));
+    }
+    CU(cudaMalloc(&h->d_forcing, sizeof(double) * RSF_COUNT * (size_t)n_cells));
+    CU(cudaMalloc(&h->d_out, sizeof(double) * RSO_COUNT * (size_t)n_cells));
+    CU(cudaMemsetAsync(h->d_out, 0, sizeof(double) * RSO_COUNT * (size_t)n_cells, h->stream));
+    CU(cudaMalloc(&h->d_mask, sizeof(double) * (size_t)n_cells));
+    CU(cudaMalloc(&h->d_params, sizeof(double) * RSP_COUNT * 8 * (size_t)n_cells));
+    const int64_t budget = (int64_t)128 << 20;  // staging buffer bound
+    h->stage_cells = std::max<int64_t>(32, std::min<int64_t>(n_cells, budget / (8 * (int64_t)settings->ages)));
+    CU(cudaMalloc(&h->d_stage, sizeof(double) * (size_t)h->stage_cells * (size_t)settings->ages));
+    PwPlan plan{};
+    plan.n_leaves = (int)len.size();
+    for (size_t l = 0; l < len.size(); l++) { plan.len[l] = (short)len[l]; plan.merges[l] = (unsigned char)merges[l]; }
+    CU(cudaMalloc(&h->d_plan, sizeof(PwPlan)));
+    CU(cudaMemcpyAsync(h->d_plan, &plan, sizeof(PwPlan), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+void roger_sas_destroy(roger_sas* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto p : h->d_state) cudaFree(p);
+    cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
+    cudaFree(h->d_mask); cudaFree(h->d_params); cudaFree(h->d_stage); cudaFree(h->d_plan);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int roger_sas_upload_state(roger_sas* h, int which, const double* host) {
+    if (!h || !host || which < 0 || which > 3) return fail(ROGER_EINVAL, "roger_sas_upload_state: bad argument");
+    CU(cudaSetDevice(h->device));
+    return transfer_state(h, h->d_state[which], h->base, const_cast<double*>(host), true);
+}
+
+int roger_sas_download_state(roger_sas* h, int which, double* host) {
+    if (!h || !host || which < 0 || which > 3) return fail(ROGER_EINVAL, "roger_sas_download_state: bad argument");
+    CU(cudaSetDevice(h->device));
+    return transfer_state(h, h->d_state[which], h->base, host, false);
+}
+
+uint64_t roger_sas_state_ptr(roger_sas* h, int which) {
+    if (!h || which < 0 || which > 3) return 0;
+    return (uint64_t)(uintptr_t)h->d_state[which];
+}
+
+int roger_sas_age_base(roger_sas* h) { return h ? h->base : -1; }
+
+int roger_sas_init_linear(roger_sas* h, const double* S_rz, const double* S_ss, double conc0) {
+    if (!h || !S_rz || !S_ss) return fail(ROGER_EINVAL, "roger_sas_init_linear: bad argument");
+    CU(cudaSetDevice(h->device));
+    // the two storage vectors travel through the forcing buffer (2 planes of C doubles)
+    const size_t plane = sizeof(double) * (size_t)h->C;
+    CU(cudaMemcpyAsync(h->d_forcing, S_rz, plane, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_forcing + h->C, S_ss, plane, cudaMemcpyHostToDevice, h->stream));
+    h->base = 0;
+    k_init_linear<<<(int)((h->C + 127) / 128), 128, 0, h->stream>>>(h->planes(), h->params(), h->d_forcing, h->d_forcing + h->C, conc0);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int roger_sas_set_parameters(roger_sas* h, const double* mask_catch, const double* sas_params) {
+    if (!h || !mask_catch || !sas_params) return fail(ROGER_EINVAL, "roger_sas_set_parameters: bad argument");
+    CU(cudaSetDevice(h->device));
+    const int64_t C = h->C;
+    std::vector<double> t((size_t)RSP_COUNT * 8 * (size_t)C);
+    for (int p = 0; p < RSP_COUNT; p++)
+        for (int64_t i = 0; i < C; i++) {
+            const double* row = sas_params + ((size_t)p * (size_t)C + (size_t)i) * 8;
+            const double id = row[0];
+            const bool ok = id == 0 || id == 1 || id == 2 || id == 3 || (id >= 31 && id <= 37 && id == std::floor(id)) || id == 51 ||
+                            id == 6 || id == 61 || id == 62;
+            if (!ok) {
+                char buf[320];
+                snprintf(buf, sizeof buf, "roger_sas_set_parameters: SAS function id %g (process %d, cell %lld) is not implemented on the device "
+                         "(gamma = 4 and time-reversed exponential = 52 are outside this backend)", id, p, (long long)i);
+                return fail(ROGER_ENOTSUP, buf);
+            }
+            for (int k = 0; k < 8; k++) t[((size_t)p * 8 + (size_t)k) * (size_t)C + (size_t)i] = row[k];
+        }
+    CU(cudaMemcpyAsync(h->d_params, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_mask, mask_catch, sizeof(double) * (size_t)C, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_params = true;
+    return 0;
+}
+
+static int step_common(roger_sas* h, const double* d_forcing) {
+    if (!h->have_params) return fail(ROGER_EINVAL, "roger_sas_step: roger_sas_set_parameters has not been called");
+    CU(cudaEventRecord(h->ev0, h->stream));
+    const int threads = ROGER_SAS_BLOCK;
+    const int blocks = (int)((h->C + threads - 1) / threads);
+    k_sas_day<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->base = (h->base == 0) ? h->st.ages - 1 : h->base - 1;  // ageing: the plane ring rotates by one bin
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_kernel_ms = ms;
+    h->last_launches = 1;
+    return 0;
+}
+
+int roger_sas_step(roger_sas* h, const double* forcing) {
+    if (!h || !forcing) return fail(ROGER_EINVAL, "roger_sas_step: bad argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->d_forcing, forcing, sizeof(double) * RSF_COUNT * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+    return step_common(h, h->d_forcing);
+}
+
+int roger_sas_step_device(roger_sas* h, uint64_t forcing) {
+    if (!h || !forcing) return fail(ROGER_EINVAL, "roger_sas_step_device: bad argument");
+    CU(cudaSetDevice(h->device));
+    return step_common(h, (const double*)(uintptr_t)forcing);
+}
+
+int roger_sas_download_outputs(roger_sas* h, double* host) {
+    if (!h || !host) return fail(ROGER_EINVAL, "roger_sas_download_outputs: bad argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(host, h->d_out, sizeof(double) * RSO_COUNT * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int roger_sas_download_tt(roger_sas* h, int process, double* host) {
+    if (!h || !host || process < 0 || process >= RSP_COUNT) return fail(ROGER_EINVAL, "roger_sas_download_tt: bad argument");
+    if (!h->d_tt) return fail(ROGER_EINVAL, "roger_sas_download_tt: handle was created without settings.store_tt");
+    CU(cudaSetDevice(h->device));
+    return transfer_state(h, h->d_tt + (size_t)process * (size_t)h->st.ages * (size_t)h->C, 0, host, false);
+}
+
+// out[i] = roger_pow(x[i], y[i]) (or roger_exp(x[i]) when y is NULL) evaluated on the device: lets the tests prove
+// that the device and host builds of roger_pow.h return identical bits.  Host pointers.
+int roger_pow_device(const double* x, const double* y, double* out, int64_t n, int device) {
+    if (!x || !out || n <= 0) return fail(ROGER_EINVAL, "roger_pow_device: bad argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(ROGER_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    CU(cudaSetDevice(device));
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    CU(cudaMalloc(&dx, bytes));
+    CU(cudaMalloc(&dout, bytes));
+    CU(cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice));
+    if (y) {
+        CU(cudaMalloc(&dy, bytes));
+        CU(cudaMemcpy(dy, y, bytes, cudaMemcpyHostToDevice));
+    }
+    k_pow_array<<<148 * 8, 256>>>(dx, dy, dout, n, y ? 0 : 1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return 0;
+}
+
+int roger_sas_synchronize(roger_sas* h) {
+    if (!h) return fail(ROGER_EINVAL, "roger_sas_synchronize: null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int roger_sas_last_timing(roger_sas* h, double* kernel_ms, int64_t* launches) {
+    if (!h) return fail(ROGER_EINVAL, "roger_sas_last_timing: null handle");
+    if (kernel_ms) *kernel_ms = h->last_kernel_ms;
+    if (launches) *launches = h->last_launches;
+    return 0;
+}
+
+}  // extern "C"

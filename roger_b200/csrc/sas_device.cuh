@@ -1,0 +1,461 @@
+// sas_device.cuh -- per-cell device code of the offline oxygen-18 StorAge-selection transport step
+// (roger/core/transport.py:948-991 svat_transport_model_deterministic and the *_transport_iso_kernel of the
+// process modules it calls).
+//
+// Execution model: ONE THREAD PER CELL, age axis walked sequentially, arrays stored AGE-MAJOR (one plane of
+// C doubles per age bin, cell index fastest) so that the 32 threads of a warp -- 32 neighbouring cells at
+// the same age bin -- read and write 256 contiguous bytes per access.
+//
+// Why sequential and not a warp-shuffle scan: the reference's cumulative sums are NumPy `cumsum`s, i.e.
+// sequentially rounded, and the solver takes hard decisions on the results (`flux*tt > sa`, `SA > 0`,
+// `sa <= 0`; transport.py:431, :494, :614, sas.py:232).  With the power-law exponents < 1 of the benchmark a
+// last-bit difference in one cumulative sum flips such a decision and shows up as a 1e-6 relative difference
+// within days ("SAS parity chain").  Walking the age axis in the reference's own order -- and
+// summing with NumPy's pairwise tree, and calling the shared roger_pow() -- makes the kernel reproduce the
+// CPU oracle bit for bit; a reassociating scan cannot.
+//
+// Ageing (transport.py:682-739) is a rotation of the plane ring (`base`), not a copy: bin j lives in plane
+// (base + j) mod A, and the daily shift decrements base.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "roger_pow.h"
+#include "../../include/roger_b200_sas.h"
+
+namespace rsas {
+
+constexpr int kMaxLeaves = 96;
+
+// NumPy's pairwise summation of n contiguous doubles (np.add.reduce: blocks of <= 128 summed in 8 lanes, halves
+// split at a multiple of 8) flattened into a left-to-right list of leaves; after leaf l, `merges[l]` pairs of
+// partial sums on the stack are combined.
+struct PwPlan {
+    int n_leaves;
+    short len[kMaxLeaves];
+    unsigned char merges[kMaxLeaves];
+};
+
+struct SasParams {
+    int A, substeps;
+    int store_tt;
+    int base;  // plane of age bin 0
+    double vsmow, dmin, dmax;
+    int64_t C;
+};
+
+struct Planes {  // age-major arrays
+    double* sa[2];   // 0 rz, 1 ss
+    double* msa[2];
+    double* san;     // scratch: StorAge inside the sub-step loop
+    double* TTn;     // scratch: accumulated cumulative travel-time distribution (index j holds TTn[j + 1])
+    double* tt;      // optional: RSP_COUNT x A x C
+};
+
+// walks age bins 0..A-1 of one cell through the plane ring
+struct Cursor {
+    int64_t off;     // element offset of the current bin
+    int64_t C;
+    int64_t wrap_at; // offset at which the ring wraps
+    int64_t span;    // A * C
+    __device__ __forceinline__ Cursor(const SasParams& P, int64_t i) {
+        C = P.C;
+        span = (int64_t)P.A * P.C;
+        off = (int64_t)P.base * P.C + i;
+        wrap_at = span + i;
+    }
+    __device__ __forceinline__ void next() {
+        off += C;
+        if (off == wrap_at) off -= span;
+    }
+};
+
+__device__ __forceinline__ bool isnan_d(double x) { return x != x; }
+
+// running np.max (propagates the first NaN, as npx.max does)
+struct NpMax {
+    double mx;
+    bool nan;
+    __device__ __forceinline__ void init(double a0) { mx = a0; nan = false; }
+    __device__ __forceinline__ void push(double a) {
+        if (!nan) {
+            if (isnan_d(a)) { mx = a; nan = true; }
+            else if (a > mx) mx = a;
+        }
+    }
+};
+
+__device__ __forceinline__ double conc_to_delta(const SasParams& P, double conc) {  // transport.py:328-340
+    const double d = 1000. * (conc / (P.vsmow * (1. - conc)) - 1.);
+    return ((d < P.dmin) || (d > P.dmax)) ? __longlong_as_double(0x7ff8000000000000LL) : d;
+}
+
+// ---- SAS functions (roger/core/sas.py) --------------------------------------------------------------------
+struct Family {
+    double sp[8];      // parameter row, modified in place by the storage-dependent variants (the loop carry)
+    double m;
+    // per sub-step
+    double S;          // max(SA) * m
+    double uS, ulam, umask;
+    bool is_uniform, is_dirac, is_kum, is_exp51, is_pow;
+    bool fast;         // every inactive family provably contributes +0.0
+};
+
+__device__ __forceinline__ double s_rel(double S, const double* sp, double m) {
+    double r = (S - sp[5]) / (sp[6] - sp[5]) * m;
+    r = (r < 0) ? 0 : r;
+    r = (r > 1) ? 1 : r;
+    return r;
+}
+
+__device__ __forceinline__ void family_begin(Family& f, const double* sp_global, int64_t stride, double m) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) f.sp[k] = sp_global[k * stride];
+    f.m = m;
+}
+
+// per sub-step preparation: everything that depends on max(SA) only
+__device__ __forceinline__ void family_prepare(Family& f, double mx) {
+    const double m = f.m;
+    const double id = f.sp[0];
+    f.is_uniform = (id == 1);
+    f.umask = f.is_uniform ? 1.0 : 0.0;
+    f.uS = mx * f.umask * m;              // sas.py:14-20
+    f.ulam = 1 / f.uS * f.umask * m;
+    f.is_dirac = (id == 2);
+    f.S = mx * m;
+    f.is_kum = (id == 3 || id == 31 || id == 32 || id == 33 || id == 34 || id == 35 || id == 36 || id == 37);
+    {   // sas.py:51-108
+        const double r = s_rel(f.S, f.sp, m);
+        double* sp = f.sp;
+        if (id == 31) { sp[1] = 1; sp[2] = sp[3] + (r * sp[4]); }
+        if (id == 32) { sp[1] = sp[3] + ((1 - r) * sp[4]); sp[2] = 1; }
+        if (id == 33) { sp[1] = 1; sp[2] = sp[3] + ((1 - r) * sp[4]); }
+        if (id == 34) { sp[1] = sp[3] + (r * sp[4]); sp[2] = 1; }
+        if (id == 35) { sp[1] = sp[3] + ((1 - r) * sp[4]); sp[2] = sp[3] + (r * sp[4]); }
+        if (id == 36) { sp[1] = sp[3] + ((1 - r) * sp[4]); }
+        if (id == 37) { sp[2] = sp[3] + (r * sp[4]); }
+    }
+    f.is_exp51 = (id == 51);
+    f.is_pow = (id == 6 || id == 61 || id == 62);
+    {   // sas.py:209-229
+        const double r = s_rel(f.S, f.sp, m);
+        if (id == 61) f.sp[1] = f.sp[3] + ((1 - r) * f.sp[4]);
+        if (id == 62) f.sp[1] = f.sp[3] + (r * f.sp[4]);
+    }
+    // An inactive Kumaraswamy / power term is `value * 0`; it is +0.0 unless value is NaN or infinite, which needs a
+    // negative or non-finite shape parameter.  With both shape parameters finite and >= 0 the skipped terms are
+    // exactly +0.0 and skipping them changes nothing.
+    f.fast = (f.sp[1] >= 0) && (f.sp[2] >= 0) && (f.sp[1] <= 1.7e308) && (f.sp[2] <= 1.7e308) && (m == 1.0);
+}
+
+// cumulative SAS distribution at age index jj (0..A) where the cumulative StorAge is SA: the sum of the five
+// families in the reference's order (transport.py:399-428; the gamma family and the time-reversed exponential,
+// ids 4 and 52, are rejected by roger_sas_set_parameters)
+__device__ __forceinline__ double omega(const Family& f, const SasParams& P, const roger_pow_tables tabs, int jj, double SA) {
+    const double m = f.m;
+    double t = 0.0;
+    if (f.is_uniform || !f.fast) {  // sas.py:5-35
+        double o = ((SA < f.uS) ? ((SA > 0) ? f.ulam * SA : 0.) : 1.) * f.umask * m;
+        if (jj == P.A) o = ((f.umask != 0) ? 1 : o) * m;
+        o = ((f.uS <= 0) ? 0 : o) * m;
+        t += o;
+    }
+    if (f.is_dirac || !f.fast) {  // sas.py:243-264
+        double o = ((f.is_dirac && ((double)jj <= f.sp[1])) ? 0 : 1) * m;
+        o = ((f.S <= 0) ? 0 : o) * (f.is_dirac ? 1.0 : 0.0) * m;
+        t += o;
+    }
+    if (f.is_kum || !f.fast) {  // sas.py:38-134
+        const double S = f.S;
+        double v;
+        const bool need_f = (S >= 0) ? ((SA > 0) && (SA < S)) : (SA > 0);
+        if (need_f) v = 1 - roger_pow(1 - roger_pow(SA / S, f.sp[1], tabs), f.sp[2], tabs);
+        else v = (S >= 0) ? ((SA > 0) ? 1. : 0.) : 0.;
+        double o = v * (f.is_kum ? 1.0 : 0.0) * m;
+        o = ((S <= 0) ? 0 : o) * m;
+        t += o;
+    }
+    if (f.is_exp51 || !f.fast) {  // sas.py:163-191
+        const double S = f.S;
+        double o = 0.0;
+        if (f.is_exp51) o = (SA > 0) ? ((SA < S) ? 1 - roger_exp(f.sp[1] * (-1) * (SA / S), tabs) : 1.) : 0.;
+        o = o * m;
+        o = o * m;  // the id-52 select of sas.py:183 multiplies by maskCatch once more
+        o = ((S <= 0) ? 0 : o) * m;
+        t += o;
+    }
+    if (f.is_pow || !f.fast) {  // sas.py:194-240
+        const double S = f.S;
+        double o = ((SA > 0) ? ((SA <= S) ? roger_pow(SA / S, f.sp[1], tabs) : 1.) : 0.) * (f.is_pow ? 1.0 : 0.0) * m;
+        o = ((S <= 0) ? 0 : o) * m;
+        t += o;
+    }
+    return t;
+}
+
+// ---- streaming NumPy pairwise sums -------------------------------------------------------------------------
+// body(j, v) fills v[0..NS) with the NS summands of bin j; bins are visited once, in order.
+template <int NS, class Body>
+__device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Body body, double* out) {
+    double st[NS][8];
+    int sp = 0;
+    int j = 0;
+    const int nl = plan->n_leaves;
+    for (int l = 0; l < nl; l++) {
+        const int len = plan->len[l];
+        double res[NS];
+        if (len < 8) {
+#pragma unroll
+            for (int k = 0; k < NS; k++) res[k] = 0.;
+            for (int i = 0; i < len; i++, j++) {
+                double v[NS];
+                body(j, v);
+#pragma unroll
+                for (int k = 0; k < NS; k++) res[k] += v[k];
+            }
+        } else {
+            double r[NS][8];
+#pragma unroll
+            for (int k = 0; k < NS; k++)
+#pragma unroll
+                for (int q = 0; q < 8; q++) r[k][q] = -0.0;  // x + (-0.0) == x: the first chunk initialises the lanes
+            const int len8 = len - (len % 8);
+            for (int i = 0; i < len8; i += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; q++, j++) {
+                    double v[NS];
+                    body(j, v);
+#pragma unroll
+                    for (int k = 0; k < NS; k++) r[k][q] += v[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NS; k++)
+                res[k] = ((r[k][0] + r[k][1]) + (r[k][2] + r[k][3])) + ((r[k][4] + r[k][5]) + (r[k][6] + r[k][7]));
+            for (int i = len8; i < len; i++, j++) {
+                double v[NS];
+                body(j, v);
+#pragma unroll
+                for (int k = 0; k < NS; k++) res[k] += v[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NS; k++) st[k][sp] = res[k];
+        sp++;
+        for (int c = plan->merges[l]; c > 0; c--) {
+            sp--;
+#pragma unroll
+            for (int k = 0; k < NS; k++) st[k][sp - 1] = st[k][sp - 1] + st[k][sp];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) out[k] = 0.0 + st[k][0];
+}
+
+struct CellCtx {
+    SasParams P;
+    Planes pl;
+    const PwPlan* plan;
+    roger_pow_tables tabs;
+    int64_t i;
+};
+
+// ---- one SAS-controlled withdrawal from layer `src`, optionally received by layer `dst` (dst < 0: leaves the
+// soil).  evapotranspiration.py:653-716, :831-895; subsurface_runoff.py:1531-1625, :1753-1815;
+// capillary_rise.py:404-500.
+__device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
+                                        double m, double* C_flux, double* C_iso_flux, int process) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    double* __restrict__ sa = cx.pl.sa[src];
+    double* __restrict__ msa = cx.pl.msa[src];
+    double* __restrict__ san = cx.pl.san;
+    double* __restrict__ TTn = cx.pl.TTn;
+    const int64_t i = cx.i;
+    const int64_t C = P.C;
+    const double h = 1.0 / P.substeps;
+    const bool active = (flux * h > 0);  // otherwise every sub-step leaves san and TTn untouched (tti = 0)
+
+    if (active) {
+        // cumulative StorAge of the layer (transport.py:343-359) -> S = max(SA)
+        NpMax mx;
+        const double SA0 = 0. * m;
+        mx.init(SA0);
+        {
+            Cursor c(P, i);
+            double acc = 0;
+            for (int j = 0; j < A; j++, c.next()) {
+                acc += sa[c.off];
+                mx.push(acc * m);
+            }
+        }
+        Family fam;
+        family_begin(fam, sp_global, sp_stride, m);
+        const double fh = flux * h;
+        for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
+            family_prepare(fam, mx.mx);
+            double om_prev = omega(fam, P, cx.tabs, 0, SA0);
+            double acc_in = 0, acc_new = 0, acc_t = 0;
+            NpMax mxn;
+            mxn.init(SA0);
+            const double* __restrict__ X = (s == 0) ? sa : san;
+            Cursor c(P, i);
+            int64_t lin = i;  // scratch arrays are not rotated
+            for (int j = 0; j < A; j++, c.next(), lin += C) {
+                const double x = (s == 0) ? X[c.off] : X[lin];
+                acc_in += x;
+                const double SAj = (s == 0) ? acc_in * m : acc_in;
+                const double om = omega(fam, P, cx.tabs, j + 1, SAj);
+                const double d = om - om_prev;
+                om_prev = om;
+                double tti = (d >= 0) ? d : 0;
+                const double q = flux * tti * h;
+                const double ttqi = (q > x) ? x : q;
+                tti = ttqi / fh;
+                const double xn = x + -tti * flux * h;
+                san[lin] = xn;
+                acc_new += xn;
+                mxn.push(acc_new);
+                acc_t += tti;
+                TTn[lin] = ((s == 0) ? 0.0 : TTn[lin]) + acc_t;
+            }
+            mx = mxn;
+        }
+    }
+
+    // aggregate (transport.py:472-496), flux concentration (:512-535), isotope mixing into the receiving layer,
+    // StorAge update (:599-619)
+    double* __restrict__ sa_d = (dst >= 0) ? cx.pl.sa[dst] : nullptr;
+    double* __restrict__ msa_d = (dst >= 0) ? cx.pl.msa[dst] : nullptr;
+    double* __restrict__ tt_out = (P.store_tt && cx.pl.tt) ? cx.pl.tt + (size_t)process * (size_t)A * (size_t)C : nullptr;
+    const double nsub = (double)P.substeps;
+    double prev = 0. / nsub;
+    Cursor c(P, i);
+    int64_t lin = i;
+    double sums[2];
+    stream_sums<2>(cx.plan, [&](int j, double* v) {
+        const double cur = (active ? TTn[lin] : 0.) / nsub;
+        double t = cur - prev;
+        prev = cur;
+        const double s_j = sa[c.off];
+        const double q = flux * t;
+        const double ttq = (q > s_j) ? s_j : q;
+        t = (flux > 0) ? ttq / flux : 0;
+        t = t * m;
+        const double ms_j = msa[c.off];
+        const double mtt = ((t > 0) ? ms_j : 0) * m;
+        v[0] = t;
+        v[1] = mtt * t;
+        if (dst >= 0) {
+            const double in = t * flux;
+            const double sd = sa_d[c.off];
+            const double md = msa_d[c.off];
+            const double tot = in + sd;
+            const double mixed = (tot > 0) ? md * (sd / tot) + mtt * (in / tot) : md;
+            msa_d[c.off] = mixed * m;
+            sa_d[c.off] = sd + t * flux * m;
+        }
+        double u = s_j + -flux * t;
+        u = ((u > -1e-5) && (u < 0)) ? 0 : u;
+        u = u * m;
+        sa[c.off] = u;
+        msa[c.off] = ((u <= 0) ? 0 : ms_j) * m;
+        if (tt_out) tt_out[lin] = t;
+        c.next();
+        lin += C;
+    }, sums);
+    double conc = (sums[0] > 0) ? sums[1] / sums[0] : __longlong_as_double(0x7ff8000000000000LL);
+    conc = (conc != 0) ? conc : __longlong_as_double(0x7ff8000000000000LL);
+    *C_flux = conc * m;
+    *C_iso_flux = conc_to_delta(P, *C_flux) * m;
+}
+
+// infiltration of `inf` with concentration C_in into bin 0 (infiltration.py:2218-2345, :2441-2500)
+__device__ __forceinline__ void inflow(const CellCtx& cx, int layer, double inf, double C_in, double m, double* C_out, double* C_iso_out) {
+    const SasParams& P = cx.P;
+    double* __restrict__ sa = cx.pl.sa[layer];
+    double* __restrict__ msa = cx.pl.msa[layer];
+    *C_out = ((inf > 0) ? C_in : 0) * m;
+    *C_iso_out = conc_to_delta(P, *C_out) * m;
+    const double tt0 = ((inf > 0) ? 1 : 0) * m;
+    const double mtt0 = ((inf > 0) ? C_in : 0) * m;
+    Cursor c(P, cx.i);
+    // bins j > 0 receive nothing: msa*(sa/sa) + 0 == msa, so with m == 1 only bin 0 changes
+    const int n = (m == 1.0) ? 1 : P.A;
+    for (int j = 0; j < n; j++, c.next()) {
+        const double ttj = (j == 0) ? tt0 : 0.0, mttj = (j == 0) ? mtt0 : 0.0;
+        const double s = sa[c.off], ms = msa[c.off];
+        double v;
+        if (inf * ttj + s > 0) v = ms * (s / (ttj * inf + s)) + mttj * ((ttj * inf) / (inf * ttj + s));
+        else v = ms;
+        msa[c.off] = v * m;
+        if (j == 0) sa[c.off] = s + inf * m;
+    }
+}
+
+// storage kernels (root_zone.py:189-215, subsoil.py:153-180, soil.py:1036-1092) followed by ageing
+// (transport.py:682-739) as a ring rotation
+__device__ __forceinline__ void storage_and_ageing(const CellCtx& cx, double m, double* out, int64_t oC) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    double* __restrict__ s_rz = cx.pl.sa[0];
+    double* __restrict__ s_ss = cx.pl.sa[1];
+    double* __restrict__ m_rz = cx.pl.msa[0];
+    double* __restrict__ m_ss = cx.pl.msa[1];
+    Cursor c(P, cx.i);
+    double sums[6];
+    stream_sums<6>(cx.plan, [&](int j, double* v) {
+        double a = s_rz[c.off];
+        a = (a < 1e-8) ? 0 : a;
+        s_rz[c.off] = a;
+        double b = s_ss[c.off];
+        b = (b < 1e-8) ? 0 : b;
+        s_ss[c.off] = b;
+        const double ma = m_rz[c.off], mb = m_ss[c.off];
+        v[0] = a;
+        v[1] = ma * a;
+        v[2] = b;
+        v[3] = mb * b;
+        const double s = a + b * m;
+        const double tot = a + b;
+        double ms = (tot > 0) ? ma * (a / tot) + mb * (b / tot) : 0;
+        ms = isnan_d(ms) ? 0 : ms;
+        v[4] = s;
+        v[5] = ms * s;
+        c.next();
+    }, sums);
+    const double C_rz = ((sums[0] > 0) ? sums[1] / sums[0] : 0) * m;
+    const double C_ss = ((sums[2] > 0) ? sums[3] / sums[2] : 0) * m;
+    const double C_s = ((sums[4] > 0) ? sums[5] / sums[4] : 0) * m;
+    const int64_t i = cx.i;
+    out[RSO_C_rz * oC + i] = C_rz;
+    out[RSO_C_ss * oC + i] = C_ss;
+    out[RSO_C_s * oC + i] = C_s;
+    out[RSO_C_iso_rz * oC + i] = conc_to_delta(P, C_rz) * m;
+    out[RSO_C_iso_ss * oC + i] = conc_to_delta(P, C_ss) * m;
+    out[RSO_C_iso_s * oC + i] = conc_to_delta(P, C_s) * m;
+
+    // ageing: new bin j = old bin j-1; the oldest two bins merge; bin 0 is emptied.  With base' = base - 1 the old
+    // bin A-1 becomes the new bin 0 and the old bin A-2 the new bin A-1.
+    const int64_t C = P.C;
+    const int b_new = (P.base == 0) ? A - 1 : P.base - 1;            // plane of old bin A-1 = new bin 0
+    const int b_last = (b_new == 0) ? A - 1 : b_new - 1;             // plane of old bin A-2 = new bin A-1
+    for (int L = 0; L < 2; L++) {
+        double* __restrict__ sa = cx.pl.sa[L];
+        double* __restrict__ msa = cx.pl.msa[L];
+        const double sam1_last = sa[(int64_t)b_new * C + i], msam1_last = msa[(int64_t)b_new * C + i];
+        const double s_l = sa[(int64_t)b_last * C + i], ms_l = msa[(int64_t)b_last * C + i];
+        const double tot = s_l + sam1_last;
+        double v = (tot > 0) ? msam1_last * (sam1_last / tot) + ms_l * (s_l / tot) : 0;
+        v = isnan_d(v) ? 0 : v;
+        double s_new = s_l + sam1_last;
+        s_new = (s_new < 1e-8) ? 0 : s_new;
+        v = (s_new <= 0) ? __longlong_as_double(0x7ff8000000000000LL) : v;
+        sa[(int64_t)b_last * C + i] = s_new;
+        msa[(int64_t)b_last * C + i] = v;
+        sa[(int64_t)b_new * C + i] = 0;
+        msa[(int64_t)b_new * C + i] = 0;
+    }
+}
+
+}  // namespace rsas

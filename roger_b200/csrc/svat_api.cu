@@ -222,6 +222,9 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return -code;
 }
+namespace roger {
+int set_last_error(int code, const std::string& msg) { return fail(code, msg); }  // shared with sas_api.cu
+}
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \

@@ -3,9 +3,23 @@
 Daily hydrologic forcing comes from an online SVAT run of the (already pinned) CPU oracle.
 
     python tests/golden/make_sas_golden.py [case ...]
+
+Which libm.  The SAS solver amplifies last-bit differences of `power` ("SAS parity chain"), so the
+fixture has to say which `power` produced it.  The main records (`rec_*`) are produced with NumPy's AVX512 / AVX2
+SIMD dispatch switched off (NPY_DISABLE_CPU_FEATURES, a documented NumPy runtime switch): float64 `power` then calls
+the C library's pow, which is what the C oracle calls, and oracle and reference agree bit for bit.  A second run with
+NumPy's default dispatch (Intel SVML `power` on this AVX512 host) is stored as `simd_rec_*` for a few variables: it
+documents how far two runs of the *unmodified reference itself* drift apart when only the libm differs.
 """
 import os
+import subprocess
 import sys
+import tempfile
+
+NO_SIMD = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX2 FMA3"
+if "--simd" not in sys.argv and os.environ.get("NPY_DISABLE_CPU_FEATURES") != NO_SIMD:
+    os.environ["NPY_DISABLE_CPU_FEATURES"] = NO_SIMD  # must be set before numpy is imported
+    os.execv(sys.executable, [sys.executable] + sys.argv)
 
 import numpy as np
 
@@ -62,7 +76,10 @@ def build(name):
     return case
 
 
-def run(name):
+SIMD_KEEP = ["sa_rz", "sa_ss", "C_rz", "C_iso_transp", "C_iso_q_ss"]
+
+
+def run(name, simd_out=None):
     case = build(name)
     Setup = rh.make_o18_setup(case)
     model = Setup()
@@ -95,7 +112,16 @@ def run(name):
     for day in range(case["ndays"]):
         model.step(state)
         recs.append(grab())
+    if simd_out is not None:
+        np.savez(simd_out, **{"simd_rec_" + k: np.stack([r[k] for r in recs]) for k in SIMD_KEEP})
+        return
     out = dict(nx=nx, ny=ny, ndays=case["ndays"], ages=ages, substeps=6)
+    with tempfile.TemporaryDirectory() as td:
+        tmp = os.path.join(td, "simd.npz")
+        env = {k: v for k, v in os.environ.items() if k != "NPY_DISABLE_CPU_FEATURES"}
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--simd", tmp, name], env=env, stdout=subprocess.DEVNULL)
+        with np.load(tmp) as z:
+            out.update({k: z[k] for k in z.files})
     for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES) + ["C_ISO_IN"]:
         out["in_" + k] = case[k].reshape(C, -1)
     for proc, arr in case["sas"].items():
@@ -111,5 +137,9 @@ def run(name):
 
 
 if __name__ == "__main__":
-    for n in sys.argv[1:] or list(CASES):
-        run(n)
+    if "--simd" in sys.argv:
+        k = sys.argv.index("--simd")
+        run(sys.argv[k + 2], simd_out=sys.argv[k + 1])
+    else:
+        for n in sys.argv[1:] or list(CASES):
+            run(n)

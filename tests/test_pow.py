@@ -1,0 +1,68 @@
+"""roger_pow / roger_exp (roger_b200/csrc/roger_pow.h), host build: accuracy against mpmath and the C library."""
+import ctypes as C
+import math
+
+import numpy as np
+
+from oracle.engine import lib
+
+dp = C.POINTER(C.c_double)
+
+
+def host_pow(x, y):
+    L = lib()
+    L.roger_pow_host_array.argtypes = [dp, dp, dp, C.c_int64]
+    L.roger_pow_host_array.restype = None
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(np.broadcast_to(y, x.shape), dtype=np.float64)
+    out = np.empty_like(x)
+    L.roger_pow_host_array(x.ctypes.data_as(dp), y.ctypes.data_as(dp), out.ctypes.data_as(dp), x.size)
+    return out
+
+
+def test_within_one_ulp_of_libm_and_mostly_identical():
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(0, 1, 100000), np.exp(rng.uniform(-200, 200, 100000))])
+    y = np.concatenate([rng.choice([0.2, 0.5, 1.5, 1 / 3, 3.0, 0.01, 7.3], 100000), rng.uniform(-2, 2, 100000)])
+    a = host_pow(x, y)
+    b = np.array([math.pow(v, w) for v, w in zip(x, y)])
+    ok = (b > 1e-300) & np.isfinite(b)
+    ulp = np.abs(a[ok] - b[ok]) / np.spacing(b[ok])
+    assert ulp.max() <= 1.0
+    assert (ulp > 0).mean() < 2e-3
+
+
+def test_error_against_exact_value_below_0_53_ulp():
+    import mpmath as mp
+
+    mp.mp.prec = 200
+    rng = np.random.default_rng(2)
+    x = rng.uniform(0, 1, 4000)
+    y = rng.choice([0.2, 0.5, 1.5, 2.7], 4000)
+    a = host_pow(x, y)
+    worst = 0.0
+    for v, k, r in zip(x, y, a):
+        t = mp.mpf(float(v)) ** mp.mpf(float(k))
+        worst = max(worst, float(abs((mp.mpf(float(r)) - t) / mp.mpf(float(np.spacing(r))))))
+    assert worst < 0.53
+
+
+def test_special_values():
+    L = lib()
+    L.roger_pow_host.restype = C.c_double
+    L.roger_pow_host.argtypes = [C.c_double, C.c_double]
+    f = L.roger_pow_host
+    inf, nan = float("inf"), float("nan")
+    assert f(0.0, 0.5) == 0.0 and f(0.0, -1.0) == inf and f(0.0, 0.0) == 1.0
+    assert f(1.0, nan) == 1.0 and f(nan, 0.0) == 1.0 and math.isnan(f(nan, 1.0)) and math.isnan(f(-1.0, 0.5))
+    assert f(2.0, 1024.0) == inf and f(2.0, -1080.0) == 0.0 and f(inf, -1.0) == 0.0 and f(0.5, inf) == 0.0
+    assert f(5e-324, 0.5) == math.pow(5e-324, 0.5)
+    assert f(4.0, 0.5) == 2.0 and f(0.25, 1.5) == 0.125 and f(3.0, 2.0) == 9.0
+    L.roger_exp_host.restype = C.c_double
+    L.roger_exp_host.argtypes = [C.c_double]
+    assert L.roger_exp_host(0.0) == 1.0 and L.roger_exp_host(-1e4) == 0.0 and L.roger_exp_host(1e4) == inf
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-50, 5, 20000)
+    a = np.array([L.roger_exp_host(v) for v in x])
+    b = np.exp(x)
+    assert (np.abs(a - b) / np.spacing(b)).max() <= 1.0

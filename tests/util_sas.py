@@ -1,0 +1,98 @@
+"""Shared helpers of the StorAge-selection parity tests: fixture -> SasModel, replay, comparison."""
+import os
+
+import numpy as np
+
+from roger_b200 import sas
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SAS_CASES = ["sas_power", "sas_power_snow", "sas_families"]
+
+
+def load_case(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as d:
+        return {k: d[k] for k in d.files}
+
+
+def model_from_fixture(fx, engine_cls, store_tt=True, engine_kwargs=None, mask=None):
+    C = int(fx["nx"]) * int(fx["ny"])
+    A = int(fx["ages"])
+    daily = {k[3:]: fx[k] for k in fx if k.startswith("in_")}
+    spec = {p: fx["sas_" + p] for p in sas.PROCESSES}
+    m = sas.SasModel(engine_cls, C, A, daily, spec, substeps=int(fx["substeps"]), store_tt=store_tt, mask=mask,
+                     engine_kwargs=engine_kwargs)
+    m.setup()
+    for k in sas.STATE:  # start from the reference's own post-setup state
+        m.engine.upload_state(k, fx["init_" + k])
+    return m
+
+
+def same(a, b):
+    """bit-level equality of values (NaN == NaN, -0.0 == 0.0)"""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def rel_err(a, b):
+    """max |a - b| / max |b| with NaN patterns required to agree"""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if (np.isnan(a) != np.isnan(b)).any():
+        return np.inf
+    ok = ~np.isnan(b)
+    if not ok.any():
+        return 0.0
+    scale = np.max(np.abs(b[ok]))
+    d = np.max(np.abs(a[ok] - b[ok]))
+    return float(d / scale) if scale > 0 else float(d)
+
+
+def snapshot(model):
+    """every compared quantity of the current step"""
+    out = {k: model.state(k) for k in sas.STATE}
+    if model.settings.store_tt:
+        for p in sas.PROCESSES:
+            out["tt_" + p] = model.tt(p)
+    out.update(model.outputs())
+    out["C_in"] = model.C_in.copy()
+    return out
+
+
+def replay_against_fixture(fx, model, exact=True, tol=None, skip_nan_pattern=()):
+    """Steps through the fixture's days; returns {name: (worst error, day)}; asserts when exact / tol is given."""
+    worst = {}
+    for day in range(int(fx["ndays"])):
+        model.step()
+        snap = snapshot(model)
+        for k, x in snap.items():
+            if "rec_" + k not in fx:
+                continue
+            r = fx["rec_" + k][day]
+            if exact:
+                assert same(x, r), f"day {day}: {k} differs from the reference fixture (max abs diff {np.nanmax(np.abs(x - r))})"
+            else:
+                e = rel_err(x, r)
+                if e > worst.get(k, (0, 0))[0]:
+                    worst[k] = (e, day)
+    if tol is not None:
+        bad = {k: v for k, v in worst.items() if v[0] > tol}
+        assert not bad, f"above {tol}: {bad}"
+    return worst
+
+
+def replay_pair(model_a, model_b, ndays, exact=True):
+    """Steps two models side by side and compares every quantity each day."""
+    worst = {}
+    for day in range(ndays):
+        model_a.step()
+        model_b.step()
+        sa, sb = snapshot(model_a), snapshot(model_b)
+        for k in sa:
+            if exact:
+                assert same(sa[k], sb[k]), f"day {day}: {k} differs (max abs diff {np.nanmax(np.abs(sa[k] - sb[k]))})"
+            else:
+                e = rel_err(sa[k], sb[k])
+                if e > worst.get(k, (0, 0))[0]:
+                    worst[k] = (e, day)
+    return worst
