@@ -111,7 +111,7 @@ def _random_case(C_, A, ndays, seed, families=False):
         "C_ISO_IN": rng.uniform(-12, -5, (C_, t)),
     }
     # one cell receives a capillary rise that empties young subsoil bins (the clamp path)
-    d["CPR_RZ"][0, 3] = 60.0
+    d["CPR_RZ"][0, min(3, t - 1)] = 60.0
     spec = {}
     if families:
         ids = {"evap_soil": [1, 6, 3], "cpr_rz": [51, 6, 2], "transp": [3, 32, 6], "q_rz": [61, 62, 35], "q_ss": [35, 31, 6]}
