@@ -150,6 +150,22 @@ ROGER_POW_FN double roger_pow_exp(double x, double xtail, const roger_pow_exp_en
     return roger_pow_fma(scale, tmp, scale);
 }
 
+/* x^y for a positive NORMAL x given as bits and a finite y, without branches (range handling by selects): the form
+ * the CUDA kernels inline several times per loop iteration so that independent evaluations interleave.
+ * roger_pow() below is this function behind the special cases; both return the same bits on the common domain. */
+ROGER_POW_FN double roger_pow_core(uint64_t ix, double y, const roger_pow_tables tabs)
+{
+    double lo;
+    const double hi = roger_pow_log(ix, &lo, tabs.log_tab);
+    const double ehi = roger_pow_mul(y, hi);
+    const double elo = roger_pow_add(roger_pow_mul(y, lo), roger_pow_fma(y, hi, -ehi));
+    const int ovf = !(ehi < 0x1.62e42fefa39efp+9); /* >= 1024 ln2: overflow              */
+    const int unf = ehi < -0x1.6232bdd7abcd2p+9;   /* result below 2^-1022: flushed to 0 */
+    const int out = ovf | unf;
+    const double res = roger_pow_exp(out ? 0.0 : ehi, out ? 0.0 : elo, tabs.exp_tab);
+    return ovf ? roger_pow_asd(0x7ff0000000000000ULL) : (unf ? 0.0 : res);
+}
+
 ROGER_POW_FN double roger_pow(double x, double y, const roger_pow_tables tabs)
 {
     uint64_t ix = roger_pow_asu(x);
@@ -166,14 +182,11 @@ ROGER_POW_FN double roger_pow(double x, double y, const roger_pow_tables tabs)
         ix = roger_pow_asu(roger_pow_mul(x, 0x1p52));
         ix -= 52ULL << 52;
     }
-    double lo;
-    const double hi = roger_pow_log(ix, &lo, tabs.log_tab);
-    const double ehi = roger_pow_mul(y, hi);
-    const double elo = roger_pow_add(roger_pow_mul(y, lo), roger_pow_fma(y, hi, -ehi));
-    if (!(ehi < 0x1.62e42fefa39efp+9)) return roger_pow_asd(0x7ff0000000000000ULL); /* >= 1024 ln2: overflow */
-    if (ehi < -0x1.6232bdd7abcd2p+9) return 0.0;                                      /* < 2^-1022: flushed   */
-    return roger_pow_exp(ehi, elo, tabs.exp_tab);
+    return roger_pow_core(ix, y, tabs);
 }
+
+/* true when x is a positive normal number (the domain of roger_pow_core) */
+ROGER_POW_FN int roger_pow_is_pos_normal(uint64_t ix) { return ((ix >> 52) - 1ULL) < 0x7feULL; }
 
 /* exp(x) by the same reduction (tail 0): overflow -> +inf, results below 2^-1022 flushed to 0 */
 ROGER_POW_FN double roger_exp(double x, const roger_pow_tables tabs)

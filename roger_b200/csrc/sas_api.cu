@@ -36,9 +36,12 @@ __device__ const roger_pow_exp_entry d_pow_exp_tab[ROGER_POW_N] = {ROGER_POW_EXP
 #ifndef ROGER_SAS_BLOCK
 #define ROGER_SAS_BLOCK 128
 #endif
+#ifndef ROGER_SAS_MIN_BLOCKS
+#define ROGER_SAS_MIN_BLOCKS 4
+#endif
 
 // One daily transport step of every cell (transport.py:948-991), one thread per cell.
-__global__ void __launch_bounds__(ROGER_SAS_BLOCK)
+__global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
 k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
           const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];

@@ -186,7 +186,16 @@ __device__ __forceinline__ double omega(const Family& f, const SasParams& P, con
     }
     if (f.is_pow || !f.fast) {  // sas.py:194-240
         const double S = f.S;
-        double o = ((SA > 0) ? ((SA <= S) ? roger_pow(SA / S, f.sp[1], tabs) : 1.) : 0.) * (f.is_pow ? 1.0 : 0.0) * m;
+        const bool in = (SA > 0) && (SA <= S);
+        const double xr = SA / S;
+        const uint64_t ixr = roger_pow_asu(xr);
+        const double y = f.sp[1];
+        // branch-free evaluation on the common domain (positive normal base, finite exponent) so that the evaluations of
+        // neighbouring age bins interleave; anything else takes the general entry point (same bits where both apply)
+        const bool easy = in && roger_pow_is_pos_normal(ixr) && (y - y == 0.0);
+        double p = roger_pow_core(easy ? ixr : 0x3fe0000000000000ULL, easy ? y : 1.0, tabs);
+        if (in && !easy) p = roger_pow(xr, y, tabs);
+        double o = ((SA > 0) ? ((SA <= S) ? p : 1.) : 0.) * (f.is_pow ? 1.0 : 0.0) * m;
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
     }
@@ -194,9 +203,11 @@ __device__ __forceinline__ double omega(const Family& f, const SasParams& P, con
 }
 
 // ---- streaming NumPy pairwise sums -------------------------------------------------------------------------
-// body(j, v) fills v[0..NS) with the NS summands of bin j; bins are visited once, in order.
-template <int NS, class Body>
-__device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Body body, double* out) {
+// Bins are visited once, in order.  load(j, L) reads the NL inputs of bin j (and may record addresses); work(j, L, v)
+// computes the bin, performs its stores and fills the NS summands v.  Within a chunk of 8 bins all loads are issued
+// before the first dependent instruction, so eight bins' worth of memory latency overlap.
+template <int NS, int NL, class Load, class Work>
+__device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Load load, Work work, double* out) {
     double st[NS][8];
     int sp = 0;
     int j = 0;
@@ -208,8 +219,9 @@ __device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Bod
 #pragma unroll
             for (int k = 0; k < NS; k++) res[k] = 0.;
             for (int i = 0; i < len; i++, j++) {
-                double v[NS];
-                body(j, v);
+                double L[NL], v[NS];
+                load(j, L);
+                work(j, L, v);
 #pragma unroll
                 for (int k = 0; k < NS; k++) res[k] += v[k];
             }
@@ -220,11 +232,14 @@ __device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Bod
 #pragma unroll
                 for (int q = 0; q < 8; q++) r[k][q] = -0.0;  // x + (-0.0) == x: the first chunk initialises the lanes
             const int len8 = len - (len % 8);
-            for (int i = 0; i < len8; i += 8) {
+            for (int i = 0; i < len8; i += 8, j += 8) {
+                double L[8][NL];
 #pragma unroll
-                for (int q = 0; q < 8; q++, j++) {
+                for (int q = 0; q < 8; q++) load(j + q, L[q]);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
                     double v[NS];
-                    body(j, v);
+                    work(j + q, L[q], v);
 #pragma unroll
                     for (int k = 0; k < NS; k++) r[k][q] += v[k];
                 }
@@ -233,8 +248,9 @@ __device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Bod
             for (int k = 0; k < NS; k++)
                 res[k] = ((r[k][0] + r[k][1]) + (r[k][2] + r[k][3])) + ((r[k][4] + r[k][5]) + (r[k][6] + r[k][7]));
             for (int i = len8; i < len; i++, j++) {
-                double v[NS];
-                body(j, v);
+                double L[NL], v[NS];
+                load(j, L);
+                work(j, L, v);
 #pragma unroll
                 for (int k = 0; k < NS; k++) res[k] += v[k];
             }
@@ -258,34 +274,102 @@ struct CellCtx {
     const PwPlan* plan;
     roger_pow_tables tabs;
     int64_t i;
+    // element offset of age bin j of this cell in a rotated (state) array / in a scratch array
+    __device__ __forceinline__ int64_t ring(int j) const {
+        int p = P.base + j;
+        if (p >= P.A) p -= P.A;
+        return (int64_t)p * P.C + i;
+    }
+    __device__ __forceinline__ int64_t lin(int j) const { return (int64_t)j * P.C + i; }
 };
+
+#ifndef ROGER_SAS_UNROLL
+#define ROGER_SAS_UNROLL 2
+#endif
+
+// One sub-step of the deterministic solver for `n` consecutive bins starting at j0 (transport.py:388-470).  The n values
+// of san / TTn were loaded by the caller (xb, tb); the cumulative SAS function of the n bins is evaluated first --
+// independent evaluations the compiler interleaves -- then the sequentially dependent bookkeeping runs.
+struct SubstepCarry {
+    double acc_in, acc_new, acc_t, om_prev;
+    NpMax mxn;
+};
+template <int U>
+__device__ __forceinline__ void substep_block(const CellCtx& cx, const Family& fam, SubstepCarry& k, int j0, int n, const double* xb,
+                                              const double* tb, bool first, double flux, double h, double fh, double m,
+                                              double* __restrict__ san, double* __restrict__ TTn) {
+    double om[U];
+    double SAv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (u < n) {
+            k.acc_in += xb[u];
+            SAv[u] = first ? k.acc_in * m : k.acc_in;
+        } else SAv[u] = 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) om[u] = (u < n) ? omega(fam, cx.P, cx.tabs, j0 + u + 1, SAv[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (u < n) {
+            const double x = xb[u];
+            const double d = om[u] - k.om_prev;
+            k.om_prev = om[u];
+            double tti = (d >= 0) ? d : 0;
+            const double q = flux * tti * h;
+            const double ttqi = (q > x) ? x : q;
+            tti = ttqi / fh;
+            const double xn = x + -tti * flux * h;
+            const int64_t o = cx.lin(j0 + u);
+            san[o] = xn;
+            k.acc_new += xn;
+            k.mxn.push(k.acc_new);
+            k.acc_t += tti;
+            TTn[o] = (first ? 0.0 : tb[u]) + k.acc_t;
+        }
+    }
+}
 
 // ---- one SAS-controlled withdrawal from layer `src`, optionally received by layer `dst` (dst < 0: leaves the
 // soil).  evapotranspiration.py:653-716, :831-895; subsurface_runoff.py:1531-1625, :1753-1815;
 // capillary_rise.py:404-500.
 __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
                                         double m, double* C_flux, double* C_iso_flux, int process) {
+    constexpr int U = ROGER_SAS_UNROLL;
     const SasParams& P = cx.P;
     const int A = P.A;
     double* __restrict__ sa = cx.pl.sa[src];
     double* __restrict__ msa = cx.pl.msa[src];
     double* __restrict__ san = cx.pl.san;
     double* __restrict__ TTn = cx.pl.TTn;
-    const int64_t i = cx.i;
     const int64_t C = P.C;
     const double h = 1.0 / P.substeps;
     const bool active = (flux * h > 0);  // otherwise every sub-step leaves san and TTn untouched (tti = 0)
 
     if (active) {
-        // cumulative StorAge of the layer (transport.py:343-359) -> S = max(SA)
+        // cumulative StorAge of the layer (transport.py:343-359) -> S = max(SA); the layer's StorAge is copied into the
+        // (unrotated) scratch array the sub-steps work on
         NpMax mx;
         const double SA0 = 0. * m;
         mx.init(SA0);
         {
-            Cursor c(P, i);
             double acc = 0;
-            for (int j = 0; j < A; j++, c.next()) {
-                acc += sa[c.off];
+            int j = 0;
+            for (; j + 8 <= A; j += 8) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = sa[cx.ring(j + q)];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    san[cx.lin(j + q)] = v[q];
+                    acc += v[q];
+                    mx.push(acc * m);
+                }
+            }
+            for (; j < A; j++) {
+                const double v = sa[cx.ring(j)];
+                san[cx.lin(j)] = v;
+                acc += v;
                 mx.push(acc * m);
             }
         }
@@ -294,32 +378,33 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
         const double fh = flux * h;
         for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
             family_prepare(fam, mx.mx);
-            double om_prev = omega(fam, P, cx.tabs, 0, SA0);
-            double acc_in = 0, acc_new = 0, acc_t = 0;
-            NpMax mxn;
-            mxn.init(SA0);
-            const double* __restrict__ X = (s == 0) ? sa : san;
-            Cursor c(P, i);
-            int64_t lin = i;  // scratch arrays are not rotated
-            for (int j = 0; j < A; j++, c.next(), lin += C) {
-                const double x = (s == 0) ? X[c.off] : X[lin];
-                acc_in += x;
-                const double SAj = (s == 0) ? acc_in * m : acc_in;
-                const double om = omega(fam, P, cx.tabs, j + 1, SAj);
-                const double d = om - om_prev;
-                om_prev = om;
-                double tti = (d >= 0) ? d : 0;
-                const double q = flux * tti * h;
-                const double ttqi = (q > x) ? x : q;
-                tti = ttqi / fh;
-                const double xn = x + -tti * flux * h;
-                san[lin] = xn;
-                acc_new += xn;
-                mxn.push(acc_new);
-                acc_t += tti;
-                TTn[lin] = ((s == 0) ? 0.0 : TTn[lin]) + acc_t;
+            SubstepCarry k;
+            k.om_prev = omega(fam, P, cx.tabs, 0, SA0);
+            k.acc_in = 0; k.acc_new = 0; k.acc_t = 0;
+            k.mxn.init(SA0);
+            const bool first = (s == 0);
+            // register double buffer: the loads of block b+1 are in flight while block b is computed
+            double xn_[U], tn_[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                xn_[u] = (u < A) ? san[cx.lin(u)] : 0.0;
+                tn_[u] = (!first && u < A) ? TTn[cx.lin(u)] : 0.0;
             }
-            mx = mxn;
+            int j0 = 0;
+            for (; j0 + U <= A; j0 += U) {
+                double xb[U], tb[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) { xb[u] = xn_[u]; tb[u] = tn_[u]; }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int jn = j0 + U + u;
+                    xn_[u] = (jn < A) ? san[cx.lin(jn)] : 0.0;
+                    tn_[u] = (!first && jn < A) ? TTn[cx.lin(jn)] : 0.0;
+                }
+                substep_block<U>(cx, fam, k, j0, U, xb, tb, first, flux, h, fh, m, san, TTn);
+            }
+            if (j0 < A) substep_block<U>(cx, fam, k, j0, A - j0, xn_, tn_, first, flux, h, fh, m, san, TTn);
+            mx = k.mxn;
         }
     }
 
@@ -330,40 +415,45 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
     double* __restrict__ tt_out = (P.store_tt && cx.pl.tt) ? cx.pl.tt + (size_t)process * (size_t)A * (size_t)C : nullptr;
     const double nsub = (double)P.substeps;
     double prev = 0. / nsub;
-    Cursor c(P, i);
-    int64_t lin = i;
     double sums[2];
-    stream_sums<2>(cx.plan, [&](int j, double* v) {
-        const double cur = (active ? TTn[lin] : 0.) / nsub;
-        double t = cur - prev;
-        prev = cur;
-        const double s_j = sa[c.off];
-        const double q = flux * t;
-        const double ttq = (q > s_j) ? s_j : q;
-        t = (flux > 0) ? ttq / flux : 0;
-        t = t * m;
-        const double ms_j = msa[c.off];
-        const double mtt = ((t > 0) ? ms_j : 0) * m;
-        v[0] = t;
-        v[1] = mtt * t;
-        if (dst >= 0) {
-            const double in = t * flux;
-            const double sd = sa_d[c.off];
-            const double md = msa_d[c.off];
-            const double tot = in + sd;
-            const double mixed = (tot > 0) ? md * (sd / tot) + mtt * (in / tot) : md;
-            msa_d[c.off] = mixed * m;
-            sa_d[c.off] = sd + t * flux * m;
-        }
-        double u = s_j + -flux * t;
-        u = ((u > -1e-5) && (u < 0)) ? 0 : u;
-        u = u * m;
-        sa[c.off] = u;
-        msa[c.off] = ((u <= 0) ? 0 : ms_j) * m;
-        if (tt_out) tt_out[lin] = t;
-        c.next();
-        lin += C;
-    }, sums);
+    stream_sums<2, 5>(cx.plan,
+        [&](int j, double* L) {
+            const int64_t o = cx.ring(j);
+            L[0] = active ? TTn[cx.lin(j)] : 0.;
+            L[1] = sa[o];
+            L[2] = msa[o];
+            if (dst >= 0) { L[3] = sa_d[o]; L[4] = msa_d[o]; }
+        },
+        [&](int j, const double* L, double* v) {
+            const int64_t o = cx.ring(j);
+            const double cur = L[0] / nsub;
+            double t = cur - prev;
+            prev = cur;
+            const double s_j = L[1];
+            const double q = flux * t;
+            const double ttq = (q > s_j) ? s_j : q;
+            t = (flux > 0) ? ttq / flux : 0;
+            t = t * m;
+            const double ms_j = L[2];
+            const double mtt = ((t > 0) ? ms_j : 0) * m;
+            v[0] = t;
+            v[1] = mtt * t;
+            if (dst >= 0) {
+                const double in = t * flux;
+                const double sd = L[3];
+                const double md = L[4];
+                const double tot = in + sd;
+                const double mixed = (tot > 0) ? md * (sd / tot) + mtt * (in / tot) : md;
+                msa_d[o] = mixed * m;
+                sa_d[o] = sd + t * flux * m;
+            }
+            double u = s_j + -flux * t;
+            u = ((u > -1e-5) && (u < 0)) ? 0 : u;
+            u = u * m;
+            sa[o] = u;
+            msa[o] = ((u <= 0) ? 0 : ms_j) * m;
+            if (tt_out) tt_out[cx.lin(j)] = t;
+        }, sums);
     double conc = (sums[0] > 0) ? sums[1] / sums[0] : __longlong_as_double(0x7ff8000000000000LL);
     conc = (conc != 0) ? conc : __longlong_as_double(0x7ff8000000000000LL);
     *C_flux = conc * m;
@@ -402,28 +492,32 @@ __device__ __forceinline__ void storage_and_ageing(const CellCtx& cx, double m, 
     double* __restrict__ s_ss = cx.pl.sa[1];
     double* __restrict__ m_rz = cx.pl.msa[0];
     double* __restrict__ m_ss = cx.pl.msa[1];
-    Cursor c(P, cx.i);
     double sums[6];
-    stream_sums<6>(cx.plan, [&](int j, double* v) {
-        double a = s_rz[c.off];
-        a = (a < 1e-8) ? 0 : a;
-        s_rz[c.off] = a;
-        double b = s_ss[c.off];
-        b = (b < 1e-8) ? 0 : b;
-        s_ss[c.off] = b;
-        const double ma = m_rz[c.off], mb = m_ss[c.off];
-        v[0] = a;
-        v[1] = ma * a;
-        v[2] = b;
-        v[3] = mb * b;
-        const double s = a + b * m;
-        const double tot = a + b;
-        double ms = (tot > 0) ? ma * (a / tot) + mb * (b / tot) : 0;
-        ms = isnan_d(ms) ? 0 : ms;
-        v[4] = s;
-        v[5] = ms * s;
-        c.next();
-    }, sums);
+    stream_sums<6, 4>(cx.plan,
+        [&](int j, double* L) {
+            const int64_t o = cx.ring(j);
+            L[0] = s_rz[o]; L[1] = s_ss[o]; L[2] = m_rz[o]; L[3] = m_ss[o];
+        },
+        [&](int j, const double* L, double* v) {
+            const int64_t o = cx.ring(j);
+            double a = L[0];
+            a = (a < 1e-8) ? 0 : a;
+            s_rz[o] = a;
+            double b = L[1];
+            b = (b < 1e-8) ? 0 : b;
+            s_ss[o] = b;
+            const double ma = L[2], mb = L[3];
+            v[0] = a;
+            v[1] = ma * a;
+            v[2] = b;
+            v[3] = mb * b;
+            const double s = a + b * m;
+            const double tot = a + b;
+            double ms = (tot > 0) ? ma * (a / tot) + mb * (b / tot) : 0;
+            ms = isnan_d(ms) ? 0 : ms;
+            v[4] = s;
+            v[5] = ms * s;
+        }, sums);
     const double C_rz = ((sums[0] > 0) ? sums[1] / sums[0] : 0) * m;
     const double C_ss = ((sums[2] > 0) ? sums[3] / sums[2] : 0) * m;
     const double C_s = ((sums[4] > 0) ? sums[5] / sums[4] : 0) * m;
