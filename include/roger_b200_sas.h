@@ -78,6 +78,9 @@ int roger_sas_download_tt(roger_sas *h, int process, double *host);
  * roger_b200/csrc/roger_pow.h (host pointers, n doubles each): the parity tests use it to prove that the device and
  * the host evaluate the shared power function to identical bits. */
 int roger_pow_device(const double *x, const double *y, double *out, int64_t n, int device);
+/* self-test of the kernel's hoisted-reciprocal division (sas_device.cuh div_by) against the division instruction on n
+ * pseudo-random operand pairs; *mismatches must come back 0 */
+int roger_selftest_division(int64_t n, uint64_t seed, int device, int64_t *mismatches);
 int roger_sas_synchronize(roger_sas *h);
 int roger_sas_last_timing(roger_sas *h, double *kernel_ms, int64_t *launches);
 

@@ -154,6 +154,33 @@ __global__ void k_pow_array(const double* __restrict__ x, const double* __restri
         out[i] = use_exp ? roger_exp(x[i], tabs) : roger_pow(x[i], y[i], tabs);
 }
 
+// div_by() against the division instruction on pseudo-random operand pairs (splitmix64 bits -> doubles with
+// exponents inside the guarded range, quotients on both sides of one)
+__global__ void k_div_selftest(uint64_t seed, int64_t n, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(t + 1);
+        uint64_t w[2];
+        for (int k = 0; k < 2; k++) {
+            z += 0x9E3779B97F4A7C15ULL;
+            uint64_t x = z;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+            w[k] = x ^ (x >> 31);
+        }
+        // mantissas random; exponents: b in 2^[-40, 40], a = b * 2^[-60, 4] (a / b mostly below one, as SA / S)
+        const int eb = (int)((w[0] >> 52) % 81) - 40;
+        const int ea = eb + (int)((w[1] >> 52) % 65) - 60;
+        const double b = __longlong_as_double((long long)(((uint64_t)(1023 + eb) << 52) | (w[0] & 0xFFFFFFFFFFFFFULL)));
+        double a = __longlong_as_double((long long)(((uint64_t)(1023 + ea) << 52) | (w[1] & 0xFFFFFFFFFFFFFULL)));
+        if ((t & 7) == 0) a = -a;
+        if ((t & 1023) == 5) a = b;  // quotient exactly one
+        const double q = rsas::div_by(a, b, 1.0 / b);
+        if (q != a / b) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ================================================================================================
 struct roger_sas {
     int64_t C = 0;
@@ -411,6 +438,26 @@ int roger_pow_device(const double* x, const double* y, double* out, int64_t n, i
     CU(cudaGetLastError());
     CU(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return 0;
+}
+
+// number of operand pairs (out of n) for which the hoisted-reciprocal division of the SAS kernel differs from the
+// division instruction; the parity tests require 0
+int roger_selftest_division(int64_t n, uint64_t seed, int device, int64_t* mismatches) {
+    if (n <= 0 || !mismatches) return fail(ROGER_EINVAL, "roger_selftest_division: bad argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(ROGER_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    CU(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, sizeof(unsigned long long)));
+    k_div_selftest<<<148 * 8, 256>>>(seed, n, d);
+    CU(cudaGetLastError());
+    unsigned long long hbad = 0;
+    CU(cudaMemcpy(&hbad, d, sizeof hbad, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches = (int64_t)hbad;
     return 0;
 }
 

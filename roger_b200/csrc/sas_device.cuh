@@ -71,18 +71,34 @@ struct Cursor {
 
 __device__ __forceinline__ bool isnan_d(double x) { return x != x; }
 
-// running np.max (propagates the first NaN, as npx.max does)
+// running np.max: npx.max returns the first NaN it meets, else the maximum.  Which NaN is returned is unobservable
+// (the result only enters comparisons and arithmetic), so a sticky flag replaces the early exit.
 struct NpMax {
     double mx;
     bool nan;
     __device__ __forceinline__ void init(double a0) { mx = a0; nan = false; }
     __device__ __forceinline__ void push(double a) {
-        if (!nan) {
-            if (isnan_d(a)) { mx = a; nan = true; }
-            else if (a > mx) mx = a;
-        }
+        nan = nan || isnan_d(a);
+        mx = (a > mx) ? a : mx;
     }
+    __device__ __forceinline__ double get() const { return nan ? __longlong_as_double(0x7ff8000000000000LL) : mx; }
 };
+
+// a / b for a divisor that is constant over a loop: rb = 1 / b (correctly rounded, computed once), then two
+// fma-corrected quotient refinements.  With rb = RN(1/b) and a faithful quotient the last fma returns the correctly
+// rounded a / b (Markstein's theorem) as long as nothing under- or overflows: div_range_ok() guards that, callers
+// fall back to the division instruction otherwise.  tests/test_sas_gpu.py checks the equality on 1e8 random pairs.
+__device__ __forceinline__ double div_by(double a, double b, double rb) {
+    double q = __dmul_rn(a, rb);
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, rb, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, rb, q);
+}
+__device__ __forceinline__ bool div_range_ok(double v) {  // |v| in [2^-500, 2^500]
+    const unsigned e = (unsigned)((roger_pow_asu(v) >> 52) & 0x7ff);
+    return (e - 523u) <= 1000u;
+}
 
 __device__ __forceinline__ double conc_to_delta(const SasParams& P, double conc) {  // transport.py:328-340
     const double d = 1000. * (conc / (P.vsmow * (1. - conc)) - 1.);
@@ -330,6 +346,71 @@ __device__ __forceinline__ void substep_block(const CellCtx& cx, const Family& f
     }
 }
 
+// The sub-step pass of the benchmark configuration -- power-law SAS function, cell inside the catchment (m == 1),
+// S and flux * h in the range where div_by() is exact -- with everything that is constant over the age axis hoisted:
+// same operations on the same values as substep_block<> / omega(), far fewer instructions.
+template <int U>
+__device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, double y, bool first, double flux, double h, double fh,
+                                                   double* __restrict__ san, double* __restrict__ TTn) {
+    const int A = cx.P.A;
+    const int64_t C = cx.P.C;
+    const double rS = 1.0 / S, rfh = 1.0 / fh;
+    const roger_pow_tables tabs = cx.tabs;
+    double acc_in = 0, acc_new = 0, acc_t = 0, om_prev = 0.0;
+    double mxv = 0.0;  // SA[0] = 0 * m
+    bool anynan = false;
+    int64_t o = cx.i;       // offset of the block being computed
+    double xn_[U], tn_[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        xn_[u] = (u < A) ? san[o + u * C] : 0.0;
+        tn_[u] = (!first && u < A) ? TTn[o + u * C] : 0.0;
+    }
+    for (int j0 = 0; j0 < A; j0 += U, o += U * C) {
+        double xb[U], tb[U], om[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { xb[u] = xn_[u]; tb[u] = tn_[u]; }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = (j0 + U + u < A);
+            xn_[u] = ok ? san[o + (U + u) * C] : 0.0;
+            tn_[u] = (!first && ok) ? TTn[o + (U + u) * C] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            acc_in += (j0 + u < A) ? xb[u] : 0.0;
+            const double SA = acc_in;
+            const bool in = (SA > 0) && (SA <= S);
+            const double xr = div_by(SA, S, rS);
+            const uint64_t ixr = roger_pow_asu(xr);
+            const bool easy = in && roger_pow_is_pos_normal(ixr) && div_range_ok(SA);
+            double p = roger_pow_core(easy ? ixr : 0x3fe0000000000000ULL, y, tabs);
+            if (in && !easy) p = roger_pow(SA / S, y, tabs);
+            om[u] = (SA > 0) ? ((SA <= S) ? p : 1.) : 0.;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (j0 + u < A) {
+                const double x = xb[u];
+                const double d = om[u] - om_prev;
+                om_prev = om[u];
+                double tti = (d >= 0) ? d : 0;
+                const double q = flux * tti * h;
+                const double ttqi = (q > x) ? x : q;
+                tti = (ttqi == 0 || div_range_ok(ttqi)) ? div_by(ttqi, fh, rfh) : ttqi / fh;
+                const double xn = x + -tti * flux * h;
+                san[o + u * C] = xn;
+                acc_new += xn;
+                anynan = anynan || isnan_d(acc_new);
+                mxv = (acc_new > mxv) ? acc_new : mxv;
+                acc_t += tti;
+                TTn[o + u * C] = (first ? 0.0 : tb[u]) + acc_t;
+            }
+        }
+    }
+    return anynan ? __longlong_as_double(0x7ff8000000000000LL) : mxv;
+}
+
 // ---- one SAS-controlled withdrawal from layer `src`, optionally received by layer `dst` (dst < 0: leaves the
 // soil).  evapotranspiration.py:653-716, :831-895; subsurface_runoff.py:1531-1625, :1753-1815;
 // capillary_rise.py:404-500.
@@ -377,12 +458,17 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
         family_begin(fam, sp_global, sp_stride, m);
         const double fh = flux * h;
         for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
-            family_prepare(fam, mx.mx);
+            family_prepare(fam, mx.get());
+            const bool first = (s == 0);
+            if (fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh)) {
+                const double S_next = substep_pass_pow<U>(cx, fam.S, fam.sp[1], first, flux, h, fh, san, TTn);
+                mx.init(S_next);
+                continue;
+            }
             SubstepCarry k;
             k.om_prev = omega(fam, P, cx.tabs, 0, SA0);
             k.acc_in = 0; k.acc_new = 0; k.acc_t = 0;
             k.mxn.init(SA0);
-            const bool first = (s == 0);
             // register double buffer: the loads of block b+1 are in flight while block b is computed
             double xn_[U], tn_[U];
 #pragma unroll

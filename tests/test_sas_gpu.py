@@ -56,6 +56,16 @@ def test_device_pow_is_bit_identical_to_host_pow():
     assert u.same(oute, np.array([L.roger_exp_host(v) for v in xe]))
 
 
+def test_hoisted_division_equals_division_instruction():
+    from roger_b200.engine import load_library, _check
+
+    lib = load_library()
+    lib.roger_selftest_division.argtypes = [C.c_int64, C.c_uint64, C.c_int, C.POINTER(C.c_int64)]
+    bad = C.c_int64(-1)
+    _check(lib, lib.roger_selftest_division(200_000_000, 12345, 0, C.byref(bad)))
+    assert bad.value == 0
+
+
 @pytest.mark.parametrize("case", u.SAS_CASES)
 def test_cuda_equals_oracle_bit_for_bit_on_fixture_inputs(case, oracle_roger_pow):
     fx = u.load_case(case)
