@@ -29,6 +29,11 @@ from roger_b200.svat import SvatModel  # noqa: E402
 
 # algorithmic bytes per cell-timestep (2*state + parameters + forcing)
 ALGO_BYTES = {"svat": 984.0, "oned": 1200.0}
+
+
+def sas_algo_bytes(ages):
+    """each of sa_rz, sa_ss, msa_rz, msa_ss read and written once per day + forcing + scalar outputs"""
+    return 64.0 * ages + 344.0
 START_DOY = 121  # 1 May: rain events, hourly and daily steps, no snow
 
 
@@ -109,6 +114,32 @@ def run_reference(args):
     from oracle.engine import OracleSvatEngine
 
     cores = os.cpu_count() or 1
+    if args.workload == "sas":
+        from oracle.engine import OracleSasEngine
+        from roger_b200 import sas
+
+        cells = args.ref_cells
+        daily = sas_daily_tile(OracleSvatEngine, args.steps + args.warmup + 2)
+        eng = OracleSasEngine(cells, sas.default_settings(args.ages))
+        model = SasBenchModel(eng, cells, args.ages, daily)
+        for _ in range(args.warmup):
+            eng.step(model.day_forcing())
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.step(model.day_forcing())
+        el = time.perf_counter() - t0
+        v = cells * args.steps / el
+        print(json.dumps({
+            "impl": "reference", "metric": "cell-timesteps/s", "value": v, "unit": "cell-timesteps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"svat_oxygen18 offline SAS transport {args.sas_side}x{args.sas_side} cells per GPU, {args.ages} age bins, "
+                                   "power-law SAS (SVATOXYGEN18_benchmark.py), 6 sub-steps"},
+            "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port",
+                             "sample": f"{cells} cells x {args.ages} age bins of the same workload, {args.steps} daily steps, OpenMP over cells"},
+            "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
     side = args.ref_side
     shape = (side, side)
     m = build_model(OracleSvatEngine, shape, args.workload, seed=43)
@@ -143,6 +174,23 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from roger_b200.engine import CudaSvatEngine
+
+    if args.workload == "sas":
+        sampler = ClockSampler(local)
+        sampler.start()
+        res = run_sas_cuda(args, local, world, rank, dist if world > 1 else None, args.steps, max(args.warmup, 1), args.sas_side, args.ages)
+        clocks = sampler.stop()
+        if rank == 0:
+            line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": res["steps"],
+                    "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(res["config"], parallelism=f"cell-block x{world}"),
+                    "roofline": res["roofline"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks}
+            if world == 1 and not args.no_cpu_baseline:
+                line["cpu_baseline"] = sas_cpu_baseline(args.ages, cells=args.ref_cells)
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     side = args.side
     shape = (side, side)
@@ -214,6 +262,14 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * C * args.steps / float(t[0])
 
+    sas_res = None
+    if not args.no_sas:
+        # second half of the BASELINE metric: SVAT + offline oxygen-18 SAS transport (configs[2]) on the same GPU(s)
+        eng.close()
+        del m
+        torch.cuda.empty_cache()
+        sas_res = run_sas_cuda(args, local, world, rank, dist if world > 1 else None, min(args.steps, args.sas_steps), 3, args.sas_side, args.ages)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         algo = ALGO_BYTES[args.workload]
@@ -234,11 +290,163 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if sas_res is not None:
+            line["sas"] = sas_res
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+            if sas_res is not None:
+                line["sas"]["cpu_baseline"] = sas_cpu_baseline(args.ages, cells=args.ref_cells)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SVAT + offline oxygen-18 StorAge-selection transport (BASELINE.json configs[2]: power-law SAS, 1024x1024 cells)
+SAS_SPEC = dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))  # SVATOXYGEN18_benchmark.py:129-138
+SAS_TILE = (64, 64)
+
+
+def sas_daily_tile(svat_engine_cls, ndays, engine_kwargs=None):
+    """Daily hydrologic forcing of the transport model: an online SVAT run (the product's own SVAT path on the GPU arm,
+    the oracle on the CPU arm) of a heterogeneous 64x64 tile, aggregated per day as the reference's
+    test/make_data_for_svat_transport.py:279-300 does.  The tile is repeated over the transport grid."""
+    from roger_b200 import sas_inputs
+
+    forcing = synth.mixed_forcing(ndays + 2, seed=42, start_doy=START_DOY)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(SAS_TILE, seed=44)
+    m = SvatModel(svat_engine_cls, SAS_TILE, forcing, prim, th_rz, th_ss, engine_kwargs=engine_kwargs)
+    m.setup()
+    daily = sas_inputs.daily_fluxes_from_svat(m, ndays)
+    if hasattr(m.engine, "close"):
+        m.engine.close()
+    rng = np.random.default_rng(45)
+    daily["C_ISO_IN"] = rng.uniform(-12, -5, daily["PREC"].shape)
+    return daily
+
+
+class SasBenchModel:
+    """The driver loop of the offline transport benchmark over a tiled grid: per day, the host-side `set_forcing`
+    (roger_b200.sas.SasModel._set_forcing on the tile) expanded to all cells, one engine step."""
+
+    def __init__(self, engine, n_cells, ages, daily_tile):
+        from roger_b200 import sas
+
+        self.sas = sas
+        self.engine = engine
+        self.C = n_cells
+        nt = daily_tile["PREC"].shape[0]
+        self.tile = sas.SasModel(_NullEngine, nt, ages, daily_tile, SAS_SPEC)
+        self.idx = np.arange(n_cells) % nt
+        engine.set_parameters(np.ones(n_cells), sas.sas_parameter_block(n_cells, SAS_SPEC))
+        if hasattr(engine, "init_linear"):
+            engine.init_linear(daily_tile["S_RZ"][self.idx, 0], daily_tile["S_SS"][self.idx, 0], float(sas.delta_to_conc(-10.0)))
+        else:
+            c0 = float(sas.delta_to_conc(-10.0))
+            msa = np.full((n_cells, ages), c0)
+            msa[:, 0] = 0
+            engine.upload_state("sa_rz", sas.initial_age_distribution(daily_tile["S_RZ"][self.idx, 0], ages))
+            engine.upload_state("sa_ss", sas.initial_age_distribution(daily_tile["S_SS"][self.idx, 0], ages))
+            engine.upload_state("msa_rz", msa)
+            engine.upload_state("msa_ss", msa.copy())
+
+    def day_forcing(self):
+        """host planes (9, C) of the next day"""
+        self.tile.itt += 1
+        f = self.tile._set_forcing()
+        self.tile.C_snow[:, 0] = self.tile.C_snow[:, 1]
+        return np.ascontiguousarray(f[:, self.idx])
+
+
+class _NullEngine:
+    def __init__(self, *a, **k):
+        pass
+
+
+def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages):
+    """Returns the `sas` result dict (value / roofline / e2e) measured on this rank's GPU, max over ranks."""
+    import torch
+    from roger_b200 import sas
+    from roger_b200.engine import CudaSvatEngine
+    from roger_b200.sas_engine import CudaSasEngine
+
+    C = side * side
+    ndays = 2 * (steps + warmup) + 1
+    daily = sas_daily_tile(CudaSvatEngine, ndays, engine_kwargs={"device": local})
+    eng = CudaSasEngine(C, sas.default_settings(ages), device=local)
+    model = SasBenchModel(eng, C, ages, daily)
+    host_days = [model.day_forcing() for _ in range(ndays - 1)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # value: forcing planes already resident in HBM
+    dev_days = [torch.from_numpy(f).to(f"cuda:{local}") for f in host_days[: steps + warmup]]
+    for d in range(warmup):
+        eng.step_device(dev_days[d].data_ptr())
+    barrier()
+    eng.kernel_ms = 0.0
+    eng.launches = 0
+    t0 = time.perf_counter()
+    for d in range(warmup, warmup + steps):
+        eng.step_device(dev_days[d].data_ptr())
+    eng.synchronize()
+    wall = time.perf_counter() - t0
+    kernel_ms, launches = eng.kernel_ms, eng.launches
+    del dev_days
+    # e2e: host forcing planes in, per-cell result planes (22 concentrations / delta values) out, every day
+    pinned = [torch.from_numpy(f).pin_memory() for f in host_days[steps + warmup: 2 * steps + warmup]]
+    out = None
+    barrier()
+    t0 = time.perf_counter()
+    for f in pinned:
+        eng.step(f.numpy())
+        out = eng.download_outputs()
+    eng.synchronize()
+    e2e_wall = time.perf_counter() - t0
+    t = torch.tensor([wall, kernel_ms / 1e3, e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, kern, e2e_wall = (float(v) for v in t)
+    peak, peak_src = measured_peak()
+    algo = sas_algo_bytes(ages)
+    ach = algo * C * steps / kern / 1e9
+    finite = float(np.isfinite(out[sas.OUTPUTS.index("C_rz")]).mean())
+    eng.close()
+    return {
+        "metric": "cell-timesteps/s", "value": world * C * steps / wall, "unit": "cell-timesteps/s", "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * wall / steps,
+        "config": {"workload": f"svat_oxygen18 offline SAS transport {side}x{side} cells per GPU, {ages} age bins, power-law SAS "
+                               "(SVATOXYGEN18_benchmark.py), 6 sub-steps, daily forcing from an online SVAT run of a 64x64 tile",
+                   "cells_per_gpu": C, "ages": ages,
+                   "l2": "age-ranked state is %.1f GB per GPU, far larger than the 126 MB L2" % (C * ages * 8 * 4 / 1e9)},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_cell_timestep": algo, "kernel_ms_per_step": 1e3 * kern / steps,
+                     "note": "exact-order solver streams its two scratch arrays once per sub-step: measured DRAM traffic is ~20x the "
+                             "algorithmic bytes (profiles/), see DESIGN.md"},
+        "e2e": {"value": world * C * steps / e2e_wall, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 9 * 8 * C,
+                "d2h_bytes_per_step": len(sas.OUTPUTS) * 8 * C},
+        "gpu_launches": int(launches), "finite_C_rz_fraction": finite,
+    }
+
+
+def sas_cpu_baseline(ages, cells=192, days=2):
+    from oracle.engine import OracleSasEngine, OracleSvatEngine
+    from roger_b200 import sas
+
+    daily = sas_daily_tile(OracleSvatEngine, days + 2)
+    eng = OracleSasEngine(cells, sas.default_settings(ages))
+    model = SasBenchModel(eng, cells, ages, daily)
+    eng.step(model.day_forcing())
+    t0 = time.perf_counter()
+    for _ in range(days):
+        eng.step(model.day_forcing())
+    el = time.perf_counter() - t0
+    return {"value": cells * days / el, "unit": "cell-timesteps/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{cells} cells x {ages} age bins of the same workload, {days} daily steps, OpenMP over cells"}
 
 
 def cpu_baseline(args):
@@ -263,7 +471,12 @@ def main():
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
-    ap.add_argument("--workload", choices=["svat", "oned"], default="oned")
+    ap.add_argument("--workload", choices=["svat", "oned", "sas"], default="oned")
+    ap.add_argument("--sas-side", type=int, default=1024, help="SAS transport grid side per GPU (configs[2]: 1024)")
+    ap.add_argument("--ages", type=int, default=1500, help="age bins of the SAS transport (BASELINE: ~1500)")
+    ap.add_argument("--sas-steps", type=int, default=4, help="timed daily steps of the secondary SAS measurement")
+    ap.add_argument("--ref-cells", type=int, default=2048, help="cells of the CPU sample of the SAS workload")
+    ap.add_argument("--no-sas", action="store_true", help="skip the secondary SVAT + oxygen-18 SAS measurement")
     ap.add_argument("--side", type=int, default=4096)
     ap.add_argument("--ref-side", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
