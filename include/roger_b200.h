@@ -77,6 +77,11 @@ int roger_svat_field_kind(int field);
  *      for the fields the step owns, roger/state.py:213-251).  `host` holds n_cells doubles. */
 int roger_svat_upload(roger_svat *h, int field, const double *host);
 int roger_svat_download(roger_svat *h, int field, double *host);
+/* Asynchronous diagnostic read-back (replaces the reference's threaded netCDF hand-over, roger/io_tools/netcdf.py:145-210):
+ * snapshots the plane as of the steps issued so far and copies it to `host_pinned` (page-locked, n_cells doubles) on a
+ * second stream while later steps run.  The buffer is valid after roger_svat_download_wait(). */
+int roger_svat_download_async(roger_svat *h, int field, double *host_pinned);
+int roger_svat_download_wait(roger_svat *h);
 /* raw device address of a plane (for zero-copy use from torch / other kernels) */
 uint64_t roger_svat_plane_ptr(roger_svat *h, int field);
 

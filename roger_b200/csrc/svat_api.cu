@@ -251,6 +251,9 @@ struct roger_svat {
     bool ks_ss_synced = false;
     bool have_forcing = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // asynchronous diagnostic read-back (roger_svat_download_async)
+    std::vector<double*> snap_free, snap_busy;   // device snapshot planes
+    cudaEvent_t ev_snap = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_kernel_ms = 0;
     int64_t last_launches = 0;
@@ -318,6 +321,10 @@ void roger_svat_destroy(roger_svat* h) {
     cudaFree(h->d_fl);
     cudaFree(h->d_prec_m1);
     for (auto p : h->d_forc) cudaFree(p);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (auto p : h->snap_free) cudaFree(p);
+    for (auto p : h->snap_busy) cudaFree(p);
+    if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     cudaFree(h->d_flags);
     cudaFreeHost(h->h_flags);
     cudaEventDestroy(h->ev0);
@@ -343,6 +350,38 @@ int roger_svat_download(roger_svat* h, int field, double* host) {
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
     CU(cudaMemcpyAsync(host, h->planes().at(field), sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// Snapshot of a plane as of the steps issued so far, copied to the host off the critical path: a device-to-device copy
+// on the compute stream (microseconds), then the PCIe transfer on a second stream while later steps run.
+int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
+    if (!h || !host_pinned || field < 0 || field >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_download_async: bad argument");
+    CU(cudaSetDevice(h->device));
+    if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
+    if (!h->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+    }
+    const size_t plane = sizeof(double) * (size_t)h->C;
+    double* snap = nullptr;
+    if (!h->snap_free.empty()) { snap = h->snap_free.back(); h->snap_free.pop_back(); }
+    else CU(cudaMalloc(&snap, plane));
+    h->snap_busy.push_back(snap);
+    CU(cudaMemcpyAsync(snap, h->planes().at(field), plane, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaEventRecord(h->ev_snap, h->stream));
+    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    CU(cudaMemcpyAsync(host_pinned, snap, plane, cudaMemcpyDeviceToHost, h->copy_stream));
+    return 0;
+}
+
+int roger_svat_download_wait(roger_svat* h) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_download_wait: null handle");
+    if (!h->copy_stream) return 0;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->copy_stream));
+    for (auto p : h->snap_busy) h->snap_free.push_back(p);
+    h->snap_busy.clear();
     return 0;
 }
 

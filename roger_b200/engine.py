@@ -42,6 +42,8 @@ def load_library():
     lib.roger_svat_field_kind.argtypes = [C.c_int]
     lib.roger_svat_upload.argtypes = [hp, C.c_int, dp]
     lib.roger_svat_download.argtypes = [hp, C.c_int, dp]
+    lib.roger_svat_download_async.argtypes = [hp, C.c_int, dp]
+    lib.roger_svat_download_wait.argtypes = [hp]
     lib.roger_svat_plane_ptr.argtypes = [hp, C.c_int]
     lib.roger_svat_plane_ptr.restype = C.c_uint64
     lib.roger_svat_set_scalars.argtypes = [hp, C.POINTER(abi.SvatScalars)]
@@ -113,6 +115,16 @@ class CudaSvatEngine:
         out = np.empty(self.n, dtype=np.float64)
         _check(self.lib, self.lib.roger_svat_download(self.h, abi.FIELD_ID[name], self._dp(out)))
         return out
+
+    def download_async(self, name, host_pinned):
+        """host_pinned: page-locked float64 array of n_cells values (e.g. a pinned torch tensor's .numpy()); valid after
+        download_wait()."""
+        if host_pinned.size != self.n or host_pinned.dtype != np.float64 or not host_pinned.flags["C_CONTIGUOUS"]:
+            raise ValueError("download_async: contiguous float64 buffer of n_cells values expected")
+        _check(self.lib, self.lib.roger_svat_download_async(self.h, abi.FIELD_ID[name], self._dp(host_pinned)))
+
+    def download_wait(self):
+        _check(self.lib, self.lib.roger_svat_download_wait(self.h))
 
     def plane_ptr(self, name):
         return int(self.lib.roger_svat_plane_ptr(self.h, abi.FIELD_ID[name]))

@@ -1,0 +1,189 @@
+"""Drop-in step driver for an existing RoGeR setup: runs `RogerSetup.step` (roger/roger.py:355-489, online SVAT / oneD
+branch) with the per-cell work on the CUDA engine while the setup's own hooks (`read_data`, `set_boundary_conditions`,
+`set_forcing`, `set_parameters`, `after_timestep`), its `RogerState`, `RogerVariables` and tau/taum1 time levels stay
+exactly as the reference defines them.
+
+    model = MySvatSetup()          # any RogerSetup subclass of the online SVAT / oneD family, unchanged
+    model.setup()
+    driver = CudaStepDriver(model) # uploads the post-setup state
+    while vs.time < runlen:
+        driver.step()              # instead of model.step(model.state)
+
+`INTEGRATION.md` shows the few lines that make `roger.runtime_settings.backend = "cuda"` route `RogerSetup.step` here.
+This module imports nothing from the reference: it only touches the objects it is handed (duck typing on
+`setup.state.variables / settings / var_meta`), so it is importable without RoGeR installed.
+
+Coherence contract.  The engine owns the per-cell state between steps.  After every step the variables named in `pull`
+(default: every state and flux plane that is an active reference variable) are written back into `vs.<name>[2:-2, 2:-2
+(, tau)]` so that `after_timestep`, diagnostics and user code observe the values the NumPy backend would have produced;
+host-side changes of parameter arrays (e.g. the monthly land-use refresh in `set_parameters`, models/svat/svat.py:116-120)
+are detected by array identity -- the reference's `update()` returns new arrays -- and re-uploaded before the step.
+State arrays modified by user code between steps must be announced with `driver.push(name)`.
+"""
+import numpy as np
+
+from . import abi
+
+DAY = 24 * 60 * 60
+_SCALARS = ("time", "itt", "dt_secs", "itt_day", "event_id_counter", "time_event0")
+
+
+class CudaStepDriver:
+    def __init__(self, setup, engine_cls=None, engine_kwargs=None, pull="all", forcing_uniform=None,
+                 clamp_small_negative_storage=None):
+        if engine_cls is None:
+            from .engine import CudaSvatEngine as engine_cls  # no fallback: raises without the CUDA library / a device
+        self.setup = setup
+        self.state = setup.state
+        vs, st = self.state.variables, self.state.settings
+        if getattr(st, "enable_offline_transport", False):
+            raise ValueError("CudaStepDriver drives the online SVAT / oneD models; use roger_b200.sas for offline transport")
+        for flag in ("enable_groundwater", "enable_groundwater_boundary", "enable_film_flow", "enable_crop_phenology", "enable_routing"):
+            if getattr(st, flag, False):
+                raise NotImplementedError(f"settings.{flag} is outside the CUDA hot path (DESIGN.md section 7)")
+        self.nx, self.ny = int(st.nx), int(st.ny)
+        self.C = self.nx * self.ny
+        self.lateral = bool(getattr(st, "enable_lateral_flow", False))
+        self._uniform = forcing_uniform
+        self._clamp = (not self.lateral) if clamp_small_negative_storage is None else bool(clamp_small_negative_storage)
+        self._engine_cls = engine_cls
+        self._engine_kwargs = dict(engine_kwargs or {})
+        self.engine = None
+        meta = self.state.var_meta
+        self._active = {n for n, m in meta.items() if m.active}
+        kinds = dict(zip(abi.FIELD_NAMES, abi.FIELD_KINDS))
+        if pull == "all":
+            pull = [n for n in abi.FIELD_NAMES if kinds[n] in "SF" and n in self._active]
+            pull.append("ks_ss")  # the one parameter plane a step writes (subsoil.calc_ks, roger/core/subsoil.py:6-20)
+        self.pull = list(pull)
+        self._write_fluxes = any(kinds[n] == "F" for n in self.pull)
+        self._param_ids = {}
+        self._pushed = set()
+
+    # ------------------------------------------------------------------ vs <-> planes
+    def _interior(self, name):
+        vs = self.state.variables
+        if name == "maskRiverLake":
+            a = np.asarray(vs.maskRiver) | np.asarray(vs.maskLake)
+            return a[2:-2, 2:-2].reshape(-1).astype(np.float64)
+        a = np.asarray(getattr(vs, name))
+        if a.ndim == 3:
+            a = a[:, :, int(vs.tau)]
+        return a[2:-2, 2:-2].reshape(-1).astype(np.float64)
+
+    def _store(self, name, values):
+        vs = self.state.variables
+        cur = np.array(getattr(vs, name))  # copy: reference arrays are read-only
+        v = values.reshape(self.nx, self.ny).astype(cur.dtype)
+        if cur.ndim == 3:
+            cur[2:-2, 2:-2, int(vs.tau)] = v
+        else:
+            cur[2:-2, 2:-2] = v
+        setattr(vs, name, cur)
+        if name in self._param_ids:
+            self._param_ids[name] = id(getattr(vs, name))
+
+    def _settings_struct(self, uniform):
+        st = self.state.settings
+        over = {}
+        for k in ("ta_fm", "hpi", "end_event", "sf", "rmax", "r_mp", "l_sc", "pi", "transp_water_stress", "dx", "atol", "rtol"):
+            if hasattr(st, k):
+                over[k] = float(getattr(st, k))
+        s = abi.default_settings(lateral=self.lateral, forcing_uniform=uniform, **over)
+        s.enable_macropore_lower_boundary_condition = int(bool(getattr(st, "enable_macropore_lower_boundary_condition", False)))
+        s.clamp_small_negative_storage = int(self._clamp)
+        return s
+
+    def _create_engine(self, uniform):
+        self.engine = self._engine_cls(self.C, self._settings_struct(uniform), **self._engine_kwargs)
+        vs = self.state.variables
+        zeros = np.zeros(self.C)
+        for name in abi.FIELD_NAMES:
+            if name == "maskRiverLake" or name in self._active:
+                self.engine.upload(name, self._interior(name))
+                if abi.FIELD_KINDS[abi.FIELD_ID[name]] == "P" and name != "maskRiverLake":
+                    self._param_ids[name] = id(getattr(vs, name))
+            else:
+                self.engine.upload(name, zeros)
+
+    def push(self, name):
+        """Announce that user code changed `vs.<name>` on the host; it is uploaded before the next step."""
+        self._pushed.add(name)
+
+    # ------------------------------------------------------------------ the step
+    def _scalars_to_engine(self):
+        vs = self.state.variables
+        sc = abi.SvatScalars()
+        for k in _SCALARS:
+            setattr(sc, k, int(np.asarray(getattr(vs, k))))
+        sc.event_id[0], sc.event_id[1] = int(vs.event_id[0]), int(vs.event_id[1])
+        sc.month = int(vs.month[int(vs.tau)])
+        sc.dt = float(np.asarray(vs.dt))
+        sc.sanity_ok = 1
+        self.engine.set_scalars(sc)
+
+    def _scalars_from_engine(self):
+        vs = self.state.variables
+        sc = self.engine.get_scalars()
+        with vs.unlock():
+            for k in _SCALARS:
+                setattr(vs, k, getattr(sc, k))
+            vs.dt = sc.dt
+            ev = np.array(vs.event_id)
+            # engine.step ends with the after_timestep roll (event_id[taum1] <- event_id[tau]); the reference's hook redoes it
+            ev[int(vs.tau)] = sc.event_id[1]
+            vs.event_id = ev
+        return sc
+
+    def _hand_forcing_day(self):
+        vs = self.state.variables
+        blocks = [np.asarray(getattr(vs, n))[2:-2, 2:-2, :].reshape(self.C, abi.SLOTS_PER_DAY) for n in ("prec_day", "ta_day", "pet_day")]
+        uniform_today = all((b == b[0]).all() | (np.isnan(b).all()) for b in blocks)
+        if self.engine is None:
+            uniform = uniform_today if self._uniform is None else bool(self._uniform)
+            self._create_engine(uniform)
+            self._uniform = uniform
+        if self._uniform:
+            if not uniform_today:
+                raise RuntimeError("forcing differs between cells but the engine was created for spatially uniform forcing; "
+                                   "construct CudaStepDriver(..., forcing_uniform=False)")
+            self.engine.set_forcing_day(*[b[0].copy() for b in blocks])
+        else:
+            self.engine.set_forcing_day(*[np.ascontiguousarray(b, dtype=np.float64) for b in blocks])
+
+    def step(self):
+        setup, state = self.setup, self.state
+        vs = state.variables
+        setup._ensure_setup_done()
+        setup.read_data(state)
+        setup.set_boundary_conditions(state)
+        setup.set_forcing(state)
+        if int(np.asarray(vs.time)) % DAY == 0 or self.engine is None:
+            self._hand_forcing_day()
+        setup.set_parameters(state)
+        for name, old in list(self._param_ids.items()):  # host-side parameter refresh (monthly land use)
+            if id(getattr(vs, name)) != old:
+                self.engine.upload(name, self._interior(name))
+                self._param_ids[name] = id(getattr(vs, name))
+        for name in self._pushed:
+            self.engine.upload(name, self._interior(name))
+        self._pushed.clear()
+        self._scalars_to_engine()
+        self.engine.step(self._write_fluxes)
+        sc = self._scalars_from_engine()
+        with vs.unlock():
+            for name in self.pull:
+                self._store(name, self.engine.download(name))
+        if not sc.sanity_ok:
+            import warnings
+
+            warnings.warn(f"Solution diverged at iteration {sc.itt} (numerics.sanity_check)")
+        setup.after_timestep(state)
+        return sc
+
+    def run(self, runlen=None):
+        vs = self.state.variables
+        runlen = float(self.state.settings.runlen) if runlen is None else runlen
+        start = int(np.asarray(vs.time))
+        while int(np.asarray(vs.time)) - start < runlen:
+            self.step()
