@@ -31,12 +31,23 @@ def lib():
 class OracleSvatEngine:
     """Same engine interface as roger_b200.engine.CudaSvatEngine, computed by the C oracle."""
 
-    def __init__(self, n_cells, settings):
+    def __init__(self, n_cells, settings, flag_reducer=None):
         from roger_b200 import abi
 
         self.abi = abi
         self.n = int(n_cells)
         self.settings = settings
+        self._reducer = None
+        if flag_reducer is not None:  # same contract as CudaSvatEngine(flag_reducer=...): one engine per process
+            fn_t = C.CFUNCTYPE(None, C.POINTER(C.c_uint32), C.c_int, C.c_void_p)
+
+            def _cb(ptr, n, _user):
+                vals = flag_reducer([int(ptr[i]) for i in range(n)])
+                for i in range(n):
+                    ptr[i] = vals[i]
+
+            self._reducer = fn_t(_cb)
+            lib().svat_oracle_set_flag_reducer(self._reducer, None)
         self.planes = np.zeros((abi.N_FIELDS, self.n), dtype=np.float64)
         self.scalars = abi.initial_scalars()
         self.forcing = None

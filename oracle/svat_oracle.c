@@ -1155,6 +1155,18 @@ typedef struct {
 
 static const double *row_of(const double *day, int64_t i, int uniform) { return uniform ? day : day + (size_t)i * NSLOT; }
 
+/* Multi-process runs (cells partitioned over ranks, roger_b200/parallel.py): the grid-wide any()/all() below must see
+ * every rank's cells.  Same contract as roger_svat_set_flag_reducer (include/roger_b200.h): the callback ORs the flag
+ * words in place across all ranks.  all(x) travels as !any(!x). */
+static roger_flag_reduce_fn g_reduce_fn = NULL;
+static void *g_reduce_user = NULL;
+void svat_oracle_set_flag_reducer(roger_flag_reduce_fn fn, void *user) { g_reduce_fn = fn; g_reduce_user = user; }
+static uint32_t reduce_or(uint32_t w)
+{
+    if (g_reduce_fn) g_reduce_fn(&w, 1, g_reduce_user);
+    return w;
+}
+
 void svat_oracle_step(int64_t C, double *planes, const double *prec_day, const double *ta_day,
                       const double *pet_day, roger_svat_scalars *sc, const roger_svat_settings *st)
 {
@@ -1188,6 +1200,15 @@ void svat_oracle_step(int64_t C, double *planes, const double *prec_day, const d
         all_swetop_le0 &= (swe_top[i] <= 0);
         any_swe |= (swe[i] > 0);
         any_swetop |= (swe_top[i] > 0);
+    }
+    {
+        uint32_t w = (uint32_t)(!all_prec_le0) | (uint32_t)(!all_ta_gt) << 1 | (uint32_t)any_snowfall << 2 | (uint32_t)(!all_dry_cold) << 3 |
+                     (uint32_t)any_hpi << 4 | (uint32_t)any_prec << 5 | (uint32_t)any_ta_gt << 6 | (uint32_t)(!all_le_hpi) << 7 |
+                     (uint32_t)(!all_swe_le0) << 8 | (uint32_t)(!all_swetop_le0) << 9 | (uint32_t)any_swe << 10 | (uint32_t)any_swetop << 11;
+        w = reduce_or(w);
+        all_prec_le0 = !(w & 1); all_ta_gt = !(w >> 1 & 1); any_snowfall = w >> 2 & 1; all_dry_cold = !(w >> 3 & 1);
+        any_hpi = w >> 4 & 1; any_prec = w >> 5 & 1; any_ta_gt = w >> 6 & 1; all_le_hpi = !(w >> 7 & 1);
+        all_swe_le0 = !(w >> 8 & 1); all_swetop_le0 = !(w >> 9 & 1); any_swe = w >> 10 & 1; any_swetop = w >> 11 & 1;
     }
     int cond0 = all_prec_le0 && all_swe_le0 && all_swetop_le0 && all_ta_gt;
     int cond00 = any_snowfall || all_dry_cold;
@@ -1225,6 +1246,13 @@ void svat_oracle_step(int64_t C, double *planes, const double *prec_day, const d
         all_snowing &= ((prec[i] > 0) && (ta[i] <= ta_fm));
         any_swe_m1 |= (swe[i] > 0);
         all_swe_le0_now &= (swe[i] <= 0);
+    }
+    {
+        uint32_t w = (uint32_t)ev1a | (uint32_t)ev1b << 1 | (uint32_t)(!all_p_le0) << 2 | (uint32_t)(!all_snowing) << 3 |
+                     (uint32_t)any_swe_m1 << 4 | (uint32_t)(!all_swe_le0_now) << 5;
+        w = reduce_or(w);
+        ev1a = w & 1; ev1b = w >> 1 & 1; all_p_le0 = !(w >> 2 & 1); all_snowing = !(w >> 3 & 1);
+        any_swe_m1 = w >> 4 & 1; all_swe_le0_now = !(w >> 5 & 1);
     }
     int cond_event1 = ev1a || ev1b;
     int cond_event2 = all_p_le0 || all_snowing || (any_swe_m1 && all_swe_le0_now);
@@ -1326,7 +1354,7 @@ void svat_oracle_step(int64_t C, double *planes, const double *prec_day, const d
     free(prec_m1);
     sc->itt += 1;
     sc->time += sc->dt_secs;
-    sc->sanity_ok = all_ok;
+    sc->sanity_ok = !reduce_or((uint32_t)!all_ok);
     sc->event_id[0] = sc->event_id[1]; /* after_timestep */
 #undef PL
 }
