@@ -210,8 +210,21 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM, device-timed ---------------------------------------------
-    for _ in range(args.warmup):
-        m.step(False)
+    def advance(n):
+        """exactly n adaptive steps (day-blocked launches where the scheduler allows); returns {dt_secs: count}"""
+        kinds, left = {}, n
+        while left > 0:
+            t_before = eng.get_scalars().time
+            done = m.run_steps(left)
+            sc = eng.get_scalars()
+            if done == 1:
+                kinds[int(sc.dt_secs)] = kinds.get(int(sc.dt_secs), 0) + 1
+            else:
+                kinds["blocked"] = kinds.get("blocked", 0) + done
+            left -= done
+        return kinds
+
+    advance(args.warmup)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -220,10 +233,7 @@ def run_cuda(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    kinds = {}
-    for _ in range(args.steps):
-        sc = m.step(False)
-        kinds[int(sc.dt_secs)] = kinds.get(int(sc.dt_secs), 0) + 1
+    kinds = advance(args.steps)
     eng.synchronize()
     ev1.record()
     torch.cuda.synchronize()
@@ -244,13 +254,15 @@ def run_cuda(args):
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
-    for _ in range(args.steps):
+    left = args.steps
+    while left > 0:
         sc0 = eng.get_scalars()
-        midnight = sc0.time % 86400 == 0
-        sc = m.step(False)
-        d2h += 4 + 88
-        if midnight:
+        if sc0.time % 86400 == 0:
             h2d += 3 * 144 * 8
+        done = m.run_steps(left)
+        left -= done
+        sc = eng.get_scalars()
+        d2h += (4 + 88) * done
         if sc.time % 86400 == 0:
             eng.download_wait()  # the previous day's slabs have left the pinned buffers (the writer thread owns copies)
             eng.download_async("theta_rz", pin[0])

@@ -113,6 +113,12 @@ int roger_svat_step(roger_svat *h, int write_fluxes);
 /* run adaptive steps until vs.time reaches the next midnight (at most 144 steps); returns the
  * number of steps taken through *n_steps. */
 int roger_svat_run_day(roger_svat *h, int write_fluxes, int *n_steps);
+/* up to max_steps adaptive steps, never past the next midnight; *n_steps = steps taken.  With spatially uniform forcing and
+ * no snow anywhere the scheduler lays out the coming steps in advance and runs them in ONE kernel launch (state re-read
+ * from L2 instead of HBM); results are identical to single steps. */
+int roger_svat_run_steps(roger_svat *h, int write_fluxes, int max_steps, int *n_steps);
+/* switch the day-blocked launch off / on (default on) and bound the steps per launch (2..144) */
+int roger_svat_set_block_stepping(roger_svat *h, int enabled, int max_block);
 int roger_svat_synchronize(roger_svat *h);
 /* CUDA-event time (ms) spent in kernels of the most recent roger_svat_step / run_day call and the
  * number of kernel launches it made (bench.py roofline / gpu_launches). */

@@ -210,6 +210,47 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
     warp_or(flags, bits);
 }
 
+// Several consecutive adaptive steps of every cell in ONE launch (uniform forcing, snow-free stretch of a day: the
+// host scheduler knows every step's dt / aggregates in advance, svat_api.cu plan_day_block).  A thread re-reads the
+// state it stored in the previous step: at 4 blocks x 128 cells x ~120 planes per SM the whole grid's resident working
+// set is ~70 MB and stays in the 126 MB L2, so HBM sees the state once per launch instead of once per step.
+template <bool LAT>
+__global__ void __launch_bounds__(ROGER_BLOCK, ROGER_MIN_BLOCKS)
+k_svat_steps(Planes pl, const StepPlan* __restrict__ plans, int n_plans, unsigned* flags) {
+    __shared__ StepPlan sp;
+    const int64_t C = pl.C;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int s = 0; s < n_plans; s++) {
+        __syncthreads();
+        {
+            const unsigned* src = reinterpret_cast<const unsigned*>(plans + s);
+            unsigned* dst = reinterpret_cast<unsigned*>(&sp);
+            for (int k = threadIdx.x; k < (int)(sizeof(StepPlan) / sizeof(unsigned)); k += blockDim.x) dst[k] = src[k];
+        }
+        __syncthreads();
+        const StepPlan& p = sp;
+        unsigned bits = 0;
+        if (i < C) {
+            Cell c;
+            const Io io{pl.ps, pl.fl, C, i};
+            c.maskCatch = io.ldp(RF_maskCatch);
+            c.m = c.maskCatch;
+            c.prec = io.lds(RF_prec); c.ta = io.lds(RF_ta); c.pet = io.lds(RF_pet);
+            c.prec_m1 = c.prec;
+            if (p.class_a) { c.prec = p.u_prec; c.ta = p.u_ta_a; }
+            if (p.class_b) { c.pet = p.u_pet; c.ta = p.u_ta_b; }
+            io.sts(RF_prec, c.prec); io.sts(RF_ta, c.ta); io.sts(RF_pet, c.pet);
+            const bool ok = (c.m == 1.0) ? cell_step<LAT, false, true>(c, p, io) : cell_step<LAT, false, false>(c, p, io);
+            bits |= (c.swe > 0) ? FLAG_SWE_GT0 : 0;
+            bits |= !(c.swe <= 0) ? FLAG_SWE_NOT_LE0 : 0;
+            bits |= (c.swe_top > 0) ? FLAG_SWETOP_GT0 : 0;
+            bits |= !(c.swe_top <= 0) ? FLAG_SWETOP_NOT_LE0 : 0;
+            bits |= ok ? 0 : FLAG_INSANE;
+        }
+        warp_or(flags + s, bits);
+    }
+}
+
 }  // namespace roger
 
 // ================================================================================================
@@ -250,6 +291,16 @@ struct roger_svat {
     bool snow_flags_valid = false;
     bool ks_ss_synced = false;
     bool have_forcing = false;
+    // uniform forcing: the (uniform) value the prec / ta planes currently hold, tracked by the scheduler
+    double u_cur_prec = 0, u_cur_ta = 0;
+    bool u_cur_valid = false;
+    // day-blocked stepping (run_block)
+    int max_block = 144;
+    bool block_stepping = true;
+    void* d_plans = nullptr;
+    void* h_plans = nullptr;
+    unsigned* d_block_flags = nullptr;
+    unsigned* h_block_flags = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // asynchronous diagnostic read-back (roger_svat_download_async)
     std::vector<double*> snap_free, snap_busy;   // device snapshot planes
@@ -325,6 +376,9 @@ void roger_svat_destroy(roger_svat* h) {
     for (auto p : h->snap_free) cudaFree(p);
     for (auto p : h->snap_busy) cudaFree(p);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+    cudaFree(h->d_plans); cudaFree(h->d_block_flags);
+    if (h->h_plans) cudaFreeHost(h->h_plans);
+    if (h->h_block_flags) cudaFreeHost(h->h_block_flags);
     cudaFree(h->d_flags);
     cudaFreeHost(h->h_flags);
     cudaEventDestroy(h->ev0);
@@ -340,6 +394,7 @@ int roger_svat_upload(roger_svat* h, int field, const double* host) {
     CU(cudaMemcpyAsync(h->planes().at(field), host, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (field == RF_swe || field == RF_swe_top) h->snow_flags_valid = false;
+    if (field == RF_prec || field == RF_ta) h->u_cur_valid = false;
     if (field == RF_ks_ss) h->ks_ss_synced = (h->sc.itt > 0) ? false : h->ks_ss_synced;
     return 0;
 }
@@ -467,91 +522,71 @@ int roger_svat_set_forcing_day_device(roger_svat* h, uint64_t prec_day, uint64_t
     return after_forcing(h);
 }
 
-// One adaptive time step.  Host side = the grid-wide part of adaptive_time_stepping_kernel
-// (adaptive_time_stepping.py:34-381) evaluated on reduction flags; device side = everything per cell.
-static int step_impl(roger_svat* h, int write_fluxes) {
-    if (!h->have_forcing) return fail(ROGER_EINVAL, "roger_svat_step: no forcing day set");
-    CU(cudaSetDevice(h->device));
-    if (write_fluxes) { int r = ensure_flux_planes(h); if (r) return r; }
-    const roger_svat_settings& st = h->st;
-    roger_svat_scalars& sc = h->sc;
-    const int threads = ROGER_BLOCK;
-    const int blocks = (int)((h->C + threads - 1) / threads);
-    int64_t launches = 0;
-    CU(cudaEventRecord(h->ev0, h->stream));
+// ---- host scheduler: the grid-wide part of adaptive_time_stepping_kernel (adaptive_time_stepping.py:34-381) evaluated on
+// reduction flags.  Split in two halves around the event conditions (:191-201), which need prec / ta [tau] of every cell.
+struct SchedA {  // what the second half needs from the first
+    bool any_swe, any_swetop, all_swe_le0;
+    int itt_day;
+};
 
-    if (!h->snow_flags_valid) {
-        CU(cudaMemsetAsync(h->d_flags, 0, sizeof(unsigned), h->stream));
-        k_snow_flags<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(h->planes(), h->d_flags);
-        CU(cudaGetLastError());
-        launches++;
-        CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        h->snow_flags = h->reduce(h->h_flags[0]);
-        h->snow_flags_valid = true;
-    }
-    const unsigned sf = h->snow_flags, df = h->day_flags;
+static int schedule_first_half(roger_svat* h, unsigned sf, roger_svat_scalars& sc, StepPlan& p, SchedA& a) {
+    const unsigned df = h->day_flags;
     const bool all_prec_le0 = !(df & DAY_NOT_PREC_LE0), all_ta_gt = !(df & DAY_NOT_TA_GT);
     const bool any_snowfall = df & DAY_SNOWFALL, all_dry_cold = !(df & DAY_NOT_DRY_COLD);
     const bool any_hpi = df & DAY_HPI, any_prec = df & DAY_PREC, any_ta_gt = df & DAY_TA_GT, all_le_hpi = !(df & DAY_NOT_LE_HPI);
-    const bool any_swe = sf & FLAG_SWE_GT0, any_swetop = sf & FLAG_SWETOP_GT0;
-    const bool all_swe_le0 = !(sf & FLAG_SWE_NOT_LE0), all_swetop_le0 = !(sf & FLAG_SWETOP_NOT_LE0);
-    const bool cond0 = all_prec_le0 && all_swe_le0 && all_swetop_le0 && all_ta_gt;
+    a.any_swe = sf & FLAG_SWE_GT0;
+    a.any_swetop = sf & FLAG_SWETOP_GT0;
+    a.all_swe_le0 = !(sf & FLAG_SWE_NOT_LE0);
+    const bool all_swetop_le0 = !(sf & FLAG_SWETOP_NOT_LE0);
+    const bool cond0 = all_prec_le0 && a.all_swe_le0 && all_swetop_le0 && all_ta_gt;
     const bool cond00 = any_snowfall || all_dry_cold;
     const bool cond1 = any_hpi && any_prec && any_ta_gt;
     const bool cond2 = all_le_hpi && any_prec && any_ta_gt;
-    const bool snow_warm = (any_swe || any_swetop) && any_ta_gt;
+    const bool snow_warm = (a.any_swe || a.any_swetop) && any_ta_gt;
     const bool cond3 = any_hpi && any_prec && snow_warm;
     const bool cond4 = all_le_hpi && any_prec && snow_warm;
     const bool cond5 = all_prec_le0 && snow_warm;
     const bool daily = cond0 || cond00;
     const bool hourly = (cond2 || cond4 || cond5) && !cond1 && !cond3;
     const bool tenmin = (cond1 || cond3) && !cond2 && !cond4 && !cond5;
-    const int itt_day = (int)sc.itt_day;
-    if (itt_day < 0 || itt_day > 143) return fail(ROGER_EINVAL, "roger_svat_step: itt_day outside the forcing day (set_forcing_day not called at midnight?)");
-
-    StepPlan p{};
+    a.itt_day = (int)sc.itt_day;
+    if (a.itt_day < 0 || a.itt_day > 143)
+        return fail(ROGER_EINVAL, "roger_svat_step: itt_day outside the forcing day (set_forcing_day not called at midnight?)");
+    p = StepPlan{};
     p.class_a = tenmin ? 3 : (hourly ? 2 : (daily ? 1 : 0));
     sc.dt_secs = (sc.time % 86400 == 0) ? 86400 : 3600;
     if (hourly) sc.dt_secs = 3600;
     if (tenmin) sc.dt_secs = 600;
+    return 0;
+}
 
+// uniform forcing: prec / ta [tau] after the first aggregation block are known on the host
+static void uniform_first_aggregates(roger_svat* h, StepPlan& p, int itt_day) {
+    const double* pr = h->h_forc[0];
+    const double* tr = h->h_forc[1];
+    double pa = h->u_cur_prec, ta_a = h->u_cur_ta;
+    if (p.class_a == 1) { pa = RowAgg::day_sum(pr); ta_a = RowAgg::day_nanmean(tr); }
+    else if (p.class_a == 2) { pa = RowAgg::win_sum(pr, itt_day); ta_a = RowAgg::win_nanmean(tr, itt_day); }
+    else if (p.class_a == 3) { pa = pr[itt_day]; ta_a = tr[itt_day]; }
+    p.u_prec = pa;
+    p.u_ta_a = ta_a;
+}
+
+static unsigned uniform_event_flags(const roger_svat_settings& st, const StepPlan& p, const SchedA& a) {
     unsigned ev = 0;
-    if (st.forcing_uniform) {
-        // event conditions need prec/ta[tau]; with class "keep" they are the stored planes' (uniform) values:
-        // the scheduler keeps the last uniform aggregates on the host.
-        static_assert(sizeof(double) == 8, "");
-        double pa, ta_a;
-        const double* pr = h->h_forc[0];
-        const double* tr = h->h_forc[1];
-        if (p.class_a == 1) { pa = RowAgg::day_sum(pr); ta_a = RowAgg::day_nanmean(tr); }
-        else if (p.class_a == 2) { pa = RowAgg::win_sum(pr, itt_day); ta_a = RowAgg::win_nanmean(tr, itt_day); }
-        else if (p.class_a == 3) { pa = pr[itt_day]; ta_a = tr[itt_day]; }
-        else {
-            // keep: read one cell's current value (uniform planes) -- rare path
-            CU(cudaMemcpyAsync(&pa, h->planes().at(RF_prec), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            CU(cudaMemcpyAsync(&ta_a, h->planes().at(RF_ta), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            CU(cudaStreamSynchronize(h->stream));
-        }
-        p.u_prec = pa;
-        p.u_ta_a = ta_a;
-        ev |= ((pa > 0) && (ta_a > st.ta_fm)) ? EV_RAIN_WARM : 0;
-        ev |= ((any_swe || any_swetop) && (ta_a > st.ta_fm)) ? EV_SNOW_WARM : 0;
-        ev |= !(pa <= 0) ? EV_NOT_PREC_LE0 : 0;
-        ev |= !((pa > 0) && (ta_a <= st.ta_fm)) ? EV_NOT_SNOWING : 0;
-    } else {
-        CU(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(unsigned), h->stream));
-        k_aggregate_a<<<blocks, threads, 0, h->stream>>>(h->planes(), h->d_prec_m1, h->forc[0], h->forc[1], p.class_a, itt_day,
-                                                          st.ta_fm, h->d_flags + 2);
-        CU(cudaGetLastError());
-        launches++;
-        CU(cudaMemcpyAsync(h->h_flags + 2, h->d_flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        ev = h->reduce(h->h_flags[2]);
-    }
+    ev |= ((p.u_prec > 0) && (p.u_ta_a > st.ta_fm)) ? EV_RAIN_WARM : 0;
+    ev |= ((a.any_swe || a.any_swetop) && (p.u_ta_a > st.ta_fm)) ? EV_SNOW_WARM : 0;
+    ev |= !(p.u_prec <= 0) ? EV_NOT_PREC_LE0 : 0;
+    ev |= !((p.u_prec > 0) && (p.u_ta_a <= st.ta_fm)) ? EV_NOT_SNOWING : 0;
+    return ev;
+}
+
+static void schedule_second_half(roger_svat* h, unsigned ev, const SchedA& a, roger_svat_scalars& sc, StepPlan& p) {
+    const roger_svat_settings& st = h->st;
+    const int itt_day = a.itt_day;
     const bool cond_event1 = (ev & EV_RAIN_WARM) || (ev & EV_SNOW_WARM);
     // swe[taum1] == swe[tau] at this point (after_timestep copied it): any(swe_m1 > 0) & all(swe <= 0)
-    const bool cond_event2 = !(ev & EV_NOT_PREC_LE0) || !(ev & EV_NOT_SNOWING) || (any_swe && all_swe_le0);
+    const bool cond_event2 = !(ev & EV_NOT_PREC_LE0) || !(ev & EV_NOT_SNOWING) || (a.any_swe && a.all_swe_le0);
     if (cond_event1) sc.time_event0 = 0;
     if (cond_event2) sc.time_event0 = sc.time_event0 + sc.dt_secs;
 
@@ -594,6 +629,73 @@ static int step_impl(roger_svat* h, int write_fluxes) {
     p.uniform = st.forcing_uniform;
     p.lbc = st.enable_macropore_lower_boundary_condition;
     p.clamp = st.clamp_small_negative_storage;
+}
+
+// bookkeeping at the end of a step (roger.py:447-448 and the after_timestep roll)
+static void finish_step_scalars(roger_svat* h, const StepPlan& p, roger_svat_scalars& sc) {
+    sc.itt += 1;
+    sc.time += sc.dt_secs;
+    sc.event_id[0] = sc.event_id[1];
+    if (h->st.forcing_uniform) {  // the (uniform) values the prec / ta planes hold now
+        if (p.class_a) { h->u_cur_prec = p.u_prec; h->u_cur_ta = p.u_ta_a; }
+        if (p.class_b) h->u_cur_ta = p.u_ta_b;
+    }
+}
+
+static int ensure_snow_flags(roger_svat* h, int64_t* launches) {
+    if (h->snow_flags_valid) return 0;
+    CU(cudaMemsetAsync(h->d_flags, 0, sizeof(unsigned), h->stream));
+    k_snow_flags<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(h->planes(), h->d_flags);
+    CU(cudaGetLastError());
+    (*launches)++;
+    CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->snow_flags = h->reduce(h->h_flags[0]);
+    h->snow_flags_valid = true;
+    return 0;
+}
+
+static int ensure_uniform_current(roger_svat* h) {  // the "keep" class reads prec / ta [tau] as they are
+    if (!h->st.forcing_uniform || h->u_cur_valid) return 0;
+    CU(cudaMemcpyAsync(&h->u_cur_prec, h->planes().at(RF_prec), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&h->u_cur_ta, h->planes().at(RF_ta), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->u_cur_valid = true;
+    return 0;
+}
+
+// One adaptive time step: host scheduler + one launch of the fused per-cell kernel.
+static int step_impl(roger_svat* h, int write_fluxes) {
+    if (!h->have_forcing) return fail(ROGER_EINVAL, "roger_svat_step: no forcing day set");
+    CU(cudaSetDevice(h->device));
+    if (write_fluxes) { int r = ensure_flux_planes(h); if (r) return r; }
+    const roger_svat_settings& st = h->st;
+    roger_svat_scalars& sc = h->sc;
+    const int threads = ROGER_BLOCK;
+    const int blocks = (int)((h->C + threads - 1) / threads);
+    int64_t launches = 0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    { int r = ensure_snow_flags(h, &launches); if (r) return r; }
+    { int r = ensure_uniform_current(h); if (r) return r; }
+
+    StepPlan p;
+    SchedA a;
+    { int r = schedule_first_half(h, h->snow_flags, sc, p, a); if (r) return r; }
+    unsigned ev = 0;
+    if (st.forcing_uniform) {
+        uniform_first_aggregates(h, p, a.itt_day);
+        ev = uniform_event_flags(st, p, a);
+    } else {
+        CU(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(unsigned), h->stream));
+        k_aggregate_a<<<blocks, threads, 0, h->stream>>>(h->planes(), h->d_prec_m1, h->forc[0], h->forc[1], p.class_a, a.itt_day,
+                                                          st.ta_fm, h->d_flags + 2);
+        CU(cudaGetLastError());
+        launches++;
+        CU(cudaMemcpyAsync(h->h_flags + 2, h->d_flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        ev = h->reduce(h->h_flags[2]);
+    }
+    schedule_second_half(h, ev, a, sc, p);
 
     CU(cudaMemsetAsync(h->d_flags, 0, sizeof(unsigned), h->stream));
     const Planes pl = h->planes();
@@ -617,10 +719,84 @@ static int step_impl(roger_svat* h, int write_fluxes) {
     h->last_kernel_ms += ms;
     h->last_launches += launches;
 
-    sc.itt += 1;
-    sc.time += sc.dt_secs;
+    finish_step_scalars(h, p, sc);
     sc.sanity_ok = (h->snow_flags & FLAG_INSANE) ? 0 : 1;
-    sc.event_id[0] = sc.event_id[1];  // after_timestep
+    return 0;
+}
+
+// Day-blocked stepping.  With spatially uniform forcing every input of the scheduler except the four snow flags is known
+// on the host.  While no cell holds snow and every step's air temperature is above the freeze / melt threshold, no snow
+// can accrue (interception.py:163, snow.py:14), the flags stay clear, and the schedule of the coming steps -- dt,
+// aggregates, event bookkeeping -- can be laid out in advance and executed by ONE launch (k_svat_steps).  Returns the
+// number of steps executed through *n_done (0: the stretch does not qualify, the caller steps one at a time).
+static int run_block(roger_svat* h, int max_steps, int* n_done) {
+    *n_done = 0;
+    const roger_svat_settings& st = h->st;
+    if (!st.forcing_uniform || !h->ks_ss_synced || !h->have_forcing || max_steps < 2) return 0;
+    CU(cudaSetDevice(h->device));
+    int64_t launches = 0;
+    { int r = ensure_snow_flags(h, &launches); if (r) return r; }
+    { int r = ensure_uniform_current(h); if (r) return r; }
+    const unsigned snow_bits = FLAG_SWE_GT0 | FLAG_SWE_NOT_LE0 | FLAG_SWETOP_GT0 | FLAG_SWETOP_NOT_LE0;
+    if (h->snow_flags & snow_bits) return 0;
+    const unsigned sf = 0;  // no snow anywhere, and it stays that way while every step is warm
+
+    std::vector<StepPlan> plans;
+    roger_svat_scalars sc = h->sc;  // tentative: committed once the block has run
+    const double save_prec = h->u_cur_prec, save_ta = h->u_cur_ta;
+    while ((int)plans.size() < max_steps && (int)plans.size() < (int)h->max_block) {
+        roger_svat_scalars sc_try = sc;
+        StepPlan p;
+        SchedA a;
+        { int r = schedule_first_half(h, sf, sc_try, p, a); if (r) return r; }
+        uniform_first_aggregates(h, p, a.itt_day);
+        schedule_second_half(h, uniform_event_flags(st, p, a), a, sc_try, p);
+        const double ta_seen_a = p.u_ta_a;                                  // ta [tau] during interception .. (class a / kept)
+        const double ta_final = p.class_b ? p.u_ta_b : ta_seen_a;          // ta [tau] the processes see
+        if (!(ta_seen_a > st.ta_fm) || !(ta_final > st.ta_fm)) break;       // a cold step: snow may accrue, stop before it
+        finish_step_scalars(h, p, sc_try);
+        sc = sc_try;
+        plans.push_back(p);
+        if (sc.time % 86400 == 0) break;  // the next day needs a new forcing block
+    }
+    if (plans.size() < 2) {  // not worth a block; undo the tentative bookkeeping
+        h->u_cur_prec = save_prec; h->u_cur_ta = save_ta;
+        return 0;
+    }
+    const int n = (int)plans.size();
+    if (!h->d_plans) {
+        CU(cudaMalloc(&h->d_plans, sizeof(StepPlan) * h->max_block));
+        CU(cudaMalloc(&h->d_block_flags, sizeof(unsigned) * h->max_block));
+        CU(cudaHostAlloc(&h->h_plans, sizeof(StepPlan) * h->max_block, cudaHostAllocDefault));
+        CU(cudaHostAlloc(&h->h_block_flags, sizeof(unsigned) * h->max_block, cudaHostAllocDefault));
+    }
+    memcpy(h->h_plans, plans.data(), sizeof(StepPlan) * n);
+    const int threads = ROGER_BLOCK;
+    const int blocks = (int)((h->C + threads - 1) / threads);
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(cudaMemcpyAsync(h->d_plans, h->h_plans, sizeof(StepPlan) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->d_block_flags, 0, sizeof(unsigned) * n, h->stream));
+    const Planes pl = h->planes();
+    if (st.enable_lateral_flow) k_svat_steps<true><<<blocks, threads, 0, h->stream>>>(pl, (const StepPlan*)h->d_plans, n, h->d_block_flags);
+    else k_svat_steps<false><<<blocks, threads, 0, h->stream>>>(pl, (const StepPlan*)h->d_plans, n, h->d_block_flags);
+    CU(cudaGetLastError());
+    launches++;
+    CU(cudaMemcpyAsync(h->h_block_flags, h->d_block_flags, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    unsigned all = 0;
+    std::vector<uint32_t> words(h->h_block_flags, h->h_block_flags + n);
+    if (h->reduce_fn) h->reduce_fn(words.data(), n, h->reduce_user);
+    for (int k = 0; k < n; k++) all |= words[k];
+    if (all & snow_bits) return fail(ROGER_EINVAL, "internal error: snow appeared inside a block scheduled as snow-free");
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_kernel_ms += ms;
+    h->last_launches += launches;
+    h->snow_flags = words[n - 1] & ~FLAG_INSANE;
+    h->sc = sc;
+    h->sc.sanity_ok = (all & FLAG_INSANE) ? 0 : 1;
+    *n_done = n;
     return 0;
 }
 
@@ -631,17 +807,38 @@ int roger_svat_step(roger_svat* h, int write_fluxes) {
     return step_impl(h, write_fluxes);
 }
 
-int roger_svat_run_day(roger_svat* h, int write_fluxes, int* n_steps) {
-    if (!h) return fail(ROGER_EINVAL, "roger_svat_run_day: null handle");
+// Up to max_steps adaptive steps, never past the next midnight (a new forcing block is due there).  Uses the day-blocked
+// launch where the stretch qualifies (run_block) and single steps otherwise; the results are identical either way.
+int roger_svat_run_steps(roger_svat* h, int write_fluxes, int max_steps, int* n_steps) {
+    if (!h || max_steps < 1) return fail(ROGER_EINVAL, "roger_svat_run_steps: bad argument");
     h->last_kernel_ms = 0;
     h->last_launches = 0;
     int n = 0;
     do {
-        int r = step_impl(h, write_fluxes);
-        if (r) return r;
-        n++;
-    } while (h->sc.time % 86400 != 0 && n < 144);
+        int nb = 0;
+        if (!write_fluxes && h->block_stepping) {
+            int r = run_block(h, max_steps - n, &nb);
+            if (r) return r;
+        }
+        if (nb == 0) {
+            int r = step_impl(h, write_fluxes);
+            if (r) return r;
+            nb = 1;
+        }
+        n += nb;
+    } while (h->sc.time % 86400 != 0 && n < max_steps);
     if (n_steps) *n_steps = n;
+    return 0;
+}
+
+int roger_svat_run_day(roger_svat* h, int write_fluxes, int* n_steps) {
+    return roger_svat_run_steps(h, write_fluxes, 144, n_steps);
+}
+
+int roger_svat_set_block_stepping(roger_svat* h, int enabled, int max_block) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_set_block_stepping: null handle");
+    h->block_stepping = enabled != 0;
+    if (max_block >= 2 && max_block <= 144 && !h->d_plans) h->max_block = max_block;
     return 0;
 }
 

@@ -52,6 +52,8 @@ def load_library():
     lib.roger_svat_set_forcing_day_device.argtypes = [hp, C.c_uint64, C.c_uint64, C.c_uint64]
     lib.roger_svat_step.argtypes = [hp, C.c_int]
     lib.roger_svat_run_day.argtypes = [hp, C.c_int, C.POINTER(C.c_int)]
+    lib.roger_svat_run_steps.argtypes = [hp, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.roger_svat_set_block_stepping.argtypes = [hp, C.c_int, C.c_int]
     lib.roger_svat_synchronize.argtypes = [hp]
     lib.roger_svat_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
     lib.roger_svat_set_flag_reducer.argtypes = [hp, FLAG_REDUCE_FN, C.c_void_p]
@@ -165,6 +167,16 @@ class CudaSvatEngine:
         _check(self.lib, self.lib.roger_svat_run_day(self.h, int(bool(write_fluxes)), C.byref(n)))
         self._timing()
         return n.value
+
+    def run_steps(self, max_steps, write_fluxes=False):
+        """Up to max_steps adaptive steps, never past the next midnight; returns the number taken."""
+        n = C.c_int()
+        _check(self.lib, self.lib.roger_svat_run_steps(self.h, int(bool(write_fluxes)), int(max_steps), C.byref(n)))
+        self._timing()
+        return n.value
+
+    def set_block_stepping(self, enabled, max_block=0):
+        _check(self.lib, self.lib.roger_svat_set_block_stepping(self.h, int(bool(enabled)), int(max_block)))
 
     def synchronize(self):
         _check(self.lib, self.lib.roger_svat_synchronize(self.h))

@@ -100,6 +100,27 @@ class SvatModel:
         self.n_steps += 1
         return self.engine.get_scalars()
 
+    def run_steps(self, max_steps, write_fluxes=False):
+        """Up to max_steps adaptive steps but never past the next midnight (where the hooks have to run again).
+        Returns the number of steps taken.  Engines with `run_steps` may execute them in one launch."""
+        assert self._setup_done
+        sc = self.engine.get_scalars()
+        self._set_forcing(sc)
+        self.engine.set_scalars(sc)
+        self._set_parameters(sc)
+        if hasattr(self.engine, "run_steps"):
+            n = self.engine.run_steps(max_steps, write_fluxes)
+        else:
+            n = 0
+            while True:
+                self.engine.step(write_fluxes)
+                n += 1
+                if n >= max_steps or self.engine.get_scalars().time % DAY == 0:
+                    break
+        self.month[0] = self.month[1]
+        self.n_steps += n
+        return n
+
     def run(self, runlen_seconds, write_fluxes=False, callback=None):
         sc = self.engine.get_scalars()
         start = sc.time

@@ -53,3 +53,39 @@ def test_async_download_is_a_snapshot():
         assert np.array_equal(pins[n], want[n])
     # the state has moved on in the meantime
     assert any(not np.array_equal(eng.download(n), want[n]) for n in want)
+
+
+@pytest.mark.parametrize("lateral,doy,ndays", [(True, 121, 25), (False, 121, 25), (False, 40, 30), (True, 330, 20)])
+def test_day_blocked_stepping_equals_single_steps(lateral, doy, ndays):
+    """roger_svat_run_steps lays out snow-free stretches in advance and runs them in one launch; every plane and every
+    scalar must be bit-identical to stepping one launch at a time (doy 40 / 330: snow periods, mixed paths)."""
+    from roger_b200 import abi, synth
+    from roger_b200.svat import SvatModel
+
+    shape = (24, 16)
+    forcing = synth.mixed_forcing(ndays + 1, seed=42, start_doy=doy)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, lateral=lateral, lu_choices=(10, 11, 12, 8, 5, 9))
+    models = [SvatModel(_engine(), shape, forcing, prim, th_rz, th_ss, lateral=lateral) for _ in range(2)]
+    for m in models:
+        m.setup()
+    models[1].engine.set_block_stepping(False)
+    launches = [0, 0]
+    kinds = {n: k for n, k in zip(abi.FIELD_NAMES, abi.FIELD_KINDS)}
+    total = 0
+    for day in range(ndays):
+        n0 = models[0].run_steps(144)
+        n1 = models[1].run_steps(144)
+        assert n0 == n1
+        total += n0
+        a, b = models[0].engine.get_scalars(), models[1].engine.get_scalars()
+        for k in ("time", "itt", "dt_secs", "itt_day", "event_id_counter", "time_event0", "dt", "sanity_ok"):
+            assert getattr(a, k) == getattr(b, k), (day, k)
+        assert list(a.event_id) == list(b.event_id)
+        for n in abi.FIELD_NAMES:
+            if kinds[n] == "S" or n == "ks_ss":
+                x, y = models[0].get(n), models[1].get(n)
+                assert np.array_equal(x, y, equal_nan=True), (day, n)
+    launches = [m.engine.launches for m in models]
+    assert launches[1] >= total
+    if doy == 121:
+        assert launches[0] < launches[1] / 3  # the blocked path really ran
