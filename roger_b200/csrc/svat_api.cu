@@ -214,8 +214,14 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
 // host scheduler knows every step's dt / aggregates in advance, svat_api.cu plan_day_block).  A thread re-reads the
 // state it stored in the previous step: at 4 blocks x 128 cells x ~120 planes per SM the whole grid's resident working
 // set is ~70 MB and stays in the 126 MB L2, so HBM sees the state once per launch instead of once per step.
+#ifndef ROGER_STEPS_MIN_BLOCKS
+#define ROGER_STEPS_MIN_BLOCKS 2
+#endif
+#ifndef ROGER_STEPS_BLOCK
+#define ROGER_STEPS_BLOCK 128
+#endif
 template <bool LAT>
-__global__ void __launch_bounds__(ROGER_BLOCK, ROGER_MIN_BLOCKS)
+__global__ void __launch_bounds__(ROGER_STEPS_BLOCK, ROGER_STEPS_MIN_BLOCKS)
 k_svat_steps(Planes pl, const StepPlan* __restrict__ plans, int n_plans, unsigned* flags) {
     __shared__ StepPlan sp;
     const int64_t C = pl.C;
@@ -350,6 +356,10 @@ int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settin
     h->sc.event_id_counter = 1;
     h->sc.sanity_ok = 1;
     h->sc.month = 1;
+    // Day-blocked launches pay off where the per-step launch + flag read-back latency (~35 us) is comparable to the kernel
+    // time; on large grids the per-step kernel (4 blocks / SM) is faster per step than the blocked one (measured on B200:
+    // 5.8 vs 6.9 ms per step at 4096^2 cells -- the step is bound by dependent-instruction latency, not by HBM).
+    h->block_stepping = n_cells <= 262144;
     const size_t plane = sizeof(double) * (size_t)n_cells;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&h->d_ps, plane * kNumPS));
@@ -771,7 +781,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done) {
         CU(cudaHostAlloc(&h->h_block_flags, sizeof(unsigned) * h->max_block, cudaHostAllocDefault));
     }
     memcpy(h->h_plans, plans.data(), sizeof(StepPlan) * n);
-    const int threads = ROGER_BLOCK;
+    const int threads = ROGER_STEPS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(cudaMemcpyAsync(h->d_plans, h->h_plans, sizeof(StepPlan) * n, cudaMemcpyHostToDevice, h->stream));
