@@ -31,6 +31,15 @@ from roger_b200.svat import SvatModel  # noqa: E402
 ALGO_BYTES = {"svat": 984.0, "oned": 1200.0}
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs time the oracle on every host core and say how many"""
+    from oracle import engine
+
+    n = os.cpu_count() or 1
+    engine.lib().roger_oracle_set_threads(n)
+    return n
+
+
 def sas_algo_bytes(ages):
     """each of sa_rz, sa_ss, msa_rz, msa_ss read and written once per day + forcing + scalar outputs"""
     return 64.0 * ages + 344.0
@@ -113,7 +122,7 @@ def run_reference(args):
         return
     from oracle.engine import OracleSvatEngine
 
-    cores = os.cpu_count() or 1
+    cores = use_all_host_cores()
     if args.workload == "sas":
         from oracle.engine import OracleSasEngine
         from roger_b200 import sas
@@ -214,13 +223,13 @@ def run_cuda(args):
         """exactly n adaptive steps (day-blocked launches where the scheduler allows); returns {dt_secs: count}"""
         kinds, left = {}, n
         while left > 0:
-            t_before = eng.get_scalars().time
-            done = m.run_steps(left)
+            # large grids step one launch at a time (the engine's default there), which also records the dt of each step
+            done = m.run_steps(1 if C > 262144 else left)
             sc = eng.get_scalars()
             if done == 1:
                 kinds[int(sc.dt_secs)] = kinds.get(int(sc.dt_secs), 0) + 1
             else:
-                kinds["blocked"] = kinds.get("blocked", 0) + done
+                kinds["day-blocked"] = kinds.get("day-blocked", 0) + done
             left -= done
         return kinds
 
@@ -451,6 +460,7 @@ def sas_cpu_baseline(ages, cells=192, days=2):
     from oracle.engine import OracleSasEngine, OracleSvatEngine
     from roger_b200 import sas
 
+    use_all_host_cores()
     daily = sas_daily_tile(OracleSvatEngine, days + 2)
     eng = OracleSasEngine(cells, sas.default_settings(ages))
     model = SasBenchModel(eng, cells, ages, daily)
@@ -466,6 +476,7 @@ def sas_cpu_baseline(ages, cells=192, days=2):
 def cpu_baseline(args):
     from oracle.engine import OracleSvatEngine
 
+    use_all_host_cores()
     side = args.ref_side
     m = build_model(OracleSvatEngine, (side, side), args.workload, seed=43)
     for _ in range(2):

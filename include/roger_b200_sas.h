@@ -37,6 +37,19 @@ enum roger_sas_output {
     RSO_COUNT
 };
 
+/* per-cell age statistics and balance errors of a step (settings.age_statistics != 0):
+ * transport.calculate_age_statistics_* (roger/core/transport.py:59-312) and numerics.calc_dS_num_error / calc_dC_num_error
+ * (roger/core/numerics.py:424-445, :476-516).  Percentile ages follow numpy.interp(p, CDF[1:], 1..ages). */
+enum roger_sas_statistic {
+    RSS_tt10_transp = 0, RSS_tt25_transp, RSS_tt50_transp, RSS_tt75_transp, RSS_tt90_transp, RSS_ttavg_transp,
+    RSS_tt10_q_ss, RSS_tt25_q_ss, RSS_tt50_q_ss, RSS_tt75_q_ss, RSS_tt90_q_ss, RSS_ttavg_q_ss,
+    RSS_rt25_rz, RSS_rt50_rz, RSS_rt75_rz, RSS_rtavg_rz,
+    RSS_rt25_ss, RSS_rt50_ss, RSS_rt75_ss, RSS_rtavg_ss,
+    RSS_rt10_s, RSS_rt25_s, RSS_rt50_s, RSS_rt75_s, RSS_rt90_s, RSS_rtavg_s,
+    RSS_dS_num_error, RSS_dC_num_error,
+    RSS_COUNT
+};
+
 typedef struct roger_sas_settings {
     int32_t ages;          /* settings.ages (number of age bins)                       */
     int32_t substeps;      /* settings.sas_solver_substeps                              */
@@ -44,7 +57,7 @@ typedef struct roger_sas_settings {
     double d18O_min;       /* settings.d18O_min                                         */
     double d18O_max;       /* settings.d18O_max                                         */
     int32_t store_tt;      /* keep the five travel-time distributions tt_* (diagnostics) */
-    int32_t reserved;
+    int32_t age_statistics; /* compute the RSS_* planes every step (settings.enable_age_statistics + numerical errors) */
 } roger_sas_settings;
 
 typedef struct roger_sas roger_sas; /* opaque handle */
@@ -72,6 +85,11 @@ int roger_sas_step(roger_sas *h, const double *forcing);
 int roger_sas_step_device(roger_sas *h, uint64_t forcing);
 /* per-cell scalar results of the last step: RSO_COUNT planes of n_cells doubles */
 int roger_sas_download_outputs(roger_sas *h, double *host);
+/* RSS_COUNT planes of n_cells doubles from the last step (needs settings.age_statistics) */
+int roger_sas_download_statistics(roger_sas *h, double *host);
+/* the previous step's storage concentration C_s per cell, which the solute balance error differences against
+ * (vs.C_s[taum1]); set once after the initial state, then maintained by the steps.  n_cells doubles. */
+int roger_sas_set_balance_reference(roger_sas *h, const double *C_s_prev);
 /* travel-time distribution of process p from the last step (needs settings.store_tt): n_cells*ages doubles */
 int roger_sas_download_tt(roger_sas *h, int process, double *host);
 /* out[i] = roger_pow(x[i], y[i]) -- or roger_exp(x[i]) when y is NULL -- evaluated by the device build of

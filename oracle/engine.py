@@ -91,7 +91,9 @@ class OracleSasEngine:
         self.state = {k: np.zeros((self.n, self.A)) for k in sas.STATE}
         self.out = np.zeros((len(sas.OUTPUTS), self.n))
         self.ttbuf = np.zeros((len(sas.PROCESSES), self.n, self.A)) if settings.store_tt else None
-        self._fn = lib().sas_oracle_day
+        self.stats = np.zeros((len(sas.STATISTICS), self.n)) if settings.age_statistics else None
+        self.balance_prev = np.zeros(self.n)
+        self._fn = lib().sas_oracle_day_stats
         self._fn.restype = None
 
     def set_parameters(self, mask, sas_params):
@@ -109,7 +111,14 @@ class OracleSasEngine:
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         s = self.state
         self._fn(C.c_int64(self.n), C.byref(self.settings), dp(s["sa_rz"]), dp(s["sa_ss"]), dp(s["msa_rz"]), dp(s["msa_ss"]),
-                 dp(f), dp(self.mask), dp(self.params), dp(self.out), dp(self.ttbuf) if self.ttbuf is not None else None)
+                 dp(f), dp(self.mask), dp(self.params), dp(self.out), dp(self.ttbuf) if self.ttbuf is not None else None,
+                 dp(self.stats) if self.stats is not None else None, dp(self.balance_prev))
+
+    def set_balance_reference(self, C_s_prev):
+        self.balance_prev[:] = np.asarray(C_s_prev, dtype=np.float64).reshape(-1)
+
+    def download_statistics(self):
+        return self.stats.copy()
 
     def download_outputs(self):
         return self.out.copy()

@@ -321,8 +321,103 @@ static void ageing(int A, double *sa, double *msa)
     msa[A - 1] = (sa[A - 1] <= 0) ? NAN : msa[A - 1];
 }
 
+/* numpy.interp for one scalar x (numpy/_core/src/multiarray/compiled_base.c: arr_interp + binary_search_with_guess,
+ * initial guess 0), as called by calc_age_percentile (transport.py:9-56) */
+static long np_binary_search_with_guess(double key, const double *arr, long len, long guess)
+{
+    long imin = 0, imax = len;
+    if (key > arr[len - 1]) return len;
+    else if (key < arr[0]) return -1;
+    if (len <= 4) {
+        long i;
+        for (i = 1; i < len && key >= arr[i]; ++i);
+        return i - 1;
+    }
+    if (guess > len - 3) guess = len - 3;
+    if (guess < 1) guess = 1;
+    if (key < arr[guess]) {
+        if (key < arr[guess - 1]) {
+            imax = guess - 1;
+            if (guess > 8 && key >= arr[guess - 8]) imin = guess - 8;
+        } else return guess - 1;
+    } else {
+        if (key < arr[guess + 1]) return guess;
+        else if (key < arr[guess + 2]) return guess + 1;
+        else {
+            imin = guess + 2;
+            if (guess < len - 8 - 1 && key < arr[guess + 8]) imax = guess + 8;
+        }
+    }
+    while (imin < imax) {
+        const long imid = imin + ((imax - imin) >> 1);
+        if (key >= arr[imid]) imin = imid + 1;
+        else imax = imid;
+    }
+    return imin - 1;
+}
+static double np_interp1(double x, const double *xp, const double *fp, long n)
+{
+    if (isnan(x)) return x;
+    const long j = np_binary_search_with_guess(x, xp, n, 0);
+    if (j == -1) return fp[0];
+    if (j == n) return fp[n - 1];
+    if (j == n - 1) return fp[j];
+    if (xp[j] == x) return fp[j];
+    const double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+    double res = slope * (x - xp[j]) + fp[j];
+    if (isnan(res)) {
+        res = slope * (x - xp[j + 1]) + fp[j + 1];
+        if (isnan(res) && fp[j] == fp[j + 1]) res = fp[j];
+    }
+    return res;
+}
+/* calc_age_percentile, transport.py:9-56: cdf = cumulative distribution at ages 1..A */
+static double age_percentile(int A, const double *cdf, const double *ages, double p)
+{
+    double v = np_interp1(p, cdf, ages, A);
+    return (np_max(cdf, A) <= 0) ? NAN : v;
+}
+/* transport.py:59-107 (transpiration), :110-158 (subsoil percolation) */
+static void flux_age_statistics(int A, const double *tt, const double *ages, double *work, double *st5, double *avg)
+{
+    double *TT = work, *tmp = work + A;
+    double acc = 0;
+    for (int j = 0; j < A; j++) { acc += tt[j]; TT[j] = acc; } /* TT[1:] = cumsum(tt) */
+    const double pcts[5] = {0.1, 0.25, 0.5, 0.75, 0.9};
+    for (int k = 0; k < 5; k++) st5[k] = age_percentile(A, TT, ages, pcts[k]);
+    for (int j = 0; j < A; j++) tmp[j] = ages[j] * tt[j];
+    *avg = (np_sum(tt, A) > 0) ? np_sum(tmp, A) : NAN;
+}
+/* transport.py:161-312: residence-time statistics of a storage with StorAge sa (SA = cumsum(sa) * m) */
+static void storage_age_statistics(int A, const double *sa, double m, const double *ages, double *work, const double *pcts, int np_, double *stp,
+                                   double *avg)
+{
+    double *SA = work, *RT = SA + (A + 1), *rt = RT + (A + 1), *tmp = rt + A;
+    calc_SA(A, sa, SA);
+    for (int j = 0; j <= A; j++) SA[j] = SA[j] * m;
+    const double mx = np_max(SA, A + 1);
+    for (int j = 0; j <= A; j++) RT[j] = (mx > 0) ? SA[j] / mx : 0;
+    for (int j = 0; j < A; j++) rt[j] = RT[j + 1] - RT[j];
+    for (int k = 0; k < np_; k++) stp[k] = age_percentile(A, RT + 1, ages, pcts[k]);
+    for (int j = 0; j < A; j++) tmp[j] = ages[j] * rt[j];
+    *avg = (np_sum(rt, A) > 0) ? np_sum(tmp, A) : NAN;
+}
+static double nan0(double x) { return isnan(x) ? 0 : x; }
+
+void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
+                          const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
+                          double *stats, double *balance_prev);
+
 void sas_oracle_day(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
                     const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out)
+{
+    sas_oracle_day_stats(C, st, sa_rz, sa_ss, msa_rz, msa_ss, forcing, mask, sas_params, out, tt_out, NULL, NULL);
+}
+
+/* stats: RSS_COUNT planes (or NULL); balance_prev: C_s of the previous step per cell (in / out) */
+void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
+                          const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
+                          double *stats, double *balance_prev)
 {
     sas_ctx ctx = {st->ages, st->substeps, st->VSMOW_conc18O, st->d18O_min, st->d18O_max};
     const int A = ctx.A;
@@ -330,6 +425,9 @@ void sas_oracle_day(int64_t C, const roger_sas_settings *st, double *sa_rz, doub
     {
         double *work = (double *)malloc(sizeof(double) * (size_t)(16 * (A + 2)));
         double *tmp = (double *)malloc(sizeof(double) * (size_t)(4 * (A + 2)));
+        double *ttk = (double *)malloc(sizeof(double) * (size_t)(3 * (A + 2))); /* tt of evap, transp, q_ss (statistics) */
+        double *ages = (double *)malloc(sizeof(double) * (size_t)A);
+        for (int j = 0; j < A; j++) ages[j] = (double)(j + 1);
 #pragma omp for schedule(static)
         for (int64_t i = 0; i < C; i++) {
             const double m = mask[i];
@@ -338,8 +436,17 @@ void sas_oracle_day(int64_t C, const roger_sas_settings *st, double *sa_rz, doub
 #define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
 #define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
 #define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)
-#define TT(p) (tt_out ? tt_out + ((size_t)(p) * (size_t)C + (size_t)i) * A : NULL)
+#define TT(p) (tt_out ? tt_out + ((size_t)(p) * (size_t)C + (size_t)i) * A : \
+               (stats ? ((p) == RSP_evap_soil ? ttk : (p) == RSP_transp ? ttk + (A + 2) : (p) == RSP_q_ss ? ttk + 2 * (A + 2) : NULL) : NULL))
+#define ST(k) stats[(size_t)(k) * (size_t)C + (size_t)i]
             const double C_in = F(RSF_C_in);
+            /* vs.sa_s[taum1] as the soil kernel of THIS step recomputes it (soil.py:1044-1048 writes both time levels):
+             * the aged StorAge of both layers as the step finds them */
+            double sum_sa_s_m1 = 0;
+            if (stats) {
+                for (int j = 0; j < A; j++) tmp[j] = s_rz[j] + s_ss[j] * m;
+                sum_sa_s_m1 = np_sum(tmp, A);
+            }
             /* infiltration into the root zone: matrix, then preferential flow */
             inflow(&ctx, s_rz, ms_rz, F(RSF_inf_mat_rz), C_in, m, &O(RSO_C_inf_mat_rz), &O(RSO_C_iso_inf_mat_rz));
             inflow(&ctx, s_rz, ms_rz, F(RSF_inf_pf_rz), C_in, m, &O(RSO_C_inf_pf_rz), &O(RSO_C_iso_inf_pf_rz));
@@ -366,6 +473,43 @@ void sas_oracle_day(int64_t C, const roger_sas_settings *st, double *sa_rz, doub
                 }
                 O(RSO_C_s) = storage_conc(&ctx, sa_s, msa_s, tmp) * m;
                 O(RSO_C_iso_s) = conc_to_delta(&ctx, O(RSO_C_s)) * m;
+                if (stats) {
+                    const double p5[5] = {0.1, 0.25, 0.5, 0.75, 0.9}, p3[3] = {0.25, 0.5, 0.75};
+                    /* the five percentiles of a group are RSS-consecutive but plane-strided: write them one by one */
+                    double s5[5], s3[3], avg;
+                    flux_age_statistics(A, TT(RSP_transp), ages, work, s5, &avg);
+                    for (int k = 0; k < 5; k++) ST(RSS_tt10_transp + k) = s5[k];
+                    ST(RSS_ttavg_transp) = avg;
+                    flux_age_statistics(A, TT(RSP_q_ss), ages, work, s5, &avg);
+                    for (int k = 0; k < 5; k++) ST(RSS_tt10_q_ss + k) = s5[k];
+                    ST(RSS_ttavg_q_ss) = avg;
+                    storage_age_statistics(A, s_rz, m, ages, work, p3, 3, s3, &avg);
+                    for (int k = 0; k < 3; k++) ST(RSS_rt25_rz + k) = s3[k];
+                    ST(RSS_rtavg_rz) = avg;
+                    storage_age_statistics(A, s_ss, m, ages, work, p3, 3, s3, &avg);
+                    for (int k = 0; k < 3; k++) ST(RSS_rt25_ss + k) = s3[k];
+                    ST(RSS_rtavg_ss) = avg;
+                    storage_age_statistics(A, sa_s, m, ages, work, p5, 5, s5, &avg);
+                    for (int k = 0; k < 5; k++) ST(RSS_rt10_s + k) = s5[k];
+                    ST(RSS_rtavg_s) = avg;
+                    /* numerics.py:424-445 and :476-516 (settings.h = 1) */
+                    double *bp_C = balance_prev + i; /* vs.C_s[taum1] */
+                    const double sum_s = np_sum(sa_s, A);
+                    double w[3];
+                    const int procs[3] = {RSP_evap_soil, RSP_transp, RSP_q_ss};
+                    const double flx[3] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_ss)};
+                    for (int k = 0; k < 3; k++) {
+                        const double *t = TT(procs[k]);
+                        for (int j = 0; j < A; j++) tmp[j] = flx[k] * t[j];
+                        w[k] = np_sum(tmp, A);
+                    }
+                    ST(RSS_dS_num_error) = fabs((sum_s - sum_sa_s_m1) - (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - w[0] - w[1] - w[2]) * 1.0);
+                    ST(RSS_dC_num_error) = fabs((sum_s * O(RSO_C_s) - sum_sa_s_m1 * *bp_C) -
+                                                (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                                                 F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[0] * nan0(O(RSO_C_evap_soil)) -
+                                                 w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss))) * 1.0);
+                    *bp_C = O(RSO_C_s);
+                }
             }
             ageing(A, s_rz, ms_rz);
             ageing(A, s_ss, ms_ss);
@@ -373,8 +517,11 @@ void sas_oracle_day(int64_t C, const roger_sas_settings *st, double *sa_rz, doub
 #undef O
 #undef SP
 #undef TT
+#undef ST
         }
         free(work);
         free(tmp);
+        free(ttk);
+        free(ages);
     }
 }

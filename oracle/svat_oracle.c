@@ -23,6 +23,19 @@
 #include <string.h>
 #include "../include/roger_b200.h"
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline legs of bench.py ask for all host cores */
+void roger_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 #define NSLOT ROGER_SLOTS_PER_DAY
 #define V(name) f[RF_##name]
 

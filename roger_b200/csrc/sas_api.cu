@@ -40,10 +40,13 @@ __device__ const roger_pow_exp_entry d_pow_exp_tab[ROGER_POW_N] = {ROGER_POW_EXP
 #define ROGER_SAS_MIN_BLOCKS 4
 #endif
 
-// One daily transport step of every cell (transport.py:948-991), one thread per cell.
+// One daily transport step of every cell (transport.py:948-991), one thread per cell.  STATS additionally evaluates the
+// age statistics (transport.py:59-312) and the water / solute balance errors (numerics.py:424-445, :476-516).
+template <bool STATS>
 __global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
 k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
-          const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out) {
+          const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out,
+          double* __restrict__ stats, double* __restrict__ C_s_prev) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
     __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
     for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
@@ -58,28 +61,72 @@ k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double*
     const double m = mask[i];
 #define F(k) forcing[(int64_t)(k) * C + i]
 #define O(k) out[(int64_t)(k) * C + i]
+#define ST(k) stats[(int64_t)(k) * C + i]
 #define SP(p) (sas_params + (int64_t)(p) * 8 * C + i)
     const double C_in = F(RSF_C_in);
+    double sum_sa_s_m1 = 0;
+    if (STATS) {  // vs.sa_s[taum1] as this step's soil kernel recomputes it (soil.py:1044-1048): the aged StorAge as found
+        double sm[1];
+        stream_sums<1, 2>(cx.plan,
+            [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = pl.sa[0][o]; L[1] = pl.sa[1][o]; },
+            [&](int, const double* L, double* v) { v[0] = L[0] + L[1] * m; }, sm);
+        sum_sa_s_m1 = sm[0];
+    }
     double a, b;
+    FluxStats fs_evap, fs_transp, fs_qss;
     inflow(cx, 0, F(RSF_inf_mat_rz), C_in, m, &a, &b);
     O(RSO_C_inf_mat_rz) = a; O(RSO_C_iso_inf_mat_rz) = b;
+    const double C_inf_mat_rz = a;
     inflow(cx, 0, F(RSF_inf_pf_rz), C_in, m, &a, &b);
     O(RSO_C_inf_pf_rz) = a; O(RSO_C_iso_inf_pf_rz) = b;
-    withdrawal(cx, 0, -1, F(RSF_evap_soil), SP(RSP_evap_soil), C, m, &a, &b, RSP_evap_soil);
+    const double C_inf_pf_rz = a;
+    withdrawal<STATS>(cx, 0, -1, F(RSF_evap_soil), SP(RSP_evap_soil), C, m, &a, &b, RSP_evap_soil, &fs_evap);
     O(RSO_C_evap_soil) = a; O(RSO_C_iso_evap_soil) = b;
-    withdrawal(cx, 0, -1, F(RSF_transp), SP(RSP_transp), C, m, &a, &b, RSP_transp);
+    const double C_evap = a;
+    withdrawal<STATS>(cx, 0, -1, F(RSF_transp), SP(RSP_transp), C, m, &a, &b, RSP_transp, &fs_transp);
     O(RSO_C_transp) = a; O(RSO_C_iso_transp) = b;
-    withdrawal(cx, 0, 1, F(RSF_q_rz), SP(RSP_q_rz), C, m, &a, &b, RSP_q_rz);
+    const double C_transp = a;
+    withdrawal<STATS>(cx, 0, 1, F(RSF_q_rz), SP(RSP_q_rz), C, m, &a, &b, RSP_q_rz, nullptr);
     O(RSO_C_q_rz) = a; O(RSO_C_iso_q_rz) = b;
     inflow(cx, 1, F(RSF_inf_pf_ss), C_in, m, &a, &b);
     O(RSO_C_inf_pf_ss) = a; O(RSO_C_iso_inf_pf_ss) = b;
-    withdrawal(cx, 1, -1, F(RSF_q_ss), SP(RSP_q_ss), C, m, &a, &b, RSP_q_ss);
+    const double C_inf_pf_ss = a;
+    withdrawal<STATS>(cx, 1, -1, F(RSF_q_ss), SP(RSP_q_ss), C, m, &a, &b, RSP_q_ss, &fs_qss);
     O(RSO_C_q_ss) = a; O(RSO_C_iso_q_ss) = b;
-    withdrawal(cx, 1, 0, F(RSF_cpr_rz), SP(RSP_cpr_rz), C, m, &a, &b, RSP_cpr_rz);
+    const double C_q_ss = a;
+    withdrawal<STATS>(cx, 1, 0, F(RSF_cpr_rz), SP(RSP_cpr_rz), C, m, &a, &b, RSP_cpr_rz, nullptr);
     O(RSO_C_cpr_rz) = a; O(RSO_C_iso_cpr_rz) = b;
-    storage_and_ageing(cx, m, out, C);
+    double sum_sa_s, C_s;
+    storage_concentrations(cx, m, out, C, &sum_sa_s, &C_s);
+    if (STATS) {
+        for (int k = 0; k < 5; k++) { ST(RSS_tt10_transp + k) = fs_transp.pct[k]; ST(RSS_tt10_q_ss + k) = fs_qss.pct[k]; }
+        ST(RSS_ttavg_transp) = fs_transp.avg;
+        ST(RSS_ttavg_q_ss) = fs_qss.avg;
+        const double p5[5] = {0.1, 0.25, 0.5, 0.75, 0.9}, p3[3] = {0.25, 0.5, 0.75};
+        double pc[5], avg;
+        storage_age_statistics(cx, 0, m, 3, p3, pc, &avg);
+        for (int k = 0; k < 3; k++) ST(RSS_rt25_rz + k) = pc[k];
+        ST(RSS_rtavg_rz) = avg;
+        storage_age_statistics(cx, 1, m, 3, p3, pc, &avg);
+        for (int k = 0; k < 3; k++) ST(RSS_rt25_ss + k) = pc[k];
+        ST(RSS_rtavg_ss) = avg;
+        storage_age_statistics(cx, 2, m, 5, p5, pc, &avg);
+        for (int k = 0; k < 5; k++) ST(RSS_rt10_s + k) = pc[k];
+        ST(RSS_rtavg_s) = avg;
+        auto nan0 = [](double x) { return (x != x) ? 0.0 : x; };
+        const double Cp = C_s_prev[i];
+        ST(RSS_dS_num_error) = fabs((sum_sa_s - sum_sa_s_m1) -
+                                    (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - fs_evap.wsum - fs_transp.wsum - fs_qss.wsum) * 1.0);
+        ST(RSS_dC_num_error) = fabs((sum_sa_s * C_s - sum_sa_s_m1 * Cp) -
+                                    (F(RSF_inf_mat_rz) * nan0(C_inf_mat_rz) + F(RSF_inf_pf_rz) * nan0(C_inf_pf_rz) +
+                                     F(RSF_inf_pf_ss) * nan0(C_inf_pf_ss) - fs_evap.wsum * nan0(C_evap) - fs_transp.wsum * nan0(C_transp) -
+                                     fs_qss.wsum * nan0(C_q_ss)) * 1.0);
+        C_s_prev[i] = C_s;
+    }
+    ageing(cx);
 #undef F
 #undef O
+#undef ST
 #undef SP
 }
 
@@ -193,6 +240,8 @@ struct roger_sas {
     double* d_tt = nullptr;
     double* d_forcing = nullptr;
     double* d_out = nullptr;
+    double* d_stats = nullptr;     // RSS_COUNT planes (settings.age_statistics)
+    double* d_C_s_prev = nullptr;  // vs.C_s[taum1]
     double* d_mask = nullptr;
     double* d_params = nullptr;
     double* d_stage = nullptr;
@@ -284,6 +333,12 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     CU(cudaMalloc(&h->d_forcing, sizeof(double) * RSF_COUNT * (size_t)n_cells));
     CU(cudaMalloc(&h->d_out, sizeof(double) * RSO_COUNT * (size_t)n_cells));
     CU(cudaMemsetAsync(h->d_out, 0, sizeof(double) * RSO_COUNT * (size_t)n_cells, h->stream));
+    if (settings->age_statistics) {
+        CU(cudaMalloc(&h->d_stats, sizeof(double) * RSS_COUNT * (size_t)n_cells));
+        CU(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * RSS_COUNT * (size_t)n_cells, h->stream));
+        CU(cudaMalloc(&h->d_C_s_prev, sizeof(double) * (size_t)n_cells));
+        CU(cudaMemsetAsync(h->d_C_s_prev, 0, sizeof(double) * (size_t)n_cells, h->stream));
+    }
     CU(cudaMalloc(&h->d_mask, sizeof(double) * (size_t)n_cells));
     CU(cudaMalloc(&h->d_params, sizeof(double) * RSP_COUNT * 8 * (size_t)n_cells));
     const int64_t budget = (int64_t)128 << 20;  // staging buffer bound
@@ -306,6 +361,7 @@ void roger_sas_destroy(roger_sas* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto p : h->d_state) cudaFree(p);
+    cudaFree(h->d_stats); cudaFree(h->d_C_s_prev);
     cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_params); cudaFree(h->d_stage); cudaFree(h->d_plan);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -377,7 +433,12 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     CU(cudaEventRecord(h->ev0, h->stream));
     const int threads = ROGER_SAS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
-    k_sas_day<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out);
+    if (h->st.age_statistics)
+        k_sas_day<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+                                                           h->d_stats, h->d_C_s_prev);
+    else
+        k_sas_day<false><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+                                                            nullptr, nullptr);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -406,6 +467,24 @@ int roger_sas_download_outputs(roger_sas* h, double* host) {
     if (!h || !host) return fail(ROGER_EINVAL, "roger_sas_download_outputs: bad argument");
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(host, h->d_out, sizeof(double) * RSO_COUNT * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int roger_sas_download_statistics(roger_sas* h, double* host) {
+    if (!h || !host) return fail(ROGER_EINVAL, "roger_sas_download_statistics: bad argument");
+    if (!h->d_stats) return fail(ROGER_EINVAL, "roger_sas_download_statistics: handle was created without settings.age_statistics");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(host, h->d_stats, sizeof(double) * RSS_COUNT * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int roger_sas_set_balance_reference(roger_sas* h, const double* C_s_prev) {
+    if (!h || !C_s_prev) return fail(ROGER_EINVAL, "roger_sas_set_balance_reference: bad argument");
+    if (!h->d_C_s_prev) return fail(ROGER_EINVAL, "roger_sas_set_balance_reference: handle was created without settings.age_statistics");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->d_C_s_prev, C_s_prev, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -284,6 +284,38 @@ __device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Loa
     for (int k = 0; k < NS; k++) out[k] = 0.0 + st[k][0];
 }
 
+// numpy.interp(p, cdf, 1..A) evaluated while the (non-decreasing) cdf streams by: the last index with cdf <= p and the
+// value that follows it (calc_age_percentile, transport.py:9-56; numpy's bisection returns the same index for a
+// non-decreasing array).
+struct PctTracker {
+    double p, x0, x1;
+    int j;
+    bool got1;
+    __device__ __forceinline__ void init(double p_) { p = p_; j = -1; got1 = false; x0 = 0; x1 = 0; }
+    __device__ __forceinline__ void push(int jbin, double v) {
+        if (v <= p) { j = jbin; x0 = v; got1 = false; }
+        else if (!got1) { x1 = v; got1 = true; }
+    }
+    __device__ __forceinline__ double result(int A, double cdf_max) const {
+        double r;
+        if (j == -1) r = 1.0;
+        else if (j == A - 1) r = (double)A;
+        else if (x0 == p) r = (double)(j + 1);
+        else {
+            const double slope = ((double)(j + 2) - (double)(j + 1)) / (x1 - x0);
+            r = slope * (p - x0) + (double)(j + 1);
+            if (isnan_d(r)) r = slope * (p - x1) + (double)(j + 2);
+        }
+        return (cdf_max <= 0) ? __longlong_as_double(0x7ff8000000000000LL) : r;
+    }
+};
+
+struct FluxStats {   // diagnostics of one withdrawal (STATS kernels only)
+    double wsum;     // sum(flux * tt), numerics.py:437-439
+    double pct[5];   // 10 / 25 / 50 / 75 / 90 percentile ages of the travel-time distribution
+    double avg;      // mean travel time
+};
+
 struct CellCtx {
     SasParams P;
     Planes pl;
@@ -414,8 +446,9 @@ __device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, 
 // ---- one SAS-controlled withdrawal from layer `src`, optionally received by layer `dst` (dst < 0: leaves the
 // soil).  evapotranspiration.py:653-716, :831-895; subsurface_runoff.py:1531-1625, :1753-1815;
 // capillary_rise.py:404-500.
+template <bool STATS>
 __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
-                                        double m, double* C_flux, double* C_iso_flux, int process) {
+                                        double m, double* C_flux, double* C_iso_flux, int process, FluxStats* fs) {
     constexpr int U = ROGER_SAS_UNROLL;
     const SasParams& P = cx.P;
     const int A = P.A;
@@ -501,8 +534,18 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
     double* __restrict__ tt_out = (P.store_tt && cx.pl.tt) ? cx.pl.tt + (size_t)process * (size_t)A * (size_t)C : nullptr;
     const double nsub = (double)P.substeps;
     double prev = 0. / nsub;
-    double sums[2];
-    stream_sums<2, 5>(cx.plan,
+    constexpr int NS = STATS ? 4 : 2;
+    double sums[NS];
+    PctTracker trk[STATS ? 5 : 1];
+    double cdf = 0;
+    NpMax cdf_max;
+    if (STATS) {
+        const double pcts[5] = {0.1, 0.25, 0.5, 0.75, 0.9};
+#pragma unroll
+        for (int k = 0; k < 5; k++) trk[k].init(pcts[k]);
+    }
+    bool first_bin = true;
+    stream_sums<NS, 5>(cx.plan,
         [&](int j, double* L) {
             const int64_t o = cx.ring(j);
             L[0] = active ? TTn[cx.lin(j)] : 0.;
@@ -524,6 +567,14 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
             const double mtt = ((t > 0) ? ms_j : 0) * m;
             v[0] = t;
             v[1] = mtt * t;
+            if (STATS) {
+                v[2] = flux * t;
+                v[3] = (double)(j + 1) * t;
+                cdf += t;  // TT[1:] = cumsum(tt)
+                if (first_bin) { cdf_max.init(cdf); first_bin = false; } else cdf_max.push(cdf);
+#pragma unroll
+                for (int k = 0; k < 5; k++) trk[k].push(j, cdf);
+            }
             if (dst >= 0) {
                 const double in = t * flux;
                 const double sd = L[3];
@@ -540,6 +591,12 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
             msa[o] = ((u <= 0) ? 0 : ms_j) * m;
             if (tt_out) tt_out[cx.lin(j)] = t;
         }, sums);
+    if (STATS && fs) {
+        fs->wsum = sums[2];
+#pragma unroll
+        for (int k = 0; k < 5; k++) fs->pct[k] = trk[k].result(A, cdf_max.get());
+        fs->avg = (sums[0] > 0) ? sums[3] : __longlong_as_double(0x7ff8000000000000LL);
+    }
     double conc = (sums[0] > 0) ? sums[1] / sums[0] : __longlong_as_double(0x7ff8000000000000LL);
     conc = (conc != 0) ? conc : __longlong_as_double(0x7ff8000000000000LL);
     *C_flux = conc * m;
@@ -569,9 +626,54 @@ __device__ __forceinline__ void inflow(const CellCtx& cx, int layer, double inf,
     }
 }
 
+// residence-time statistics of a storage (transport.py:161-312): RT = SA / max(SA) with SA = cumsum(sa) * m of the layer
+// (which 0: root zone, 1: subsoil, 2: soil = root zone + subsoil * m), percentile ages and the mean residence time
+__device__ __noinline__ void storage_age_statistics(const CellCtx& cx, int which, double m, int n_pct, const double* pcts, double* pct_out,
+                                                    double* avg_out) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    const double* __restrict__ s_rz = cx.pl.sa[0];
+    const double* __restrict__ s_ss = cx.pl.sa[1];
+    auto value = [&](int j) {
+        const int64_t o = cx.ring(j);
+        if (which == 0) return s_rz[o];
+        if (which == 1) return s_ss[o];
+        return s_rz[o] + s_ss[o] * m;
+    };
+    NpMax mx;
+    const double SA0 = 0. * m;
+    mx.init(SA0);
+    {
+        double acc = 0;
+        for (int j = 0; j < A; j++) { acc += value(j); mx.push(acc * m); }
+    }
+    const double mxv = mx.get();
+    PctTracker trk[5];
+    for (int k = 0; k < 5; k++) trk[k].init(k < n_pct ? pcts[k] : 0.5);
+    double acc = 0;
+    double RT_prev = (mxv > 0) ? SA0 / mxv : 0;
+    NpMax rt_max;
+    bool first_bin = true;
+    double sums[2];
+    stream_sums<2, 1>(cx.plan,
+        [&](int j, double* L) { L[0] = value(j); },
+        [&](int j, const double* L, double* v) {
+            acc += L[0];
+            const double RT = (mxv > 0) ? (acc * m) / mxv : 0;
+            const double rt = RT - RT_prev;
+            RT_prev = RT;
+            v[0] = rt;
+            v[1] = (double)(j + 1) * rt;
+            if (first_bin) { rt_max.init(RT); first_bin = false; } else rt_max.push(RT);
+            for (int k = 0; k < 5; k++) trk[k].push(j, RT);
+        }, sums);
+    for (int k = 0; k < n_pct; k++) pct_out[k] = trk[k].result(A, rt_max.get());
+    *avg_out = (sums[0] > 0) ? sums[1] : __longlong_as_double(0x7ff8000000000000LL);
+}
+
 // storage kernels (root_zone.py:189-215, subsoil.py:153-180, soil.py:1036-1092) followed by ageing
 // (transport.py:682-739) as a ring rotation
-__device__ __forceinline__ void storage_and_ageing(const CellCtx& cx, double m, double* out, int64_t oC) {
+__device__ __forceinline__ void storage_concentrations(const CellCtx& cx, double m, double* out, int64_t oC, double* sum_sa_s, double* C_s_out) {
     const SasParams& P = cx.P;
     const int A = P.A;
     double* __restrict__ s_rz = cx.pl.sa[0];
@@ -614,7 +716,14 @@ __device__ __forceinline__ void storage_and_ageing(const CellCtx& cx, double m, 
     out[RSO_C_iso_rz * oC + i] = conc_to_delta(P, C_rz) * m;
     out[RSO_C_iso_ss * oC + i] = conc_to_delta(P, C_ss) * m;
     out[RSO_C_iso_s * oC + i] = conc_to_delta(P, C_s) * m;
+    *sum_sa_s = sums[4];
+    *C_s_out = C_s;
+}
 
+__device__ __forceinline__ void ageing(const CellCtx& cx) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    const int64_t i = cx.i;
     // ageing: new bin j = old bin j-1; the oldest two bins merge; bin 0 is emptied.  With base' = base - 1 the old
     // bin A-1 becomes the new bin 0 and the old bin A-2 the new bin A-1.
     const int64_t C = P.C;

@@ -15,17 +15,23 @@ OUTPUTS = [
     "C_iso_cpr_rz", "C_rz", "C_ss", "C_s", "C_iso_rz", "C_iso_ss", "C_iso_s",
 ]
 STATE = ["sa_rz", "sa_ss", "msa_rz", "msa_ss"]
+STATISTICS = [
+    "tt10_transp", "tt25_transp", "tt50_transp", "tt75_transp", "tt90_transp", "ttavg_transp",
+    "tt10_q_ss", "tt25_q_ss", "tt50_q_ss", "tt75_q_ss", "tt90_q_ss", "ttavg_q_ss",
+    "rt25_rz", "rt50_rz", "rt75_rz", "rtavg_rz", "rt25_ss", "rt50_ss", "rt75_ss", "rtavg_ss",
+    "rt10_s", "rt25_s", "rt50_s", "rt75_s", "rt90_s", "rtavg_s", "dS_num_error", "dC_num_error",
+]
 VSMOW_conc18O = 2005.2e-6  # roger/settings.py
 D18O_MIN, D18O_MAX = -20.0, 0.0
 
 
 class SasSettings(C.Structure):
     _fields_ = [("ages", C.c_int32), ("substeps", C.c_int32), ("VSMOW_conc18O", C.c_double), ("d18O_min", C.c_double),
-                ("d18O_max", C.c_double), ("store_tt", C.c_int32), ("reserved", C.c_int32)]
+                ("d18O_max", C.c_double), ("store_tt", C.c_int32), ("age_statistics", C.c_int32)]
 
 
-def default_settings(ages, substeps=6, store_tt=False):
-    return SasSettings(int(ages), int(substeps), VSMOW_conc18O, D18O_MIN, D18O_MAX, int(store_tt), 0)
+def default_settings(ages, substeps=6, store_tt=False, age_statistics=False):
+    return SasSettings(int(ages), int(substeps), VSMOW_conc18O, D18O_MIN, D18O_MAX, int(store_tt), int(age_statistics))
 
 
 def delta_to_conc(delta):
@@ -66,13 +72,13 @@ def initial_age_distribution(S, ages):
 
 class SasModel:
     def __init__(self, engine_cls, n_cells, ages, daily, sas_spec, d18O_soil=-10.0, mask=None, substeps=6, store_tt=False,
-                 engine_kwargs=None):
+                 engine_kwargs=None, age_statistics=False):
         """daily: dict of (n_cells, ndays + 1) arrays PREC, INF_MAT_RZ, INF_PF_RZ, INF_PF_SS, TRANSP, EVAP_SOIL, CPR_RZ,
         Q_RZ, Q_SS, S_RZ, S_SS, S_SNOW, C_ISO_IN (index 0 = initial state, as in the reference's SVAT.nc)."""
         self.C = int(n_cells)
         self.ages = int(ages)
         self.daily = {k: np.asarray(v, dtype=np.float64) for k, v in daily.items()}
-        self.settings = default_settings(ages, substeps, store_tt)
+        self.settings = default_settings(ages, substeps, store_tt, age_statistics)
         self.engine = engine_cls(self.C, self.settings, **(engine_kwargs or {}))
         self.mask = np.ones(self.C) if mask is None else np.asarray(mask, dtype=np.float64)
         self.sas_params = sas_parameter_block(self.C, sas_spec)
@@ -96,6 +102,11 @@ class SasModel:
         self.engine.upload_state("sa_ss", sa_ss)
         self.engine.upload_state("msa_rz", msa)
         self.engine.upload_state("msa_ss", msa.copy())
+        if self.settings.age_statistics:
+            # vs.C_s[taum1] of the first step: the storage concentration of the initial state (what the reference's warmup
+            # leaves there, roger/roger.py:497-521)
+            c_s = np.where(np.sum(sa_rz + sa_ss, axis=-1) > 0, c0, 0.0)
+            self.engine.set_balance_reference(c_s)
 
     def _set_forcing(self):
         """benchmarks/SVATOXYGEN18_benchmark.py:385-444 (per-cell vectors)."""
@@ -127,6 +138,10 @@ class SasModel:
     def outputs(self):
         o = self.engine.download_outputs()
         return {n: o[k] for k, n in enumerate(OUTPUTS)}
+
+    def statistics(self):
+        o = self.engine.download_statistics()
+        return {n: o[k] for k, n in enumerate(STATISTICS)}
 
     def state(self, name):
         return self.engine.download_state(name)

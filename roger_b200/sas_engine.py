@@ -30,6 +30,8 @@ def _bind(lib):
     lib.roger_sas_step_device.argtypes = [hp, C.c_uint64]
     lib.roger_sas_download_outputs.argtypes = [hp, dp]
     lib.roger_sas_download_tt.argtypes = [hp, C.c_int, dp]
+    lib.roger_sas_download_statistics.argtypes = [hp, dp]
+    lib.roger_sas_set_balance_reference.argtypes = [hp, dp]
     lib.roger_sas_synchronize.argtypes = [hp]
     lib.roger_sas_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
     _bound = True
@@ -107,6 +109,17 @@ class CudaSasEngine:
         out = np.empty((len(sas.OUTPUTS), self.n))
         _check(self.lib, self.lib.roger_sas_download_outputs(self.h, self._dp(out)))
         return out
+
+    def download_statistics(self):
+        out = np.empty((len(sas.STATISTICS), self.n))
+        _check(self.lib, self.lib.roger_sas_download_statistics(self.h, self._dp(out)))
+        return out
+
+    def set_balance_reference(self, C_s_prev):
+        a = np.ascontiguousarray(C_s_prev, dtype=np.float64).reshape(-1)
+        if a.size != self.n:
+            raise ValueError("set_balance_reference: n_cells values expected")
+        _check(self.lib, self.lib.roger_sas_set_balance_reference(self.h, self._dp(a)))
 
     def download_tt(self, process):
         out = np.empty((self.n, self.A))

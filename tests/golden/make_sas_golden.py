@@ -38,6 +38,9 @@ CASES = {
     "sas_power": dict(shape=(2, 3), ndays=30, ages=60, doy=100, sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     # winter start: snow storage, isotope mixing in the snow pack
     "sas_power_snow": dict(shape=(2, 2), ndays=25, ages=50, doy=20, sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5)), var_input=True),
+    # age statistics (percentile ages by numpy.interp) and the water / solute balance errors
+    "sas_power_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=105, age_statistics=True,
+                            sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
     "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
                          sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
@@ -53,7 +56,7 @@ def build(name):
     svat = SvatModel(OracleSvatEngine, (nx, ny), forcing, prim, th_rz, th_ss)
     svat.setup()
     daily = sas_inputs.daily_fluxes_from_svat(svat, ndays)
-    case = dict(nx=nx, ny=ny, ndays=ndays, ages=ages)
+    case = dict(nx=nx, ny=ny, ndays=ndays, ages=ages, age_statistics=bool(c.get("age_statistics", False)))
     for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES):
         case[k] = daily[k].reshape(nx, ny, ndays + 1)
     for k in ("S_pwp_rz", "S_pwp_ss"):
@@ -94,6 +97,10 @@ def run(name, simd_out=None):
     scal_vars = ["C_evap_soil", "C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz", "C_iso_evap_soil", "C_iso_transp", "C_iso_q_rz", "C_iso_q_ss",
                  "C_iso_cpr_rz", "C_inf_mat_rz", "C_inf_pf_rz", "C_inf_pf_ss", "C_in"]
     lvl_vars = ["C_rz", "C_ss", "C_s", "C_iso_rz", "C_iso_ss", "C_iso_s", "C_snow"]
+    if case["age_statistics"]:
+        from roger_b200 import sas as _sas
+
+        scal_vars = scal_vars + list(_sas.STATISTICS)
 
     def grab():
         d = {}

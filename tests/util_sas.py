@@ -6,7 +6,7 @@ import numpy as np
 from roger_b200 import sas
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SAS_CASES = ["sas_power", "sas_power_snow", "sas_families"]
+SAS_CASES = ["sas_power", "sas_power_snow", "sas_families", "sas_power_stats"]
 
 
 def load_case(name):
@@ -14,16 +14,20 @@ def load_case(name):
         return {k: d[k] for k in d.files}
 
 
-def model_from_fixture(fx, engine_cls, store_tt=True, engine_kwargs=None, mask=None):
+def model_from_fixture(fx, engine_cls, store_tt=True, engine_kwargs=None, mask=None, age_statistics=None):
     C = int(fx["nx"]) * int(fx["ny"])
     A = int(fx["ages"])
     daily = {k[3:]: fx[k] for k in fx if k.startswith("in_")}
     spec = {p: fx["sas_" + p] for p in sas.PROCESSES}
+    if age_statistics is None:
+        age_statistics = "rec_dC_num_error" in fx
     m = sas.SasModel(engine_cls, C, A, daily, spec, substeps=int(fx["substeps"]), store_tt=store_tt, mask=mask,
-                     engine_kwargs=engine_kwargs)
+                     engine_kwargs=engine_kwargs, age_statistics=age_statistics)
     m.setup()
     for k in sas.STATE:  # start from the reference's own post-setup state
         m.engine.upload_state(k, fx["init_" + k])
+    if age_statistics:
+        m.engine.set_balance_reference(fx["init_C_s"])
     return m
 
 
@@ -55,6 +59,8 @@ def snapshot(model):
         for p in sas.PROCESSES:
             out["tt_" + p] = model.tt(p)
     out.update(model.outputs())
+    if model.settings.age_statistics:
+        out.update(model.statistics())
     out["C_in"] = model.C_in.copy()
     return out
 
