@@ -324,8 +324,12 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
         CU(cudaMalloc(&h->d_state[k], arr));
         CU(cudaMemsetAsync(h->d_state[k], 0, arr, h->stream));
     }
-    CU(cudaMalloc(&h->d_san, arr));
-    CU(cudaMalloc(&h->d_TTn, arr));
+    // the scratch arrays carry a few planes of padding: the sub-step pass prefetches ROGER_SAS_UNROLL bins ahead unguarded
+    const size_t pad = sizeof(double) * (size_t)n_cells * 8;
+    CU(cudaMalloc(&h->d_san, arr + pad));
+    CU(cudaMalloc(&h->d_TTn, arr + pad));
+    CU(cudaMemsetAsync(h->d_san, 0, arr + pad, h->stream));
+    CU(cudaMemsetAsync(h->d_TTn, 0, arr + pad, h->stream));
     if (settings->store_tt) {
         CU(cudaMalloc(&h->d_tt, arr * RSP_COUNT));
         CU(cudaMemsetAsync(h->d_tt, 0, arr * RSP_COUNT, h->stream));

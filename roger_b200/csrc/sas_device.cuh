@@ -381,66 +381,95 @@ __device__ __forceinline__ void substep_block(const CellCtx& cx, const Family& f
 // The sub-step pass of the benchmark configuration -- power-law SAS function, cell inside the catchment (m == 1),
 // S and flux * h in the range where div_by() is exact -- with everything that is constant over the age axis hoisted:
 // same operations on the same values as substep_block<> / omega(), far fewer instructions.
-template <int U>
-__device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, double y, bool first, double flux, double h, double fh,
+struct PowPassCarry {
+    double acc_in, acc_new, acc_t, om_prev, mxv;
+    bool anynan;
+};
+struct PowPassConst {
+    double S, rS, y, flux, h, fh, rfh;
+};
+
+// N consecutive bins whose san / TTn values are already in registers (xb, tb)
+template <int N, bool FIRST>
+__device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarry& c, const roger_pow_tables tabs, const double* xb,
+                                              const double* tb, double* __restrict__ san_o, double* __restrict__ TTn_o, int64_t C) {
+    double om[N];
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        c.acc_in += xb[u];
+        const double SA = c.acc_in;
+        const bool in = (SA > 0) && (SA <= k.S);
+        // SA >= 2^-500 and S <= 2^500 (checked by the caller) keep the quotient normal and div_by() exact
+        const bool easy = in && (SA >= 0x1p-500);
+        const double xr = div_by(SA, k.S, k.rS);
+        double p = roger_pow_core(easy ? roger_pow_asu(xr) : 0x3fe0000000000000ULL, k.y, tabs);
+        if (in && !easy) p = roger_pow(SA / k.S, k.y, tabs);
+        om[u] = (SA > 0) ? ((SA <= k.S) ? p : 1.) : 0.;
+    }
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        const double x = xb[u];
+        const double d = om[u] - c.om_prev;
+        c.om_prev = om[u];
+        double tti = (d >= 0) ? d : 0;
+        const double q = k.flux * tti * k.h;
+        const double ttqi = (q > x) ? x : q;
+        tti = (ttqi == 0 || div_range_ok(ttqi)) ? div_by(ttqi, k.fh, k.rfh) : ttqi / k.fh;
+        const double xn = x + -tti * k.flux * k.h;
+        san_o[u * C] = xn;
+        c.acc_new += xn;
+        c.anynan = c.anynan || isnan_d(c.acc_new);
+        c.mxv = (c.acc_new > c.mxv) ? c.acc_new : c.mxv;
+        c.acc_t += tti;
+        TTn_o[u * C] = (FIRST ? 0.0 : tb[u]) + c.acc_t;
+    }
+}
+
+template <bool FIRST>
+__device__ __noinline__ void pow_pass_tail(const PowPassConst& k, PowPassCarry& c, const roger_pow_tables tabs, double* __restrict__ san_o,
+                                           double* __restrict__ TTn_o, int64_t C, int n) {
+    for (int u = 0; u < n; u++) {
+        const double xb = san_o[u * C];
+        const double tb = FIRST ? 0.0 : TTn_o[u * C];
+        pow_pass_bins<1, FIRST>(k, c, tabs, &xb, &tb, san_o + u * C, TTn_o + u * C, C);
+    }
+}
+
+// returns max(cumsum(san)) after the sub-step (np.max semantics)
+template <int U, bool FIRST>
+__device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, double y, double flux, double h, double fh,
                                                    double* __restrict__ san, double* __restrict__ TTn) {
     const int A = cx.P.A;
     const int64_t C = cx.P.C;
-    const double rS = 1.0 / S, rfh = 1.0 / fh;
+    PowPassConst k{S, 1.0 / S, y, flux, h, fh, 1.0 / fh};
+    PowPassCarry c{0, 0, 0, 0.0, 0.0, false};  // om_prev = omega(SA[0] = 0) = 0, running max starts at SA[0] = 0
     const roger_pow_tables tabs = cx.tabs;
-    double acc_in = 0, acc_new = 0, acc_t = 0, om_prev = 0.0;
-    double mxv = 0.0;  // SA[0] = 0 * m
-    bool anynan = false;
-    int64_t o = cx.i;       // offset of the block being computed
+    double* __restrict__ ps = san + cx.i;
+    double* __restrict__ pt = TTn + cx.i;
+    const int nfull = A / U;
+    // register double buffer: the loads of block b + 1 are in flight while block b is computed.  The scratch arrays carry
+    // U planes of padding, so the look-ahead of the last block needs no guard.
     double xn_[U], tn_[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        xn_[u] = (u < A) ? san[o + u * C] : 0.0;
-        tn_[u] = (!first && u < A) ? TTn[o + u * C] : 0.0;
+        xn_[u] = ps[u * C];
+        tn_[u] = FIRST ? 0.0 : pt[u * C];
     }
-    for (int j0 = 0; j0 < A; j0 += U, o += U * C) {
-        double xb[U], tb[U], om[U];
+    for (int b = 0; b < nfull; b++) {
+        double xb[U], tb[U];
 #pragma unroll
         for (int u = 0; u < U; u++) { xb[u] = xn_[u]; tb[u] = tn_[u]; }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const bool ok = (j0 + U + u < A);
-            xn_[u] = ok ? san[o + (U + u) * C] : 0.0;
-            tn_[u] = (!first && ok) ? TTn[o + (U + u) * C] : 0.0;
+            xn_[u] = ps[(U + u) * C];
+            tn_[u] = FIRST ? 0.0 : pt[(U + u) * C];
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            acc_in += (j0 + u < A) ? xb[u] : 0.0;
-            const double SA = acc_in;
-            const bool in = (SA > 0) && (SA <= S);
-            const double xr = div_by(SA, S, rS);
-            const uint64_t ixr = roger_pow_asu(xr);
-            const bool easy = in && roger_pow_is_pos_normal(ixr) && div_range_ok(SA);
-            double p = roger_pow_core(easy ? ixr : 0x3fe0000000000000ULL, y, tabs);
-            if (in && !easy) p = roger_pow(SA / S, y, tabs);
-            om[u] = (SA > 0) ? ((SA <= S) ? p : 1.) : 0.;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (j0 + u < A) {
-                const double x = xb[u];
-                const double d = om[u] - om_prev;
-                om_prev = om[u];
-                double tti = (d >= 0) ? d : 0;
-                const double q = flux * tti * h;
-                const double ttqi = (q > x) ? x : q;
-                tti = (ttqi == 0 || div_range_ok(ttqi)) ? div_by(ttqi, fh, rfh) : ttqi / fh;
-                const double xn = x + -tti * flux * h;
-                san[o + u * C] = xn;
-                acc_new += xn;
-                anynan = anynan || isnan_d(acc_new);
-                mxv = (acc_new > mxv) ? acc_new : mxv;
-                acc_t += tti;
-                TTn[o + u * C] = (first ? 0.0 : tb[u]) + acc_t;
-            }
-        }
+        pow_pass_bins<U, FIRST>(k, c, tabs, xb, tb, ps, pt, C);
+        ps += U * C;
+        pt += U * C;
     }
-    return anynan ? __longlong_as_double(0x7ff8000000000000LL) : mxv;
+    if (nfull * U < A) pow_pass_tail<FIRST>(k, c, tabs, ps, pt, C, A - nfull * U);
+    return c.anynan ? __longlong_as_double(0x7ff8000000000000LL) : c.mxv;
 }
 
 // ---- one SAS-controlled withdrawal from layer `src`, optionally received by layer `dst` (dst < 0: leaves the
@@ -494,7 +523,8 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
             family_prepare(fam, mx.get());
             const bool first = (s == 0);
             if (fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh)) {
-                const double S_next = substep_pass_pow<U>(cx, fam.S, fam.sp[1], first, flux, h, fh, san, TTn);
+                const double S_next = first ? substep_pass_pow<U, true>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn)
+                                            : substep_pass_pow<U, false>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn);
                 mx.init(S_next);
                 continue;
             }

@@ -160,10 +160,10 @@ __global__ void k_aggregate_a(Planes pl, double* __restrict__ prec_m1, const dou
 
 // The fused step.  One thread = one soil column; all parameters and state in registers.
 #ifndef ROGER_MIN_BLOCKS
-#define ROGER_MIN_BLOCKS 4
+#define ROGER_MIN_BLOCKS 2
 #endif
 #ifndef ROGER_BLOCK
-#define ROGER_BLOCK 128
+#define ROGER_BLOCK 256
 #endif
 template <bool LAT, bool FLUX>
 __global__ void __launch_bounds__(ROGER_BLOCK, ROGER_MIN_BLOCKS)
