@@ -34,10 +34,10 @@ __device__ const roger_pow_log_entry d_pow_log_tab[ROGER_POW_N] = {ROGER_POW_LOG
 __device__ const roger_pow_exp_entry d_pow_exp_tab[ROGER_POW_N] = {ROGER_POW_EXP_TABLE};
 
 #ifndef ROGER_SAS_BLOCK
-#define ROGER_SAS_BLOCK 128
+#define ROGER_SAS_BLOCK 256
 #endif
 #ifndef ROGER_SAS_MIN_BLOCKS
-#define ROGER_SAS_MIN_BLOCKS 4
+#define ROGER_SAS_MIN_BLOCKS 2
 #endif
 
 // One daily transport step of every cell (transport.py:948-991), one thread per cell.  STATS additionally evaluates the
@@ -57,7 +57,8 @@ k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double*
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t C = P.C;
     if (i >= C) return;
-    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    extern __shared__ double s_ring[];  // (ROGER_SAS_STAGES + 1) * 2 * ROGER_SAS_UNROLL doubles per thread
+    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i, s_ring + threadIdx.x, (int)blockDim.x};
     const double m = mask[i];
 #define F(k) forcing[(int64_t)(k) * C + i]
 #define O(k) out[(int64_t)(k) * C + i]
@@ -325,7 +326,7 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
         CU(cudaMemsetAsync(h->d_state[k], 0, arr, h->stream));
     }
     // the scratch arrays carry a few planes of padding: the sub-step pass prefetches ROGER_SAS_UNROLL bins ahead unguarded
-    const size_t pad = sizeof(double) * (size_t)n_cells * 8;
+    const size_t pad = sizeof(double) * (size_t)n_cells * (size_t)(ROGER_SAS_STAGES * ROGER_SAS_UNROLL);
     CU(cudaMalloc(&h->d_san, arr + pad));
     CU(cudaMalloc(&h->d_TTn, arr + pad));
     CU(cudaMemsetAsync(h->d_san, 0, arr + pad, h->stream));
@@ -437,11 +438,12 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     CU(cudaEventRecord(h->ev0, h->stream));
     const int threads = ROGER_SAS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
+    const size_t ring_bytes = sizeof(double) * (size_t)(ROGER_SAS_STAGES + 1) * 2 * ROGER_SAS_UNROLL * (size_t)threads;
     if (h->st.age_statistics)
-        k_sas_day<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+        k_sas_day<true><<<blocks, threads, ring_bytes, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
                                                            h->d_stats, h->d_C_s_prev);
     else
-        k_sas_day<false><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+        k_sas_day<false><<<blocks, threads, ring_bytes, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
                                                             nullptr, nullptr);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, h->stream));
