@@ -57,8 +57,7 @@ k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double*
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t C = P.C;
     if (i >= C) return;
-    extern __shared__ double s_ring[];  // (ROGER_SAS_STAGES + 1) * 2 * ROGER_SAS_UNROLL doubles per thread
-    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i, s_ring + threadIdx.x, (int)blockDim.x};
+    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
     const double m = mask[i];
 #define F(k) forcing[(int64_t)(k) * C + i]
 #define O(k) out[(int64_t)(k) * C + i]
@@ -326,7 +325,7 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
         CU(cudaMemsetAsync(h->d_state[k], 0, arr, h->stream));
     }
     // the scratch arrays carry a few planes of padding: the sub-step pass prefetches ROGER_SAS_UNROLL bins ahead unguarded
-    const size_t pad = sizeof(double) * (size_t)n_cells * (size_t)(ROGER_SAS_STAGES * ROGER_SAS_UNROLL);
+    const size_t pad = sizeof(double) * (size_t)n_cells * 8;
     CU(cudaMalloc(&h->d_san, arr + pad));
     CU(cudaMalloc(&h->d_TTn, arr + pad));
     CU(cudaMemsetAsync(h->d_san, 0, arr + pad, h->stream));
@@ -438,12 +437,11 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     CU(cudaEventRecord(h->ev0, h->stream));
     const int threads = ROGER_SAS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
-    const size_t ring_bytes = sizeof(double) * (size_t)(ROGER_SAS_STAGES + 1) * 2 * ROGER_SAS_UNROLL * (size_t)threads;
     if (h->st.age_statistics)
-        k_sas_day<true><<<blocks, threads, ring_bytes, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+        k_sas_day<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
                                                            h->d_stats, h->d_C_s_prev);
     else
-        k_sas_day<false><<<blocks, threads, ring_bytes, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+        k_sas_day<false><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
                                                             nullptr, nullptr);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, h->stream));

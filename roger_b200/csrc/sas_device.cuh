@@ -322,8 +322,6 @@ struct CellCtx {
     const PwPlan* plan;
     roger_pow_tables tabs;
     int64_t i;
-    double* pf;       // this thread's slot 0 of the shared-memory prefetch ring (slot s at pf[s * ring_stride])
-    int ring_stride;  // = blockDim.x
     // element offset of age bin j of this cell in a rotated (state) array / in a scratch array
     __device__ __forceinline__ int64_t ring(int j) const {
         int p = P.base + j;
@@ -398,6 +396,14 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
     double om[N];
 #pragma unroll
     for (int u = 0; u < N; u++) {
+        if (xb[u] == 0) {
+            // an empty bin leaves the cumulative StorAge -- and therefore the SAS function value -- bit-identical to the
+            // previous bin's: reuse it.  (Every dry day leaves an empty bin behind, and under spatially uniform forcing
+            // whole warps skip together.)
+            c.acc_in += xb[u];
+            om[u] = (u == 0) ? c.om_prev : om[u - 1];
+            continue;
+        }
         c.acc_in += xb[u];
         const double SA = c.acc_in;
         const bool in = (SA > 0) && (SA <= k.S);
@@ -437,30 +443,10 @@ __device__ __noinline__ void pow_pass_tail(const PowPassConst& k, PowPassCarry& 
     }
 }
 
-#ifndef ROGER_SAS_STAGES
-#define ROGER_SAS_STAGES 4   // blocks of ROGER_SAS_UNROLL bins in flight per thread
-#endif
-
-// 8-byte asynchronous global -> shared copy (LDGSTS); each thread prefetches its own elements into its own ring slots, so
-// no cross-thread synchronisation is involved: a thread waits on its own copy groups only.
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// returns max(cumsum(san)) after the sub-step (np.max semantics).
-// Memory pipeline: the san / TTn values of the next ROGER_SAS_STAGES blocks are in flight as cp.async copies into a
-// per-thread shared-memory ring (STAGES + 1 slots, so a slot is refilled one iteration after it was read); the loop body
-// reads registers and shared memory only.  The scratch arrays carry STAGES * U planes of padding: no look-ahead guard.
+// returns max(cumsum(san)) after the sub-step (np.max semantics)
 template <int U, bool FIRST>
 __device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, double y, double flux, double h, double fh,
                                                    double* __restrict__ san, double* __restrict__ TTn) {
-    constexpr int D = ROGER_SAS_STAGES;
-    constexpr int SLOTS = D + 1;
-    constexpr int PER = FIRST ? U : 2 * U;  // doubles per ring slot
     const int A = cx.P.A;
     const int64_t C = cx.P.C;
     PowPassConst k{S, 1.0 / S, y, flux, h, fh, 1.0 / fh};
@@ -468,37 +454,28 @@ __device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, 
     const roger_pow_tables tabs = cx.tabs;
     double* __restrict__ ps = san + cx.i;
     double* __restrict__ pt = TTn + cx.i;
-    double* const ring = cx.pf;
-    const int rs = cx.ring_stride;
     const int nfull = A / U;
-    auto issue = [&](int blk) {  // copies of block `blk` into slot blk % SLOTS
-        double* slot = ring + (size_t)((blk % SLOTS) * (2 * U)) * rs;
-        const int64_t off = (int64_t)blk * U * C;
+    // register double buffer: the loads of block b + 1 are in flight while block b is computed.  The scratch arrays carry
+    // U planes of padding, so the look-ahead of the last block needs no guard.
+    double xn_[U], tn_[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            cp_async8(slot + u * rs, san + cx.i + off + u * C);
-            if (!FIRST) cp_async8(slot + (U + u) * rs, TTn + cx.i + off + u * C);
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int b = 0; b < D; b++) issue(b);
+    for (int u = 0; u < U; u++) {
+        xn_[u] = ps[u * C];
+        tn_[u] = FIRST ? 0.0 : pt[u * C];
+    }
     for (int b = 0; b < nfull; b++) {
-        cp_async_wait<D - 1>();  // this thread's copies of block b have landed
-        const double* slot = ring + (size_t)((b % SLOTS) * (2 * U)) * rs;
         double xb[U], tb[U];
 #pragma unroll
+        for (int u = 0; u < U; u++) { xb[u] = xn_[u]; tb[u] = tn_[u]; }
+#pragma unroll
         for (int u = 0; u < U; u++) {
-            xb[u] = slot[u * rs];
-            tb[u] = FIRST ? 0.0 : slot[(U + u) * rs];
+            xn_[u] = ps[(U + u) * C];
+            tn_[u] = FIRST ? 0.0 : pt[(U + u) * C];
         }
-        issue(b + D);
         pow_pass_bins<U, FIRST>(k, c, tabs, xb, tb, ps, pt, C);
         ps += U * C;
         pt += U * C;
     }
-    cp_async_wait<0>();
-    (void)PER;
     if (nfull * U < A) pow_pass_tail<FIRST>(k, c, tabs, ps, pt, C, A - nfull * U);
     return c.anynan ? __longlong_as_double(0x7ff8000000000000LL) : c.mxv;
 }
