@@ -29,6 +29,10 @@ from roger_b200.svat import SvatModel  # noqa: E402
 
 # algorithmic bytes per cell-timestep (2*state + parameters + forcing)
 ALGO_BYTES = {"svat": 984.0, "oned": 1200.0}
+# DRAM bytes per cell and launch of the dominant kernel from the committed `ncu --set full` captures (profiles/r1_ncu_summary.md:
+# dram__bytes_read.sum + dram__bytes_write.sum divided by the cells of the captured launch); None where no capture exists
+NCU_DRAM_BYTES_PER_CELL = {"oned": 1137.0, "svat": None}
+NCU_DRAM_BYTES_PER_BIN_DAY = 1327.0  # k_sas_day, per cell and age bin
 
 
 def use_all_host_cores():
@@ -219,21 +223,26 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM, device-timed ---------------------------------------------
+    ms_by_dt = {}
+
     def advance(n):
         """exactly n adaptive steps (day-blocked launches where the scheduler allows); returns {dt_secs: count}"""
         kinds, left = {}, n
         while left > 0:
             # large grids step one launch at a time (the engine's default there), which also records the dt of each step
+            ms0 = eng.kernel_ms
             done = m.run_steps(1 if C > 262144 else left)
             sc = eng.get_scalars()
             if done == 1:
                 kinds[int(sc.dt_secs)] = kinds.get(int(sc.dt_secs), 0) + 1
+                ms_by_dt[int(sc.dt_secs)] = ms_by_dt.get(int(sc.dt_secs), 0.0) + (eng.kernel_ms - ms0)
             else:
                 kinds["day-blocked"] = kinds.get("day-blocked", 0) + done
             left -= done
         return kinds
 
     advance(args.warmup)
+    ms_by_dt.clear()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -306,9 +315,12 @@ def run_cuda(args):
                 "cells_per_gpu": C, "step_mix_dt_secs": kinds, "l2": "state planes are %.1f GB per GPU, far larger than the 126 MB L2" % (C * 8 * 120 / 1e9),
                 "parallelism": f"cell-block x{world}",
             },
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": (NCU_DRAM_BYTES_PER_CELL[args.workload] * C if NCU_DRAM_BYTES_PER_CELL[args.workload] else None),
+                         "traffic_source": "profiles/r1_ncu_summary.md (bytes per cell of the captured launch x cells per launch)",
                          "peak_source": peak_src, "algorithmic_bytes_per_cell_timestep": algo,
-                         "kernel_ms_per_step": 1e3 * kern_time / args.steps},
+                         "kernel_ms_per_step": 1e3 * kern_time / args.steps,
+                         "kernel_ms_per_step_by_dt_secs": {k: v / kinds[k] for k, v in ms_by_dt.items() if kinds.get(k)}},
             "e2e": {"value": e2e_value, "unit": "cell-timesteps/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -446,7 +458,9 @@ def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages):
                                "(SVATOXYGEN18_benchmark.py), 6 sub-steps, daily forcing from an online SVAT run of a 64x64 tile",
                    "cells_per_gpu": C, "ages": ages,
                    "l2": "age-ranked state is %.1f GB per GPU, far larger than the 126 MB L2" % (C * ages * 8 * 4 / 1e9)},
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": NCU_DRAM_BYTES_PER_BIN_DAY * ages * C, "traffic_frac_of_peak": NCU_DRAM_BYTES_PER_BIN_DAY * ages * C * steps / kern / 1e9 / peak,
+                     "traffic_source": "profiles/r1_ncu_summary.md (bytes per cell and age bin of the captured launch x cells x bins)",
                      "peak_source": peak_src, "algorithmic_bytes_per_cell_timestep": algo, "kernel_ms_per_step": 1e3 * kern / steps,
                      "note": "exact-order solver streams its two scratch arrays once per sub-step: measured DRAM traffic is ~20x the "
                              "algorithmic bytes (profiles/), see DESIGN.md"},
