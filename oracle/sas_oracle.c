@@ -19,7 +19,9 @@
  * (roger_b200/csrc/roger_pow.h), the fixed IEEE operation sequence the CUDA kernels also evaluate, so that GPU
  * results can be compared with this oracle bit for bit (the two modes differ by at most 1 ulp per call). */
 ROGER_POW_DEFINE_HOST_TABLES(static const)
-static int g_pow_mode = 0;
+int g_roger_oracle_pow_mode = 0; /* shared with svat_oracle.c */
+#define g_pow_mode g_roger_oracle_pow_mode
+void roger_oracle_set_pow(int mode) { g_pow_mode = mode; }
 void sas_oracle_set_pow(int mode) { g_pow_mode = mode; }
 double roger_pow_host(double x, double y)
 {

@@ -36,6 +36,13 @@ void roger_oracle_set_threads(int n)
 #endif
 }
 
+/* Which pow the physics calls (see sas_oracle.c): 0 the C library's pow -- the mode the oracle is pinned in against the
+ * reference fixtures -- 1 roger_pow(), the fixed IEEE operation sequence the CUDA kernels evaluate, for bit-for-bit
+ * comparisons with the GPU. */
+extern int g_roger_oracle_pow_mode;
+double roger_pow_host(double x, double y);
+static double opow(double x, double y) { return g_roger_oracle_pow_mode ? roger_pow_host(x, y) : pow(x, y); }
+
 #define NSLOT ROGER_SLOTS_PER_DAY
 #define V(name) f[RF_##name]
 
@@ -284,7 +291,7 @@ static void calc_transp(double *f, const step_ctx *c) /* evapotranspiration.py:3
     int mask_anoxia = (V(lu_id) > 500) && (V(lu_id) < 599) && (V(theta_rz) >= 0.8 * V(theta_sat));
     if (mask_anoxia) {
         double r = V(S_lp_rz) / V(S_ac_rz);
-        V(transp_coeff) = (((r >= 0) && (r <= 1)) ? 1 - pow(r, 1.5) : 1) * m;
+        V(transp_coeff) = (((r >= 0) && (r <= 1)) ? 1 - opow(r, 1.5) : 1) * m;
     } else {
         V(transp_coeff) = V(transp_coeff) * m;
     }
@@ -649,8 +656,8 @@ static void calc_inf_mp(double *f, const step_ctx *c, const cell_m1 *p) /* infil
         b2 = (r_mp * (V(theta_d) * V(theta_d))) * (12 * cc - a + b1) * m;
         b2 = (isnan(b2) ? 0 : b2) * m;
         b2 = ((b2 <= 0) ? 0 : b2) * m;
-        y1 = ((pow(b2, 1.0 / 3)) / V(theta_d)) * 0.5 * m;
-        y2 = (a / (pow(b2, 1.0 / 3))) * 0.5 * m;
+        y1 = ((opow(b2, 1.0 / 3)) / V(theta_d)) * 0.5 * m;
+        y2 = (a / (opow(b2, 1.0 / 3))) * 0.5 * m;
         y = (y1 + y2 + ym1) * m;
         y = ((y < r_mp) ? r_mp : y) * m;
         y = ((y < ym1) ? ym1 : y) * m;
@@ -663,7 +670,7 @@ static void calc_inf_mp(double *f, const step_ctx *c, const cell_m1 *p) /* infil
         inf_mp_event_csum += inf_mp_di * m;
         y = r_mp + sqrt((inf_mp_event_csum / (V(dmpv) * V(theta_d))) / pi) * m; /* :728-730 */
         y = ((y < r_mp) ? r_mp : y) * m;
-        t = V(theta_d) / (V(ks) * V(wfs) * r_mp) * (pow(y, 3) / 3.0 - (y * y) * r_mp / 2.0 + (r_mp * r_mp * r_mp) / 6.0) * m;
+        t = V(theta_d) / (V(ks) * V(wfs) * r_mp) * (opow(y, 3) / 3.0 - (y * y) * r_mp / 2.0 + (r_mp * r_mp * r_mp) / 6.0) * m;
         inf_mp = ((inf_mp < 0) ? 0 : inf_mp) * m;
         ym1 = y * m;
     }
@@ -876,8 +883,8 @@ static void calc_potential_percolation_rz(double *f, const step_ctx *c, const ce
     perc_pot = (mask2 ? V(k_rz) * dt : perc_pot) * m;
     double z = (V(z_soil) - V(z_root)) - V(z_sat);
     if (mask3) {
-        double pa = pow(z / (-V(ha) * 10.2), -V(n_salv));
-        double pb = pow(-V(h_rz) / -V(ha), -V(n_salv));
+        double pa = opow(z / (-V(ha) * 10.2), -V(n_salv));
+        double pb = opow(-V(h_rz) / -V(ha), -V(n_salv));
         perc_pot = (((pa - pb) / (1 + pb + (V(n_salv) - 1) * pa)) * dt * V(ks) * (-1)) * m;
     } else {
         perc_pot = perc_pot * m;
@@ -925,8 +932,8 @@ static void calc_potential_percolation_ss(double *f, const step_ctx *c) /* subsu
     const double zgw = V(z_gw);
     double z = (zgw * 1000 - V(z_soil)) + ((V(z_soil) - V(z_root)) / 2) * m;
     double perc_pot;
-    double pa = pow(z / (-V(ha) * 10.2), -V(n_salv));
-    double pb = pow(-V(h_ss) / -V(ha), -V(n_salv));
+    double pa = opow(z / (-V(ha) * 10.2), -V(n_salv));
+    double pb = opow(-V(h_ss) / -V(ha), -V(n_salv));
     double kmin = fmin(fmin(V(kf) * dt, V(ks_ss) * dt), V(k_ss) * dt);
     /* first assignment (z_gw > 10) :984-1003 */
     if ((zgw > 10) && (zgw * 1000 > V(z_soil)) && (V(z_sat) > 0))
@@ -1062,8 +1069,8 @@ static void calc_cpr_rz(double *f, const step_ctx *c) /* capillary_rise.py:7-173
 {
     const double m = V(maskCatch), dt = c->dt;
     double z = ((V(z_root) + (V(z_soil) - V(z_root)) / 2) - V(z_root) / 2) * m;
-    double pa = pow(z / (-V(ha) * 10.2), -V(n_salv));
-    double pb = pow(-V(h_rz) / -V(ha), -V(n_salv));
+    double pa = opow(z / (-V(ha) * 10.2), -V(n_salv));
+    double pb = opow(-V(h_rz) / -V(ha), -V(n_salv));
     V(cpr_rz) = (pa - pb) / (1 + pb + (V(n_salv) - 1) * pa) * dt * V(ks) * m;
     V(cpr_rz) = ((V(cpr_rz) < 0) ? 0 : V(cpr_rz)) * m;
     V(cpr_rz) = (isnan(V(cpr_rz)) ? 0 : V(cpr_rz)) * m;
@@ -1107,23 +1114,23 @@ static void calc_storages(double *f, const step_ctx *c, const cell_m1 *p)
     } else {
         V(irr_demand) = 0;
     }
-    V(k_rz) = (V(ks) / (1 + pow(V(theta_rz) / V(theta_sat), -V(m_bc)))) * m;
-    V(h_rz) = (V(ha) / pow(V(theta_rz) / V(theta_sat), 1 / V(lambda_bc))) * m;
+    V(k_rz) = (V(ks) / (1 + opow(V(theta_rz) / V(theta_sat), -V(m_bc)))) * m;
+    V(h_rz) = (V(ha) / opow(V(theta_rz) / V(theta_sat), 1 / V(lambda_bc))) * m;
     /* subsoil */
     V(S_ss) = (V(S_pwp_ss) + V(S_fp_ss) + V(S_lp_ss)) * m;
     V(dS_ss) = (V(S_ss) - p->S_ss) * m;
     V(theta_ss) = ((V(S_fp_ss) + V(S_lp_ss)) / (V(z_soil) - V(z_root)) + V(theta_pwp)) * m;
     V(ks_ss) = V(ks); /* subsoil.py:6-20 (no soil compaction) */
-    V(k_ss) = (V(ks) / (1 + pow(V(theta_ss) / V(theta_sat), -V(m_bc)))) * m;
-    V(h_ss) = (V(ha) / pow(V(theta_ss) / V(theta_sat), 1 / V(lambda_bc))) * m;
+    V(k_ss) = (V(ks) / (1 + opow(V(theta_ss) / V(theta_sat), -V(m_bc)))) * m;
+    V(h_ss) = (V(ha) / opow(V(theta_ss) / V(theta_sat), 1 / V(lambda_bc))) * m;
     /* soil */
     V(S_fp_s) = (V(S_fp_rz) + V(S_fp_ss)) * m;
     V(S_lp_s) = (V(S_lp_rz) + V(S_lp_ss)) * m;
     V(S_s) = (V(S_pwp_s) + V(S_fp_s) + V(S_lp_s)) * m;
     V(dS_s) = (V(S_s) - p->S_s) * m;
     V(theta) = ((V(S_fp_s) + V(S_lp_s)) / V(z_soil) + V(theta_pwp)) * m;
-    V(k) = (V(ks) / (1 + pow(V(theta) / V(theta_sat), -V(m_bc)))) * m;
-    V(h) = (V(ha) / pow(V(theta) / V(theta_sat), 1 / V(lambda_bc))) * m;
+    V(k) = (V(ks) / (1 + opow(V(theta) / V(theta_sat), -V(m_bc)))) * m;
+    V(h) = (V(ha) / opow(V(theta) / V(theta_sat), 1 / V(lambda_bc))) * m;
     /* numerics.calc_storage_kernel */
     V(S) = V(S_sur) + V(S_s) * m;       /* numerics.py:134 */
     V(dS) = V(S) - p->S * m;            /* numerics.py:147 */

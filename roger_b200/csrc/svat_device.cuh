@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "../../include/roger_b200.h"
+#include "roger_pow.h"
 
 namespace roger {
 
@@ -45,13 +46,20 @@ struct StepPlan {
 #define RD __device__ __forceinline__
 
 // ---- arithmetic helpers ---------------------------------------------------------------------
-// ROGER_FAST_MATH (default): transcendental powers are evaluated as exp(y*log(x)) with the logarithm shared
-// between powers of the same base, the cube root / cube of the macropore front use cbrt() / y*y*y, and
-// divisions with a zero operand skip the IEEE slow path.  Results stay within a few ulp of libm's pow
-// (far inside the 1e-10 parity tolerance); build with -DROGER_FAST_MATH=0 for pow() everywhere.
+// ROGER_FAST_MATH = 0 (default): every power of the reference (`**` / npx.power on float64) is roger_pow()
+// (roger_pow.h), the fixed IEEE operation sequence the CPU oracle can be switched to as well, so that kernel and oracle
+// agree bit for bit -- the step takes hard decisions on cancellation residues (e.g. z_sat = +-1e-18 switches the
+// lateral-flow branch, subsurface_runoff.py:52-246), which turn a last-bit difference of pow into a visibly different
+// trajectory of single cells.
+// ROGER_FAST_MATH = 1: powers as exp(y*log(x)) with the logarithm shared between powers of the same base, cbrt() and
+// y*y*y for the macropore front: a few ulp from libm's pow, ~1e-10 parity on most cells but not bit-reproducible.
 #ifndef ROGER_FAST_MATH
-#define ROGER_FAST_MATH 1
+#define ROGER_FAST_MATH 0
 #endif
+
+static __device__ const roger_pow_log_entry g_svat_pow_log_tab[ROGER_POW_N] = {ROGER_POW_LOG_TABLE};
+static __device__ const roger_pow_exp_entry g_svat_pow_exp_tab[ROGER_POW_N] = {ROGER_POW_EXP_TABLE};
+RD double xpow(double x, double y) { return roger_pow(x, y, roger_pow_tables{g_svat_pow_log_tab, g_svat_pow_exp_tab}); }
 
 // IEEE-identical a / b.  nvcc's inline double division branches to a ~60-instruction slow path whenever an
 // operand's exponent field is 0 (i.e. also for an exact zero); on dry steps most numerators of the
@@ -73,21 +81,21 @@ RD double powr(double x, double y) {  // x ** y (numpy power on float64)
 #if ROGER_FAST_MATH
     return exp(y * log(x));
 #else
-    return pow(x, y);
+    return xpow(x, y);
 #endif
 }
 RD double cube_root(double x) {  // x ** (1 / 3)
 #if ROGER_FAST_MATH
     return cbrt(x);
 #else
-    return pow(x, 1.0 / 3);
+    return xpow(x, 1.0 / 3);
 #endif
 }
 RD double cube(double x) {  // x ** 3
 #if ROGER_FAST_MATH
     return x * x * x;
 #else
-    return pow(x, 3.0);
+    return xpow(x, 3.0);
 #endif
 }
 
@@ -305,7 +313,7 @@ RD void evapotranspiration(Cell& c, const StepPlan& p, const Io& io) {
         bool anoxia = (c.lu_id > 500) && (c.lu_id < 599) && (c.theta_rz >= 0.8 * c.theta_sat);
         if (anoxia) {
             double r = c.S_lp_rz / c.S_ac_rz;
-            tc = ((r >= 0) && (r <= 1)) ? 1 - pow(r, 1.5) : 1.0;
+            tc = ((r >= 0) && (r <= 1)) ? 1 - powr(r, 1.5) : 1.0;
         }
         tc = M(tc);
         c.transp_coeff = tc;
@@ -1099,8 +1107,8 @@ RD void brooks_corey(const Cell& c, double theta, double mm, double inv_lambda, 
     k = M(c.ks / (1 + exp(mm * lr)));
     h = M(c.ha / exp(inv_lambda * lr));
 #else
-    k = M(c.ks / (1 + pow(r, mm)));
-    h = M(c.ha / pow(r, inv_lambda));
+    k = M(c.ks / (1 + powr(r, mm)));
+    h = M(c.ha / powr(r, inv_lambda));
 #endif
 }
 

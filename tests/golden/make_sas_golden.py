@@ -17,7 +17,7 @@ import sys
 import tempfile
 
 NO_SIMD = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX2 FMA3"
-if "--simd" not in sys.argv and os.environ.get("NPY_DISABLE_CPU_FEATURES") != NO_SIMD:
+if __name__ == "__main__" and "--simd" not in sys.argv and os.environ.get("NPY_DISABLE_CPU_FEATURES") != NO_SIMD:
     os.environ["NPY_DISABLE_CPU_FEATURES"] = NO_SIMD  # must be set before numpy is imported
     os.execv(sys.executable, [sys.executable] + sys.argv)
 

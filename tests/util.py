@@ -60,7 +60,14 @@ def normalised_max_error(a, b):
     return float(np.max(diff) / scale)
 
 
-def replay_and_compare(fx, model, tol, kinds=("S", "F"), skip=(), write_fluxes=True, collect=None):
+def same_bits(a, b):
+    """value equality of every element (NaN == NaN, -0.0 == 0.0)"""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def replay_and_compare(fx, model, tol, kinds=("S", "F"), skip=(), write_fluxes=True, collect=None, exact=False):
     names = [str(n) for n in fx["field_names"]]
     kinds_of = {str(n): str(k) for n, k in zip(fx["field_names"], fx["field_kinds"])}
     rec_steps = [int(s) for s in fx["rec_steps"]]
@@ -79,6 +86,9 @@ def replay_and_compare(fx, model, tol, kinds=("S", "F"), skip=(), write_fluxes=T
             ref = fx["rec_fields"][rec[step]]
             for n, row in zip(names, ref):
                 if kinds_of[n] not in kinds or n in skip or np.isnan(row).all():
+                    continue
+                if exact:
+                    assert same_bits(row, model.get(n)), f"step {step}: {n} differs from the reference fixture"
                     continue
                 if n.endswith("_num_error"):
                     # closure residuals are O(1e-14) rounding noise: compared absolutely (mm)
