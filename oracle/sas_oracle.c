@@ -28,6 +28,11 @@ double roger_pow_host(double x, double y)
     const roger_pow_tables t = {roger_pow_log_tab_h, roger_pow_exp_tab_h};
     return roger_pow(x, y, t);
 }
+void roger_pow2_host(double x, double y1, double y2, double *r1, double *r2)
+{
+    const roger_pow_tables t = {roger_pow_log_tab_h, roger_pow_exp_tab_h};
+    roger_pow2(x, y1, y2, t, r1, r2);
+}
 void roger_pow_host_array(const double *x, const double *y, double *out, int64_t n)
 {
     for (int64_t i = 0; i < n; i++) out[i] = roger_pow_host(x[i], y[i]);

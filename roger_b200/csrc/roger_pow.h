@@ -171,10 +171,18 @@ ROGER_POW_FN double roger_pow_exp(double x, double xtail, const roger_pow_exp_en
 /* x^y for a positive NORMAL x given as bits and a finite y, without branches (range handling by selects): the form
  * the CUDA kernels inline several times per loop iteration so that independent evaluations interleave.
  * roger_pow() below is this function behind the special cases; both return the same bits on the common domain. */
+/* second half of the evaluation: exp(y * (hi + lo)) with the range handling by selects */
+ROGER_POW_FN double roger_pow_from_log(double hi, double lo, double y, const roger_pow_tables tabs);
+
 ROGER_POW_FN double roger_pow_core(uint64_t ix, double y, const roger_pow_tables tabs)
 {
     double lo;
     const double hi = roger_pow_log(ix, &lo, tabs.log_tab);
+    return roger_pow_from_log(hi, lo, y, tabs);
+}
+
+ROGER_POW_FN double roger_pow_from_log(double hi, double lo, double y, const roger_pow_tables tabs)
+{
     const double ehi = roger_pow_mul(y, hi);
     const double elo = roger_pow_add(roger_pow_mul(y, lo), roger_pow_fma(y, hi, -ehi));
     const int ovf = !(ehi < RPK(ovf, 0x1.62e42fefa39efp+9)); /* >= 1024 ln2: overflow              */
@@ -205,6 +213,22 @@ ROGER_POW_FN double roger_pow(double x, double y, const roger_pow_tables tabs)
 
 /* true when x is a positive normal number (the domain of roger_pow_core) */
 ROGER_POW_FN int roger_pow_is_pos_normal(uint64_t ix) { return ((ix >> 52) - 1ULL) < 0x7feULL; }
+
+/* x^y1 and x^y2 with the logarithm of the common base evaluated once; each result has the bits roger_pow(x, y) returns */
+ROGER_POW_FN void roger_pow2(double x, double y1, double y2, const roger_pow_tables tabs, double *r1, double *r2)
+{
+    const uint64_t ix = roger_pow_asu(x);
+    const int plain = roger_pow_is_pos_normal(ix) && x != 1.0 && (y1 - y1 == 0.0) && (y2 - y2 == 0.0) && y1 != 0.0 && y2 != 0.0;
+    if (!plain) {
+        *r1 = roger_pow(x, y1, tabs);
+        *r2 = roger_pow(x, y2, tabs);
+        return;
+    }
+    double lo;
+    const double hi = roger_pow_log(ix, &lo, tabs.log_tab);
+    *r1 = roger_pow_from_log(hi, lo, y1, tabs);
+    *r2 = roger_pow_from_log(hi, lo, y2, tabs);
+}
 
 /* exp(x) by the same reduction (tail 0): overflow -> +inf, results below 2^-1022 flushed to 0 */
 ROGER_POW_FN double roger_exp(double x, const roger_pow_tables tabs)

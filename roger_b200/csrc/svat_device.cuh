@@ -1107,8 +1107,10 @@ RD void brooks_corey(const Cell& c, double theta, double mm, double inv_lambda, 
     k = M(c.ks / (1 + exp(mm * lr)));
     h = M(c.ha / exp(inv_lambda * lr));
 #else
-    k = M(c.ks / (1 + powr(r, mm)));
-    h = M(c.ha / powr(r, inv_lambda));
+    double pk, ph;  // r**mm and r**inv_lambda, one logarithm (bit-identical to two separate powers)
+    roger_pow2(r, mm, inv_lambda, roger_pow_tables{g_svat_pow_log_tab, g_svat_pow_exp_tab}, &pk, &ph);
+    k = M(c.ks / (1 + pk));
+    h = M(c.ha / ph);
 #endif
 }
 

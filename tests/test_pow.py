@@ -66,3 +66,20 @@ def test_special_values():
     a = np.array([L.roger_exp_host(v) for v in x])
     b = np.exp(x)
     assert (np.abs(a - b) / np.spacing(b)).max() <= 1.0
+
+
+def test_pow2_returns_the_bits_of_two_separate_powers():
+    L = lib()
+    L.roger_pow2_host.argtypes = [C.c_double, C.c_double, C.c_double, dp, dp]
+    L.roger_pow2_host.restype = None
+    L.roger_pow_host.restype = C.c_double
+    L.roger_pow_host.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(4)
+    xs = np.concatenate([rng.uniform(0, 2, 20000), [0.0, 1.0, np.inf, np.nan, -1.0, 5e-324, 1e-310]])
+    for x in xs:
+        y1, y2 = rng.uniform(-3, 3), rng.choice([0.0, 0.5, 2.0, np.inf, -np.inf, np.nan, 7.3])
+        r1, r2 = C.c_double(), C.c_double()
+        L.roger_pow2_host(float(x), float(y1), float(y2), C.byref(r1), C.byref(r2))
+        for got, y in ((r1.value, y1), (r2.value, y2)):
+            want = L.roger_pow_host(float(x), float(y))
+            assert got == want or (math.isnan(got) and math.isnan(want)), (x, y, got, want)
