@@ -192,7 +192,16 @@ ROGER_POW_FN double roger_pow_from_log(double hi, double lo, double y, const rog
     return ovf ? roger_pow_asd(0x7ff0000000000000ULL) : (unf ? 0.0 : res);
 }
 
-ROGER_POW_FN double roger_pow(double x, double y, const roger_pow_tables tabs)
+/* true when x is a positive normal number (the domain of roger_pow_core) */
+ROGER_POW_FN int roger_pow_is_pos_normal(uint64_t ix) { return ((ix >> 52) - 1ULL) < 0x7feULL; }
+
+/* everything outside "positive normal base, finite exponent": zeros, subnormals, infinities, NaNs, negative bases */
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+static
+#endif
+double roger_pow_special(double x, double y, const roger_pow_tables tabs)
 {
     uint64_t ix = roger_pow_asu(x);
     const uint64_t iy = roger_pow_asu(y);
@@ -211,8 +220,16 @@ ROGER_POW_FN double roger_pow(double x, double y, const roger_pow_tables tabs)
     return roger_pow_core(ix, y, tabs);
 }
 
-/* true when x is a positive normal number (the domain of roger_pow_core) */
-ROGER_POW_FN int roger_pow_is_pos_normal(uint64_t ix) { return ((ix >> 52) - 1ULL) < 0x7feULL; }
+/* The common case -- positive normal base, finite exponent -- goes straight to the core (which returns exactly 1 for
+ * x == 1 or y == 0); everything else takes the out-of-line special-case path.  Same bits as evaluating the special-case
+ * chain first. */
+ROGER_POW_FN double roger_pow(double x, double y, const roger_pow_tables tabs)
+{
+    const uint64_t ix = roger_pow_asu(x);
+    const uint64_t iy = roger_pow_asu(y);
+    if (roger_pow_is_pos_normal(ix) && ((iy >> 52) & 0x7ffULL) != 0x7ffULL) return roger_pow_core(ix, y, tabs);
+    return roger_pow_special(x, y, tabs);
+}
 
 /* x^y1 and x^y2 with the logarithm of the common base evaluated once; each result has the bits roger_pow(x, y) returns */
 ROGER_POW_FN void roger_pow2(double x, double y1, double y2, const roger_pow_tables tabs, double *r1, double *r2)
