@@ -197,7 +197,7 @@ ROGER_POW_FN int roger_pow_is_pos_normal(uint64_t ix) { return ((ix >> 52) - 1UL
 
 /* everything outside "positive normal base, finite exponent": zeros, subnormals, infinities, NaNs, negative bases */
 #if defined(__CUDACC__)
-__host__ __device__ __noinline__
+static __host__ __device__ __noinline__
 #else
 static
 #endif
