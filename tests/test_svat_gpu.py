@@ -117,3 +117,56 @@ def test_day_blocked_stepping_equals_single_steps(lateral, doy, ndays):
     assert launches[1] >= total
     if doy == 121:
         assert launches[0] < launches[1] / 3  # the blocked path really ran
+
+
+@pytest.mark.parametrize("lateral,doy,dist", [(False, 45, True), (True, 121, False)])
+def test_drop_in_driver_on_the_cuda_engine(lateral, doy, dist):
+    """roger_b200.integration.CudaStepDriver driving the CUDA engine through a setup object with the
+    reference's conventions (ghost cells, tau / taum1 levels, hooks; tests/mini_setup.py) against the plain host-side
+    driver on the oracle: every variable the driver writes back, both time levels, and the scalars -- across a month
+    change (land-use parameter refresh) and, for doy 45, snow."""
+    from oracle.engine import OracleSvatEngine, lib
+    from roger_b200 import abi, synth
+    from roger_b200.integration import CudaStepDriver
+    from roger_b200.svat import SvatModel
+    from tests.mini_setup import TWO_LEVEL, MiniSvatSetup
+
+    shape = (8, 6)
+    nsteps = 220
+    forcing = synth.mixed_forcing(60, seed=42, start_doy=doy)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, lateral=lateral, lu_choices=(10, 11, 12, 8, 5, 9), masked_fraction=0.1)
+    weights = synth.distributed_weights(shape, seed=44) if dist else None
+    lib().roger_oracle_set_pow(1)
+    try:
+        setup = MiniSvatSetup(shape, forcing, prim, th_rz, th_ss, lateral=lateral, weights=weights)
+        setup.setup()
+        driver = CudaStepDriver(setup, engine_cls=_engine())
+        ref = SvatModel(OracleSvatEngine, shape, forcing, prim, th_rz, th_ss, lateral=lateral, weights=weights)
+        ref.setup()
+        vs = setup.state.variables
+        kinds = dict(zip(abi.FIELD_NAMES, abi.FIELD_KINDS))
+        months = set()
+        for step in range(nsteps):
+            prev = {n: np.array(getattr(vs, n))[2:-2, 2:-2, 1].copy() for n in ("S", "theta_rz", "swe")}
+            sc = driver.step()
+            rs = ref.step(True)
+            months.add(int(vs.month[1]))
+            for k in ("time", "itt", "dt_secs", "itt_day", "event_id_counter", "time_event0", "dt"):
+                assert float(np.asarray(getattr(vs, k))) == float(getattr(rs, k)), (step, k)
+            assert [int(v) for v in vs.event_id] == [int(rs.event_id[0]), int(rs.event_id[1])]
+            if step % 10 == 0 or step == nsteps - 1:
+                for n in abi.FIELD_NAMES:
+                    if kinds[n] == "P" and n != "ks_ss" or n == "maskRiverLake":
+                        continue
+                    a = np.asarray(getattr(vs, n))
+                    want = ref.get(n).reshape(shape)
+                    got = a[2:-2, 2:-2, 1] if a.ndim == 3 else a[2:-2, 2:-2]
+                    assert util.same_bits(got, want), (step, n)
+                    if a.ndim == 3 and n in TWO_LEVEL:
+                        assert util.same_bits(a[2:-2, 2:-2, 0], want), (step, n, "taum1")
+                    assert np.all(a[:2] == 0) and np.all(a[-2:] == 0)  # ghost cells untouched
+            for n, before in prev.items():
+                pass
+        assert len(months) >= 2  # the monthly parameter refresh was exercised
+    finally:
+        lib().roger_oracle_set_pow(0)
