@@ -187,3 +187,99 @@ class CudaStepDriver:
         start = int(np.asarray(vs.time))
         while int(np.asarray(vs.time)) - start < runlen:
             self.step()
+
+
+class CudaTransportDriver:
+    """Drop-in for the offline oxygen-18 transport branch of `RogerSetup.step` (roger/roger.py:467-483): the setup's own
+    hooks feed `vs.inf_mat_rz, vs.transp, ... vs.C_in` for the day, the engine runs
+    `transport.svat_transport_model_deterministic` (core/transport.py:948-991) for every cell, and the results are written
+    back into `vs` with both time levels as `after_substep_iso` (:3421-3520) leaves them.
+
+        model = MyOxygen18Setup(); model.setup(); model.warmup()
+        driver = CudaTransportDriver(model)
+        for day in range(ndays): driver.step()
+
+    `pull_state=False` leaves the four age-ranked arrays on the device (they are (cells x ages) each); the per-cell
+    concentrations and delta values are always written back.
+    """
+
+    _FORCING = ("inf_mat_rz", "inf_pf_rz", "inf_pf_ss", "evap_soil", "transp", "q_rz", "q_ss", "cpr_rz", "C_in")
+
+    def __init__(self, setup, engine_cls=None, engine_kwargs=None, pull_state=True, store_tt=True):
+        from . import sas
+
+        if engine_cls is None:
+            from .sas_engine import CudaSasEngine as engine_cls  # no fallback
+        self.sas = sas
+        self.setup = setup
+        self.state = setup.state
+        vs, st = self.state.variables, self.state.settings
+        if not getattr(st, "enable_offline_transport", False) or not getattr(st, "enable_oxygen18", False):
+            raise ValueError("CudaTransportDriver drives the offline oxygen-18 transport model")
+        if getattr(st, "sas_solver", None) != "deterministic":
+            raise NotImplementedError("only sas_solver = 'deterministic' runs on the device (DESIGN.md section 7)")
+        self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
+        self.C = self.nx * self.ny
+        self.pull_state = bool(pull_state)
+        self.stats = bool(getattr(st, "enable_age_statistics", False))
+        s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(st.VSMOW_conc18O), float(st.d18O_min), float(st.d18O_max),
+                            int(bool(store_tt)), int(self.stats))
+        self.settings = s
+        self.engine = engine_cls(self.C, s, **(engine_kwargs or {}))
+        tau = int(vs.tau)
+        mask = np.asarray(vs.maskCatch)[2:-2, 2:-2].reshape(-1).astype(np.float64)
+        block = np.stack([np.asarray(getattr(vs, "sas_params_" + p))[2:-2, 2:-2, :].reshape(self.C, 8) for p in sas.PROCESSES])
+        self.engine.set_parameters(mask, block.astype(np.float64))
+        for name in sas.STATE:
+            self.engine.upload_state(name, np.asarray(getattr(vs, name))[2:-2, 2:-2, tau, :].reshape(self.C, self.A))
+        if self.stats:
+            self.engine.set_balance_reference(np.asarray(vs.C_s)[2:-2, 2:-2, int(vs.taum1)].reshape(-1))
+
+    def _put(self, name, values, level=None):
+        vs = self.state.variables
+        cur = np.array(getattr(vs, name))
+        v = np.asarray(values, dtype=cur.dtype)
+        if level is None:
+            cur[2:-2, 2:-2, ...] = v.reshape(cur[2:-2, 2:-2, ...].shape)
+        else:
+            for lv in level:
+                cur[2:-2, 2:-2, lv, ...] = v.reshape(cur[2:-2, 2:-2, lv, ...].shape)
+        setattr(vs, name, cur)
+
+    def step(self):
+        setup, state, sas = self.setup, self.state, self.sas
+        vs = state.variables
+        setup._ensure_setup_done()
+        with vs.unlock():
+            vs.itt = vs.itt + 1
+            vs.time = vs.time + vs.dt_secs
+        setup.read_data(state)
+        setup.set_boundary_conditions(state)
+        setup.set_forcing(state)
+        setup.set_parameters(state)
+        f = np.stack([np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64) for n in self._FORCING])
+        self.engine.step(f)
+        out = self.engine.download_outputs()
+        tau, taum1 = int(vs.tau), int(vs.taum1)
+        active = {n for n, m in state.var_meta.items() if m.active}
+        with vs.unlock():
+            for k, name in enumerate(sas.OUTPUTS):
+                if name not in active:
+                    continue
+                if np.asarray(getattr(vs, name)).ndim == 3:  # C_rz, C_ss, C_s, C_iso_*: both levels after after_substep_iso
+                    self._put(name, out[k], level=(tau, taum1))
+                else:
+                    self._put(name, out[k])
+            if self.pull_state:
+                for name in sas.STATE:
+                    self._put(name, self.engine.download_state(name), level=(tau, taum1))
+            if self.settings.store_tt:
+                for p in sas.PROCESSES:
+                    if "tt_" + p in active:
+                        self._put("tt_" + p, self.engine.download_tt(p))
+            if self.stats:
+                st = self.engine.download_statistics()
+                for k, name in enumerate(sas.STATISTICS):
+                    if name in active:
+                        self._put(name, st[k])
+        setup.after_timestep(state)

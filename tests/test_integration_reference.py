@@ -74,3 +74,38 @@ def test_driver_refuses_offline_transport_and_has_no_fallback():
         d = CudaStepDriver(m)  # product default engine
         with pytest.raises(RogerCudaError, match="no CUDA device"):
             d.step()
+
+
+@pytest.mark.parametrize("name,ndays,tol", [("sas_families", 12, 1e-10), ("sas_power", 5, 1e-10)])
+def test_transport_driver_reproduces_reference_step(name, ndays, tol):
+    """The offline oxygen-18 branch: an unmodified RogerSetup subclass of the reference stepped by `RogerSetup.step` and by
+    `CudaTransportDriver.step` (oracle engine plugged in).  The reference runs on NumPy's default SVML `power` here, so
+    the power-law case is compared over the days before its first rounding-decided clamp."""
+    import make_sas_golden as mg
+    import ref_harness as rh
+    from oracle.engine import OracleSasEngine, lib
+    from roger_b200 import sas
+    from roger_b200.integration import CudaTransportDriver
+    from tests.util_sas import rel_err
+
+    lib().roger_oracle_set_pow(0)
+    case = mg.build(name)
+    Setup = rh.make_o18_setup(case)
+    ref = Setup()
+    ref.setup()
+    ref.warmup()
+    dut = Setup()
+    dut.setup()
+    dut.warmup()
+    driver = CudaTransportDriver(dut, engine_cls=OracleSasEngine)
+    a, b = ref.state.variables, dut.state.variables
+    names = list(sas.STATE) + ["tt_" + p for p in sas.PROCESSES] + [n for n in sas.OUTPUTS if hasattr(a, n)]
+    for day in range(ndays):
+        ref.step(ref.state)
+        driver.step()
+        assert int(a.itt) == int(b.itt) and int(a.time) == int(b.time)
+        for n in names:
+            x, y = np.asarray(getattr(a, n))[2:-2, 2:-2], np.asarray(getattr(b, n))[2:-2, 2:-2]
+            assert x.shape == y.shape
+            lim = 1e-9 if n.startswith("C_iso") else tol  # delta values amplify concentration rounding ~1e3
+            assert rel_err(y, x) < lim, (day, n)
