@@ -105,8 +105,13 @@ class CudaSasEngine:
         _check(self.lib, self.lib.roger_sas_step_device(self.h, int(forcing_ptr)))
         self._timing()
 
-    def download_outputs(self):
-        out = np.empty((len(sas.OUTPUTS), self.n))
+    def download_outputs(self, out=None):
+        """(22, n_cells) result planes of the last step; pass a preallocated (ideally page-locked) array to avoid the
+        staging copy of pageable memory"""
+        if out is None:
+            out = np.empty((len(sas.OUTPUTS), self.n))
+        elif out.shape != (len(sas.OUTPUTS), self.n) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("download_outputs: contiguous float64 array of shape (22, n_cells) expected")
         _check(self.lib, self.lib.roger_sas_download_outputs(self.h, self._dp(out)))
         return out
 
