@@ -220,8 +220,8 @@ __device__ __forceinline__ double omega(const Family& f, const SasParams& P, con
 
 // ---- streaming NumPy pairwise sums -------------------------------------------------------------------------
 // Bins are visited once, in order.  load(j, L) reads the NL inputs of bin j (and may record addresses); work(j, L, v)
-// computes the bin, performs its stores and fills the NS summands v.  Within a chunk of 8 bins all loads are issued
-// before the first dependent instruction, so eight bins' worth of memory latency overlap.
+// computes the bin, performs its stores and fills the NS summands v.  Within a group of 4 bins all loads are issued
+// before the first dependent instruction, so four bins' worth of memory latency overlap.
 template <int NS, int NL, class Load, class Work>
 __device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Load load, Work work, double* out) {
     double st[NS][8];
@@ -249,15 +249,18 @@ __device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Loa
                 for (int q = 0; q < 8; q++) r[k][q] = -0.0;  // x + (-0.0) == x: the first chunk initialises the lanes
             const int len8 = len - (len % 8);
             for (int i = 0; i < len8; i += 8, j += 8) {
-                double L[8][NL];
 #pragma unroll
-                for (int q = 0; q < 8; q++) load(j + q, L[q]);
+                for (int g = 0; g < 8; g += 4) {  // four bins' loads in flight at a time (eight would not fit the register file)
+                    double L[4][NL];
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    double v[NS];
-                    work(j + q, L[q], v);
+                    for (int q = 0; q < 4; q++) load(j + g + q, L[q]);
 #pragma unroll
-                    for (int k = 0; k < NS; k++) r[k][q] += v[k];
+                    for (int q = 0; q < 4; q++) {
+                        double v[NS];
+                        work(j + g + q, L[q], v);
+#pragma unroll
+                        for (int k = 0; k < NS; k++) r[k][g + q] += v[k];
+                    }
                 }
             }
 #pragma unroll
@@ -433,6 +436,32 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
     }
 }
 
+// The travel-time increment of ONE bin in a power-law sub-step: the arithmetic of pow_pass_bins<> without the StorAge
+// bookkeeping (the last sub-step's san / max are never used).  Keep in step with pow_pass_bins<>.
+__device__ __forceinline__ double pow_bin_tti(const PowPassConst& k, PowPassCarry& c, const roger_pow_tables tabs, double x) {
+    double om;
+    c.acc_in += x;
+    if (x == 0) {
+        om = c.om_prev;
+    } else {
+        const double SA = c.acc_in;
+        const bool in = (SA > 0) && (SA <= k.S);
+        const bool easy = in && (SA >= 0x1p-500);
+        const double xr = div_by(SA, k.S, k.rS);
+        double p = roger_pow_core(easy ? roger_pow_asu(xr) : 0x3fe0000000000000ULL, k.y, tabs);
+        if (in && !easy) p = roger_pow(SA / k.S, k.y, tabs);
+        om = (SA > 0) ? ((SA <= k.S) ? p : 1.) : 0.;
+    }
+    const double d = om - c.om_prev;
+    c.om_prev = om;
+    double tti = (d >= 0) ? d : 0;
+    const double q = k.flux * tti * k.h;
+    const double ttqi = (q > x) ? x : q;
+    tti = (ttqi == 0 || div_range_ok(ttqi)) ? div_by(ttqi, k.fh, k.rfh) : ttqi / k.fh;
+    c.acc_t += tti;
+    return tti;
+}
+
 template <bool FIRST>
 __device__ __noinline__ void pow_pass_tail(const PowPassConst& k, PowPassCarry& c, const roger_pow_tables tabs, double* __restrict__ san_o,
                                            double* __restrict__ TTn_o, int64_t C, int n) {
@@ -496,6 +525,9 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
     const int64_t C = P.C;
     const double h = 1.0 / P.substeps;
     const bool active = (flux * h > 0);  // otherwise every sub-step leaves san and TTn untouched (tti = 0)
+    bool fused = false, fused_first = false;
+    PowPassConst fk{};
+    PowPassCarry fc{0, 0, 0, 0.0, 0.0, false};
 
     if (active) {
         // cumulative StorAge of the layer (transport.py:343-359) -> S = max(SA); the layer's StorAge is copied into the
@@ -530,7 +562,16 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
         for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
             family_prepare(fam, mx.get());
             const bool first = (s == 0);
-            if (fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh)) {
+            const bool pow_fast = fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh);
+            if (pow_fast && s == P.substeps - 1) {
+                // The last sub-step's StorAge is never read again and its contribution to TTn is consumed bin by bin by the
+                // aggregation below: it runs inside that pass (no san / TTn stores, no TTn re-read).
+                fused = true;
+                fused_first = first;
+                fk = PowPassConst{fam.S, 1.0 / fam.S, fam.sp[1], flux, h, fh, 1.0 / fh};
+                break;
+            }
+            if (pow_fast) {
                 const double S_next = first ? substep_pass_pow<U, true>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn)
                                             : substep_pass_pow<U, false>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn);
                 mx.init(S_next);
@@ -583,17 +624,24 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
         for (int k = 0; k < 5; k++) trk[k].init(pcts[k]);
     }
     bool first_bin = true;
-    stream_sums<NS, 5>(cx.plan,
+    const roger_pow_tables tabs = cx.tabs;
+    stream_sums<NS, 6>(cx.plan,
         [&](int j, double* L) {
             const int64_t o = cx.ring(j);
-            L[0] = active ? TTn[cx.lin(j)] : 0.;
+            L[0] = (active && !(fused && fused_first)) ? TTn[cx.lin(j)] : 0.;
             L[1] = sa[o];
             L[2] = msa[o];
             if (dst >= 0) { L[3] = sa_d[o]; L[4] = msa_d[o]; }
+            if (fused) L[5] = san[cx.lin(j)];
         },
         [&](int j, const double* L, double* v) {
             const int64_t o = cx.ring(j);
-            const double cur = L[0] / nsub;
+            double ttn = L[0];
+            if (fused) {  // TTn[j + 1] of the last sub-step, accumulated on the fly
+                pow_bin_tti(fk, fc, tabs, L[5]);
+                ttn = (fused_first ? 0.0 : L[0]) + fc.acc_t;
+            }
+            const double cur = ttn / nsub;
             double t = cur - prev;
             prev = cur;
             const double s_j = L[1];
