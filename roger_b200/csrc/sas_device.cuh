@@ -22,6 +22,10 @@
 #include "roger_pow.h"
 #include "../../include/roger_b200_sas.h"
 
+#ifndef ROGER_SAS_LOADGROUP
+#define ROGER_SAS_LOADGROUP 2
+#endif
+
 namespace rsas {
 
 constexpr int kMaxLeaves = 96;
@@ -250,12 +254,12 @@ __device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Loa
             const int len8 = len - (len % 8);
             for (int i = 0; i < len8; i += 8, j += 8) {
 #pragma unroll
-                for (int g = 0; g < 8; g += 4) {  // four bins' loads in flight at a time (eight would not fit the register file)
-                    double L[4][NL];
+                for (int g = 0; g < 8; g += ROGER_SAS_LOADGROUP) {  // this many bins' loads in flight at a time
+                    double L[ROGER_SAS_LOADGROUP][NL];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) load(j + g + q, L[q]);
+                    for (int q = 0; q < ROGER_SAS_LOADGROUP; q++) load(j + g + q, L[q]);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
+                    for (int q = 0; q < ROGER_SAS_LOADGROUP; q++) {
                         double v[NS];
                         work(j + g + q, L[q], v);
 #pragma unroll
@@ -336,6 +340,9 @@ struct CellCtx {
 
 #ifndef ROGER_SAS_UNROLL
 #define ROGER_SAS_UNROLL 2
+#endif
+#ifndef ROGER_SAS_FUSE_LAST
+#define ROGER_SAS_FUSE_LAST 0  // measured slower (2.5e6 vs 2.9e6 cell-days/s): the fused pass loses the two-bin interleave of the pow evaluations
 #endif
 
 // One sub-step of the deterministic solver for `n` consecutive bins starting at j0 (transport.py:388-470).  The n values
@@ -563,7 +570,7 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
             family_prepare(fam, mx.get());
             const bool first = (s == 0);
             const bool pow_fast = fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh);
-            if (pow_fast && s == P.substeps - 1) {
+            if (ROGER_SAS_FUSE_LAST && pow_fast && s == P.substeps - 1) {
                 // The last sub-step's StorAge is never read again and its contribution to TTn is consumed bin by bin by the
                 // aggregation below: it runs inside that pass (no san / TTn stores, no TTn re-read).
                 fused = true;
