@@ -69,7 +69,13 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []  # (arrival time, text)
+        self.t_mark = 0.0
+
+    def mark(self):
+        """start of the timed region: only samples from here on are reported (earlier ones are the fallback for regions
+        shorter than the sampling period)"""
+        self.t_mark = time.time()
 
     def start(self):
         try:
@@ -83,7 +89,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -95,7 +101,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        timed = [ln for t, ln in self.lines if t >= self.t_mark]
+        if not timed:
+            timed = [ln for _, ln in self.lines[-3:]]
+        for ln in timed:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -142,7 +151,7 @@ def run_reference(args):
             eng.step(model.day_forcing())
         el = time.perf_counter() - t0
         v = cells * args.steps / el
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "cell-timesteps/s", "value": v, "unit": "cell-timesteps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -151,7 +160,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port",
                              "sample": f"{cells} cells x {args.ages} age bins of the same workload, {args.steps} daily steps, OpenMP over cells"},
             "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        })
         return
     side = args.ref_side
     shape = (side, side)
@@ -173,7 +182,7 @@ def run_reference(args):
                          "sample": f"{side}x{side} cells of the same workload, {args.steps} adaptive steps, OpenMP over cells"},
         "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_cuda(args):
@@ -191,7 +200,8 @@ def run_cuda(args):
     if args.workload == "sas":
         sampler = ClockSampler(local)
         sampler.start()
-        res = run_sas_cuda(args, local, world, rank, dist if world > 1 else None, args.steps, max(args.warmup, 1), args.sas_side, args.ages)
+        res = run_sas_cuda(args, local, world, rank, dist if world > 1 else None, args.steps, max(args.warmup, 1), args.sas_side, args.ages,
+                           sampler=sampler)
         clocks = sampler.stop()
         if rank == 0:
             line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": res["steps"],
@@ -200,7 +210,7 @@ def run_cuda(args):
                     "roofline": res["roofline"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks}
             if world == 1 and not args.no_cpu_baseline:
                 line["cpu_baseline"] = sas_cpu_baseline(args.ages, cells=args.ref_cells)
-            print(json.dumps(line))
+            emit(line)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -241,11 +251,12 @@ def run_cuda(args):
             left -= done
         return kinds
 
+    sampler = ClockSampler(local)
+    sampler.start()
     advance(args.warmup)
     ms_by_dt.clear()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     eng.kernel_ms = 0.0
     eng.launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,7 +342,7 @@ def run_cuda(args):
             line["cpu_baseline"] = cpu_baseline(args)
             if sas_res is not None:
                 line["sas"]["cpu_baseline"] = sas_cpu_baseline(args.ages, cells=args.ref_cells)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -398,7 +409,7 @@ class _NullEngine:
         pass
 
 
-def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages):
+def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages, sampler=None):
     """Returns the `sas` result dict (value / roofline / e2e) measured on this rank's GPU, max over ranks."""
     import torch
     from roger_b200 import sas
@@ -423,6 +434,8 @@ def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages):
     for d in range(warmup):
         eng.step_device(dev_days[d].data_ptr())
     barrier()
+    if sampler is not None:
+        sampler.mark()
     eng.kernel_ms = 0.0
     eng.launches = 0
     t0 = time.perf_counter()
@@ -504,7 +517,26 @@ def cpu_baseline(args):
             "sample": f"{side}x{side} cells of the same workload, {n} adaptive steps, OpenMP over cells"}
 
 
+def _claim_stdout():
+    """Libraries (NCCL's version banner, launch notices) write to file descriptor 1; the contract is ONE JSON line there.
+    Everything else is sent to stderr and the line is written to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    global _JSON_OUT
+    _JSON_OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=48)
