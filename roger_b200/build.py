@@ -7,7 +7,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.environ.get("ROGER_B200_LIB") or os.path.join(LIBDIR, "libroger_b200.so")
 SOURCES = ["svat_api.cu", "sas_api.cu"]
-HEADERS = ["svat_device.cuh", os.path.join("..", "..", "include", "roger_b200.h"),
+HEADERS = ["svat_device.cuh", "sas_device.cuh", "roger_pow.h", "roger_pow_tables.h", os.path.join("..", "..", "include", "roger_b200.h"),
            os.path.join("..", "..", "include", "roger_b200_fields.h"), os.path.join("..", "..", "include", "roger_b200_sas.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
