@@ -119,6 +119,13 @@ int roger_svat_run_day(roger_svat *h, int write_fluxes, int *n_steps);
 int roger_svat_run_steps(roger_svat *h, int write_fluxes, int max_steps, int *n_steps);
 /* switch the day-blocked launch off / on (default on) and bound the steps per launch (2..144) */
 int roger_svat_set_block_stepping(roger_svat *h, int enabled, int max_block);
+/* ---- RATE diagnostics on the device (roger/diagnostics/rate.py:72-91): the named planes are added into accumulator planes
+ *      after every step (sums over the output interval; the daily sums that drive the offline transport model,
+ *      test/make_data_for_svat_transport.py:279-300).  Accumulating a flux plane switches the steps to the
+ *      flux-storing kernels. */
+int roger_svat_set_rate_fields(roger_svat *h, const int *fields, int n);
+int roger_svat_download_rates(roger_svat *h, double *host, int reset);
+uint64_t roger_svat_rates_ptr(roger_svat *h);
 int roger_svat_synchronize(roger_svat *h);
 /* CUDA-event time (ms) spent in kernels of the most recent roger_svat_step / run_day call and the
  * number of kernel launches it made (bench.py roofline / gpu_launches). */

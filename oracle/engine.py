@@ -74,6 +74,18 @@ class OracleSvatEngine:
         p, t, e = self.forcing
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         self._fn(C.c_int64(self.n), dp(self.planes), dp(p), dp(t), dp(e), C.byref(self.scalars), C.byref(self.settings))
+        for k, name in enumerate(getattr(self, "_rate_names", ())):
+            self._rates[k] += self.planes[self.abi.FIELD_ID[name]]
+
+    def set_rate_fields(self, names):
+        self._rate_names = list(names)
+        self._rates = np.zeros((len(self._rate_names), self.n))
+
+    def download_rates(self, reset=True):
+        out = dict(zip(self._rate_names, self._rates.copy()))
+        if reset:
+            self._rates[:] = 0
+        return out
 
     def synchronize(self):
         pass

@@ -210,6 +210,13 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
     warp_or(flags, bits);
 }
 
+// RATE diagnostics (roger/diagnostics/rate.py:72-81): acc[k] += plane(field[k]) after every step, on the device
+__global__ void k_accumulate_rates(Planes pl, double* __restrict__ acc, const int* __restrict__ fields, int n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pl.C) return;
+    for (int k = 0; k < n; k++) acc[(size_t)k * pl.C + i] += pl.at(fields[k])[i];
+}
+
 // Several consecutive adaptive steps of every cell in ONE launch (uniform forcing, snow-free stretch of a day: the
 // host scheduler knows every step's dt / aggregates in advance, svat_api.cu plan_day_block).  A thread re-reads the
 // state it stored in the previous step: at 4 blocks x 128 cells x ~120 planes per SM the whole grid's resident working
@@ -300,6 +307,11 @@ struct roger_svat {
     // uniform forcing: the (uniform) value the prec / ta planes currently hold, tracked by the scheduler
     double u_cur_prec = 0, u_cur_ta = 0;
     bool u_cur_valid = false;
+    // RATE diagnostics accumulated on the device (roger_svat_set_rate_fields)
+    std::vector<int> rate_fields;
+    bool rates_need_flux = false;
+    double* d_rates = nullptr;
+    int* d_rate_fields = nullptr;
     // day-blocked stepping (run_block)
     int max_block = 144;
     bool block_stepping = true;
@@ -386,6 +398,7 @@ void roger_svat_destroy(roger_svat* h) {
     for (auto p : h->snap_free) cudaFree(p);
     for (auto p : h->snap_busy) cudaFree(p);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+    cudaFree(h->d_rates); cudaFree(h->d_rate_fields);
     cudaFree(h->d_plans); cudaFree(h->d_block_flags);
     if (h->h_plans) cudaFreeHost(h->h_plans);
     if (h->h_block_flags) cudaFreeHost(h->h_block_flags);
@@ -678,6 +691,7 @@ static int ensure_uniform_current(roger_svat* h) {  // the "keep" class reads pr
 static int step_impl(roger_svat* h, int write_fluxes) {
     if (!h->have_forcing) return fail(ROGER_EINVAL, "roger_svat_step: no forcing day set");
     CU(cudaSetDevice(h->device));
+    if (h->rates_need_flux) write_fluxes = 1;  // flux rates are accumulated from the flux planes
     if (write_fluxes) { int r = ensure_flux_planes(h); if (r) return r; }
     const roger_svat_settings& st = h->st;
     roger_svat_scalars& sc = h->sc;
@@ -716,6 +730,11 @@ static int step_impl(roger_svat* h, int write_fluxes) {
 #undef LAUNCH
     CU(cudaGetLastError());
     launches++;
+    if (!h->rate_fields.empty()) {
+        k_accumulate_rates<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(pl, h->d_rates, h->d_rate_fields, (int)h->rate_fields.size());
+        CU(cudaGetLastError());
+        launches++;
+    }
     if (!h->ks_ss_synced) {  // subsoil.calc_ks (subsoil.py:6-20): ks_ss = ks from the end of the first step on
         CU(cudaMemcpyAsync(pl.at(RF_ks_ss), pl.at(RF_ks), sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToDevice, h->stream));
         h->ks_ss_synced = true;
@@ -826,7 +845,7 @@ int roger_svat_run_steps(roger_svat* h, int write_fluxes, int max_steps, int* n_
     int n = 0;
     do {
         int nb = 0;
-        if (!write_fluxes && h->block_stepping) {
+        if (!write_fluxes && h->block_stepping && h->rate_fields.empty()) {
             int r = run_block(h, max_steps - n, &nb);
             if (r) return r;
         }
@@ -844,6 +863,43 @@ int roger_svat_run_steps(roger_svat* h, int write_fluxes, int max_steps, int* n_
 int roger_svat_run_day(roger_svat* h, int write_fluxes, int* n_steps) {
     return roger_svat_run_steps(h, write_fluxes, 144, n_steps);
 }
+
+// RATE diagnostics on the device: after every step the named planes are added into accumulator planes.
+int roger_svat_set_rate_fields(roger_svat* h, const int* fields, int n) {
+    if (!h || n < 0 || n > 64 || (n > 0 && !fields)) return fail(ROGER_EINVAL, "roger_svat_set_rate_fields: bad argument");
+    CU(cudaSetDevice(h->device));
+    for (int k = 0; k < n; k++)
+        if (fields[k] < 0 || fields[k] >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_set_rate_fields: bad field id");
+    cudaFree(h->d_rates); h->d_rates = nullptr;
+    cudaFree(h->d_rate_fields); h->d_rate_fields = nullptr;
+    h->rate_fields.assign(fields, fields + n);
+    h->rates_need_flux = false;
+    for (int f : h->rate_fields) h->rates_need_flux = h->rates_need_flux || kind_is_F(f);
+    if (n == 0) return 0;
+    if (h->rates_need_flux) { int r = ensure_flux_planes(h); if (r) return r; }
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)h->C;
+    CU(cudaMalloc(&h->d_rates, bytes));
+    CU(cudaMemsetAsync(h->d_rates, 0, bytes, h->stream));
+    CU(cudaMalloc(&h->d_rate_fields, sizeof(int) * n));
+    CU(cudaMemcpyAsync(h->d_rate_fields, h->rate_fields.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// the accumulated planes (n_fields x n_cells doubles, in the order given to roger_svat_set_rate_fields); reset != 0 zeroes
+// them afterwards (start of the next output interval, roger/diagnostics/rate.py:83-91)
+int roger_svat_download_rates(roger_svat* h, double* host, int reset) {
+    if (!h || !host) return fail(ROGER_EINVAL, "roger_svat_download_rates: bad argument");
+    if (h->rate_fields.empty()) return fail(ROGER_EINVAL, "roger_svat_download_rates: no rate fields set");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * h->rate_fields.size() * (size_t)h->C;
+    CU(cudaMemcpyAsync(host, h->d_rates, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CU(cudaMemsetAsync(h->d_rates, 0, bytes, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+uint64_t roger_svat_rates_ptr(roger_svat* h) { return h ? (uint64_t)(uintptr_t)h->d_rates : 0; }
 
 int roger_svat_set_block_stepping(roger_svat* h, int enabled, int max_block) {
     if (!h) return fail(ROGER_EINVAL, "roger_svat_set_block_stepping: null handle");

@@ -54,6 +54,10 @@ def load_library():
     lib.roger_svat_run_day.argtypes = [hp, C.c_int, C.POINTER(C.c_int)]
     lib.roger_svat_run_steps.argtypes = [hp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.roger_svat_set_block_stepping.argtypes = [hp, C.c_int, C.c_int]
+    lib.roger_svat_set_rate_fields.argtypes = [hp, C.POINTER(C.c_int), C.c_int]
+    lib.roger_svat_download_rates.argtypes = [hp, dp, C.c_int]
+    lib.roger_svat_rates_ptr.argtypes = [hp]
+    lib.roger_svat_rates_ptr.restype = C.c_uint64
     lib.roger_svat_synchronize.argtypes = [hp]
     lib.roger_svat_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
     lib.roger_svat_set_flag_reducer.argtypes = [hp, FLAG_REDUCE_FN, C.c_void_p]
@@ -174,6 +178,17 @@ class CudaSvatEngine:
         _check(self.lib, self.lib.roger_svat_run_steps(self.h, int(bool(write_fluxes)), int(max_steps), C.byref(n)))
         self._timing()
         return n.value
+
+    def set_rate_fields(self, names):
+        """RATE diagnostics: sum the named planes over the steps until the next download_rates(reset=True)."""
+        self._rate_names = list(names)
+        ids = (C.c_int * len(self._rate_names))(*[abi.FIELD_ID[n] for n in self._rate_names])
+        _check(self.lib, self.lib.roger_svat_set_rate_fields(self.h, ids, len(self._rate_names)))
+
+    def download_rates(self, reset=True):
+        out = np.empty((len(self._rate_names), self.n))
+        _check(self.lib, self.lib.roger_svat_download_rates(self.h, self._dp(out), int(bool(reset))))
+        return dict(zip(self._rate_names, out))
 
     def set_block_stepping(self, enabled, max_block=0):
         _check(self.lib, self.lib.roger_svat_set_block_stepping(self.h, int(bool(enabled)), int(max_block)))

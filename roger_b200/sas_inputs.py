@@ -17,19 +17,23 @@ def daily_fluxes_from_svat(model, ndays):
     for k, f in STATES.items():
         out[k][:, 0] = model.get(f)
     day = 1
-    acc = {k: np.zeros(C) for k in SUMS}
+    # RATE diagnostics of the engine: the flux planes are summed over the day's steps where the state lives (on the device
+    # for the CUDA engine); one read-back per day
+    names = sorted({f for fields in SUMS.values() for f in fields})
+    model.engine.set_rate_fields(names)
     while day <= ndays:
         sc = model.step(write_fluxes=True)
-        for k, fields in SUMS.items():
-            for f in fields:
-                acc[k] += model.get(f)
         if sc.time % 86400 == 0:
-            for k in SUMS:
-                out[k][:, day] = acc[k]
-                acc[k][:] = 0
+            rates = model.engine.download_rates(reset=True)
+            for k, fields in SUMS.items():
+                acc = np.zeros(C)
+                for f in fields:
+                    acc += rates[f]
+                out[k][:, day] = acc
             for k, f in STATES.items():
                 out[k][:, day] = model.get(f)
             day += 1
+    model.engine.set_rate_fields([])
     for k in ("S_pwp_rz", "S_pwp_ss"):
         out[k] = model.get(k)
     return out

@@ -170,3 +170,27 @@ def test_drop_in_driver_on_the_cuda_engine(lateral, doy, dist):
         assert len(months) >= 2  # the monthly parameter refresh was exercised
     finally:
         lib().roger_oracle_set_pow(0)
+
+
+def test_rate_diagnostics_accumulated_on_the_device():
+    """RATE accumulators (roger/diagnostics/rate.py): daily sums of flux planes built on the device equal the sums the oracle
+    builds step by step -- the daily hydrologic forcing of the offline transport model."""
+    from oracle.engine import OracleSvatEngine, lib
+    from roger_b200 import sas_inputs, synth
+    from roger_b200.svat import SvatModel
+
+    shape = (16, 12)
+    forcing = synth.mixed_forcing(8, seed=42, start_doy=121)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43)
+    lib().roger_oracle_set_pow(1)
+    try:
+        daily = []
+        for e in (_engine(), OracleSvatEngine):
+            m = SvatModel(e, shape, forcing, prim, th_rz, th_ss)
+            m.setup()
+            daily.append(sas_inputs.daily_fluxes_from_svat(m, 5))
+        for k in daily[0]:
+            assert util.same_bits(daily[0][k], daily[1][k]), k
+        assert daily[0]["TRANSP"][:, 1:].sum() > 0 and daily[0]["PREC"][:, 1:].sum() > 0
+    finally:
+        lib().roger_oracle_set_pow(0)
