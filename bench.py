@@ -483,7 +483,7 @@ def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages, samp
     }
 
 
-def sas_cpu_baseline(ages, cells=192, days=2):
+def sas_cpu_baseline(ages, cells=8192, days=4):
     from oracle.engine import OracleSasEngine, OracleSvatEngine
     from roger_b200 import sas
 
@@ -546,10 +546,10 @@ def main():
     ap.add_argument("--sas-side", type=int, default=1024, help="SAS transport grid side per GPU (configs[2]: 1024)")
     ap.add_argument("--ages", type=int, default=1500, help="age bins of the SAS transport (BASELINE: ~1500)")
     ap.add_argument("--sas-steps", type=int, default=4, help="timed daily steps of the secondary SAS measurement")
-    ap.add_argument("--ref-cells", type=int, default=2048, help="cells of the CPU sample of the SAS workload")
+    ap.add_argument("--ref-cells", type=int, default=8192, help="cells of the CPU sample of the SAS workload")
     ap.add_argument("--no-sas", action="store_true", help="skip the secondary SVAT + oxygen-18 SAS measurement")
     ap.add_argument("--side", type=int, default=4096)
-    ap.add_argument("--ref-side", type=int, default=384)
+    ap.add_argument("--ref-side", type=int, default=768, help="grid side of the CPU sample of the SVAT / oneD workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -141,6 +141,22 @@ def _random_case(C_, A, ndays, seed, families=False):
     return d, spec
 
 
+@pytest.mark.parametrize("C_,A,ndays,substeps", [(1, 2, 6, 6), (5, 3, 6, 1), (3, 8, 5, 6), (7, 9, 5, 2), (2, 129, 4, 6), (33, 257, 3, 3), (257, 16, 4, 6)])
+def test_edge_shapes(C_, A, ndays, substeps, oracle_roger_pow):
+    """smallest grids and age axes, sizes around the block / summation-tree boundaries (8, 128, 2 x 128 bins; one cell; one
+    more cell than a block), one to six sub-steps, a day without any flux, a fully masked grid"""
+    from roger_b200 import sas
+
+    daily, spec = _random_case(C_, A, ndays, seed=500 + A)
+    for k in ("INF_MAT_RZ", "INF_PF_RZ", "INF_PF_SS", "EVAP_SOIL", "TRANSP", "Q_RZ", "Q_SS", "CPR_RZ", "PREC"):
+        daily[k][:, 2] = 0.0  # a day on which nothing moves
+    mask = np.ones(C_) if A != 9 else np.zeros(C_)
+    models = [sas.SasModel(e, C_, A, daily, spec, store_tt=True, mask=mask, substeps=substeps, age_statistics=True) for e in (_cuda(), oracle_roger_pow)]
+    for m in models:
+        m.setup()
+    u.replay_pair(models[0], models[1], ndays, exact=True)
+
+
 @pytest.mark.parametrize("C_,A,ndays,families", [(700, 136, 12, False), (333, 77, 10, True), (64, 1000, 3, False), (40, 1500, 2, False)])
 def test_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, families, oracle_roger_pow):
     from roger_b200 import sas

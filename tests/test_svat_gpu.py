@@ -194,3 +194,28 @@ def test_rate_diagnostics_accumulated_on_the_device():
         assert daily[0]["TRANSP"][:, 1:].sum() > 0 and daily[0]["PREC"][:, 1:].sum() > 0
     finally:
         lib().roger_oracle_set_pow(0)
+
+
+@pytest.mark.parametrize("shape,masked", [((1, 1), 0.0), ((257, 1), 0.0), ((3, 5), 1.0), ((31, 9), 0.3)])
+def test_edge_grids_bit_for_bit(shape, masked):
+    """a single cell, one cell more than a thread block, a grid entirely outside the catchment (maskCatch = 0 everywhere),
+    a heavily masked grid; per-cell forcing with a snow period"""
+    from oracle.engine import OracleSvatEngine, lib
+    from roger_b200 import abi, synth
+    from roger_b200.svat import SvatModel
+
+    forcing = synth.mixed_forcing(30, seed=42, start_doy=50)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, lu_choices=(10, 11, 12, 8, 5), masked_fraction=masked)
+    weights = synth.distributed_weights(shape, seed=44)
+    lib().roger_oracle_set_pow(1)
+    try:
+        models = [SvatModel(e, shape, forcing, prim, th_rz, th_ss, weights=weights) for e in (_engine(), OracleSvatEngine)]
+        for m in models:
+            m.setup()
+        for step in range(60):
+            a, b = models[0].step(True), models[1].step(True)
+            assert (a.time, a.dt_secs, a.itt_day, a.event_id[1], a.time_event0) == (b.time, b.dt_secs, b.itt_day, b.event_id[1], b.time_event0), step
+        for n in abi.FIELD_NAMES:
+            assert util.same_bits(models[0].get(n), models[1].get(n)), n
+    finally:
+        lib().roger_oracle_set_pow(0)
