@@ -47,6 +47,8 @@ enum roger_sas_statistic {
     RSS_rt25_ss, RSS_rt50_ss, RSS_rt75_ss, RSS_rtavg_ss,
     RSS_rt10_s, RSS_rt25_s, RSS_rt50_s, RSS_rt75_s, RSS_rt90_s, RSS_rtavg_s,
     RSS_dS_num_error, RSS_dC_num_error,
+    RSS_sanity_ok, /* 1 / 0 per cell: water balance, solute balance and storage bounds of numerics.sanity_check (numerics.py:1051-1122);
+                      the reference's scalar result is the AND over all cells */
     RSS_COUNT
 };
 
@@ -90,6 +92,10 @@ int roger_sas_download_statistics(roger_sas *h, double *host);
 /* the previous step's storage concentration C_s per cell, which the solute balance error differences against
  * (vs.C_s[taum1]); set once after the initial state, then maintained by the steps.  n_cells doubles. */
 int roger_sas_set_balance_reference(roger_sas *h, const double *C_s_prev);
+/* storage bounds of the sanity check (vs.S_sat_rz, vs.S_sat_ss, vs.S_pwp_rz, vs.S_pwp_ss; n_cells doubles each) and its
+ * tolerances (settings.atol, settings.rtol).  Default: no upper bound, atol = rtol = 1e-2. */
+int roger_sas_set_sanity_bounds(roger_sas *h, const double *S_sat_rz, const double *S_sat_ss, const double *S_pwp_rz,
+                                const double *S_pwp_ss, double atol, double rtol);
 /* travel-time distribution of process p from the last step (needs settings.store_tt): n_cells*ages doubles */
 int roger_sas_download_tt(roger_sas *h, int process, double *host);
 /* out[i] = roger_pow(x[i], y[i]) -- or roger_exp(x[i]) when y is NULL -- evaluated by the device build of

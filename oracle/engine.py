@@ -130,6 +130,14 @@ class OracleSasEngine:
     def set_balance_reference(self, C_s_prev):
         self.balance_prev[:] = np.asarray(C_s_prev, dtype=np.float64).reshape(-1)
 
+    def set_sanity_bounds(self, S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss, atol=1e-2, rtol=1e-2):
+        self._bounds = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss)]
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        fn = lib().sas_oracle_set_sanity_bounds
+        fn.argtypes = [C.POINTER(C.c_double)] * 4 + [C.c_double, C.c_double]
+        fn.restype = None
+        fn(*[dp(a) for a in self._bounds], float(atol), float(rtol))
+
     def download_statistics(self):
         return self.stats.copy()
 

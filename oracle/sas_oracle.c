@@ -410,6 +410,17 @@ static void storage_age_statistics(int A, const double *sa, double m, const doub
     *avg = (np_sum(rt, A) > 0) ? np_sum(tmp, A) : NAN;
 }
 static double nan0(double x) { return isnan(x) ? 0 : x; }
+/* numpy.isclose(x, y, rtol, atol): (|x - y| <= atol + rtol * |y|) & isfinite(y) | (x == y) */
+static int np_isclose(double x, double y, double rtol, double atol) { return ((fabs(x - y) <= atol + rtol * fabs(y)) && isfinite(y)) || (x == y); }
+/* storage bounds and tolerances of numerics.sanity_check (set by the test / driver; default: unbounded, 1e-2) */
+static const double *g_bounds[4] = {NULL, NULL, NULL, NULL};
+static double g_atol = 1e-2, g_rtol = 1e-2;
+void sas_oracle_set_sanity_bounds(const double *S_sat_rz, const double *S_sat_ss, const double *S_pwp_rz, const double *S_pwp_ss, double atol,
+                                  double rtol)
+{
+    g_bounds[0] = S_sat_rz; g_bounds[1] = S_sat_ss; g_bounds[2] = S_pwp_rz; g_bounds[3] = S_pwp_ss;
+    g_atol = atol; g_rtol = rtol;
+}
 
 void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
                           const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
@@ -515,6 +526,23 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
                                                 (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
                                                  F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[0] * nan0(O(RSO_C_evap_soil)) -
                                                  w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss))) * 1.0);
+                    { /* numerics.py:1051-1122 */
+                        const double lhs1 = sum_s - sum_sa_s_m1;
+                        const double rhs1 = (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - w[0] - w[1] - w[2]) * 1.0;
+                        const double lhs2 = sum_s * O(RSO_C_s) - sum_sa_s_m1 * *bp_C;
+                        const double rhs2 = (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                                             F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[0] * nan0(O(RSO_C_evap_soil)) -
+                                             w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss))) * 1.0;
+                        const int c1 = (m != 0) ? np_isclose(lhs1, rhs1, g_rtol, g_atol) : 1;
+                        const int c2 = (m != 0) ? np_isclose(lhs2, rhs2, g_rtol, g_atol) : 1;
+                        const double sat_rz = g_bounds[0] ? g_bounds[0][i] : INFINITY, sat_ss = g_bounds[1] ? g_bounds[1][i] : INFINITY;
+                        const double pwp_rz = g_bounds[2] ? g_bounds[2][i] : 0.0, pwp_ss = g_bounds[3] ? g_bounds[3][i] : 0.0;
+                        const double sum_rz = np_sum(s_rz, A), sum_ss = np_sum(s_ss, A);
+                        const int b3 = (sum_s <= (sat_rz + sat_ss) - (pwp_rz + pwp_ss)) && (sum_s >= 0);
+                        const int b4 = (sum_rz <= sat_rz - pwp_rz) && (sum_rz >= 0);
+                        const int b5 = (sum_ss <= sat_ss - pwp_ss) && (sum_ss >= 0);
+                        ST(RSS_sanity_ok) = (c1 && c2 && b3 && b4 && b5) ? 1.0 : 0.0;
+                    }
                     *bp_C = O(RSO_C_s);
                 }
             }

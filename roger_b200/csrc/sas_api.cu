@@ -46,7 +46,7 @@ template <bool STATS>
 __global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
 k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
           const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out,
-          double* __restrict__ stats, double* __restrict__ C_s_prev) {
+          double* __restrict__ stats, double* __restrict__ C_s_prev, const double* __restrict__ bounds, double atol, double rtol) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
     __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
     for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
@@ -96,8 +96,8 @@ k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double*
     const double C_q_ss = a;
     withdrawal<STATS>(cx, 1, 0, F(RSF_cpr_rz), SP(RSP_cpr_rz), C, m, &a, &b, RSP_cpr_rz, nullptr);
     O(RSO_C_cpr_rz) = a; O(RSO_C_iso_cpr_rz) = b;
-    double sum_sa_s, C_s;
-    storage_concentrations(cx, m, out, C, &sum_sa_s, &C_s);
+    double sum_sa_s, C_s, sum_sa_rz, sum_sa_ss;
+    storage_concentrations(cx, m, out, C, &sum_sa_s, &C_s, &sum_sa_rz, &sum_sa_ss);
     if (STATS) {
         for (int k = 0; k < 5; k++) { ST(RSS_tt10_transp + k) = fs_transp.pct[k]; ST(RSS_tt10_q_ss + k) = fs_qss.pct[k]; }
         ST(RSS_ttavg_transp) = fs_transp.avg;
@@ -121,6 +121,24 @@ k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double*
                                     (F(RSF_inf_mat_rz) * nan0(C_inf_mat_rz) + F(RSF_inf_pf_rz) * nan0(C_inf_pf_rz) +
                                      F(RSF_inf_pf_ss) * nan0(C_inf_pf_ss) - fs_evap.wsum * nan0(C_evap) - fs_transp.wsum * nan0(C_transp) -
                                      fs_qss.wsum * nan0(C_q_ss)) * 1.0);
+        {   // numerics.sanity_check, oxygen-18 branch (numerics.py:1051-1122), per cell
+            auto isclose = [&](double x, double y) { return ((fabs(x - y) <= atol + rtol * fabs(y)) && isfinite(y)) || (x == y); };
+            const double lhs1 = sum_sa_s - sum_sa_s_m1;
+            const double rhs1 = (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - fs_evap.wsum - fs_transp.wsum - fs_qss.wsum) * 1.0;
+            const double lhs2 = sum_sa_s * C_s - sum_sa_s_m1 * Cp;
+            const double rhs2 = (F(RSF_inf_mat_rz) * nan0(C_inf_mat_rz) + F(RSF_inf_pf_rz) * nan0(C_inf_pf_rz) +
+                                 F(RSF_inf_pf_ss) * nan0(C_inf_pf_ss) - fs_evap.wsum * nan0(C_evap) - fs_transp.wsum * nan0(C_transp) -
+                                 fs_qss.wsum * nan0(C_q_ss)) * 1.0;
+            const bool c1 = (m != 0) ? isclose(lhs1, rhs1) : true;
+            const bool c2 = (m != 0) ? isclose(lhs2, rhs2) : true;
+            const double inf = __longlong_as_double(0x7ff0000000000000LL);
+            const double sat_rz = bounds ? bounds[i] : inf, sat_ss = bounds ? bounds[C + i] : inf;
+            const double pwp_rz = bounds ? bounds[2 * C + i] : 0.0, pwp_ss = bounds ? bounds[3 * C + i] : 0.0;
+            const bool b3 = (sum_sa_s <= (sat_rz + sat_ss) - (pwp_rz + pwp_ss)) && (sum_sa_s >= 0);
+            const bool b4 = (sum_sa_rz <= sat_rz - pwp_rz) && (sum_sa_rz >= 0);
+            const bool b5 = (sum_sa_ss <= sat_ss - pwp_ss) && (sum_sa_ss >= 0);
+            ST(RSS_sanity_ok) = (c1 && c2 && b3 && b4 && b5) ? 1.0 : 0.0;
+        }
         C_s_prev[i] = C_s;
     }
     ageing(cx);
@@ -242,6 +260,8 @@ struct roger_sas {
     double* d_out = nullptr;
     double* d_stats = nullptr;     // RSS_COUNT planes (settings.age_statistics)
     double* d_C_s_prev = nullptr;  // vs.C_s[taum1]
+    double* d_bounds = nullptr;    // S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss (sanity check), optional
+    double atol = 1e-2, rtol = 1e-2;
     double* d_mask = nullptr;
     double* d_params = nullptr;
     double* d_stage = nullptr;
@@ -365,7 +385,7 @@ void roger_sas_destroy(roger_sas* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto p : h->d_state) cudaFree(p);
-    cudaFree(h->d_stats); cudaFree(h->d_C_s_prev);
+    cudaFree(h->d_stats); cudaFree(h->d_C_s_prev); cudaFree(h->d_bounds);
     cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_params); cudaFree(h->d_stage); cudaFree(h->d_plan);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -439,10 +459,10 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     const int blocks = (int)((h->C + threads - 1) / threads);
     if (h->st.age_statistics)
         k_sas_day<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
-                                                           h->d_stats, h->d_C_s_prev);
+                                                           h->d_stats, h->d_C_s_prev, h->d_bounds, h->atol, h->rtol);
     else
         k_sas_day<false><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
-                                                            nullptr, nullptr);
+                                                            nullptr, nullptr, nullptr, 0.0, 0.0);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -490,6 +510,20 @@ int roger_sas_set_balance_reference(roger_sas* h, const double* C_s_prev) {
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(h->d_C_s_prev, C_s_prev, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int roger_sas_set_sanity_bounds(roger_sas* h, const double* S_sat_rz, const double* S_sat_ss, const double* S_pwp_rz, const double* S_pwp_ss,
+                                double atol, double rtol) {
+    if (!h || !S_sat_rz || !S_sat_ss || !S_pwp_rz || !S_pwp_ss) return fail(ROGER_EINVAL, "roger_sas_set_sanity_bounds: bad argument");
+    CU(cudaSetDevice(h->device));
+    const size_t plane = sizeof(double) * (size_t)h->C;
+    if (!h->d_bounds) CU(cudaMalloc(&h->d_bounds, 4 * plane));
+    const double* src[4] = {S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss};
+    for (int k = 0; k < 4; k++) CU(cudaMemcpyAsync(h->d_bounds + (size_t)k * h->C, src[k], plane, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->atol = atol;
+    h->rtol = rtol;
     return 0;
 }
 

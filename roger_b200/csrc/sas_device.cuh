@@ -766,7 +766,8 @@ __device__ __noinline__ void storage_age_statistics(const CellCtx& cx, int which
 
 // storage kernels (root_zone.py:189-215, subsoil.py:153-180, soil.py:1036-1092) followed by ageing
 // (transport.py:682-739) as a ring rotation
-__device__ __forceinline__ void storage_concentrations(const CellCtx& cx, double m, double* out, int64_t oC, double* sum_sa_s, double* C_s_out) {
+__device__ __forceinline__ void storage_concentrations(const CellCtx& cx, double m, double* out, int64_t oC, double* sum_sa_s, double* C_s_out,
+                                                       double* sum_sa_rz, double* sum_sa_ss) {
     const SasParams& P = cx.P;
     const int A = P.A;
     double* __restrict__ s_rz = cx.pl.sa[0];
@@ -810,6 +811,8 @@ __device__ __forceinline__ void storage_concentrations(const CellCtx& cx, double
     out[RSO_C_iso_ss * oC + i] = conc_to_delta(P, C_ss) * m;
     out[RSO_C_iso_s * oC + i] = conc_to_delta(P, C_s) * m;
     *sum_sa_s = sums[4];
+    *sum_sa_rz = sums[0];
+    *sum_sa_ss = sums[2];
     *C_s_out = C_s;
 }
 

@@ -19,7 +19,7 @@ STATISTICS = [
     "tt10_transp", "tt25_transp", "tt50_transp", "tt75_transp", "tt90_transp", "ttavg_transp",
     "tt10_q_ss", "tt25_q_ss", "tt50_q_ss", "tt75_q_ss", "tt90_q_ss", "ttavg_q_ss",
     "rt25_rz", "rt50_rz", "rt75_rz", "rtavg_rz", "rt25_ss", "rt50_ss", "rt75_ss", "rtavg_ss",
-    "rt10_s", "rt25_s", "rt50_s", "rt75_s", "rt90_s", "rtavg_s", "dS_num_error", "dC_num_error",
+    "rt10_s", "rt25_s", "rt50_s", "rt75_s", "rt90_s", "rtavg_s", "dS_num_error", "dC_num_error", "sanity_ok",
 ]
 VSMOW_conc18O = 2005.2e-6  # roger/settings.py
 D18O_MIN, D18O_MAX = -20.0, 0.0

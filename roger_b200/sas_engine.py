@@ -32,6 +32,7 @@ def _bind(lib):
     lib.roger_sas_download_tt.argtypes = [hp, C.c_int, dp]
     lib.roger_sas_download_statistics.argtypes = [hp, dp]
     lib.roger_sas_set_balance_reference.argtypes = [hp, dp]
+    lib.roger_sas_set_sanity_bounds.argtypes = [hp, dp, dp, dp, dp, C.c_double, C.c_double]
     lib.roger_sas_synchronize.argtypes = [hp]
     lib.roger_sas_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
     _bound = True
@@ -125,6 +126,12 @@ class CudaSasEngine:
         if a.size != self.n:
             raise ValueError("set_balance_reference: n_cells values expected")
         _check(self.lib, self.lib.roger_sas_set_balance_reference(self.h, self._dp(a)))
+
+    def set_sanity_bounds(self, S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss, atol=1e-2, rtol=1e-2):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss)]
+        if any(a.size != self.n for a in arrs):
+            raise ValueError("set_sanity_bounds: n_cells values expected")
+        _check(self.lib, self.lib.roger_sas_set_sanity_bounds(self.h, *[self._dp(a) for a in arrs], float(atol), float(rtol)))
 
     def download_tt(self, process):
         out = np.empty((self.n, self.A))

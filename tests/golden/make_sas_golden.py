@@ -100,7 +100,7 @@ def run(name, simd_out=None):
     if case["age_statistics"]:
         from roger_b200 import sas as _sas
 
-        scal_vars = scal_vars + list(_sas.STATISTICS)
+        scal_vars = scal_vars + [n for n in _sas.STATISTICS if n != "sanity_ok"]
 
     def grab():
         d = {}
@@ -114,11 +114,28 @@ def run(name, simd_out=None):
             d[v] = np.asarray(getattr(vs, v))[2:-2, 2:-2, 1].reshape(C).copy()
         return d
 
+    # the scalar result of numerics.sanity_check as write_output sees it (first call of every step, transport.py:3406)
+    import roger.core.numerics as numerics
+    import roger.core.transport as transport_mod
+
+    sanity = []
+    orig_check = numerics.sanity_check
+    seen = {"itt": None}
+
+    def recording_check(st):
+        r = orig_check(st)
+        if seen["itt"] != int(vs.itt):
+            seen["itt"] = int(vs.itt)
+            sanity.append(bool(r))
+        return r
+
+    numerics.sanity_check = recording_check
     init = grab()
     recs = []
     for day in range(case["ndays"]):
         model.step(state)
         recs.append(grab())
+    numerics.sanity_check = orig_check
     if simd_out is not None:
         np.savez(simd_out, **{"simd_rec_" + k: np.stack([r[k] for r in recs]) for k in SIMD_KEEP})
         return
@@ -133,6 +150,10 @@ def run(name, simd_out=None):
         out["in_" + k] = case[k].reshape(C, -1)
     for proc, arr in case["sas"].items():
         out["sas_" + proc] = arr.reshape(C, 8)
+    for k in ("S_sat_rz", "S_sat_ss", "S_pwp_rz", "S_pwp_ss"):
+        out["par_" + k] = np.asarray(case[k], dtype=np.float64).reshape(C)
+    if len(sanity) == case["ndays"]:
+        out["rec_sanity_all"] = np.asarray(sanity)
     for k, v in init.items():
         out["init_" + k] = v
     for k in recs[0]:

@@ -249,3 +249,27 @@ def test_water_and_solute_balance_closure_no_worse_than_oracle(oracle_roger_pow)
         # fluxes larger than the stored water are truncated by the solver (transport.py:431): closure holds where they fit
         ok = np.abs((s1 - s0) - net) < 1e-9
         assert ok.mean() > 0.5
+
+
+def test_sanity_flag_with_violated_bounds(oracle_roger_pow):
+    """numerics.sanity_check per cell: storage bounds that some cells exceed and a tolerance tight enough to trip the balance
+    checks must flag the same cells on the device and in the oracle"""
+    from roger_b200 import sas
+
+    C_, A, ndays = 150, 40, 5
+    daily, spec = _random_case(C_, A, ndays, seed=31)
+    rng = np.random.default_rng(32)
+    bounds = (rng.uniform(60, 400, C_), rng.uniform(150, 900, C_), rng.uniform(0, 60, C_), rng.uniform(0, 150, C_))
+    models = [sas.SasModel(e, C_, A, daily, spec, age_statistics=True) for e in (_cuda(), oracle_roger_pow)]
+    for m in models:
+        m.setup()
+        m.engine.set_sanity_bounds(*bounds, atol=1e-13, rtol=1e-13)
+    flags = []
+    for day in range(ndays):
+        for m in models:
+            m.step()
+        a, b = models[0].statistics()["sanity_ok"], models[1].statistics()["sanity_ok"]
+        assert np.array_equal(a, b), day
+        flags.append(a)
+    flags = np.stack(flags)
+    assert 0.0 < flags.mean() < 1.0  # both outcomes occur

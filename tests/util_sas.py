@@ -28,6 +28,8 @@ def model_from_fixture(fx, engine_cls, store_tt=True, engine_kwargs=None, mask=N
         m.engine.upload_state(k, fx["init_" + k])
     if age_statistics:
         m.engine.set_balance_reference(fx["init_C_s"])
+        if "par_S_sat_rz" in fx:
+            m.engine.set_sanity_bounds(fx["par_S_sat_rz"], fx["par_S_sat_ss"], fx["par_S_pwp_rz"], fx["par_S_pwp_ss"])
     return m
 
 
@@ -71,6 +73,8 @@ def replay_against_fixture(fx, model, exact=True, tol=None, skip_nan_pattern=())
     for day in range(int(fx["ndays"])):
         model.step()
         snap = snapshot(model)
+        if "rec_sanity_all" in fx and "sanity_ok" in snap:
+            assert bool(np.all(snap["sanity_ok"] == 1.0)) == bool(fx["rec_sanity_all"][day]), f"day {day}: sanity_check differs"
         for k, x in snap.items():
             if "rec_" + k not in fx:
                 continue
