@@ -123,6 +123,7 @@ class OracleSasEngine:
         f = np.ascontiguousarray(forcing, dtype=np.float64)
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         s = self.state
+        self._install_bounds()
         self._fn(C.c_int64(self.n), C.byref(self.settings), dp(s["sa_rz"]), dp(s["sa_ss"]), dp(s["msa_rz"]), dp(s["msa_ss"]),
                  dp(f), dp(self.mask), dp(self.params), dp(self.out), dp(self.ttbuf) if self.ttbuf is not None else None,
                  dp(self.stats) if self.stats is not None else None, dp(self.balance_prev))
@@ -132,11 +133,17 @@ class OracleSasEngine:
 
     def set_sanity_bounds(self, S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss, atol=1e-2, rtol=1e-2):
         self._bounds = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss)]
+        self._tol = (float(atol), float(rtol))
+
+    def _install_bounds(self):
+        """the C oracle keeps the bounds in file-scope variables: (re)install this engine's before every step"""
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         fn = lib().sas_oracle_set_sanity_bounds
         fn.argtypes = [C.POINTER(C.c_double)] * 4 + [C.c_double, C.c_double]
         fn.restype = None
-        fn(*[dp(a) for a in self._bounds], float(atol), float(rtol))
+        b = getattr(self, "_bounds", None)
+        atol, rtol = getattr(self, "_tol", (1e-2, 1e-2))
+        fn(*([dp(a) for a in b] if b else [None] * 4), atol, rtol)
 
     def download_statistics(self):
         return self.stats.copy()
