@@ -180,7 +180,10 @@ def test_age_statistics_and_balance_errors_against_reference_fixture():
     for day in range(4):
         m.step()
         st = m.statistics()
+        assert bool(np.all(st["sanity_ok"] == 1.0)) == bool(fx["rec_sanity_all"][day])
         for k in sas.STATISTICS:
+            if k == "sanity_ok":
+                continue
             r = fx["rec_" + k][day]
             if k.endswith("_num_error"):
                 assert np.all(np.abs(st[k] - r) < 1e-12), (k, day)
