@@ -214,16 +214,18 @@ class CudaTransportDriver:
         self.setup = setup
         self.state = setup.state
         vs, st = self.state.variables, self.state.settings
-        if not getattr(st, "enable_offline_transport", False) or not getattr(st, "enable_oxygen18", False):
-            raise ValueError("CudaTransportDriver drives the offline oxygen-18 transport model")
+        iso18, iso2 = bool(getattr(st, "enable_oxygen18", False)), bool(getattr(st, "enable_deuterium", False))
+        if not getattr(st, "enable_offline_transport", False) or not (iso18 or iso2):
+            raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium transport model")
         if getattr(st, "sas_solver", None) != "deterministic":
             raise NotImplementedError("only sas_solver = 'deterministic' runs on the device (DESIGN.md section 7)")
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
         self.C = self.nx * self.ny
         self.pull_state = bool(pull_state)
         self.stats = bool(getattr(st, "enable_age_statistics", False))
-        s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(st.VSMOW_conc18O), float(st.d18O_min), float(st.d18O_max),
-                            int(bool(store_tt)), int(self.stats))
+        # deuterium runs the same kernels with its own standard ratio and plausibility window (transport.py:315-340)
+        vsmow, dmin, dmax = (st.VSMOW_conc18O, st.d18O_min, st.d18O_max) if iso18 else (st.VSMOW_conc2H, st.d2H_min, st.d2H_max)
+        s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats))
         self.settings = s
         self.engine = engine_cls(self.C, s, **(engine_kwargs or {}))
         tau = int(vs.tau)
