@@ -119,10 +119,17 @@ int roger_svat_run_day(roger_svat *h, int write_fluxes, int *n_steps);
 int roger_svat_run_steps(roger_svat *h, int write_fluxes, int max_steps, int *n_steps);
 /* switch the day-blocked launch off / on (default on) and bound the steps per launch (2..144) */
 int roger_svat_set_block_stepping(roger_svat *h, int enabled, int max_block);
-/* ---- RATE diagnostics on the device (roger/diagnostics/rate.py:72-91): the named planes are added into accumulator planes
- *      after every step (sums over the output interval; the daily sums that drive the offline transport model,
+/* ---- diagnostics accumulators on the device (roger/diagnostics/{rate,average,maximum,minimum}.py): the named planes are
+ *      folded into accumulator planes after every step (e.g. the daily sums that drive the offline transport model,
  *      test/make_data_for_svat_transport.py:279-300).  Accumulating a flux plane switches the steps to the
  *      flux-storing kernels. */
+#define ROGER_DIAG_RATE 0    /* sum over the interval,                      roger/diagnostics/rate.py:72-81     */
+#define ROGER_DIAG_AVERAGE 1 /* mean over the steps of the interval,        roger/diagnostics/average.py:71-97  */
+#define ROGER_DIAG_MAXIMUM 2 /* running maximum of a 2-D variable,          roger/diagnostics/maximum.py:76-92  */
+#define ROGER_DIAG_MINIMUM 3 /* running minimum of a 2-D variable,          roger/diagnostics/minimum.py        */
+int roger_svat_set_diagnostics(roger_svat *h, const int *fields, const int *modes, int n);
+int roger_svat_download_diagnostics(roger_svat *h, double *host, int reset);
+/* RATE only (modes = NULL) */
 int roger_svat_set_rate_fields(roger_svat *h, const int *fields, int n);
 int roger_svat_download_rates(roger_svat *h, double *host, int reset);
 uint64_t roger_svat_rates_ptr(roger_svat *h);

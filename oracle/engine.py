@@ -74,17 +74,45 @@ class OracleSvatEngine:
         p, t, e = self.forcing
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         self._fn(C.c_int64(self.n), dp(self.planes), dp(p), dp(t), dp(e), C.byref(self.scalars), C.byref(self.settings))
-        for k, name in enumerate(getattr(self, "_rate_names", ())):
-            self._rates[k] += self.planes[self.abi.FIELD_ID[name]]
+        if getattr(self, "_rate_names", None):
+            self._diagnose()
+
+    def set_diagnostics(self, spec):
+        """NumPy restatement of roger/diagnostics/{rate,average,maximum,minimum}.py for 2-D variables"""
+        self._rate_names = [n for n, _ in spec]
+        self._rate_modes = [m for _, m in spec]
+        self._rates = np.zeros((len(spec), self.n))
+        self._diag_count = 0
 
     def set_rate_fields(self, names):
-        self._rate_names = list(names)
-        self._rates = np.zeros((len(self._rate_names), self.n))
+        self.set_diagnostics([(n, "rate") for n in names])
+
+    def _diagnose(self):
+        self._diag_count += 1
+        for k, (name, mode) in enumerate(zip(self._rate_names, self._rate_modes)):
+            v = self.planes[self.abi.FIELD_ID[name]]
+            a = self._rates[k]
+            with np.errstate(all="ignore"):
+                if mode == "rate":
+                    self._rates[k] = a + v
+                elif mode == "average":
+                    self._rates[k] = np.where(np.isnan(a), 0, a) + v
+                elif mode == "maximum":
+                    d0 = np.where((a == 0) & (v < 0), np.nan, a)
+                    self._rates[k] = np.where(np.isnan(d0), v, np.where(np.isnan(v), d0, np.maximum(d0, v)))
+                else:
+                    d0 = np.where((a == 0) & (v > 0), np.nan, a)
+                    self._rates[k] = np.where(np.isnan(d0), v, np.where(np.isnan(v), d0, np.minimum(d0, v)))
 
     def download_rates(self, reset=True):
-        out = dict(zip(self._rate_names, self._rates.copy()))
+        vals = self._rates.copy()
+        for k, mode in enumerate(self._rate_modes):
+            if mode == "average" and self._diag_count > 0:
+                vals[k] = vals[k] / self._diag_count
+        out = dict(zip(self._rate_names, vals))
         if reset:
             self._rates[:] = 0
+            self._diag_count = 0
         return out
 
     def synchronize(self):

@@ -210,11 +210,28 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
     warp_or(flags, bits);
 }
 
-// RATE diagnostics (roger/diagnostics/rate.py:72-81): acc[k] += plane(field[k]) after every step, on the device
-__global__ void k_accumulate_rates(Planes pl, double* __restrict__ acc, const int* __restrict__ fields, int n) {
+// Diagnostics accumulators on the device, updated after every step (the reference's `diagnose`):
+//   RATE    acc += v                                         roger/diagnostics/rate.py:72-81
+//   AVERAGE acc = (isnan(acc) ? 0 : acc) + v, / count later  average.py:71-84, :94-97
+//   MAXIMUM acc = nanmax(acc', v), acc' = NaN if acc == 0 and v < 0     maximum.py:76-92 (2-D variables)
+//   MINIMUM acc = nanmin(acc', v), acc' = NaN if acc == 0 and v > 0     minimum.py
+__global__ void k_accumulate_rates(Planes pl, double* __restrict__ acc, const int* __restrict__ fields, const int* __restrict__ modes, int n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pl.C) return;
-    for (int k = 0; k < n; k++) acc[(size_t)k * pl.C + i] += pl.at(fields[k])[i];
+    for (int k = 0; k < n; k++) {
+        const double v = pl.at(fields[k])[i];
+        double a = acc[(size_t)k * pl.C + i];
+        const int mode = modes[k];
+        if (mode == ROGER_DIAG_RATE) a = a + v;
+        else if (mode == ROGER_DIAG_AVERAGE) a = ((a != a) ? 0.0 : a) + v;
+        else {
+            const bool mx = (mode == ROGER_DIAG_MAXIMUM);
+            if ((a == 0) && (mx ? (v < 0) : (v > 0))) a = __longlong_as_double(0x7ff8000000000000ULL);
+            if (a != a) a = v;                    // nanmax / nanmin of (NaN, v) = v (NaN if both are)
+            else if (v == v) a = mx ? ((v > a) ? v : a) : ((v < a) ? v : a);
+        }
+        acc[(size_t)k * pl.C + i] = a;
+    }
 }
 
 // Several consecutive adaptive steps of every cell in ONE launch (uniform forcing, snow-free stretch of a day: the
@@ -308,10 +325,11 @@ struct roger_svat {
     double u_cur_prec = 0, u_cur_ta = 0;
     bool u_cur_valid = false;
     // RATE diagnostics accumulated on the device (roger_svat_set_rate_fields)
-    std::vector<int> rate_fields;
+    std::vector<int> rate_fields, rate_modes;
     bool rates_need_flux = false;
     double* d_rates = nullptr;
-    int* d_rate_fields = nullptr;
+    int* d_rate_fields = nullptr;  // n field ids followed by n modes
+    int64_t diag_count = 0;        // steps accumulated since the last reset (average_nitts)
     // day-blocked stepping (run_block)
     int max_block = 144;
     bool block_stepping = true;
@@ -731,9 +749,11 @@ static int step_impl(roger_svat* h, int write_fluxes) {
     CU(cudaGetLastError());
     launches++;
     if (!h->rate_fields.empty()) {
-        k_accumulate_rates<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(pl, h->d_rates, h->d_rate_fields, (int)h->rate_fields.size());
+        const int n = (int)h->rate_fields.size();
+        k_accumulate_rates<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(pl, h->d_rates, h->d_rate_fields, h->d_rate_fields + n, n);
         CU(cudaGetLastError());
         launches++;
+        h->diag_count++;
     }
     if (!h->ks_ss_synced) {  // subsoil.calc_ks (subsoil.py:6-20): ks_ss = ks from the end of the first step on
         CU(cudaMemcpyAsync(pl.at(RF_ks_ss), pl.at(RF_ks), sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToDevice, h->stream));
@@ -864,40 +884,60 @@ int roger_svat_run_day(roger_svat* h, int write_fluxes, int* n_steps) {
     return roger_svat_run_steps(h, write_fluxes, 144, n_steps);
 }
 
-// RATE diagnostics on the device: after every step the named planes are added into accumulator planes.
-int roger_svat_set_rate_fields(roger_svat* h, const int* fields, int n) {
-    if (!h || n < 0 || n > 64 || (n > 0 && !fields)) return fail(ROGER_EINVAL, "roger_svat_set_rate_fields: bad argument");
+// Diagnostics accumulators on the device: after every step the named planes are folded into accumulator planes.
+int roger_svat_set_diagnostics(roger_svat* h, const int* fields, const int* modes, int n) {
+    if (!h || n < 0 || n > 64 || (n > 0 && !fields)) return fail(ROGER_EINVAL, "roger_svat_set_diagnostics: bad argument");
     CU(cudaSetDevice(h->device));
-    for (int k = 0; k < n; k++)
-        if (fields[k] < 0 || fields[k] >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_set_rate_fields: bad field id");
+    for (int k = 0; k < n; k++) {
+        if (fields[k] < 0 || fields[k] >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_set_diagnostics: bad field id");
+        const int m = modes ? modes[k] : ROGER_DIAG_RATE;
+        if (m < ROGER_DIAG_RATE || m > ROGER_DIAG_MINIMUM) return fail(ROGER_EINVAL, "roger_svat_set_diagnostics: bad mode");
+    }
     cudaFree(h->d_rates); h->d_rates = nullptr;
     cudaFree(h->d_rate_fields); h->d_rate_fields = nullptr;
     h->rate_fields.assign(fields, fields + n);
+    h->rate_modes.assign(n, ROGER_DIAG_RATE);
+    if (modes) h->rate_modes.assign(modes, modes + n);
     h->rates_need_flux = false;
+    h->diag_count = 0;
     for (int f : h->rate_fields) h->rates_need_flux = h->rates_need_flux || kind_is_F(f);
     if (n == 0) return 0;
     if (h->rates_need_flux) { int r = ensure_flux_planes(h); if (r) return r; }
     const size_t bytes = sizeof(double) * (size_t)n * (size_t)h->C;
     CU(cudaMalloc(&h->d_rates, bytes));
     CU(cudaMemsetAsync(h->d_rates, 0, bytes, h->stream));
-    CU(cudaMalloc(&h->d_rate_fields, sizeof(int) * n));
+    CU(cudaMalloc(&h->d_rate_fields, sizeof(int) * 2 * n));
     CU(cudaMemcpyAsync(h->d_rate_fields, h->rate_fields.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_rate_fields + n, h->rate_modes.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
-// the accumulated planes (n_fields x n_cells doubles, in the order given to roger_svat_set_rate_fields); reset != 0 zeroes
-// them afterwards (start of the next output interval, roger/diagnostics/rate.py:83-91)
-int roger_svat_download_rates(roger_svat* h, double* host, int reset) {
-    if (!h || !host) return fail(ROGER_EINVAL, "roger_svat_download_rates: bad argument");
-    if (h->rate_fields.empty()) return fail(ROGER_EINVAL, "roger_svat_download_rates: no rate fields set");
+int roger_svat_set_rate_fields(roger_svat* h, const int* fields, int n) { return roger_svat_set_diagnostics(h, fields, nullptr, n); }
+
+// the accumulated planes (n_fields x n_cells doubles, in the order given to roger_svat_set_diagnostics); AVERAGE planes are
+// divided by the number of accumulated steps (average.py:94-97); reset != 0 zeroes the accumulators afterwards (start of the
+// next output interval)
+int roger_svat_download_diagnostics(roger_svat* h, double* host, int reset) {
+    if (!h || !host) return fail(ROGER_EINVAL, "roger_svat_download_diagnostics: bad argument");
+    if (h->rate_fields.empty()) return fail(ROGER_EINVAL, "roger_svat_download_diagnostics: no diagnostics set");
     CU(cudaSetDevice(h->device));
     const size_t bytes = sizeof(double) * h->rate_fields.size() * (size_t)h->C;
     CU(cudaMemcpyAsync(host, h->d_rates, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (reset) CU(cudaMemsetAsync(h->d_rates, 0, bytes, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->diag_count > 0)
+        for (size_t k = 0; k < h->rate_fields.size(); k++)
+            if (h->rate_modes[k] == ROGER_DIAG_AVERAGE) {
+                double* p = host + k * (size_t)h->C;
+                const double cnt = (double)h->diag_count;
+                for (int64_t i = 0; i < h->C; i++) p[i] = p[i] / cnt;
+            }
+    if (reset) h->diag_count = 0;
     return 0;
 }
+
+int roger_svat_download_rates(roger_svat* h, double* host, int reset) { return roger_svat_download_diagnostics(h, host, reset); }
 
 uint64_t roger_svat_rates_ptr(roger_svat* h) { return h ? (uint64_t)(uintptr_t)h->d_rates : 0; }
 

@@ -55,6 +55,8 @@ def load_library():
     lib.roger_svat_run_steps.argtypes = [hp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.roger_svat_set_block_stepping.argtypes = [hp, C.c_int, C.c_int]
     lib.roger_svat_set_rate_fields.argtypes = [hp, C.POINTER(C.c_int), C.c_int]
+    lib.roger_svat_set_diagnostics.argtypes = [hp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+    lib.roger_svat_download_diagnostics.argtypes = [hp, dp, C.c_int]
     lib.roger_svat_download_rates.argtypes = [hp, dp, C.c_int]
     lib.roger_svat_rates_ptr.argtypes = [hp]
     lib.roger_svat_rates_ptr.restype = C.c_uint64
@@ -179,11 +181,20 @@ class CudaSvatEngine:
         self._timing()
         return n.value
 
+    DIAG_MODES = {"rate": 0, "average": 1, "maximum": 2, "minimum": 3}
+
+    def set_diagnostics(self, spec):
+        """spec: list of (field name, "rate" | "average" | "maximum" | "minimum"); accumulated on the device after every step
+        until download_rates(reset=True)."""
+        self._rate_names = [n for n, _ in spec]
+        n = len(spec)
+        ids = (C.c_int * n)(*[abi.FIELD_ID[name] for name, _ in spec])
+        modes = (C.c_int * n)(*[self.DIAG_MODES[m] for _, m in spec])
+        _check(self.lib, self.lib.roger_svat_set_diagnostics(self.h, ids, modes, n))
+
     def set_rate_fields(self, names):
         """RATE diagnostics: sum the named planes over the steps until the next download_rates(reset=True)."""
-        self._rate_names = list(names)
-        ids = (C.c_int * len(self._rate_names))(*[abi.FIELD_ID[n] for n in self._rate_names])
-        _check(self.lib, self.lib.roger_svat_set_rate_fields(self.h, ids, len(self._rate_names)))
+        self.set_diagnostics([(n, "rate") for n in names])
 
     def download_rates(self, reset=True):
         out = np.empty((len(self._rate_names), self.n))

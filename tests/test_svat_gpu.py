@@ -219,3 +219,36 @@ def test_edge_grids_bit_for_bit(shape, masked):
             assert util.same_bits(models[0].get(n), models[1].get(n)), n
     finally:
         lib().roger_oracle_set_pow(0)
+
+
+def test_average_maximum_minimum_diagnostics_on_the_device():
+    """AVERAGE / MAXIMUM / MINIMUM accumulators (roger/diagnostics/average.py, maximum.py, minimum.py) against their NumPy
+    restatement on the oracle engine, over output intervals of one day"""
+    from oracle.engine import OracleSvatEngine, lib
+    from roger_b200 import synth
+    from roger_b200.svat import SvatModel
+
+    shape = (12, 9)
+    forcing = synth.mixed_forcing(8, seed=42, start_doy=121)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, masked_fraction=0.1)
+    spec = [("theta_rz", "average"), ("q_ss", "maximum"), ("dS", "minimum"), ("aet", "rate"), ("q_sur", "maximum"), ("z_sat", "average")]
+    lib().roger_oracle_set_pow(1)
+    try:
+        models = [SvatModel(e, shape, forcing, prim, th_rz, th_ss) for e in (_engine(), OracleSvatEngine)]
+        for m in models:
+            m.setup()
+            m.engine.set_diagnostics(spec)
+        for day in range(4):
+            while True:
+                a, b = models[0].step(True), models[1].step(True)
+                if a.time % 86400 == 0:
+                    break
+            da, db = models[0].engine.download_rates(reset=True), models[1].engine.download_rates(reset=True)
+            for (name, mode), x, y in zip(spec, da.values(), db.values()):
+                pass
+            xa = np.stack(list(models[0].engine.download_rates(reset=False).values()))
+            assert np.all(xa == 0)  # reset
+            for k in da:
+                assert util.same_bits(da[k], db[k]), (day, k)
+    finally:
+        lib().roger_oracle_set_pow(0)
