@@ -60,6 +60,10 @@ typedef struct roger_sas_settings {
     double d18O_max;       /* settings.d18O_max                                         */
     int32_t store_tt;      /* keep the five travel-time distributions tt_* (diagnostics) */
     int32_t age_statistics; /* compute the RSS_* planes every step (settings.enable_age_statistics + numerical errors) */
+    int32_t solute;         /* 0: stable isotope (oxygen-18 / deuterium: msa holds bin concentrations);
+                               1: conservative anion (bromide / chloride: msa holds bin solute MASS, the *_transport_anion_kernel
+                                  family of the reference; the RSO_C_iso_* result planes then hold the solute masses M_*) */
+    int32_t reserved;
 } roger_sas_settings;
 
 typedef struct roger_sas roger_sas; /* opaque handle */
@@ -81,6 +85,11 @@ int roger_sas_age_base(roger_sas *h);
 int roger_sas_init_linear(roger_sas *h, const double *S_rz, const double *S_ss, double conc0);
 /* maskCatch (n_cells) and SAS parameters (RSP_COUNT * n_cells * 8), roger/variables.py:4275 */
 int roger_sas_set_parameters(roger_sas *h, const double *mask_catch, const double *sas_params);
+/* anion transport only: partition coefficients of transpiration and percolation (vs.alpha_transp, vs.alpha_q), land use
+ * and root-zone saturation storage (crop nutrient uptake stops above 80 % saturation, evapotranspiration.py:931-938);
+ * n_cells doubles each */
+int roger_sas_set_anion_parameters(roger_sas *h, const double *alpha_transp, const double *alpha_q, const double *lu_id,
+                                   const double *S_sat_rz);
 /* one daily step.  forcing: RSF_COUNT planes of n_cells doubles (host memory). */
 int roger_sas_step(roger_sas *h, const double *forcing);
 /* same with forcing already on the device (raw address of RSF_COUNT * n_cells doubles) */

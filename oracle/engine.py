@@ -163,6 +163,9 @@ class OracleSasEngine:
         self._bounds = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss)]
         self._tol = (float(atol), float(rtol))
 
+    def set_anion_parameters(self, alpha_transp, alpha_q, lu_id, S_sat_rz):
+        self._anion = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (alpha_transp, alpha_q, lu_id, S_sat_rz)]
+
     def _install_bounds(self):
         """the C oracle keeps the bounds in file-scope variables: (re)install this engine's before every step"""
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
@@ -172,6 +175,11 @@ class OracleSasEngine:
         b = getattr(self, "_bounds", None)
         atol, rtol = getattr(self, "_tol", (1e-2, 1e-2))
         fn(*([dp(a) for a in b] if b else [None] * 4), atol, rtol)
+        fa = lib().sas_oracle_set_anion_parameters
+        fa.argtypes = [C.POINTER(C.c_double)] * 4
+        fa.restype = None
+        a = getattr(self, "_anion", None)
+        fa(*([dp(x) for x in a] if a else [None] * 4))
 
     def download_statistics(self):
         return self.stats.copy()

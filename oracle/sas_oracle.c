@@ -422,6 +422,176 @@ void sas_oracle_set_sanity_bounds(const double *S_sat_rz, const double *S_sat_ss
     g_atol = atol; g_rtol = rtol;
 }
 
+
+/* ================================================================================================================
+ * Conservative anions (bromide / chloride): msa holds the solute MASS of every age bin.
+ * infiltration.py:2350-2422, :2504-2560; evapotranspiration.py:620-651, :905-982; subsurface_runoff.py (anion kernels);
+ * capillary_rise.py (anion kernel); root_zone.py / subsoil.py / soil.py anion storage kernels; transport.py:582-596 calc_mtt,
+ * :622-679 ageing.
+ * ================================================================================================================ */
+static const double *g_anion[4] = {NULL, NULL, NULL, NULL}; /* alpha_transp, alpha_q, lu_id, S_sat_rz */
+void sas_oracle_set_anion_parameters(const double *alpha_transp, const double *alpha_q, const double *lu_id, const double *S_sat_rz)
+{
+    g_anion[0] = alpha_transp; g_anion[1] = alpha_q; g_anion[2] = lu_id; g_anion[3] = S_sat_rz;
+}
+static double np_nansum(const double *a, int n, double *tmp)
+{
+    for (int j = 0; j < n; j++) tmp[j] = isnan(a[j]) ? 0 : a[j];
+    return np_sum(tmp, n);
+}
+/* transport.py:582-596 */
+static void anion_mtt(int A, const double *sa, const double *tt, double flux, const double *msa, double alpha, double m, double *mtt)
+{
+    for (int j = 0; j < A; j++) {
+        double v = ((sa[j] > 0) ? (msa[j] / sa[j]) : 0) * alpha * tt[j] * flux;
+        v = (v <= 0) ? 0 : v;
+        v = (v > msa[j]) ? msa[j] : v;
+        mtt[j] = v * m;
+    }
+}
+/* water part of a withdrawal: cumulative StorAge, travel-time distribution (kept in tt) */
+static void anion_tt(const sas_ctx *c, const double *sa_src, double flux, const double *sp, double m, double *tt, double *work)
+{
+    const int A = c->A, N = A + 1;
+    double *SA = work, *w2 = SA + N;
+    calc_SA(A, sa_src, SA);
+    for (int j = 0; j < N; j++) SA[j] = SA[j] * m;
+    calc_tt(c, SA, sa_src, flux, sp, m, tt, w2);
+    for (int j = 0; j < A; j++) tt[j] = tt[j] * m;
+}
+static void keep_tt(double *dst, const double *tt, int A)
+{
+    if (dst) memcpy(dst, tt, sizeof(double) * (size_t)A);
+}
+static void anion_ageing(int A, double *sa, double *msa)
+{
+    const double sam1_last = sa[A - 1], msam1_last = msa[A - 1];
+    for (int j = A - 1; j >= 1; j--) sa[j] = sa[j - 1];
+    sa[0] = 0;
+    sa[A - 1] += sam1_last;
+    sa[A - 1] = (sa[A - 1] < 1e-8) ? 0 : sa[A - 1];
+    for (int j = A - 1; j >= 1; j--) msa[j] = msa[j - 1];
+    msa[0] = 0;
+    msa[A - 1] += msam1_last;
+}
+
+static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss,
+                           const double *forcing, double m, const double *sas_params, double *out, double *tt_out, double *work, double *tmp)
+{
+    const int A = c->A;
+#define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
+#define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
+#define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)
+#define TTO(p) (tt_out ? tt_out + ((size_t)(p) * (size_t)C + (size_t)i) * A : NULL)
+    double *tt = work, *mtt = tt + (A + 2), *w2 = mtt + (A + 2);
+    const double C_in = F(RSF_C_in);
+    const double alpha_q = g_anion[1] ? g_anion[1][i] : 1.0;
+    /* infiltration into the root zone */
+    O(RSO_C_inf_mat_rz) = ((F(RSF_inf_mat_rz) > 0) ? C_in : 0) * m;
+    O(RSO_C_inf_pf_rz) = ((F(RSF_inf_pf_rz) > 0) ? C_in : 0) * m;
+    O(RSO_C_iso_inf_mat_rz) = O(RSO_C_inf_mat_rz) * F(RSF_inf_mat_rz) * m; /* M_inf_mat_rz */
+    O(RSO_C_iso_inf_pf_rz) = O(RSO_C_inf_pf_rz) * F(RSF_inf_pf_rz) * m;    /* M_inf_pf_rz  */
+    s_rz[0] += F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) * m;
+    ms_rz[0] += O(RSO_C_iso_inf_mat_rz) + O(RSO_C_iso_inf_pf_rz) * m;
+    /* soil evaporation: water only */
+    anion_tt(c, s_rz, F(RSF_evap_soil), SP(RSP_evap_soil), m, tt, w2);
+    update_sa(A, s_rz, tt, F(RSF_evap_soil), m);
+    keep_tt(TTO(RSP_evap_soil), tt, A);
+    O(RSO_C_evap_soil) = 0;
+    O(RSO_C_iso_evap_soil) = 0;
+    /* transpiration */
+    {
+        anion_tt(c, s_rz, F(RSF_transp), SP(RSP_transp), m, tt, w2);
+        const double lu = g_anion[2] ? g_anion[2][i] : 0.0, sat = g_anion[3] ? g_anion[3][i] : INFINITY;
+        const int crop_wet = (lu > 500) && (lu < 599) && (np_sum(s_rz, A) >= 0.8 * sat);
+        const double alpha = (crop_wet ? 0 : (g_anion[0] ? g_anion[0][i] : 1.0)) * m;
+        anion_mtt(A, s_rz, tt, F(RSF_transp), ms_rz, alpha, m, mtt);
+        const double M = np_sum(mtt, A);
+        O(RSO_C_transp) = ((F(RSF_transp) > 0) ? M / F(RSF_transp) : 0) * m;
+        O(RSO_C_iso_transp) = M * m;
+        update_sa(A, s_rz, tt, F(RSF_transp), m);
+        for (int j = 0; j < A; j++) ms_rz[j] += -mtt[j] * m;
+        keep_tt(TTO(RSP_transp), tt, A);
+    }
+    /* percolation of the root zone into the subsoil */
+    {
+        anion_tt(c, s_rz, F(RSF_q_rz), SP(RSP_q_rz), m, tt, w2);
+        anion_mtt(A, s_rz, tt, F(RSF_q_rz), ms_rz, alpha_q, m, mtt);
+        const double M = np_sum(mtt, A);
+        O(RSO_C_q_rz) = ((F(RSF_q_rz) > 0) ? M / F(RSF_q_rz) : 0) * m;
+        O(RSO_C_iso_q_rz) = M * m;
+        update_sa(A, s_rz, tt, F(RSF_q_rz), m);
+        for (int j = 0; j < A; j++) {
+            ms_rz[j] += -mtt[j] * m;
+            ms_ss[j] += mtt[j] * m;
+            s_ss[j] += tt[j] * F(RSF_q_rz) * m;
+        }
+        keep_tt(TTO(RSP_q_rz), tt, A);
+    }
+    /* infiltration into the subsoil */
+    O(RSO_C_inf_pf_ss) = ((F(RSF_inf_pf_ss) > 0) ? C_in : 0) * m;
+    O(RSO_C_iso_inf_pf_ss) = O(RSO_C_inf_pf_ss) * F(RSF_inf_pf_ss) * m; /* M_inf_pf_ss */
+    s_ss[0] += F(RSF_inf_pf_ss) * m;
+    ms_ss[0] += O(RSO_C_iso_inf_pf_ss) * m;
+    /* percolation of the subsoil */
+    {
+        anion_tt(c, s_ss, F(RSF_q_ss), SP(RSP_q_ss), m, tt, w2);
+        anion_mtt(A, s_ss, tt, F(RSF_q_ss), ms_ss, alpha_q, m, mtt);
+        const double M = np_sum(mtt, A);
+        O(RSO_C_q_ss) = ((F(RSF_q_ss) > 0) ? M / F(RSF_q_ss) : 0) * m;
+        O(RSO_C_iso_q_ss) = M * m;
+        update_sa(A, s_ss, tt, F(RSF_q_ss), m);
+        for (int j = 0; j < A; j++) ms_ss[j] += -mtt[j] * m;
+        keep_tt(TTO(RSP_q_ss), tt, A);
+    }
+    /* capillary rise into the root zone */
+    {
+        anion_tt(c, s_ss, F(RSF_cpr_rz), SP(RSP_cpr_rz), m, tt, w2);
+        anion_mtt(A, s_ss, tt, F(RSF_cpr_rz), ms_ss, alpha_q, m, mtt);
+        const double M = np_sum(mtt, A);
+        O(RSO_C_cpr_rz) = ((F(RSF_cpr_rz) > 0) ? M / F(RSF_cpr_rz) : 0) * m;
+        O(RSO_C_iso_cpr_rz) = M * m;
+        update_sa(A, s_ss, tt, F(RSF_cpr_rz), m);
+        for (int j = 0; j < A; j++) {
+            ms_ss[j] += -mtt[j] * m;
+            s_rz[j] += tt[j] * F(RSF_cpr_rz) * m;
+            ms_rz[j] += mtt[j] * m;
+        }
+        keep_tt(TTO(RSP_cpr_rz), tt, A);
+    }
+    /* storage kernels */
+    for (int j = 0; j < A; j++) s_rz[j] = (s_rz[j] < 1e-8) ? 0 : s_rz[j];
+    for (int j = 0; j < A; j++) ms_rz[j] = (s_rz[j] <= 0) ? 0 : ms_rz[j];
+    {
+        const double M = np_nansum(ms_rz, A, tmp) * m, S = np_sum(s_rz, A);
+        O(RSO_C_iso_rz) = M;
+        O(RSO_C_rz) = (S > 0) ? M / S : 0;
+    }
+    for (int j = 0; j < A; j++) s_ss[j] = (s_ss[j] < 1e-8) ? 0 : s_ss[j];
+    for (int j = 0; j < A; j++) ms_ss[j] = (s_ss[j] <= 0) ? 0 : ms_ss[j];
+    {
+        const double M = np_nansum(ms_ss, A, tmp) * m, S = np_sum(s_ss, A);
+        O(RSO_C_iso_ss) = M;
+        O(RSO_C_ss) = (S > 0) ? M / S : 0;
+    }
+    {
+        double *sa_s = tmp + (A + 2), *msa_s = sa_s + (A + 2);
+        for (int j = 0; j < A; j++) {
+            sa_s[j] = s_rz[j] + s_ss[j] * m;
+            msa_s[j] = ms_rz[j] + ms_ss[j] * m;
+        }
+        const double M = np_nansum(msa_s, A, tmp) * m, S = np_sum(sa_s, A);
+        O(RSO_C_iso_s) = M;
+        O(RSO_C_s) = (S > 0) ? M / S : 0;
+    }
+    anion_ageing(A, s_rz, ms_rz);
+    anion_ageing(A, s_ss, ms_ss);
+#undef F
+#undef O
+#undef SP
+#undef TTO
+}
+
 void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
                           const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
                           double *stats, double *balance_prev);
@@ -451,6 +621,10 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
             const double m = mask[i];
             double *s_rz = sa_rz + (size_t)i * A, *s_ss = sa_ss + (size_t)i * A;
             double *ms_rz = msa_rz + (size_t)i * A, *ms_ss = msa_ss + (size_t)i * A;
+            if (st->solute == 1) {
+                anion_day_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out, work, tmp);
+                continue;
+            }
 #define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
 #define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
 #define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)

@@ -148,6 +148,23 @@ k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double*
 #undef SP
 }
 
+// One daily step of the conservative-anion transport (bromide / chloride), one thread per cell.
+__global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
+k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
+                const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap) {
+    __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
+    __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
+    for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
+        s_log[k] = d_pow_log_tab[k];
+        s_exp[k] = d_pow_exp_tab[k];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.C) return;
+    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    anion_day(cx, forcing, mask[i], sas_params, ap, out);
+}
+
 // (cells, A) row-major staging block <-> age-major planes, 32 x 32 tiles through shared memory
 __global__ void k_stage_to_planes(const double* __restrict__ stage, double* __restrict__ planes, int64_t C, int A, int base,
                                   int64_t cell0, int ncell) {
@@ -261,6 +278,7 @@ struct roger_sas {
     double* d_stats = nullptr;     // RSS_COUNT planes (settings.age_statistics)
     double* d_C_s_prev = nullptr;  // vs.C_s[taum1]
     double* d_bounds = nullptr;    // S_sat_rz, S_sat_ss, S_pwp_rz, S_pwp_ss (sanity check), optional
+    double* d_anion = nullptr;     // alpha_transp, alpha_q, lu_id, S_sat_rz (anion transport), optional
     double atol = 1e-2, rtol = 1e-2;
     double* d_mask = nullptr;
     double* d_params = nullptr;
@@ -325,6 +343,9 @@ extern "C" {
 int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings* settings, int device) {
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_sas_create: bad argument");
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
+    if (settings->solute != 0 && settings->solute != 1) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope) or 1 (anion)");
+    if (settings->solute == 1 && settings->age_statistics)
+        return fail(ROGER_ENOTSUP, "roger_sas_create: age statistics are implemented for the isotope transport only");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -385,7 +406,7 @@ void roger_sas_destroy(roger_sas* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto p : h->d_state) cudaFree(p);
-    cudaFree(h->d_stats); cudaFree(h->d_C_s_prev); cudaFree(h->d_bounds);
+    cudaFree(h->d_stats); cudaFree(h->d_C_s_prev); cudaFree(h->d_bounds); cudaFree(h->d_anion);
     cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_params); cudaFree(h->d_stage); cudaFree(h->d_plan);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -457,7 +478,11 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     CU(cudaEventRecord(h->ev0, h->stream));
     const int threads = ROGER_SAS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
-    if (h->st.age_statistics)
+    if (h->st.solute == 1) {
+        AnionParams ap{nullptr, nullptr, nullptr, nullptr};
+        if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
+        k_sas_day_anion<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out, ap);
+    } else if (h->st.age_statistics)
         k_sas_day<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
                                                            h->d_stats, h->d_C_s_prev, h->d_bounds, h->atol, h->rtol);
     else
@@ -524,6 +549,17 @@ int roger_sas_set_sanity_bounds(roger_sas* h, const double* S_sat_rz, const doub
     CU(cudaStreamSynchronize(h->stream));
     h->atol = atol;
     h->rtol = rtol;
+    return 0;
+}
+
+int roger_sas_set_anion_parameters(roger_sas* h, const double* alpha_transp, const double* alpha_q, const double* lu_id, const double* S_sat_rz) {
+    if (!h || !alpha_transp || !alpha_q || !lu_id || !S_sat_rz) return fail(ROGER_EINVAL, "roger_sas_set_anion_parameters: bad argument");
+    CU(cudaSetDevice(h->device));
+    const size_t plane = sizeof(double) * (size_t)h->C;
+    if (!h->d_anion) CU(cudaMalloc(&h->d_anion, 4 * plane));
+    const double* src[4] = {alpha_transp, alpha_q, lu_id, S_sat_rz};
+    for (int k = 0; k < 4; k++) CU(cudaMemcpyAsync(h->d_anion + (size_t)k * h->C, src[k], plane, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -341,9 +341,6 @@ struct CellCtx {
 #ifndef ROGER_SAS_UNROLL
 #define ROGER_SAS_UNROLL 2
 #endif
-#ifndef ROGER_SAS_FUSE_LAST
-#define ROGER_SAS_FUSE_LAST 0  // measured slower (2.5e6 vs 2.9e6 cell-days/s): the fused pass loses the two-bin interleave of the pow evaluations
-#endif
 
 // One sub-step of the deterministic solver for `n` consecutive bins starting at j0 (transport.py:388-470).  The n values
 // of san / TTn were loaded by the caller (xb, tb); the cumulative SAS function of the n bins is evaluated first --
@@ -443,32 +440,6 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
     }
 }
 
-// The travel-time increment of ONE bin in a power-law sub-step: the arithmetic of pow_pass_bins<> without the StorAge
-// bookkeeping (the last sub-step's san / max are never used).  Keep in step with pow_pass_bins<>.
-__device__ __forceinline__ double pow_bin_tti(const PowPassConst& k, PowPassCarry& c, const roger_pow_tables tabs, double x) {
-    double om;
-    c.acc_in += x;
-    if (x == 0) {
-        om = c.om_prev;
-    } else {
-        const double SA = c.acc_in;
-        const bool in = (SA > 0) && (SA <= k.S);
-        const bool easy = in && (SA >= 0x1p-500);
-        const double xr = div_by(SA, k.S, k.rS);
-        double p = roger_pow_core(easy ? roger_pow_asu(xr) : 0x3fe0000000000000ULL, k.y, tabs);
-        if (in && !easy) p = roger_pow(SA / k.S, k.y, tabs);
-        om = (SA > 0) ? ((SA <= k.S) ? p : 1.) : 0.;
-    }
-    const double d = om - c.om_prev;
-    c.om_prev = om;
-    double tti = (d >= 0) ? d : 0;
-    const double q = k.flux * tti * k.h;
-    const double ttqi = (q > x) ? x : q;
-    tti = (ttqi == 0 || div_range_ok(ttqi)) ? div_by(ttqi, k.fh, k.rfh) : ttqi / k.fh;
-    c.acc_t += tti;
-    return tti;
-}
-
 template <bool FIRST>
 __device__ __noinline__ void pow_pass_tail(const PowPassConst& k, PowPassCarry& c, const roger_pow_tables tabs, double* __restrict__ san_o,
                                            double* __restrict__ TTn_o, int64_t C, int n) {
@@ -519,99 +490,96 @@ __device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, 
 // ---- one SAS-controlled withdrawal from layer `src`, optionally received by layer `dst` (dst < 0: leaves the
 // soil).  evapotranspiration.py:653-716, :831-895; subsurface_runoff.py:1531-1625, :1753-1815;
 // capillary_rise.py:404-500.
-template <bool STATS>
-__device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
-                                        double m, double* C_flux, double* C_iso_flux, int process, FluxStats* fs) {
+// The sub-step solver of one flux (transport.py:362-470): leaves the accumulated cumulative travel-time distribution of
+// the layer `src` in the scratch array TTn (index j holds TTn[j + 1]).  Returns false when flux * h <= 0: every sub-step
+// then leaves StorAge and TTn untouched and TTn counts as zero.
+__device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double flux, const double* sp_global, int64_t sp_stride, double m) {
     constexpr int U = ROGER_SAS_UNROLL;
     const SasParams& P = cx.P;
     const int A = P.A;
     double* __restrict__ sa = cx.pl.sa[src];
-    double* __restrict__ msa = cx.pl.msa[src];
     double* __restrict__ san = cx.pl.san;
     double* __restrict__ TTn = cx.pl.TTn;
-    const int64_t C = P.C;
     const double h = 1.0 / P.substeps;
-    const bool active = (flux * h > 0);  // otherwise every sub-step leaves san and TTn untouched (tti = 0)
-    bool fused = false, fused_first = false;
-    PowPassConst fk{};
-    PowPassCarry fc{0, 0, 0, 0.0, 0.0, false};
-
-    if (active) {
-        // cumulative StorAge of the layer (transport.py:343-359) -> S = max(SA); the layer's StorAge is copied into the
-        // (unrotated) scratch array the sub-steps work on
-        NpMax mx;
-        const double SA0 = 0. * m;
-        mx.init(SA0);
-        {
-            double acc = 0;
-            int j = 0;
-            for (; j + 8 <= A; j += 8) {
-                double v[8];
+    if (!(flux * h > 0)) return false;
+    // cumulative StorAge of the layer (transport.py:343-359) -> S = max(SA); the layer's StorAge is copied into the
+    // (unrotated) scratch array the sub-steps work on
+    NpMax mx;
+    const double SA0 = 0. * m;
+    mx.init(SA0);
+    {
+        double acc = 0;
+        int j = 0;
+        for (; j + 8 <= A; j += 8) {
+            double v[8];
 #pragma unroll
-                for (int q = 0; q < 8; q++) v[q] = sa[cx.ring(j + q)];
+            for (int q = 0; q < 8; q++) v[q] = sa[cx.ring(j + q)];
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    san[cx.lin(j + q)] = v[q];
-                    acc += v[q];
-                    mx.push(acc * m);
-                }
-            }
-            for (; j < A; j++) {
-                const double v = sa[cx.ring(j)];
-                san[cx.lin(j)] = v;
-                acc += v;
+            for (int q = 0; q < 8; q++) {
+                san[cx.lin(j + q)] = v[q];
+                acc += v[q];
                 mx.push(acc * m);
             }
         }
-        Family fam;
-        family_begin(fam, sp_global, sp_stride, m);
-        const double fh = flux * h;
-        for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
-            family_prepare(fam, mx.get());
-            const bool first = (s == 0);
-            const bool pow_fast = fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh);
-            if (ROGER_SAS_FUSE_LAST && pow_fast && s == P.substeps - 1) {
-                // The last sub-step's StorAge is never read again and its contribution to TTn is consumed bin by bin by the
-                // aggregation below: it runs inside that pass (no san / TTn stores, no TTn re-read).
-                fused = true;
-                fused_first = first;
-                fk = PowPassConst{fam.S, 1.0 / fam.S, fam.sp[1], flux, h, fh, 1.0 / fh};
-                break;
-            }
-            if (pow_fast) {
-                const double S_next = first ? substep_pass_pow<U, true>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn)
-                                            : substep_pass_pow<U, false>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn);
-                mx.init(S_next);
-                continue;
-            }
-            SubstepCarry k;
-            k.om_prev = omega(fam, P, cx.tabs, 0, SA0);
-            k.acc_in = 0; k.acc_new = 0; k.acc_t = 0;
-            k.mxn.init(SA0);
-            // register double buffer: the loads of block b+1 are in flight while block b is computed
-            double xn_[U], tn_[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                xn_[u] = (u < A) ? san[cx.lin(u)] : 0.0;
-                tn_[u] = (!first && u < A) ? TTn[cx.lin(u)] : 0.0;
-            }
-            int j0 = 0;
-            for (; j0 + U <= A; j0 += U) {
-                double xb[U], tb[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) { xb[u] = xn_[u]; tb[u] = tn_[u]; }
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int jn = j0 + U + u;
-                    xn_[u] = (jn < A) ? san[cx.lin(jn)] : 0.0;
-                    tn_[u] = (!first && jn < A) ? TTn[cx.lin(jn)] : 0.0;
-                }
-                substep_block<U>(cx, fam, k, j0, U, xb, tb, first, flux, h, fh, m, san, TTn);
-            }
-            if (j0 < A) substep_block<U>(cx, fam, k, j0, A - j0, xn_, tn_, first, flux, h, fh, m, san, TTn);
-            mx = k.mxn;
+        for (; j < A; j++) {
+            const double v = sa[cx.ring(j)];
+            san[cx.lin(j)] = v;
+            acc += v;
+            mx.push(acc * m);
         }
     }
+    Family fam;
+    family_begin(fam, sp_global, sp_stride, m);
+    const double fh = flux * h;
+    for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
+        family_prepare(fam, mx.get());
+        const bool first = (s == 0);
+        if (fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh)) {
+            const double S_next = first ? substep_pass_pow<U, true>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn)
+                                        : substep_pass_pow<U, false>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn);
+            mx.init(S_next);
+            continue;
+        }
+        SubstepCarry k;
+        k.om_prev = omega(fam, P, cx.tabs, 0, SA0);
+        k.acc_in = 0; k.acc_new = 0; k.acc_t = 0;
+        k.mxn.init(SA0);
+        // register double buffer: the loads of block b+1 are in flight while block b is computed
+        double xn_[U], tn_[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            xn_[u] = (u < A) ? san[cx.lin(u)] : 0.0;
+            tn_[u] = (!first && u < A) ? TTn[cx.lin(u)] : 0.0;
+        }
+        int j0 = 0;
+        for (; j0 + U <= A; j0 += U) {
+            double xb[U], tb[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { xb[u] = xn_[u]; tb[u] = tn_[u]; }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int jn = j0 + U + u;
+                xn_[u] = (jn < A) ? san[cx.lin(jn)] : 0.0;
+                tn_[u] = (!first && jn < A) ? TTn[cx.lin(jn)] : 0.0;
+            }
+            substep_block<U>(cx, fam, k, j0, U, xb, tb, first, flux, h, fh, m, san, TTn);
+        }
+        if (j0 < A) substep_block<U>(cx, fam, k, j0, A - j0, xn_, tn_, first, flux, h, fh, m, san, TTn);
+        mx = k.mxn;
+    }
+    return true;
+}
+
+template <bool STATS>
+__device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
+                                        double m, double* C_flux, double* C_iso_flux, int process, FluxStats* fs) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    double* __restrict__ sa = cx.pl.sa[src];
+    double* __restrict__ msa = cx.pl.msa[src];
+    double* __restrict__ TTn = cx.pl.TTn;
+    const int64_t C = P.C;
+    const bool active = solve_substeps(cx, src, flux, sp_global, sp_stride, m);
 
     // aggregate (transport.py:472-496), flux concentration (:512-535), isotope mixing into the receiving layer,
     // StorAge update (:599-619)
@@ -631,24 +599,17 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
         for (int k = 0; k < 5; k++) trk[k].init(pcts[k]);
     }
     bool first_bin = true;
-    const roger_pow_tables tabs = cx.tabs;
-    stream_sums<NS, 6>(cx.plan,
+    stream_sums<NS, 5>(cx.plan,
         [&](int j, double* L) {
             const int64_t o = cx.ring(j);
-            L[0] = (active && !(fused && fused_first)) ? TTn[cx.lin(j)] : 0.;
+            L[0] = active ? TTn[cx.lin(j)] : 0.;
             L[1] = sa[o];
             L[2] = msa[o];
             if (dst >= 0) { L[3] = sa_d[o]; L[4] = msa_d[o]; }
-            if (fused) L[5] = san[cx.lin(j)];
         },
         [&](int j, const double* L, double* v) {
             const int64_t o = cx.ring(j);
-            double ttn = L[0];
-            if (fused) {  // TTn[j + 1] of the last sub-step, accumulated on the fly
-                pow_bin_tti(fk, fc, tabs, L[5]);
-                ttn = (fused_first ? 0.0 : L[0]) + fc.acc_t;
-            }
-            const double cur = ttn / nsub;
+            const double cur = L[0] / nsub;
             double t = cur - prev;
             prev = cur;
             const double s_j = L[1];
@@ -694,6 +655,182 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
     conc = (conc != 0) ? conc : __longlong_as_double(0x7ff8000000000000LL);
     *C_flux = conc * m;
     *C_iso_flux = conc_to_delta(P, *C_flux) * m;
+}
+
+// ================================================================================================================
+// Conservative anions (bromide / chloride): msa holds the solute MASS of every age bin
+// (infiltration.py:2350-2422, :2504-2560; evapotranspiration.py:620-651, :905-982; the anion kernels of
+// subsurface_runoff.py and capillary_rise.py; transport.py:582-596 calc_mtt, :622-679 ageing).
+// ================================================================================================================
+// One flux out of layer `src`: water by the SAS solver, solute as mtt = clip(msa / sa * alpha * tt * flux, 0, msa); the
+// receiving layer (dst >= 0) takes both.  with_solute = false is the water-only soil evaporation.  Returns sum(mtt).
+__device__ __noinline__ double anion_withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
+                                                double m, double alpha, bool with_solute, int process) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    double* __restrict__ sa = cx.pl.sa[src];
+    double* __restrict__ msa = cx.pl.msa[src];
+    double* __restrict__ TTn = cx.pl.TTn;
+    const int64_t C = P.C;
+    const bool active = solve_substeps(cx, src, flux, sp_global, sp_stride, m);
+    double* __restrict__ sa_d = (dst >= 0) ? cx.pl.sa[dst] : nullptr;
+    double* __restrict__ msa_d = (dst >= 0) ? cx.pl.msa[dst] : nullptr;
+    double* __restrict__ tt_out = (P.store_tt && cx.pl.tt) ? cx.pl.tt + (size_t)process * (size_t)A * (size_t)C : nullptr;
+    const double nsub = (double)P.substeps;
+    double prev = 0. / nsub;
+    double sums[1];
+    stream_sums<1, 5>(cx.plan,
+        [&](int j, double* L) {
+            const int64_t o = cx.ring(j);
+            L[0] = active ? TTn[cx.lin(j)] : 0.;
+            L[1] = sa[o];
+            if (with_solute) L[2] = msa[o];
+            if (dst >= 0) { L[3] = sa_d[o]; L[4] = msa_d[o]; }
+        },
+        [&](int j, const double* L, double* v) {
+            const int64_t o = cx.ring(j);
+            const double cur = L[0] / nsub;
+            double t = cur - prev;
+            prev = cur;
+            const double s_j = L[1];
+            const double q = flux * t;
+            const double ttq = (q > s_j) ? s_j : q;
+            t = (flux > 0) ? ttq / flux : 0;
+            t = t * m;
+            double mtt = 0.0;
+            if (with_solute) {
+                const double ms_j = L[2];
+                double w = ((s_j > 0) ? (ms_j / s_j) : 0) * alpha * t * flux;
+                w = (w <= 0) ? 0 : w;
+                w = (w > ms_j) ? ms_j : w;
+                mtt = w * m;
+                msa[o] = ms_j + -mtt * m;
+            }
+            v[0] = mtt;
+            double u = s_j + -flux * t;
+            u = ((u > -1e-5) && (u < 0)) ? 0 : u;
+            sa[o] = u * m;
+            if (dst >= 0) {
+                msa_d[o] = L[4] + mtt * m;
+                sa_d[o] = L[3] + t * flux * m;
+            }
+            if (tt_out) tt_out[cx.lin(j)] = t;
+        }, sums);
+    return sums[0];
+}
+
+struct AnionParams {  // per-cell planes (may be null: alpha = 1, no crops)
+    const double* alpha_transp;
+    const double* alpha_q;
+    const double* lu_id;
+    const double* S_sat_rz;
+};
+
+__device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
+                                          const AnionParams ap, double* __restrict__ out) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    const int64_t C = P.C, i = cx.i;
+    double* __restrict__ s_rz = cx.pl.sa[0];
+    double* __restrict__ s_ss = cx.pl.sa[1];
+    double* __restrict__ m_rz = cx.pl.msa[0];
+    double* __restrict__ m_ss = cx.pl.msa[1];
+#define F(k) forcing[(int64_t)(k) * C + i]
+#define O(k) out[(int64_t)(k) * C + i]
+#define SP(p) (sas_params + (int64_t)(p) * 8 * C + i)
+    const double C_in = F(RSF_C_in);
+    const double alpha_q = ap.alpha_q ? ap.alpha_q[i] : 1.0;
+    const int64_t o0 = cx.ring(0);
+    {   // infiltration into the root zone
+        const double c1 = ((F(RSF_inf_mat_rz) > 0) ? C_in : 0) * m, c2 = ((F(RSF_inf_pf_rz) > 0) ? C_in : 0) * m;
+        const double M1 = c1 * F(RSF_inf_mat_rz) * m, M2 = c2 * F(RSF_inf_pf_rz) * m;
+        O(RSO_C_inf_mat_rz) = c1; O(RSO_C_inf_pf_rz) = c2; O(RSO_C_iso_inf_mat_rz) = M1; O(RSO_C_iso_inf_pf_rz) = M2;
+        s_rz[o0] = s_rz[o0] + (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) * m);
+        m_rz[o0] = m_rz[o0] + (M1 + M2 * m);
+    }
+    anion_withdrawal(cx, 0, -1, F(RSF_evap_soil), SP(RSP_evap_soil), C, m, 0.0, false, RSP_evap_soil);  // water only
+    O(RSO_C_evap_soil) = 0; O(RSO_C_iso_evap_soil) = 0;
+    {   // transpiration: crop nutrient uptake stops above 80 % saturation (evapotranspiration.py:931-938)
+        const double lu = ap.lu_id ? ap.lu_id[i] : 0.0;
+        bool crop_wet = false;
+        if ((lu > 500) && (lu < 599)) {
+            double sm[1];
+            stream_sums<1, 1>(cx.plan, [&](int j, double* L) { L[0] = s_rz[cx.ring(j)]; }, [&](int, const double* L, double* v) { v[0] = L[0]; }, sm);
+            const double sat = ap.S_sat_rz ? ap.S_sat_rz[i] : __longlong_as_double(0x7ff0000000000000LL);
+            crop_wet = sm[0] >= 0.8 * sat;
+        }
+        const double alpha = (crop_wet ? 0 : (ap.alpha_transp ? ap.alpha_transp[i] : 1.0)) * m;
+        const double M = anion_withdrawal(cx, 0, -1, F(RSF_transp), SP(RSP_transp), C, m, alpha, true, RSP_transp);
+        O(RSO_C_transp) = ((F(RSF_transp) > 0) ? M / F(RSF_transp) : 0) * m;
+        O(RSO_C_iso_transp) = M * m;
+    }
+    {
+        const double M = anion_withdrawal(cx, 0, 1, F(RSF_q_rz), SP(RSP_q_rz), C, m, alpha_q, true, RSP_q_rz);
+        O(RSO_C_q_rz) = ((F(RSF_q_rz) > 0) ? M / F(RSF_q_rz) : 0) * m;
+        O(RSO_C_iso_q_rz) = M * m;
+    }
+    {   // infiltration into the subsoil
+        const double c3 = ((F(RSF_inf_pf_ss) > 0) ? C_in : 0) * m;
+        const double M3 = c3 * F(RSF_inf_pf_ss) * m;
+        O(RSO_C_inf_pf_ss) = c3; O(RSO_C_iso_inf_pf_ss) = M3;
+        s_ss[o0] = s_ss[o0] + F(RSF_inf_pf_ss) * m;
+        m_ss[o0] = m_ss[o0] + M3 * m;
+    }
+    {
+        const double M = anion_withdrawal(cx, 1, -1, F(RSF_q_ss), SP(RSP_q_ss), C, m, alpha_q, true, RSP_q_ss);
+        O(RSO_C_q_ss) = ((F(RSF_q_ss) > 0) ? M / F(RSF_q_ss) : 0) * m;
+        O(RSO_C_iso_q_ss) = M * m;
+    }
+    {
+        const double M = anion_withdrawal(cx, 1, 0, F(RSF_cpr_rz), SP(RSP_cpr_rz), C, m, alpha_q, true, RSP_cpr_rz);
+        O(RSO_C_cpr_rz) = ((F(RSF_cpr_rz) > 0) ? M / F(RSF_cpr_rz) : 0) * m;
+        O(RSO_C_iso_cpr_rz) = M * m;
+    }
+    {   // storage kernels (root_zone.py:219-261, subsoil.py anion, soil.py anion): clip, solute of empty bins removed, masses
+        double sums[6];
+        stream_sums<6, 4>(cx.plan,
+            [&](int j, double* L) {
+                const int64_t o = cx.ring(j);
+                L[0] = s_rz[o]; L[1] = s_ss[o]; L[2] = m_rz[o]; L[3] = m_ss[o];
+            },
+            [&](int j, const double* L, double* v) {
+                const int64_t o = cx.ring(j);
+                double a = L[0];
+                a = (a < 1e-8) ? 0 : a;
+                double b = L[1];
+                b = (b < 1e-8) ? 0 : b;
+                const double ma = (a <= 0) ? 0 : L[2], mb = (b <= 0) ? 0 : L[3];
+                s_rz[o] = a; s_ss[o] = b; m_rz[o] = ma; m_ss[o] = mb;
+                const double ms = ma + mb * m;
+                v[0] = isnan_d(ma) ? 0 : ma;
+                v[1] = a;
+                v[2] = isnan_d(mb) ? 0 : mb;
+                v[3] = b;
+                v[4] = isnan_d(ms) ? 0 : ms;
+                v[5] = a + b * m;
+            }, sums);
+        const double M_rz = sums[0] * m, M_ss = sums[2] * m, M_s = sums[4] * m;
+        O(RSO_C_iso_rz) = M_rz; O(RSO_C_rz) = (sums[1] > 0) ? M_rz / sums[1] : 0;
+        O(RSO_C_iso_ss) = M_ss; O(RSO_C_ss) = (sums[3] > 0) ? M_ss / sums[3] : 0;
+        O(RSO_C_iso_s) = M_s;   O(RSO_C_s) = (sums[5] > 0) ? M_s / sums[5] : 0;
+    }
+    {   // ageing (transport.py:622-679) as a rotation of the plane ring: the oldest two bins merge, bin 0 is emptied
+        const int b_new = (P.base == 0) ? A - 1 : P.base - 1;
+        const int b_last = (b_new == 0) ? A - 1 : b_new - 1;
+        for (int L = 0; L < 2; L++) {
+            double* __restrict__ sa = cx.pl.sa[L];
+            double* __restrict__ msa = cx.pl.msa[L];
+            double s_new = sa[(int64_t)b_last * C + i] + sa[(int64_t)b_new * C + i];
+            s_new = (s_new < 1e-8) ? 0 : s_new;
+            sa[(int64_t)b_last * C + i] = s_new;
+            msa[(int64_t)b_last * C + i] = msa[(int64_t)b_last * C + i] + msa[(int64_t)b_new * C + i];
+            sa[(int64_t)b_new * C + i] = 0;
+            msa[(int64_t)b_new * C + i] = 0;
+        }
+    }
+#undef F
+#undef O
+#undef SP
 }
 
 // infiltration of `inf` with concentration C_in into bin 0 (infiltration.py:2218-2345, :2441-2500)

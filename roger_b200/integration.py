@@ -225,7 +225,7 @@ class CudaTransportDriver:
         self.stats = bool(getattr(st, "enable_age_statistics", False))
         # deuterium runs the same kernels with its own standard ratio and plausibility window (transport.py:315-340)
         vsmow, dmin, dmax = (st.VSMOW_conc18O, st.d18O_min, st.d18O_max) if iso18 else (st.VSMOW_conc2H, st.d2H_min, st.d2H_max)
-        s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats))
+        s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats), 0, 0)
         self.settings = s
         self.engine = engine_cls(self.C, s, **(engine_kwargs or {}))
         tau = int(vs.tau)

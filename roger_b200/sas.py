@@ -27,11 +27,15 @@ D18O_MIN, D18O_MAX = -20.0, 0.0
 
 class SasSettings(C.Structure):
     _fields_ = [("ages", C.c_int32), ("substeps", C.c_int32), ("VSMOW_conc18O", C.c_double), ("d18O_min", C.c_double),
-                ("d18O_max", C.c_double), ("store_tt", C.c_int32), ("age_statistics", C.c_int32)]
+                ("d18O_max", C.c_double), ("store_tt", C.c_int32), ("age_statistics", C.c_int32), ("solute", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
-def default_settings(ages, substeps=6, store_tt=False, age_statistics=False):
-    return SasSettings(int(ages), int(substeps), VSMOW_conc18O, D18O_MIN, D18O_MAX, int(store_tt), int(age_statistics))
+ISOTOPE, ANION = 0, 1
+
+
+def default_settings(ages, substeps=6, store_tt=False, age_statistics=False, solute=ISOTOPE):
+    return SasSettings(int(ages), int(substeps), VSMOW_conc18O, D18O_MIN, D18O_MAX, int(store_tt), int(age_statistics), int(solute), 0)
 
 
 def delta_to_conc(delta):
@@ -72,19 +76,22 @@ def initial_age_distribution(S, ages):
 
 class SasModel:
     def __init__(self, engine_cls, n_cells, ages, daily, sas_spec, d18O_soil=-10.0, mask=None, substeps=6, store_tt=False,
-                 engine_kwargs=None, age_statistics=False):
+                 engine_kwargs=None, age_statistics=False, solute=ISOTOPE, anion_parameters=None):
         """daily: dict of (n_cells, ndays + 1) arrays PREC, INF_MAT_RZ, INF_PF_RZ, INF_PF_SS, TRANSP, EVAP_SOIL, CPR_RZ,
         Q_RZ, Q_SS, S_RZ, S_SS, S_SNOW, C_ISO_IN (index 0 = initial state, as in the reference's SVAT.nc)."""
         self.C = int(n_cells)
         self.ages = int(ages)
         self.daily = {k: np.asarray(v, dtype=np.float64) for k, v in daily.items()}
-        self.settings = default_settings(ages, substeps, store_tt, age_statistics)
+        self.solute = int(solute)
+        # anion transport (roger/models/svat_bromide): dict alpha_transp, alpha_q, lu_id, S_sat_rz of n_cells values each
+        self.anion_parameters = anion_parameters
+        self.settings = default_settings(ages, substeps, store_tt, age_statistics, solute)
         self.engine = engine_cls(self.C, self.settings, **(engine_kwargs or {}))
         self.mask = np.ones(self.C) if mask is None else np.asarray(mask, dtype=np.float64)
         self.sas_params = sas_parameter_block(self.C, sas_spec)
         self.d18O_soil = d18O_soil
         self.itt = 0
-        self.C_IN = delta_to_conc(self.daily["C_ISO_IN"])
+        self.C_IN = delta_to_conc(self.daily["C_ISO_IN"]) if self.solute == ISOTOPE else self.daily["C_IN"]
         self.C_snow = np.full((self.C, 2), 0.0)  # vs.C_snow[taum1, tau], initial 0 (roger/variables.py)
         self.S_snow_m1 = self.daily["S_SNOW"][:, 0].copy()
         self.prec_m1 = np.zeros(self.C)
@@ -97,6 +104,12 @@ class SasModel:
         c0 = float(delta_to_conc(self.d18O_soil))
         msa = np.full((self.C, self.ages), c0)
         msa[:, 0] = 0
+        if self.solute == ANION:  # no solute in the soil initially (svat_bromide.py:235-266)
+            msa[:] = 0
+            p = self.anion_parameters or {}
+            one = np.ones(self.C)
+            self.engine.set_anion_parameters(p.get("alpha_transp", one), p.get("alpha_q", one), p.get("lu_id", 0 * one),
+                                             p.get("S_sat_rz", np.inf * one))
         self.engine.set_parameters(self.mask, self.sas_params)
         self.engine.upload_state("sa_rz", sa_rz)
         self.engine.upload_state("sa_ss", sa_ss)
@@ -109,8 +122,15 @@ class SasModel:
             self.engine.set_balance_reference(c_s)
 
     def _set_forcing(self):
-        """benchmarks/SVATOXYGEN18_benchmark.py:385-444 (per-cell vectors)."""
+        """benchmarks/SVATOXYGEN18_benchmark.py:385-444 (per-cell vectors); roger/models/svat_bromide/svat_bromide.py:325-348."""
         d, t = self.daily, self.itt
+        if self.solute == ANION:
+            self.C_in = self.C_IN[:, t].copy()
+            f = np.empty((len(FORCING), self.C))
+            f[0], f[1], f[2] = d["INF_MAT_RZ"][:, t], d["INF_PF_RZ"][:, t], d["INF_PF_SS"][:, t]
+            f[3], f[4], f[5], f[6], f[7] = d["EVAP_SOIL"][:, t], d["TRANSP"][:, t], d["Q_RZ"][:, t], d["Q_SS"][:, t], d["CPR_RZ"][:, t]
+            f[8] = self.C_in
+            return f
         prec, S_snow = d["PREC"][:, t], d["S_SNOW"][:, t]
         C_in = self.C_IN[:, t].copy()
         cs_m1, cs = self.C_snow[:, 0], self.C_snow[:, 1]

@@ -33,6 +33,7 @@ def _bind(lib):
     lib.roger_sas_download_statistics.argtypes = [hp, dp]
     lib.roger_sas_set_balance_reference.argtypes = [hp, dp]
     lib.roger_sas_set_sanity_bounds.argtypes = [hp, dp, dp, dp, dp, C.c_double, C.c_double]
+    lib.roger_sas_set_anion_parameters.argtypes = [hp, dp, dp, dp, dp]
     lib.roger_sas_synchronize.argtypes = [hp]
     lib.roger_sas_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
     _bound = True
@@ -132,6 +133,12 @@ class CudaSasEngine:
         if any(a.size != self.n for a in arrs):
             raise ValueError("set_sanity_bounds: n_cells values expected")
         _check(self.lib, self.lib.roger_sas_set_sanity_bounds(self.h, *[self._dp(a) for a in arrs], float(atol), float(rtol)))
+
+    def set_anion_parameters(self, alpha_transp, alpha_q, lu_id, S_sat_rz):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (alpha_transp, alpha_q, lu_id, S_sat_rz)]
+        if any(a.size != self.n for a in arrs):
+            raise ValueError("set_anion_parameters: n_cells values expected")
+        _check(self.lib, self.lib.roger_sas_set_anion_parameters(self.h, *[self._dp(a) for a in arrs]))
 
     def download_tt(self, process):
         out = np.empty((self.n, self.A))

@@ -41,6 +41,9 @@ CASES = {
     # age statistics (percentile ages by numpy.interp) and the water / solute balance errors
     "sas_power_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=105, age_statistics=True,
                             sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
+    # conservative anion (bromide): solute mass per age bin, partition coefficients, a crop cell whose uptake stops when wet
+    "sas_bromide": dict(shape=(2, 3), ndays=26, ages=50, doy=100, solute="bromide",
+                        sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
     # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
     "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
                          sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
@@ -69,6 +72,21 @@ def build(name):
         ciso = rng.uniform(-12, -5, (nx, ny, ndays + 1))
     ciso[:, :, 0] = np.nan
     case["C_ISO_IN"] = ciso
+    if c.get("solute") == "bromide":
+        # a bromide pulse dissolved in the rain of days 2..4 (mg/l), nothing afterwards
+        cin = np.zeros((nx, ny, ndays + 1))
+        wet = np.flatnonzero(case["PREC"][0, 0, 1:] > 0) + 1
+        for d in list(wet[:3]) + list(wet[4:5]):  # the first three wet days and one later day carry bromide
+            cin[:, :, d] = rng.uniform(20, 80, (nx, ny)) * (case["PREC"][:, :, d] > 0)
+        case["C_IN"] = cin
+        case["alpha_transp"] = rng.uniform(0.2, 0.9, (nx, ny))
+        case["alpha_q"] = rng.uniform(0.4, 1.0, (nx, ny))
+        lu = np.full((nx, ny), 8.0)
+        lu[0, 1] = 525.0  # a crop cell ...
+        case["lu_id"] = lu
+        case["S_sat_rz"] = np.full((nx, ny), 1e4)
+        case["S_sat_rz"][0, 1] = case["S_RZ"][0, 1, 0] * 1.1  # ... close to saturation: uptake is switched off on wet days
+        case["solute"] = "bromide"
     sas = {}
     for proc, tup in c["sas"].items():
         arr = np.zeros((nx, ny, 8))
@@ -84,7 +102,8 @@ SIMD_KEEP = ["sa_rz", "sa_ss", "C_rz", "C_iso_transp", "C_iso_q_ss"]
 
 def run(name, simd_out=None):
     case = build(name)
-    Setup = rh.make_o18_setup(case)
+    bromide = case.get("solute") == "bromide"
+    Setup = rh.make_bromide_setup(case) if bromide else rh.make_o18_setup(case)
     model = Setup()
     model.setup()
     model.warmup()
@@ -97,6 +116,10 @@ def run(name, simd_out=None):
     scal_vars = ["C_evap_soil", "C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz", "C_iso_evap_soil", "C_iso_transp", "C_iso_q_rz", "C_iso_q_ss",
                  "C_iso_cpr_rz", "C_inf_mat_rz", "C_inf_pf_rz", "C_inf_pf_ss", "C_in"]
     lvl_vars = ["C_rz", "C_ss", "C_s", "C_iso_rz", "C_iso_ss", "C_iso_s", "C_snow"]
+    if bromide:
+        scal_vars = ["C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz", "C_inf_mat_rz", "C_inf_pf_rz", "C_inf_pf_ss", "C_in",
+                     "M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_inf_mat_rz", "M_inf_pf_rz", "M_inf_pf_ss"]
+        lvl_vars = ["C_rz", "C_ss", "C_s", "M_rz", "M_ss", "M_s"]
     if case["age_statistics"]:
         from roger_b200 import sas as _sas
 
@@ -137,7 +160,7 @@ def run(name, simd_out=None):
         recs.append(grab())
     numerics.sanity_check = orig_check
     if simd_out is not None:
-        np.savez(simd_out, **{"simd_rec_" + k: np.stack([r[k] for r in recs]) for k in SIMD_KEEP})
+        np.savez(simd_out, **{"simd_rec_" + k: np.stack([r[k] for r in recs]) for k in SIMD_KEEP if k in recs[0]})
         return
     out = dict(nx=nx, ny=ny, ndays=case["ndays"], ages=ages, substeps=6)
     with tempfile.TemporaryDirectory() as td:
@@ -146,8 +169,12 @@ def run(name, simd_out=None):
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "--simd", tmp, name], env=env, stdout=subprocess.DEVNULL)
         with np.load(tmp) as z:
             out.update({k: z[k] for k in z.files})
-    for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES) + ["C_ISO_IN"]:
+    for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES) + ["C_ISO_IN"] + (["C_IN"] if bromide else []):
         out["in_" + k] = case[k].reshape(C, -1)
+    if bromide:
+        out["solute"] = np.asarray(1)
+        for k in ("alpha_transp", "alpha_q", "lu_id"):
+            out["par_" + k] = np.asarray(case[k], dtype=np.float64).reshape(C)
     for proc, arr in case["sas"].items():
         out["sas_" + proc] = arr.reshape(C, 8)
     for k in ("S_sat_rz", "S_sat_ss", "S_pwp_rz", "S_pwp_ss"):
@@ -161,7 +188,7 @@ def run(name, simd_out=None):
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(name, "days", case["ndays"], "size %.1f KB" % (os.path.getsize(path) / 1024),
-          "sum sa_rz", float(np.nansum(recs[-1]["sa_rz"])), "C_iso_q_ss", recs[-1]["C_iso_q_ss"][:3])
+          "sum sa_rz", float(np.nansum(recs[-1]["sa_rz"])), "C_q_ss", recs[-1]["C_q_ss"][:3])
 
 
 if __name__ == "__main__":

@@ -436,3 +436,145 @@ def make_o18_setup(case):
         return KernelOutput(**out)
 
     return O18Setup
+
+
+def make_bromide_setup(case):
+    """Offline bromide (conservative anion) StorAge-selection transport: roger/models/svat_bromide/svat_bromide.py with
+    in-memory daily forcing on an (nx, ny) grid.
+
+    case: nx, ny, ndays, ages, daily arrays (nx, ny, ndays + 1): PREC, INF_MAT_RZ, INF_PF_RZ, INF_PF_SS, TRANSP, EVAP_SOIL, CPR_RZ,
+    Q_RZ, Q_SS, S_RZ, S_SS, C_IN (bromide concentration of the input); (nx, ny) arrays S_pwp_rz, S_pwp_ss, S_sat_rz, S_sat_ss,
+    alpha_transp, alpha_q, lu_id; sas: dict process -> (nx, ny, 8).
+    """
+    import_reference()
+    from roger import RogerSetup, roger_routine
+    from roger.variables import allocate
+    from roger.core.operators import numpy as npx, update, at
+
+    nx, ny, ndays, ages = case["nx"], case["ny"], case["ndays"], case["ages"]
+
+    class BromideSetup(RogerSetup):
+        @roger_routine
+        def set_settings(self, state):
+            s = state.settings
+            s.identifier = "GOLDEN_BR"
+            s.sas_solver = "deterministic"
+            s.sas_solver_substeps = case.get("substeps", 6)
+            s.nx, s.ny = nx, ny
+            s.runlen = 24 * 60 * 60 * ndays
+            s.runlen_warmup = 0
+            s.nitt = ndays + 1
+            s.ages = ages
+            s.nages = ages + 1
+            s.dx = 1
+            s.dy = 1
+            s.x_origin = 0.0
+            s.y_origin = 0.0
+            s.time_origin = "01-01-2022"
+            s.enable_offline_transport = True
+            s.enable_bromide = True
+            s.tm_structure = "power"
+            s.enable_age_statistics = False
+
+        @roger_routine
+        def read_data(self, state):
+            pass
+
+        @roger_routine
+        def set_grid(self, state):
+            vs = state.variables
+            settings = state.settings
+            vs.dt_secs = 60 * 60 * 24
+            vs.dt = 60 * 60 * 24 / (60 * 60)
+            vs.ages = update(vs.ages, at[:], npx.arange(1, settings.nages))
+            vs.nages = update(vs.nages, at[:], npx.arange(settings.nages))
+            dx = allocate(state.dimensions, ("x"))
+            dx = update(dx, at[:], settings.dx)
+            dy = allocate(state.dimensions, ("y"))
+            dy = update(dy, at[:], settings.dy)
+            vs.x = update(vs.x, at[3:-2], settings.x_origin + npx.cumsum(dx[3:-2]))
+            vs.y = update(vs.y, at[3:-2], settings.y_origin + npx.cumsum(dy[3:-2]))
+
+        @roger_routine
+        def set_look_up_tables(self, state):
+            pass
+
+        @roger_routine
+        def set_topography(self, state):
+            pass
+
+        @roger_routine
+        def set_parameters_setup(self, state):
+            vs = state.variables
+            for k in ("S_pwp_rz", "S_pwp_ss", "S_sat_rz", "S_sat_ss", "alpha_transp", "alpha_q"):
+                setattr(vs, k, update(getattr(vs, k), at[2:-2, 2:-2], case[k]))
+            vs.lu_id = update(vs.lu_id, at[2:-2, 2:-2], onp.asarray(case["lu_id"]).astype(vs.lu_id.dtype))
+            for proc, arr in case["sas"].items():
+                name = "sas_params_" + proc
+                setattr(vs, name, update(getattr(vs, name), at[2:-2, 2:-2, :], arr))
+
+        @roger_routine
+        def set_parameters(self, state):
+            pass
+
+        @roger_routine
+        def set_initial_conditions_setup(self, state):
+            vs = state.variables
+            vs.S_rz = update(vs.S_rz, at[2:-2, 2:-2, : vs.taup1], case["S_RZ"][:, :, 0, None])
+            vs.S_ss = update(vs.S_ss, at[2:-2, 2:-2, : vs.taup1], case["S_SS"][:, :, 0, None])
+            vs.S_s = update(vs.S_s, at[2:-2, 2:-2, : vs.taup1], vs.S_rz[2:-2, 2:-2, : vs.taup1] + vs.S_ss[2:-2, 2:-2, : vs.taup1])
+            vs.S_rz_init = update(vs.S_rz_init, at[2:-2, 2:-2], vs.S_rz[2:-2, 2:-2, 0])
+            vs.S_ss_init = update(vs.S_ss_init, at[2:-2, 2:-2], vs.S_ss[2:-2, 2:-2, 0])
+
+        @roger_routine
+        def set_initial_conditions(self, state):
+            # roger/models/svat_bromide/svat_bromide.py:235-266 (no bromide in the soil initially)
+            vs = state.variables
+            settings = state.settings
+            arr0 = allocate(state.dimensions, ("x", "y"))
+            vs.sa_rz = update(vs.sa_rz, at[2:-2, 2:-2, : vs.taup1, 1:],
+                              npx.diff(npx.linspace(arr0[2:-2, 2:-2], vs.S_rz[2:-2, 2:-2, vs.tau], settings.ages, axis=-1), axis=-1)[:, :, npx.newaxis, :])
+            vs.sa_ss = update(vs.sa_ss, at[2:-2, 2:-2, : vs.taup1, 1:],
+                              npx.diff(npx.linspace(arr0[2:-2, 2:-2], vs.S_ss[2:-2, 2:-2, vs.tau], settings.ages, axis=-1), axis=-1)[:, :, npx.newaxis, :])
+            vs.SA_rz = update(vs.SA_rz, at[2:-2, 2:-2, :, 1:], npx.cumsum(vs.sa_rz[2:-2, 2:-2, :, :], axis=-1))
+            vs.SA_ss = update(vs.SA_ss, at[2:-2, 2:-2, :, 1:], npx.cumsum(vs.sa_rz[2:-2, 2:-2, :, :], axis=-1))
+            vs.sa_s = update(vs.sa_s, at[2:-2, 2:-2, :, :], vs.sa_rz[2:-2, 2:-2, :, :] + vs.sa_ss[2:-2, 2:-2, :, :])
+            vs.SA_s = update(vs.SA_s, at[2:-2, 2:-2, :, 1:], npx.cumsum(vs.sa_s[2:-2, 2:-2, :, :], axis=-1))
+
+        @roger_routine
+        def set_boundary_conditions_setup(self, state):
+            pass
+
+        @roger_routine
+        def set_boundary_conditions(self, state):
+            pass
+
+        @roger_routine
+        def set_forcing_setup(self, state):
+            vs = state.variables
+            vs.C_IN = update(vs.C_IN, at[2:-2, 2:-2, :], case["C_IN"])
+
+        @roger_routine
+        def set_forcing(self, state):
+            # roger/models/svat_bromide/svat_bromide.py:325-348
+            vs = state.variables
+            t = vs.itt
+            vs.prec = update(vs.prec, at[2:-2, 2:-2, vs.tau], case["PREC"][:, :, t])
+            for name, key in (("inf_mat_rz", "INF_MAT_RZ"), ("inf_pf_rz", "INF_PF_RZ"), ("inf_pf_ss", "INF_PF_SS"), ("transp", "TRANSP"),
+                              ("evap_soil", "EVAP_SOIL"), ("cpr_rz", "CPR_RZ"), ("q_rz", "Q_RZ"), ("q_ss", "Q_SS")):
+                setattr(vs, name, update(getattr(vs, name), at[2:-2, 2:-2], case[key][:, :, t]))
+            vs.S_rz = update(vs.S_rz, at[2:-2, 2:-2, vs.tau], case["S_RZ"][:, :, t])
+            vs.S_ss = update(vs.S_ss, at[2:-2, 2:-2, vs.tau], case["S_SS"][:, :, t])
+            vs.S_s = update(vs.S_s, at[2:-2, 2:-2, vs.tau], vs.S_rz[2:-2, 2:-2, vs.tau] + vs.S_ss[2:-2, 2:-2, vs.tau])
+            vs.C_in = update(vs.C_in, at[2:-2, 2:-2], vs.C_IN[2:-2, 2:-2, vs.itt])
+            vs.M_in = update(vs.M_in, at[2:-2, 2:-2], vs.C_in[2:-2, 2:-2] * vs.prec[2:-2, 2:-2, vs.tau])
+
+        @roger_routine
+        def set_diagnostics(self, state):
+            pass
+
+        @roger_routine
+        def after_timestep(self, state):
+            pass
+
+    return BromideSetup

@@ -66,7 +66,7 @@ def test_hoisted_division_equals_division_instruction():
     assert bad.value == 0
 
 
-@pytest.mark.parametrize("case", u.SAS_CASES)
+@pytest.mark.parametrize("case", u.SAS_CASES + u.ANION_CASES)
 def test_cuda_equals_oracle_bit_for_bit_on_fixture_inputs(case, oracle_roger_pow):
     fx = u.load_case(case)
     a = u.model_from_fixture(fx, _cuda())
@@ -276,3 +276,35 @@ def test_sanity_flag_with_violated_bounds(oracle_roger_pow):
         flags.append(a)
     flags = np.stack(flags)
     assert 0.0 < flags.mean() < 1.0  # both outcomes occur
+
+
+def test_anion_transport_against_reference_fixture():
+    """bromide (roger/models/svat_bromide): solute mass per age bin, partition coefficients, crop uptake switch; the pulse
+    arrives on day 17, so the comparison covers the first days of solute dynamics before libm effects can build up"""
+    fx = u.load_case("sas_bromide")
+    m = u.model_from_fixture(fx, _cuda())
+    assert float(np.max(fx["rec_M_s"])) > 100
+    for day in range(21):
+        m.step()
+        snap = u.snapshot(m)
+        for k in ("sa_rz", "sa_ss", "msa_rz", "msa_ss", "M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_rz", "M_ss", "M_s", "C_rz", "C_ss", "C_s", "C_q_ss"):
+            assert u.rel_err(snap[k], fx["rec_" + k][day]) < 1e-9, (k, day)
+
+
+@pytest.mark.parametrize("C_,A,ndays", [(300, 96, 10), (65, 513, 4), (1, 5, 6)])
+def test_anion_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, oracle_roger_pow):
+    from roger_b200 import sas
+
+    daily, spec = _random_case(C_, A, ndays, seed=900 + A)
+    rng = np.random.default_rng(901)
+    daily["C_IN"] = rng.uniform(0, 50, daily["PREC"].shape) * (daily["PREC"] > 0)
+    lu = rng.choice([8.0, 525.0, 10.0, 560.0], C_)
+    ap = dict(alpha_transp=rng.uniform(0, 1, C_), alpha_q=rng.uniform(0.2, 1, C_), lu_id=lu,
+              S_sat_rz=daily["S_RZ"][:, 0] * rng.uniform(0.9, 2.0, C_))
+    mask = np.ones(C_)
+    mask[3::11] = 0.0
+    models = [sas.SasModel(e, C_, A, daily, spec, store_tt=True, mask=mask, solute=sas.ANION, anion_parameters=ap) for e in (_cuda(), oracle_roger_pow)]
+    for m in models:
+        m.setup()
+    u.replay_pair(models[0], models[1], ndays, exact=True)
+    assert float(np.nansum(models[0].state("msa_ss"))) > 0

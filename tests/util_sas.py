@@ -7,6 +7,7 @@ from roger_b200 import sas
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SAS_CASES = ["sas_power", "sas_power_snow", "sas_families", "sas_power_stats"]
+ANION_CASES = ["sas_bromide"]
 
 
 def load_case(name):
@@ -21,8 +22,13 @@ def model_from_fixture(fx, engine_cls, store_tt=True, engine_kwargs=None, mask=N
     spec = {p: fx["sas_" + p] for p in sas.PROCESSES}
     if age_statistics is None:
         age_statistics = "rec_dC_num_error" in fx
+    anion = "solute" in fx and int(fx["solute"]) == 1
+    kw = {}
+    if anion:
+        kw = dict(solute=sas.ANION, anion_parameters=dict(alpha_transp=fx["par_alpha_transp"], alpha_q=fx["par_alpha_q"], lu_id=fx["par_lu_id"],
+                                                          S_sat_rz=fx["par_S_sat_rz"]))
     m = sas.SasModel(engine_cls, C, A, daily, spec, substeps=int(fx["substeps"]), store_tt=store_tt, mask=mask,
-                     engine_kwargs=engine_kwargs, age_statistics=age_statistics)
+                     engine_kwargs=engine_kwargs, age_statistics=age_statistics, **kw)
     m.setup()
     for k in sas.STATE:  # start from the reference's own post-setup state
         m.engine.upload_state(k, fx["init_" + k])
@@ -61,6 +67,10 @@ def snapshot(model):
         for p in sas.PROCESSES:
             out["tt_" + p] = model.tt(p)
     out.update(model.outputs())
+    if model.settings.solute == 1:  # anion transport: the C_iso_* result planes carry the solute masses M_*
+        for k in list(out):
+            if k.startswith("C_iso_"):
+                out["M_" + k[len("C_iso_"):]] = out.pop(k)
     if model.settings.age_statistics:
         out.update(model.statistics())
     out["C_in"] = model.C_in.copy()
