@@ -215,23 +215,28 @@ class CudaTransportDriver:
         self.state = setup.state
         vs, st = self.state.variables, self.state.settings
         iso18, iso2 = bool(getattr(st, "enable_oxygen18", False)), bool(getattr(st, "enable_deuterium", False))
-        if not getattr(st, "enable_offline_transport", False) or not (iso18 or iso2):
-            raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium transport model")
+        self.anion = bool(getattr(st, "enable_bromide", False)) or bool(getattr(st, "enable_chloride", False))
+        if not getattr(st, "enable_offline_transport", False) or not (iso18 or iso2 or self.anion):
+            raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium / bromide / chloride transport models")
         if getattr(st, "sas_solver", None) != "deterministic":
             raise NotImplementedError("only sas_solver = 'deterministic' runs on the device (DESIGN.md section 7)")
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
         self.C = self.nx * self.ny
         self.pull_state = bool(pull_state)
-        self.stats = bool(getattr(st, "enable_age_statistics", False))
+        self.stats = bool(getattr(st, "enable_age_statistics", False)) and not self.anion  # (age statistics: isotope kernels only)
         # deuterium runs the same kernels with its own standard ratio and plausibility window (transport.py:315-340)
-        vsmow, dmin, dmax = (st.VSMOW_conc18O, st.d18O_min, st.d18O_max) if iso18 else (st.VSMOW_conc2H, st.d2H_min, st.d2H_max)
-        s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats), 0, 0)
+        vsmow, dmin, dmax = (st.VSMOW_conc2H, st.d2H_min, st.d2H_max) if iso2 else (st.VSMOW_conc18O, st.d18O_min, st.d18O_max)
+        s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats),
+                            sas.ANION if self.anion else sas.ISOTOPE, 0)
         self.settings = s
         self.engine = engine_cls(self.C, s, **(engine_kwargs or {}))
         tau = int(vs.tau)
         mask = np.asarray(vs.maskCatch)[2:-2, 2:-2].reshape(-1).astype(np.float64)
         block = np.stack([np.asarray(getattr(vs, "sas_params_" + p))[2:-2, 2:-2, :].reshape(self.C, 8) for p in sas.PROCESSES])
         self.engine.set_parameters(mask, block.astype(np.float64))
+        if self.anion:
+            inner = lambda n: np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64)  # noqa: E731
+            self.engine.set_anion_parameters(inner("alpha_transp"), inner("alpha_q"), inner("lu_id"), inner("S_sat_rz"))
         for name in sas.STATE:
             self.engine.upload_state(name, np.asarray(getattr(vs, name))[2:-2, 2:-2, tau, :].reshape(self.C, self.A))
         if self.stats:
@@ -266,6 +271,8 @@ class CudaTransportDriver:
         active = {n for n, m in state.var_meta.items() if m.active}
         with vs.unlock():
             for k, name in enumerate(sas.OUTPUTS):
+                if self.anion and name.startswith("C_iso_"):  # anion transport: these planes carry the solute masses M_*
+                    name = "M_" + name[len("C_iso_"):]
                 if name not in active:
                     continue
                 if np.asarray(getattr(vs, name)).ndim == 3:  # C_rz, C_ss, C_s, C_iso_*: both levels after after_substep_iso

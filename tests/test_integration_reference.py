@@ -76,11 +76,13 @@ def test_driver_refuses_offline_transport_and_has_no_fallback():
             d.step()
 
 
-@pytest.mark.parametrize("name,ndays,tol", [("sas_families", 12, 1e-10), ("sas_power", 5, 1e-10)])
+@pytest.mark.parametrize("name,ndays,tol", [("sas_families", 12, 1e-10), ("sas_power", 5, 1e-10), ("sas_bromide", 22, 1e-3)])
 def test_transport_driver_reproduces_reference_step(name, ndays, tol):
     """The offline oxygen-18 branch: an unmodified RogerSetup subclass of the reference stepped by `RogerSetup.step` and by
     `CudaTransportDriver.step` (oracle engine plugged in).  The reference runs on NumPy's default SVML `power` here, so
-    the power-law case is compared over the days before its first rounding-decided clamp."""
+    the power-law case is compared over the days before its first rounding-decided clamp; the bromide
+    case (exponent 0.1, clamp on day 14, solute pulse on day 17) is compared inside the reference's own libm envelope -- its
+    bit-for-bit pin is tests/test_sas_oracle_golden.py, where both sides call the same pow."""
     import make_sas_golden as mg
     import ref_harness as rh
     from oracle.engine import OracleSasEngine, lib
@@ -90,7 +92,8 @@ def test_transport_driver_reproduces_reference_step(name, ndays, tol):
 
     lib().roger_oracle_set_pow(0)
     case = mg.build(name)
-    Setup = rh.make_o18_setup(case)
+    bromide = case.get("solute") == "bromide"
+    Setup = rh.make_bromide_setup(case) if bromide else rh.make_o18_setup(case)
     ref = Setup()
     ref.setup()
     ref.warmup()
@@ -99,7 +102,10 @@ def test_transport_driver_reproduces_reference_step(name, ndays, tol):
     dut.warmup()
     driver = CudaTransportDriver(dut, engine_cls=OracleSasEngine)
     a, b = ref.state.variables, dut.state.variables
-    names = list(sas.STATE) + ["tt_" + p for p in sas.PROCESSES] + [n for n in sas.OUTPUTS if hasattr(a, n)]
+    meta = ref.state.var_meta
+    names = list(sas.STATE) + ["tt_" + p for p in sas.PROCESSES] + [n for n in sas.OUTPUTS if n in meta and meta[n].active]
+    if bromide:  # (the travel-time distributions of a power law with exponent 0.1 react to the libm by up to 3e-3: left out)
+        names = [n for n in names if n != "C_evap_soil" and not n.startswith("tt_")] + ["M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_rz", "M_ss", "M_s"]
     for day in range(ndays):
         ref.step(ref.state)
         driver.step()
@@ -107,5 +113,5 @@ def test_transport_driver_reproduces_reference_step(name, ndays, tol):
         for n in names:
             x, y = np.asarray(getattr(a, n))[2:-2, 2:-2], np.asarray(getattr(b, n))[2:-2, 2:-2]
             assert x.shape == y.shape
-            lim = 1e-9 if n.startswith("C_iso") else tol  # delta values amplify concentration rounding ~1e3
+            lim = max(1e-9, tol) if n.startswith("C_iso") else tol  # delta values amplify concentration rounding ~1e3
             assert rel_err(y, x) < lim, (day, n)
