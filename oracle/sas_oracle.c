@@ -475,14 +475,27 @@ static void anion_ageing(int A, double *sa, double *msa)
     msa[A - 1] += msam1_last;
 }
 
+static void flux_age_statistics(int A, const double *tt, const double *ages, double *work, double *st5, double *avg);
+static void storage_age_statistics(int A, const double *sa, double m, const double *ages, double *work, const double *pcts, int np_, double *stp,
+                                   double *avg);
+static double nan0(double x);
+
 static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss,
-                           const double *forcing, double m, const double *sas_params, double *out, double *tt_out, double *work, double *tmp)
+                           const double *forcing, double m, const double *sas_params, double *out, double *tt_out, double *work, double *tmp,
+                           double *stats, double *balance_prev, double *ttk, const double *ages)
 {
     const int A = c->A;
+    double sum_sa_s_m1 = 0;
+    if (stats) { /* vs.sa_s[taum1] as this step's soil kernel recomputes it */
+        for (int j = 0; j < A; j++) tmp[j] = s_rz[j] + s_ss[j] * m;
+        sum_sa_s_m1 = np_sum(tmp, A);
+    }
 #define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
 #define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
 #define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)
-#define TTO(p) (tt_out ? tt_out + ((size_t)(p) * (size_t)C + (size_t)i) * A : NULL)
+#define TTO(p) (tt_out ? tt_out + ((size_t)(p) * (size_t)C + (size_t)i) * A : \
+                (stats ? ((p) == RSP_evap_soil ? ttk : (p) == RSP_transp ? ttk + (A + 2) : (p) == RSP_q_ss ? ttk + 2 * (A + 2) : NULL) : NULL))
+#define ST(k) stats[(size_t)(k) * (size_t)C + (size_t)i]
     double *tt = work, *mtt = tt + (A + 2), *w2 = mtt + (A + 2);
     const double C_in = F(RSF_C_in);
     const double alpha_q = g_anion[1] ? g_anion[1][i] : 1.0;
@@ -583,6 +596,39 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
         const double M = np_nansum(msa_s, A, tmp) * m, S = np_sum(sa_s, A);
         O(RSO_C_iso_s) = M;
         O(RSO_C_s) = (S > 0) ? M / S : 0;
+        if (stats) { /* age statistics (water only, transport.py:59-312) and balance errors (numerics.py:424-445, :640-673) */
+            const double p5[5] = {0.1, 0.25, 0.5, 0.75, 0.9}, p3[3] = {0.25, 0.5, 0.75};
+            double s5[5], s3[3], avg, w[3];
+            const int procs[3] = {RSP_evap_soil, RSP_transp, RSP_q_ss};
+            const double flx[3] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_ss)};
+            for (int k = 0; k < 3; k++) {
+                const double *t = TTO(procs[k]);
+                for (int j = 0; j < A; j++) tmp[j] = flx[k] * t[j];
+                w[k] = np_sum(tmp, A);
+            }
+            flux_age_statistics(A, TTO(RSP_transp), ages, w2, s5, &avg);
+            for (int k = 0; k < 5; k++) ST(RSS_tt10_transp + k) = s5[k];
+            ST(RSS_ttavg_transp) = avg;
+            flux_age_statistics(A, TTO(RSP_q_ss), ages, w2, s5, &avg);
+            for (int k = 0; k < 5; k++) ST(RSS_tt10_q_ss + k) = s5[k];
+            ST(RSS_ttavg_q_ss) = avg;
+            storage_age_statistics(A, s_rz, m, ages, w2, p3, 3, s3, &avg);
+            for (int k = 0; k < 3; k++) ST(RSS_rt25_rz + k) = s3[k];
+            ST(RSS_rtavg_rz) = avg;
+            storage_age_statistics(A, s_ss, m, ages, w2, p3, 3, s3, &avg);
+            for (int k = 0; k < 3; k++) ST(RSS_rt25_ss + k) = s3[k];
+            ST(RSS_rtavg_ss) = avg;
+            storage_age_statistics(A, sa_s, m, ages, w2, p5, 5, s5, &avg);
+            for (int k = 0; k < 5; k++) ST(RSS_rt10_s + k) = s5[k];
+            ST(RSS_rtavg_s) = avg;
+            double *bp_C = balance_prev + i;
+            ST(RSS_dS_num_error) = fabs((S - sum_sa_s_m1) - (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - w[0] - w[1] - w[2]) * 1.0);
+            ST(RSS_dC_num_error) = fabs((S * O(RSO_C_s) - sum_sa_s_m1 * *bp_C) -
+                                        (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                                         F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss))) * 1.0);
+            ST(RSS_sanity_ok) = NAN; /* the anion branch of numerics.sanity_check is not restated */
+            *bp_C = O(RSO_C_s);
+        }
     }
     anion_ageing(A, s_rz, ms_rz);
     anion_ageing(A, s_ss, ms_ss);
@@ -590,6 +636,7 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
 #undef O
 #undef SP
 #undef TTO
+#undef ST
 }
 
 void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
@@ -622,7 +669,7 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
             double *s_rz = sa_rz + (size_t)i * A, *s_ss = sa_ss + (size_t)i * A;
             double *ms_rz = msa_rz + (size_t)i * A, *ms_ss = msa_ss + (size_t)i * A;
             if (st->solute == 1) {
-                anion_day_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out, work, tmp);
+                anion_day_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out, work, tmp, stats, balance_prev, ttk, ages);
                 continue;
             }
 #define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]

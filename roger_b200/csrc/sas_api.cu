@@ -149,9 +149,11 @@ k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double*
 }
 
 // One daily step of the conservative-anion transport (bromide / chloride), one thread per cell.
+template <bool STATS>
 __global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
 k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
-                const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap) {
+                const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap,
+                double* __restrict__ stats, double* __restrict__ C_s_prev) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
     __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
     for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
@@ -162,7 +164,7 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
-    anion_day(cx, forcing, mask[i], sas_params, ap, out);
+    anion_day<STATS>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev);
 }
 
 // (cells, A) row-major staging block <-> age-major planes, 32 x 32 tiles through shared memory
@@ -344,8 +346,6 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_sas_create: bad argument");
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
     if (settings->solute != 0 && settings->solute != 1) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope) or 1 (anion)");
-    if (settings->solute == 1 && settings->age_statistics)
-        return fail(ROGER_ENOTSUP, "roger_sas_create: age statistics are implemented for the isotope transport only");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -481,7 +481,12 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     if (h->st.solute == 1) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
-        k_sas_day_anion<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out, ap);
+        if (h->st.age_statistics)
+            k_sas_day_anion<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
+                                                                     h->d_out, ap, h->d_stats, h->d_C_s_prev);
+        else
+            k_sas_day_anion<false><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
+                                                                      h->d_out, ap, nullptr, nullptr);
     } else if (h->st.age_statistics)
         k_sas_day<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
                                                            h->d_stats, h->d_C_s_prev, h->d_bounds, h->atol, h->rtol);

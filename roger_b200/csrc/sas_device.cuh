@@ -664,8 +664,9 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
 // ================================================================================================================
 // One flux out of layer `src`: water by the SAS solver, solute as mtt = clip(msa / sa * alpha * tt * flux, 0, msa); the
 // receiving layer (dst >= 0) takes both.  with_solute = false is the water-only soil evaporation.  Returns sum(mtt).
+template <bool STATS>
 __device__ __noinline__ double anion_withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
-                                                double m, double alpha, bool with_solute, int process) {
+                                                double m, double alpha, bool with_solute, int process, FluxStats* fs) {
     const SasParams& P = cx.P;
     const int A = P.A;
     double* __restrict__ sa = cx.pl.sa[src];
@@ -678,8 +679,18 @@ __device__ __noinline__ double anion_withdrawal(const CellCtx& cx, int src, int 
     double* __restrict__ tt_out = (P.store_tt && cx.pl.tt) ? cx.pl.tt + (size_t)process * (size_t)A * (size_t)C : nullptr;
     const double nsub = (double)P.substeps;
     double prev = 0. / nsub;
-    double sums[1];
-    stream_sums<1, 5>(cx.plan,
+    constexpr int NS = STATS ? 4 : 1;
+    double sums[NS];
+    PctTracker trk[STATS ? 5 : 1];
+    double cdf = 0;
+    NpMax cdf_max;
+    if (STATS) {
+        const double pcts[5] = {0.1, 0.25, 0.5, 0.75, 0.9};
+#pragma unroll
+        for (int k = 0; k < 5; k++) trk[k].init(pcts[k]);
+    }
+    bool first_bin = true;
+    stream_sums<NS, 5>(cx.plan,
         [&](int j, double* L) {
             const int64_t o = cx.ring(j);
             L[0] = active ? TTn[cx.lin(j)] : 0.;
@@ -707,6 +718,15 @@ __device__ __noinline__ double anion_withdrawal(const CellCtx& cx, int src, int 
                 msa[o] = ms_j + -mtt * m;
             }
             v[0] = mtt;
+            if (STATS) {
+                v[1] = t;
+                v[2] = flux * t;
+                v[3] = (double)(j + 1) * t;
+                cdf += t;
+                if (first_bin) { cdf_max.init(cdf); first_bin = false; } else cdf_max.push(cdf);
+#pragma unroll
+                for (int k = 0; k < 5; k++) trk[k].push(j, cdf);
+            }
             double u = s_j + -flux * t;
             u = ((u > -1e-5) && (u < 0)) ? 0 : u;
             sa[o] = u * m;
@@ -716,8 +736,17 @@ __device__ __noinline__ double anion_withdrawal(const CellCtx& cx, int src, int 
             }
             if (tt_out) tt_out[cx.lin(j)] = t;
         }, sums);
+    if (STATS && fs) {
+        fs->wsum = sums[2];
+#pragma unroll
+        for (int k = 0; k < 5; k++) fs->pct[k] = trk[k].result(A, cdf_max.get());
+        fs->avg = (sums[1] > 0) ? sums[3] : __longlong_as_double(0x7ff8000000000000LL);
+    }
     return sums[0];
 }
+
+__device__ __noinline__ void storage_age_statistics(const CellCtx& cx, int which, double m, int n_pct, const double* pcts, double* pct_out,
+                                                    double* avg_out);
 
 struct AnionParams {  // per-cell planes (may be null: alpha = 1, no crops)
     const double* alpha_transp;
@@ -726,8 +755,9 @@ struct AnionParams {  // per-cell planes (may be null: alpha = 1, no crops)
     const double* S_sat_rz;
 };
 
+template <bool STATS>
 __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
-                                          const AnionParams ap, double* __restrict__ out) {
+                                          const AnionParams ap, double* __restrict__ out, double* __restrict__ stats, double* __restrict__ C_s_prev) {
     const SasParams& P = cx.P;
     const int A = P.A;
     const int64_t C = P.C, i = cx.i;
@@ -741,14 +771,25 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
     const double C_in = F(RSF_C_in);
     const double alpha_q = ap.alpha_q ? ap.alpha_q[i] : 1.0;
     const int64_t o0 = cx.ring(0);
+    double sum_sa_s_m1 = 0;
+    if (STATS) {  // vs.sa_s[taum1] as this step's soil kernel recomputes it
+        double sm[1];
+        stream_sums<1, 2>(cx.plan,
+            [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = s_rz[o]; L[1] = s_ss[o]; },
+            [&](int, const double* L, double* v) { v[0] = L[0] + L[1] * m; }, sm);
+        sum_sa_s_m1 = sm[0];
+    }
+    FluxStats fs_evap, fs_transp, fs_qss;
+    double C_transp_v = 0, C_q_ss_v = 0, C_inf1 = 0, C_inf2 = 0, C_inf3 = 0;
     {   // infiltration into the root zone
         const double c1 = ((F(RSF_inf_mat_rz) > 0) ? C_in : 0) * m, c2 = ((F(RSF_inf_pf_rz) > 0) ? C_in : 0) * m;
         const double M1 = c1 * F(RSF_inf_mat_rz) * m, M2 = c2 * F(RSF_inf_pf_rz) * m;
         O(RSO_C_inf_mat_rz) = c1; O(RSO_C_inf_pf_rz) = c2; O(RSO_C_iso_inf_mat_rz) = M1; O(RSO_C_iso_inf_pf_rz) = M2;
+        C_inf1 = c1; C_inf2 = c2;
         s_rz[o0] = s_rz[o0] + (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) * m);
         m_rz[o0] = m_rz[o0] + (M1 + M2 * m);
     }
-    anion_withdrawal(cx, 0, -1, F(RSF_evap_soil), SP(RSP_evap_soil), C, m, 0.0, false, RSP_evap_soil);  // water only
+    anion_withdrawal<STATS>(cx, 0, -1, F(RSF_evap_soil), SP(RSP_evap_soil), C, m, 0.0, false, RSP_evap_soil, &fs_evap);  // water only
     O(RSO_C_evap_soil) = 0; O(RSO_C_iso_evap_soil) = 0;
     {   // transpiration: crop nutrient uptake stops above 80 % saturation (evapotranspiration.py:931-938)
         const double lu = ap.lu_id ? ap.lu_id[i] : 0.0;
@@ -760,12 +801,13 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
             crop_wet = sm[0] >= 0.8 * sat;
         }
         const double alpha = (crop_wet ? 0 : (ap.alpha_transp ? ap.alpha_transp[i] : 1.0)) * m;
-        const double M = anion_withdrawal(cx, 0, -1, F(RSF_transp), SP(RSP_transp), C, m, alpha, true, RSP_transp);
-        O(RSO_C_transp) = ((F(RSF_transp) > 0) ? M / F(RSF_transp) : 0) * m;
+        const double M = anion_withdrawal<STATS>(cx, 0, -1, F(RSF_transp), SP(RSP_transp), C, m, alpha, true, RSP_transp, &fs_transp);
+        C_transp_v = ((F(RSF_transp) > 0) ? M / F(RSF_transp) : 0) * m;
+        O(RSO_C_transp) = C_transp_v;
         O(RSO_C_iso_transp) = M * m;
     }
     {
-        const double M = anion_withdrawal(cx, 0, 1, F(RSF_q_rz), SP(RSP_q_rz), C, m, alpha_q, true, RSP_q_rz);
+        const double M = anion_withdrawal<STATS>(cx, 0, 1, F(RSF_q_rz), SP(RSP_q_rz), C, m, alpha_q, true, RSP_q_rz, nullptr);
         O(RSO_C_q_rz) = ((F(RSF_q_rz) > 0) ? M / F(RSF_q_rz) : 0) * m;
         O(RSO_C_iso_q_rz) = M * m;
     }
@@ -773,16 +815,18 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
         const double c3 = ((F(RSF_inf_pf_ss) > 0) ? C_in : 0) * m;
         const double M3 = c3 * F(RSF_inf_pf_ss) * m;
         O(RSO_C_inf_pf_ss) = c3; O(RSO_C_iso_inf_pf_ss) = M3;
+        C_inf3 = c3;
         s_ss[o0] = s_ss[o0] + F(RSF_inf_pf_ss) * m;
         m_ss[o0] = m_ss[o0] + M3 * m;
     }
     {
-        const double M = anion_withdrawal(cx, 1, -1, F(RSF_q_ss), SP(RSP_q_ss), C, m, alpha_q, true, RSP_q_ss);
-        O(RSO_C_q_ss) = ((F(RSF_q_ss) > 0) ? M / F(RSF_q_ss) : 0) * m;
+        const double M = anion_withdrawal<STATS>(cx, 1, -1, F(RSF_q_ss), SP(RSP_q_ss), C, m, alpha_q, true, RSP_q_ss, &fs_qss);
+        C_q_ss_v = ((F(RSF_q_ss) > 0) ? M / F(RSF_q_ss) : 0) * m;
+        O(RSO_C_q_ss) = C_q_ss_v;
         O(RSO_C_iso_q_ss) = M * m;
     }
     {
-        const double M = anion_withdrawal(cx, 1, 0, F(RSF_cpr_rz), SP(RSP_cpr_rz), C, m, alpha_q, true, RSP_cpr_rz);
+        const double M = anion_withdrawal<STATS>(cx, 1, 0, F(RSF_cpr_rz), SP(RSP_cpr_rz), C, m, alpha_q, true, RSP_cpr_rz, nullptr);
         O(RSO_C_cpr_rz) = ((F(RSF_cpr_rz) > 0) ? M / F(RSF_cpr_rz) : 0) * m;
         O(RSO_C_iso_cpr_rz) = M * m;
     }
@@ -812,7 +856,35 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
         const double M_rz = sums[0] * m, M_ss = sums[2] * m, M_s = sums[4] * m;
         O(RSO_C_iso_rz) = M_rz; O(RSO_C_rz) = (sums[1] > 0) ? M_rz / sums[1] : 0;
         O(RSO_C_iso_ss) = M_ss; O(RSO_C_ss) = (sums[3] > 0) ? M_ss / sums[3] : 0;
-        O(RSO_C_iso_s) = M_s;   O(RSO_C_s) = (sums[5] > 0) ? M_s / sums[5] : 0;
+        const double C_s = (sums[5] > 0) ? M_s / sums[5] : 0;
+        O(RSO_C_iso_s) = M_s;   O(RSO_C_s) = C_s;
+        if (STATS) {  // age statistics (water only) and balance errors (numerics.py:424-445, :640-673)
+#define ST(k) stats[(int64_t)(k) * C + i]
+            for (int k = 0; k < 5; k++) { ST(RSS_tt10_transp + k) = fs_transp.pct[k]; ST(RSS_tt10_q_ss + k) = fs_qss.pct[k]; }
+            ST(RSS_ttavg_transp) = fs_transp.avg;
+            ST(RSS_ttavg_q_ss) = fs_qss.avg;
+            const double p5[5] = {0.1, 0.25, 0.5, 0.75, 0.9}, p3[3] = {0.25, 0.5, 0.75};
+            double pc[5], avg;
+            storage_age_statistics(cx, 0, m, 3, p3, pc, &avg);
+            for (int k = 0; k < 3; k++) ST(RSS_rt25_rz + k) = pc[k];
+            ST(RSS_rtavg_rz) = avg;
+            storage_age_statistics(cx, 1, m, 3, p3, pc, &avg);
+            for (int k = 0; k < 3; k++) ST(RSS_rt25_ss + k) = pc[k];
+            ST(RSS_rtavg_ss) = avg;
+            storage_age_statistics(cx, 2, m, 5, p5, pc, &avg);
+            for (int k = 0; k < 5; k++) ST(RSS_rt10_s + k) = pc[k];
+            ST(RSS_rtavg_s) = avg;
+            auto nan0 = [](double x) { return (x != x) ? 0.0 : x; };
+            const double Cp = C_s_prev[i];
+            ST(RSS_dS_num_error) = fabs((sums[5] - sum_sa_s_m1) -
+                                        (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - fs_evap.wsum - fs_transp.wsum - fs_qss.wsum) * 1.0);
+            ST(RSS_dC_num_error) = fabs((sums[5] * C_s - sum_sa_s_m1 * Cp) -
+                                        (F(RSF_inf_mat_rz) * nan0(C_inf1) + F(RSF_inf_pf_rz) * nan0(C_inf2) + F(RSF_inf_pf_ss) * nan0(C_inf3) -
+                                         fs_transp.wsum * nan0(C_transp_v) - fs_qss.wsum * nan0(C_q_ss_v)) * 1.0);
+            ST(RSS_sanity_ok) = __longlong_as_double(0x7ff8000000000000LL);  // the anion branch of sanity_check is not evaluated
+            C_s_prev[i] = C_s;
+#undef ST
+        }
     }
     {   // ageing (transport.py:622-679) as a rotation of the plane ring: the oldest two bins merge, bin 0 is emptied
         const int b_new = (P.base == 0) ? A - 1 : P.base - 1;

@@ -42,7 +42,7 @@ CASES = {
     "sas_power_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=105, age_statistics=True,
                             sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     # conservative anion (bromide): solute mass per age bin, partition coefficients, a crop cell whose uptake stops when wet
-    "sas_bromide": dict(shape=(2, 3), ndays=26, ages=50, doy=100, solute="bromide",
+    "sas_bromide": dict(shape=(2, 3), ndays=26, ages=50, doy=100, solute="bromide", age_statistics=True,
                         sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
     # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
     "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
@@ -120,9 +120,9 @@ def run(name, simd_out=None):
         scal_vars = ["C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz", "C_inf_mat_rz", "C_inf_pf_rz", "C_inf_pf_ss", "C_in",
                      "M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_inf_mat_rz", "M_inf_pf_rz", "M_inf_pf_ss"]
         lvl_vars = ["C_rz", "C_ss", "C_s", "M_rz", "M_ss", "M_s"]
-    if case["age_statistics"]:
-        from roger_b200 import sas as _sas
+    from roger_b200 import sas as _sas
 
+    if case["age_statistics"]:
         scal_vars = scal_vars + [n for n in _sas.STATISTICS if n != "sanity_ok"]
 
     def grab():

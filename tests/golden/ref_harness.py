@@ -474,7 +474,7 @@ def make_bromide_setup(case):
             s.enable_offline_transport = True
             s.enable_bromide = True
             s.tm_structure = "power"
-            s.enable_age_statistics = False
+            s.enable_age_statistics = bool(case.get("age_statistics", False))
 
         @roger_routine
         def read_data(self, state):

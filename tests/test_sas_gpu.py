@@ -303,7 +303,8 @@ def test_anion_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, ora
               S_sat_rz=daily["S_RZ"][:, 0] * rng.uniform(0.9, 2.0, C_))
     mask = np.ones(C_)
     mask[3::11] = 0.0
-    models = [sas.SasModel(e, C_, A, daily, spec, store_tt=True, mask=mask, solute=sas.ANION, anion_parameters=ap) for e in (_cuda(), oracle_roger_pow)]
+    models = [sas.SasModel(e, C_, A, daily, spec, store_tt=True, mask=mask, solute=sas.ANION, anion_parameters=ap, age_statistics=(A != 513))
+              for e in (_cuda(), oracle_roger_pow)]
     for m in models:
         m.setup()
     u.replay_pair(models[0], models[1], ndays, exact=True)
