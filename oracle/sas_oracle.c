@@ -165,6 +165,24 @@ static void sas_power(const sas_ctx *c, const double *SA, double *sp, double m, 
     for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
 }
 
+/* the sum of the SAS families in the reference's order (transport.py:399-428 and calc_TT_num :866-892) */
+static void sas_sum_families(const sas_ctx *c, const double *SA, double *sp, double m, double *TT, double *Om)
+{
+    const int N = c->A + 1;
+    for (int j = 0; j < N; j++) TT[j] = 0;
+    sas_uniform(c, SA, sp, m, Om);
+    for (int j = 0; j < N; j++) TT[j] += Om[j];
+    sas_dirac(c, SA, sp, m, Om);
+    for (int j = 0; j < N; j++) TT[j] += Om[j];
+    sas_kumaraswami(c, SA, sp, m, Om);
+    for (int j = 0; j < N; j++) TT[j] += Om[j];
+    /* gamma family (id 4) not restated: contributes 0 for every other id */
+    sas_exponential(c, SA, sp, m, Om);
+    for (int j = 0; j < N; j++) TT[j] += Om[j];
+    sas_power(c, SA, sp, m, Om);
+    for (int j = 0; j < N; j++) TT[j] += Om[j];
+}
+
 /* transport.py:343-359 */
 static void calc_SA(int A, const double *sa, double *SA)
 {
@@ -187,18 +205,7 @@ static void calc_tt(const sas_ctx *c, const double *SA_in, const double *sa, dou
     memset(TTn, 0, sizeof(double) * N);
     const double h = 1.0 / c->substeps;
     for (int s = 0; s < c->substeps; s++) {
-        for (int j = 0; j < N; j++) TTi[j] = 0;
-        sas_uniform(c, SAn, sp, m, Om);
-        for (int j = 0; j < N; j++) TTi[j] += Om[j];
-        sas_dirac(c, SAn, sp, m, Om);
-        for (int j = 0; j < N; j++) TTi[j] += Om[j];
-        sas_kumaraswami(c, SAn, sp, m, Om);
-        for (int j = 0; j < N; j++) TTi[j] += Om[j];
-        /* gamma family (id 4) not restated: contributes 0 for every other id */
-        sas_exponential(c, SAn, sp, m, Om);
-        for (int j = 0; j < N; j++) TTi[j] += Om[j];
-        sas_power(c, SAn, sp, m, Om);
-        for (int j = 0; j < N; j++) TTi[j] += Om[j];
+        sas_sum_families(c, SAn, sp, m, TTi, Om);
         for (int j = 0; j < A; j++) {
             double d = TTi[j + 1] - TTi[j];
             tti[j] = (d >= 0) ? d : 0;
@@ -639,6 +646,194 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
 #undef ST
 }
 
+
+/* ---- explicit Euler solver (settings.sas_solver = "Euler"), isotope branch --------------------------------------------
+ * svat_transport_model_euler (transport.py:2063-2413) with calc_TT_num (:859-907) and calc_TT_num_nonneg (:910-945);
+ * driven `substeps` times per day by calculate_storage_selection (:3221-3258) with settings.h = 1 / substeps. */
+
+/* backward travel-time distribution of one flux from the StorAge snapshot SA (nages points) */
+static void euler_tt(const sas_ctx *c, const double *SA, const double *sas_params, double fh, double m, double *tt, double *work)
+{
+    const int A = c->A, N = A + 1;
+    double *TTq = work, *Om = TTq + N, *ttq = Om + N, *TTn = ttq + N;
+    double sp[8];
+    memcpy(sp, sas_params, sizeof(sp));
+    sas_sum_families(c, SA, sp, m, TTq, Om);
+    for (int j = 0; j < N; j++) TTq[j] = (fh <= 0) ? 0 : TTq[j];
+    for (int j = 0; j < A; j++) {
+        const double sa_d = SA[j + 1] - SA[j];
+        double q = (TTq[j + 1] - TTq[j]) * fh;
+        q = (sa_d + q < 0) ? -sa_d : q;
+        q = (q == 0) ? 0.0 : q; /* where(ttq == -0, 0, ttq): both zeros become +0 */
+        ttq[j] = q;
+    }
+    const double ssum = np_sum(ttq, A);
+    for (int j = 0; j < A; j++) ttq[j] = (ttq[j] > 0) ? ttq[j] / ssum : 0;
+    TTn[0] = 0;
+    {
+        double acc = ttq[0];
+        TTn[1] = acc;
+        for (int j = 1; j < A; j++) { acc += ttq[j]; TTn[j + 1] = acc; }
+    }
+    for (int j = 0; j < A; j++) {
+        const double d = TTn[j + 1] - TTn[j];
+        tt[j] = (d >= 0) ? d : 0;
+    }
+}
+
+/* isotope mixing of an inflow dsa1 carrying dmsa1 into one bin: the two-statement update of transport.py:2115-2130 /
+ * :2278-2293; `need_pos` is the extra (msa > 0) condition the root-zone statements carry */
+static double euler_mix(double msa, double sa, double dsa1, double dmsa1, int need_pos)
+{
+    const double tot = dsa1 + sa;
+    const int c1 = need_pos ? ((tot > 0) && (msa > 0)) : (tot > 0);
+    double v = (c1 ? msa * (sa / tot) : 0) + ((tot > 0) ? dmsa1 * (dsa1 / tot) : 0);
+    v = ((dsa1 > 0) && (v <= 0)) ? dmsa1 : v;
+    return v;
+}
+
+static double euler_flux_conc(int A, const double *mtt, const double *tt, double *tmp)
+{ /* calc_conc_iso_flux transport.py:512-535 */
+    for (int j = 0; j < A; j++) tmp[j] = mtt[j] * tt[j];
+    const double st = np_sum(tt, A);
+    double conc = (st > 0) ? np_sum(tmp, A) / st : NAN;
+    return (conc != 0) ? conc : NAN;
+}
+
+static void euler_substep_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss,
+                               const double *forcing, double m, const double *sas_params, double *out, double *tt_out, double *work)
+{
+#define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
+#define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
+#define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)
+    const int A = c->A, N = A + 1;
+    const double h = 1.0 / c->substeps;
+    double *SA_rz = work, *SA_ss = SA_rz + N, *tt_e = SA_ss + N, *tt_t = tt_e + N, *tt_q = tt_t + N, *tt_c = tt_q + N, *tt_s = tt_c + N;
+    double *tmp = tt_s + N, *mtt = tmp + N, *w2 = mtt + N;
+    const double inf_mat = F(RSF_inf_mat_rz), inf_pf = F(RSF_inf_pf_rz), inf_ss = F(RSF_inf_pf_ss), C_in = F(RSF_C_in);
+    const double evap = F(RSF_evap_soil), transp = F(RSF_transp), q_rz = F(RSF_q_rz), q_ss = F(RSF_q_ss), cpr = F(RSF_cpr_rz);
+    /* upper boundary condition :2071-2143: infiltration enters age bin 0 */
+    for (int j = 0; j < A; j++) {
+        const double tt_im = (j == 0) ? ((inf_mat > 0) ? 1 : 0) * m : 0.0, tt_ip = (j == 0) ? ((inf_pf > 0) ? 1 : 0) * m : 0.0;
+        const double tt_is = (j == 0) ? ((inf_ss > 0) ? 1 : 0) * m : 0.0;
+        const double mtt_im = (j == 0) ? ((inf_mat > 0) ? C_in : 0) * m : 0.0, mtt_ip = (j == 0) ? ((inf_pf > 0) ? C_in : 0) * m : 0.0;
+        const double mtt_is = (j == 0) ? ((inf_ss > 0) ? C_in : 0) * m : 0.0;
+        const double dsa_rz = (inf_mat * tt_im + inf_pf * tt_ip) * h;
+        const double dsa_ss = (inf_ss * tt_is) * h;
+        const double dmsa_rz1 = nan0(mtt_im) * ((dsa_rz > 0) ? ((inf_mat * tt_im * h) / dsa_rz) : 0) +
+                                nan0(mtt_ip) * ((dsa_rz > 0) ? ((inf_pf * tt_ip * h) / dsa_rz) : 0);
+        const double dmsa_ss1 = nan0(mtt_is) * ((dsa_ss > 0) ? ((inf_ss * tt_is * h) / dsa_ss) : 0);
+        ms_rz[j] = euler_mix(ms_rz[j], s_rz[j], dsa_rz, dmsa_rz1, 1);
+        ms_ss[j] = euler_mix(ms_ss[j], s_ss[j], dsa_ss, dmsa_ss1, 0);
+        s_rz[j] += dsa_rz;
+        s_ss[j] += dsa_ss;
+        ms_rz[j] = (s_rz[j] <= 0) ? 0 : ms_rz[j];
+        ms_ss[j] = (s_ss[j] <= 0) ? 0 : ms_ss[j];
+    }
+    calc_SA(A, s_rz, SA_rz);
+    for (int j = 0; j < N; j++) SA_rz[j] = SA_rz[j] * m;
+    calc_SA(A, s_ss, SA_ss);
+    for (int j = 0; j < N; j++) SA_ss[j] = SA_ss[j] * m;
+    /* travel-time distributions of the five fluxes from the same snapshot :2157-2250 */
+    euler_tt(c, SA_rz, SP(RSP_evap_soil), evap * h, m, tt_e, w2);
+    euler_tt(c, SA_rz, SP(RSP_transp), transp * h, m, tt_t, w2);
+    euler_tt(c, SA_rz, SP(RSP_q_rz), q_rz * h, m, tt_q, w2);
+    euler_tt(c, SA_ss, SP(RSP_cpr_rz), cpr * h, m, tt_c, w2);
+    euler_tt(c, SA_ss, SP(RSP_q_ss), q_ss * h, m, tt_s, w2);
+    /* flux concentrations :2322-2357 (calc_mtt isotope branch :575-580: mtt = where(tt > 0, msa, 0)) + delta_fluxes_svat :3659 */
+    {
+        const double *tts[5] = {tt_e, tt_t, tt_q, tt_c, tt_s};
+        const double *src[5] = {ms_rz, ms_rz, ms_rz, ms_ss, ms_ss};
+        const int oc[5] = {RSO_C_evap_soil, RSO_C_transp, RSO_C_q_rz, RSO_C_cpr_rz, RSO_C_q_ss};
+        const int oi[5] = {RSO_C_iso_evap_soil, RSO_C_iso_transp, RSO_C_iso_q_rz, RSO_C_iso_cpr_rz, RSO_C_iso_q_ss};
+        const int pr[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
+        for (int k = 0; k < 5; k++) {
+            for (int j = 0; j < A; j++) mtt[j] = (tts[k][j] > 0) ? src[k][j] : 0;
+            O(oc[k]) = euler_flux_conc(A, mtt, tts[k], tmp) * m;
+            O(oi[k]) = conc_to_delta(c, O(oc[k])) * m;
+            if (tt_out) memcpy(tt_out + ((size_t)pr[k] * (size_t)C + (size_t)i) * A, tts[k], sizeof(double) * A);
+        }
+        O(RSO_C_inf_mat_rz) = ((inf_mat > 0) ? C_in : NAN) * m;
+        O(RSO_C_inf_pf_rz) = ((inf_pf > 0) ? C_in : NAN) * m;
+        O(RSO_C_inf_pf_ss) = ((inf_ss > 0) ? C_in : NAN) * m;
+        O(RSO_C_iso_inf_mat_rz) = conc_to_delta(c, O(RSO_C_inf_mat_rz)) * m;
+        O(RSO_C_iso_inf_pf_rz) = conc_to_delta(c, O(RSO_C_inf_pf_rz)) * m;
+        O(RSO_C_iso_inf_pf_ss) = conc_to_delta(c, O(RSO_C_inf_pf_ss)) * m;
+    }
+    /* update StorAge :2266-2319 */
+    for (int j = 0; j < A; j++) {
+        const double mtt_c = (tt_c[j] > 0) ? ms_ss[j] : 0, mtt_q = (tt_q[j] > 0) ? ms_rz[j] : 0;
+        double dsa_rz = (cpr * tt_c[j] - evap * tt_e[j] - transp * tt_t[j] - q_rz * tt_q[j]) * h;
+        dsa_rz = (s_rz[j] + dsa_rz < 0) ? -s_rz[j] : dsa_rz;
+        double dsa_ss = (q_rz * tt_q[j] - cpr * tt_c[j] - q_ss * tt_s[j]) * h;
+        dsa_ss = (s_ss[j] + dsa_ss < 0) ? -s_ss[j] : dsa_ss;
+        const double dsa_rz1 = (cpr * tt_c[j]) * h;
+        const double dmsa_rz1 = nan0(mtt_c) * ((dsa_rz1 > 0) ? ((cpr * tt_c[j] * h) / dsa_rz1) : 0);
+        const double dsa_ss1 = (q_rz * tt_q[j]) * h;
+        const double dmsa_ss1 = nan0(mtt_q) * ((dsa_ss1 > 0) ? ((q_rz * tt_q[j] * h) / dsa_ss1) : 0);
+        ms_rz[j] = euler_mix(ms_rz[j], s_rz[j], dsa_rz1, dmsa_rz1, 1);
+        ms_ss[j] = euler_mix(ms_ss[j], s_ss[j], dsa_ss1, dmsa_ss1, 0);
+        s_rz[j] += dsa_rz;
+        s_ss[j] += dsa_ss;
+        ms_rz[j] = (s_rz[j] <= 0) ? 0 : ms_rz[j];
+        ms_ss[j] = (s_ss[j] <= 0) ? 0 : ms_ss[j];
+    }
+#undef F
+#undef O
+#undef SP
+}
+
+/* storage kernels root_zone.py:189-215, subsoil.py:153-180, soil.py:1036-1092 (run after every Euler sub-step) */
+static void storage_kernels_iso(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, const double *ms_rz, const double *ms_ss,
+                                double m, double *out, double *tmp)
+{
+#define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
+    const int A = c->A;
+    for (int j = 0; j < A; j++) s_rz[j] = (s_rz[j] < 1e-8) ? 0 : s_rz[j];
+    O(RSO_C_rz) = storage_conc(c, s_rz, ms_rz, tmp) * m;
+    O(RSO_C_iso_rz) = conc_to_delta(c, O(RSO_C_rz)) * m;
+    for (int j = 0; j < A; j++) s_ss[j] = (s_ss[j] < 1e-8) ? 0 : s_ss[j];
+    O(RSO_C_ss) = storage_conc(c, s_ss, ms_ss, tmp) * m;
+    O(RSO_C_iso_ss) = conc_to_delta(c, O(RSO_C_ss)) * m;
+    double *sa_s = tmp + (A + 2), *msa_s = sa_s + (A + 2);
+    for (int j = 0; j < A; j++) {
+        sa_s[j] = s_rz[j] + s_ss[j] * m;
+        const double tot = s_rz[j] + s_ss[j];
+        const double v = (tot > 0) ? ms_rz[j] * (s_rz[j] / tot) + ms_ss[j] * (s_ss[j] / tot) : 0;
+        msa_s[j] = isnan(v) ? 0 : v;
+    }
+    O(RSO_C_s) = storage_conc(c, sa_s, msa_s, tmp) * m;
+    O(RSO_C_iso_s) = conc_to_delta(c, O(RSO_C_s)) * m;
+#undef O
+}
+
+/* one day = `substeps` explicit Euler steps of every cell, ageing with the last one (transport.py:3221-3258) */
+static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
+                      const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out)
+{
+    sas_ctx ctx = {st->ages, st->substeps, st->VSMOW_conc18O, st->d18O_min, st->d18O_max};
+    const int A = ctx.A;
+#pragma omp parallel
+    {
+        double *work = (double *)malloc(sizeof(double) * (size_t)(16 * (A + 2)));
+        double *tmp = (double *)malloc(sizeof(double) * (size_t)(4 * (A + 2)));
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < C; i++) {
+            const double m = mask[i];
+            double *s_rz = sa_rz + (size_t)i * A, *s_ss = sa_ss + (size_t)i * A;
+            double *ms_rz = msa_rz + (size_t)i * A, *ms_ss = msa_ss + (size_t)i * A;
+            for (int s = 0; s < ctx.substeps; s++) {
+                euler_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out, work);
+                storage_kernels_iso(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
+            }
+            ageing(A, s_rz, ms_rz);
+            ageing(A, s_ss, ms_ss);
+        }
+        free(work);
+        free(tmp);
+    }
+}
+
 void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
                           const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
                           double *stats, double *balance_prev);
@@ -654,6 +849,10 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
                           const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
                           double *stats, double *balance_prev)
 {
+    if (st->solver == 1) { /* explicit Euler: isotope branch, no statistics (callers check) */
+        euler_day(C, st, sa_rz, sa_ss, msa_rz, msa_ss, forcing, mask, sas_params, out, tt_out);
+        return;
+    }
     sas_ctx ctx = {st->ages, st->substeps, st->VSMOW_conc18O, st->d18O_min, st->d18O_max};
     const int A = ctx.A;
 #pragma omp parallel

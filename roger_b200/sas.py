@@ -28,14 +28,15 @@ D18O_MIN, D18O_MAX = -20.0, 0.0
 class SasSettings(C.Structure):
     _fields_ = [("ages", C.c_int32), ("substeps", C.c_int32), ("VSMOW_conc18O", C.c_double), ("d18O_min", C.c_double),
                 ("d18O_max", C.c_double), ("store_tt", C.c_int32), ("age_statistics", C.c_int32), ("solute", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("solver", C.c_int32)]
 
 
 ISOTOPE, ANION = 0, 1
+DETERMINISTIC, EULER = 0, 1  # settings.sas_solver of the reference (roger/settings.py)
 
 
-def default_settings(ages, substeps=6, store_tt=False, age_statistics=False, solute=ISOTOPE):
-    return SasSettings(int(ages), int(substeps), VSMOW_conc18O, D18O_MIN, D18O_MAX, int(store_tt), int(age_statistics), int(solute), 0)
+def default_settings(ages, substeps=6, store_tt=False, age_statistics=False, solute=ISOTOPE, solver=DETERMINISTIC):
+    return SasSettings(int(ages), int(substeps), VSMOW_conc18O, D18O_MIN, D18O_MAX, int(store_tt), int(age_statistics), int(solute), int(solver))
 
 
 def delta_to_conc(delta):
@@ -76,7 +77,7 @@ def initial_age_distribution(S, ages):
 
 class SasModel:
     def __init__(self, engine_cls, n_cells, ages, daily, sas_spec, d18O_soil=-10.0, mask=None, substeps=6, store_tt=False,
-                 engine_kwargs=None, age_statistics=False, solute=ISOTOPE, anion_parameters=None):
+                 engine_kwargs=None, age_statistics=False, solute=ISOTOPE, anion_parameters=None, solver=DETERMINISTIC):
         """daily: dict of (n_cells, ndays + 1) arrays PREC, INF_MAT_RZ, INF_PF_RZ, INF_PF_SS, TRANSP, EVAP_SOIL, CPR_RZ,
         Q_RZ, Q_SS, S_RZ, S_SS, S_SNOW, C_ISO_IN (index 0 = initial state, as in the reference's SVAT.nc)."""
         self.C = int(n_cells)
@@ -85,7 +86,7 @@ class SasModel:
         self.solute = int(solute)
         # anion transport (roger/models/svat_bromide): dict alpha_transp, alpha_q, lu_id, S_sat_rz of n_cells values each
         self.anion_parameters = anion_parameters
-        self.settings = default_settings(ages, substeps, store_tt, age_statistics, solute)
+        self.settings = default_settings(ages, substeps, store_tt, age_statistics, solute, solver)
         self.engine = engine_cls(self.C, self.settings, **(engine_kwargs or {}))
         self.mask = np.ones(self.C) if mask is None else np.asarray(mask, dtype=np.float64)
         self.sas_params = sas_parameter_block(self.C, sas_spec)

@@ -47,6 +47,12 @@ CASES = {
     # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
     "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
                          sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
+    # explicit Euler solver (settings.sas_solver = "Euler", 6 steps per day): benchmark power law; snow + variable input with mixed families
+    "sas_euler": dict(shape=(2, 3), ndays=24, ages=50, doy=100, sas_solver="Euler",
+                      sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
+    "sas_euler_families": dict(shape=(2, 2), ndays=22, ages=45, doy=20, sas_solver="Euler", var_input=True,
+                               sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0),
+                                        q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
 }
 
 
@@ -59,7 +65,8 @@ def build(name):
     svat = SvatModel(OracleSvatEngine, (nx, ny), forcing, prim, th_rz, th_ss)
     svat.setup()
     daily = sas_inputs.daily_fluxes_from_svat(svat, ndays)
-    case = dict(nx=nx, ny=ny, ndays=ndays, ages=ages, age_statistics=bool(c.get("age_statistics", False)))
+    case = dict(nx=nx, ny=ny, ndays=ndays, ages=ages, age_statistics=bool(c.get("age_statistics", False)),
+                sas_solver=c.get("sas_solver", "deterministic"))
     for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES):
         case[k] = daily[k].reshape(nx, ny, ndays + 1)
     for k in ("S_pwp_rz", "S_pwp_ss"):
@@ -171,6 +178,8 @@ def run(name, simd_out=None):
             out.update({k: z[k] for k in z.files})
     for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES) + ["C_ISO_IN"] + (["C_IN"] if bromide else []):
         out["in_" + k] = case[k].reshape(C, -1)
+    if case["sas_solver"] == "Euler":
+        out["solver"] = np.asarray(1)
     if bromide:
         out["solute"] = np.asarray(1)
         for k in ("alpha_transp", "alpha_q", "lu_id"):

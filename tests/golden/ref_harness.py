@@ -264,8 +264,10 @@ def make_o18_setup(case):
         def set_settings(self, state):
             s = state.settings
             s.identifier = "GOLDEN_O18"
-            s.sas_solver = "deterministic"
+            s.sas_solver = case.get("sas_solver", "deterministic")
             s.sas_solver_substeps = case.get("substeps", 6)
+            if s.sas_solver in ("RK4", "Euler"):  # roger/models/svat_oxygen18/svat_oxygen18.py:_set_settings
+                s.h = 1 / s.sas_solver_substeps
             s.nx, s.ny = nx, ny
             s.runlen = 24 * 60 * 60 * ndays
             s.runlen_warmup = 0
@@ -458,8 +460,10 @@ def make_bromide_setup(case):
         def set_settings(self, state):
             s = state.settings
             s.identifier = "GOLDEN_BR"
-            s.sas_solver = "deterministic"
+            s.sas_solver = case.get("sas_solver", "deterministic")
             s.sas_solver_substeps = case.get("substeps", 6)
+            if s.sas_solver in ("RK4", "Euler"):  # roger/models/svat_oxygen18/svat_oxygen18.py:_set_settings
+                s.h = 1 / s.sas_solver_substeps
             s.nx, s.ny = nx, ny
             s.runlen = 24 * 60 * 60 * ndays
             s.runlen_warmup = 0

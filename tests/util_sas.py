@@ -8,6 +8,7 @@ from roger_b200 import sas
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SAS_CASES = ["sas_power", "sas_power_snow", "sas_families", "sas_power_stats"]
 ANION_CASES = ["sas_bromide"]
+EULER_CASES = ["sas_euler", "sas_euler_families"]
 
 
 def load_case(name):
@@ -27,6 +28,8 @@ def model_from_fixture(fx, engine_cls, store_tt=True, engine_kwargs=None, mask=N
     if anion:
         kw = dict(solute=sas.ANION, anion_parameters=dict(alpha_transp=fx["par_alpha_transp"], alpha_q=fx["par_alpha_q"], lu_id=fx["par_lu_id"],
                                                           S_sat_rz=fx["par_S_sat_rz"]))
+    if "solver" in fx:
+        kw["solver"] = int(fx["solver"])
     m = sas.SasModel(engine_cls, C, A, daily, spec, substeps=int(fx["substeps"]), store_tt=store_tt, mask=mask,
                      engine_kwargs=engine_kwargs, age_statistics=age_statistics, **kw)
     m.setup()
