@@ -167,6 +167,23 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     anion_day<STATS>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev);
 }
 
+// One day of the explicit Euler solver (`substeps` Euler steps, ageing with the last one), one thread per cell.
+__global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
+k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
+                const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out) {
+    __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
+    __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
+    for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
+        s_log[k] = d_pow_log_tab[k];
+        s_exp[k] = d_pow_exp_tab[k];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.C) return;
+    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    euler_day(cx, forcing, mask[i], sas_params, out);
+}
+
 // (cells, A) row-major staging block <-> age-major planes, 32 x 32 tiles through shared memory
 __global__ void k_stage_to_planes(const double* __restrict__ stage, double* __restrict__ planes, int64_t C, int A, int base,
                                   int64_t cell0, int ncell) {
@@ -346,6 +363,9 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_sas_create: bad argument");
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
     if (settings->solute != 0 && settings->solute != 1) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope) or 1 (anion)");
+    if (settings->solver != 0 && settings->solver != 1) return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic) or 1 (Euler)");
+    if (settings->solver == 1 && (settings->solute != 0 || settings->age_statistics))
+        return fail(ROGER_ENOTSUP, "roger_sas_create: the explicit Euler solver covers the isotope branch without age statistics");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -478,7 +498,9 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     CU(cudaEventRecord(h->ev0, h->stream));
     const int threads = ROGER_SAS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
-    if (h->st.solute == 1) {
+    if (h->st.solver == 1) {
+        k_sas_day_euler<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out);
+    } else if (h->st.solute == 1) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
         if (h->st.age_statistics)

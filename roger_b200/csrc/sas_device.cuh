@@ -1052,4 +1052,254 @@ __device__ __forceinline__ void ageing(const CellCtx& cx) {
     }
 }
 
+
+// ================================================================================================================
+// Explicit Euler solver (settings.sas_solver = "Euler"): svat_transport_model_euler (transport.py:2063-2413) with
+// calc_TT_num (:859-907) and calc_TT_num_nonneg (:910-945), isotope branch.  `substeps` Euler steps per day
+// (calculate_storage_selection, :3221-3258; settings.h = 1 / substeps); all five fluxes are evaluated from ONE
+// StorAge snapshot per step, so a step is three walks over the age axis:
+//   P1  S = max(cumsum(sa)) of both layers,
+//   P2  the un-normalised non-negative pdf of every flux, summed with NumPy's pairwise tree (the normalisation constant),
+//   P3  the same pdf again -> normalised -> cumulated -> differenced (tt), isotope mixing and StorAge update of both
+//       layers, the storage kernels' `sa < 1e-8 -> 0` fused into the store.
+// The flux concentrations -- and the travel-time distributions handed out -- are those of the day's LAST step (every
+// earlier step's are overwritten in the reference as well), so only that step carries the ten concentration sums.
+// ================================================================================================================
+struct EulerFlux {
+    Family fam;
+    double flux, fh;    // flux, flux * h
+    bool active;        // calc_TT_num zeroes TTq where flux * h <= 0
+    double om_prev;     // TTq of the previous age index
+    double ssum;        // np.sum(ttq_nonneg)
+    double accT, Tprev; // cumsum of the normalised pdf
+};
+
+// ttq_nonneg of bin j (calc_TT_num_nonneg :919-931) given the masked cumulative StorAge at its upper edge
+__device__ __forceinline__ double euler_q(EulerFlux& e, const CellCtx& cx, int j, double SA, double sa_d) {
+    const double om = e.active ? omega(e.fam, cx.P, cx.tabs, j + 1, SA) : 0.0;
+    double q = (om - e.om_prev) * e.fh;
+    e.om_prev = om;
+    q = (sa_d + q < 0) ? -sa_d : q;
+    q = (q == 0) ? 0.0 : q;  // where(ttq == -0, 0, ttq)
+    return q;
+}
+
+// the two-statement isotope mixing of transport.py:2115-2130 / :2278-2293 for one bin
+__device__ __forceinline__ double euler_mix(double msa, double sa, double dsa1, double dmsa1, bool need_pos) {
+    const double tot = dsa1 + sa;
+    const bool c1 = need_pos ? ((tot > 0) && (msa > 0)) : (tot > 0);
+    double v = (c1 ? msa * (sa / tot) : 0) + ((tot > 0) ? dmsa1 * (dsa1 / tot) : 0);
+    v = ((dsa1 > 0) && (v <= 0)) ? dmsa1 : v;
+    return v;
+}
+
+template <bool LAST>
+__device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
+                                        double* __restrict__ out) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    const int64_t C = P.C, i = cx.i;
+    double* __restrict__ s_rz = cx.pl.sa[0];
+    double* __restrict__ s_ss = cx.pl.sa[1];
+    double* __restrict__ m_rz = cx.pl.msa[0];
+    double* __restrict__ m_ss = cx.pl.msa[1];
+    auto nan0 = [](double x) { return (x != x) ? 0.0 : x; };
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#define F(k) forcing[(int64_t)(k) * C + i]
+#define O(k) out[(int64_t)(k) * C + i]
+#define SP(p) (sas_params + (int64_t)(p) * 8 * C + i)
+    const double h = 1.0 / (double)P.substeps;
+    const double inf_mat = F(RSF_inf_mat_rz), inf_pf = F(RSF_inf_pf_rz), inf_ss = F(RSF_inf_pf_ss), C_in = F(RSF_C_in);
+    {   // upper boundary condition :2071-2143: infiltration enters age bin 0 (bins j > 0: see clean_* below)
+        const int64_t o = cx.ring(0);
+        const double tt_im = ((inf_mat > 0) ? 1 : 0) * m, tt_ip = ((inf_pf > 0) ? 1 : 0) * m, tt_is = ((inf_ss > 0) ? 1 : 0) * m;
+        const double mtt_im = ((inf_mat > 0) ? C_in : 0) * m, mtt_ip = ((inf_pf > 0) ? C_in : 0) * m, mtt_is = ((inf_ss > 0) ? C_in : 0) * m;
+        const double dsa_rz = (inf_mat * tt_im + inf_pf * tt_ip) * h;
+        const double dsa_ss = (inf_ss * tt_is) * h;
+        const double dmsa_rz1 = nan0(mtt_im) * ((dsa_rz > 0) ? ((inf_mat * tt_im * h) / dsa_rz) : 0) +
+                                nan0(mtt_ip) * ((dsa_rz > 0) ? ((inf_pf * tt_ip * h) / dsa_rz) : 0);
+        const double dmsa_ss1 = nan0(mtt_is) * ((dsa_ss > 0) ? ((inf_ss * tt_is * h) / dsa_ss) : 0);
+        double a = s_rz[o], b = s_ss[o];
+        double ma = euler_mix(m_rz[o], a, dsa_rz, dmsa_rz1, true);
+        double mb = euler_mix(m_ss[o], b, dsa_ss, dmsa_ss1, false);
+        a += dsa_rz;
+        b += dsa_ss;
+        s_rz[o] = a;
+        s_ss[o] = b;
+        m_rz[o] = (a <= 0) ? 0 : ma;
+        m_ss[o] = (b <= 0) ? 0 : mb;
+    }
+    // what the boundary-condition statements do to a bin that receives nothing (dsa1 = 0, dmsa1 = 0):
+    //   msa*(sa/(0 + sa)) + 0*(0/sa) under the statements' conditions, then msa = 0 where sa <= 0
+    auto clean_rz = [](double ms, double s) {
+        const double one = (s < 1.7976931348623157e308) ? 1.0 : s / s;
+        return ((s > 0) && (ms > 0)) ? ms * one + 0.0 : 0.0;
+    };
+    auto clean_ss = [](double ms, double s) {
+        const double one = (s < 1.7976931348623157e308) ? 1.0 : s / s;
+        return (s > 0) ? ms * one + 0.0 : 0.0;
+    };
+    // P1: S of both layers (calc_SA :343-359 times maskCatch, np.max over nages points)
+    NpMax mx_rz, mx_ss;
+    mx_rz.init(0.0 * m);
+    mx_ss.init(0.0 * m);
+    {
+        double acc_a = 0, acc_b = 0;
+        Cursor c(P, i);
+        for (int j = 0; j < A; j++, c.next()) {
+            acc_a += s_rz[c.off];
+            acc_b += s_ss[c.off];
+            mx_rz.push(acc_a * m);
+            mx_ss.push(acc_b * m);
+        }
+    }
+    EulerFlux fx[5];  // evap_soil, transp, q_rz (root zone); cpr_rz, q_ss (subsoil)
+    {
+        const int procs[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
+        const double flx[5] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_rz), F(RSF_cpr_rz), F(RSF_q_ss)};
+        const double mxa = mx_rz.get(), mxb = mx_ss.get();
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            family_begin(fx[k].fam, SP(procs[k]), C, m);
+            family_prepare(fx[k].fam, (k < 3) ? mxa : mxb);
+            fx[k].flux = flx[k];
+            fx[k].fh = flx[k] * h;
+            fx[k].active = !(fx[k].fh <= 0);
+        }
+    }
+    auto reset = [&]() {
+#pragma unroll
+        for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega(fx[k].fam, P, cx.tabs, 0, 0.0 * m) : 0.0;
+    };
+    // P2: normalisation constants
+    {
+        reset();
+        double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
+        double sums[5];
+        stream_sums<5, 2>(cx.plan,
+            [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = s_rz[o]; L[1] = s_ss[o]; },
+            [&](int j, const double* L, double* v) {
+                acc_a += L[0];
+                acc_b += L[1];
+                const double na = acc_a * m, nb = acc_b * m;
+                const double da = na - SAa, db = nb - SAb;
+                SAa = na;
+                SAb = nb;
+#pragma unroll
+                for (int k = 0; k < 5; k++) v[k] = euler_q(fx[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db);
+            }, sums);
+#pragma unroll
+        for (int k = 0; k < 5; k++) fx[k].ssum = sums[k];
+    }
+    // P3: travel-time distributions, mixing, update
+    {
+        reset();
+#pragma unroll
+        for (int k = 0; k < 5; k++) { fx[k].accT = 0; fx[k].Tprev = 0; }
+        double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
+        const double evap = fx[0].flux, transp = fx[1].flux, q_rz = fx[2].flux, cpr = fx[3].flux, q_ss = fx[4].flux;
+        double* __restrict__ tt_base = (LAST && P.store_tt && cx.pl.tt) ? cx.pl.tt : nullptr;
+        auto bin = [&](int j, const double* L, double* v) {
+            const int64_t o = cx.ring(j);
+            const double a = L[0], b = L[1];
+            const double ma = (j == 0) ? L[2] : clean_rz(L[2], a);
+            const double mb = (j == 0) ? L[3] : clean_ss(L[3], b);
+            acc_a += a;
+            acc_b += b;
+            const double na = acc_a * m, nb = acc_b * m;
+            const double da = na - SAa, db = nb - SAb;
+            SAa = na;
+            SAb = nb;
+            double tt[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const double q = euler_q(fx[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db);
+                const double p = (q > 0) ? q / fx[k].ssum : 0;
+                fx[k].accT = (j == 0) ? p : fx[k].accT + p;  // np.cumsum starts from the first element
+                const double d = fx[k].accT - fx[k].Tprev;
+                fx[k].Tprev = fx[k].accT;
+                tt[k] = (d >= 0) ? d : 0;
+            }
+            const double tt_e = tt[0], tt_t = tt[1], tt_q = tt[2], tt_c = tt[3], tt_s = tt[4];
+            const double mtt_c = (tt_c > 0) ? mb : 0, mtt_q = (tt_q > 0) ? ma : 0;
+            if (LAST) {
+                v[0] = tt_e; v[1] = ((tt_e > 0) ? ma : 0) * tt_e;
+                v[2] = tt_t; v[3] = ((tt_t > 0) ? ma : 0) * tt_t;
+                v[4] = tt_q; v[5] = mtt_q * tt_q;
+                v[6] = tt_c; v[7] = mtt_c * tt_c;
+                v[8] = tt_s; v[9] = ((tt_s > 0) ? mb : 0) * tt_s;
+                if (tt_base) {
+                    const int64_t span = (int64_t)A * C, l = cx.lin(j);
+                    tt_base[RSP_evap_soil * span + l] = tt_e;
+                    tt_base[RSP_transp * span + l] = tt_t;
+                    tt_base[RSP_q_rz * span + l] = tt_q;
+                    tt_base[RSP_cpr_rz * span + l] = tt_c;
+                    tt_base[RSP_q_ss * span + l] = tt_s;
+                }
+            }
+            double dsa_rz = (cpr * tt_c - evap * tt_e - transp * tt_t - q_rz * tt_q) * h;
+            dsa_rz = (a + dsa_rz < 0) ? -a : dsa_rz;
+            double dsa_ss = (q_rz * tt_q - cpr * tt_c - q_ss * tt_s) * h;
+            dsa_ss = (b + dsa_ss < 0) ? -b : dsa_ss;
+            const double dsa_rz1 = (cpr * tt_c) * h;
+            const double dmsa_rz1 = nan0(mtt_c) * ((dsa_rz1 > 0) ? ((cpr * tt_c * h) / dsa_rz1) : 0);
+            const double dsa_ss1 = (q_rz * tt_q) * h;
+            const double dmsa_ss1 = nan0(mtt_q) * ((dsa_ss1 > 0) ? ((q_rz * tt_q * h) / dsa_ss1) : 0);
+            double ma2 = euler_mix(ma, a, dsa_rz1, dmsa_rz1, true);
+            double mb2 = euler_mix(mb, b, dsa_ss1, dmsa_ss1, false);
+            double a2 = a + dsa_rz, b2 = b + dsa_ss;
+            ma2 = (a2 <= 0) ? 0 : ma2;
+            mb2 = (b2 <= 0) ? 0 : mb2;
+            a2 = (a2 < 1e-8) ? 0 : a2;  // root_zone.py:196-199, subsoil.py:160-163 (run after every Euler step)
+            b2 = (b2 < 1e-8) ? 0 : b2;
+            s_rz[o] = a2;
+            s_ss[o] = b2;
+            m_rz[o] = ma2;
+            m_ss[o] = mb2;
+        };
+        auto load = [&](int j, double* L) {
+            const int64_t o = cx.ring(j);
+            L[0] = s_rz[o]; L[1] = s_ss[o]; L[2] = m_rz[o]; L[3] = m_ss[o];
+        };
+        if (LAST) {
+            double sums[10];
+            stream_sums<10, 4>(cx.plan, load, bin, sums);
+            // calc_conc_iso_flux :512-535, delta_fluxes_svat :3659-3697
+            const int oc[5] = {RSO_C_evap_soil, RSO_C_transp, RSO_C_q_rz, RSO_C_cpr_rz, RSO_C_q_ss};
+            const int oi[5] = {RSO_C_iso_evap_soil, RSO_C_iso_transp, RSO_C_iso_q_rz, RSO_C_iso_cpr_rz, RSO_C_iso_q_ss};
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                double conc = (sums[2 * k] > 0) ? sums[2 * k + 1] / sums[2 * k] : qnan;
+                conc = (conc != 0) ? conc : qnan;
+                conc = conc * m;
+                O(oc[k]) = conc;
+                O(oi[k]) = conc_to_delta(P, conc) * m;
+            }
+            const double c1 = ((inf_mat > 0) ? C_in : qnan) * m, c2 = ((inf_pf > 0) ? C_in : qnan) * m, c3 = ((inf_ss > 0) ? C_in : qnan) * m;
+            O(RSO_C_inf_mat_rz) = c1; O(RSO_C_iso_inf_mat_rz) = conc_to_delta(P, c1) * m;
+            O(RSO_C_inf_pf_rz) = c2; O(RSO_C_iso_inf_pf_rz) = conc_to_delta(P, c2) * m;
+            O(RSO_C_inf_pf_ss) = c3; O(RSO_C_iso_inf_pf_ss) = conc_to_delta(P, c3) * m;
+        } else {
+            double L[2][4], v[1];
+            load(0, L[0]);
+            for (int j = 0; j < A; j++) {  // next bin's loads in flight while this bin computes
+                if (j + 1 < A) load(j + 1, L[(j + 1) & 1]);
+                bin(j, L[j & 1], v);
+            }
+        }
+    }
+#undef F
+#undef O
+#undef SP
+}
+
+__device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
+                                          double* __restrict__ out) {
+    for (int s = 0; s + 1 < cx.P.substeps; s++) euler_step<false>(cx, forcing, m, sas_params, out);
+    euler_step<true>(cx, forcing, m, sas_params, out);
+    double sum_sa_s, C_s, sum_sa_rz, sum_sa_ss;
+    storage_concentrations(cx, m, out, cx.P.C, &sum_sa_s, &C_s, &sum_sa_rz, &sum_sa_ss);
+    ageing(cx);
+}
+
 }  // namespace rsas
