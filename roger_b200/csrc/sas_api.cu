@@ -168,7 +168,13 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
 }
 
 // One day of the explicit Euler solver (`substeps` Euler steps, ageing with the last one), one thread per cell.
-__global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
+#ifndef ROGER_EULER_BLOCK
+#define ROGER_EULER_BLOCK 256
+#endif
+#ifndef ROGER_EULER_MIN_BLOCKS
+#define ROGER_EULER_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(ROGER_EULER_BLOCK, ROGER_EULER_MIN_BLOCKS)
 k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
                 const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
@@ -499,7 +505,8 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     const int threads = ROGER_SAS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
     if (h->st.solver == 1) {
-        k_sas_day_euler<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out);
+        const int eb = (int)((h->C + ROGER_EULER_BLOCK - 1) / ROGER_EULER_BLOCK);
+        k_sas_day_euler<<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out);
     } else if (h->st.solute == 1) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};

@@ -291,6 +291,70 @@ __device__ __forceinline__ void stream_sums(const PwPlan* __restrict__ plan, Loa
     for (int k = 0; k < NS; k++) out[k] = 0.0 + st[k][0];
 }
 
+// The same sums with ONE copy of work() in the instruction stream (stream_sums<> unrolls it ten times, which is right for
+// the light passes and thrashes the instruction cache for a heavy one).  The eight lanes stay in registers as a shift
+// register: the lane a bin adds to is always lane 0, and the lanes rotate by one after every bin; a chunk is a multiple
+// of 8 bins, so they are back in place when the tree sum is taken.  The next bin's loads are issued before this bin's work.
+template <int NS, int NL, class Load, class Work>
+__device__ __forceinline__ void stream_sums_rolled(const PwPlan* __restrict__ plan, int n_bins, Load load, Work work, double* out) {
+    double st[NS][8];
+    int sp = 0;
+    int j = 0;
+    const int nl = plan->n_leaves;
+    double Lc[NL], Ln[NL];
+    load(0, Lc);
+    for (int l = 0; l < nl; l++) {
+        const int len = plan->len[l];
+        const int len8 = (len < 8) ? 0 : len - (len % 8);
+        double res[NS], r[NS][8];
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+            res[k] = 0.;
+#pragma unroll
+            for (int q = 0; q < 8; q++) r[k][q] = -0.0;
+        }
+        for (int i = 0; i < len; i++, j++) {
+            if (i == len8 && len8 > 0) {
+#pragma unroll
+                for (int k = 0; k < NS; k++)
+                    res[k] = ((r[k][0] + r[k][1]) + (r[k][2] + r[k][3])) + ((r[k][4] + r[k][5]) + (r[k][6] + r[k][7]));
+            }
+            if (j + 1 < n_bins) load(j + 1, Ln);
+            double v[NS];
+            work(j, Lc, v);
+#pragma unroll
+            for (int q = 0; q < NL; q++) Lc[q] = Ln[q];
+            if (i < len8) {
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    const double t = r[k][0] + v[k];
+#pragma unroll
+                    for (int q = 0; q < 7; q++) r[k][q] = r[k][q + 1];
+                    r[k][7] = t;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NS; k++) res[k] += v[k];
+            }
+        }
+        if (len8 == len && len8 > 0) {
+#pragma unroll
+            for (int k = 0; k < NS; k++)
+                res[k] = ((r[k][0] + r[k][1]) + (r[k][2] + r[k][3])) + ((r[k][4] + r[k][5]) + (r[k][6] + r[k][7]));
+        }
+#pragma unroll
+        for (int k = 0; k < NS; k++) st[k][sp] = res[k];
+        sp++;
+        for (int c = plan->merges[l]; c > 0; c--) {
+            sp--;
+#pragma unroll
+            for (int k = 0; k < NS; k++) st[k][sp - 1] = st[k][sp - 1] + st[k][sp];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) out[k] = 0.0 + st[k][0];
+}
+
 // numpy.interp(p, cdf, 1..A) evaluated while the (non-decreasing) cdf streams by: the last index with cdf <= p and the
 // value that follows it (calc_age_percentile, transport.py:9-56; numpy's bisection returns the same index for a
 // non-decreasing array).
@@ -1072,11 +1136,44 @@ struct EulerFlux {
     double om_prev;     // TTq of the previous age index
     double ssum;        // np.sum(ttq_nonneg)
     double accT, Tprev; // cumsum of the normalised pdf
+    // exact shortcuts (same bits as the general path, see euler_q)
+    bool sa_only;       // the SAS function depends on the cumulative StorAge only, not on the age index
+    bool powfast;       // power law, cell inside the catchment, S in the range where div_by() is exact
+    bool ssum_ok;       // ssum in that range as well
+    double rS, rssum;
 };
 
+// out-of-line copies for the Euler kernel, whose hot path is the hoisted power law: keeps the loop bodies small
+__device__ __noinline__ double omega_call(const Family& f, const SasParams& P, const roger_pow_tables tabs, int jj, double SA) {
+    return omega(f, P, tabs, jj, SA);
+}
+__device__ __noinline__ double pow_call(double x, double y, const roger_pow_tables tabs) { return roger_pow(x, y, tabs); }
+
+// log(SA / S) of one layer's bin, shared by the layer's power-law fluxes (x^y1, x^y2, ... of one base: cf. roger_pow2)
+struct EulerLog {
+    double hi, lo;
+    bool in, easy;
+};
+__device__ __forceinline__ EulerLog euler_log(const CellCtx& cx, double SA, double S, double rS) {
+    EulerLog g;
+    g.in = (SA > 0) && (SA <= S);
+    g.easy = g.in && (SA >= 0x1p-500);  // keeps the quotient normal and div_by() exact
+    const double xr = div_by(SA, S, rS);
+    g.hi = roger_pow_log(g.easy ? roger_pow_asu(xr) : 0x3fe0000000000000ULL, &g.lo, cx.tabs.log_tab);
+    return g;
+}
+
 // ttq_nonneg of bin j (calc_TT_num_nonneg :919-931) given the masked cumulative StorAge at its upper edge
-__device__ __forceinline__ double euler_q(EulerFlux& e, const CellCtx& cx, int j, double SA, double sa_d) {
-    const double om = e.active ? omega(e.fam, cx.P, cx.tabs, j + 1, SA) : 0.0;
+__device__ __forceinline__ double euler_q(EulerFlux& e, const CellCtx& cx, int j, double SA, double sa_d, const EulerLog& g) {
+    double om;
+    if (!e.active) om = 0.0;
+    else if (e.sa_only && sa_d == 0) om = e.om_prev;  // an empty bin: same cumulative StorAge, same SAS function value
+    else if (e.powfast) {                               // omega() for the power law with the division hoisted (cf. pow_pass_bins)
+        const double S = e.fam.S;
+        double p = roger_pow_from_log(g.hi, g.lo, e.fam.sp[1], cx.tabs);
+        if (g.in && !g.easy) p = pow_call(SA / S, e.fam.sp[1], cx.tabs);
+        om = (SA > 0) ? ((SA <= S) ? p : 1.) : 0.;
+    } else om = omega_call(e.fam, cx.P, cx.tabs, j + 1, SA);
     double q = (om - e.om_prev) * e.fh;
     e.om_prev = om;
     q = (sa_d + q < 0) ? -sa_d : q;
@@ -1158,25 +1255,38 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         const int procs[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
         const double flx[5] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_rz), F(RSF_cpr_rz), F(RSF_q_ss)};
         const double mxa = mx_rz.get(), mxb = mx_ss.get();
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 5; k++) {
             family_begin(fx[k].fam, SP(procs[k]), C, m);
             family_prepare(fx[k].fam, (k < 3) ? mxa : mxb);
             fx[k].flux = flx[k];
             fx[k].fh = flx[k] * h;
             fx[k].active = !(fx[k].fh <= 0);
+            const Family& f = fx[k].fam;
+            fx[k].sa_only = f.fast && !f.is_uniform && !f.is_dirac;
+            fx[k].powfast = f.fast && f.is_pow && (f.S > 0) && div_range_ok(f.S) && (f.sp[1] - f.sp[1] == 0.0);
+            fx[k].rS = 1.0 / f.S;
         }
     }
+    // one logarithm per layer and bin serves every power-law flux of the layer (skipped for empty bins)
+    const bool logs_a = (fx[0].active && fx[0].powfast) || (fx[1].active && fx[1].powfast) || (fx[2].active && fx[2].powfast);
+    const bool logs_b = (fx[3].active && fx[3].powfast) || (fx[4].active && fx[4].powfast);
+    const double S_a = fx[0].fam.S, rS_a = fx[0].rS, S_b = fx[3].fam.S, rS_b = fx[3].rS;
+    auto layer_log = [&](int layer, double SA, double sa_d) {
+        EulerLog g{0.0, 0.0, false, false};
+        if ((layer == 0 ? logs_a : logs_b) && !(sa_d == 0)) g = euler_log(cx, SA, layer == 0 ? S_a : S_b, layer == 0 ? rS_a : rS_b);
+        return g;
+    };
     auto reset = [&]() {
-#pragma unroll
-        for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega(fx[k].fam, P, cx.tabs, 0, 0.0 * m) : 0.0;
+#pragma unroll 1
+        for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega_call(fx[k].fam, P, cx.tabs, 0, 0.0 * m) : 0.0;
     };
     // P2: normalisation constants
     {
         reset();
         double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
         double sums[5];
-        stream_sums<5, 2>(cx.plan,
+        stream_sums_rolled<5, 2>(cx.plan, A,
             [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = s_rz[o]; L[1] = s_ss[o]; },
             [&](int j, const double* L, double* v) {
                 acc_a += L[0];
@@ -1185,11 +1295,16 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
                 const double da = na - SAa, db = nb - SAb;
                 SAa = na;
                 SAb = nb;
+                const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
 #pragma unroll
-                for (int k = 0; k < 5; k++) v[k] = euler_q(fx[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db);
+                for (int k = 0; k < 5; k++) v[k] = euler_q(fx[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
             }, sums);
 #pragma unroll
-        for (int k = 0; k < 5; k++) fx[k].ssum = sums[k];
+        for (int k = 0; k < 5; k++) {
+            fx[k].ssum = sums[k];
+            fx[k].ssum_ok = (sums[k] > 0) && div_range_ok(sums[k]);
+            fx[k].rssum = 1.0 / sums[k];
+        }
     }
     // P3: travel-time distributions, mixing, update
     {
@@ -1211,10 +1326,11 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             SAa = na;
             SAb = nb;
             double tt[5];
+            const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
 #pragma unroll
             for (int k = 0; k < 5; k++) {
-                const double q = euler_q(fx[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db);
-                const double p = (q > 0) ? q / fx[k].ssum : 0;
+                const double q = euler_q(fx[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
+                const double p = (q > 0) ? ((fx[k].ssum_ok && div_range_ok(q)) ? div_by(q, fx[k].ssum, fx[k].rssum) : q / fx[k].ssum) : 0;
                 fx[k].accT = (j == 0) ? p : fx[k].accT + p;  // np.cumsum starts from the first element
                 const double d = fx[k].accT - fx[k].Tprev;
                 fx[k].Tprev = fx[k].accT;
@@ -1242,11 +1358,14 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             double dsa_ss = (q_rz * tt_q - cpr * tt_c - q_ss * tt_s) * h;
             dsa_ss = (b + dsa_ss < 0) ? -b : dsa_ss;
             const double dsa_rz1 = (cpr * tt_c) * h;
-            const double dmsa_rz1 = nan0(mtt_c) * ((dsa_rz1 > 0) ? ((cpr * tt_c * h) / dsa_rz1) : 0);
+            // (cpr * tt_c * h) / dsa_rz1 divides a value by itself: exactly 1 for a finite positive value
+            auto self_ratio = [](double x) { return (x < 1.7976931348623157e308) ? 1.0 : x / x; };
+            const double dmsa_rz1 = nan0(mtt_c) * ((dsa_rz1 > 0) ? self_ratio(dsa_rz1) : 0);
             const double dsa_ss1 = (q_rz * tt_q) * h;
-            const double dmsa_ss1 = nan0(mtt_q) * ((dsa_ss1 > 0) ? ((q_rz * tt_q * h) / dsa_ss1) : 0);
-            double ma2 = euler_mix(ma, a, dsa_rz1, dmsa_rz1, true);
-            double mb2 = euler_mix(mb, b, dsa_ss1, dmsa_ss1, false);
+            const double dmsa_ss1 = nan0(mtt_q) * ((dsa_ss1 > 0) ? self_ratio(dsa_ss1) : 0);
+            // a bin that receives nothing keeps its concentration: the general expression reduces to clean_*()
+            double ma2 = (dsa_rz1 == 0 && dmsa_rz1 == 0 && j > 0) ? ma : euler_mix(ma, a, dsa_rz1, dmsa_rz1, true);
+            double mb2 = (dsa_ss1 == 0 && dmsa_ss1 == 0 && j > 0) ? mb : euler_mix(mb, b, dsa_ss1, dmsa_ss1, false);
             double a2 = a + dsa_rz, b2 = b + dsa_ss;
             ma2 = (a2 <= 0) ? 0 : ma2;
             mb2 = (b2 <= 0) ? 0 : mb2;
@@ -1263,7 +1382,7 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         };
         if (LAST) {
             double sums[10];
-            stream_sums<10, 4>(cx.plan, load, bin, sums);
+            stream_sums_rolled<10, 4>(cx.plan, A, load, bin, sums);
             // calc_conc_iso_flux :512-535, delta_fluxes_svat :3659-3697
             const int oc[5] = {RSO_C_evap_soil, RSO_C_transp, RSO_C_q_rz, RSO_C_cpr_rz, RSO_C_q_ss};
             const int oi[5] = {RSO_C_iso_evap_soil, RSO_C_iso_transp, RSO_C_iso_q_rz, RSO_C_iso_cpr_rz, RSO_C_iso_q_ss};
@@ -1280,11 +1399,13 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             O(RSO_C_inf_pf_rz) = c2; O(RSO_C_iso_inf_pf_rz) = conc_to_delta(P, c2) * m;
             O(RSO_C_inf_pf_ss) = c3; O(RSO_C_iso_inf_pf_ss) = conc_to_delta(P, c3) * m;
         } else {
-            double L[2][4], v[1];
-            load(0, L[0]);
+            double Lc[4], Ln[4], v[1];
+            load(0, Lc);
             for (int j = 0; j < A; j++) {  // next bin's loads in flight while this bin computes
-                if (j + 1 < A) load(j + 1, L[(j + 1) & 1]);
-                bin(j, L[j & 1], v);
+                if (j + 1 < A) load(j + 1, Ln);
+                bin(j, Lc, v);
+#pragma unroll
+                for (int q = 0; q < 4; q++) Lc[q] = Ln[q];
             }
         }
     }

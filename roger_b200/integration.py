@@ -192,7 +192,8 @@ class CudaStepDriver:
 class CudaTransportDriver:
     """Drop-in for the offline oxygen-18 transport branch of `RogerSetup.step` (roger/roger.py:467-483): the setup's own
     hooks feed `vs.inf_mat_rz, vs.transp, ... vs.C_in` for the day, the engine runs
-    `transport.svat_transport_model_deterministic` (core/transport.py:948-991) for every cell, and the results are written
+    `transport.svat_transport_model_deterministic` (core/transport.py:948-991) -- or, with `settings.sas_solver = "Euler"`,
+    the day's explicit Euler steps (`svat_transport_model_euler`, :2063-2413, driven by :3221-3258) -- for every cell, and the results are written
     back into `vs` with both time levels as `after_substep_iso` (:3421-3520) leaves them.
 
         model = MyOxygen18Setup(); model.setup(); model.warmup()
@@ -218,8 +219,12 @@ class CudaTransportDriver:
         self.anion = bool(getattr(st, "enable_bromide", False)) or bool(getattr(st, "enable_chloride", False))
         if not getattr(st, "enable_offline_transport", False) or not (iso18 or iso2 or self.anion):
             raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium / bromide / chloride transport models")
-        if getattr(st, "sas_solver", None) != "deterministic":
-            raise NotImplementedError("only sas_solver = 'deterministic' runs on the device (DESIGN.md section 7)")
+        solver = getattr(st, "sas_solver", None)
+        if solver not in ("deterministic", "Euler"):
+            raise NotImplementedError("sas_solver = 'deterministic' and 'Euler' run on the device (DESIGN.md section 7)")
+        self.euler = solver == "Euler"
+        if self.euler and (self.anion or bool(getattr(st, "enable_age_statistics", False))):
+            raise NotImplementedError("the explicit Euler solver covers the isotope branch without age statistics")
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
         self.C = self.nx * self.ny
         self.pull_state = bool(pull_state)
@@ -227,7 +232,7 @@ class CudaTransportDriver:
         # deuterium runs the same kernels with its own standard ratio and plausibility window (transport.py:315-340)
         vsmow, dmin, dmax = (st.VSMOW_conc2H, st.d2H_min, st.d2H_max) if iso2 else (st.VSMOW_conc18O, st.d18O_min, st.d18O_max)
         s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats),
-                            sas.ANION if self.anion else sas.ISOTOPE, 0)
+                            sas.ANION if self.anion else sas.ISOTOPE, sas.EULER if self.euler else sas.DETERMINISTIC)
         self.settings = s
         self.engine = engine_cls(self.C, s, **(engine_kwargs or {}))
         tau = int(vs.tau)
@@ -259,11 +264,19 @@ class CudaTransportDriver:
         setup._ensure_setup_done()
         with vs.unlock():
             vs.itt = vs.itt + 1
-            vs.time = vs.time + vs.dt_secs
+            if not self.euler:  # roger.py:470-471
+                vs.time = vs.time + vs.dt_secs
         setup.read_data(state)
         setup.set_boundary_conditions(state)
         setup.set_forcing(state)
         setup.set_parameters(state)
+        if self.euler:  # the clock advances with the Euler steps (transport.py:3234), ageing when it reaches midnight (:3247)
+            n = int(self.settings.substeps)
+            with vs.unlock():
+                vs.time = vs.time + n * int(vs.dt_secs / n)
+                vs.itt_substep = n - 1
+            if int(vs.time) % (24 * 60 * 60) != 0:
+                raise NotImplementedError("Euler steps that do not add up to whole days (the device ages the StorAge once per call)")
         f = np.stack([np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64) for n in self._FORCING])
         self.engine.step(f)
         out = self.engine.download_outputs()
