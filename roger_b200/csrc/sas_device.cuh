@@ -1129,6 +1129,16 @@ __device__ __forceinline__ void ageing(const CellCtx& cx) {
 // The flux concentrations -- and the travel-time distributions handed out -- are those of the day's LAST step (every
 // earlier step's are overwritten in the reference as well), so only that step carries the ten concentration sums.
 // ================================================================================================================
+#ifndef ROGER_EULER_ROLLED
+#define ROGER_EULER_ROLLED 1
+#endif
+#if ROGER_EULER_ROLLED
+#define EULER_SUMS stream_sums_rolled
+#define EULER_SUMS_ARG A,
+#else
+#define EULER_SUMS stream_sums
+#define EULER_SUMS_ARG
+#endif
 struct EulerFlux {
     Family fam;
     double flux, fh;    // flux, flux * h
@@ -1142,12 +1152,6 @@ struct EulerFlux {
     bool ssum_ok;       // ssum in that range as well
     double rS, rssum;
 };
-
-// out-of-line copies for the Euler kernel, whose hot path is the hoisted power law: keeps the loop bodies small
-__device__ __noinline__ double omega_call(const Family& f, const SasParams& P, const roger_pow_tables tabs, int jj, double SA) {
-    return omega(f, P, tabs, jj, SA);
-}
-__device__ __noinline__ double pow_call(double x, double y, const roger_pow_tables tabs) { return roger_pow(x, y, tabs); }
 
 // log(SA / S) of one layer's bin, shared by the layer's power-law fluxes (x^y1, x^y2, ... of one base: cf. roger_pow2)
 struct EulerLog {
@@ -1171,9 +1175,9 @@ __device__ __forceinline__ double euler_q(EulerFlux& e, const CellCtx& cx, int j
     else if (e.powfast) {                               // omega() for the power law with the division hoisted (cf. pow_pass_bins)
         const double S = e.fam.S;
         double p = roger_pow_from_log(g.hi, g.lo, e.fam.sp[1], cx.tabs);
-        if (g.in && !g.easy) p = pow_call(SA / S, e.fam.sp[1], cx.tabs);
+        if (g.in && !g.easy) p = roger_pow(SA / S, e.fam.sp[1], cx.tabs);
         om = (SA > 0) ? ((SA <= S) ? p : 1.) : 0.;
-    } else om = omega_call(e.fam, cx.P, cx.tabs, j + 1, SA);
+    } else om = omega(e.fam, cx.P, cx.tabs, j + 1, SA);
     double q = (om - e.om_prev) * e.fh;
     e.om_prev = om;
     q = (sa_d + q < 0) ? -sa_d : q;
@@ -1255,7 +1259,7 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         const int procs[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
         const double flx[5] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_rz), F(RSF_cpr_rz), F(RSF_q_ss)};
         const double mxa = mx_rz.get(), mxb = mx_ss.get();
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < 5; k++) {
             family_begin(fx[k].fam, SP(procs[k]), C, m);
             family_prepare(fx[k].fam, (k < 3) ? mxa : mxb);
@@ -1278,15 +1282,15 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         return g;
     };
     auto reset = [&]() {
-#pragma unroll 1
-        for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega_call(fx[k].fam, P, cx.tabs, 0, 0.0 * m) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega(fx[k].fam, P, cx.tabs, 0, 0.0 * m) : 0.0;
     };
     // P2: normalisation constants
     {
         reset();
         double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
         double sums[5];
-        stream_sums_rolled<5, 2>(cx.plan, A,
+        EULER_SUMS<5, 2>(cx.plan, EULER_SUMS_ARG
             [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = s_rz[o]; L[1] = s_ss[o]; },
             [&](int j, const double* L, double* v) {
                 acc_a += L[0];
@@ -1382,7 +1386,7 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         };
         if (LAST) {
             double sums[10];
-            stream_sums_rolled<10, 4>(cx.plan, A, load, bin, sums);
+            EULER_SUMS<10, 4>(cx.plan, EULER_SUMS_ARG load, bin, sums);
             // calc_conc_iso_flux :512-535, delta_fluxes_svat :3659-3697
             const int oc[5] = {RSO_C_evap_soil, RSO_C_transp, RSO_C_q_rz, RSO_C_cpr_rz, RSO_C_q_ss};
             const int oi[5] = {RSO_C_iso_evap_soil, RSO_C_iso_transp, RSO_C_iso_q_rz, RSO_C_iso_cpr_rz, RSO_C_iso_q_ss};
