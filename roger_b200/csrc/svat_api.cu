@@ -370,6 +370,8 @@ int roger_svat_field_kind(int f) { return (f >= 0 && f < RF_COUNT) ? kFieldKind[
 
 int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settings* settings, int device) {
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_svat_create: bad argument");
+    if (n_cells >= (int64_t(1) << 29))  // the kernels address a plane by a 32-bit byte count (svat_device.cuh: Io)
+        return fail(ROGER_EINVAL, "roger_svat_create: at most 2^29 - 1 cells per handle (a plane must stay below 4 GiB); shard the grid");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

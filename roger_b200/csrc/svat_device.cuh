@@ -121,7 +121,43 @@ RD double mk(const Cell& c, double x) { return MASK1 ? x : x * c.m; }
 constexpr int kFirstFlux = RF_pet_res;  // the enum is ordered P.., S.., F..
 // (Measured alternative: per-thread base pointers + a 32-bit plane size make an access one IMAD.WIDE.U32 instead of five
 // integer instructions, but the compiler then derives each address from the previous one and the serial address chains
-// cost more than the instructions saved -- 6.05 vs 5.80 ms per step at 4096^2.  Addresses stay independent.)
+// cost more than the instructions saved -- 6.05 vs 5.80 ms per step at 4096^2.)
+#ifndef ROGER_IO_MADWIDE
+#define ROGER_IO_MADWIDE 1
+#endif
+#if ROGER_IO_MADWIDE
+// One access = one `mad.wide.u32` (plane id * plane size in bytes + the thread's own base pointer) and the load / store.
+// The plane size is a 32-bit byte count (planes < 4 GiB, i.e. < 2^29 cells per handle -- checked at create); the cell
+// offset is folded into the per-thread base pointers once.  Written as inline PTX so that every address is computed
+// independently from the two loop-invariant registers (see the note above).
+struct Io {
+    char* __restrict__ ps;  // parameter + state planes, advanced to this thread's cell
+    char* __restrict__ fl;  // flux planes (FLUX kernels only), likewise
+    unsigned Cb;            // bytes per plane
+    RD Io(double* ps_, double* fl_, int64_t C, int64_t i)
+        : ps(reinterpret_cast<char*>(ps_ + i)), fl(fl_ ? reinterpret_cast<char*>(fl_ + i) : nullptr), Cb((unsigned)(C * 8)) {}
+    RD static double* mad(const char* base, unsigned id, unsigned cb) {
+        unsigned long long a;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(cb), "r"(id), "l"((unsigned long long)base));
+        return reinterpret_cast<double*>(a);
+    }
+    RD double* at(int id) const { return mad(ps, (unsigned)id, Cb); }
+    RD double ldp(int id) const { return __ldg(at(id)); }
+    RD double lds(int id) const { return *at(id); }
+    RD void sts(int id, double v) const { *at(id) = v; }
+    template <bool FLUX>
+    RD void stf(int id, double v) const {
+        if (FLUX) *mad(fl, (unsigned)(id - kFirstFlux), Cb) = v;
+    }
+    RD void pf(int id) const {
+#if ROGER_L2_PREFETCH == 2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(id)));
+#else
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(at(id)));
+#endif
+    }
+};
+#else
 struct Io {
     double* __restrict__ ps;  // parameter + state planes
     double* __restrict__ fl;  // flux planes (FLUX kernels only)
@@ -141,6 +177,7 @@ struct Io {
 #endif
     }
 };
+#endif
 #define LDP(name) c.name = io.ldp(RF_##name)
 #define LDS(name) c.name = io.lds(RF_##name)
 #define STS(name) io.sts(RF_##name, c.name)
