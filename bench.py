@@ -31,7 +31,7 @@ from roger_b200.svat import SvatModel  # noqa: E402
 ALGO_BYTES = {"svat": 984.0, "oned": 1200.0}
 # DRAM bytes per cell and launch of the dominant kernel from the committed `ncu --set full` captures (profiles/r1_ncu_summary.md:
 # dram__bytes_read.sum + dram__bytes_write.sum divided by the cells of the captured launch); None where no capture exists
-NCU_DRAM_BYTES_PER_CELL = {"oned": 1137.0, "svat": None}
+NCU_DRAM_BYTES_PER_CELL = {"oned": 1122.0, "svat": None}  # r1f capture: 4.707 GB per launch at 2048^2
 NCU_DRAM_BYTES_PER_BIN_DAY = 1327.0  # k_sas_day, per cell and age bin
 
 

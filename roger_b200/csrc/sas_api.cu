@@ -172,7 +172,7 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
 #define ROGER_EULER_BLOCK 256
 #endif
 #ifndef ROGER_EULER_MIN_BLOCKS
-#define ROGER_EULER_MIN_BLOCKS 2
+#define ROGER_EULER_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(ROGER_EULER_BLOCK, ROGER_EULER_MIN_BLOCKS)
 k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
