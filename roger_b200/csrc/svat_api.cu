@@ -215,6 +215,14 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
 //   AVERAGE acc = (isnan(acc) ? 0 : acc) + v, / count later  average.py:71-84, :94-97
 //   MAXIMUM acc = nanmax(acc', v), acc' = NaN if acc == 0 and v < 0     maximum.py:76-92 (2-D variables)
 //   MINIMUM acc = nanmin(acc', v), acc' = NaN if acc == 0 and v > 0     minimum.py
+// k, h of the soil column for the state-only kernels (svat_device.cuh: soil_kh_refresh)
+__global__ void k_soil_kh_refresh(Planes pl) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pl.C) return;
+    const Io io{pl.ps, pl.fl, pl.C, i};
+    soil_kh_refresh(io);
+}
+
 __global__ void k_accumulate_rates(Planes pl, double* __restrict__ acc, const int* __restrict__ fields, const int* __restrict__ modes, int n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pl.C) return;
@@ -320,6 +328,7 @@ struct roger_svat {
     unsigned day_flags = 0;
     bool snow_flags_valid = false;
     bool ks_ss_synced = false;
+    bool soil_kh_stale = false;   // the state-only kernels do not evaluate k, h of the soil column: refreshed on access
     bool have_forcing = false;
     // uniform forcing: the (uniform) value the prec / ta planes currently hold, tracked by the scheduler
     double u_cur_prec = 0, u_cur_ta = 0;
@@ -360,6 +369,16 @@ static int ensure_flux_planes(roger_svat* h) {
     CU(cudaMemsetAsync(h->d_fl, 0, sizeof(double) * (size_t)kNumF * (size_t)h->C, h->stream));
     return 0;
 }
+
+// k, h of the soil column are evaluated lazily for the state-only kernels: bring the two planes up to date
+static int refresh_soil_kh(roger_svat* h) {
+    if (!h->soil_kh_stale) return 0;
+    k_soil_kh_refresh<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(h->planes());
+    CU(cudaGetLastError());
+    h->soil_kh_stale = false;
+    return 0;
+}
+static bool is_soil_kh(int field) { return field == RF_k || field == RF_h; }
 
 extern "C" {
 
@@ -431,6 +450,7 @@ void roger_svat_destroy(roger_svat* h) {
 }
 
 int roger_svat_upload(roger_svat* h, int field, const double* host) {
+    if (h && (field == RF_k || field == RF_h)) h->soil_kh_stale = false;  // the caller's values stand until the next state-only step
     if (!h || !host || field < 0 || field >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_upload: bad argument");
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
@@ -446,6 +466,7 @@ int roger_svat_download(roger_svat* h, int field, double* host) {
     if (!h || !host || field < 0 || field >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_download: bad argument");
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
+    if (is_soil_kh(field)) { int r = refresh_soil_kh(h); if (r) return r; }
     CU(cudaMemcpyAsync(host, h->planes().at(field), sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
@@ -457,6 +478,7 @@ int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
     if (!h || !host_pinned || field < 0 || field >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_download_async: bad argument");
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
+    if (is_soil_kh(field)) { int r = refresh_soil_kh(h); if (r) return r; }
     if (!h->copy_stream) {
         CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
@@ -486,6 +508,7 @@ int roger_svat_download_wait(roger_svat* h) {
 uint64_t roger_svat_plane_ptr(roger_svat* h, int field) {
     if (!h || field < 0 || field >= RF_COUNT) return 0;
     if (kind_is_F(field) && ensure_flux_planes(h)) return 0;
+    if (is_soil_kh(field) && refresh_soil_kh(h)) return 0;  // current as of this call; later state-only steps do not update it
     return (uint64_t)(uintptr_t)h->planes().at(field);
 }
 
@@ -748,6 +771,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
     if (st.enable_lateral_flow) { if (write_fluxes) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (write_fluxes) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
+    h->soil_kh_stale = !write_fluxes;
     CU(cudaGetLastError());
     launches++;
     if (!h->rate_fields.empty()) {
@@ -830,6 +854,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done) {
     const Planes pl = h->planes();
     if (st.enable_lateral_flow) k_svat_steps<true><<<blocks, threads, 0, h->stream>>>(pl, (const StepPlan*)h->d_plans, n, h->d_block_flags);
     else k_svat_steps<false><<<blocks, threads, 0, h->stream>>>(pl, (const StepPlan*)h->d_plans, n, h->d_block_flags);
+    h->soil_kh_stale = true;
     CU(cudaGetLastError());
     launches++;
     CU(cudaMemcpyAsync(h->h_block_flags, h->d_block_flags, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -902,7 +927,7 @@ int roger_svat_set_diagnostics(roger_svat* h, const int* fields, const int* mode
     if (modes) h->rate_modes.assign(modes, modes + n);
     h->rates_need_flux = false;
     h->diag_count = 0;
-    for (int f : h->rate_fields) h->rates_need_flux = h->rates_need_flux || kind_is_F(f);
+    for (int f : h->rate_fields) h->rates_need_flux = h->rates_need_flux || kind_is_F(f) || is_soil_kh(f);  // k, h: full kernel only
     if (n == 0) return 0;
     if (h->rates_need_flux) { int r = ensure_flux_planes(h); if (r) return r; }
     const size_t bytes = sizeof(double) * (size_t)n * (size_t)h->C;

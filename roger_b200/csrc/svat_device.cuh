@@ -1179,12 +1179,30 @@ RD void storages(Cell& c, const StepPlan& p, const Io& io) {
     c.S_s = M(c.S_pwp_s + c.S_fp_s + c.S_lp_s);
     c.dS_s = M(c.S_s - c.S_s_m1);
     c.theta = M((c.S_fp_s + c.S_lp_s) / c.z_soil + c.theta_pwp);
-    brooks_corey<MASK1>(c, c.theta, mm, inv_lambda, c.k, c.h);
+    // k, h of the whole soil column (soil.py:9-42) are results only -- no process reads them -- so the state-only kernels
+    // leave them to soil_kh_refresh() below, which the host runs before anybody looks at those two planes
+    if (FLUX) brooks_corey<MASK1>(c, c.theta, mm, inv_lambda, c.k, c.h);
     c.S = c.S_sur + M(c.S_s);       // numerics.py:134
     c.dS = c.S - M(c.S_m1);         // numerics.py:147
     STS(S_rz); STS(theta_rz); STS(k_rz); STS(h_rz); STS(S_ss); STS(theta_ss); STS(k_ss); STS(h_ss);
-    STS(S_s); STS(theta); STS(k); STS(h); STS(S);
+    STS(S_s); STS(theta); STS(S);
+    if (FLUX) { STS(k); STS(h); }
     STF(S_fp_s); STF(S_lp_s); STF(dS_rz); STF(dS_ss); STF(dS_s); STF(dS); STF(irr_demand);
+}
+
+// k, h of the soil column from the stored theta: the statements storages<> skips in the state-only kernels, evaluated with
+// the mask multiplications spelled out (x * 1.0 == x, so cells inside the catchment get the bits of the MASK1 path)
+RD void soil_kh_refresh(const Io& io) {
+    Cell c;
+    c.m = io.ldp(RF_maskCatch);
+    LDP(theta_ac); LDP(theta_ufc); LDP(theta_pwp); LDP(ks); LDP(ha); LDP(m_bc); LDP(lambda_bc);
+    LDS(theta);
+    constexpr bool MASK1 = false;
+    c.theta_sat = M(c.theta_ac + c.theta_ufc + c.theta_pwp);
+    const double inv_lambda = 1 / c.lambda_bc;
+    const double mm = -c.m_bc;
+    brooks_corey<MASK1>(c, c.theta, mm, inv_lambda, c.k, c.h);
+    STS(k); STS(h);
 }
 
 // numerics.py:217-346 calc_dS_num_error and :742-800 / :978-1016 sanity_check; returns the cell's verdict

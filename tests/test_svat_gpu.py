@@ -252,3 +252,37 @@ def test_average_maximum_minimum_diagnostics_on_the_device():
                 assert util.same_bits(da[k], db[k]), (day, k)
     finally:
         lib().roger_oracle_set_pow(0)
+
+
+def test_lazy_soil_conductivity_and_potential_planes():
+    """The state-only kernels skip k, h of the whole soil column (results nobody reads inside the step); a download, an async
+    snapshot or a plane pointer brings them up to date from theta.  Bit-identical to the oracle, which always evaluates them,
+    and to the flux-storing kernel; masked cells included."""
+    from oracle.engine import OracleSvatEngine, lib
+    from roger_b200 import synth
+    from roger_b200.svat import SvatModel
+
+    lib().roger_oracle_set_pow(1)
+    try:
+        shape = (16, 16)
+        forcing = synth.mixed_forcing(3, seed=3, start_doy=150)
+        prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=5, lateral=True, masked_fraction=0.1)
+        models = [SvatModel(e, shape, forcing, prim, th_rz, th_ss, lateral=True) for e in (_engine(), OracleSvatEngine)]
+        for m in models:
+            m.setup()
+        for step in range(40):
+            for m in models:
+                m.step(write_fluxes=(step % 10 == 9))
+            if step in (0, 7, 9, 10, 39):
+                for n in ("theta", "k", "h"):
+                    assert util.same_bits(models[0].get(n), models[1].get(n)), (step, n)
+        for m in models:  # day-blocked launches leave the planes stale as well
+            m.run_steps(30)
+        eng = models[0].engine
+        pinned = np.empty(shape[0] * shape[1])
+        eng.download_async("k", pinned)
+        eng.download_wait()
+        assert util.same_bits(pinned, models[1].get("k").reshape(-1))
+        assert util.same_bits(models[0].get("h"), models[1].get("h"))
+    finally:
+        lib().roger_oracle_set_pow(0)
