@@ -129,6 +129,15 @@ int roger_svat_set_block_stepping(roger_svat *h, int enabled, int max_block);
 #define ROGER_DIAG_MINIMUM 3 /* running minimum of a 2-D variable,          roger/diagnostics/minimum.py        */
 int roger_svat_set_diagnostics(roger_svat *h, const int *fields, const int *modes, int n);
 int roger_svat_download_diagnostics(roger_svat *h, double *host, int reset);
+/* The same hand-over off the critical path (the reference's writer thread, io_tools/netcdf.py:145-210): the accumulators are
+ * snapshotted on the compute stream, optionally reset, and copied to `host_pinned` on the copy stream while later steps run.
+ * `*count` receives the number of accumulated steps (AVERAGE accumulators are delivered as SUMS: divide by it).
+ * roger_svat_download_fence() marks the copy stream after the transfers issued so far and returns a token (>= 0);
+ * roger_svat_fence_wait(token) blocks until that point is reached and may be called from another thread (it touches no
+ * handle state besides the token's event).  roger_svat_download_wait() still recycles the snapshot buffers. */
+int roger_svat_download_diagnostics_async(roger_svat *h, double *host_pinned, int reset, int64_t *count);
+int roger_svat_download_fence(roger_svat *h);
+int roger_svat_fence_wait(roger_svat *h, int token);
 /* RATE only (modes = NULL) */
 int roger_svat_set_rate_fields(roger_svat *h, const int *fields, int n);
 int roger_svat_download_rates(roger_svat *h, double *host, int reset);

@@ -115,6 +115,28 @@ class OracleSvatEngine:
             self._diag_count = 0
         return out
 
+    # the asynchronous hand-over of roger_b200.engine.CudaSvatEngine, executed synchronously
+    def download_async(self, name, host_pinned):
+        host_pinned[:] = self.download(name).reshape(-1)
+
+    def download_wait(self):
+        pass
+
+    def download_diagnostics_async(self, host_pinned, reset=True):
+        n = len(self._rate_names)
+        host_pinned[: n * self.n] = self._rates.reshape(-1)
+        count = self._diag_count
+        if reset:
+            self._rates[:] = 0
+            self._diag_count = 0
+        return count
+
+    def download_fence(self):
+        return 0
+
+    def fence_wait(self, token):
+        pass
+
     def synchronize(self):
         pass
 

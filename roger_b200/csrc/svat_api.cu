@@ -350,6 +350,9 @@ struct roger_svat {
     cudaStream_t copy_stream = nullptr;          // asynchronous diagnostic read-back (roger_svat_download_async)
     std::vector<double*> snap_free, snap_busy;   // device snapshot planes
     cudaEvent_t ev_snap = nullptr;
+    static constexpr int kFences = 64;           // ring of copy-stream fences (roger_svat_download_fence)
+    cudaEvent_t fences[kFences] = {};
+    int fence_next = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_kernel_ms = 0;
     int64_t last_launches = 0;
@@ -437,6 +440,7 @@ void roger_svat_destroy(roger_svat* h) {
     for (auto p : h->snap_free) cudaFree(p);
     for (auto p : h->snap_busy) cudaFree(p);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+    for (auto& e : h->fences) if (e) cudaEventDestroy(e);
     cudaFree(h->d_rates); cudaFree(h->d_rate_fields);
     cudaFree(h->d_plans); cudaFree(h->d_block_flags);
     if (h->h_plans) cudaFreeHost(h->h_plans);
@@ -472,6 +476,8 @@ int roger_svat_download(roger_svat* h, int field, double* host) {
     return 0;
 }
 
+static int ensure_copy_stream(roger_svat* h);
+
 // Snapshot of a plane as of the steps issued so far, copied to the host off the critical path: a device-to-device copy
 // on the compute stream (microseconds), then the PCIe transfer on a second stream while later steps run.
 int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
@@ -479,10 +485,7 @@ int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
     if (is_soil_kh(field)) { int r = refresh_soil_kh(h); if (r) return r; }
-    if (!h->copy_stream) {
-        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
-    }
+    { int r = ensure_copy_stream(h); if (r) return r; }
     const size_t plane = sizeof(double) * (size_t)h->C;
     double* snap = nullptr;
     if (!h->snap_free.empty()) { snap = h->snap_free.back(); h->snap_free.pop_back(); }
@@ -492,6 +495,57 @@ int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
     CU(cudaEventRecord(h->ev_snap, h->stream));
     CU(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
     CU(cudaMemcpyAsync(host_pinned, snap, plane, cudaMemcpyDeviceToHost, h->copy_stream));
+    return 0;
+}
+
+static int ensure_copy_stream(roger_svat* h) {
+    if (!h->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int roger_svat_download_diagnostics_async(roger_svat* h, double* host_pinned, int reset, int64_t* count) {
+    if (!h || !host_pinned) return fail(ROGER_EINVAL, "roger_svat_download_diagnostics_async: bad argument");
+    if (h->rate_fields.empty()) return fail(ROGER_EINVAL, "roger_svat_download_diagnostics_async: no diagnostics set");
+    CU(cudaSetDevice(h->device));
+    { int r = ensure_copy_stream(h); if (r) return r; }
+    const size_t plane = sizeof(double) * (size_t)h->C;
+    const size_t n = h->rate_fields.size();
+    std::vector<double*> snaps(n);
+    for (size_t k = 0; k < n; k++) {
+        double* snap = nullptr;
+        if (!h->snap_free.empty()) { snap = h->snap_free.back(); h->snap_free.pop_back(); }
+        else CU(cudaMalloc(&snap, plane));
+        h->snap_busy.push_back(snap);
+        snaps[k] = snap;
+        CU(cudaMemcpyAsync(snap, h->d_rates + k * (size_t)h->C, plane, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (reset) CU(cudaMemsetAsync(h->d_rates, 0, plane * n, h->stream));
+    CU(cudaEventRecord(h->ev_snap, h->stream));
+    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    for (size_t k = 0; k < n; k++)
+        CU(cudaMemcpyAsync(host_pinned + k * (size_t)h->C, snaps[k], plane, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (count) *count = h->diag_count;
+    if (reset) h->diag_count = 0;
+    return 0;
+}
+
+int roger_svat_download_fence(roger_svat* h) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_download_fence: null handle");
+    CU(cudaSetDevice(h->device));
+    { int r = ensure_copy_stream(h); if (r) return r; }
+    const int t = h->fence_next;
+    h->fence_next = (h->fence_next + 1) % roger_svat::kFences;
+    if (!h->fences[t]) CU(cudaEventCreateWithFlags(&h->fences[t], cudaEventDisableTiming | cudaEventBlockingSync));
+    CU(cudaEventRecord(h->fences[t], h->copy_stream));
+    return t;
+}
+
+int roger_svat_fence_wait(roger_svat* h, int token) {
+    if (!h || token < 0 || token >= roger_svat::kFences || !h->fences[token]) return fail(ROGER_EINVAL, "roger_svat_fence_wait: bad token");
+    CU(cudaEventSynchronize(h->fences[token]));
     return 0;
 }
 

@@ -43,6 +43,9 @@ def load_library():
     lib.roger_svat_upload.argtypes = [hp, C.c_int, dp]
     lib.roger_svat_download.argtypes = [hp, C.c_int, dp]
     lib.roger_svat_download_async.argtypes = [hp, C.c_int, dp]
+    lib.roger_svat_download_diagnostics_async.argtypes = [hp, dp, C.c_int, C.POINTER(C.c_int64)]
+    lib.roger_svat_download_fence.argtypes = [hp]
+    lib.roger_svat_fence_wait.argtypes = [hp, C.c_int]
     lib.roger_svat_download_wait.argtypes = [hp]
     lib.roger_svat_plane_ptr.argtypes = [hp, C.c_int]
     lib.roger_svat_plane_ptr.restype = C.c_uint64
@@ -133,6 +136,26 @@ class CudaSvatEngine:
 
     def download_wait(self):
         _check(self.lib, self.lib.roger_svat_download_wait(self.h))
+
+    def download_diagnostics_async(self, host_pinned, reset=True):
+        """Hands the accumulators (len(spec), n_cells) to `host_pinned` off the critical path; returns the number of accumulated
+        steps ("average" accumulators arrive as sums).  The buffer is valid after fence_wait(download_fence())."""
+        n = len(self._rate_names)
+        if host_pinned.size != n * self.n or host_pinned.dtype != np.float64 or not host_pinned.flags["C_CONTIGUOUS"]:
+            raise ValueError("download_diagnostics_async: contiguous float64 buffer of (fields, n_cells) values expected")
+        cnt = C.c_int64(0)
+        _check(self.lib, self.lib.roger_svat_download_diagnostics_async(self.h, self._dp(host_pinned), int(bool(reset)), C.byref(cnt)))
+        return int(cnt.value)
+
+    def download_fence(self):
+        t = int(self.lib.roger_svat_download_fence(self.h))
+        if t < 0:
+            _check(self.lib, t)
+        return t
+
+    def fence_wait(self, token):
+        """may be called from another thread"""
+        _check(self.lib, self.lib.roger_svat_fence_wait(self.h, int(token)))
 
     def plane_ptr(self, name):
         return int(self.lib.roger_svat_plane_ptr(self.h, abi.FIELD_ID[name]))

@@ -286,3 +286,25 @@ def test_lazy_soil_conductivity_and_potential_planes():
         assert util.same_bits(models[0].get("h"), models[1].get("h"))
     finally:
         lib().roger_oracle_set_pow(0)
+
+
+def test_async_diagnostic_output_file(tmp_path):
+    """roger_b200.output.AsyncDiagnosticOutput on the CUDA engine (device accumulators, snapshot + copy stream + writer thread):
+    the file holds the same values as the one written from the oracle engine, record by record (rate / average / maximum /
+    minimum / collect), and every record is complete although steps keep running while it is copied and written."""
+    from oracle.engine import OracleSvatEngine, lib
+    from scipy.io import netcdf_file
+
+    from tests.test_output import SPEC, run_with_output
+
+    lib().roger_oracle_set_pow(1)
+    try:
+        pa, pb = str(tmp_path / "cuda.nc"), str(tmp_path / "oracle.nc")
+        run_with_output(_engine(), pa, ndays=4, shape=(24, 20))
+        run_with_output(OracleSvatEngine, pb, ndays=4, shape=(24, 20))
+    finally:
+        lib().roger_oracle_set_pow(0)
+    with netcdf_file(pa, "r", mmap=False) as fa, netcdf_file(pb, "r", mmap=False) as fb:
+        assert np.array_equal(fa.variables["Time"][:], fb.variables["Time"][:]) and fa.variables["Time"].shape == (4,)
+        for name, _ in SPEC:
+            assert util.same_bits(fa.variables[name][:], fb.variables[name][:]), name
