@@ -233,21 +233,22 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM, device-timed ---------------------------------------------
-    ms_by_dt = {}
+    ms_by_dt, n_by_dt = {}, {}
 
     def advance(n):
         """exactly n adaptive steps (day-blocked launches where the scheduler allows); returns {dt_secs: count}"""
         kinds, left = {}, n
         while left > 0:
-            # large grids step one launch at a time (the engine's default there), which also records the dt of each step
+            # the engine batches pre-schedulable steps (one launch per batch on small grids, queued single-step launches on
+            # large ones); last_step_dts() tells which steps they were
             ms0 = eng.kernel_ms
-            done = m.run_steps(1 if C > 262144 else left)
-            sc = eng.get_scalars()
-            if done == 1:
-                kinds[int(sc.dt_secs)] = kinds.get(int(sc.dt_secs), 0) + 1
-                ms_by_dt[int(sc.dt_secs)] = ms_by_dt.get(int(sc.dt_secs), 0.0) + (eng.kernel_ms - ms0)
-            else:
-                kinds["day-blocked"] = kinds.get("day-blocked", 0) + done
+            done = m.run_steps(left)
+            dts = eng.last_step_dts()
+            for d in dts:
+                kinds[d] = kinds.get(d, 0) + 1
+            if len(set(dts)) == 1:
+                ms_by_dt[dts[0]] = ms_by_dt.get(dts[0], 0.0) + (eng.kernel_ms - ms0)
+                n_by_dt[dts[0]] = n_by_dt.get(dts[0], 0) + done
             left -= done
         return kinds
 
@@ -255,6 +256,7 @@ def run_cuda(args):
     sampler.start()
     advance(args.warmup)
     ms_by_dt.clear()
+    n_by_dt.clear()
     barrier()
     sampler.mark()
     eng.kernel_ms = 0.0
@@ -331,7 +333,7 @@ def run_cuda(args):
                          "traffic_source": "profiles/r1_ncu_summary.md (bytes per cell of the captured launch x cells per launch)",
                          "peak_source": peak_src, "algorithmic_bytes_per_cell_timestep": algo,
                          "kernel_ms_per_step": 1e3 * kern_time / args.steps,
-                         "kernel_ms_per_step_by_dt_secs": {k: v / kinds[k] for k, v in ms_by_dt.items() if kinds.get(k)}},
+                         "kernel_ms_per_step_by_dt_secs": {k: v / n_by_dt[k] for k, v in ms_by_dt.items() if n_by_dt.get(k)}},
             "e2e": {"value": e2e_value, "unit": "cell-timesteps/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,

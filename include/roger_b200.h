@@ -117,7 +117,13 @@ int roger_svat_run_day(roger_svat *h, int write_fluxes, int *n_steps);
  * no snow anywhere the scheduler lays out the coming steps in advance and runs them in ONE kernel launch (state re-read
  * from L2 instead of HBM); results are identical to single steps. */
 int roger_svat_run_steps(roger_svat *h, int write_fluxes, int max_steps, int *n_steps);
-/* switch the day-blocked launch off / on (default on) and bound the steps per launch (2..144) */
+/* vs.dt_secs of every step the last roger_svat_step / roger_svat_run_steps / roger_svat_run_day call took (at most `capacity`
+ * values are written); returns their number */
+int roger_svat_last_step_dts(roger_svat *h, int *dt_secs, int capacity);
+/* how such pre-scheduled steps are executed: 0 = never batch (one launch + flag read-back per step), 1 = ONE launch of the
+ * multi-step kernel per batch (default up to 262144 cells), 2 = the ordinary step kernel launched once per step, back to
+ * back, with a single flag read-back (and, on several ranks, a single flag exchange) per batch (default for larger grids;
+ * also with write_fluxes and diagnostics accumulators); max_block bounds the steps per batch (2..144) */
 int roger_svat_set_block_stepping(roger_svat *h, int enabled, int max_block);
 /* ---- diagnostics accumulators on the device (roger/diagnostics/{rate,average,maximum,minimum}.py): the named planes are
  *      folded into accumulator planes after every step (e.g. the daily sums that drive the offline transport model,

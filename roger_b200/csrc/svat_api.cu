@@ -341,7 +341,9 @@ struct roger_svat {
     int64_t diag_count = 0;        // steps accumulated since the last reset (average_nitts)
     // day-blocked stepping (run_block)
     int max_block = 144;
-    bool block_stepping = true;
+    std::vector<int> last_dts;   // dt_secs of every step of the last roger_svat_step / roger_svat_run_steps call
+    int step_batching = 1;   // 0: one launch + flag read-back per step; 1: several steps in ONE launch (k_svat_steps);
+                             // 2: one launch per step, queued back to back with a single read-back per batch
     void* d_plans = nullptr;
     void* h_plans = nullptr;
     unsigned* d_block_flags = nullptr;
@@ -413,7 +415,7 @@ int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settin
     // Day-blocked launches pay off where the per-step launch + flag read-back latency (~35 us) is comparable to the kernel
     // time; on large grids the per-step kernel (4 blocks / SM) is faster per step than the blocked one (measured on B200:
     // 5.8 vs 6.9 ms per step at 4096^2 cells -- the step is bound by dependent-instruction latency, not by HBM).
-    h->block_stepping = n_cells <= 262144;
+    h->step_batching = (n_cells <= 262144) ? 1 : 2;
     const size_t plane = sizeof(double) * (size_t)n_cells;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&h->d_ps, plane * kNumPS));
@@ -850,6 +852,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
 
     finish_step_scalars(h, p, sc);
     sc.sanity_ok = (h->snow_flags & FLAG_INSANE) ? 0 : 1;
+    h->last_dts.push_back((int)sc.dt_secs);
     return 0;
 }
 
@@ -858,7 +861,12 @@ static int step_impl(roger_svat* h, int write_fluxes) {
 // can accrue (interception.py:163, snow.py:14), the flags stay clear, and the schedule of the coming steps -- dt,
 // aggregates, event bookkeeping -- can be laid out in advance and executed by ONE launch (k_svat_steps).  Returns the
 // number of steps executed through *n_done (0: the stretch does not qualify, the caller steps one at a time).
-static int run_block(roger_svat* h, int max_steps, int* n_done) {
+// Steps whose scheduler inputs are all known on the host (spatially uniform forcing, no snow anywhere, every step warmer than
+// ta_fm so that none can accrue) are laid out in advance and executed without a host round trip in between: `queued` = false
+// runs them in ONE launch of k_svat_steps (the state comes back from L2: right for catchment-scale grids), `queued` = true
+// launches the ordinary step kernel once per step, back to back, and reads all flag words back once -- no launch gap, no
+// read-back latency and, on several GPUs, one flag exchange per batch instead of one per step.
+static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int write_fluxes) {
     *n_done = 0;
     const roger_svat_settings& st = h->st;
     if (!st.forcing_uniform || !h->ks_ss_synced || !h->have_forcing || max_steps < 2) return 0;
@@ -871,6 +879,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done) {
     const unsigned sf = 0;  // no snow anywhere, and it stays that way while every step is warm
 
     std::vector<StepPlan> plans;
+    std::vector<int> dts;
     roger_svat_scalars sc = h->sc;  // tentative: committed once the block has run
     const double save_prec = h->u_cur_prec, save_ta = h->u_cur_ta;
     while ((int)plans.size() < max_steps && (int)plans.size() < (int)h->max_block) {
@@ -886,6 +895,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done) {
         finish_step_scalars(h, p, sc_try);
         sc = sc_try;
         plans.push_back(p);
+        dts.push_back((int)sc_try.dt_secs);
         if (sc.time % 86400 == 0) break;  // the next day needs a new forcing block
     }
     if (plans.size() < 2) {  // not worth a block; undo the tentative bookkeeping
@@ -893,24 +903,48 @@ static int run_block(roger_svat* h, int max_steps, int* n_done) {
         return 0;
     }
     const int n = (int)plans.size();
+    if (write_fluxes) { int r = ensure_flux_planes(h); if (r) return r; }
     if (!h->d_plans) {
         CU(cudaMalloc(&h->d_plans, sizeof(StepPlan) * h->max_block));
         CU(cudaMalloc(&h->d_block_flags, sizeof(unsigned) * h->max_block));
         CU(cudaHostAlloc(&h->h_plans, sizeof(StepPlan) * h->max_block, cudaHostAllocDefault));
         CU(cudaHostAlloc(&h->h_block_flags, sizeof(unsigned) * h->max_block, cudaHostAllocDefault));
     }
-    memcpy(h->h_plans, plans.data(), sizeof(StepPlan) * n);
-    const int threads = ROGER_STEPS_BLOCK;
-    const int blocks = (int)((h->C + threads - 1) / threads);
     CU(cudaEventRecord(h->ev0, h->stream));
-    CU(cudaMemcpyAsync(h->d_plans, h->h_plans, sizeof(StepPlan) * n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->d_block_flags, 0, sizeof(unsigned) * n, h->stream));
     const Planes pl = h->planes();
-    if (st.enable_lateral_flow) k_svat_steps<true><<<blocks, threads, 0, h->stream>>>(pl, (const StepPlan*)h->d_plans, n, h->d_block_flags);
-    else k_svat_steps<false><<<blocks, threads, 0, h->stream>>>(pl, (const StepPlan*)h->d_plans, n, h->d_block_flags);
-    h->soil_kh_stale = true;
-    CU(cudaGetLastError());
-    launches++;
+    if (queued) {
+        const int threads = ROGER_BLOCK;
+        const int blocks = (int)((h->C + threads - 1) / threads);
+        for (int k = 0; k < n; k++) {
+            const StepPlan& p = plans[k];
+#define LAUNCH(LAT, FLUX) \
+    k_svat_step<LAT, FLUX><<<blocks, threads, 0, h->stream>>>(pl, h->d_prec_m1, h->forc[1], h->forc[2], p, h->d_block_flags + k)
+            if (st.enable_lateral_flow) { if (write_fluxes) LAUNCH(true, true); else LAUNCH(true, false); }
+            else { if (write_fluxes) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+            CU(cudaGetLastError());
+            launches++;
+            if (!h->rate_fields.empty()) {
+                const int nr = (int)h->rate_fields.size();
+                k_accumulate_rates<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(pl, h->d_rates, h->d_rate_fields, h->d_rate_fields + nr, nr);
+                CU(cudaGetLastError());
+                launches++;
+                h->diag_count++;
+            }
+        }
+        h->soil_kh_stale = !write_fluxes;
+    } else {
+        const int threads = ROGER_STEPS_BLOCK;
+        const int blocks = (int)((h->C + threads - 1) / threads);
+        memcpy(h->h_plans, plans.data(), sizeof(StepPlan) * n);
+        CU(cudaMemcpyAsync(h->d_plans, h->h_plans, sizeof(StepPlan) * n, cudaMemcpyHostToDevice, h->stream));
+        if (st.enable_lateral_flow) k_svat_steps<true><<<blocks, threads, 0, h->stream>>>(pl, (const StepPlan*)h->d_plans, n, h->d_block_flags);
+        else k_svat_steps<false><<<blocks, threads, 0, h->stream>>>(pl, (const StepPlan*)h->d_plans, n, h->d_block_flags);
+        h->soil_kh_stale = true;
+        CU(cudaGetLastError());
+        launches++;
+    }
     CU(cudaMemcpyAsync(h->h_block_flags, h->d_block_flags, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -924,6 +958,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done) {
     h->last_kernel_ms += ms;
     h->last_launches += launches;
     h->snow_flags = words[n - 1] & ~FLAG_INSANE;
+    h->last_dts.insert(h->last_dts.end(), dts.begin(), dts.end());
     h->sc = sc;
     h->sc.sanity_ok = (all & FLAG_INSANE) ? 0 : 1;
     *n_done = n;
@@ -934,6 +969,7 @@ int roger_svat_step(roger_svat* h, int write_fluxes) {
     if (!h) return fail(ROGER_EINVAL, "roger_svat_step: null handle");
     h->last_kernel_ms = 0;
     h->last_launches = 0;
+    h->last_dts.clear();
     return step_impl(h, write_fluxes);
 }
 
@@ -943,11 +979,15 @@ int roger_svat_run_steps(roger_svat* h, int write_fluxes, int max_steps, int* n_
     if (!h || max_steps < 1) return fail(ROGER_EINVAL, "roger_svat_run_steps: bad argument");
     h->last_kernel_ms = 0;
     h->last_launches = 0;
+    h->last_dts.clear();
     int n = 0;
     do {
         int nb = 0;
-        if (!write_fluxes && h->block_stepping && h->rate_fields.empty()) {
-            int r = run_block(h, max_steps - n, &nb);
+        if (h->step_batching == 1 && !write_fluxes && h->rate_fields.empty() && !h->rates_need_flux) {
+            int r = run_block(h, max_steps - n, &nb, false, 0);
+            if (r) return r;
+        } else if (h->step_batching == 2) {
+            int r = run_block(h, max_steps - n, &nb, true, (write_fluxes || h->rates_need_flux) ? 1 : 0);
             if (r) return r;
         }
         if (nb == 0) {
@@ -1022,9 +1062,17 @@ int roger_svat_download_rates(roger_svat* h, double* host, int reset) { return r
 
 uint64_t roger_svat_rates_ptr(roger_svat* h) { return h ? (uint64_t)(uintptr_t)h->d_rates : 0; }
 
+int roger_svat_last_step_dts(roger_svat* h, int* dt_secs, int capacity) {
+    if (!h || (!dt_secs && capacity > 0)) return fail(ROGER_EINVAL, "roger_svat_last_step_dts: bad argument");
+    const int n = (int)h->last_dts.size();
+    for (int k = 0; k < n && k < capacity; k++) dt_secs[k] = h->last_dts[k];
+    return n;
+}
+
 int roger_svat_set_block_stepping(roger_svat* h, int enabled, int max_block) {
     if (!h) return fail(ROGER_EINVAL, "roger_svat_set_block_stepping: null handle");
-    h->block_stepping = enabled != 0;
+    if (enabled < 0 || enabled > 2) return fail(ROGER_EINVAL, "roger_svat_set_block_stepping: mode 0 (off), 1 (one launch per batch) or 2 (queued launches)");
+    h->step_batching = enabled;
     if (max_block >= 2 && max_block <= 144 && !h->d_plans) h->max_block = max_block;
     return 0;
 }

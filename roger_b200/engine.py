@@ -57,6 +57,7 @@ def load_library():
     lib.roger_svat_run_day.argtypes = [hp, C.c_int, C.POINTER(C.c_int)]
     lib.roger_svat_run_steps.argtypes = [hp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.roger_svat_set_block_stepping.argtypes = [hp, C.c_int, C.c_int]
+    lib.roger_svat_last_step_dts.argtypes = [hp, C.POINTER(C.c_int), C.c_int]
     lib.roger_svat_set_rate_fields.argtypes = [hp, C.POINTER(C.c_int), C.c_int]
     lib.roger_svat_set_diagnostics.argtypes = [hp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
     lib.roger_svat_download_diagnostics.argtypes = [hp, dp, C.c_int]
@@ -224,8 +225,18 @@ class CudaSvatEngine:
         _check(self.lib, self.lib.roger_svat_download_rates(self.h, self._dp(out), int(bool(reset))))
         return dict(zip(self._rate_names, out))
 
+    def last_step_dts(self):
+        """dt_secs of every step of the last step() / run_steps() call"""
+        buf = (C.c_int * 144)()
+        n = int(self.lib.roger_svat_last_step_dts(self.h, buf, 144))
+        if n < 0:
+            _check(self.lib, n)
+        return [int(buf[k]) for k in range(min(n, 144))]
+
     def set_block_stepping(self, enabled, max_block=0):
-        _check(self.lib, self.lib.roger_svat_set_block_stepping(self.h, int(bool(enabled)), int(max_block)))
+        """enabled: False / 0 one launch and one flag read-back per step; True / 1 several steps in one launch (default up to
+        262144 cells); 2 one launch per step queued back to back, one read-back per batch (default for larger grids)"""
+        _check(self.lib, self.lib.roger_svat_set_block_stepping(self.h, int(enabled), int(max_block)))
 
     def synchronize(self):
         _check(self.lib, self.lib.roger_svat_synchronize(self.h))

@@ -93,28 +93,31 @@ def test_day_blocked_stepping_equals_single_steps(lateral, doy, ndays):
     shape = (24, 16)
     forcing = synth.mixed_forcing(ndays + 1, seed=42, start_doy=doy)
     prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, lateral=lateral, lu_choices=(10, 11, 12, 8, 5, 9))
-    models = [SvatModel(_engine(), shape, forcing, prim, th_rz, th_ss, lateral=lateral) for _ in range(2)]
+    models = [SvatModel(_engine(), shape, forcing, prim, th_rz, th_ss, lateral=lateral) for _ in range(3)]
     for m in models:
         m.setup()
-    models[1].engine.set_block_stepping(False)
-    launches = [0, 0]
+    models[1].engine.set_block_stepping(0)  # one launch and one flag read-back per step
+    models[2].engine.set_block_stepping(2)  # queued single-step launches, one read-back per batch (the default of large grids)
     kinds = {n: k for n, k in zip(abi.FIELD_NAMES, abi.FIELD_KINDS)}
     total = 0
     for day in range(ndays):
         n0 = models[0].run_steps(144)
         n1 = models[1].run_steps(144)
-        assert n0 == n1
+        n2 = models[2].run_steps(144)
+        assert n0 == n1 == n2
         total += n0
-        a, b = models[0].engine.get_scalars(), models[1].engine.get_scalars()
-        for k in ("time", "itt", "dt_secs", "itt_day", "event_id_counter", "time_event0", "dt", "sanity_ok"):
-            assert getattr(a, k) == getattr(b, k), (day, k)
-        assert list(a.event_id) == list(b.event_id)
-        for n in abi.FIELD_NAMES:
-            if kinds[n] == "S" or n == "ks_ss":
-                x, y = models[0].get(n), models[1].get(n)
-                assert np.array_equal(x, y, equal_nan=True), (day, n)
+        b = models[1].engine.get_scalars()
+        for m in (models[0], models[2]):
+            a = m.engine.get_scalars()
+            for k in ("time", "itt", "dt_secs", "itt_day", "event_id_counter", "time_event0", "dt", "sanity_ok"):
+                assert getattr(a, k) == getattr(b, k), (day, k)
+            assert list(a.event_id) == list(b.event_id)
+            for n in abi.FIELD_NAMES:
+                if kinds[n] == "S" or n == "ks_ss":
+                    x, y = m.get(n), models[1].get(n)
+                    assert np.array_equal(x, y, equal_nan=True), (day, n)
     launches = [m.engine.launches for m in models]
-    assert launches[1] >= total
+    assert launches[1] >= total and launches[2] >= total
     if doy == 121:
         assert launches[0] < launches[1] / 3  # the blocked path really ran
 
