@@ -701,8 +701,9 @@ static double euler_flux_conc(int A, const double *mtt, const double *tt, double
 }
 
 static void euler_substep_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss,
-                               const double *forcing, double m, const double *sas_params, double *out, double *tt_out, double *work)
-{
+                               const double *forcing, double m, const double *sas_params, double *out, double *tt_base, size_t tt_stride,
+                               double *work)
+{ /* tt_base (may be NULL): this cell's travel-time distributions, process p at tt_base + p * tt_stride */
 #define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
 #define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
 #define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)
@@ -751,7 +752,7 @@ static void euler_substep_cell(const sas_ctx *c, int64_t C, int64_t i, double *s
             for (int j = 0; j < A; j++) mtt[j] = (tts[k][j] > 0) ? src[k][j] : 0;
             O(oc[k]) = euler_flux_conc(A, mtt, tts[k], tmp) * m;
             O(oi[k]) = conc_to_delta(c, O(oc[k])) * m;
-            if (tt_out) memcpy(tt_out + ((size_t)pr[k] * (size_t)C + (size_t)i) * A, tts[k], sizeof(double) * A);
+            if (tt_base) memcpy(tt_base + (size_t)pr[k] * tt_stride, tts[k], sizeof(double) * A);
         }
         O(RSO_C_inf_mat_rz) = ((inf_mat > 0) ? C_in : NAN) * m;
         O(RSO_C_inf_pf_rz) = ((inf_pf > 0) ? C_in : NAN) * m;
@@ -809,7 +810,8 @@ static void storage_kernels_iso(const sas_ctx *c, int64_t C, int64_t i, double *
 
 /* one day = `substeps` explicit Euler steps of every cell, ageing with the last one (transport.py:3221-3258) */
 static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, double *sa_ss, double *msa_rz, double *msa_ss,
-                      const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out)
+                      const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
+                      double *stats, double *balance_prev)
 {
     sas_ctx ctx = {st->ages, st->substeps, st->VSMOW_conc18O, st->d18O_min, st->d18O_max};
     const int A = ctx.A;
@@ -817,20 +819,90 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
     {
         double *work = (double *)malloc(sizeof(double) * (size_t)(16 * (A + 2)));
         double *tmp = (double *)malloc(sizeof(double) * (size_t)(4 * (A + 2)));
+        double *ttk = (double *)malloc(sizeof(double) * (size_t)(RSP_COUNT * A)); /* tt of the last Euler step (statistics) */
+        double *ages = (double *)malloc(sizeof(double) * (size_t)A);
+        for (int j = 0; j < A; j++) ages[j] = (double)(j + 1);
 #pragma omp for schedule(static)
         for (int64_t i = 0; i < C; i++) {
             const double m = mask[i];
             double *s_rz = sa_rz + (size_t)i * A, *s_ss = sa_ss + (size_t)i * A;
             double *ms_rz = msa_rz + (size_t)i * A, *ms_ss = msa_ss + (size_t)i * A;
+#define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
+#define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
+#define ST(k) stats[(size_t)(k) * (size_t)C + (size_t)i]
+            double sum_sa_s_m1 = 0, Cp = 0;
             for (int s = 0; s < ctx.substeps; s++) {
-                euler_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out, work);
+                const int last = (s == ctx.substeps - 1);
+                if (stats && last) { /* [taum1] of the last Euler step: the state its predecessor left (after_substep_iso :3421) */
+                    for (int j = 0; j < A; j++) tmp[j] = s_rz[j] + s_ss[j] * m;
+                    sum_sa_s_m1 = np_sum(tmp, A);
+                    Cp = (ctx.substeps > 1) ? O(RSO_C_s) : balance_prev[i];
+                }
+                if (tt_out) euler_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out + (size_t)i * A, (size_t)C * A, work);
+                else euler_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, (stats && last) ? ttk : NULL, (size_t)A, work);
                 storage_kernels_iso(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
             }
+            if (stats) { /* age statistics (transport.py:59-312) and balance errors (numerics.py:424-445, :476-516, :1051-1122) of the
+                          * last Euler step; the right-hand sides carry settings.h */
+                const double h = 1.0 / ctx.substeps;
+                const double *TT[RSP_COUNT];
+                for (int p = 0; p < RSP_COUNT; p++) TT[p] = tt_out ? tt_out + ((size_t)p * (size_t)C + (size_t)i) * A : ttk + (size_t)p * A;
+                const double p5[5] = {0.1, 0.25, 0.5, 0.75, 0.9}, p3[3] = {0.25, 0.5, 0.75};
+                double s5[5], s3[3], avg;
+                double *sa_s = tmp + (A + 2);
+                for (int j = 0; j < A; j++) sa_s[j] = s_rz[j] + s_ss[j] * m;
+                flux_age_statistics(A, TT[RSP_transp], ages, work, s5, &avg);
+                for (int k = 0; k < 5; k++) ST(RSS_tt10_transp + k) = s5[k];
+                ST(RSS_ttavg_transp) = avg;
+                flux_age_statistics(A, TT[RSP_q_ss], ages, work, s5, &avg);
+                for (int k = 0; k < 5; k++) ST(RSS_tt10_q_ss + k) = s5[k];
+                ST(RSS_ttavg_q_ss) = avg;
+                storage_age_statistics(A, s_rz, m, ages, work, p3, 3, s3, &avg);
+                for (int k = 0; k < 3; k++) ST(RSS_rt25_rz + k) = s3[k];
+                ST(RSS_rtavg_rz) = avg;
+                storage_age_statistics(A, s_ss, m, ages, work, p3, 3, s3, &avg);
+                for (int k = 0; k < 3; k++) ST(RSS_rt25_ss + k) = s3[k];
+                ST(RSS_rtavg_ss) = avg;
+                storage_age_statistics(A, sa_s, m, ages, work, p5, 5, s5, &avg);
+                for (int k = 0; k < 5; k++) ST(RSS_rt10_s + k) = s5[k];
+                ST(RSS_rtavg_s) = avg;
+                const double sum_s = np_sum(sa_s, A);
+                double w[3];
+                const int procs[3] = {RSP_evap_soil, RSP_transp, RSP_q_ss};
+                const double flx[3] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_ss)};
+                for (int k = 0; k < 3; k++) {
+                    for (int j = 0; j < A; j++) tmp[j] = flx[k] * TT[procs[k]][j];
+                    w[k] = np_sum(tmp, A);
+                }
+                const double lhs1 = sum_s - sum_sa_s_m1;
+                const double rhs1 = (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - w[0] - w[1] - w[2]) * h;
+                const double lhs2 = sum_s * O(RSO_C_s) - sum_sa_s_m1 * Cp;
+                const double rhs2 = (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                                     F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[0] * nan0(O(RSO_C_evap_soil)) -
+                                     w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss))) * h;
+                ST(RSS_dS_num_error) = fabs(lhs1 - rhs1);
+                ST(RSS_dC_num_error) = fabs(lhs2 - rhs2);
+                const int c1 = (m != 0) ? np_isclose(lhs1, rhs1, g_rtol, g_atol) : 1;
+                const int c2 = (m != 0) ? np_isclose(lhs2, rhs2, g_rtol, g_atol) : 1;
+                const double sat_rz = g_bounds[0] ? g_bounds[0][i] : INFINITY, sat_ss = g_bounds[1] ? g_bounds[1][i] : INFINITY;
+                const double pwp_rz = g_bounds[2] ? g_bounds[2][i] : 0.0, pwp_ss = g_bounds[3] ? g_bounds[3][i] : 0.0;
+                const double sum_rz = np_sum(s_rz, A), sum_ss = np_sum(s_ss, A);
+                const int b3 = (sum_s <= (sat_rz + sat_ss) - (pwp_rz + pwp_ss)) && (sum_s >= 0);
+                const int b4 = (sum_rz <= sat_rz - pwp_rz) && (sum_rz >= 0);
+                const int b5 = (sum_ss <= sat_ss - pwp_ss) && (sum_ss >= 0);
+                ST(RSS_sanity_ok) = (c1 && c2 && b3 && b4 && b5) ? 1.0 : 0.0;
+                balance_prev[i] = O(RSO_C_s);
+            }
+#undef F
+#undef O
+#undef ST
             ageing(A, s_rz, ms_rz);
             ageing(A, s_ss, ms_ss);
         }
         free(work);
         free(tmp);
+        free(ttk);
+        free(ages);
     }
 }
 
@@ -849,8 +921,8 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
                           const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
                           double *stats, double *balance_prev)
 {
-    if (st->solver == 1) { /* explicit Euler: isotope branch, no statistics (callers check) */
-        euler_day(C, st, sa_rz, sa_ss, msa_rz, msa_ss, forcing, mask, sas_params, out, tt_out);
+    if (st->solver == 1) { /* explicit Euler: isotope branch (callers check) */
+        euler_day(C, st, sa_rz, sa_ss, msa_rz, msa_ss, forcing, mask, sas_params, out, tt_out, stats, balance_prev);
         return;
     }
     sas_ctx ctx = {st->ages, st->substeps, st->VSMOW_conc18O, st->d18O_min, st->d18O_max};
