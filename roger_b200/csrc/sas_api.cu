@@ -174,9 +174,11 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
 #ifndef ROGER_EULER_MIN_BLOCKS
 #define ROGER_EULER_MIN_BLOCKS 1
 #endif
+template <bool STATS>
 __global__ void __launch_bounds__(ROGER_EULER_BLOCK, ROGER_EULER_MIN_BLOCKS)
 k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
-                const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out) {
+                const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out,
+                double* __restrict__ stats, double* __restrict__ C_s_prev, const double* __restrict__ bounds, double atol, double rtol) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
     __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
     for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
@@ -187,7 +189,7 @@ k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
-    euler_day(cx, forcing, mask[i], sas_params, out);
+    euler_day<STATS>(cx, forcing, mask[i], sas_params, out, stats, C_s_prev, bounds, atol, rtol);
 }
 
 // (cells, A) row-major staging block <-> age-major planes, 32 x 32 tiles through shared memory
@@ -370,8 +372,8 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
     if (settings->solute != 0 && settings->solute != 1) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope) or 1 (anion)");
     if (settings->solver != 0 && settings->solver != 1) return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic) or 1 (Euler)");
-    if (settings->solver == 1 && (settings->solute != 0 || settings->age_statistics))
-        return fail(ROGER_ENOTSUP, "roger_sas_create: the explicit Euler solver covers the isotope branch without age statistics");
+    if (settings->solver == 1 && settings->solute != 0)
+        return fail(ROGER_ENOTSUP, "roger_sas_create: the explicit Euler solver covers the isotope branch (oxygen-18 / deuterium)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -506,7 +508,12 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     const int blocks = (int)((h->C + threads - 1) / threads);
     if (h->st.solver == 1) {
         const int eb = (int)((h->C + ROGER_EULER_BLOCK - 1) / ROGER_EULER_BLOCK);
-        k_sas_day_euler<<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out);
+        if (h->st.age_statistics)
+            k_sas_day_euler<true><<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
+                                                                           h->d_out, h->d_stats, h->d_C_s_prev, h->d_bounds, h->atol, h->rtol);
+        else
+            k_sas_day_euler<false><<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
+                                                                            h->d_out, nullptr, nullptr, nullptr, 0.0, 0.0);
     } else if (h->st.solute == 1) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};

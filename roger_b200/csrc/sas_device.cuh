@@ -1194,9 +1194,15 @@ __device__ __forceinline__ double euler_mix(double msa, double sa, double dsa1, 
     return v;
 }
 
-template <bool LAST>
+struct EulerStats {  // diagnostics of the day's last Euler step (STATS kernels): evap_soil, transp, q_ss
+    double wsum[3];    // sum(flux * tt), numerics.py:437-439
+    double pct[2][5];  // percentile ages of the transpiration / subsoil-percolation travel-time distributions
+    double avg[2];     // mean travel times
+};
+
+template <bool LAST, bool STATS>
 __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
-                                        double* __restrict__ out) {
+                                        double* __restrict__ out, EulerStats* es) {
     const SasParams& P = cx.P;
     const int A = P.A;
     const int64_t C = P.C, i = cx.i;
@@ -1318,6 +1324,14 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
         const double evap = fx[0].flux, transp = fx[1].flux, q_rz = fx[2].flux, cpr = fx[3].flux, q_ss = fx[4].flux;
         double* __restrict__ tt_base = (LAST && P.store_tt && cx.pl.tt) ? cx.pl.tt : nullptr;
+        PctTracker trk[(LAST && STATS) ? 10 : 1];
+        double cdf_t = 0, cdf_s = 0;
+        NpMax cmax_t, cmax_s;
+        if (LAST && STATS) {
+            const double pcts[5] = {0.1, 0.25, 0.5, 0.75, 0.9};
+#pragma unroll
+            for (int k = 0; k < 5; k++) { trk[k].init(pcts[k]); trk[5 + k].init(pcts[k]); }
+        }
         auto bin = [&](int j, const double* L, double* v) {
             const int64_t o = cx.ring(j);
             const double a = L[0], b = L[1];
@@ -1348,6 +1362,15 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
                 v[4] = tt_q; v[5] = mtt_q * tt_q;
                 v[6] = tt_c; v[7] = mtt_c * tt_c;
                 v[8] = tt_s; v[9] = ((tt_s > 0) ? mb : 0) * tt_s;
+                if (STATS) {  // transport.py:59-152 (TT[1:] = cumsum(tt)), numerics.py:437-439
+                    v[10] = evap * tt_e; v[11] = transp * tt_t; v[12] = q_ss * tt_s;
+                    v[13] = (double)(j + 1) * tt_t; v[14] = (double)(j + 1) * tt_s;
+                    cdf_t += tt_t;
+                    cdf_s += tt_s;
+                    if (j == 0) { cmax_t.init(cdf_t); cmax_s.init(cdf_s); } else { cmax_t.push(cdf_t); cmax_s.push(cdf_s); }
+#pragma unroll
+                    for (int k = 0; k < 5; k++) { trk[k].push(j, cdf_t); trk[5 + k].push(j, cdf_s); }
+                }
                 if (tt_base) {
                     const int64_t span = (int64_t)A * C, l = cx.lin(j);
                     tt_base[RSP_evap_soil * span + l] = tt_e;
@@ -1385,8 +1408,17 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             L[0] = s_rz[o]; L[1] = s_ss[o]; L[2] = m_rz[o]; L[3] = m_ss[o];
         };
         if (LAST) {
-            double sums[10];
-            EULER_SUMS<10, 4>(cx.plan, EULER_SUMS_ARG load, bin, sums);
+            constexpr int NS = STATS ? 15 : 10;
+            double sums[NS];
+            EULER_SUMS<NS, 4>(cx.plan, EULER_SUMS_ARG load, bin, sums);
+            if (STATS && es) {
+                const double qn = __longlong_as_double(0x7ff8000000000000LL);
+                es->wsum[0] = sums[NS - 5]; es->wsum[1] = sums[NS - 4]; es->wsum[2] = sums[NS - 3];
+#pragma unroll
+                for (int k = 0; k < 5; k++) { es->pct[0][k] = trk[k].result(A, cmax_t.get()); es->pct[1][k] = trk[(STATS ? 5 : 0) + k].result(A, cmax_s.get()); }
+                es->avg[0] = (sums[2] > 0) ? sums[NS - 2] : qn;
+                es->avg[1] = (sums[8] > 0) ? sums[NS - 1] : qn;
+            }
             // calc_conc_iso_flux :512-535, delta_fluxes_svat :3659-3697
             const int oc[5] = {RSO_C_evap_soil, RSO_C_transp, RSO_C_q_rz, RSO_C_cpr_rz, RSO_C_q_ss};
             const int oi[5] = {RSO_C_iso_evap_soil, RSO_C_iso_transp, RSO_C_iso_q_rz, RSO_C_iso_cpr_rz, RSO_C_iso_q_ss};
@@ -1418,12 +1450,75 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
 #undef SP
 }
 
+template <bool STATS>
 __device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
-                                          double* __restrict__ out) {
-    for (int s = 0; s + 1 < cx.P.substeps; s++) euler_step<false>(cx, forcing, m, sas_params, out);
-    euler_step<true>(cx, forcing, m, sas_params, out);
+                                          double* __restrict__ out, double* __restrict__ stats, double* __restrict__ C_s_prev,
+                                          const double* __restrict__ bounds, double atol, double rtol) {
+    const SasParams& P = cx.P;
+    const int64_t C = P.C, i = cx.i;
+    const int n = P.substeps;
+    for (int s = 0; s + 2 < n; s++) euler_step<false, false>(cx, forcing, m, sas_params, out, nullptr);
+    if (n > 1) euler_step<false, false>(cx, forcing, m, sas_params, out, nullptr);
     double sum_sa_s, C_s, sum_sa_rz, sum_sa_ss;
-    storage_concentrations(cx, m, out, cx.P.C, &sum_sa_s, &C_s, &sum_sa_rz, &sum_sa_ss);
+    double sum_sa_s_m1 = 0, Cp = 0;
+    if (STATS) {  // [taum1] of the last Euler step: what its predecessor left (after_substep_iso, transport.py:3421-3520)
+        if (n > 1) {
+            storage_concentrations(cx, m, out, C, &sum_sa_s, &C_s, &sum_sa_rz, &sum_sa_ss);
+            Cp = C_s;
+        } else Cp = C_s_prev[i];
+        double sm[1];
+        stream_sums<1, 2>(cx.plan,
+            [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = cx.pl.sa[0][o]; L[1] = cx.pl.sa[1][o]; },
+            [&](int, const double* L, double* v) { v[0] = L[0] + L[1] * m; }, sm);
+        sum_sa_s_m1 = sm[0];
+    }
+    EulerStats es;
+    euler_step<true, STATS>(cx, forcing, m, sas_params, out, &es);
+    storage_concentrations(cx, m, out, C, &sum_sa_s, &C_s, &sum_sa_rz, &sum_sa_ss);
+    if (STATS) {
+#define F(k) forcing[(int64_t)(k) * C + i]
+#define O(k) out[(int64_t)(k) * C + i]
+#define ST(k) stats[(int64_t)(k) * C + i]
+        for (int k = 0; k < 5; k++) { ST(RSS_tt10_transp + k) = es.pct[0][k]; ST(RSS_tt10_q_ss + k) = es.pct[1][k]; }
+        ST(RSS_ttavg_transp) = es.avg[0];
+        ST(RSS_ttavg_q_ss) = es.avg[1];
+        const double p5[5] = {0.1, 0.25, 0.5, 0.75, 0.9}, p3[3] = {0.25, 0.5, 0.75};
+        double pc[5], avg;
+        storage_age_statistics(cx, 0, m, 3, p3, pc, &avg);
+        for (int k = 0; k < 3; k++) ST(RSS_rt25_rz + k) = pc[k];
+        ST(RSS_rtavg_rz) = avg;
+        storage_age_statistics(cx, 1, m, 3, p3, pc, &avg);
+        for (int k = 0; k < 3; k++) ST(RSS_rt25_ss + k) = pc[k];
+        ST(RSS_rtavg_ss) = avg;
+        storage_age_statistics(cx, 2, m, 5, p5, pc, &avg);
+        for (int k = 0; k < 5; k++) ST(RSS_rt10_s + k) = pc[k];
+        ST(RSS_rtavg_s) = avg;
+        // numerics.py:424-445, :476-516, :1051-1122: the right-hand sides carry settings.h = 1 / substeps
+        auto nan0 = [](double x) { return (x != x) ? 0.0 : x; };
+        const double h = 1.0 / (double)n;
+        const double lhs1 = sum_sa_s - sum_sa_s_m1;
+        const double rhs1 = (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - es.wsum[0] - es.wsum[1] - es.wsum[2]) * h;
+        const double lhs2 = sum_sa_s * C_s - sum_sa_s_m1 * Cp;
+        const double rhs2 = (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                             F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - es.wsum[0] * nan0(O(RSO_C_evap_soil)) -
+                             es.wsum[1] * nan0(O(RSO_C_transp)) - es.wsum[2] * nan0(O(RSO_C_q_ss))) * h;
+        ST(RSS_dS_num_error) = fabs(lhs1 - rhs1);
+        ST(RSS_dC_num_error) = fabs(lhs2 - rhs2);
+        auto isclose = [&](double x, double y) { return ((fabs(x - y) <= atol + rtol * fabs(y)) && isfinite(y)) || (x == y); };
+        const bool c1 = (m != 0) ? isclose(lhs1, rhs1) : true;
+        const bool c2 = (m != 0) ? isclose(lhs2, rhs2) : true;
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        const double sat_rz = bounds ? bounds[i] : inf, sat_ss = bounds ? bounds[C + i] : inf;
+        const double pwp_rz = bounds ? bounds[2 * C + i] : 0.0, pwp_ss = bounds ? bounds[3 * C + i] : 0.0;
+        const bool b3 = (sum_sa_s <= (sat_rz + sat_ss) - (pwp_rz + pwp_ss)) && (sum_sa_s >= 0);
+        const bool b4 = (sum_sa_rz <= sat_rz - pwp_rz) && (sum_sa_rz >= 0);
+        const bool b5 = (sum_sa_ss <= sat_ss - pwp_ss) && (sum_sa_ss >= 0);
+        ST(RSS_sanity_ok) = (c1 && c2 && b3 && b4 && b5) ? 1.0 : 0.0;
+        C_s_prev[i] = C_s;
+#undef F
+#undef O
+#undef ST
+    }
     ageing(cx);
 }
 
