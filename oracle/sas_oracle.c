@@ -784,6 +784,109 @@ static void euler_substep_cell(const sas_ctx *c, int64_t C, int64_t i, double *s
 #undef SP
 }
 
+/* one explicit Euler step, anion branch (bromide / chloride; transport.py:2144-2156, :2320-2343, :2378-2407): msa holds
+ * solute mass per bin; calc_mtt (:582-596) without the deterministic kernels' crop switch */
+static void euler_substep_cell_anion(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss,
+                                     const double *forcing, double m, const double *sas_params, double *out, double *tt_base,
+                                     size_t tt_stride, double *work)
+{
+#define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
+#define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
+#define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)
+    const int A = c->A, N = A + 1;
+    const double h = 1.0 / c->substeps;
+    double *SA_rz = work, *SA_ss = SA_rz + N, *tt_e = SA_ss + N, *tt_t = tt_e + N, *tt_q = tt_t + N, *tt_c = tt_q + N, *tt_s = tt_c + N;
+    double *mtt_t = tt_s + N, *mtt_q = mtt_t + N, *mtt_c = mtt_q + N, *mtt_s = mtt_c + N, *w2 = mtt_s + N;
+    const double inf_mat = F(RSF_inf_mat_rz), inf_pf = F(RSF_inf_pf_rz), inf_ss = F(RSF_inf_pf_ss), C_in = F(RSF_C_in);
+    const double evap = F(RSF_evap_soil), transp = F(RSF_transp), q_rz = F(RSF_q_rz), q_ss = F(RSF_q_ss), cpr = F(RSF_cpr_rz);
+    const double alpha_t = g_anion[0] ? g_anion[0][i] : 1.0, alpha_q = g_anion[1] ? g_anion[1][i] : 1.0;
+    /* upper boundary condition: water by the infiltration, solute as mtt_inf * h with mtt_inf[0] = C_in * mask (:2089-2101) */
+    for (int j = 0; j < A; j++) {
+        const double tt_im = (j == 0) ? ((inf_mat > 0) ? 1 : 0) * m : 0.0, tt_ip = (j == 0) ? ((inf_pf > 0) ? 1 : 0) * m : 0.0;
+        const double tt_is = (j == 0) ? ((inf_ss > 0) ? 1 : 0) * m : 0.0;
+        const double mtt_i = (j == 0) ? C_in * m : 0.0; /* the same value in all three infiltration arrays */
+        s_rz[j] += (inf_mat * tt_im + inf_pf * tt_ip) * h;
+        s_ss[j] += (inf_ss * tt_is) * h;
+        ms_rz[j] += nan0(mtt_i) * h + nan0(mtt_i) * h;
+        ms_ss[j] += nan0(mtt_i) * h;
+    }
+    calc_SA(A, s_rz, SA_rz);
+    for (int j = 0; j < N; j++) SA_rz[j] = SA_rz[j] * m;
+    calc_SA(A, s_ss, SA_ss);
+    for (int j = 0; j < N; j++) SA_ss[j] = SA_ss[j] * m;
+    euler_tt(c, SA_rz, SP(RSP_evap_soil), evap * h, m, tt_e, w2);
+    euler_tt(c, SA_rz, SP(RSP_transp), transp * h, m, tt_t, w2);
+    euler_tt(c, SA_rz, SP(RSP_q_rz), q_rz * h, m, tt_q, w2);
+    euler_tt(c, SA_ss, SP(RSP_cpr_rz), cpr * h, m, tt_c, w2);
+    euler_tt(c, SA_ss, SP(RSP_q_ss), q_ss * h, m, tt_s, w2);
+    anion_mtt(A, s_rz, tt_t, transp * h, ms_rz, alpha_t, 1.0, mtt_t);
+    anion_mtt(A, s_rz, tt_q, q_rz * h, ms_rz, alpha_q, 1.0, mtt_q);
+    anion_mtt(A, s_ss, tt_c, cpr * h, ms_ss, alpha_q, 1.0, mtt_c);
+    anion_mtt(A, s_ss, tt_s, q_ss * h, ms_ss, alpha_q, 1.0, mtt_s);
+    if (tt_base) {
+        const double *tts[5] = {tt_e, tt_t, tt_q, tt_c, tt_s};
+        const int pr[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
+        for (int k = 0; k < 5; k++) memcpy(tt_base + (size_t)pr[k] * tt_stride, tts[k], sizeof(double) * A);
+    }
+    /* concentrations :2378-2407 from the solute travel-time distributions of this step */
+    O(RSO_C_inf_mat_rz) = ((inf_mat * h > 0) ? C_in : 0) * m;
+    O(RSO_C_inf_pf_rz) = ((inf_pf * h > 0) ? C_in : 0) * m;
+    O(RSO_C_inf_pf_ss) = ((inf_ss * h > 0) ? C_in : 0) * m;
+    O(RSO_C_transp) = ((transp > 0) ? np_sum(mtt_t, A) / (transp * h) : 0) * m;
+    O(RSO_C_q_rz) = ((q_rz > 0) ? np_sum(mtt_q, A) / (q_rz * h) : 0) * m;
+    O(RSO_C_cpr_rz) = ((cpr > 0) ? np_sum(mtt_c, A) / (cpr * h) : 0) * m;
+    O(RSO_C_q_ss) = ((q_ss > 0) ? np_sum(mtt_s, A) / (q_ss * h) : 0) * m;
+    /* update :2320-2343 */
+    for (int j = 0; j < A; j++) {
+        double dsa_rz = (cpr * tt_c[j] - evap * tt_e[j] - transp * tt_t[j] - q_rz * tt_q[j]) * h;
+        dsa_rz = (s_rz[j] + dsa_rz < 0) ? -s_rz[j] : dsa_rz;
+        double dsa_ss = (q_rz * tt_q[j] - cpr * tt_c[j] - q_ss * tt_s[j]) * h;
+        dsa_ss = (s_ss[j] + dsa_ss < 0) ? -s_ss[j] : dsa_ss;
+        s_rz[j] += dsa_rz;
+        s_ss[j] += dsa_ss;
+        double dmsa_rz = nan0(mtt_c[j]) - nan0(mtt_t[j]) - nan0(mtt_q[j]);
+        double dmsa_ss = nan0(mtt_q[j]) - nan0(mtt_c[j]) - nan0(mtt_s[j]);
+        dmsa_rz = (ms_rz[j] + dmsa_rz < 0) ? 0 : dmsa_rz;
+        dmsa_ss = (ms_ss[j] + dmsa_ss < 0) ? 0 : dmsa_ss;
+        ms_rz[j] += dmsa_rz;
+        ms_ss[j] += dmsa_ss;
+    }
+#undef F
+#undef O
+#undef SP
+}
+
+/* anion storage kernels (root_zone.py:219-258, subsoil.py, soil.py anion kernels) */
+static void storage_kernels_anion(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss, double m,
+                                  double *out, double *tmp)
+{
+#define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
+    const int A = c->A;
+    for (int j = 0; j < A; j++) s_rz[j] = (s_rz[j] < 1e-8) ? 0 : s_rz[j];
+    for (int j = 0; j < A; j++) ms_rz[j] = (s_rz[j] <= 0) ? 0 : ms_rz[j];
+    {
+        const double M = np_nansum(ms_rz, A, tmp) * m, S = np_sum(s_rz, A);
+        O(RSO_C_iso_rz) = M;
+        O(RSO_C_rz) = (S > 0) ? M / S : 0;
+    }
+    for (int j = 0; j < A; j++) s_ss[j] = (s_ss[j] < 1e-8) ? 0 : s_ss[j];
+    for (int j = 0; j < A; j++) ms_ss[j] = (s_ss[j] <= 0) ? 0 : ms_ss[j];
+    {
+        const double M = np_nansum(ms_ss, A, tmp) * m, S = np_sum(s_ss, A);
+        O(RSO_C_iso_ss) = M;
+        O(RSO_C_ss) = (S > 0) ? M / S : 0;
+    }
+    double *sa_s = tmp + (A + 2), *msa_s = sa_s + (A + 2);
+    for (int j = 0; j < A; j++) {
+        sa_s[j] = s_rz[j] + s_ss[j] * m;
+        msa_s[j] = ms_rz[j] + ms_ss[j] * m;
+    }
+    const double M = np_nansum(msa_s, A, tmp) * m, S = np_sum(sa_s, A);
+    O(RSO_C_iso_s) = M;
+    O(RSO_C_s) = (S > 0) ? M / S : 0;
+#undef O
+}
+
 /* storage kernels root_zone.py:189-215, subsoil.py:153-180, soil.py:1036-1092 (run after every Euler sub-step) */
 static void storage_kernels_iso(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, const double *ms_rz, const double *ms_ss,
                                 double m, double *out, double *tmp)
@@ -838,9 +941,20 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
                     sum_sa_s_m1 = np_sum(tmp, A);
                     Cp = (ctx.substeps > 1) ? O(RSO_C_s) : balance_prev[i];
                 }
+                if (st->solute == 1) {
+                    euler_substep_cell_anion(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out,
+                                             tt_out ? tt_out + (size_t)i * A : NULL, (size_t)C * A, work);
+                    storage_kernels_anion(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
+                    continue;
+                }
                 if (tt_out) euler_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out + (size_t)i * A, (size_t)C * A, work);
                 else euler_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, (stats && last) ? ttk : NULL, (size_t)A, work);
                 storage_kernels_iso(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
+            }
+            if (st->solute == 1) {
+                anion_ageing(A, s_rz, ms_rz);
+                anion_ageing(A, s_ss, ms_ss);
+                continue;
             }
             if (stats) { /* age statistics (transport.py:59-312) and balance errors (numerics.py:424-445, :476-516, :1051-1122) of the
                           * last Euler step; the right-hand sides carry settings.h */

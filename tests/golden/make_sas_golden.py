@@ -52,6 +52,8 @@ CASES = {
                       sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     "sas_euler_stats": dict(shape=(2, 2), ndays=14, ages=40, doy=105, sas_solver="Euler", age_statistics=True,
                             sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
+    "sas_euler_bromide": dict(shape=(2, 3), ndays=20, ages=50, doy=100, solute="bromide", sas_solver="Euler",
+                              sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
     "sas_euler_families": dict(shape=(2, 2), ndays=22, ages=45, doy=20, sas_solver="Euler", var_input=True,
                                sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0),
                                         q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
