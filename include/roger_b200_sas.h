@@ -64,8 +64,8 @@ typedef struct roger_sas_settings {
                                1: conservative anion (bromide / chloride: msa holds bin solute MASS, the *_transport_anion_kernel
                                   family of the reference; the RSO_C_iso_* result planes then hold the solute masses M_*) */
     int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day
-                               (svat_transport_model_euler, transport.py:2063-2413; isotope branch; statistics / balance errors are those of
-                               the day's last Euler step, as the reference's output shows them) */
+                               (svat_transport_model_euler, transport.py:2063-2413; statistics / balance errors are those of the day's
+                               last Euler step, as the reference's output shows them; the anion branch runs without statistics) */
 } roger_sas_settings;
 
 typedef struct roger_sas roger_sas; /* opaque handle */

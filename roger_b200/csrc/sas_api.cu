@@ -192,6 +192,22 @@ k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     euler_day<STATS>(cx, forcing, mask[i], sas_params, out, stats, C_s_prev, bounds, atol, rtol);
 }
 
+__global__ void __launch_bounds__(ROGER_EULER_BLOCK, ROGER_EULER_MIN_BLOCKS)
+k_sas_day_euler_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
+                      const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap) {
+    __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
+    __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
+    for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
+        s_log[k] = d_pow_log_tab[k];
+        s_exp[k] = d_pow_exp_tab[k];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.C) return;
+    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    euler_day_anion(cx, forcing, mask[i], sas_params, ap, out);
+}
+
 // (cells, A) row-major staging block <-> age-major planes, 32 x 32 tiles through shared memory
 __global__ void k_stage_to_planes(const double* __restrict__ stage, double* __restrict__ planes, int64_t C, int A, int base,
                                   int64_t cell0, int ncell) {
@@ -372,8 +388,8 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
     if (settings->solute != 0 && settings->solute != 1) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope) or 1 (anion)");
     if (settings->solver != 0 && settings->solver != 1) return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic) or 1 (Euler)");
-    if (settings->solver == 1 && settings->solute != 0)
-        return fail(ROGER_ENOTSUP, "roger_sas_create: the explicit Euler solver covers the isotope branch (oxygen-18 / deuterium)");
+    if (settings->solver == 1 && settings->solute != 0 && settings->age_statistics)
+        return fail(ROGER_ENOTSUP, "roger_sas_create: the anion branch of the explicit Euler solver runs without age statistics");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -508,7 +524,12 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     const int blocks = (int)((h->C + threads - 1) / threads);
     if (h->st.solver == 1) {
         const int eb = (int)((h->C + ROGER_EULER_BLOCK - 1) / ROGER_EULER_BLOCK);
-        if (h->st.age_statistics)
+        if (h->st.solute == 1) {
+            AnionParams ap{nullptr, nullptr, nullptr, nullptr};
+            if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
+            k_sas_day_euler_anion<<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
+                                                                           h->d_out, ap);
+        } else if (h->st.age_statistics)
             k_sas_day_euler<true><<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
                                                                            h->d_out, h->d_stats, h->d_C_s_prev, h->d_bounds, h->atol, h->rtol);
         else

@@ -1200,9 +1200,12 @@ struct EulerStats {  // diagnostics of the day's last Euler step (STATS kernels)
     double avg[2];     // mean travel times
 };
 
-template <bool LAST, bool STATS>
+// ANION: the conservative-solute branch (bromide / chloride; transport.py:2144-2156, :2320-2343, :2378-2407): msa holds solute
+// mass, calc_mtt (:582-596) with the partition coefficients alpha_transp / alpha_q, no mixing statements, the anion storage
+// kernels' `msa = 0 where sa <= 0` fused into the store.
+template <bool LAST, bool STATS, bool ANION>
 __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
-                                        double* __restrict__ out, EulerStats* es) {
+                                        double* __restrict__ out, EulerStats* es, double alpha_t, double alpha_q) {
     const SasParams& P = cx.P;
     const int A = P.A;
     const int64_t C = P.C, i = cx.i;
@@ -1227,14 +1230,22 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
                                 nan0(mtt_ip) * ((dsa_rz > 0) ? ((inf_pf * tt_ip * h) / dsa_rz) : 0);
         const double dmsa_ss1 = nan0(mtt_is) * ((dsa_ss > 0) ? ((inf_ss * tt_is * h) / dsa_ss) : 0);
         double a = s_rz[o], b = s_ss[o];
-        double ma = euler_mix(m_rz[o], a, dsa_rz, dmsa_rz1, true);
-        double mb = euler_mix(m_ss[o], b, dsa_ss, dmsa_ss1, false);
-        a += dsa_rz;
-        b += dsa_ss;
-        s_rz[o] = a;
-        s_ss[o] = b;
-        m_rz[o] = (a <= 0) ? 0 : ma;
-        m_ss[o] = (b <= 0) ? 0 : mb;
+        if (ANION) {  // solute enters as mtt_inf * h with mtt_inf[0] = C_in * mask in all three infiltration arrays (:2089-2101, :2150-2156)
+            const double mi = nan0(C_in * m);
+            s_rz[o] = a + dsa_rz;
+            s_ss[o] = b + dsa_ss;
+            m_rz[o] = m_rz[o] + (mi * h + mi * h);
+            m_ss[o] = m_ss[o] + mi * h;
+        } else {
+            double ma = euler_mix(m_rz[o], a, dsa_rz, dmsa_rz1, true);
+            double mb = euler_mix(m_ss[o], b, dsa_ss, dmsa_ss1, false);
+            a += dsa_rz;
+            b += dsa_ss;
+            s_rz[o] = a;
+            s_ss[o] = b;
+            m_rz[o] = (a <= 0) ? 0 : ma;
+            m_ss[o] = (b <= 0) ? 0 : mb;
+        }
     }
     // what the boundary-condition statements do to a bin that receives nothing (dsa1 = 0, dmsa1 = 0):
     //   msa*(sa/(0 + sa)) + 0*(0/sa) under the statements' conditions, then msa = 0 where sa <= 0
@@ -1335,8 +1346,8 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         auto bin = [&](int j, const double* L, double* v) {
             const int64_t o = cx.ring(j);
             const double a = L[0], b = L[1];
-            const double ma = (j == 0) ? L[2] : clean_rz(L[2], a);
-            const double mb = (j == 0) ? L[3] : clean_ss(L[3], b);
+            const double ma = (ANION || j == 0) ? L[2] : clean_rz(L[2], a);
+            const double mb = (ANION || j == 0) ? L[3] : clean_ss(L[3], b);
             acc_a += a;
             acc_b += b;
             const double na = acc_a * m, nb = acc_b * m;
@@ -1355,6 +1366,45 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
                 tt[k] = (d >= 0) ? d : 0;
             }
             const double tt_e = tt[0], tt_t = tt[1], tt_q = tt[2], tt_c = tt[3], tt_s = tt[4];
+            if (ANION) {
+                auto amtt = [](double sa_, double msa_, double alpha, double t, double fh) {  // calc_mtt, transport.py:582-596
+                    double w = ((sa_ > 0) ? (msa_ / sa_) : 0) * alpha * t * fh;
+                    w = (w <= 0) ? 0 : w;
+                    return (w > msa_) ? msa_ : w;
+                };
+                const double mt = amtt(a, ma, alpha_t, tt_t, fx[1].fh), mq = amtt(a, ma, alpha_q, tt_q, fx[2].fh);
+                const double mc = amtt(b, mb, alpha_q, tt_c, fx[3].fh), msq = amtt(b, mb, alpha_q, tt_s, fx[4].fh);
+                if (LAST) {
+                    v[0] = mt; v[1] = mq; v[2] = mc; v[3] = msq;
+                    if (tt_base) {
+                        const int64_t span = (int64_t)A * C, l = cx.lin(j);
+                        tt_base[RSP_evap_soil * span + l] = tt_e;
+                        tt_base[RSP_transp * span + l] = tt_t;
+                        tt_base[RSP_q_rz * span + l] = tt_q;
+                        tt_base[RSP_cpr_rz * span + l] = tt_c;
+                        tt_base[RSP_q_ss * span + l] = tt_s;
+                    }
+                }
+                double dsa_rz = (cpr * tt_c - evap * tt_e - transp * tt_t - q_rz * tt_q) * h;
+                dsa_rz = (a + dsa_rz < 0) ? -a : dsa_rz;
+                double dsa_ss = (q_rz * tt_q - cpr * tt_c - q_ss * tt_s) * h;
+                dsa_ss = (b + dsa_ss < 0) ? -b : dsa_ss;
+                double a2 = a + dsa_rz, b2 = b + dsa_ss;
+                double dma = nan0(mc) - nan0(mt) - nan0(mq);
+                double dmb = nan0(mq) - nan0(mc) - nan0(msq);
+                dma = (ma + dma < 0) ? 0 : dma;
+                dmb = (mb + dmb < 0) ? 0 : dmb;
+                double ma2 = ma + dma, mb2 = mb + dmb;
+                a2 = (a2 < 1e-8) ? 0 : a2;   // anion storage kernels (root_zone.py:219-240, subsoil.py), run after every Euler step
+                b2 = (b2 < 1e-8) ? 0 : b2;
+                ma2 = (a2 <= 0) ? 0 : ma2;
+                mb2 = (b2 <= 0) ? 0 : mb2;
+                s_rz[o] = a2;
+                s_ss[o] = b2;
+                m_rz[o] = ma2;
+                m_ss[o] = mb2;
+                return;
+            }
             const double mtt_c = (tt_c > 0) ? mb : 0, mtt_q = (tt_q > 0) ? ma : 0;
             if (LAST) {
                 v[0] = tt_e; v[1] = ((tt_e > 0) ? ma : 0) * tt_e;
@@ -1408,9 +1458,19 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             L[0] = s_rz[o]; L[1] = s_ss[o]; L[2] = m_rz[o]; L[3] = m_ss[o];
         };
         if (LAST) {
-            constexpr int NS = STATS ? 15 : 10;
+            constexpr int NS = ANION ? 4 : (STATS ? 15 : 10);
             double sums[NS];
             EULER_SUMS<NS, 4>(cx.plan, EULER_SUMS_ARG load, bin, sums);
+            if (ANION) {  // :2378-2407; C_evap_soil and the M_* flux planes are not touched by the Euler solver
+                O(RSO_C_inf_mat_rz) = ((inf_mat * h > 0) ? C_in : 0) * m;
+                O(RSO_C_inf_pf_rz) = ((inf_pf * h > 0) ? C_in : 0) * m;
+                O(RSO_C_inf_pf_ss) = ((inf_ss * h > 0) ? C_in : 0) * m;
+                O(RSO_C_transp) = ((transp > 0) ? sums[0] / fx[1].fh : 0) * m;
+                O(RSO_C_q_rz) = ((q_rz > 0) ? sums[1] / fx[2].fh : 0) * m;
+                O(RSO_C_cpr_rz) = ((cpr > 0) ? sums[2] / fx[3].fh : 0) * m;
+                O(RSO_C_q_ss) = ((q_ss > 0) ? sums[3] / fx[4].fh : 0) * m;
+                return;
+            }
             if (STATS && es) {
                 const double qn = __longlong_as_double(0x7ff8000000000000LL);
                 es->wsum[0] = sums[NS - 5]; es->wsum[1] = sums[NS - 4]; es->wsum[2] = sums[NS - 3];
@@ -1450,6 +1510,70 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
 #undef SP
 }
 
+// anion storage kernels (root_zone.py:219-261, subsoil.py / soil.py anion kernels) and ageing (transport.py:622-679) as used
+// by anion_day<>, for the Euler solver
+__device__ __forceinline__ void anion_storage(const CellCtx& cx, double m, double* __restrict__ out) {
+    const int64_t C = cx.P.C, i = cx.i;
+    double* __restrict__ s_rz = cx.pl.sa[0];
+    double* __restrict__ s_ss = cx.pl.sa[1];
+    double* __restrict__ m_rz = cx.pl.msa[0];
+    double* __restrict__ m_ss = cx.pl.msa[1];
+    double sums[6];
+    stream_sums<6, 4>(cx.plan,
+        [&](int j, double* L) {
+            const int64_t o = cx.ring(j);
+            L[0] = s_rz[o]; L[1] = s_ss[o]; L[2] = m_rz[o]; L[3] = m_ss[o];
+        },
+        [&](int j, const double* L, double* v) {
+            const int64_t o = cx.ring(j);
+            double a = L[0];
+            a = (a < 1e-8) ? 0 : a;
+            double b = L[1];
+            b = (b < 1e-8) ? 0 : b;
+            const double ma = (a <= 0) ? 0 : L[2], mb = (b <= 0) ? 0 : L[3];
+            s_rz[o] = a; s_ss[o] = b; m_rz[o] = ma; m_ss[o] = mb;
+            const double ms = ma + mb * m;
+            v[0] = isnan_d(ma) ? 0 : ma;
+            v[1] = a;
+            v[2] = isnan_d(mb) ? 0 : mb;
+            v[3] = b;
+            v[4] = isnan_d(ms) ? 0 : ms;
+            v[5] = a + b * m;
+        }, sums);
+#define O(k) out[(int64_t)(k) * C + i]
+    const double M_rz = sums[0] * m, M_ss = sums[2] * m, M_s = sums[4] * m;
+    O(RSO_C_iso_rz) = M_rz; O(RSO_C_rz) = (sums[1] > 0) ? M_rz / sums[1] : 0;
+    O(RSO_C_iso_ss) = M_ss; O(RSO_C_ss) = (sums[3] > 0) ? M_ss / sums[3] : 0;
+    O(RSO_C_iso_s) = M_s;   O(RSO_C_s) = (sums[5] > 0) ? M_s / sums[5] : 0;
+#undef O
+}
+__device__ __forceinline__ void anion_ageing(const CellCtx& cx) {
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    const int64_t C = P.C, i = cx.i;
+    const int b_new = (P.base == 0) ? A - 1 : P.base - 1;
+    const int b_last = (b_new == 0) ? A - 1 : b_new - 1;
+    for (int L = 0; L < 2; L++) {
+        double* __restrict__ sa = cx.pl.sa[L];
+        double* __restrict__ msa = cx.pl.msa[L];
+        double s_new = sa[(int64_t)b_last * C + i] + sa[(int64_t)b_new * C + i];
+        s_new = (s_new < 1e-8) ? 0 : s_new;
+        sa[(int64_t)b_last * C + i] = s_new;
+        msa[(int64_t)b_last * C + i] = msa[(int64_t)b_last * C + i] + msa[(int64_t)b_new * C + i];
+        sa[(int64_t)b_new * C + i] = 0;
+        msa[(int64_t)b_new * C + i] = 0;
+    }
+}
+
+__device__ __forceinline__ void euler_day_anion(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
+                                                const AnionParams ap, double* __restrict__ out) {
+    const double alpha_t = ap.alpha_transp ? ap.alpha_transp[cx.i] : 1.0, alpha_q = ap.alpha_q ? ap.alpha_q[cx.i] : 1.0;
+    for (int s = 0; s + 1 < cx.P.substeps; s++) euler_step<false, false, true>(cx, forcing, m, sas_params, out, nullptr, alpha_t, alpha_q);
+    euler_step<true, false, true>(cx, forcing, m, sas_params, out, nullptr, alpha_t, alpha_q);
+    anion_storage(cx, m, out);
+    anion_ageing(cx);
+}
+
 template <bool STATS>
 __device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
                                           double* __restrict__ out, double* __restrict__ stats, double* __restrict__ C_s_prev,
@@ -1457,8 +1581,8 @@ __device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __res
     const SasParams& P = cx.P;
     const int64_t C = P.C, i = cx.i;
     const int n = P.substeps;
-    for (int s = 0; s + 2 < n; s++) euler_step<false, false>(cx, forcing, m, sas_params, out, nullptr);
-    if (n > 1) euler_step<false, false>(cx, forcing, m, sas_params, out, nullptr);
+    for (int s = 0; s + 2 < n; s++) euler_step<false, false, false>(cx, forcing, m, sas_params, out, nullptr, 1.0, 1.0);
+    if (n > 1) euler_step<false, false, false>(cx, forcing, m, sas_params, out, nullptr, 1.0, 1.0);
     double sum_sa_s, C_s, sum_sa_rz, sum_sa_ss;
     double sum_sa_s_m1 = 0, Cp = 0;
     if (STATS) {  // [taum1] of the last Euler step: what its predecessor left (after_substep_iso, transport.py:3421-3520)
@@ -1473,7 +1597,7 @@ __device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __res
         sum_sa_s_m1 = sm[0];
     }
     EulerStats es;
-    euler_step<true, STATS>(cx, forcing, m, sas_params, out, &es);
+    euler_step<true, STATS, false>(cx, forcing, m, sas_params, out, &es, 1.0, 1.0);
     storage_concentrations(cx, m, out, C, &sum_sa_s, &C_s, &sum_sa_rz, &sum_sa_ss);
     if (STATS) {
 #define F(k) forcing[(int64_t)(k) * C + i]

@@ -223,8 +223,8 @@ class CudaTransportDriver:
         if solver not in ("deterministic", "Euler"):
             raise NotImplementedError("sas_solver = 'deterministic' and 'Euler' run on the device (DESIGN.md section 7)")
         self.euler = solver == "Euler"
-        if self.euler and self.anion:
-            raise NotImplementedError("the explicit Euler solver covers the isotope branch (oxygen-18 / deuterium)")
+        if self.euler and self.anion and bool(getattr(st, "enable_age_statistics", False)):
+            raise NotImplementedError("the anion branch of the explicit Euler solver runs without age statistics")
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
         self.C = self.nx * self.ny
         self.pull_state = bool(pull_state)
