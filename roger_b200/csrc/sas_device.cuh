@@ -1139,8 +1139,7 @@ __device__ __forceinline__ void ageing(const CellCtx& cx) {
 #define EULER_SUMS stream_sums
 #define EULER_SUMS_ARG
 #endif
-struct EulerFlux {
-    Family fam;
+struct EulerFlux {      // the hot per-flux scalars (registers); the Family descriptors of the general path live beside them
     double flux, fh;    // flux, flux * h
     bool active;        // calc_TT_num zeroes TTq where flux * h <= 0
     double om_prev;     // TTq of the previous age index
@@ -1150,7 +1149,7 @@ struct EulerFlux {
     bool sa_only;       // the SAS function depends on the cumulative StorAge only, not on the age index
     bool powfast;       // power law, cell inside the catchment, S in the range where div_by() is exact
     bool ssum_ok;       // ssum in that range as well
-    double rS, rssum;
+    double S, rS, y, rssum;  // S = max(SA) * m of the flux's layer, its reciprocal, the power-law exponent
 };
 
 // log(SA / S) of one layer's bin, shared by the layer's power-law fluxes (x^y1, x^y2, ... of one base: cf. roger_pow2)
@@ -1168,16 +1167,16 @@ __device__ __forceinline__ EulerLog euler_log(const CellCtx& cx, double SA, doub
 }
 
 // ttq_nonneg of bin j (calc_TT_num_nonneg :919-931) given the masked cumulative StorAge at its upper edge
-__device__ __forceinline__ double euler_q(EulerFlux& e, const CellCtx& cx, int j, double SA, double sa_d, const EulerLog& g) {
+__device__ __forceinline__ double euler_q(EulerFlux& e, const Family& fam, const CellCtx& cx, int j, double SA, double sa_d, const EulerLog& g) {
     double om;
     if (!e.active) om = 0.0;
     else if (e.sa_only && sa_d == 0) om = e.om_prev;  // an empty bin: same cumulative StorAge, same SAS function value
     else if (e.powfast) {                               // omega() for the power law with the division hoisted (cf. pow_pass_bins)
-        const double S = e.fam.S;
-        double p = roger_pow_from_log(g.hi, g.lo, e.fam.sp[1], cx.tabs);
-        if (g.in && !g.easy) p = roger_pow(SA / S, e.fam.sp[1], cx.tabs);
+        const double S = e.S;
+        double p = roger_pow_from_log(g.hi, g.lo, e.y, cx.tabs);
+        if (g.in && !g.easy) p = roger_pow(SA / S, e.y, cx.tabs);
         om = (SA > 0) ? ((SA <= S) ? p : 1.) : 0.;
-    } else om = omega(e.fam, cx.P, cx.tabs, j + 1, SA);
+    } else om = omega(fam, cx.P, cx.tabs, j + 1, SA);
     double q = (om - e.om_prev) * e.fh;
     e.om_prev = om;
     q = (sa_d + q < 0) ? -sa_d : q;
@@ -1272,27 +1271,30 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         }
     }
     EulerFlux fx[5];  // evap_soil, transp, q_rz (root zone); cpr_rz, q_ss (subsoil)
+    Family fams[5];
     {
         const int procs[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
         const double flx[5] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_rz), F(RSF_cpr_rz), F(RSF_q_ss)};
         const double mxa = mx_rz.get(), mxb = mx_ss.get();
 #pragma unroll
         for (int k = 0; k < 5; k++) {
-            family_begin(fx[k].fam, SP(procs[k]), C, m);
-            family_prepare(fx[k].fam, (k < 3) ? mxa : mxb);
+            family_begin(fams[k], SP(procs[k]), C, m);
+            family_prepare(fams[k], (k < 3) ? mxa : mxb);
             fx[k].flux = flx[k];
             fx[k].fh = flx[k] * h;
             fx[k].active = !(fx[k].fh <= 0);
-            const Family& f = fx[k].fam;
+            const Family& f = fams[k];
             fx[k].sa_only = f.fast && !f.is_uniform && !f.is_dirac;
             fx[k].powfast = f.fast && f.is_pow && (f.S > 0) && div_range_ok(f.S) && (f.sp[1] - f.sp[1] == 0.0);
+            fx[k].S = f.S;
+            fx[k].y = f.sp[1];
             fx[k].rS = 1.0 / f.S;
         }
     }
     // one logarithm per layer and bin serves every power-law flux of the layer (skipped for empty bins)
     const bool logs_a = (fx[0].active && fx[0].powfast) || (fx[1].active && fx[1].powfast) || (fx[2].active && fx[2].powfast);
     const bool logs_b = (fx[3].active && fx[3].powfast) || (fx[4].active && fx[4].powfast);
-    const double S_a = fx[0].fam.S, rS_a = fx[0].rS, S_b = fx[3].fam.S, rS_b = fx[3].rS;
+    const double S_a = fx[0].S, rS_a = fx[0].rS, S_b = fx[3].S, rS_b = fx[3].rS;
     auto layer_log = [&](int layer, double SA, double sa_d) {
         EulerLog g{0.0, 0.0, false, false};
         if ((layer == 0 ? logs_a : logs_b) && !(sa_d == 0)) g = euler_log(cx, SA, layer == 0 ? S_a : S_b, layer == 0 ? rS_a : rS_b);
@@ -1300,7 +1302,7 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
     };
     auto reset = [&]() {
 #pragma unroll
-        for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega(fx[k].fam, P, cx.tabs, 0, 0.0 * m) : 0.0;
+        for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega(fams[k], P, cx.tabs, 0, 0.0 * m) : 0.0;
     };
     // P2: normalisation constants
     {
@@ -1318,7 +1320,7 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
                 SAb = nb;
                 const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
 #pragma unroll
-                for (int k = 0; k < 5; k++) v[k] = euler_q(fx[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
+                for (int k = 0; k < 5; k++) v[k] = euler_q(fx[k], fams[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
             }, sums);
 #pragma unroll
         for (int k = 0; k < 5; k++) {
@@ -1358,7 +1360,7 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
 #pragma unroll
             for (int k = 0; k < 5; k++) {
-                const double q = euler_q(fx[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
+                const double q = euler_q(fx[k], fams[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
                 const double p = (q > 0) ? ((fx[k].ssum_ok && div_range_ok(q)) ? div_by(q, fx[k].ssum, fx[k].rssum) : q / fx[k].ssum) : 0;
                 fx[k].accT = (j == 0) ? p : fx[k].accT + p;  // np.cumsum starts from the first element
                 const double d = fx[k].accT - fx[k].Tprev;
