@@ -1248,14 +1248,15 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
     }
     // what the boundary-condition statements do to a bin that receives nothing (dsa1 = 0, dmsa1 = 0):
     //   msa*(sa/(0 + sa)) + 0*(0/sa) under the statements' conditions, then msa = 0 where sa <= 0
-    auto clean_rz = [](double ms, double s) {
-        const double one = (s < 1.7976931348623157e308) ? 1.0 : s / s;
-        return ((s > 0) && (ms > 0)) ? ms * one + 0.0 : 0.0;
+    // (the rare sides of these shortcuts sit behind `asm volatile("")`: without it the compiler if-converts the selects and
+    // executes the divisions anyway -- 5 of the 8 divisions per bin and step in the first capture)
+    auto self_ratio = [](double x) {  // x / x: exactly 1 for a finite non-zero x
+        double one = 1.0;
+        if (!(x < 1.7976931348623157e308)) { asm volatile(""); one = x / x; }
+        return one;
     };
-    auto clean_ss = [](double ms, double s) {
-        const double one = (s < 1.7976931348623157e308) ? 1.0 : s / s;
-        return (s > 0) ? ms * one + 0.0 : 0.0;
-    };
+    auto clean_rz = [&](double ms, double s) { return ((s > 0) && (ms > 0)) ? ms * self_ratio(s) + 0.0 : 0.0; };
+    auto clean_ss = [&](double ms, double s) { return (s > 0) ? ms * self_ratio(s) + 0.0 : 0.0; };
     // P1: S of both layers (calc_SA :343-359 times maskCatch, np.max over nages points)
     NpMax mx_rz, mx_ss;
     mx_rz.init(0.0 * m);
@@ -1438,13 +1439,13 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             dsa_ss = (b + dsa_ss < 0) ? -b : dsa_ss;
             const double dsa_rz1 = (cpr * tt_c) * h;
             // (cpr * tt_c * h) / dsa_rz1 divides a value by itself: exactly 1 for a finite positive value
-            auto self_ratio = [](double x) { return (x < 1.7976931348623157e308) ? 1.0 : x / x; };
             const double dmsa_rz1 = nan0(mtt_c) * ((dsa_rz1 > 0) ? self_ratio(dsa_rz1) : 0);
             const double dsa_ss1 = (q_rz * tt_q) * h;
             const double dmsa_ss1 = nan0(mtt_q) * ((dsa_ss1 > 0) ? self_ratio(dsa_ss1) : 0);
             // a bin that receives nothing keeps its concentration: the general expression reduces to clean_*()
-            double ma2 = (dsa_rz1 == 0 && dmsa_rz1 == 0 && j > 0) ? ma : euler_mix(ma, a, dsa_rz1, dmsa_rz1, true);
-            double mb2 = (dsa_ss1 == 0 && dmsa_ss1 == 0 && j > 0) ? mb : euler_mix(mb, b, dsa_ss1, dmsa_ss1, false);
+            double ma2 = ma, mb2 = mb;
+            if (!(dsa_rz1 == 0 && dmsa_rz1 == 0 && j > 0)) { asm volatile(""); ma2 = euler_mix(ma, a, dsa_rz1, dmsa_rz1, true); }
+            if (!(dsa_ss1 == 0 && dmsa_ss1 == 0 && j > 0)) { asm volatile(""); mb2 = euler_mix(mb, b, dsa_ss1, dmsa_ss1, false); }
             double a2 = a + dsa_rz, b2 = b + dsa_ss;
             ma2 = (a2 <= 0) ? 0 : ma2;
             mb2 = (b2 <= 0) ? 0 : mb2;
