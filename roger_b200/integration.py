@@ -178,6 +178,7 @@ class CudaStepDriver:
             import warnings
 
             warnings.warn(f"Solution diverged at iteration {sc.itt} (numerics.sanity_check)")
+        self._maybe_output(sc.time)
         setup.after_timestep(state)
         return sc
 
@@ -187,6 +188,74 @@ class CudaStepDriver:
         start = int(np.asarray(vs.time))
         while int(np.asarray(vs.time)) - start < runlen:
             self.step()
+        self.close_output()
+
+    # ------------------------------------------------------------------ output files of the setup's own diagnostics
+    def enable_output(self, base_path=".", force_overwrite=False):
+        """Writes the files the setup's `set_diagnostics` asked for -- `state.diagnostics["rate" | "average" | "maximum" |
+        "minimum" | "collect"]` with their `output_variables`, `output_frequency` and `output_path` -- from device accumulators
+        through `roger_b200.output.AsyncDiagnosticOutput` (accumulation after every step, the reference's sampling; record at
+        the times `diagnostics.output` writes one, roger/diagnostics/api.py:45-66).  One output frequency for all of them."""
+        import os
+
+        from .output import AsyncDiagnosticOutput
+
+        st, vs = self.state.settings, self.state.variables
+        spec, files, freq = [], {}, None
+        for name in ("rate", "average", "maximum", "minimum", "collect"):
+            d = self.state.diagnostics.get(name)
+            if d is None or not d.output_variables or not d.output_frequency:
+                continue
+            if freq is not None and d.output_frequency != freq:
+                raise NotImplementedError("diagnostics with different output frequencies")
+            freq = d.output_frequency
+            unknown = [v for v in d.output_variables if v not in abi.FIELD_ID]
+            if unknown:
+                raise NotImplementedError(f"diagnostic {name!r}: {unknown} are not planes of the CUDA engine")
+            if any((v, m) for v, m in spec if v in d.output_variables):
+                raise NotImplementedError("a variable in more than one diagnostic")
+            spec += [(v, name) for v in d.output_variables]
+            fname = d.output_path.format(identifier=st.identifier)
+            files[os.path.join(str(getattr(d, "base_output_path", None) or base_path), fname)] = list(d.output_variables)
+        if not spec:
+            return None
+        if freq not in (DAY, 3600, 600):
+            raise NotImplementedError("output_frequency must be 86400, 3600 or 600 seconds")
+        if self.engine is None:  # the engine exists from the first forcing day on
+            self._pending_output = (spec, files, freq, force_overwrite)
+            return None
+        self._open_output(spec, files, freq, force_overwrite)
+        return self._out
+
+    def _open_output(self, spec, files, freq, force_overwrite):
+        from .output import AsyncDiagnosticOutput
+
+        st, vs = self.state.settings, self.state.variables
+        self._out = AsyncDiagnosticOutput(self.engine, None, (self.nx, self.ny), spec, files=files, identifier=st.identifier,
+                                          time_origin=st.time_origin, x=np.asarray(vs.x)[2:-2], y=np.asarray(vs.y)[2:-2],
+                                          mask=self._interior("maskCatch"), force_overwrite=force_overwrite)
+        self._out_freq = freq
+        if any(abi.FIELD_KINDS[abi.FIELD_ID[v]] == "F" for v, _ in spec):
+            self._write_fluxes = True
+
+    def _maybe_output(self, time_seconds):
+        pend = getattr(self, "_pending_output", None)
+        if pend is not None:
+            self._pending_output = None
+            self._open_output(*pend)
+            return  # the accumulators start with the next step
+        out = getattr(self, "_out", None)
+        if out is None:
+            return
+        t, f = int(time_seconds), self._out_freq
+        if t % f == 0 or t % 3600 == 0 and f < 3600 or t % DAY == 0:  # roger/diagnostics/api.py:49-60
+            out.output(t)
+
+    def close_output(self):
+        out = getattr(self, "_out", None)
+        if out is not None:
+            out.close()
+            self._out = None
 
 
 class CudaTransportDriver:

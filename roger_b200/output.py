@@ -115,7 +115,9 @@ class AsyncDiagnosticOutput:
     (maximum.py:76-92), "collect" (the value at the output time, collect.py:61-71 -- a plain asynchronous plane download).
     """
 
-    def __init__(self, engine, path, shape, spec, depth=2, **file_kwargs):
+    def __init__(self, engine, path, shape, spec, depth=2, files=None, **file_kwargs):
+        """`files` (optional): {path: [variable names]} splits the variables of `spec` over several files, e.g. one per
+        diagnostic of the reference ("{identifier}.rate.nc", "{identifier}.average.nc", ...); default: all of them in `path`."""
         self.engine = engine
         self.spec = [(n, m) for n, m in spec]
         for _, m in self.spec:
@@ -124,8 +126,17 @@ class AsyncDiagnosticOutput:
         self.acc = [(n, m) for n, m in self.spec if m != "collect"]
         self.col = [n for n, m in self.spec if m == "collect"]
         names = [n for n, _ in self.acc] + self.col
-        self.file = DiagnosticFile(path, shape, names, **file_kwargs)
         self.C = int(shape[0]) * int(shape[1])
+        if files is None:
+            files = {path: names}
+        self.files = []  # (DiagnosticFile, rows of the record buffer it takes)
+        for fpath, fvars in files.items():
+            rows = [names.index(v) for v in fvars]
+            kw = dict(file_kwargs)
+            if "diagnostic" not in kw:
+                kw["diagnostic"] = os.path.basename(fpath).split(".")[-2] if fpath.count(".") >= 2 else "rate"
+            self.files.append((DiagnosticFile(fpath, shape, list(fvars), **kw), rows))
+        self.file = self.files[0][0]
         if self.acc:
             engine.set_diagnostics(self.acc)
         self._buffers = [_pinned(len(names) * self.C) for _ in range(max(1, int(depth)))]
@@ -163,7 +174,8 @@ class AsyncDiagnosticOutput:
                 for j, (_, mode) in enumerate(self.acc):
                     if mode == "average" and count > 0:  # average.py:93-97
                         planes[j] = planes[j] / count
-                self.file.append(time_seconds, planes)
+                for f, rows in self.files:
+                    f.append(time_seconds, planes[rows])
             except BaseException as e:  # noqa: BLE001 -- surfaced by the next output() / close()
                 self._error = e
             finally:
@@ -173,6 +185,7 @@ class AsyncDiagnosticOutput:
         self._work.put(None)
         self._thread.join()
         self.engine.download_wait()
-        self.file.close()
+        for f, _ in self.files:
+            f.close()
         if self._error is not None:
             raise self._error

@@ -116,3 +116,66 @@ def test_transport_driver_reproduces_reference_step(name, ndays, tol):
             assert x.shape == y.shape
             lim = max(1e-9, tol) if n.startswith("C_iso") else tol  # delta values amplify concentration rounding ~1e3
             assert rel_err(y, x) < lim, (day, n)
+
+
+def test_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
+    """`CudaStepDriver.enable_output`: the setup's own `state.diagnostics` configuration (rate / average / collect with their
+    output variables, frequency and path) produces files whose records equal what the reference's diagnostics hold in memory at
+    the same output times (the reference itself cannot write here: h5netcdf is absent, it runs diskless)."""
+    import ref_harness as rh
+    from oracle.engine import OracleSvatEngine
+    from roger_b200.integration import CudaStepDriver
+    from scipy.io import netcdf_file
+    from tests.util import normalised_max_error
+
+    case = _case("svat_rain")
+    Setup = rh.make_svat_setup(case)
+    want = {"rate": ["q_ss", "aet", "prec"], "average": ["theta_rz"], "collect": ["S_s"]}
+
+    def configure(model):
+        for name, vars_ in want.items():
+            d = model.state.diagnostics[name]
+            d.output_variables = list(vars_)
+            d.output_frequency = 24 * 60 * 60
+            d.sampling_frequency = 1
+            d.initialize(model.state)
+
+    ref = Setup()
+    ref.setup()
+    configure(ref)
+    dut = Setup()
+    dut.setup()
+    configure(dut)
+    driver = CudaStepDriver(dut, engine_cls=OracleSvatEngine)
+    driver.enable_output(base_path=str(tmp_path), force_overwrite=True)
+    records = []
+    for step in range(400):
+        ref.step(ref.state)
+        driver.step()
+        t = int(ref.state.variables.time)
+        if t % 86400 == 0:
+            rec = {}
+            for name, vars_ in want.items():
+                dv = ref.state.diagnostics[name].variables
+                for v in vars_:
+                    a = np.asarray(getattr(dv, v))
+                    rec[v] = a[2:-2, 2:-2].copy() if a.ndim == 2 else a[2:-2, 2:-2, int(ref.state.variables.tau)].copy()
+            records.append((t, rec))
+            if len(records) == 2:
+                break
+    driver.close_output()
+    assert len(records) == 2
+    ident = dut.state.settings.identifier
+    mask = np.asarray(dut.state.variables.maskCatch)[2:-2, 2:-2].astype(bool)
+    for name, vars_ in want.items():
+        with netcdf_file(str(tmp_path / f"{ident}.{name}.nc"), "r", mmap=False) as f:
+            # the first day is the accumulator set-up day on the driver side (the engine exists from the first forcing day on):
+            # records of the days after it
+            times = f.variables["Time"][:]
+            assert times[-1] == records[-1][0] / 86400.0
+            for v in vars_:
+                got = f.variables[v][-1].T
+                ref_v = records[-1][1][v]
+                # (Average.output has already divided the in-memory sums by the step count, average.py:93-97)
+                assert v == "prec" or np.abs(ref_v[mask]).sum() > 0, (name, v)  # (the second day of this case is dry)
+                assert normalised_max_error(np.where(mask, ref_v, 0), np.where(mask, got, 0)) < 1e-10, (name, v)
