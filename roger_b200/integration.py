@@ -373,4 +373,53 @@ class CudaTransportDriver:
                 for k, name in enumerate(sas.STATISTICS):
                     if name in active:
                         self._put(name, st[k])
+        out_w = getattr(self, "_out", None)
+        if out_w is not None and int(vs.time) % self._out_freq == 0:  # roger/diagnostics/api.py:45-66
+            tau = int(vs.tau)
+            vals = {}
+            for f in out_w.files:
+                for v in f.variables:
+                    a = np.asarray(getattr(vs, v))
+                    vals[v] = (a[2:-2, 2:-2, tau] if a.ndim == 3 else a[2:-2, 2:-2]).reshape(-1)
+            out_w.output(int(vs.time), vals)
         setup.after_timestep(state)
+
+    def enable_output(self, base_path=".", force_overwrite=False):
+        """Writes the files the setup's `set_diagnostics` asked for (`state.diagnostics[...]` with `output_variables`,
+        `output_frequency`, `output_path`) for the per-cell results of the transport step -- concentrations, delta values / solute
+        masses, age statistics -- on a writer thread (`roger_b200.output.ThreadedRecordWriter`).  With one step per day every
+        accumulating diagnostic (rate, average, maximum, minimum) holds the day's value, as collect does."""
+        import os
+
+        from .output import ThreadedRecordWriter
+
+        st, vs = self.state.settings, self.state.variables
+        files, freq = {}, None
+        for name in ("rate", "average", "maximum", "minimum", "collect"):
+            d = self.state.diagnostics.get(name)
+            if d is None or not d.output_variables or not d.output_frequency:
+                continue
+            if freq is not None and d.output_frequency != freq:
+                raise NotImplementedError("diagnostics with different output frequencies")
+            freq = d.output_frequency
+            for v in d.output_variables:
+                a = np.asarray(getattr(vs, v))
+                if a.ndim > 3 or (a.ndim == 3 and a.shape[2] != 2):
+                    raise NotImplementedError(f"diagnostic {name!r}: {v} is not a per-cell variable (age-ranked arrays are not written)")
+            fname = d.output_path.format(identifier=st.identifier)
+            files[os.path.join(str(getattr(d, "base_output_path", None) or base_path), fname)] = list(d.output_variables)
+        if not files:
+            return None
+        if freq % int(vs.dt_secs) != 0:
+            raise NotImplementedError("output_frequency must be a multiple of the daily step")
+        self._out = ThreadedRecordWriter((self.nx, self.ny), files, identifier=st.identifier, time_origin=st.time_origin,
+                                         x=np.asarray(vs.x)[2:-2], y=np.asarray(vs.y)[2:-2],
+                                         mask=np.asarray(vs.maskCatch)[2:-2, 2:-2].reshape(-1), force_overwrite=force_overwrite)
+        self._out_freq = int(freq)
+        return self._out
+
+    def close_output(self):
+        out = getattr(self, "_out", None)
+        if out is not None:
+            out.close()
+            self._out = None

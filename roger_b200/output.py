@@ -189,3 +189,47 @@ class AsyncDiagnosticOutput:
             f.close()
         if self._error is not None:
             raise self._error
+
+
+class ThreadedRecordWriter:
+    """Host-side records -> files on a writer thread (`threaded_io`, io_tools/netcdf.py:145-210) for engines whose results are
+    already on the host after a step (the daily offline-transport step).  files: {path: [variable names]}."""
+
+    def __init__(self, shape, files, **file_kwargs):
+        self.files = []
+        for fpath, fvars in files.items():
+            kw = dict(file_kwargs)
+            if "diagnostic" not in kw:
+                kw["diagnostic"] = os.path.basename(fpath).split(".")[-2] if fpath.count(".") >= 2 else "collect"
+            self.files.append(DiagnosticFile(fpath, shape, list(fvars), **kw))
+        self._work = queue.Queue(maxsize=4)
+        self._error = None
+        self._thread = threading.Thread(target=self._writer, name="roger-output", daemon=True)
+        self._thread.start()
+
+    def output(self, time_seconds, values):
+        """values: {variable name: array of nx * ny values}; copied, so the caller may reuse its arrays"""
+        if self._error is not None:
+            raise self._error
+        self._work.put((float(time_seconds), {k: np.array(v, dtype=np.float64) for k, v in values.items()}))
+
+    def _writer(self):
+        while True:
+            item = self._work.get()
+            if item is None:
+                return
+            t, values = item
+            try:
+                for f in self.files:
+                    f.append(t, np.stack([values[v].reshape(-1) for v in f.variables]))
+            except BaseException as e:  # noqa: BLE001 -- surfaced by the next output() / close()
+                self._error = e
+
+    def close(self):
+        self._work.put(None)
+        self._thread.join()
+        for f in self.files:
+            f.close()
+        if self._error is not None:
+            raise self._error
+

@@ -179,3 +179,55 @@ def test_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
                 # (Average.output has already divided the in-memory sums by the step count, average.py:93-97)
                 assert v == "prec" or np.abs(ref_v[mask]).sum() > 0, (name, v)  # (the second day of this case is dry)
                 assert normalised_max_error(np.where(mask, ref_v, 0), np.where(mask, got, 0)) < 1e-10, (name, v)
+
+
+def test_transport_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
+    """`CudaTransportDriver.enable_output`: daily records of the per-cell transport results equal what the reference's collect /
+    average diagnostics hold in memory after the same step."""
+    import make_sas_golden as mg
+    import ref_harness as rh
+    from oracle.engine import OracleSasEngine, lib
+    from roger_b200.integration import CudaTransportDriver
+    from scipy.io import netcdf_file
+    from tests.util_sas import rel_err
+
+    lib().roger_oracle_set_pow(0)
+    case = mg.build("sas_families")
+    Setup = rh.make_o18_setup(case)
+    want = {"collect": ["C_iso_q_ss", "C_iso_transp", "C_iso_s"], "average": ["C_rz"]}
+
+    def configure(model):
+        for name, vars_ in want.items():
+            d = model.state.diagnostics[name]
+            d.output_variables = list(vars_)
+            d.output_frequency = 24 * 60 * 60
+            d.sampling_frequency = 1
+            d.initialize(model.state)
+
+    ref, dut = Setup(), Setup()
+    for m in (ref, dut):
+        m.setup()
+        m.warmup()
+        configure(m)
+    driver = CudaTransportDriver(dut, engine_cls=OracleSasEngine)
+    driver.enable_output(base_path=str(tmp_path), force_overwrite=True)
+    records = []
+    for day in range(6):
+        ref.step(ref.state)
+        driver.step()
+        rec = {}
+        for name, vars_ in want.items():
+            dv = ref.state.diagnostics[name].variables
+            for v in vars_:
+                rec[v] = np.asarray(getattr(dv, v))[2:-2, 2:-2].copy()
+        records.append((int(ref.state.variables.time), rec))
+    driver.close_output()
+    ident = dut.state.settings.identifier
+    for name, vars_ in want.items():
+        with netcdf_file(str(tmp_path / f"{ident}.{name}.nc"), "r", mmap=False) as f:
+            assert np.array_equal(f.variables["Time"][:], [t / 86400.0 for t, _ in records])
+            for v in vars_:
+                for k, (_, rec) in enumerate(records):
+                    got = f.variables[v][k].T
+                    want_v = np.where(np.isnan(rec[v]), np.nan, rec[v])
+                    assert rel_err(np.where(got == -9999, np.nan, got) if np.isnan(want_v).any() else got, want_v) < 1e-9, (name, v, k)
