@@ -168,6 +168,10 @@ class CudaStepDriver:
         for name in self._pushed:
             self.engine.upload(name, self._interior(name))
         self._pushed.clear()
+        pend = getattr(self, "_pending_output", None)
+        if pend is not None:  # enable_output() was called before the engine existed: the accumulators start with this step
+            self._pending_output = None
+            self._open_output(*pend)
         self._scalars_to_engine()
         self.engine.step(self._write_fluxes)
         sc = self._scalars_from_engine()
@@ -239,11 +243,6 @@ class CudaStepDriver:
             self._write_fluxes = True
 
     def _maybe_output(self, time_seconds):
-        pend = getattr(self, "_pending_output", None)
-        if pend is not None:
-            self._pending_output = None
-            self._open_output(*pend)
-            return  # the accumulators start with the next step
         out = getattr(self, "_out", None)
         if out is None:
             return

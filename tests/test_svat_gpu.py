@@ -311,3 +311,46 @@ def test_async_diagnostic_output_file(tmp_path):
         assert np.array_equal(fa.variables["Time"][:], fb.variables["Time"][:]) and fa.variables["Time"].shape == (4,)
         for name, _ in SPEC:
             assert util.same_bits(fa.variables[name][:], fb.variables[name][:]), name
+
+
+def test_driver_output_files_on_the_cuda_engine(tmp_path):
+    """CudaStepDriver.enable_output with the CUDA engine: the files of a setup's rate / average / collect diagnostics equal,
+    bit for bit, those the same driver writes with the oracle engine plugged in (which tests/test_integration_reference.py
+    checks against the reference's own diagnostics)."""
+    import types
+
+    from oracle.engine import OracleSvatEngine, lib
+    from roger_b200 import synth
+    from roger_b200.integration import CudaStepDriver
+    from scipy.io import netcdf_file
+    from tests.mini_setup import MiniSvatSetup
+
+    shape = (8, 6)
+    want = {"rate": ["q_ss", "aet", "prec"], "average": ["theta_rz"], "collect": ["S_s"]}
+    forcing = synth.mixed_forcing(6, seed=42, start_doy=140)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, masked_fraction=0.1)
+    lib().roger_oracle_set_pow(1)
+    try:
+        for tag, eng in (("cuda", _engine()), ("oracle", OracleSvatEngine)):
+            setup = MiniSvatSetup(shape, forcing, prim, th_rz, th_ss)
+            setup.setup()
+            st = setup.state
+            st.settings.identifier, st.settings.time_origin = "MINI", "2021-12-31 00:00:00"
+            st.variables.x, st.variables.y = np.arange(shape[0] + 4, dtype=float), np.arange(shape[1] + 4, dtype=float)
+            st.diagnostics = {n: types.SimpleNamespace(output_variables=v, output_frequency=86400, output_path="{identifier}." + n + ".nc",
+                                                       base_output_path=None) for n, v in want.items()}
+            out_dir = tmp_path / tag
+            out_dir.mkdir()
+            driver = CudaStepDriver(setup, engine_cls=eng)
+            driver.enable_output(base_path=str(out_dir))
+            while int(np.asarray(st.variables.time)) < 3 * 86400:
+                driver.step()
+            driver.close_output()
+    finally:
+        lib().roger_oracle_set_pow(0)
+    for name, vars_ in want.items():
+        with netcdf_file(str(tmp_path / "cuda" / f"MINI.{name}.nc"), "r", mmap=False) as fa, \
+                netcdf_file(str(tmp_path / "oracle" / f"MINI.{name}.nc"), "r", mmap=False) as fb:
+            assert fa.variables["Time"].shape[0] >= 2 and np.array_equal(fa.variables["Time"][:], fb.variables["Time"][:])
+            for v in vars_:
+                assert util.same_bits(fa.variables[v][:], fb.variables[v][:]), (name, v)
