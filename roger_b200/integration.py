@@ -202,9 +202,7 @@ class CudaStepDriver:
         the times `diagnostics.output` writes one, roger/diagnostics/api.py:45-66).  One output frequency for all of them."""
         import os
 
-        from .output import AsyncDiagnosticOutput
-
-        st, vs = self.state.settings, self.state.variables
+        st = self.state.settings
         spec, files, freq = [], {}, None
         for name in ("rate", "average", "maximum", "minimum", "collect"):
             d = self.state.diagnostics.get(name)
