@@ -784,6 +784,167 @@ static void euler_substep_cell(const sas_ctx *c, int64_t C, int64_t i, double *s
 #undef SP
 }
 
+/* ---- Runge-Kutta solver (settings.sas_solver = "RK4"), isotope branch: svat_transport_model_rk4 (transport.py:1138-2047).
+ * Four stages of the Euler building blocks on stage copies of the StorAge; the stage updates are restated as written
+ * (stage 1 advances by h, stages 2 and 3 by h / 2 with mass-like bookkeeping of the stage concentrations, stage 3 tests
+ * sarkn - dsarkn < 0, dsarkn_ss1 of stage 1 lacks the flux), then tt = (k1 + 2 k2 + 2 k3 + k4) / 6 and one Euler-style update. */
+static void rk4_substep_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss,
+                             const double *forcing, double m, const double *sas_params, double *out, double *tt_base, size_t tt_stride,
+                             double *work)
+{
+#define F(k) forcing[(size_t)(k) * (size_t)C + (size_t)i]
+#define O(k) out[(size_t)(k) * (size_t)C + (size_t)i]
+#define SP(p) (sas_params + ((size_t)(p) * (size_t)C + (size_t)i) * 8)
+    const int A = c->A, N = A + 1;
+    const double h = 1.0 / c->substeps;
+    /* work: 2 SA + 4 stage arrays + 20 tt (5 fluxes x 4 stages) + 5 mtt + tmp + euler_tt scratch (4 N) */
+    double *SAr = work, *SAs = SAr + N, *sr = SAs + N, *ss = sr + N, *mr = ss + N, *mss = mr + N;
+    double *ttk = mss + N;       /* [stage][flux][N] */
+    double *mttk = ttk + 20 * N; /* [flux][N] of the current stage */
+    double *tmp = mttk + 5 * N, *w2 = tmp + N;
+    const double inf_mat = F(RSF_inf_mat_rz), inf_pf = F(RSF_inf_pf_rz), inf_ss = F(RSF_inf_pf_ss), C_in = F(RSF_C_in);
+    const double flux[5] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_rz), F(RSF_cpr_rz), F(RSF_q_ss)};
+    const int procs[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
+    const double evap = flux[0], transp = flux[1], q_rz = flux[2], cpr = flux[3], q_ss = flux[4];
+    /* upper boundary condition :1146-1222 (the Euler solver's) */
+    for (int j = 0; j < A; j++) {
+        const double tt_im = (j == 0) ? ((inf_mat > 0) ? 1 : 0) * m : 0.0, tt_ip = (j == 0) ? ((inf_pf > 0) ? 1 : 0) * m : 0.0;
+        const double tt_is = (j == 0) ? ((inf_ss > 0) ? 1 : 0) * m : 0.0;
+        const double mtt_im = (j == 0) ? ((inf_mat > 0) ? C_in : 0) * m : 0.0, mtt_ip = (j == 0) ? ((inf_pf > 0) ? C_in : 0) * m : 0.0;
+        const double mtt_is = (j == 0) ? ((inf_ss > 0) ? C_in : 0) * m : 0.0;
+        const double dsa_rz = (inf_mat * tt_im + inf_pf * tt_ip) * h;
+        const double dsa_ss = (inf_ss * tt_is) * h;
+        const double dmsa_rz1 = nan0(mtt_im) * ((dsa_rz > 0) ? ((inf_mat * tt_im * h) / dsa_rz) : 0) +
+                                nan0(mtt_ip) * ((dsa_rz > 0) ? ((inf_pf * tt_ip * h) / dsa_rz) : 0);
+        const double dmsa_ss1 = nan0(mtt_is) * ((dsa_ss > 0) ? ((inf_ss * tt_is * h) / dsa_ss) : 0);
+        ms_rz[j] = euler_mix(ms_rz[j], s_rz[j], dsa_rz, dmsa_rz1, 1);
+        ms_ss[j] = euler_mix(ms_ss[j], s_ss[j], dsa_ss, dmsa_ss1, 0);
+        s_rz[j] += dsa_rz;
+        s_ss[j] += dsa_ss;
+        ms_rz[j] = (s_rz[j] <= 0) ? 0 : ms_rz[j];
+        ms_ss[j] = (s_ss[j] <= 0) ? 0 : ms_ss[j];
+    }
+    calc_SA(A, s_rz, SAr);
+    for (int j = 0; j < N; j++) SAr[j] = SAr[j] * m;
+    calc_SA(A, s_ss, SAs);
+    for (int j = 0; j < N; j++) SAs[j] = SAs[j] * m;
+    memcpy(sr, s_rz, sizeof(double) * A);
+    memcpy(ss, s_ss, sizeof(double) * A);
+    memcpy(mr, ms_rz, sizeof(double) * A);
+    memcpy(mss, ms_ss, sizeof(double) * A);
+#define TTK(st, f) (ttk + ((size_t)(st) * 5 + (size_t)(f)) * N)
+#define MTT(f) (mttk + (size_t)(f) * N)
+    for (int st = 0; st < 4; st++) {
+        const int half = (st == 1 || st == 2);
+        for (int f = 0; f < 5; f++) {
+            const double fh = half ? flux[f] * h / 2 : flux[f] * h;
+            euler_tt(c, (f < 3) ? SAr : SAs, SP(procs[f]), fh, m, TTK(st, f), w2);
+            const double *msrc = (f < 3) ? mr : mss;
+            for (int j = 0; j < A; j++) MTT(f)[j] = (TTK(st, f)[j] > 0) ? msrc[j] : 0;
+        }
+        const double *tt_e = TTK(st, 0), *tt_t = TTK(st, 1), *tt_q = TTK(st, 2), *tt_c = TTK(st, 3), *tt_s = TTK(st, 4);
+        if (st == 0) { /* :1388-1431 */
+            for (int j = 0; j < A; j++) {
+                double dsa_rz = (cpr * tt_c[j] - evap * tt_e[j] - transp * tt_t[j] - q_rz * tt_q[j]) * h;
+                dsa_rz = (sr[j] + dsa_rz < 0) ? -sr[j] : dsa_rz;
+                double dsa_ss = (q_rz * tt_q[j] - cpr * tt_c[j] - q_ss * tt_s[j]) * h;
+                dsa_ss = (ss[j] + dsa_ss < 0) ? -ss[j] : dsa_ss;
+                const double dsa_rz1 = (cpr * tt_c[j]) * h;
+                const double dmsa_rz1 = nan0(MTT(3)[j]) * ((dsa_rz1 > 0) ? ((cpr * tt_c[j] * h) / dsa_rz1) : 0);
+                const double dsa_ss1 = (tt_q[j]) * h;
+                const double dmsa_ss1 = nan0(MTT(2)[j]) * ((dsa_ss1 > 0) ? ((q_rz * tt_q[j] * h) / dsa_ss1) : 0);
+                mr[j] = euler_mix(mr[j], sr[j], dsa_rz1, dmsa_rz1, 1);
+                mss[j] = euler_mix(mss[j], ss[j], dsa_ss1, dmsa_ss1, 0);
+                sr[j] += dsa_rz;
+                ss[j] += dsa_ss;
+                mr[j] = (sr[j] <= 0) ? 0 : mr[j];
+                mss[j] = (ss[j] <= 0) ? 0 : mss[j];
+            }
+        } else if (st == 1 || st == 2) { /* :1551-1581, :1699-1729 */
+            for (int j = 0; j < A; j++) {
+                double dsa_rz = (cpr * tt_c[j] - evap * tt_e[j] - transp * tt_t[j] - q_rz * tt_q[j]) * h / 2;
+                double dsa_ss = (q_rz * tt_q[j] - cpr * tt_c[j] - q_ss * tt_s[j]) * h / 2;
+                if (st == 1) {
+                    dsa_rz = (sr[j] + dsa_rz < 0) ? -sr[j] : dsa_rz;
+                    dsa_ss = (ss[j] + dsa_ss < 0) ? -ss[j] : dsa_ss;
+                } else {
+                    dsa_rz = (sr[j] - dsa_rz < 0) ? -sr[j] : dsa_rz;
+                    dsa_ss = (ss[j] - dsa_ss < 0) ? -ss[j] : dsa_ss;
+                }
+                sr[j] += dsa_rz;
+                ss[j] += dsa_ss;
+                const double r1 = nan0(MTT(3)[j]);
+                const double r2 = nan0(MTT(0)[j]) + nan0(MTT(1)[j]) + nan0(MTT(2)[j]);
+                double s1 = nan0(MTT(2)[j]);
+                double s2 = nan0(MTT(3)[j]) + nan0(MTT(4)[j]);
+                if (st == 1) { s1 = s1 * h / 2; s2 = s2 * h / 2; }
+                double dr = ((r1 < 0) && (r2 >= 0)) ? r1 + r2 : r1 - r2;
+                double ds = ((s1 < 0) && (s2 >= 0)) ? s1 + s2 : s1 - s2;
+                dr = (dr > 0) ? ((mr[j] + dr > 0) ? -mr[j] : dr) : dr;
+                ds = (ds > 0) ? ((mss[j] + ds > 0) ? -mss[j] : ds) : ds;
+                mr[j] += dr;
+                mss[j] += ds;
+            }
+        }
+        if (st < 3) { /* SArkn[1, 1:] = cumsum(sarkn[1]) */
+            double acc = sr[0];
+            SAr[1] = acc;
+            for (int j = 1; j < A; j++) { acc += sr[j]; SAr[j + 1] = acc; }
+            acc = ss[0];
+            SAs[1] = acc;
+            for (int j = 1; j < A; j++) { acc += ss[j]; SAs[j + 1] = acc; }
+        }
+    }
+    /* combination :1836-1856 into stage slot 0, solute travel-time distributions :1879-1897 */
+    for (int f = 0; f < 5; f++) {
+        double *t0 = TTK(0, f);
+        const double *t1 = TTK(1, f), *t2 = TTK(2, f), *t3 = TTK(3, f);
+        for (int j = 0; j < A; j++) t0[j] = (t0[j] + 2 * t1[j] + 2 * t2[j] + t3[j]) / 6.;
+        const double *msrc = (f < 3) ? ms_rz : ms_ss;
+        for (int j = 0; j < A; j++) MTT(f)[j] = (t0[j] > 0) ? msrc[j] : 0;
+        if (tt_base) memcpy(tt_base + (size_t)procs[f] * tt_stride, t0, sizeof(double) * A);
+    }
+    {
+        const int oc[5] = {RSO_C_evap_soil, RSO_C_transp, RSO_C_q_rz, RSO_C_cpr_rz, RSO_C_q_ss};
+        const int oi[5] = {RSO_C_iso_evap_soil, RSO_C_iso_transp, RSO_C_iso_q_rz, RSO_C_iso_cpr_rz, RSO_C_iso_q_ss};
+        for (int f = 0; f < 5; f++) {
+            O(oc[f]) = euler_flux_conc(A, MTT(f), TTK(0, f), tmp) * m;
+            O(oi[f]) = conc_to_delta(c, O(oc[f])) * m;
+        }
+        O(RSO_C_inf_mat_rz) = ((inf_mat > 0) ? C_in : NAN) * m;
+        O(RSO_C_inf_pf_rz) = ((inf_pf > 0) ? C_in : NAN) * m;
+        O(RSO_C_inf_pf_ss) = ((inf_ss > 0) ? C_in : NAN) * m;
+        O(RSO_C_iso_inf_mat_rz) = conc_to_delta(c, O(RSO_C_inf_mat_rz)) * m;
+        O(RSO_C_iso_inf_pf_rz) = conc_to_delta(c, O(RSO_C_inf_pf_rz)) * m;
+        O(RSO_C_iso_inf_pf_ss) = conc_to_delta(c, O(RSO_C_inf_pf_ss)) * m;
+    }
+    { /* update :1899-1945 (the Euler solver's) */
+        const double *tt_e = TTK(0, 0), *tt_t = TTK(0, 1), *tt_q = TTK(0, 2), *tt_c = TTK(0, 3), *tt_s = TTK(0, 4);
+        for (int j = 0; j < A; j++) {
+            const double mtt_c = MTT(3)[j], mtt_q = MTT(2)[j];
+            double dsa_rz = (cpr * tt_c[j] - evap * tt_e[j] - transp * tt_t[j] - q_rz * tt_q[j]) * h;
+            dsa_rz = (s_rz[j] + dsa_rz < 0) ? -s_rz[j] : dsa_rz;
+            double dsa_ss = (q_rz * tt_q[j] - cpr * tt_c[j] - q_ss * tt_s[j]) * h;
+            dsa_ss = (s_ss[j] + dsa_ss < 0) ? -s_ss[j] : dsa_ss;
+            const double dsa_rz1 = (cpr * tt_c[j]) * h;
+            const double dmsa_rz1 = nan0(mtt_c) * ((dsa_rz1 > 0) ? ((cpr * tt_c[j] * h) / dsa_rz1) : 0);
+            const double dsa_ss1 = (q_rz * tt_q[j]) * h;
+            const double dmsa_ss1 = nan0(mtt_q) * ((dsa_ss1 > 0) ? ((q_rz * tt_q[j] * h) / dsa_ss1) : 0);
+            ms_rz[j] = euler_mix(ms_rz[j], s_rz[j], dsa_rz1, dmsa_rz1, 1);
+            ms_ss[j] = euler_mix(ms_ss[j], s_ss[j], dsa_ss1, dmsa_ss1, 0);
+            s_rz[j] += dsa_rz;
+            s_ss[j] += dsa_ss;
+            ms_rz[j] = (s_rz[j] <= 0) ? 0 : ms_rz[j];
+            ms_ss[j] = (s_ss[j] <= 0) ? 0 : ms_ss[j];
+        }
+    }
+#undef TTK
+#undef MTT
+#undef F
+#undef O
+#undef SP
+}
+
 /* one explicit Euler step, anion branch (bromide / chloride; transport.py:2144-2156, :2320-2343, :2378-2407): msa holds
  * solute mass per bin; calc_mtt (:582-596) without the deterministic kernels' crop switch */
 static void euler_substep_cell_anion(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss,
@@ -923,6 +1084,7 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
         double *work = (double *)malloc(sizeof(double) * (size_t)(16 * (A + 2)));
         double *tmp = (double *)malloc(sizeof(double) * (size_t)(4 * (A + 2)));
         double *ttk = (double *)malloc(sizeof(double) * (size_t)(RSP_COUNT * A)); /* tt of the last Euler step (statistics) */
+        double *rkwork = (double *)malloc(sizeof(double) * (size_t)(40 * (A + 2)));
         double *ages = (double *)malloc(sizeof(double) * (size_t)A);
         for (int j = 0; j < A; j++) ages[j] = (double)(j + 1);
 #pragma omp for schedule(static)
@@ -945,6 +1107,12 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
                     euler_substep_cell_anion(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out,
                                              tt_out ? tt_out + (size_t)i * A : NULL, (size_t)C * A, work);
                     storage_kernels_anion(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
+                    continue;
+                }
+                if (st->solver == 2) {
+                    rk4_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out,
+                                     tt_out ? tt_out + (size_t)i * A : NULL, (size_t)C * A, rkwork);
+                    storage_kernels_iso(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
                     continue;
                 }
                 if (tt_out) euler_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out + (size_t)i * A, (size_t)C * A, work);
@@ -1016,6 +1184,7 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
         free(work);
         free(tmp);
         free(ttk);
+        free(rkwork);
         free(ages);
     }
 }
@@ -1035,7 +1204,7 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
                           const double *forcing, const double *mask, const double *sas_params, double *out, double *tt_out,
                           double *stats, double *balance_prev)
 {
-    if (st->solver == 1) { /* explicit Euler: isotope branch (callers check) */
+    if (st->solver == 1 || st->solver == 2) { /* explicit Euler / RK4 (callers check the supported combinations) */
         euler_day(C, st, sa_rz, sa_ss, msa_rz, msa_ss, forcing, mask, sas_params, out, tt_out, stats, balance_prev);
         return;
     }

@@ -54,6 +54,9 @@ CASES = {
                             sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     "sas_euler_bromide": dict(shape=(2, 3), ndays=20, ages=50, doy=100, solute="bromide", sas_solver="Euler",
                               sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
+    # Runge-Kutta solver (settings.sas_solver = "RK4"): oracle only so far
+    "sas_rk4": dict(shape=(2, 2), ndays=12, ages=40, doy=100, sas_solver="RK4",
+                    sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     "sas_euler_families": dict(shape=(2, 2), ndays=22, ages=45, doy=20, sas_solver="Euler", var_input=True,
                                sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0),
                                         q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
@@ -156,7 +159,7 @@ def run(name, simd_out=None):
     orig_check = numerics.sanity_check
     seen = {"itt": None}
 
-    euler = case["sas_solver"] == "Euler"
+    euler = case["sas_solver"] in ("Euler", "RK4")
 
     def recording_check(st):
         r = orig_check(st)
@@ -186,8 +189,8 @@ def run(name, simd_out=None):
             out.update({k: z[k] for k in z.files})
     for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES) + ["C_ISO_IN"] + (["C_IN"] if bromide else []):
         out["in_" + k] = case[k].reshape(C, -1)
-    if case["sas_solver"] == "Euler":
-        out["solver"] = np.asarray(1)
+    if case["sas_solver"] in ("Euler", "RK4"):
+        out["solver"] = np.asarray({"Euler": 1, "RK4": 2}[case["sas_solver"]])
     if bromide:
         out["solute"] = np.asarray(1)
         for k in ("alpha_transp", "alpha_q", "lu_id"):

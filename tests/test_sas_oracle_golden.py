@@ -18,7 +18,7 @@ def _libm_pow():
     lib().sas_oracle_set_pow(0)
 
 
-@pytest.mark.parametrize("case", u.SAS_CASES + u.ANION_CASES + u.EULER_CASES)
+@pytest.mark.parametrize("case", u.SAS_CASES + u.ANION_CASES + u.EULER_CASES + u.RK4_CASES)
 def test_oracle_reproduces_reference_bit_for_bit(case):
     fx = u.load_case(case)
     m = u.model_from_fixture(fx, OracleSasEngine)
