@@ -63,10 +63,10 @@ typedef struct roger_sas_settings {
     int32_t solute;         /* 0: stable isotope (oxygen-18 / deuterium: msa holds bin concentrations);
                                1: conservative anion (bromide / chloride: msa holds bin solute MASS, the *_transport_anion_kernel
                                   family of the reference; the RSO_C_iso_* result planes then hold the solute masses M_*) */
-    int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day;
-                               (2: RK4, transport.py:1138-2047 -- restated in the CPU oracle only, roger_sas_create rejects it)
+    int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day
                                (svat_transport_model_euler, transport.py:2063-2413; statistics / balance errors are those of the day's
-                               last Euler step, as the reference's output shows them; the anion branch runs without statistics) */
+                               last Euler step, as the reference's output shows them; the anion branch runs without statistics);
+                               2: RK4 (transport.py:1138-2047) is restated in the CPU oracle only -- roger_sas_create rejects it */
 } roger_sas_settings;
 
 typedef struct roger_sas roger_sas; /* opaque handle */
