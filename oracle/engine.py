@@ -156,8 +156,8 @@ class OracleSasEngine:
         self.ttbuf = np.zeros((len(sas.PROCESSES), self.n, self.A)) if settings.store_tt else None
         self.stats = np.zeros((len(sas.STATISTICS), self.n)) if settings.age_statistics else None
         self.balance_prev = np.zeros(self.n)
-        if settings.solver == 2 and (settings.solute != 0 or settings.age_statistics):
-            raise NotImplementedError("RK4 solver: isotope branch without age statistics")
+        if settings.solver == 2 and settings.solute != 0:
+            raise NotImplementedError("RK4 solver: isotope branch only")
         if settings.solver == 1 and settings.solute != 0 and settings.age_statistics:
             raise NotImplementedError("explicit Euler solver, anion branch: without age statistics")
         self._fn = lib().sas_oracle_day_stats

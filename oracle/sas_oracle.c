@@ -1111,7 +1111,7 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
                 }
                 if (st->solver == 2) {
                     rk4_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out,
-                                     tt_out ? tt_out + (size_t)i * A : NULL, (size_t)C * A, rkwork);
+                                     tt_out ? tt_out + (size_t)i * A : ((stats && last) ? ttk : NULL), tt_out ? (size_t)C * A : (size_t)A, rkwork);
                     storage_kernels_iso(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
                     continue;
                 }

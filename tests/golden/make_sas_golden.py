@@ -57,6 +57,8 @@ CASES = {
     # Runge-Kutta solver (settings.sas_solver = "RK4"): oracle only so far
     "sas_rk4": dict(shape=(2, 2), ndays=12, ages=40, doy=100, sas_solver="RK4",
                     sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
+    "sas_rk4_stats": dict(shape=(2, 2), ndays=10, ages=36, doy=105, sas_solver="RK4", age_statistics=True, var_input=True,
+                          sas=dict(evap_soil=(6, 0.2), cpr_rz=(3, 0.7, 1.6), transp=(6, 0.5), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(6, 1.5))),
     "sas_euler_families": dict(shape=(2, 2), ndays=22, ages=45, doy=20, sas_solver="Euler", var_input=True,
                                sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0),
                                         q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),

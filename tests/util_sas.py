@@ -8,7 +8,7 @@ from roger_b200 import sas
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SAS_CASES = ["sas_power", "sas_power_snow", "sas_families", "sas_power_stats"]
 ANION_CASES = ["sas_bromide"]
-RK4_CASES = ["sas_rk4"]  # oracle only: the device rejects solver = 2 so far
+RK4_CASES = ["sas_rk4", "sas_rk4_stats"]  # oracle only: the device rejects solver = 2 so far
 EULER_CASES = ["sas_euler", "sas_euler_families", "sas_euler_stats", "sas_euler_bromide"]
 
 
