@@ -379,3 +379,13 @@ def test_euler_anion_with_statistics_is_rejected():
     daily["C_IN"] = daily["C_ISO_IN"] * 0
     with pytest.raises(RogerCudaError):
         sas.SasModel(_cuda(), 4, 8, daily, spec, solver=sas.EULER, solute=sas.ANION, age_statistics=True)
+
+
+def test_rk4_solver_is_rejected_on_the_device():
+    """the RK4 solver is restated in the CPU oracle only: the device says so instead of computing something else"""
+    from roger_b200 import sas
+    from roger_b200.engine import RogerCudaError
+
+    daily, spec = _random_case(4, 8, 2, seed=1)
+    with pytest.raises(RogerCudaError):
+        sas.SasModel(_cuda(), 4, 8, daily, spec, solver=sas.RK4)
