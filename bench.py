@@ -196,6 +196,10 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from roger_b200.engine import CudaSvatEngine
+    from roger_b200.parallel import bind_to_gpu_numa_node
+
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)  # page-locked buffers are first-touched on the GPU's own NUMA node
 
     if args.workload == "sas":
         sampler = ClockSampler(local)
@@ -209,6 +213,7 @@ def run_cuda(args):
                     "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(res["config"], parallelism=f"cell-block x{world}"),
                     "roofline": res["roofline"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks}
             if world == 1 and not args.no_cpu_baseline:
+                os.sched_setaffinity(0, affinity0)  # the CPU leg runs on every host core
                 line["cpu_baseline"] = sas_cpu_baseline(args.ages, cells=args.ref_cells)
             emit(line)
         if world > 1:
@@ -282,6 +287,7 @@ def run_cuda(args):
     # per step: scalars + flags read back (always); at each midnight: the day's forcing block from
     # host memory and a D2H of the daily output slab (theta_rz, S) as the reference's diagnostics would write.
     pin = [torch.empty(C, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    eng.reserve_snapshots(2)  # what a driver does when it configures its output: nothing is allocated inside the stepping loop
     # Steady-state placement of the window: a daily slab leaves the device asynchronously while the NEXT day's steps run, so a
     # window that happens to end a few steps after a midnight would time the tail of a copy a long run never waits for.  The
     # (untimed) steps below move the window's start to noon; the window still holds one midnight per simulated day.
@@ -349,7 +355,9 @@ def run_cuda(args):
         }
         if sas_res is not None:
             line["sas"] = sas_res
+        line["e2e"]["host_numa_binding"] = numa
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, affinity0)  # the CPU leg runs on every host core
             line["cpu_baseline"] = cpu_baseline(args)
             if sas_res is not None:
                 line["sas"]["cpu_baseline"] = sas_cpu_baseline(args.ages, cells=args.ref_cells)

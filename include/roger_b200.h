@@ -82,16 +82,29 @@ int roger_svat_download(roger_svat *h, int field, double *host);
  * second stream while later steps run.  The buffer is valid after roger_svat_download_wait(). */
 int roger_svat_download_async(roger_svat *h, int field, double *host_pinned);
 int roger_svat_download_wait(roger_svat *h);
-/* raw device address of a plane (for zero-copy use from torch / other kernels) */
-uint64_t roger_svat_plane_ptr(roger_svat *h, int field);
+/* Makes sure `n` device snapshot planes exist so that roger_svat_download_async / _diagnostics_async never allocate inside
+ * a stepping loop; a driver calls it once when it configures its output (n = planes handed over per output time).  The
+ * copy stream, its events and the fence ring are created by roger_svat_create. */
+int roger_svat_reserve_snapshots(roger_svat *h, int n);
+/* Device layout of the planes, for zero-copy use from other kernels: tile-major, [tile][plane][cell] with `tile_cells`
+ * consecutive cells per tile; plane `f` (a P or S field id) of cell i is the double at
+ *   ps_base + (((i / tile_cells) * n_ps_planes + f) * tile_cells + i % tile_cells) * 8,
+ * flux field f likewise with flux_base, n_flux_planes and f - n_ps_planes (flux_base is 0 until a flux plane was asked for). */
+typedef struct roger_svat_layout {
+    uint64_t ps_base, flux_base;
+    int64_t n_tiles;
+    int32_t tile_cells, n_ps_planes, n_flux_planes, reserved;
+} roger_svat_layout;
+int roger_svat_tile_layout(roger_svat *h, roger_svat_layout *out);
 
 int roger_svat_set_scalars(roger_svat *h, const roger_svat_scalars *s);
 int roger_svat_get_scalars(roger_svat *h, roger_svat_scalars *s);
 
 /* ---- forcing: the day block that RogerSetup.set_forcing writes into vs.prec_day/ta_day/pet_day
  *      at midnight (roger/models/svat/svat.py:150-174).  Host pointers; 144 doubles each when
- *      settings.forcing_uniform, else n_cells*144 in the reference's (cell, slot) order.
- *      The copy is asynchronous on the handle's stream from the caller's (ideally pinned) buffer. */
+ *      settings.forcing_uniform, else n_cells*144 in the reference's (cell, slot) order; per-cell blocks are re-tiled on
+ *      the device to [tile][slot][cell] so that the 144-slot aggregations of adaptive_time_stepping.py:385-437 read
+ *      coalesced.  The copy is asynchronous on the handle's stream from the caller's (ideally pinned) buffer. */
 int roger_svat_set_forcing_day(roger_svat *h, const double *prec_day, const double *ta_day,
                                const double *pet_day);
 /* same, from buffers already resident on the device (raw addresses) */

@@ -39,6 +39,13 @@ class SvatScalars(C.Structure):
     ]
 
 
+class SvatLayout(C.Structure):
+    _fields_ = [
+        ("ps_base", C.c_uint64), ("flux_base", C.c_uint64), ("n_tiles", C.c_int64),
+        ("tile_cells", C.c_int32), ("n_ps_planes", C.c_int32), ("n_flux_planes", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 def default_settings(lateral=False, forcing_uniform=True, **over):
     from .params import SETTINGS_DEFAULTS as D
 

@@ -2,10 +2,11 @@
 // hot path (include/roger_b200.h).  sm_100a only; there is no CPU fallback: every entry point
 // fails with -ROGER_ENODEV / -ROGER_ECUDA if no usable CUDA device is present.
 //
-// Data layout in HBM: structure of arrays, one plane of C doubles per field
-// (include/roger_b200_fields.h), cell index fastest, so a warp's 32 threads read/write 256
-// contiguous bytes per field.  Parameter (P) and state (S) planes live in one allocation; flux (F)
-// planes are allocated lazily, only when a caller asks for diagnostics.
+// Data layout in HBM: tile-major structure of arrays, [tile of 256 cells][plane][cell] (svat_device.cuh: Io): a warp's
+// 32 threads read / write 256 contiguous bytes per field, a block's whole working set is one contiguous region and a
+// plane access is base + immediate.  Parameter (P) and state (S) planes live in one allocation; flux (F) planes are
+// allocated lazily, only when a caller asks for diagnostics.  Per-cell forcing day blocks arrive in the reference's
+// (cell, slot) order and are re-tiled to [tile][slot][cell] on upload, so the 144-slot aggregations read coalesced.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -62,20 +63,33 @@ __host__ __device__ inline double pairwise144(F at) {
     return 0.0 + (half[0] + half[1]);
 }
 
+// one cell's 144 forcing slots inside a re-tiled day block ([tile][slot][cell]: consecutive slots are kTile doubles apart)
+struct TiledRow {
+    const double* p;
+    __host__ __device__ double operator[](int k) const { return p[(size_t)k * kTile]; }
+};
+__host__ __device__ inline TiledRow tiled_row(const double* day, int64_t i) {
+    return TiledRow{day + (size_t)(i >> kTileShift) * (144 * kTile) + (size_t)(i & kTileMask)};
+}
+
 struct RowAgg {  // aggregates of one forcing row for the three time-step classes
-    __host__ __device__ static double day_sum(const double* row) {
+    template <class R>
+    __host__ __device__ static double day_sum(R row) {
         return pairwise144([&](int k) { return row[k]; });
     }
-    __host__ __device__ static double day_nanmean(const double* row) {
+    template <class R>
+    __host__ __device__ static double day_nanmean(R row) {
         int cnt = 0;
         for (int k = 0; k < 144; k++) cnt += (row[k] == row[k]) ? 1 : 0;
         double tot = pairwise144([&](int k) { double v = row[k]; return (v == v) ? v : 0.0; });
         return tot / (double)cnt;
     }
-    __host__ __device__ static double win_sum(const double* row, int itt_day) {
+    template <class R>
+    __host__ __device__ static double win_sum(R row, int itt_day) {
         return pairwise144([&](int k) { return (k >= itt_day && k < itt_day + 6) ? row[k] : 0.0; });
     }
-    __host__ __device__ static double win_nanmean(const double* row, int itt_day) {
+    template <class R>
+    __host__ __device__ static double win_nanmean(R row, int itt_day) {
         int cnt = 0;
         for (int k = itt_day; k < itt_day + 6 && k < 144; k++) cnt += (row[k] == row[k]) ? 1 : 0;
         double tot = pairwise144([&](int k) {
@@ -88,10 +102,14 @@ struct RowAgg {  // aggregates of one forcing row for the three time-step classe
 
 // ------------------------------------------------------------------------------------------------
 struct Planes {
-    double* ps;  // kNumPS planes
-    double* fl;  // kNumF planes (may be null)
+    double* ps;  // n_tiles x kNumPS x kTile
+    double* fl;  // n_tiles x kNumF x kTile (may be null)
     int64_t C;
-    __host__ __device__ double* at(int id) const { return kind_is_F(id) ? fl + (size_t)(id - kNumPS) * C : ps + (size_t)id * C; }
+    __host__ __device__ double* at(int id, int64_t i) const {  // plane `id` of cell i
+        const size_t t = (size_t)(i >> kTileShift), l = (size_t)(i & kTileMask);
+        return kind_is_F(id) ? fl + ((t * kNumF + (size_t)(id - kNumPS)) << kTileShift) + l
+                             : ps + ((t * kNumPS + (size_t)id) << kTileShift) + l;
+    }
 };
 
 __device__ __forceinline__ void warp_or(unsigned* flags, unsigned bits) {
@@ -104,7 +122,7 @@ __global__ void k_snow_flags(Planes pl, unsigned* flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned bits = 0;
     if (i < pl.C) {
-        double swe = pl.at(RF_swe)[i], st = pl.at(RF_swe_top)[i];
+        double swe = *pl.at(RF_swe, i), st = *pl.at(RF_swe_top, i);
         bits |= (swe > 0) ? FLAG_SWE_GT0 : 0;
         bits |= !(swe <= 0) ? FLAG_SWE_NOT_LE0 : 0;
         bits |= (st > 0) ? FLAG_SWETOP_GT0 : 0;
@@ -113,7 +131,8 @@ __global__ void k_snow_flags(Planes pl, unsigned* flags) {
     warp_or(flags, bits);
 }
 
-// grid-wide conditions on the day's forcing block (adaptive_time_stepping.py:38-80), distributed forcing
+// grid-wide conditions on the day's forcing block (adaptive_time_stepping.py:38-80), distributed forcing; any order of
+// the elements will do, so the re-tiled block is walked linearly (the padding cells of the last tile hold copies of cell 0)
 __global__ void k_day_flags(const double* __restrict__ prec_day, const double* __restrict__ ta_day, int64_t n,
                             double ta_fm, double hpi, unsigned* flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,17 +158,16 @@ __global__ void k_aggregate_a(Planes pl, double* __restrict__ prec_m1, const dou
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned bits = 0;
     if (i < pl.C) {
-        double* prec = pl.at(RF_prec);
-        double* ta = pl.at(RF_ta);
-        double p = prec[i], t = ta[i];
+        double* prec = pl.at(RF_prec, i);
+        double* ta = pl.at(RF_ta, i);
+        double p = *prec, t = *ta;
         prec_m1[i] = p;
-        const double* pr = prec_day + (size_t)i * 144;
-        const double* tr = ta_day + (size_t)i * 144;
+        const TiledRow pr = tiled_row(prec_day, i), tr = tiled_row(ta_day, i);
         if (class_a == 1) { p = RowAgg::day_sum(pr); t = RowAgg::day_nanmean(tr); }
         else if (class_a == 2) { p = RowAgg::win_sum(pr, itt_day); t = RowAgg::win_nanmean(tr, itt_day); }
         else if (class_a == 3) { p = pr[itt_day]; t = tr[itt_day]; }
-        if (class_a) { prec[i] = p; ta[i] = t; }
-        double swe = pl.at(RF_swe)[i], st = pl.at(RF_swe_top)[i];
+        if (class_a) { *prec = p; *ta = t; }
+        double swe = *pl.at(RF_swe, i), st = *pl.at(RF_swe_top, i);
         bits |= ((p > 0) && (t > ta_fm)) ? EV_RAIN_WARM : 0;
         bits |= (((swe > 0) || (st > 0)) && (t > ta_fm)) ? EV_SNOW_WARM : 0;
         bits |= !(p <= 0) ? EV_NOT_PREC_LE0 : 0;
@@ -165,6 +183,17 @@ __global__ void k_aggregate_a(Planes pl, double* __restrict__ prec_m1, const dou
 #ifndef ROGER_BLOCK
 #define ROGER_BLOCK 256
 #endif
+#ifndef ROGER_BULK_PREFETCH
+#define ROGER_BULK_PREFETCH 1
+#endif
+#ifndef ROGER_BULK_PREFETCH_DIST
+#define ROGER_BULK_PREFETCH_DIST 0  // tiles ahead of the block's own
+#endif
+constexpr unsigned kPrefetchChunk = 32 * kTile * sizeof(double);  // 64 KB per instruction
+constexpr unsigned kPrefetchChunks = (unsigned)((kTileBytesPS + kPrefetchChunk - 1) / kPrefetchChunk);
+template <bool LAT>
+__host__ __device__ constexpr unsigned kPrefetchEnd() { return (unsigned)kTileBytesPS; }
+static_assert(ROGER_BLOCK == kTile, "one k_svat_step block per tile");
 template <bool LAT, bool FLUX>
 __global__ void __launch_bounds__(ROGER_BLOCK, ROGER_MIN_BLOCKS)
 k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* __restrict__ ta_day,
@@ -172,6 +201,20 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
     const int64_t C = pl.C;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned bits = 0;
+#if ROGER_BULK_PREFETCH
+    // The block's tile is one contiguous region: ask the memory system for all of it (or for the tile of the block that
+    // will follow on this SM) with a handful of bulk L2 prefetches, instead of discovering the ~100 planes one dependent
+    // load group after the other.  No registers, no shared memory, no completion to wait for.
+    if (threadIdx.x < kPrefetchChunks) {
+        const int64_t tile = (int64_t)blockIdx.x + ROGER_BULK_PREFETCH_DIST;
+        if (tile * kTile < C) {
+            const char* src = reinterpret_cast<const char*>(pl.ps) + (size_t)tile * kTileBytesPS + (size_t)threadIdx.x * kPrefetchChunk;
+            const unsigned left = (unsigned)(kPrefetchEnd<LAT>() - threadIdx.x * kPrefetchChunk);
+            const unsigned bytes = left < kPrefetchChunk ? left : kPrefetchChunk;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        }
+    }
+#endif
     if (i < C) {
         Cell c;
 #ifdef ROGER_DEBUG_NAN_INIT  // use-before-load detector for the lazy loads (tests only)
@@ -180,7 +223,7 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
             for (unsigned k = 0; k < sizeof(Cell) / sizeof(double); k++) raw[k] = __longlong_as_double(0x7ff8000000000000ULL);
         }
 #endif
-        const Io io{pl.ps, pl.fl, C, i};
+        const Io io{pl.ps, pl.fl, i};
         c.maskCatch = io.ldp(RF_maskCatch);
         c.m = c.maskCatch;
         // ---- adaptive_time_stepping.py:130-189 / :256-360: forcing for this cell ----
@@ -191,8 +234,7 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
             if (p.class_b) { c.pet = p.u_pet; c.ta = p.u_ta_b; }
         } else {
             c.prec_m1 = prec_m1_plane[i];  // prec / ta already hold the class-A aggregates (k_aggregate_a)
-            const double* tr = ta_day + (size_t)i * 144;
-            const double* er = pet_day + (size_t)i * 144;
+            const TiledRow tr = tiled_row(ta_day, i), er = tiled_row(pet_day, i);
             if (p.class_b == 1) { c.pet = er[p.itt_day]; c.ta = tr[p.itt_day]; }
             else if (p.class_b == 2) { c.pet = RowAgg::win_sum(er, p.itt_day); c.ta = RowAgg::win_nanmean(tr, p.itt_day); }
             else if (p.class_b == 3) { c.pet = RowAgg::day_sum(er); c.ta = RowAgg::day_nanmean(tr); }
@@ -219,15 +261,49 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
 __global__ void k_soil_kh_refresh(Planes pl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pl.C) return;
-    const Io io{pl.ps, pl.fl, pl.C, i};
+    const Io io{pl.ps, pl.fl, i};
     soil_kh_refresh(io);
+}
+
+// ---- host-order <-> tile-order movers.  The C ABI speaks plain planes of C doubles (cell index fastest).
+__global__ void k_scatter_plane(Planes pl, int field, const double* __restrict__ src) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pl.C) *pl.at(field, i) = src[i];
+}
+__global__ void k_gather_plane(Planes pl, int field, double* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pl.C) dst[i] = *pl.at(field, i);
+}
+__global__ void k_copy_plane(Planes pl, int dst_field, int src_field) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pl.C) *pl.at(dst_field, i) = *pl.at(src_field, i);
+}
+// A chunk of a per-cell forcing day block, (cell, slot) order -> [tile][slot][cell].  One block per 32 cells: rows are read
+// with the lanes along the slots (contiguous 256 B per request), turned in shared memory and written with the lanes along
+// the cells.  `cell0` is a multiple of 32; cells at and beyond C (padding of the last tile) receive cell `C - 1`'s row so
+// that linear walks over the re-tiled block (k_day_flags) see no foreign values.
+__global__ void __launch_bounds__(256) k_forcing_to_tiles(const double* __restrict__ src, int64_t src_cell0, double* __restrict__ dst,
+                                                           int64_t cell0, int64_t C) {
+    __shared__ double t[32][145];
+    const int64_t base = cell0 + (int64_t)blockIdx.x * 32;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = w; r < 32; r += 8) {
+        int64_t cell = base + r;
+        if (cell >= C) cell = C - 1;
+        const double* row = src + (size_t)(cell - src_cell0) * 144;
+        for (int k = lane; k < 144; k += 32) t[r][k] = row[k];
+    }
+    __syncthreads();
+    const int64_t cell = base + lane;
+    double* out = dst + (size_t)(cell >> kTileShift) * (144 * kTile) + (size_t)(cell & kTileMask);
+    for (int k = w; k < 144; k += 8) out[(size_t)k * kTile] = t[lane][k];
 }
 
 __global__ void k_accumulate_rates(Planes pl, double* __restrict__ acc, const int* __restrict__ fields, const int* __restrict__ modes, int n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pl.C) return;
     for (int k = 0; k < n; k++) {
-        const double v = pl.at(fields[k])[i];
+        const double v = *pl.at(fields[k], i);
         double a = acc[(size_t)k * pl.C + i];
         const int mode = modes[k];
         if (mode == ROGER_DIAG_RATE) a = a + v;
@@ -270,7 +346,7 @@ k_svat_steps(Planes pl, const StepPlan* __restrict__ plans, int n_plans, unsigne
         unsigned bits = 0;
         if (i < C) {
             Cell c;
-            const Io io{pl.ps, pl.fl, C, i};
+            const Io io{pl.ps, pl.fl, i};
             c.maskCatch = io.ldp(RF_maskCatch);
             c.m = c.maskCatch;
             c.prec = io.lds(RF_prec); c.ta = io.lds(RF_ta); c.pet = io.lds(RF_pet);
@@ -319,8 +395,10 @@ struct roger_svat {
     double* d_ps = nullptr;
     double* d_fl = nullptr;
     double* d_prec_m1 = nullptr;
-    double* d_forc[3] = {nullptr, nullptr, nullptr};  // prec_day, ta_day, pet_day (owned copies)
+    double* d_forc[3] = {nullptr, nullptr, nullptr};  // prec_day, ta_day, pet_day re-tiled to [tile][slot][cell] (per-cell forcing)
     const double* forc[3] = {nullptr, nullptr, nullptr};
+    double* d_stage = nullptr;        // one host-order plane (upload / download) == kForcingChunk cells of a forcing day block
+    int64_t n_tiles = 0, Cpad = 0;
     double h_forc[3][144];  // uniform forcing (host copy for the scheduler)
     unsigned* d_flags = nullptr;  // [0] snow/sanity flags, [1] day flags, [2] event flags
     unsigned* h_flags = nullptr;  // pinned
@@ -365,13 +443,14 @@ struct roger_svat {
         return v;
     }
     Planes planes() const { return Planes{d_ps, d_fl, C}; }
+    int grid256() const { return (int)((C + 255) / 256); }
 };
 
 static int ensure_flux_planes(roger_svat* h) {
     if (h->d_fl) return 0;
     CU(cudaSetDevice(h->device));
-    CU(cudaMalloc(&h->d_fl, sizeof(double) * (size_t)kNumF * (size_t)h->C));
-    CU(cudaMemsetAsync(h->d_fl, 0, sizeof(double) * (size_t)kNumF * (size_t)h->C, h->stream));
+    CU(cudaMalloc(&h->d_fl, kTileBytesF * (size_t)h->n_tiles));
+    CU(cudaMemsetAsync(h->d_fl, 0, kTileBytesF * (size_t)h->n_tiles, h->stream));
     return 0;
 }
 
@@ -392,10 +471,11 @@ int roger_svat_field_count(void) { return RF_COUNT; }
 const char* roger_svat_field_name(int f) { return (f >= 0 && f < RF_COUNT) ? kFieldName[f] : nullptr; }
 int roger_svat_field_kind(int f) { return (f >= 0 && f < RF_COUNT) ? kFieldKind[f] : -1; }
 
+static int ensure_copy_stream(roger_svat* h);
+
 int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settings* settings, int device) {
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_svat_create: bad argument");
-    if (n_cells >= (int64_t(1) << 29))  // the kernels address a plane by a 32-bit byte count (svat_device.cuh: Io)
-        return fail(ROGER_EINVAL, "roger_svat_create: at most 2^29 - 1 cells per handle (a plane must stay below 4 GiB); shard the grid");
+    if (n_cells >= (int64_t(1) << 31)) return fail(ROGER_EINVAL, "roger_svat_create: at most 2^31 - 1 cells per handle; shard the grid");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -405,6 +485,8 @@ int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settin
     CU(cudaSetDevice(device));
     roger_svat* h = new roger_svat();
     h->C = n_cells;
+    h->n_tiles = (n_cells + kTile - 1) / kTile;
+    h->Cpad = h->n_tiles * kTile;
     h->device = device;
     h->st = *settings;
     h->sc.dt = 1.0;
@@ -413,19 +495,23 @@ int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settin
     h->sc.sanity_ok = 1;
     h->sc.month = 1;
     // Day-blocked launches pay off where the per-step launch + flag read-back latency (~35 us) is comparable to the kernel
-    // time; on large grids the per-step kernel (4 blocks / SM) is faster per step than the blocked one (measured on B200:
-    // 5.8 vs 6.9 ms per step at 4096^2 cells -- the step is bound by dependent-instruction latency, not by HBM).
+    // time; on large grids the per-step kernel is faster per step than the blocked one.
     h->step_batching = (n_cells <= 262144) ? 1 : 2;
     const size_t plane = sizeof(double) * (size_t)n_cells;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&h->d_ps, plane * kNumPS));
-    CU(cudaMemsetAsync(h->d_ps, 0, plane * kNumPS, h->stream));
+    CU(cudaMalloc(&h->d_ps, kTileBytesPS * (size_t)h->n_tiles));
+    CU(cudaMemsetAsync(h->d_ps, 0, kTileBytesPS * (size_t)h->n_tiles, h->stream));
     CU(cudaMalloc(&h->d_prec_m1, plane));
+    CU(cudaMalloc(&h->d_stage, plane));
     CU(cudaMalloc(&h->d_flags, 4 * sizeof(unsigned)));
     CU(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(unsigned), h->stream));
     CU(cudaHostAlloc(&h->h_flags, 4 * sizeof(unsigned), cudaHostAllocDefault));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
+    // everything the asynchronous read-back needs exists from the start: no allocation, stream or event creation ever
+    // happens inside a stepping loop (snapshot planes: roger_svat_reserve_snapshots)
+    { int r = ensure_copy_stream(h); if (r) { roger_svat_destroy(h); return r; } }
+    for (auto& f : h->fences) CU(cudaEventCreateWithFlags(&f, cudaEventDisableTiming | cudaEventBlockingSync));
     *out = h;
     return 0;
 }
@@ -437,6 +523,7 @@ void roger_svat_destroy(roger_svat* h) {
     cudaFree(h->d_ps);
     cudaFree(h->d_fl);
     cudaFree(h->d_prec_m1);
+    cudaFree(h->d_stage);
     for (auto p : h->d_forc) cudaFree(p);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (auto p : h->snap_free) cudaFree(p);
@@ -456,11 +543,13 @@ void roger_svat_destroy(roger_svat* h) {
 }
 
 int roger_svat_upload(roger_svat* h, int field, const double* host) {
-    if (h && (field == RF_k || field == RF_h)) h->soil_kh_stale = false;  // the caller's values stand until the next state-only step
     if (!h || !host || field < 0 || field >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_upload: bad argument");
+    if (field == RF_k || field == RF_h) h->soil_kh_stale = false;  // the caller's values stand until the next state-only step
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
-    CU(cudaMemcpyAsync(h->planes().at(field), host, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_stage, host, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+    k_scatter_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, h->d_stage);
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     if (field == RF_swe || field == RF_swe_top) h->snow_flags_valid = false;
     if (field == RF_prec || field == RF_ta) h->u_cur_valid = false;
@@ -473,27 +562,46 @@ int roger_svat_download(roger_svat* h, int field, double* host) {
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
     if (is_soil_kh(field)) { int r = refresh_soil_kh(h); if (r) return r; }
-    CU(cudaMemcpyAsync(host, h->planes().at(field), sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    k_gather_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, h->d_stage);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, h->d_stage, sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
-static int ensure_copy_stream(roger_svat* h);
+// a snapshot plane from the pool (roger_svat_reserve_snapshots fills it ahead of time; grows on demand otherwise)
+static int take_snapshot_plane(roger_svat* h, double** snap) {
+    if (!h->snap_free.empty()) { *snap = h->snap_free.back(); h->snap_free.pop_back(); }
+    else CU(cudaMalloc(snap, sizeof(double) * (size_t)h->C));
+    h->snap_busy.push_back(*snap);
+    return 0;
+}
 
-// Snapshot of a plane as of the steps issued so far, copied to the host off the critical path: a device-to-device copy
-// on the compute stream (microseconds), then the PCIe transfer on a second stream while later steps run.
+// Makes sure `n` snapshot planes exist, so that asynchronous read-backs inside a stepping loop never allocate: a driver
+// calls this once when it configures its output (n = planes handed over per output time).
+int roger_svat_reserve_snapshots(roger_svat* h, int n) {
+    if (!h || n < 0 || n > 4096) return fail(ROGER_EINVAL, "roger_svat_reserve_snapshots: bad argument");
+    CU(cudaSetDevice(h->device));
+    while ((int)(h->snap_free.size() + h->snap_busy.size()) < n) {
+        double* snap = nullptr;
+        CU(cudaMalloc(&snap, sizeof(double) * (size_t)h->C));
+        h->snap_free.push_back(snap);
+    }
+    return 0;
+}
+
+// Snapshot of a plane as of the steps issued so far, copied to the host off the critical path: a gather into a host-order
+// snapshot plane on the compute stream (microseconds), then the PCIe transfer on a second stream while later steps run.
 int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
     if (!h || !host_pinned || field < 0 || field >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_download_async: bad argument");
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
     if (is_soil_kh(field)) { int r = refresh_soil_kh(h); if (r) return r; }
-    { int r = ensure_copy_stream(h); if (r) return r; }
     const size_t plane = sizeof(double) * (size_t)h->C;
     double* snap = nullptr;
-    if (!h->snap_free.empty()) { snap = h->snap_free.back(); h->snap_free.pop_back(); }
-    else CU(cudaMalloc(&snap, plane));
-    h->snap_busy.push_back(snap);
-    CU(cudaMemcpyAsync(snap, h->planes().at(field), plane, cudaMemcpyDeviceToDevice, h->stream));
+    { int r = take_snapshot_plane(h, &snap); if (r) return r; }
+    k_gather_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, snap);
+    CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_snap, h->stream));
     CU(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
     CU(cudaMemcpyAsync(host_pinned, snap, plane, cudaMemcpyDeviceToHost, h->copy_stream));
@@ -512,15 +620,12 @@ int roger_svat_download_diagnostics_async(roger_svat* h, double* host_pinned, in
     if (!h || !host_pinned) return fail(ROGER_EINVAL, "roger_svat_download_diagnostics_async: bad argument");
     if (h->rate_fields.empty()) return fail(ROGER_EINVAL, "roger_svat_download_diagnostics_async: no diagnostics set");
     CU(cudaSetDevice(h->device));
-    { int r = ensure_copy_stream(h); if (r) return r; }
     const size_t plane = sizeof(double) * (size_t)h->C;
     const size_t n = h->rate_fields.size();
     std::vector<double*> snaps(n);
     for (size_t k = 0; k < n; k++) {
         double* snap = nullptr;
-        if (!h->snap_free.empty()) { snap = h->snap_free.back(); h->snap_free.pop_back(); }
-        else CU(cudaMalloc(&snap, plane));
-        h->snap_busy.push_back(snap);
+        { int r = take_snapshot_plane(h, &snap); if (r) return r; }
         snaps[k] = snap;
         CU(cudaMemcpyAsync(snap, h->d_rates + k * (size_t)h->C, plane, cudaMemcpyDeviceToDevice, h->stream));
     }
@@ -537,10 +642,8 @@ int roger_svat_download_diagnostics_async(roger_svat* h, double* host_pinned, in
 int roger_svat_download_fence(roger_svat* h) {
     if (!h) return fail(ROGER_EINVAL, "roger_svat_download_fence: null handle");
     CU(cudaSetDevice(h->device));
-    { int r = ensure_copy_stream(h); if (r) return r; }
     const int t = h->fence_next;
     h->fence_next = (h->fence_next + 1) % roger_svat::kFences;
-    if (!h->fences[t]) CU(cudaEventCreateWithFlags(&h->fences[t], cudaEventDisableTiming | cudaEventBlockingSync));
     CU(cudaEventRecord(h->fences[t], h->copy_stream));
     return t;
 }
@@ -553,7 +656,6 @@ int roger_svat_fence_wait(roger_svat* h, int token) {
 
 int roger_svat_download_wait(roger_svat* h) {
     if (!h) return fail(ROGER_EINVAL, "roger_svat_download_wait: null handle");
-    if (!h->copy_stream) return 0;
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->copy_stream));
     for (auto p : h->snap_busy) h->snap_free.push_back(p);
@@ -561,11 +663,16 @@ int roger_svat_download_wait(roger_svat* h) {
     return 0;
 }
 
-uint64_t roger_svat_plane_ptr(roger_svat* h, int field) {
-    if (!h || field < 0 || field >= RF_COUNT) return 0;
-    if (kind_is_F(field) && ensure_flux_planes(h)) return 0;
-    if (is_soil_kh(field) && refresh_soil_kh(h)) return 0;  // current as of this call; later state-only steps do not update it
-    return (uint64_t)(uintptr_t)h->planes().at(field);
+int roger_svat_tile_layout(roger_svat* h, roger_svat_layout* out) {
+    if (!h || !out) return fail(ROGER_EINVAL, "roger_svat_tile_layout: bad argument");
+    { int r = refresh_soil_kh(h); if (r) return r; }  // k, h current as of this call; later state-only steps do not update them
+    out->ps_base = (uint64_t)(uintptr_t)h->d_ps;
+    out->flux_base = (uint64_t)(uintptr_t)h->d_fl;
+    out->tile_cells = kTile;
+    out->n_tiles = h->n_tiles;
+    out->n_ps_planes = kNumPS;
+    out->n_flux_planes = kNumF;
+    return 0;
 }
 
 int roger_svat_set_scalars(roger_svat* h, const roger_svat_scalars* s) {
@@ -600,7 +707,7 @@ static int after_forcing(roger_svat* h) {
         h->day_flags = day_flags_host(h->h_forc[0], h->h_forc[1], 144, h->st.ta_fm, h->st.hpi);
     } else {
         CU(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(unsigned), h->stream));
-        int64_t n = h->C * 144;
+        int64_t n = h->Cpad * 144;  // the re-tiled block; its padding cells repeat the last cell
         int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
         k_day_flags<<<blocks, 256, 0, h->stream>>>(h->forc[0], h->forc[1], n, h->st.ta_fm, h->st.hpi, h->d_flags + 1);
         CU(cudaGetLastError());
@@ -613,6 +720,36 @@ static int after_forcing(roger_svat* h) {
     return 0;
 }
 
+// Per-cell forcing: (cell, slot) day blocks are re-tiled to [tile][slot][cell] in chunks of kForcingChunk cells through the
+// staging plane (host source) or straight from the caller's device buffer.
+static int retile_forcing(roger_svat* h, int v, const double* src, bool src_on_host) {
+    if (!h->d_forc[v]) CU(cudaMalloc(&h->d_forc[v], sizeof(double) * 144 * (size_t)h->Cpad));
+    const int64_t chunk = std::max<int64_t>(32, (h->C / 144) & ~int64_t(31));  // cells per staging pass (the plane holds C doubles)
+    if (!src_on_host) {
+        k_forcing_to_tiles<<<(int)(h->Cpad / 32), 256, 0, h->stream>>>(src, 0, h->d_forc[v], 0, h->C);
+        CU(cudaGetLastError());
+    } else if (h->C < 32 * 144) {  // tiny grids: the staging plane is smaller than one 32-cell group of rows
+        double* tmp = nullptr;
+        CU(cudaMalloc(&tmp, sizeof(double) * 144 * (size_t)h->C));
+        CU(cudaMemcpyAsync(tmp, src, sizeof(double) * 144 * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+        k_forcing_to_tiles<<<(int)(h->Cpad / 32), 256, 0, h->stream>>>(tmp, 0, h->d_forc[v], 0, h->C);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaFree(tmp));
+    } else {
+        for (int64_t c0 = 0; c0 < h->C; c0 += chunk) {
+            const int64_t n = std::min(chunk, h->C - c0);
+            const bool last = c0 + n >= h->C;
+            CU(cudaMemcpyAsync(h->d_stage, src + (size_t)c0 * 144, sizeof(double) * 144 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+            const int64_t upto = last ? h->Cpad : c0 + n;  // the last pass also fills the padding cells of the last tile
+            k_forcing_to_tiles<<<(int)((upto - c0 + 31) / 32), 256, 0, h->stream>>>(h->d_stage, c0, h->d_forc[v], c0, h->C);
+            CU(cudaGetLastError());
+        }
+    }
+    h->forc[v] = h->d_forc[v];
+    return 0;
+}
+
 int roger_svat_set_forcing_day(roger_svat* h, const double* prec_day, const double* ta_day, const double* pet_day) {
     if (!h || !prec_day || !ta_day || !pet_day) return fail(ROGER_EINVAL, "roger_svat_set_forcing_day: bad argument");
     CU(cudaSetDevice(h->device));
@@ -620,12 +757,7 @@ int roger_svat_set_forcing_day(roger_svat* h, const double* prec_day, const doub
     if (h->st.forcing_uniform) {
         for (int v = 0; v < 3; v++) memcpy(h->h_forc[v], src[v], sizeof(double) * 144);
     } else {
-        const size_t bytes = sizeof(double) * 144 * (size_t)h->C;
-        for (int v = 0; v < 3; v++) {
-            if (!h->d_forc[v]) CU(cudaMalloc(&h->d_forc[v], bytes));
-            CU(cudaMemcpyAsync(h->d_forc[v], src[v], bytes, cudaMemcpyHostToDevice, h->stream));
-            h->forc[v] = h->d_forc[v];
-        }
+        for (int v = 0; v < 3; v++) { int r = retile_forcing(h, v, src[v], true); if (r) return r; }
     }
     return after_forcing(h);
 }
@@ -639,7 +771,7 @@ int roger_svat_set_forcing_day_device(roger_svat* h, uint64_t prec_day, uint64_t
             CU(cudaMemcpyAsync(h->h_forc[v], src[v], sizeof(double) * 144, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     } else {
-        for (int v = 0; v < 3; v++) h->forc[v] = src[v];
+        for (int v = 0; v < 3; v++) { int r = retile_forcing(h, v, src[v], false); if (r) return r; }
     }
     return after_forcing(h);
 }
@@ -779,8 +911,8 @@ static int ensure_snow_flags(roger_svat* h, int64_t* launches) {
 
 static int ensure_uniform_current(roger_svat* h) {  // the "keep" class reads prec / ta [tau] as they are
     if (!h->st.forcing_uniform || h->u_cur_valid) return 0;
-    CU(cudaMemcpyAsync(&h->u_cur_prec, h->planes().at(RF_prec), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(&h->u_cur_ta, h->planes().at(RF_ta), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&h->u_cur_prec, h->planes().at(RF_prec, 0), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&h->u_cur_ta, h->planes().at(RF_ta, 0), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->u_cur_valid = true;
     return 0;
@@ -838,7 +970,9 @@ static int step_impl(roger_svat* h, int write_fluxes) {
         h->diag_count++;
     }
     if (!h->ks_ss_synced) {  // subsoil.calc_ks (subsoil.py:6-20): ks_ss = ks from the end of the first step on
-        CU(cudaMemcpyAsync(pl.at(RF_ks_ss), pl.at(RF_ks), sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToDevice, h->stream));
+        k_copy_plane<<<h->grid256(), 256, 0, h->stream>>>(pl, RF_ks_ss, RF_ks);
+        CU(cudaGetLastError());
+        launches++;
         h->ks_ss_synced = true;
     }
     CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));

@@ -119,65 +119,35 @@ RD double mk(const Cell& c, double x) { return MASK1 ? x : x * c.m; }
 #define ROGER_L2_PREFETCH 0
 #endif
 constexpr int kFirstFlux = RF_pet_res;  // the enum is ordered P.., S.., F..
-// (Measured alternative: per-thread base pointers + a 32-bit plane size make an access one IMAD.WIDE.U32 instead of five
-// integer instructions, but the compiler then derives each address from the previous one and the serial address chains
-// cost more than the instructions saved -- 6.05 vs 5.80 ms per step at 4096^2.)
-#ifndef ROGER_IO_MADWIDE
-#define ROGER_IO_MADWIDE 1
-#endif
-#if ROGER_IO_MADWIDE
-// One access = one `mad.wide.u32` (plane id * plane size in bytes + the thread's own base pointer) and the load / store.
-// The plane size is a 32-bit byte count (planes < 4 GiB, i.e. < 2^29 cells per handle -- checked at create); the cell
-// offset is folded into the per-thread base pointers once.  Written as inline PTX so that every address is computed
-// independently from the two loop-invariant registers (see the note above).
+constexpr int kNumPSPlanes = RF_pet_res;
+constexpr int kNumFPlanes = RF_COUNT - RF_pet_res;
+// Tile-major layout: the grid is cut into tiles of kTile consecutive cells and a tile holds ALL its planes back to back,
+// [tile][plane][kTile cells].  A thread keeps one pointer to its own cell inside its tile; plane `id` of that cell sits at
+// the compile-time byte offset id * kTile * 8, so every access is `LDG/STG [base + immediate]` -- no address arithmetic
+// at all (the plane-major layout of round 1 spent 14 % of the step's instructions on it) -- and a block's whole working
+// set is ONE contiguous ~220 KB region instead of ~110 streams a plane (134 MB at 4096^2 cells) apart, which is what the
+// bulk L2 prefetch below and the DRAM page / TLB locality rest on.
+constexpr int kTileShift = 8;
+constexpr int kTile = 1 << kTileShift;  // cells per tile == threads of a k_svat_step block
+constexpr int kTileMask = kTile - 1;
+constexpr size_t kTileBytesPS = (size_t)kNumPSPlanes * kTile * sizeof(double);
+constexpr size_t kTileBytesF = (size_t)kNumFPlanes * kTile * sizeof(double);
 struct Io {
-    char* __restrict__ ps;  // parameter + state planes, advanced to this thread's cell
-    char* __restrict__ fl;  // flux planes (FLUX kernels only), likewise
-    unsigned Cb;            // bytes per plane
-    RD Io(double* ps_, double* fl_, int64_t C, int64_t i)
-        : ps(reinterpret_cast<char*>(ps_ + i)), fl(fl_ ? reinterpret_cast<char*>(fl_ + i) : nullptr), Cb((unsigned)(C * 8)) {}
-    RD static double* mad(const char* base, unsigned id, unsigned cb) {
-        unsigned long long a;
-        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(cb), "r"(id), "l"((unsigned long long)base));
-        return reinterpret_cast<double*>(a);
-    }
-    RD double* at(int id) const { return mad(ps, (unsigned)id, Cb); }
+    char* __restrict__ ps;  // this thread's cell in plane 0 of its tile (parameter + state planes)
+    char* __restrict__ fl;  // likewise in the flux planes (FLUX kernels only)
+    RD Io(double* ps_, double* fl_, int64_t i)
+        : ps(reinterpret_cast<char*>(ps_) + (size_t)(i >> kTileShift) * kTileBytesPS + (size_t)(i & kTileMask) * sizeof(double)),
+          fl(fl_ ? reinterpret_cast<char*>(fl_) + (size_t)(i >> kTileShift) * kTileBytesF + (size_t)(i & kTileMask) * sizeof(double) : nullptr) {}
+    RD double* at(int id) const { return reinterpret_cast<double*>(ps + (size_t)id * (kTile * sizeof(double))); }
     RD double ldp(int id) const { return __ldg(at(id)); }
     RD double lds(int id) const { return *at(id); }
     RD void sts(int id, double v) const { *at(id) = v; }
     template <bool FLUX>
     RD void stf(int id, double v) const {
-        if (FLUX) *mad(fl, (unsigned)(id - kFirstFlux), Cb) = v;
+        if (FLUX) *reinterpret_cast<double*>(fl + (size_t)(id - kFirstFlux) * (kTile * sizeof(double))) = v;
     }
-    RD void pf(int id) const {
-#if ROGER_L2_PREFETCH == 2
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(id)));
-#else
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(at(id)));
-#endif
-    }
+    RD void pf(int id) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(at(id))); }
 };
-#else
-struct Io {
-    double* __restrict__ ps;  // parameter + state planes
-    double* __restrict__ fl;  // flux planes (FLUX kernels only)
-    int64_t C, i;
-    RD double ldp(int id) const { return __ldg(ps + (size_t)id * C + i); }
-    RD double lds(int id) const { return ps[(size_t)id * C + i]; }
-    RD void sts(int id, double v) const { ps[(size_t)id * C + i] = v; }
-    template <bool FLUX>
-    RD void stf(int id, double v) const {
-        if (FLUX) fl[(size_t)(id - kFirstFlux) * C + i] = v;
-    }
-    RD void pf(int id) const {
-#if ROGER_L2_PREFETCH == 2
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ps + (size_t)id * C + i));
-#else
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (size_t)id * C + i));
-#endif
-    }
-};
-#endif
 #define LDP(name) c.name = io.ldp(RF_##name)
 #define LDS(name) c.name = io.lds(RF_##name)
 #define STS(name) io.sts(RF_##name, c.name)

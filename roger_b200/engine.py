@@ -47,8 +47,8 @@ def load_library():
     lib.roger_svat_download_fence.argtypes = [hp]
     lib.roger_svat_fence_wait.argtypes = [hp, C.c_int]
     lib.roger_svat_download_wait.argtypes = [hp]
-    lib.roger_svat_plane_ptr.argtypes = [hp, C.c_int]
-    lib.roger_svat_plane_ptr.restype = C.c_uint64
+    lib.roger_svat_reserve_snapshots.argtypes = [hp, C.c_int]
+    lib.roger_svat_tile_layout.argtypes = [hp, C.POINTER(abi.SvatLayout)]
     lib.roger_svat_set_scalars.argtypes = [hp, C.POINTER(abi.SvatScalars)]
     lib.roger_svat_get_scalars.argtypes = [hp, C.POINTER(abi.SvatScalars)]
     lib.roger_svat_set_forcing_day.argtypes = [hp, dp, dp, dp]
@@ -158,8 +158,14 @@ class CudaSvatEngine:
         """may be called from another thread"""
         _check(self.lib, self.lib.roger_svat_fence_wait(self.h, int(token)))
 
-    def plane_ptr(self, name):
-        return int(self.lib.roger_svat_plane_ptr(self.h, abi.FIELD_ID[name]))
+    def reserve_snapshots(self, n):
+        """device snapshot planes for n asynchronous plane hand-overs per output time, allocated now (never inside the stepping loop)"""
+        _check(self.lib, self.lib.roger_svat_reserve_snapshots(self.h, int(n)))
+
+    def tile_layout(self):
+        lay = abi.SvatLayout()
+        _check(self.lib, self.lib.roger_svat_tile_layout(self.h, C.byref(lay)))
+        return lay
 
     def set_scalars(self, s):
         _check(self.lib, self.lib.roger_svat_set_scalars(self.h, C.byref(s)))

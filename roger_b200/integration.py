@@ -28,6 +28,17 @@ DAY = 24 * 60 * 60
 _SCALARS = ("time", "itt", "dt_secs", "itt_day", "event_id_counter", "time_event0")
 
 
+# settings (roger/settings.py:86-113) whose branches of RogerSetup.step the CUDA engine does not implement: a setup that
+# switches one of them on is refused instead of being run without it
+UNSUPPORTED_SETTINGS = (
+    "enable_groundwater", "enable_groundwater_boundary", "enable_film_flow", "enable_routing_1D", "enable_routing_2D",
+    "enable_runon_infiltration", "enable_urban", "enable_soil_compaction", "enable_time_variant_macropores",
+    "enable_irrigation", "enable_net_irrigation", "enable_crop_phenology", "enable_crop_rotation",
+    "enable_crop_specific_irrigation_demand", "enable_crop_partitioning", "enable_crop_water_stress", "enable_crop_optimization",
+    "enable_nitrate", "enable_virtualtracer",
+)
+
+
 class CudaStepDriver:
     def __init__(self, setup, engine_cls=None, engine_kwargs=None, pull="all", forcing_uniform=None,
                  clamp_small_negative_storage=None):
@@ -38,9 +49,12 @@ class CudaStepDriver:
         vs, st = self.state.variables, self.state.settings
         if getattr(st, "enable_offline_transport", False):
             raise ValueError("CudaStepDriver drives the online SVAT / oneD models; use roger_b200.sas for offline transport")
-        for flag in ("enable_groundwater", "enable_groundwater_boundary", "enable_film_flow", "enable_crop_phenology", "enable_routing"):
+        for flag in UNSUPPORTED_SETTINGS:  # every switch of roger/settings.py:86-113 that changes what the online step computes
             if getattr(st, flag, False):
                 raise NotImplementedError(f"settings.{flag} is outside the CUDA hot path (DESIGN.md section 7)")
+        if not getattr(st, "enable_adaptive_time_stepping", True):
+            raise NotImplementedError("settings.enable_adaptive_time_stepping = False: the CUDA step IS the adaptive time step "
+                                      "(adaptive_time_stepping.py:34-381)")
         self.nx, self.ny = int(st.nx), int(st.ny)
         self.C = self.nx * self.ny
         self.lateral = bool(getattr(st, "enable_lateral_flow", False))
@@ -138,7 +152,7 @@ class CudaStepDriver:
     def _hand_forcing_day(self):
         vs = self.state.variables
         blocks = [np.asarray(getattr(vs, n))[2:-2, 2:-2, :].reshape(self.C, abi.SLOTS_PER_DAY) for n in ("prec_day", "ta_day", "pet_day")]
-        uniform_today = all((b == b[0]).all() | (np.isnan(b).all()) for b in blocks)
+        uniform_today = all(np.array_equal(b, np.broadcast_to(b[0], b.shape), equal_nan=True) for b in blocks)
         if self.engine is None:
             uniform = uniform_today if self._uniform is None else bool(self._uniform)
             self._create_engine(uniform)

@@ -140,6 +140,8 @@ class AsyncDiagnosticOutput:
         if self.acc:
             engine.set_diagnostics(self.acc)
         self._buffers = [_pinned(len(names) * self.C) for _ in range(max(1, int(depth)))]
+        if hasattr(engine, "reserve_snapshots"):
+            engine.reserve_snapshots(len(names))  # the device side of every hand-over exists before the first step
         self._free = queue.Queue()
         for b in self._buffers:
             self._free.put(b)

@@ -32,3 +32,41 @@ def make_flag_reducer(dist, device=None):
         return [int(v) for v in (out << np.arange(32, dtype=np.uint32)[None, :]).sum(axis=1)]
 
     return reduce
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pins this process to the host cores of the NUMA node its GPU hangs off, BEFORE it allocates page-locked buffers: pinned
+    memory is then first-touched on that node, so the eight ranks of a box do not push their output slabs through one socket's
+    memory controllers (round 1: end-to-end scaled 3.96x from 1 to 8 GPUs, the device-timed kernels 7.97x).  Returns a short
+    description for the bench record; never raises (a missing sysfs entry just leaves the affinity as it is)."""
+    import os
+
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        addr = "%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open(f"/sys/bus/pci/devices/{addr}/numa_node").read().strip())
+        if node < 0:
+            return f"gpu {addr}: no NUMA node reported"
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = os.sched_getaffinity(0)
+        use = sorted(allowed & set(cpus))
+        if not use:
+            return f"gpu {addr}: node {node} has no allowed cpu"
+        os.sched_setaffinity(0, use)
+        return f"gpu {addr}: node {node}, {len(use)} cpus"
+    except Exception as e:  # pragma: no cover - depends on the box
+        return f"not bound ({type(e).__name__}: {e})"
+
+
+def _parse_cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.extend(range(int(lo), int(hi or lo) + 1))
+    return out

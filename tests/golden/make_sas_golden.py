@@ -41,6 +41,11 @@ CASES = {
     # age statistics (percentile ages by numpy.interp) and the water / solute balance errors
     "sas_power_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=105, age_statistics=True,
                             sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
+    # BASELINE-sized age axes: NumPy's pairwise summation recurses for n > 128 (sums over the age axis), np.interp walks long CDFs
+    "sas_power_300": dict(shape=(2, 2), ndays=8, ages=300, doy=105, age_statistics=True,
+                          sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
+    "sas_power_1500": dict(shape=(1, 2), ndays=4, ages=1500, doy=100,
+                           sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     # conservative anion (bromide): solute mass per age bin, partition coefficients, a crop cell whose uptake stops when wet
     "sas_bromide": dict(shape=(2, 3), ndays=26, ages=50, doy=100, solute="bromide", age_statistics=True,
                         sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),

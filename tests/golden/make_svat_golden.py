@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 import ref_harness as rh  # noqa: E402
 from roger_b200 import synth  # noqa: E402
+from tests import util as tutil  # noqa: E402
 
 
 def field_names():
@@ -50,6 +51,13 @@ CASES = {
                             masked=0.1),
     "oned_rain": dict(event="rain", ndays=10, shape=(3, 2), hetero=False, dist=False, lateral=True, doy=1, every=1),
     "oned_mixed": dict(event="mixed", ndays=30, shape=(3, 4), hetero=True, dist=False, lateral=True, doy=100, every=5),
+    # 256 heterogeneous cells (a full tile of the CUDA layout, 8 warps with divergent cells), per-cell forcing, partly sealed
+    # surfaces, masked cells; winter start: snow accumulation, rain on snow, melt.  Full planes are kept for a handful of
+    # steps only; EVERY step is pinned through per-field digests of the bit patterns (`step_digest`, tests/util.py).
+    "svat_hetero256": dict(event="mixed", ndays=30, shape=(16, 16), hetero=True, dist=True, lateral=False, doy=10, every=10 ** 9,
+                           masked=0.05, sealed=0.3, lu=(5, 6, 7, 8, 9, 10, 11, 12, 13), full_records=(1, 2, 100, 200), digest=True),
+    "oned_hetero256": dict(event="mixed", ndays=25, shape=(16, 16), hetero=True, dist=True, lateral=True, doy=95, every=10 ** 9,
+                           masked=0.05, sealed=0.3, full_records=(1, 2, 100, 200), digest=True),
 }
 
 
@@ -68,6 +76,9 @@ def build_case(name):
                                                               masked_fraction=c.get("masked", 0.0), **kw)
     else:
         params, th_rz, th_ss = synth.benchmark_parameters((nx, ny), lateral=c["lateral"])
+    if c.get("sealed"):  # sealing > 0 (infiltration.py:1563-1666 theta_d, :1767 z_sc, :1420 q_hof): a share of the cells
+        rng = np.random.default_rng(46)
+        params["sealing"] = np.where(rng.uniform(size=(nx, ny)) < c["sealed"], np.round(rng.uniform(0.05, 0.6, (nx, ny)), 2), 0.0)
     case = dict(nx=nx, ny=ny, ndays=c["ndays"], params=params, theta_rz0=th_rz, theta_ss0=th_ss, lateral=c["lateral"], **forc)
     if c["dist"]:
         case.update(synth.distributed_weights((nx, ny), seed=44))
@@ -116,6 +127,7 @@ def run(name):
 
     rec_steps, rec_fields, rec_scal = [], [], []
     all_scal = []
+    digests = []
     step = 0
     runlen = state.settings.runlen
     import roger.core.numerics as numerics
@@ -126,10 +138,14 @@ def run(name):
         step += 1
         s = scalars()
         all_scal.append([s[k] for k in sorted(s)])
-        if step <= 30 or step % c["every"] == 0:
+        keep = (step <= 30 or step % c["every"] == 0) if "full_records" not in c else step in c["full_records"]
+        if keep or c.get("digest"):
             fld, _ = record()
-            rec_steps.append(step)
-            rec_fields.append(fld)
+            if c.get("digest"):
+                digests.append(np.array([tutil.field_digest(row) for row in fld], dtype=np.uint64))
+            if keep:
+                rec_steps.append(step)
+                rec_fields.append(fld)
     fld, _ = record()
     if rec_steps[-1] != step:
         rec_steps.append(step)
@@ -148,15 +164,19 @@ def run(name):
         PREC=case["PREC"], TA=case["TA"], PET=case["PET"], YEAR=case["YEAR"], MONTH=case["MONTH"], DOY=case["DOY"],
         theta_rz0=case["theta_rz0"], theta_ss0=case["theta_ss0"],
     )
+    if digests:
+        out["step_digest"] = np.stack(digests)  # (steps, fields) uint64
+        out["digest_valid"] = ~np.isnan(init_fields).all(axis=1)
     for k, v in case["params"].items():
         out["param_" + k] = np.asarray(v)
     for k in ("prec_weight", "ta_offset", "pet_weight"):
         if k in case:
             out[k] = case[k]
     # every derived per-cell variable after setup (for the host-side parameter derivation tests)
+    fnames = set(n for _, n in fields)
     for k, v in init_snap.items():
         a = np.asarray(v)
-        if a.ndim >= 2 and a.dtype != object:
+        if a.ndim >= 2 and a.dtype != object and (not c.get("digest") or k in fnames or k in ("S_dep_tot", "ground_cover", "lai", "z_root_crop")):
             out["setup_" + k] = a
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
