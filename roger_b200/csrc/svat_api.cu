@@ -108,7 +108,7 @@ struct Planes {
     __host__ __device__ double* at(int id, int64_t i) const {  // plane `id` of cell i
         const size_t t = (size_t)(i >> kTileShift), l = (size_t)(i & kTileMask);
         return kind_is_F(id) ? fl + ((t * kNumF + (size_t)(id - kNumPS)) << kTileShift) + l
-                             : ps + ((t * kNumPS + (size_t)id) << kTileShift) + l;
+                             : ps + ((t * kNumPS + (size_t)ps_slot(id)) << kTileShift) + l;
     }
 };
 
@@ -192,7 +192,9 @@ __global__ void k_aggregate_a(Planes pl, double* __restrict__ prec_m1, const dou
 constexpr unsigned kPrefetchChunk = 32 * kTile * sizeof(double);  // 64 KB per instruction
 constexpr unsigned kPrefetchChunks = (unsigned)((kTileBytesPS + kPrefetchChunk - 1) / kPrefetchChunk);
 template <bool LAT>
-__host__ __device__ constexpr unsigned kPrefetchEnd() { return (unsigned)kTileBytesPS; }
+__host__ __device__ constexpr unsigned kPrefetchEnd() {  // the head of the tile: the planes a state-only step reads
+    return (unsigned)((LAT ? kHotOned : kHotSvat) * kTile * sizeof(double));
+}
 static_assert(ROGER_BLOCK == kTile, "one k_svat_step block per tile");
 template <bool LAT, bool FLUX>
 __global__ void __launch_bounds__(ROGER_BLOCK, ROGER_MIN_BLOCKS)
@@ -205,7 +207,7 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
     // The block's tile is one contiguous region: ask the memory system for all of it (or for the tile of the block that
     // will follow on this SM) with a handful of bulk L2 prefetches, instead of discovering the ~100 planes one dependent
     // load group after the other.  No registers, no shared memory, no completion to wait for.
-    if (threadIdx.x < kPrefetchChunks) {
+    if (threadIdx.x * kPrefetchChunk < kPrefetchEnd<LAT>()) {
         const int64_t tile = (int64_t)blockIdx.x + ROGER_BULK_PREFETCH_DIST;
         if (tile * kTile < C) {
             const char* src = reinterpret_cast<const char*>(pl.ps) + (size_t)tile * kTileBytesPS + (size_t)threadIdx.x * kPrefetchChunk;

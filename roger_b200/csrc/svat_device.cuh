@@ -77,6 +77,10 @@ RD double dv(double a, double b) {
     return a / b;
 }
 
+constexpr double kDblMax = 1.7976931348623157e308;
+RD bool pos_finite(double x) { return (x > 0) && (x <= kDblMax); }
+RD bool nonneg_finite(double x) { return (x >= 0) && (x <= kDblMax); }
+
 RD double powr(double x, double y) {  // x ** y (numpy power on float64)
 #if ROGER_FAST_MATH
     return exp(y * log(x));
@@ -132,13 +136,61 @@ constexpr int kTile = 1 << kTileShift;  // cells per tile == threads of a k_svat
 constexpr int kTileMask = kTile - 1;
 constexpr size_t kTileBytesPS = (size_t)kNumPSPlanes * kTile * sizeof(double);
 constexpr size_t kTileBytesF = (size_t)kNumFPlanes * kTile * sizeof(double);
+
+// Physical order of the parameter / state planes inside a tile (the public field ids of include/roger_b200_fields.h are
+// untouched).  Planes the state-only step READS come first, in the order the processes first need them, so that ONE bulk
+// L2 prefetch of the head of the tile fetches exactly what the block is going to load -- and in that order; then the
+// oneD-only parameters (read by the lateral-flow kernels only), then the planes a step reads only under rare conditions,
+// and last the planes the step only writes or never touches (derived parameters that are recomputed in registers).
+#define ROGER_SVAT_PS_ORDER(X) \
+    X(maskCatch) X(prec) X(ta) X(pet) \
+    X(theta_ac) X(theta_ufc) X(theta_pwp) X(z_root) X(z_soil) \
+    X(throughfall_coeff_top) X(throughfall_coeff_ground) X(S_int_top_tot) X(S_int_ground_tot) X(lu_id) \
+    X(swe_top) X(S_int_top) X(S_int_ground) X(S_snow) X(z0) X(prec_event_csum) X(swe_top_tot) X(swe_ground) \
+    X(S_dep) X(de) X(rew) X(tew) X(basal_evap_coeff) X(S_fp_rz) X(swe) X(theta_rz) X(basal_transp_coeff) X(S_lp_rz) X(z_evap) \
+    X(sealing) X(no_wf) X(z_wf) X(z_wf_t0) X(z_wf_t1) X(z_wf_fc) X(inf_mat_event_csum) X(inf_mat_pot_event_csum) \
+    X(inf_mp_event_csum) X(y_mp) X(inf_sc_event_csum) X(y_sc) X(theta_d) X(theta_d_rel) X(theta_d_t0) X(theta_d_rel_t0) \
+    X(theta_d_fp) X(t_event_csum) X(z_sc) \
+    X(ks) X(wfs) X(t_sat) X(lmpv) X(dmpv) X(mp_drain_area) X(inf_mat_rz) X(S_lp_ss) X(S_fp_ss) X(maskRiverLake) \
+    X(z_sat) X(k_rz) X(h_rz) X(h_ss) X(n_salv) X(ha) X(z_gw) X(kf) X(ks_ss) \
+    X(lambda_bc) X(m_bc) X(S) \
+    /* ---- end of the planes every state-only SVAT step reads (kHotSvat) ---- */ \
+    X(dmph) X(slope) X(v_mp_layer_1) X(v_mp_layer_2) X(v_mp_layer_3) X(v_mp_layer_4) \
+    X(v_mp_layer_5) X(v_mp_layer_6) X(v_mp_layer_7) X(v_mp_layer_8) \
+    /* ---- end of the planes every state-only oneD step reads (kHotOned) ---- */ \
+    X(theta_4) X(theta_27) X(z_sc_max) X(k_stress_transp) X(k_ss) X(S_rz) X(S_ss) X(S_s) X(theta) \
+    X(k_stress_evap) X(theta_ss) X(k) X(h) X(S_sur) \
+    X(theta_sat) X(theta_fc) X(S_ac_rz) X(S_ufc_rz) X(S_pwp_rz) X(S_ac_ss) X(S_ufc_ss) X(S_pwp_ss) X(S_pwp_s)
+#define ROGER_SLOT_ENUM(name) SLOT_##name,
+enum roger_svat_slot { ROGER_SVAT_PS_ORDER(ROGER_SLOT_ENUM) SLOT_COUNT };
+#undef ROGER_SLOT_ENUM
+static_assert(SLOT_COUNT == kNumPSPlanes, "ROGER_SVAT_PS_ORDER must list every P and S field exactly once");
+constexpr int kHotSvat = SLOT_S + 1;            // planes [0, kHotSvat) are read by every SVAT step
+constexpr int kHotOned = SLOT_v_mp_layer_8 + 1;  // planes [0, kHotOned) by every oneD step
+// field id -> slot; folds to a constant wherever the id is one (every access of the step kernels)
+__host__ __device__ constexpr int ps_slot(int id) {
+    switch (id) {
+#define ROGER_SLOT_CASE(name) case RF_##name: return SLOT_##name;
+        ROGER_SVAT_PS_ORDER(ROGER_SLOT_CASE)
+#undef ROGER_SLOT_CASE
+        default: return -1;
+    }
+}
+constexpr bool ps_order_is_permutation() {
+    for (int id = 0; id < kNumPSPlanes; id++) {
+        if (ps_slot(id) < 0) return false;
+        for (int other = 0; other < id; other++) if (ps_slot(other) == ps_slot(id)) return false;
+    }
+    return true;
+}
+static_assert(ps_order_is_permutation(), "ROGER_SVAT_PS_ORDER: a field is missing or listed twice");
 struct Io {
     char* __restrict__ ps;  // this thread's cell in plane 0 of its tile (parameter + state planes)
     char* __restrict__ fl;  // likewise in the flux planes (FLUX kernels only)
     RD Io(double* ps_, double* fl_, int64_t i)
         : ps(reinterpret_cast<char*>(ps_) + (size_t)(i >> kTileShift) * kTileBytesPS + (size_t)(i & kTileMask) * sizeof(double)),
           fl(fl_ ? reinterpret_cast<char*>(fl_) + (size_t)(i >> kTileShift) * kTileBytesF + (size_t)(i & kTileMask) * sizeof(double) : nullptr) {}
-    RD double* at(int id) const { return reinterpret_cast<double*>(ps + (size_t)id * (kTile * sizeof(double))); }
+    RD double* at(int id) const { return reinterpret_cast<double*>(ps + (size_t)ps_slot(id) * (kTile * sizeof(double))); }
     RD double ldp(int id) const { return __ldg(at(id)); }
     RD double lds(int id) const { return *at(id); }
     RD void sts(int id, double v) const { *at(id) = v; }
@@ -677,7 +729,21 @@ RD void macropores(Cell& c, const StepPlan& p, const Io& io) {
     const double rtd2 = r_mp * (c.theta_d * c.theta_d);
     const double dmtd = c.dmpv * c.theta_d;
     const double tfac = c.theta_d / (ksw * r_mp);
-    for (int i = 0; i < substeps; i++) {
+    // Exact shortcut for a cell without ponded water (z0_di == 0), the state of every cell on a dry step.  With
+    // theta_d, a, dmpv * theta_d positive and finite and ym1, nonsat, csum non-negative and finite, every quantity of a
+    // pass is non-NaN up to pot_di >= 0 (or NaN only through inf * 0 with nonsat == 0, which the nonsat select turns into
+    // 0), so inf_mp_di = min(pot_di, z0_di) = 0 in EVERY pass: csum never changes, inf_mp stays 0 and the front the loop
+    // leaves behind is r_mp + sqrt(csum / (dmpv theta_d) / pi) whatever the number of passes -- provided that value is
+    // finite (an infinite ym1 would turn the next pass's y*y - ym1*ym1 into NaN).  The general loop below needs two passes
+    // with two powers each to find that out; anything outside these conditions takes it.
+    bool quiet = false;
+    if (MASK1 && (z0_di == 0.0) && pos_finite(c.theta_d) && pos_finite(a) && pos_finite(dmtd) && nonneg_finite(ym1) &&
+        nonneg_finite(nonsat) && nonneg_finite(csum)) {
+        double yq = r_mp + sqrt(dv(dv(csum, dmtd), pi));
+        yq = (yq < r_mp) ? r_mp : yq;
+        if (yq <= kDblMax) { y = yq; quiet = true; }
+    }
+    for (int i = 0; i < substeps && !quiet; i++) {
         const double ym1_in = ym1, t_in = t, csum_in = csum;
         t += dts;
         double cc = M(ksw * t);
@@ -785,7 +851,22 @@ RD void shrinkage_cracks(Cell& c, const StepPlan& p, const Io& io) {
     const double dts = M(dt / substeps);
     const double ksw = c.ks * c.wfs;
     const double geo = nonsat * c.theta_d * l_sc;
-    for (int i = 0; i < substeps; i++) {
+    // Exact shortcut without ponded water (z0_di == 0), as for the macropores: while every quantity of a pass stays finite
+    // the pass computes a finite pot_di, clips it to >= 0 and takes min(pot_di, 0) = 0, so csum never changes and the front
+    // left behind is csum / l_sc / 2 whatever the number of passes.  Finiteness is guaranteed by keeping the operands of
+    // the pass inside [1e-30, 1e30] in magnitude (y = sqrt(2 ks wfs t / theta_d), t = ym1^2 theta_d / (2 ks wfs) with
+    // ym1 = y_sc[taum1] or csum / l_sc / 2, and t <= 24 h: nothing leaves the double range); physical values are far inside.
+    bool quiet = false;
+    {
+        auto mid = [](double v) { return (v >= 1e-30) && (v <= 1e30); };
+        auto small = [](double v) { return fabs(v) <= 1e30; };
+        if (MASK1 && (z0_di == 0.0) && mid(c.theta_d) && mid(ksw) && mid(fabs(l_sc)) && small(ym1) && small(nonsat) && small(csum) &&
+            small(geo)) {
+            y = dv(csum, l_sc) / 2;
+            quiet = true;
+        }
+    }
+    for (int i = 0; i < substeps && !quiet; i++) {
         const double ym1_in = ym1, t_in = t, csum_in = csum;
         t += dts;
         y = M(sqrt((ksw * t * 2) / c.theta_d));
