@@ -88,14 +88,25 @@ int roger_svat_download_wait(roger_svat *h);
 int roger_svat_reserve_snapshots(roger_svat *h, int n);
 /* Device layout of the planes, for zero-copy use from other kernels: tile-major, [tile][plane][cell] with `tile_cells`
  * consecutive cells per tile; plane `f` (a P or S field id) of cell i is the double at
- *   ps_base + (((i / tile_cells) * n_ps_planes + f) * tile_cells + i % tile_cells) * 8,
- * flux field f likewise with flux_base, n_flux_planes and f - n_ps_planes (flux_base is 0 until a flux plane was asked for). */
+ *   ps_base + (((i / tile_cells) * n_ps_planes + roger_svat_field_slot(f)) * tile_cells + i % tile_cells) * 8,
+ * flux field f likewise with flux_base, n_flux_planes and f - n_ps_planes (flux_base is 0 until a flux plane was asked for).
+ * i is the DEVICE position of a cell: after roger_svat_optimize_cell_order it is no longer the caller's cell index. */
 typedef struct roger_svat_layout {
     uint64_t ps_base, flux_base;
     int64_t n_tiles;
     int32_t tile_cells, n_ps_planes, n_flux_planes, reserved;
 } roger_svat_layout;
 int roger_svat_tile_layout(roger_svat *h, roger_svat_layout *out);
+
+/* physical slot of a P / S field inside a tile (see roger_svat_layout); -1 for flux fields */
+int roger_svat_field_slot(int field);
+/* Re-orders the cells on the device by infiltration capacity (sort key ks * (1 - sealing), cells outside the catchment last)
+ * so that the threads of a warp hold similar cells: the macropore / shrinkage-crack sub-step loops of
+ * roger/core/infiltration.py:430-1318 run only for ponded cells, and with spatially uncorrelated parameters every warp
+ * would pay for a few of them.  Columns are independent (no lateral routing on this path), so the results are identical;
+ * every entry point keeps speaking the caller's cell numbering.  Call after the parameters are uploaded and before the
+ * first forcing day is handed over.  (The reference has no counterpart: its arrays are (x, y) grids.) */
+int roger_svat_optimize_cell_order(roger_svat *h);
 
 int roger_svat_set_scalars(roger_svat *h, const roger_svat_scalars *s);
 int roger_svat_get_scalars(roger_svat *h, roger_svat_scalars *s);

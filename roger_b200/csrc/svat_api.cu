@@ -8,6 +8,7 @@
 // allocated lazily, only when a caller asks for diagnostics.  Per-cell forcing day blocks arrive in the reference's
 // (cell, slot) order and are re-tiled to [tile][slot][cell] on upload, so the 144-slot aggregations read coalesced.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -267,18 +268,66 @@ __global__ void k_soil_kh_refresh(Planes pl) {
     soil_kh_refresh(io);
 }
 
-// ---- host-order <-> tile-order movers.  The C ABI speaks plain planes of C doubles (cell index fastest).
-__global__ void k_scatter_plane(Planes pl, int field, const double* __restrict__ src) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < pl.C) *pl.at(field, i) = src[i];
+// ---- host-order <-> tile-order movers.  The C ABI speaks plain planes of C doubles (cell index fastest, the caller's
+// cell numbering); on the device cell position d holds the caller's cell order[d] (identity while `order` is null, see
+// roger_svat_optimize_cell_order).
+__global__ void k_scatter_plane(Planes pl, int field, const double* __restrict__ src, const int* __restrict__ order) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < pl.C) *pl.at(field, d) = src[order ? order[d] : d];
 }
-__global__ void k_gather_plane(Planes pl, int field, double* __restrict__ dst) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < pl.C) dst[i] = *pl.at(field, i);
+__global__ void k_gather_plane(Planes pl, int field, double* __restrict__ dst, const int* __restrict__ order) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < pl.C) dst[order ? order[d] : d] = *pl.at(field, d);
+}
+__global__ void k_gather_linear(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ order, int64_t C) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < C) dst[order ? order[d] : d] = src[d];
 }
 __global__ void k_copy_plane(Planes pl, int dst_field, int src_field) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < pl.C) *pl.at(dst_field, i) = *pl.at(src_field, i);
+}
+// sort key of the cell order: the matrix infiltration capacity scale ks * (1 - sealing) decides, together with the rain
+// intensity, whether a cell ponds -- i.e. whether its macropore / shrinkage-crack sub-step loops run or take the
+// no-ponding shortcut (svat_device.cuh); masked cells (a different code path altogether) sort to the end
+__global__ void k_order_keys(Planes pl, double* __restrict__ keys, int* __restrict__ ids) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pl.C) return;
+    const double m = *pl.at(RF_maskCatch, i);
+    double k = *pl.at(RF_ks, i) * (1.0 - *pl.at(RF_sealing, i));
+    if (!(k == k)) k = 0.0;
+    keys[i] = (m == 1.0) ? k : 1e300;
+    ids[i] = (int)i;
+}
+__global__ void k_compose_order(const int* __restrict__ old_order, const int* __restrict__ sorted_pos, int* __restrict__ out, int64_t C) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < C) out[d] = old_order ? old_order[sorted_pos[d]] : sorted_pos[d];
+}
+__global__ void k_invert_order(const int* __restrict__ order, int* __restrict__ inv, int64_t C) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < C) inv[order[d]] = (int)d;
+}
+// per-cell forcing under a cell order: rows [row0, row0 + n) of the caller's block (staged at `src`) go to the device
+// positions inv[row]; one warp per row, lanes along the slots (the writes are scattered by construction)
+__global__ void __launch_bounds__(256) k_forcing_scatter_rows(const double* __restrict__ src, int64_t row0, int64_t n, double* __restrict__ dst,
+                                                               const int* __restrict__ inv) {
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t d = inv[row0 + r];
+    double* out = dst + (size_t)(d >> kTileShift) * (144 * kTile) + (size_t)(d & kTileMask);
+    const double* row = src + (size_t)r * 144;
+    for (int k = lane; k < 144; k += 32) out[(size_t)k * kTile] = row[k];
+}
+__global__ void k_forcing_pad(double* __restrict__ dst, int64_t C, int64_t Cpad) {  // padding cells of the last tile repeat position C - 1
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t npad = Cpad - C;
+    if (j >= npad * 144) return;
+    const int64_t d = C + j / 144;
+    const int k = (int)(j % 144);
+    const int64_t s = C - 1;
+    dst[(size_t)(d >> kTileShift) * (144 * kTile) + (size_t)k * kTile + (size_t)(d & kTileMask)] =
+        dst[(size_t)(s >> kTileShift) * (144 * kTile) + (size_t)k * kTile + (size_t)(s & kTileMask)];
 }
 // A chunk of a per-cell forcing day block, (cell, slot) order -> [tile][slot][cell].  One block per 32 cells: rows are read
 // with the lanes along the slots (contiguous 256 B per request), turned in shared memory and written with the lanes along
@@ -400,6 +449,8 @@ struct roger_svat {
     double* d_forc[3] = {nullptr, nullptr, nullptr};  // prec_day, ta_day, pet_day re-tiled to [tile][slot][cell] (per-cell forcing)
     const double* forc[3] = {nullptr, nullptr, nullptr};
     double* d_stage = nullptr;        // one host-order plane (upload / download) == kForcingChunk cells of a forcing day block
+    int* d_order = nullptr;           // device position -> caller's cell index (null: identity), roger_svat_optimize_cell_order
+    int* d_inv = nullptr;             // caller's cell index -> device position
     int64_t n_tiles = 0, Cpad = 0;
     double h_forc[3][144];  // uniform forcing (host copy for the scheduler)
     unsigned* d_flags = nullptr;  // [0] snow/sanity flags, [1] day flags, [2] event flags
@@ -526,6 +577,7 @@ void roger_svat_destroy(roger_svat* h) {
     cudaFree(h->d_fl);
     cudaFree(h->d_prec_m1);
     cudaFree(h->d_stage);
+    cudaFree(h->d_order); cudaFree(h->d_inv);
     for (auto p : h->d_forc) cudaFree(p);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (auto p : h->snap_free) cudaFree(p);
@@ -550,7 +602,7 @@ int roger_svat_upload(roger_svat* h, int field, const double* host) {
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
     CU(cudaMemcpyAsync(h->d_stage, host, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
-    k_scatter_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, h->d_stage);
+    k_scatter_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, h->d_stage, h->d_order);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     if (field == RF_swe || field == RF_swe_top) h->snow_flags_valid = false;
@@ -564,7 +616,7 @@ int roger_svat_download(roger_svat* h, int field, double* host) {
     CU(cudaSetDevice(h->device));
     if (kind_is_F(field)) { int r = ensure_flux_planes(h); if (r) return r; }
     if (is_soil_kh(field)) { int r = refresh_soil_kh(h); if (r) return r; }
-    k_gather_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, h->d_stage);
+    k_gather_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, h->d_stage, h->d_order);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(host, h->d_stage, sizeof(double) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -602,7 +654,7 @@ int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
     const size_t plane = sizeof(double) * (size_t)h->C;
     double* snap = nullptr;
     { int r = take_snapshot_plane(h, &snap); if (r) return r; }
-    k_gather_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, snap);
+    k_gather_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), field, snap, h->d_order);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_snap, h->stream));
     CU(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
@@ -629,7 +681,8 @@ int roger_svat_download_diagnostics_async(roger_svat* h, double* host_pinned, in
         double* snap = nullptr;
         { int r = take_snapshot_plane(h, &snap); if (r) return r; }
         snaps[k] = snap;
-        CU(cudaMemcpyAsync(snap, h->d_rates + k * (size_t)h->C, plane, cudaMemcpyDeviceToDevice, h->stream));
+        k_gather_linear<<<h->grid256(), 256, 0, h->stream>>>(h->d_rates + k * (size_t)h->C, snap, h->d_order, h->C);
+        CU(cudaGetLastError());
     }
     if (reset) CU(cudaMemsetAsync(h->d_rates, 0, plane * n, h->stream));
     CU(cudaEventRecord(h->ev_snap, h->stream));
@@ -664,6 +717,8 @@ int roger_svat_download_wait(roger_svat* h) {
     h->snap_busy.clear();
     return 0;
 }
+
+int roger_svat_field_slot(int field) { return (field >= 0 && field < kNumPS) ? ps_slot(field) : -1; }
 
 int roger_svat_tile_layout(roger_svat* h, roger_svat_layout* out) {
     if (!h || !out) return fail(ROGER_EINVAL, "roger_svat_tile_layout: bad argument");
@@ -727,25 +782,35 @@ static int after_forcing(roger_svat* h) {
 static int retile_forcing(roger_svat* h, int v, const double* src, bool src_on_host) {
     if (!h->d_forc[v]) CU(cudaMalloc(&h->d_forc[v], sizeof(double) * 144 * (size_t)h->Cpad));
     const int64_t chunk = std::max<int64_t>(32, (h->C / 144) & ~int64_t(31));  // cells per staging pass (the plane holds C doubles)
+    auto place = [&](const double* dev_rows, int64_t row0, int64_t n, bool last) -> int {  // rows [row0, row0 + n) -> tiles
+        if (h->d_order) {
+            k_forcing_scatter_rows<<<(int)((n + 7) / 8), 256, 0, h->stream>>>(dev_rows, row0, n, h->d_forc[v], h->d_inv);
+            CU(cudaGetLastError());
+            if (last && h->Cpad > h->C) {
+                k_forcing_pad<<<(int)(((h->Cpad - h->C) * 144 + 255) / 256), 256, 0, h->stream>>>(h->d_forc[v], h->C, h->Cpad);
+                CU(cudaGetLastError());
+            }
+        } else {
+            const int64_t upto = last ? h->Cpad : row0 + n;  // the last pass also fills the padding cells of the last tile
+            k_forcing_to_tiles<<<(int)((upto - row0 + 31) / 32), 256, 0, h->stream>>>(dev_rows, row0, h->d_forc[v], row0, h->C);
+            CU(cudaGetLastError());
+        }
+        return 0;
+    };
     if (!src_on_host) {
-        k_forcing_to_tiles<<<(int)(h->Cpad / 32), 256, 0, h->stream>>>(src, 0, h->d_forc[v], 0, h->C);
-        CU(cudaGetLastError());
+        { int r = place(src, 0, h->C, true); if (r) return r; }
     } else if (h->C < 32 * 144) {  // tiny grids: the staging plane is smaller than one 32-cell group of rows
         double* tmp = nullptr;
         CU(cudaMalloc(&tmp, sizeof(double) * 144 * (size_t)h->C));
         CU(cudaMemcpyAsync(tmp, src, sizeof(double) * 144 * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
-        k_forcing_to_tiles<<<(int)(h->Cpad / 32), 256, 0, h->stream>>>(tmp, 0, h->d_forc[v], 0, h->C);
-        CU(cudaGetLastError());
+        { int r = place(tmp, 0, h->C, true); if (r) { cudaFree(tmp); return r; } }
         CU(cudaStreamSynchronize(h->stream));
         CU(cudaFree(tmp));
     } else {
         for (int64_t c0 = 0; c0 < h->C; c0 += chunk) {
             const int64_t n = std::min(chunk, h->C - c0);
-            const bool last = c0 + n >= h->C;
             CU(cudaMemcpyAsync(h->d_stage, src + (size_t)c0 * 144, sizeof(double) * 144 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-            const int64_t upto = last ? h->Cpad : c0 + n;  // the last pass also fills the padding cells of the last tile
-            k_forcing_to_tiles<<<(int)((upto - c0 + 31) / 32), 256, 0, h->stream>>>(h->d_stage, c0, h->d_forc[v], c0, h->C);
-            CU(cudaGetLastError());
+            { int r = place(h->d_stage, c0, n, c0 + n >= h->C); if (r) return r; }
         }
     }
     h->forc[v] = h->d_forc[v];
@@ -1179,8 +1244,17 @@ int roger_svat_download_diagnostics(roger_svat* h, double* host, int reset) {
     if (!h || !host) return fail(ROGER_EINVAL, "roger_svat_download_diagnostics: bad argument");
     if (h->rate_fields.empty()) return fail(ROGER_EINVAL, "roger_svat_download_diagnostics: no diagnostics set");
     CU(cudaSetDevice(h->device));
-    const size_t bytes = sizeof(double) * h->rate_fields.size() * (size_t)h->C;
-    CU(cudaMemcpyAsync(host, h->d_rates, bytes, cudaMemcpyDeviceToHost, h->stream));
+    const size_t plane = sizeof(double) * (size_t)h->C;
+    const size_t bytes = plane * h->rate_fields.size();
+    if (!h->d_order) {
+        CU(cudaMemcpyAsync(host, h->d_rates, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        for (size_t k = 0; k < h->rate_fields.size(); k++) {  // back to the caller's cell numbering, one plane at a time
+            k_gather_linear<<<h->grid256(), 256, 0, h->stream>>>(h->d_rates + k * (size_t)h->C, h->d_stage, h->d_order, h->C);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(host + k * (size_t)h->C, h->d_stage, plane, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
     if (reset) CU(cudaMemsetAsync(h->d_rates, 0, bytes, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (h->diag_count > 0)
@@ -1217,6 +1291,56 @@ int roger_svat_set_flag_reducer(roger_svat* h, roger_flag_reduce_fn fn, void* us
     if (!h) return fail(ROGER_EINVAL, "roger_svat_set_flag_reducer: null handle");
     h->reduce_fn = fn;
     h->reduce_user = user;
+    return 0;
+}
+
+// Re-orders the cells ON THE DEVICE so that neighbouring threads hold cells of similar infiltration capacity
+// (sort key ks * (1 - sealing), masked cells last).  Columns are independent, so any order computes the same numbers; what
+// changes is which cells share a warp: the macropore / shrinkage-crack sub-step loops run only for ponded cells, and with
+// spatially uncorrelated parameters nearly every warp holds a few of them and pays for all (measured on a rain step at
+// 4096^2 heterogeneous cells: 15 of 32 lanes active in the macropore loop).  Every entry point keeps speaking the caller's
+// cell numbering: uploads, downloads, forcing blocks and diagnostics are permuted on the way.  Call it after the
+// parameters are uploaded and before stepping; calling it again re-sorts from the current planes.
+int roger_svat_optimize_cell_order(roger_svat* h) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_optimize_cell_order: null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->copy_stream));  // no read-back in flight while the planes move
+    const int64_t C = h->C;
+    const Planes pl = h->planes();
+    double *keys = nullptr, *keys_out = nullptr;
+    int *ids = nullptr, *pos = nullptr, *new_order = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    CU(cudaMalloc(&keys, sizeof(double) * C)); CU(cudaMalloc(&keys_out, sizeof(double) * C));
+    CU(cudaMalloc(&ids, sizeof(int) * C)); CU(cudaMalloc(&pos, sizeof(int) * C)); CU(cudaMalloc(&new_order, sizeof(int) * C));
+    k_order_keys<<<h->grid256(), 256, 0, h->stream>>>(pl, keys, ids);
+    CU(cudaGetLastError());
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, ids, pos, (int)C, 0, 64, h->stream));
+    CU(cudaMalloc(&tmp, tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, ids, pos, (int)C, 0, 64, h->stream));  // stable
+    // pos[d] = current device position that moves to position d; in the caller's numbering: old_order[pos[d]]
+    k_compose_order<<<h->grid256(), 256, 0, h->stream>>>(h->d_order, pos, new_order, C);
+    CU(cudaGetLastError());
+    // move every plane: gather with the old order into the host-order staging plane, scatter with the new one
+    const int n_fields = h->d_fl ? RF_COUNT : kNumPS;
+    for (int f = 0; f < n_fields; f++) {
+        k_gather_plane<<<h->grid256(), 256, 0, h->stream>>>(pl, f, h->d_stage, h->d_order);
+        k_scatter_plane<<<h->grid256(), 256, 0, h->stream>>>(pl, f, h->d_stage, new_order);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));  // (d_prec_m1 is scratch of a single step: nothing to move)
+    if (!h->rate_fields.empty()) {  // accumulators are positional: restart them
+        CU(cudaMemsetAsync(h->d_rates, 0, sizeof(double) * h->rate_fields.size() * (size_t)C, h->stream));
+        h->diag_count = 0;
+    }
+    cudaFree(h->d_order);
+    h->d_order = new_order;
+    if (!h->d_inv) CU(cudaMalloc(&h->d_inv, sizeof(int) * C));
+    k_invert_order<<<h->grid256(), 256, 0, h->stream>>>(h->d_order, h->d_inv, C);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(keys); cudaFree(keys_out); cudaFree(ids); cudaFree(pos); cudaFree(tmp);
+    h->have_forcing = h->st.forcing_uniform ? h->have_forcing : false;  // a per-cell day block is positional: hand it over again
     return 0;
 }
 

@@ -49,6 +49,8 @@ def load_library():
     lib.roger_svat_download_wait.argtypes = [hp]
     lib.roger_svat_reserve_snapshots.argtypes = [hp, C.c_int]
     lib.roger_svat_tile_layout.argtypes = [hp, C.POINTER(abi.SvatLayout)]
+    lib.roger_svat_field_slot.argtypes = [C.c_int]
+    lib.roger_svat_optimize_cell_order.argtypes = [hp]
     lib.roger_svat_set_scalars.argtypes = [hp, C.POINTER(abi.SvatScalars)]
     lib.roger_svat_get_scalars.argtypes = [hp, C.POINTER(abi.SvatScalars)]
     lib.roger_svat_set_forcing_day.argtypes = [hp, dp, dp, dp]
@@ -161,6 +163,11 @@ class CudaSvatEngine:
     def reserve_snapshots(self, n):
         """device snapshot planes for n asynchronous plane hand-overs per output time, allocated now (never inside the stepping loop)"""
         _check(self.lib, self.lib.roger_svat_reserve_snapshots(self.h, int(n)))
+
+    def optimize_cell_order(self):
+        """sort the cells on the device by infiltration capacity (warp coherence of the ponding-dependent loops); results and
+        the cell numbering of every call are unchanged"""
+        _check(self.lib, self.lib.roger_svat_optimize_cell_order(self.h))
 
     def tile_layout(self):
         lay = abi.SvatLayout()

@@ -20,6 +20,8 @@ host-side changes of parameter arrays (e.g. the monthly land-use refresh in `set
 are detected by array identity -- the reference's `update()` returns new arrays -- and re-uploaded before the step.
 State arrays modified by user code between steps must be announced with `driver.push(name)`.
 """
+import os
+
 import numpy as np
 
 from . import abi
@@ -119,6 +121,8 @@ class CudaStepDriver:
                     self._param_ids[name] = id(getattr(vs, name))
             else:
                 self.engine.upload(name, zeros)
+        if hasattr(self.engine, "optimize_cell_order") and os.environ.get("ROGER_B200_CELL_ORDER", "1") != "0":
+            self.engine.optimize_cell_order()  # device-side only: every call keeps the setup's cell numbering
 
     def push(self, name):
         """Announce that user code changed `vs.<name>` on the host; it is uploaded before the next step."""

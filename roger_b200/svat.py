@@ -7,6 +7,8 @@ product; the tests can plug the CPU oracle in through the same interface).  Ever
 orchestration: once-per-run parameter derivation, once-per-day forcing hand-over, once-per-month
 land-use parameter refresh.
 """
+import os
+
 import numpy as np
 
 from . import abi, params
@@ -16,7 +18,7 @@ DAY = 24 * 60 * 60
 
 class SvatModel:
     def __init__(self, engine_cls, shape, forcing, primary, theta_rz0, theta_ss0, lateral=False, weights=None,
-                 settings=None, engine_kwargs=None):
+                 settings=None, engine_kwargs=None, cell_order=None):
         self.shape = tuple(shape)
         self.C = int(np.prod(self.shape))
         self.lateral = bool(lateral)
@@ -27,6 +29,8 @@ class SvatModel:
         self.weights = None if weights is None else {k: np.asarray(v, dtype=np.float64).reshape(-1) for k, v in weights.items()}
         self.settings = abi.default_settings(lateral=self.lateral, forcing_uniform=self.weights is None, **(settings or {}))
         self.engine = engine_cls(self.C, self.settings, **(engine_kwargs or {}))
+        # device-side cell ordering by infiltration capacity (engine.optimize_cell_order); ROGER_B200_CELL_ORDER=0 switches it off
+        self.cell_order = (os.environ.get("ROGER_B200_CELL_ORDER", "1") != "0") if cell_order is None else bool(cell_order)
         self.itt_forc = 0
         self.month = [1, 1]  # vs.month initial (roger/variables.py:318-326)
         self.n_steps = 0
@@ -52,6 +56,8 @@ class SvatModel:
             planes.update(override_planes)
         for n in abi.FIELD_NAMES:
             self.engine.upload(n, planes[n])
+        if self.cell_order and hasattr(self.engine, "optimize_cell_order"):
+            self.engine.optimize_cell_order()
         self.engine.set_scalars(abi.initial_scalars())
         self._setup_done = True
 

@@ -354,3 +354,43 @@ def test_driver_output_files_on_the_cuda_engine(tmp_path):
             assert fa.variables["Time"].shape[0] >= 2 and np.array_equal(fa.variables["Time"][:], fb.variables["Time"][:])
             for v in vars_:
                 assert util.same_bits(fa.variables[v][:], fb.variables[v][:]), (name, v)
+
+
+@pytest.mark.parametrize("lateral,dist", [(True, False), (False, True)])
+def test_device_cell_order_changes_nothing_but_the_placement(lateral, dist):
+    """roger_svat_optimize_cell_order sorts the cells on the device by infiltration capacity; uploads, downloads, per-cell
+    forcing blocks, asynchronous plane hand-overs and the diagnostics accumulators keep the caller's cell numbering, and every
+    plane stays identical in every bit to a run in the caller's own order (columns are independent)."""
+    import torch
+    from roger_b200 import abi, synth
+    from roger_b200.svat import SvatModel
+
+    shape = (37, 19)  # 703 cells: a ragged last tile
+    forcing = synth.mixed_forcing(20, seed=42, start_doy=100)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=47, lateral=lateral, masked_fraction=0.05)
+    weights = synth.distributed_weights(shape, seed=48) if dist else None
+    models = [SvatModel(_engine(), shape, forcing, prim, th_rz, th_ss, lateral=lateral, weights=weights, cell_order=flag) for flag in (True, False)]
+    for m in models:
+        m.setup()
+        m.engine.set_diagnostics([("q_ss", "rate"), ("theta_rz", "average"), ("S", "maximum")])
+    # the order really is a non-trivial permutation: device position 0 holds the cell with the smallest ks * (1 - sealing)
+    pins = [torch.empty(models[0].C, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    for step in range(60):
+        a, b = models[0].step(True), models[1].step(True)
+        assert (a.time, a.dt_secs, a.itt_day, a.sanity_ok) == (b.time, b.dt_secs, b.itt_day, b.sanity_ok)
+        if step % 20 == 19:
+            for n in abi.FIELD_NAMES:
+                assert util.same_bits(models[0].get(n), models[1].get(n)), (step, n)
+            for m, pin in zip(models, pins):
+                m.engine.download_async("S_fp_rz", pin)
+                m.engine.download_wait()
+            assert util.same_bits(pins[0], pins[1])
+            ra, rb = models[0].engine.download_rates(reset=True), models[1].engine.download_rates(reset=True)
+            for k in ra:
+                assert util.same_bits(ra[k], rb[k]), (step, k)
+    # a second call re-sorts from the current planes (composition of orders) and an upload after it lands in the right cells
+    models[0].engine.optimize_cell_order()
+    v = np.arange(models[0].C, dtype=np.float64)
+    models[0].engine.upload("z_gw", v)
+    assert util.same_bits(models[0].get("z_gw"), v)
+    assert util.same_bits(models[0].get("S_lp_ss"), models[1].get("S_lp_ss"))
