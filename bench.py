@@ -29,10 +29,35 @@ from roger_b200.svat import SvatModel  # noqa: E402
 
 # algorithmic bytes per cell-timestep (2*state + parameters + forcing)
 ALGO_BYTES = {"svat": 984.0, "oned": 1200.0}
-# DRAM bytes per cell and launch of the dominant kernel from the committed `ncu --set full` captures (profiles/r1_ncu_summary.md:
-# dram__bytes_read.sum + dram__bytes_write.sum divided by the cells of the captured launch); None where no capture exists
-NCU_DRAM_BYTES_PER_CELL = {"oned": 1122.0, "svat": None}  # r1f capture: 4.707 GB per launch at 2048^2
-NCU_DRAM_BYTES_PER_BIN_DAY = 1327.0  # k_sas_day, per cell and age bin
+
+
+def ncu_traffic():
+    """DRAM bytes of the dominant kernels as `ncu --set full` measured them (dram__bytes_read.sum + dram__bytes_write.sum of the
+    captured launch divided by its cells / cells x bins): read from profiles/ncu_traffic.json, which tools/ncu_traffic.py writes
+    from the committed captures; absent entries give traffic = null"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}
+
+
+def numpy_reference_record(workload, ages=None):
+    """the unmodified reference's NumPy backend timed in the build container (tools/time_numpy_reference.py; the reference is
+    pure Python and does not travel to the GPU box)"""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "numpy_reference_timing.json")))
+    except Exception:
+        return None
+    key = "SAS" if workload == "sas" else ("oneD" if workload == "oned" else "SVAT_benchmark")
+    runs = [r for r in rec["runs"] if key in r["workload"]]
+    if ages is not None and any(r.get("ages") == ages for r in runs):
+        runs = [r for r in runs if r.get("ages") == ages]
+    if not runs:
+        return None
+    best = max(runs, key=lambda r: r["cell_timesteps_per_s"])
+    return {"value": best["cell_timesteps_per_s"], "unit": "cell-timesteps/s", "cores": rec["cores_used"], "kind": "reference (NumPy backend)",
+            "sample": best["workload"] + f", {best['cells']} cells, {best['steps_timed']} steps", "where": rec["where"], "host": rec["host"],
+            "source": "profiles/numpy_reference_timing.json"}
 
 
 def use_all_host_cores():
@@ -156,9 +181,11 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"svat_oxygen18 offline SAS transport {args.sas_side}x{args.sas_side} cells per GPU, {args.ages} age bins, "
-                                   "power-law SAS (SVATOXYGEN18_benchmark.py), 6 sub-steps"},
+                                   "power-law SAS (SVATOXYGEN18_benchmark.py), 6 sub-steps",
+                       "sample": f"timed on a {cells}-cell sample of that workload, {cores} host threads"},
             "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port",
-                             "sample": f"{cells} cells x {args.ages} age bins of the same workload, {args.steps} daily steps, OpenMP over cells"},
+                             "sample": f"{cells} cells x {args.ages} age bins of the same workload, {args.steps} daily steps, OpenMP over cells",
+                             "numpy_reference": numpy_reference_record("sas", args.ages)},
             "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         })
         return
@@ -177,9 +204,11 @@ def run_reference(args):
         "impl": "reference", "metric": "cell-timesteps/s", "value": v, "unit": "cell-timesteps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload} {args.side}x{args.side} cells per GPU (oneD_benchmark.py), uniform synthetic forcing from 1 May"},
+        "config": {"workload": f"{args.workload} {args.side}x{args.side} cells per GPU (oneD_benchmark.py), uniform synthetic forcing from 1 May",
+                   "sample": f"timed on a {side}x{side}-cell sample of that workload (same parameter and forcing generators), {cores} host threads"},
         "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port",
-                         "sample": f"{side}x{side} cells of the same workload, {args.steps} adaptive steps, OpenMP over cells"},
+                         "sample": f"{side}x{side} cells of the same workload, {args.steps} adaptive steps, OpenMP over cells",
+                         "numpy_reference": numpy_reference_record(args.workload)},
         "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -223,13 +252,10 @@ def run_cuda(args):
     side = args.side
     shape = (side, side)
     C = side * side
-    reducer = None
-    if world > 1:
-        from roger_b200.parallel import make_flag_reducer
-
-        reducer = make_flag_reducer(dist, torch.device("cuda", local))
-    m = build_model(CudaSvatEngine, shape, args.workload, seed=43 + rank, engine_kwargs={"device": local, "flag_reducer": reducer})
+    m = build_model(CudaSvatEngine, shape, args.workload, seed=43 + rank, engine_kwargs={"device": local})
     eng = m.engine
+    if world > 1:  # the one data-path exchange: ncclAllGather of the scheduler's flag words on the engine's stream
+        eng.enable_nccl_flags(dist, torch.device("cuda", local))
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,8 +286,18 @@ def run_cuda(args):
     sampler = ClockSampler(local)
     sampler.start()
     advance(args.warmup)
+    # Placement of the timed window (untimed steps): it starts at noon of the first day that is stepped hourly -- the day the
+    # first rain event of the synthetic series arrives -- so that it holds rain steps as well as dry ones and exactly one
+    # midnight (one daily output in `e2e`) per 24 steps, followed by steps that overlap the output's copy as in a long run.
+    for _ in range(96):
+        sc_now = eng.get_scalars()
+        if sc_now.time % 86400 == 12 * 3600 and sc_now.dt_secs == 3600:
+            break
+        m.run_steps(1)
+    window_start_day = eng.get_scalars().time // 86400
     ms_by_dt.clear()
     n_by_dt.clear()
+    m.checkpoint()  # `e2e` below repeats exactly this simulated window (same state, same forcing days, same step mix)
     barrier()
     sampler.mark()
     eng.kernel_ms = 0.0
@@ -288,14 +324,8 @@ def run_cuda(args):
     # host memory and a D2H of the daily output slab (theta_rz, S) as the reference's diagnostics would write.
     pin = [torch.empty(C, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
     eng.reserve_snapshots(2)  # what a driver does when it configures its output: nothing is allocated inside the stepping loop
-    # Steady-state placement of the window: a daily slab leaves the device asynchronously while the NEXT day's steps run, so a
-    # window that happens to end a few steps after a midnight would time the tail of a copy a long run never waits for.  The
-    # (untimed) steps below move the window's start to noon; the window still holds one midnight per simulated day.
-    for _ in range(48):
-        if eng.get_scalars().time % 86400 == 12 * 3600:
-            break
-        m.run_steps(1)
-    e2e_start = "noon"
+    m.rollback()
+    e2e_start = "the window `value` was timed on (device-resident checkpoint, rolled back): noon of simulated day %d" % window_start_day
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
@@ -321,16 +351,23 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * C * args.steps / float(t[0])
 
+    eng.close()
+    del m
+    torch.cuda.empty_cache()
+    extras = {}
+    if not args.no_sweep:
+        extras["sweep"], extras["strong"] = run_sweep(args, local, world, rank, dist if world > 1 else None, value, step_time / args.steps)
+    if not args.no_scenarios:
+        extras["scenarios"] = {"snow_month_per_cell_forcing": run_scenario_snow_percell(args, local, world, rank, dist if world > 1 else None)}
+
     sas_res = None
     if not args.no_sas:
         # second half of the BASELINE metric: SVAT + offline oxygen-18 SAS transport (configs[2]) on the same GPU(s)
-        eng.close()
-        del m
-        torch.cuda.empty_cache()
         sas_res = run_sas_cuda(args, local, world, rank, dist if world > 1 else None, min(args.steps, args.sas_steps), 3, args.sas_side, args.ages)
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic = ncu_traffic().get(args.workload)
         algo = ALGO_BYTES[args.workload]
         ach = algo * C * args.steps / kern_time / 1e9
         line = {
@@ -339,12 +376,13 @@ def run_cuda(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"{args.workload} {side}x{side} cells per GPU (oneD_benchmark.py), uniform synthetic forcing from 1 May",
-                "cells_per_gpu": C, "step_mix_dt_secs": kinds, "l2": "state planes are %.1f GB per GPU, far larger than the 126 MB L2" % (C * 8 * 120 / 1e9),
+                "cells_per_gpu": C, "step_mix_dt_secs": kinds, "window": "starts at noon of simulated day %d (first rain event of the series)" % window_start_day,
+                "l2": "state planes are %.1f GB per GPU, far larger than the 126 MB L2" % (C * 8 * 120 / 1e9),
                 "parallelism": f"cell-block x{world}",
             },
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": (NCU_DRAM_BYTES_PER_CELL[args.workload] * C if NCU_DRAM_BYTES_PER_CELL[args.workload] else None),
-                         "traffic_source": "profiles/r1_ncu_summary.md (bytes per cell of the captured launch x cells per launch)",
+                         "traffic": (traffic["dram_bytes_per_cell"] * C if traffic else None),
+                         "traffic_source": (traffic or {}).get("source"),
                          "peak_source": peak_src, "algorithmic_bytes_per_cell_timestep": algo,
                          "kernel_ms_per_step": 1e3 * kern_time / args.steps,
                          "kernel_ms_per_step_by_dt_secs": {k: v / n_by_dt[k] for k, v in ms_by_dt.items() if n_by_dt.get(k)}},
@@ -353,6 +391,7 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        line.update(extras)
         if sas_res is not None:
             line["sas"] = sas_res
         line["e2e"]["host_numa_binding"] = numa
@@ -364,6 +403,150 @@ def run_cuda(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _max_over_ranks(values, dist):
+    import torch
+
+    t = torch.tensor(values, dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def tiled_model(engine_cls, n_cells, workload, seed, engine_kwargs, tile=65536, start_doy=START_DOY, weights=False):
+    """a grid of n_cells whose parameters repeat a heterogeneous tile of `tile` cells (BASELINE configs[4]: grids of 2^16 ..
+    2^28 cells; drawing 2^28 independent parameter sets on the host would take longer than the measurement)"""
+    lateral = workload == "oned"
+    t = min(tile, n_cells)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters((t, 1), seed=seed, lateral=lateral)
+    reps = -(-n_cells // t)
+    rep = lambda a: np.tile(np.asarray(a).reshape(-1), reps)[:n_cells]  # noqa: E731
+    prim = {k: rep(v) for k, v in prim.items()}
+    w = None
+    if weights:
+        w = {k: rep(v) for k, v in synth.distributed_weights((t, 1), seed=seed + 1).items()}
+    forcing = synth.mixed_forcing(60, seed=42, start_doy=start_doy)
+    m = SvatModel(engine_cls, (n_cells, 1), forcing, prim, rep(th_rz), rep(th_ss), lateral=lateral, weights=w, engine_kwargs=engine_kwargs)
+    m.setup()
+    return m
+
+
+def run_sweep(args, local, world, rank, dist, main_value, main_s_per_step):
+    """BASELINE configs[4]: the same step on grids of 2^16 .. 2^24 cells per GPU (weak: every rank holds that many) and, on
+    several GPUs, 2^24 cells IN TOTAL cut into contiguous blocks (strong).  2^26 and 2^27 cells per GPU with --sweep-large."""
+    import torch
+    from roger_b200.engine import CudaSvatEngine
+
+    main_cells = args.side * args.side
+    sizes = [1 << 16, 1 << 18, 1 << 20, 1 << 22] + ([1 << 26, 1 << 27] if args.sweep_large else [])
+    strong_cells = (1 << 24) // world
+    out = []
+
+    def measure(n_cells):
+        m = tiled_model(CudaSvatEngine, n_cells, args.workload, seed=43 + rank, engine_kwargs={"device": local})
+        if dist is not None:
+            m.engine.enable_nccl_flags(dist, torch.device("cuda", local))
+        steps = min(args.steps, 24)
+        left = args.warmup
+        while left > 0:
+            left -= m.run_steps(left)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        m.engine.kernel_ms = 0.0
+        t0 = time.perf_counter()
+        left = steps
+        while left > 0:
+            left -= m.run_steps(left)
+        m.engine.synchronize()
+        wall, kern = _max_over_ranks([time.perf_counter() - t0, m.engine.kernel_ms / 1e3], dist)
+        m.engine.close()
+        del m
+        torch.cuda.empty_cache()
+        return {"cells_per_gpu": n_cells, "cells_total": n_cells * world, "value": world * n_cells * steps / wall, "ms_per_step": 1e3 * wall / steps,
+                "kernel_ms_per_step": 1e3 * kern / steps, "steps": steps}
+
+    for n in sizes:
+        out.append(measure(n))
+    out.append({"cells_per_gpu": main_cells, "cells_total": main_cells * world, "value": main_value, "ms_per_step": 1e3 * main_s_per_step,
+                "steps": args.steps, "note": "the headline measurement"})
+    out.sort(key=lambda r: r["cells_per_gpu"])
+    if world == 1:
+        strong = {"cells_total": main_cells, "cells_per_gpu": main_cells, "value": main_value, "ms_per_step": 1e3 * main_s_per_step,
+                  "note": "one GPU: the strong-scaling reference point is the headline measurement"}
+    else:
+        r = measure(strong_cells)
+        strong = dict(r, cells_total=strong_cells * world, note=f"2^24 cells in total, {strong_cells} per GPU (fixed total work)")
+    return out, strong
+
+
+def run_scenario_snow_percell(args, local, world, rank, dist):
+    """A winter month with snow on the ground and per-cell forcing (Eberbaechle pattern: series x per-cell weights): no step
+    can be scheduled ahead -- every adaptive step needs the grid-wide flags of its own forcing aggregates (k_aggregate_a) and
+    of the snow state -- so every step pays two flag exchanges across the ranks.  The day blocks are built on the device
+    (inputs resident in HBM, as for `value`); only stepping is timed."""
+    import torch
+    from roger_b200.engine import CudaSvatEngine
+
+    side = args.scenario_side
+    n_cells = side * side
+    dev = torch.device("cuda", local)
+    m = tiled_model(CudaSvatEngine, n_cells, args.workload, seed=143 + rank, engine_kwargs={"device": local}, start_doy=15, weights=True)
+    eng = m.engine
+    if dist is not None:
+        eng.enable_nccl_flags(dist, dev)
+    w = {k: torch.from_numpy(v).to(dev) for k, v in m.weights.items()}
+    series = {k: torch.from_numpy(np.asarray(m.forcing[k], dtype=np.float64)).to(dev) for k in ("PREC", "TA", "PET")}
+    keep = []
+
+    def set_forcing(sc):  # SvatModel._set_forcing with the day blocks assembled on the device
+        if sc.time % 86400 != 0:
+            return
+        sc.itt_day = 0
+        i0 = m.itt_forc
+        m.month[1] = int(m.forcing["MONTH"][i0])
+        sc.month = m.month[1]
+        sl = slice(i0, i0 + 144)
+        blocks = [(series["PREC"][sl][None, :] * w["prec_weight"][:, None]).contiguous(),
+                  (series["TA"][sl][None, :] + w["ta_offset"][:, None]).contiguous(),
+                  (series["PET"][sl][None, :] * w["pet_weight"][:, None]).contiguous()]
+        torch.cuda.synchronize()
+        keep[:] = blocks
+        eng.set_forcing_day_device(*[b.data_ptr() for b in blocks])
+        m.itt_forc += 144
+
+    m._set_forcing = set_forcing
+    steps, warm = min(args.steps, 24), max(args.warmup, 3)
+    kinds = {}
+    for _ in range(warm):
+        m.run_steps(1)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    eng.kernel_ms, eng.launches = 0.0, 0
+    wall = 0.0
+    for _ in range(steps):
+        sc = eng.get_scalars()
+        m._set_forcing(sc)  # untimed: the day block is an input
+        eng.set_scalars(sc)
+        m._set_parameters(sc)
+        t0 = time.perf_counter()
+        eng.step(False)
+        wall += time.perf_counter() - t0
+        m.month[0] = m.month[1]
+        for d in eng.last_step_dts():
+            kinds[d] = kinds.get(d, 0) + 1
+    snow = float((eng.download("swe") > 0).mean())
+    wall, kern = _max_over_ranks([wall, eng.kernel_ms / 1e3], dist)
+    launches = eng.launches
+    eng.close()
+    del m
+    torch.cuda.empty_cache()
+    return {"value": world * n_cells * steps / wall, "unit": "cell-timesteps/s", "ms_per_step": 1e3 * wall / steps, "kernel_ms_per_step": 1e3 * kern / steps,
+            "steps": steps, "cells_per_gpu": n_cells, "step_mix_dt_secs": kinds, "fraction_of_cells_with_snow_at_end": snow,
+            "gpu_launches": int(launches), "flag_exchanges_per_step": 2 if world > 1 else 0,
+            "config": f"{args.workload} {side}x{side} cells per GPU, forcing from 15 January x per-cell weights, day blocks assembled on the device"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -479,6 +662,7 @@ def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages, samp
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall, kern, e2e_wall = (float(v) for v in t)
     peak, peak_src = measured_peak()
+    sas_traffic = ncu_traffic().get("sas")
     algo = sas_algo_bytes(ages)
     ach = algo * C * steps / kern / 1e9
     finite = float(np.isfinite(out[sas.OUTPUTS.index("C_rz")]).mean())
@@ -491,8 +675,9 @@ def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages, samp
                    "cells_per_gpu": C, "ages": ages,
                    "l2": "age-ranked state is %.1f GB per GPU, far larger than the 126 MB L2" % (C * ages * 8 * 4 / 1e9)},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": NCU_DRAM_BYTES_PER_BIN_DAY * ages * C, "traffic_frac_of_peak": NCU_DRAM_BYTES_PER_BIN_DAY * ages * C * steps / kern / 1e9 / peak,
-                     "traffic_source": "profiles/r1_ncu_summary.md (bytes per cell and age bin of the captured launch x cells x bins)",
+                     "traffic": (sas_traffic["dram_bytes_per_bin_day"] * ages * C if sas_traffic else None),
+                     "traffic_frac_of_peak": (sas_traffic["dram_bytes_per_bin_day"] * ages * C * steps / kern / 1e9 / peak if sas_traffic else None),
+                     "traffic_source": (sas_traffic or {}).get("source"),
                      "peak_source": peak_src, "algorithmic_bytes_per_cell_timestep": algo, "kernel_ms_per_step": 1e3 * kern / steps,
                      "note": "exact-order solver streams its two scratch arrays once per sub-step: measured DRAM traffic is ~20x the "
                              "algorithmic bytes (profiles/), see DESIGN.md"},
@@ -516,7 +701,8 @@ def sas_cpu_baseline(ages, cells=8192, days=4):
         eng.step(model.day_forcing())
     el = time.perf_counter() - t0
     return {"value": cells * days / el, "unit": "cell-timesteps/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": f"{cells} cells x {ages} age bins of the same workload, {days} daily steps, OpenMP over cells"}
+            "sample": f"{cells} cells x {ages} age bins of the same workload, {days} daily steps, OpenMP over cells",
+            "numpy_reference": numpy_reference_record("sas", ages)}
 
 
 def cpu_baseline(args):
@@ -533,7 +719,8 @@ def cpu_baseline(args):
         m.step(False)
     el = time.perf_counter() - t0
     return {"value": side * side * n / el, "unit": "cell-timesteps/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": f"{side}x{side} cells of the same workload, {n} adaptive steps, OpenMP over cells"}
+            "sample": f"{side}x{side} cells of the same workload, {n} adaptive steps, OpenMP over cells",
+            "numpy_reference": numpy_reference_record(args.workload)}
 
 
 def _claim_stdout():
@@ -570,6 +757,10 @@ def main():
     ap.add_argument("--side", type=int, default=4096)
     ap.add_argument("--ref-side", type=int, default=768, help="grid side of the CPU sample of the SVAT / oneD workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the grid-size sweep (2^16 .. 2^22 cells per GPU) and the strong-scaling point")
+    ap.add_argument("--sweep-large", action="store_true", help="add 2^26 and 2^27 cells per GPU to the sweep")
+    ap.add_argument("--no-scenarios", action="store_true", help="skip the snow-month / per-cell-forcing scenario")
+    ap.add_argument("--scenario-side", type=int, default=2048)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -128,6 +128,13 @@ int roger_svat_set_forcing_day_device(roger_svat *h, uint64_t prec_day, uint64_t
  *      Every rank calls it the same number of times per step. */
 typedef void (*roger_flag_reduce_fn)(uint32_t *flags, int n, void *user);
 int roger_svat_set_flag_reducer(roger_svat *h, roger_flag_reduce_fn fn, void *user);
+/* The same exchange without leaving the device queue: one ncclAllGather of the flag words on the handle's compute stream
+ * (NCCL over NVLink), OR-ed on the host behind the read-back every step performs anyway -- no host callback, no extra
+ * synchronisation.  Rank 0 obtains an id with roger_nccl_unique_id (128 bytes) and distributes it by any means; every rank
+ * then calls roger_svat_enable_nccl_flags with it.  NCCL is bound at run time (the libnccl.so.2 the process already carries);
+ * -ROGER_ENODEV if none is loadable.  Takes precedence over a flag reducer callback. */
+int roger_nccl_unique_id(uint8_t *id128);
+int roger_svat_enable_nccl_flags(roger_svat *h, const uint8_t *id128, int rank, int world);
 
 /* ---- the hot path: ONE adaptive time step = adaptive_time_stepping + interception + ET + snow +
  *      infiltration + percolation (+ lateral) + capillary rise + storages + numerical error +
@@ -172,7 +179,15 @@ int roger_svat_fence_wait(roger_svat *h, int token);
 int roger_svat_set_rate_fields(roger_svat *h, const int *fields, int n);
 int roger_svat_download_rates(roger_svat *h, double *host, int reset);
 uint64_t roger_svat_rates_ptr(roger_svat *h);
+/* In-memory checkpoint / rollback of the whole run state (planes, scheduler scalars and flags, the uniform forcing day); the
+ * device-resident counterpart of the reference's restart file (roger/restart.py:32-174).  A per-cell forcing day block has to
+ * be handed over again after a rollback. */
+int roger_svat_checkpoint(roger_svat *h);
+int roger_svat_rollback(roger_svat *h);
 int roger_svat_synchronize(roger_svat *h);
+/* self-test hook (no device needed): hourly window sum / nanmean of a 144-slot forcing row (adaptive_time_stepping.py:410-437)
+ * by the six-load form the kernels use and by the 144-slot form; out4 = {sum, sum_full, nanmean, nanmean_full} */
+int roger_selftest_window_sums(const double *row144, int itt_day, double *out4);
 /* CUDA-event time (ms) spent in kernels of the most recent roger_svat_step / run_day call and the
  * number of kernel launches it made (bench.py roofline / gpu_launches). */
 int roger_svat_last_timing(roger_svat *h, double *kernel_ms, int64_t *launches);

@@ -9,6 +9,7 @@
 // (cell, slot) order and are re-tiled to [tile][slot][cell] on upload, so the 144-slot aggregations read coalesced.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -85,12 +86,50 @@ struct RowAgg {  // aggregates of one forcing row for the three time-step classe
         double tot = pairwise144([&](int k) { double v = row[k]; return (v == v) ? v : 0.0; });
         return tot / (double)cnt;
     }
+    // Sum of the six slots itt_day .. itt_day + 5 as numpy's pairwise reduction of the 144-slot row with every other slot
+    // zero computes it (adaptive_time_stepping.py:410-437: the hourly aggregates are sums over a masked copy of the whole
+    // day).  The reduction keeps 8 running lanes per half of 72 slots, slot k feeding lane k mod 8 of half k / 72; six
+    // consecutive slots hit six different lanes, and a lane that sees the value v among zeros ends as v + 0.0 (exact for every
+    // v; -0.0 becomes +0.0 exactly as in the full sum).  So six loads and the two lane trees give the same bits as walking all
+    // 144 slots.  NAN0: nanmean's zero-filled copy; *cnt receives the number of non-NaN slots.
+    template <bool NAN0, class R>
+    __host__ __device__ static double window6(R row, int itt_day, int* cnt) {
+        double r0[8], r1[8];
+        int n_ok = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = itt_day + ((j - itt_day) & 7);  // the one slot of lane j inside an 8-slot span starting at itt_day
+            double v = 0.0;
+            const bool in = (k < itt_day + 6) && (k < 144);
+            if (in) {
+                v = row[k];
+                if (NAN0) { const bool ok = (v == v); n_ok += ok ? 1 : 0; v = ok ? v : 0.0; }
+                v = v + 0.0;
+            }
+            const bool upper = k >= 72;
+            r0[j] = upper ? 0.0 : v;
+            r1[j] = upper ? v : 0.0;
+        }
+        const double h0 = ((r0[0] + r0[1]) + (r0[2] + r0[3])) + ((r0[4] + r0[5]) + (r0[6] + r0[7]));
+        const double h1 = ((r1[0] + r1[1]) + (r1[2] + r1[3])) + ((r1[4] + r1[5]) + (r1[6] + r1[7]));
+        if (cnt) *cnt = n_ok;
+        return 0.0 + (h0 + h1);
+    }
     template <class R>
-    __host__ __device__ static double win_sum(R row, int itt_day) {
+    __host__ __device__ static double win_sum(R row, int itt_day) { return window6<false>(row, itt_day, nullptr); }
+    template <class R>
+    __host__ __device__ static double win_nanmean(R row, int itt_day) {
+        int cnt = 0;
+        const double tot = window6<true>(row, itt_day, &cnt);
+        return tot / (double)cnt;
+    }
+    // the straightforward forms (all 144 slots), kept for the self-test below
+    template <class R>
+    __host__ __device__ static double win_sum_full(R row, int itt_day) {
         return pairwise144([&](int k) { return (k >= itt_day && k < itt_day + 6) ? row[k] : 0.0; });
     }
     template <class R>
-    __host__ __device__ static double win_nanmean(R row, int itt_day) {
+    __host__ __device__ static double win_nanmean_full(R row, int itt_day) {
         int cnt = 0;
         for (int k = itt_day; k < itt_day + 6 && k < 144; k++) cnt += (row[k] == row[k]) ? 1 : 0;
         double tot = pairwise144([&](int k) {
@@ -491,10 +530,24 @@ struct roger_svat {
     int64_t last_launches = 0;
     roger_flag_reduce_fn reduce_fn = nullptr;
     void* reduce_user = nullptr;
-    unsigned reduce(unsigned v) const {
-        if (reduce_fn) { uint32_t w = v; reduce_fn(&w, 1, reduce_user); return w; }
-        return v;
-    }
+    // flag exchange across ranks on the compute stream (roger_svat_enable_nccl_flags)
+    void* nccl_comm = nullptr;
+    int nccl_world = 1;
+    unsigned* d_gather = nullptr;   // world x kMaxFlagWords
+    unsigned* h_gather = nullptr;   // pinned, same size
+    static constexpr int kMaxFlagWords = 144;
+    // in-memory checkpoint (roger_svat_checkpoint / roger_svat_rollback)
+    double* d_ckpt_ps = nullptr;
+    double* d_ckpt_fl = nullptr;
+    struct Saved {
+        roger_svat_scalars sc;
+        unsigned snow_flags, day_flags;
+        bool snow_flags_valid, ks_ss_synced, soil_kh_stale, have_forcing, u_cur_valid;
+        double u_cur_prec, u_cur_ta;
+        double h_forc[3][144];
+        int64_t diag_count;
+    } saved{};
+    bool have_ckpt = false;
     Planes planes() const { return Planes{d_ps, d_fl, C}; }
     int grid256() const { return (int)((C + 255) / 256); }
 };
@@ -504,6 +557,70 @@ static int ensure_flux_planes(roger_svat* h) {
     CU(cudaSetDevice(h->device));
     CU(cudaMalloc(&h->d_fl, kTileBytesF * (size_t)h->n_tiles));
     CU(cudaMemsetAsync(h->d_fl, 0, kTileBytesF * (size_t)h->n_tiles, h->stream));
+    return 0;
+}
+
+// ---- NCCL, bound at run time.  The library links against the CUDA runtime only; the all-gather of the scheduler's flag
+// words uses the NCCL the process already carries (torch's bundled libnccl.so.2, else the system one), looked up with dlopen.
+namespace {
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+    static constexpr int kUint32 = 3;  // ncclUint32 (nccl.h: ncclInt8 0, ncclUint8 1, ncclInt32 2, ncclUint32 3)
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy the process already uses (torch), if any
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { api.why = std::string("libnccl.so.2 not loadable: ") + dlerror(); return api; }
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    api.AllGather = (decltype(api.AllGather))dlsym(lib, "ncclAllGather");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+    if (!api.ok) api.why = "libnccl.so.2 lacks an expected symbol";
+    return api;
+}
+}  // namespace
+#define NCCL(call)                                                                                          \
+    do {                                                                                                    \
+        int r__ = (call);                                                                                   \
+        if (r__ != 0)                                                                                       \
+            return fail(ROGER_ECUDA, std::string(#call) + ": " + (nccl_api().GetErrorString ? nccl_api().GetErrorString(r__) : "NCCL error")); \
+    } while (0)
+
+// n flag words of this rank (device address, final on the compute stream) -> the bitwise OR over all ranks, on the host.
+// With NCCL enabled the exchange is one ncclAllGather of n words on the compute stream followed by the same read-back a
+// single rank does: no host callback, no second synchronisation.  `done` (optional) is recorded behind the transfers.
+static int fetch_flags(roger_svat* h, const unsigned* d_words, int n, uint32_t* out, cudaEvent_t done = nullptr) {
+    if (n > roger_svat::kMaxFlagWords) return fail(ROGER_EINVAL, "fetch_flags: too many words");
+    if (h->nccl_comm) {
+        NCCL(nccl_api().AllGather(d_words, h->d_gather, (size_t)n, NcclApi::kUint32, h->nccl_comm, h->stream));
+        CU(cudaMemcpyAsync(h->h_gather, h->d_gather, sizeof(unsigned) * n * h->nccl_world, cudaMemcpyDeviceToHost, h->stream));
+        if (done) CU(cudaEventRecord(done, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < n; k++) {
+            uint32_t w = 0;
+            for (int r = 0; r < h->nccl_world; r++) w |= h->h_gather[(size_t)r * n + k];
+            out[k] = w;
+        }
+        return 0;
+    }
+    CU(cudaMemcpyAsync(h->h_gather, d_words, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (done) CU(cudaEventRecord(done, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < n; k++) out[k] = h->h_gather[k];
+    if (h->reduce_fn) h->reduce_fn(out, n, h->reduce_user);
     return 0;
 }
 
@@ -559,6 +676,8 @@ int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settin
     CU(cudaMalloc(&h->d_flags, 4 * sizeof(unsigned)));
     CU(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(unsigned), h->stream));
     CU(cudaHostAlloc(&h->h_flags, 4 * sizeof(unsigned), cudaHostAllocDefault));
+    CU(cudaMalloc(&h->d_gather, sizeof(unsigned) * roger_svat::kMaxFlagWords));
+    CU(cudaHostAlloc(&h->h_gather, sizeof(unsigned) * roger_svat::kMaxFlagWords, cudaHostAllocDefault));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     // everything the asynchronous read-back needs exists from the start: no allocation, stream or event creation ever
@@ -578,6 +697,7 @@ void roger_svat_destroy(roger_svat* h) {
     cudaFree(h->d_prec_m1);
     cudaFree(h->d_stage);
     cudaFree(h->d_order); cudaFree(h->d_inv);
+    cudaFree(h->d_ckpt_ps); cudaFree(h->d_ckpt_fl);
     for (auto p : h->d_forc) cudaFree(p);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (auto p : h->snap_free) cudaFree(p);
@@ -590,6 +710,9 @@ void roger_svat_destroy(roger_svat* h) {
     if (h->h_block_flags) cudaFreeHost(h->h_block_flags);
     cudaFree(h->d_flags);
     cudaFreeHost(h->h_flags);
+    if (h->nccl_comm) nccl_api().CommDestroy(h->nccl_comm);
+    cudaFree(h->d_gather);
+    if (h->h_gather) cudaFreeHost(h->h_gather);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -768,11 +891,17 @@ static int after_forcing(roger_svat* h) {
         int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
         k_day_flags<<<blocks, 256, 0, h->stream>>>(h->forc[0], h->forc[1], n, h->st.ta_fm, h->st.hpi, h->d_flags + 1);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(h->h_flags + 1, h->d_flags + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        h->day_flags = h->h_flags[1];
+        uint32_t w = 0;
+        { int r = fetch_flags(h, h->d_flags + 1, 1, &w); if (r) return r; }
+        h->day_flags = w;
     }
-    h->day_flags = h->reduce(h->day_flags);
+    if (h->st.forcing_uniform && (h->nccl_comm || h->reduce_fn)) {  // every rank may hold its own "uniform" series
+        h->h_flags[1] = h->day_flags;
+        CU(cudaMemcpyAsync(h->d_flags + 1, h->h_flags + 1, sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
+        uint32_t w = 0;
+        { int r = fetch_flags(h, h->d_flags + 1, 1, &w); if (r) return r; }
+        h->day_flags = w;
+    }
     h->have_forcing = true;
     return 0;
 }
@@ -969,9 +1098,9 @@ static int ensure_snow_flags(roger_svat* h, int64_t* launches) {
     k_snow_flags<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(h->planes(), h->d_flags);
     CU(cudaGetLastError());
     (*launches)++;
-    CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    h->snow_flags = h->reduce(h->h_flags[0]);
+    uint32_t w = 0;
+    { int r = fetch_flags(h, h->d_flags, 1, &w); if (r) return r; }
+    h->snow_flags = w;
     h->snow_flags_valid = true;
     return 0;
 }
@@ -1013,9 +1142,9 @@ static int step_impl(roger_svat* h, int write_fluxes) {
                                                           st.ta_fm, h->d_flags + 2);
         CU(cudaGetLastError());
         launches++;
-        CU(cudaMemcpyAsync(h->h_flags + 2, h->d_flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        ev = h->reduce(h->h_flags[2]);
+        uint32_t w = 0;
+        { int r = fetch_flags(h, h->d_flags + 2, 1, &w); if (r) return r; }
+        ev = w;
     }
     schedule_second_half(h, ev, a, sc, p);
 
@@ -1042,10 +1171,12 @@ static int step_impl(roger_svat* h, int write_fluxes) {
         launches++;
         h->ks_ss_synced = true;
     }
-    CU(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaEventRecord(h->ev1, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    h->snow_flags = h->reduce(h->h_flags[0]);
+    {
+        uint32_t w = 0;
+        int r = fetch_flags(h, h->d_flags, 1, &w, h->ev1);
+        if (r) return r;
+        h->snow_flags = w;
+    }
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_kernel_ms += ms;
@@ -1146,12 +1277,9 @@ static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int
         CU(cudaGetLastError());
         launches++;
     }
-    CU(cudaMemcpyAsync(h->h_block_flags, h->d_block_flags, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaEventRecord(h->ev1, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
     unsigned all = 0;
-    std::vector<uint32_t> words(h->h_block_flags, h->h_block_flags + n);
-    if (h->reduce_fn) h->reduce_fn(words.data(), n, h->reduce_user);
+    std::vector<uint32_t> words(n);
+    { int r = fetch_flags(h, h->d_block_flags, n, words.data(), h->ev1); if (r) return r; }
     for (int k = 0; k < n; k++) all |= words[k];
     if (all & snow_bits) return fail(ROGER_EINVAL, "internal error: snow appeared inside a block scheduled as snow-free");
     float ms = 0;
@@ -1294,6 +1422,48 @@ int roger_svat_set_flag_reducer(roger_svat* h, roger_flag_reduce_fn fn, void* us
     return 0;
 }
 
+// window sums of the hourly forcing aggregates: the six-load form against the 144-slot form, on a caller-supplied row
+// (host code of the same templates the kernels instantiate; tests/test_abi.py feeds rows with NaN, -0.0 and every itt_day)
+int roger_selftest_window_sums(const double* row144, int itt_day, double* out4) {
+    if (!row144 || !out4 || itt_day < 0 || itt_day > 143) return fail(ROGER_EINVAL, "roger_selftest_window_sums: bad argument");
+    out4[0] = RowAgg::win_sum(row144, itt_day);
+    out4[1] = RowAgg::win_sum_full(row144, itt_day);
+    out4[2] = RowAgg::win_nanmean(row144, itt_day);
+    out4[3] = RowAgg::win_nanmean_full(row144, itt_day);
+    return 0;
+}
+
+int roger_nccl_unique_id(uint8_t* id128) {
+    if (!id128) return fail(ROGER_EINVAL, "roger_nccl_unique_id: null buffer");
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(ROGER_ENODEV, "NCCL unavailable: " + api.why);
+    NcclApi::UniqueId id;
+    NCCL(api.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+int roger_svat_enable_nccl_flags(roger_svat* h, const uint8_t* id128, int rank, int world) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(ROGER_EINVAL, "roger_svat_enable_nccl_flags: bad argument");
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(ROGER_ENODEV, "NCCL unavailable: " + api.why);
+    CU(cudaSetDevice(h->device));
+    NcclApi::UniqueId id;
+    memcpy(id.internal, id128, 128);
+    void* comm = nullptr;
+    NCCL(api.CommInitRank(&comm, world, id, rank));
+    if (h->nccl_comm) api.CommDestroy(h->nccl_comm);
+    h->nccl_comm = comm;
+    h->nccl_world = world;
+    cudaFree(h->d_gather);
+    cudaFreeHost(h->h_gather);
+    h->d_gather = nullptr; h->h_gather = nullptr;
+    CU(cudaMalloc(&h->d_gather, sizeof(unsigned) * roger_svat::kMaxFlagWords * world));
+    CU(cudaHostAlloc(&h->h_gather, sizeof(unsigned) * roger_svat::kMaxFlagWords * world, cudaHostAllocDefault));
+    h->snow_flags_valid = false;  // the flags known so far were this rank's own
+    return 0;
+}
+
 // Re-orders the cells ON THE DEVICE so that neighbouring threads hold cells of similar infiltration capacity
 // (sort key ks * (1 - sealing), masked cells last).  Columns are independent, so any order computes the same numbers; what
 // changes is which cells share a warp: the macropore / shrinkage-crack sub-step loops run only for ponded cells, and with
@@ -1341,6 +1511,47 @@ int roger_svat_optimize_cell_order(roger_svat* h) {
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(keys); cudaFree(keys_out); cudaFree(ids); cudaFree(pos); cudaFree(tmp);
     h->have_forcing = h->st.forcing_uniform ? h->have_forcing : false;  // a per-cell day block is positional: hand it over again
+    return 0;
+}
+
+// In-memory checkpoint of the run: every plane, the scheduler's scalars and flags, the uniform forcing day.  The reference's
+// counterpart is its restart file (roger/restart.py:32-174: all variables with `write_to_restart` + scalars); here the copy
+// stays in HBM (one device-to-device copy of the plane allocation) so that a stretch of the run can be repeated from exactly
+// the same state -- bench.py times `value` and `e2e` over the same simulated window this way.  Per-cell forcing day blocks
+// and the diagnostics accumulators' contents are not part of it: hand the day block over again after a rollback.
+int roger_svat_checkpoint(roger_svat* h) {
+    if (!h) return fail(ROGER_EINVAL, "roger_svat_checkpoint: null handle");
+    CU(cudaSetDevice(h->device));
+    const size_t ps_bytes = kTileBytesPS * (size_t)h->n_tiles, fl_bytes = kTileBytesF * (size_t)h->n_tiles;
+    if (!h->d_ckpt_ps) CU(cudaMalloc(&h->d_ckpt_ps, ps_bytes));
+    CU(cudaMemcpyAsync(h->d_ckpt_ps, h->d_ps, ps_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->d_fl) {
+        if (!h->d_ckpt_fl) CU(cudaMalloc(&h->d_ckpt_fl, fl_bytes));
+        CU(cudaMemcpyAsync(h->d_ckpt_fl, h->d_fl, fl_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    roger_svat::Saved& v = h->saved;
+    v.sc = h->sc; v.snow_flags = h->snow_flags; v.day_flags = h->day_flags; v.snow_flags_valid = h->snow_flags_valid;
+    v.ks_ss_synced = h->ks_ss_synced; v.soil_kh_stale = h->soil_kh_stale; v.have_forcing = h->have_forcing;
+    v.u_cur_valid = h->u_cur_valid; v.u_cur_prec = h->u_cur_prec; v.u_cur_ta = h->u_cur_ta; v.diag_count = h->diag_count;
+    memcpy(v.h_forc, h->h_forc, sizeof(v.h_forc));
+    h->have_ckpt = true;
+    return 0;
+}
+
+int roger_svat_rollback(roger_svat* h) {
+    if (!h || !h->have_ckpt) return fail(ROGER_EINVAL, "roger_svat_rollback: no checkpoint");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->copy_stream));
+    CU(cudaMemcpyAsync(h->d_ps, h->d_ckpt_ps, kTileBytesPS * (size_t)h->n_tiles, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->d_fl && h->d_ckpt_fl) CU(cudaMemcpyAsync(h->d_fl, h->d_ckpt_fl, kTileBytesF * (size_t)h->n_tiles, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const roger_svat::Saved& v = h->saved;
+    h->sc = v.sc; h->snow_flags = v.snow_flags; h->day_flags = v.day_flags; h->snow_flags_valid = v.snow_flags_valid;
+    h->ks_ss_synced = v.ks_ss_synced; h->soil_kh_stale = v.soil_kh_stale;
+    h->have_forcing = h->st.forcing_uniform ? v.have_forcing : false;
+    h->u_cur_valid = v.u_cur_valid; h->u_cur_prec = v.u_cur_prec; h->u_cur_ta = v.u_cur_ta; h->diag_count = v.diag_count;
+    memcpy(h->h_forc, v.h_forc, sizeof(v.h_forc));
     return 0;
 }
 

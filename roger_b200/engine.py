@@ -67,8 +67,12 @@ def load_library():
     lib.roger_svat_rates_ptr.argtypes = [hp]
     lib.roger_svat_rates_ptr.restype = C.c_uint64
     lib.roger_svat_synchronize.argtypes = [hp]
+    lib.roger_svat_checkpoint.argtypes = [hp]
+    lib.roger_svat_rollback.argtypes = [hp]
     lib.roger_svat_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
     lib.roger_svat_set_flag_reducer.argtypes = [hp, FLAG_REDUCE_FN, C.c_void_p]
+    lib.roger_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    lib.roger_svat_enable_nccl_flags.argtypes = [hp, C.POINTER(C.c_uint8), C.c_int, C.c_int]
     # the field table compiled into the library must be the one this package parsed from the header
     n = lib.roger_svat_field_count()
     names = [lib.roger_svat_field_name(i).decode() for i in range(n)]
@@ -164,6 +168,22 @@ class CudaSvatEngine:
         """device snapshot planes for n asynchronous plane hand-overs per output time, allocated now (never inside the stepping loop)"""
         _check(self.lib, self.lib.roger_svat_reserve_snapshots(self.h, int(n)))
 
+    def enable_nccl_flags(self, dist, device=None):
+        """Flag exchange of the adaptive time stepping by ncclAllGather on the engine's own stream.  `dist` is an initialised
+        torch.distributed (any backend): it only carries the 128-byte NCCL id from rank 0 to the others."""
+        import torch
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            _check(self.lib, self.lib.roger_nccl_unique_id(buf))
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if device is not None:
+            t = t.to(device)
+        dist.broadcast(t, src=0)
+        buf = (C.c_uint8 * 128)(*[int(v) for v in t.cpu().tolist()])
+        _check(self.lib, self.lib.roger_svat_enable_nccl_flags(self.h, buf, rank, world))
+
     def optimize_cell_order(self):
         """sort the cells on the device by infiltration capacity (warp coherence of the ponding-dependent loops); results and
         the cell numbering of every call are unchanged"""
@@ -250,6 +270,13 @@ class CudaSvatEngine:
         """enabled: False / 0 one launch and one flag read-back per step; True / 1 several steps in one launch (default up to
         262144 cells); 2 one launch per step queued back to back, one read-back per batch (default for larger grids)"""
         _check(self.lib, self.lib.roger_svat_set_block_stepping(self.h, int(enabled), int(max_block)))
+
+    def checkpoint(self):
+        """device-resident copy of every plane and of the scheduler state (the restart file of the reference, kept in HBM)"""
+        _check(self.lib, self.lib.roger_svat_checkpoint(self.h))
+
+    def rollback(self):
+        _check(self.lib, self.lib.roger_svat_rollback(self.h))
 
     def synchronize(self):
         _check(self.lib, self.lib.roger_svat_synchronize(self.h))

@@ -127,6 +127,15 @@ class SvatModel:
         self.n_steps += n
         return n
 
+    def checkpoint(self):
+        """the engine's in-memory checkpoint plus the host-side cursor of the hooks"""
+        self.engine.checkpoint()
+        self._saved = (self.itt_forc, list(self.month), self.n_steps)
+
+    def rollback(self):
+        self.engine.rollback()
+        self.itt_forc, self.month, self.n_steps = self._saved[0], list(self._saved[1]), self._saved[2]
+
     def run(self, runlen_seconds, write_fluxes=False, callback=None):
         sc = self.engine.get_scalars()
         start = sc.time

@@ -55,3 +55,30 @@ def test_no_device_fails_loudly(cuda_lib):
         CudaSvatEngine(16, abi.default_settings())
     with pytest.raises(RogerCudaError, match="no CUDA device"):
         CudaSasEngine(16, sas.default_settings(10))
+
+
+def test_window_sums_of_the_hourly_aggregates_equal_the_full_row_sums():
+    """the kernels read six forcing slots per hourly aggregate instead of walking the 144-slot row with 138 zeros: same bits
+    (including NaN slots, negative zeros, windows across the two halves of numpy's pairwise reduction and at the day's end)"""
+    import ctypes as C
+
+    import numpy as np
+
+    from roger_b200.build import LIB
+
+    lib = C.CDLL(LIB)
+    dp = C.POINTER(C.c_double)
+    lib.roger_selftest_window_sums.argtypes = [dp, C.c_int, dp]
+    rng = np.random.default_rng(5)
+    out = np.zeros(4)
+    for trial in range(40):
+        row = rng.normal(0, 3, 144) * (rng.random(144) < 0.7)
+        row[rng.random(144) < 0.1] = -0.0
+        if trial % 3 == 0:
+            row[rng.random(144) < 0.15] = np.nan
+        for itt_day in range(144):
+            assert lib.roger_selftest_window_sums(row.ctypes.data_as(dp), itt_day, out.ctypes.data_as(dp)) == 0
+            a, b, c, d = out.view(np.uint64)
+            nan_sum = np.isnan(out[0]) and np.isnan(out[1])
+            assert a == b or nan_sum, (trial, itt_day, out)
+            assert c == d or (np.isnan(out[2]) and np.isnan(out[3])), (trial, itt_day, out)
