@@ -13,12 +13,22 @@ exactly as the reference defines them.
 This module imports nothing from the reference: it only touches the objects it is handed (duck typing on
 `setup.state.variables / settings / var_meta`), so it is importable without RoGeR installed.
 
-Coherence contract.  The engine owns the per-cell state between steps.  After every step the variables named in `pull`
-(default: every state and flux plane that is an active reference variable) are written back into `vs.<name>[2:-2, 2:-2
-(, tau)]` so that `after_timestep`, diagnostics and user code observe the values the NumPy backend would have produced;
-host-side changes of parameter arrays (e.g. the monthly land-use refresh in `set_parameters`, models/svat/svat.py:116-120)
-are detected by array identity -- the reference's `update()` returns new arrays -- and re-uploaded before the step.
-State arrays modified by user code between steps must be announced with `driver.push(name)`.
+Coherence contract.  The engine owns the per-cell state between steps; `vs.<name>` are MIRRORS of its planes
+(`RogerVariables.__getattr__ / __setattr__`, roger/state.py:213-251, extended on the instance by `_install_mirror`):
+
+* host -> device: any assignment `vs.<name> = ...` of a variable the engine holds (the monthly land-use refresh of
+  `set_parameters`, models/svat/svat.py:116-120; a user hook changing a state array) marks it dirty and it is uploaded
+  before the next step.  Nothing has to be announced.
+* device -> host, `mirror="eager"` (default): after every step the variables named in `pull` (default: every state and flux
+  plane that is an active reference variable) are written back into `vs.<name>[2:-2, 2:-2(, tau)]`, then the setup's own
+  `after_timestep` runs: hooks, diagnostics and user code observe exactly what the NumPy backend would have produced, both
+  time levels included.  This is the mode the parity tests run.
+* device -> host, `mirror="lazy"`: after a step the mirrors are only marked stale; a variable is downloaded when somebody
+  reads `vs.<name>` (a diagnostic, a user hook, the monthly parameter refresh reading `vs.ta`).  The setup's `after_timestep`
+  -- in every shipped model a pure tau -> taum1 roll that reads all thirty rolled variables -- is replaced by the engine's
+  own roll (single time level on the device); a materialised mirror shows the step's result in BOTH time levels, i.e. the
+  state `after_timestep` leaves behind.  Flux variables are stored by the step only when they are listed in `fluxes` or
+  named by one of the setup's diagnostics; reading any other flux variable raises instead of returning stale numbers.
 """
 import os
 
@@ -43,7 +53,7 @@ UNSUPPORTED_SETTINGS = (
 
 class CudaStepDriver:
     def __init__(self, setup, engine_cls=None, engine_kwargs=None, pull="all", forcing_uniform=None,
-                 clamp_small_negative_storage=None):
+                 clamp_small_negative_storage=None, mirror="eager", fluxes=None, call_after_timestep=None):
         if engine_cls is None:
             from .engine import CudaSvatEngine as engine_cls  # no fallback: raises without the CUDA library / a device
         self.setup = setup
@@ -71,10 +81,32 @@ class CudaStepDriver:
         if pull == "all":
             pull = [n for n in abi.FIELD_NAMES if kinds[n] in "SF" and n in self._active]
             pull.append("ks_ss")  # the one parameter plane a step writes (subsoil.calc_ks, roger/core/subsoil.py:6-20)
+        if mirror not in ("eager", "lazy"):
+            raise ValueError("mirror must be 'eager' or 'lazy'")
+        self.mirror = mirror
+        self.call_after_timestep = (mirror == "eager") if call_after_timestep is None else bool(call_after_timestep)
+        if mirror == "lazy":
+            want = set(fluxes or ())
+            for d in (getattr(self.state, "diagnostics", None) or {}).values():  # what the setup's own diagnostics will read
+                want |= set(getattr(d, "output_variables", None) or ())
+            flux_names = [n for n in abi.FIELD_NAMES if kinds[n] == "F" and n in self._active]
+            self._untracked_fluxes = set(flux_names) - want
+            pull = [n for n in abi.FIELD_NAMES if (kinds[n] == "S" or (kinds[n] == "F" and n in want)) and n in self._active]
+            pull.append("ks_ss")
+        else:
+            self._untracked_fluxes = set()
         self.pull = list(pull)
         self._write_fluxes = any(kinds[n] == "F" for n in self.pull)
-        self._param_ids = {}
-        self._pushed = set()
+        self._device_names = set(n for n in abi.FIELD_NAMES if n in self._active and n != "maskRiverLake")
+        self._dirty = set()      # assigned on the host since the last upload
+        self._stale = set()      # lazy mode: the device holds a newer value than the host array
+        self._shadow = {}        # lazy mode: the host arrays of stale / untracked variables (ghost cells, both levels)
+        self._writing_back = False
+        self._uploaded_fp = {}   # fingerprint of the last upload of every plane
+        # planes a step writes: the uploaded fingerprint says nothing about their current device content
+        self._device_written = set(n for n in abi.FIELD_NAMES if kinds[n] in "SF") | {"ks_ss"}
+        self.downloads = 0       # planes downloaded through the mirrors (bench / tests)
+        self.uploads = 0
 
     # ------------------------------------------------------------------ vs <-> planes
     def _interior(self, name):
@@ -95,9 +127,98 @@ class CudaStepDriver:
             cur[2:-2, 2:-2, int(vs.tau)] = v
         else:
             cur[2:-2, 2:-2] = v
-        setattr(vs, name, cur)
-        if name in self._param_ids:
-            self._param_ids[name] = id(getattr(vs, name))
+        self._writing_back = True
+        try:
+            setattr(vs, name, cur)
+        finally:
+            self._writing_back = False
+
+    # ------------------------------------------------------------------ mirrors (roger/state.py:213-251 on this instance)
+    def _install_mirror(self):
+        """Gives `vs` (whatever class it is: the reference's RogerVariables or a stand-in) the two mirror hooks: an assignment
+        of a device-held variable marks it dirty; a read of a stale one downloads it."""
+        vs = self.state.variables
+        base = vs.__class__
+        if getattr(base, "_roger_b200_mirrored", False):
+            object.__setattr__(vs, "_cuda_driver", self)
+            return
+        driver_of = lambda obj: obj.__dict__.get("_cuda_driver")  # noqa: E731
+
+        def __setattr__(obj, name, val):
+            base.__setattr__(obj, name, val)
+            drv = driver_of(obj)
+            if drv is not None and not drv._writing_back and name in drv._device_names:
+                drv._dirty.add(name)
+                drv._stale.discard(name)
+                drv._shadow.pop(name, None)
+
+        def __getattr__(obj, name):
+            drv = obj.__dict__.get("_cuda_driver")
+            if drv is not None:
+                if name in drv._stale:
+                    return drv._materialise(name)
+                if name in drv._untracked_fluxes and name in drv._shadow:
+                    raise RuntimeError(f"vs.{name} is a flux the lazy cuda mirror does not store (it is written by the step only on "
+                                       f"request): construct CudaStepDriver(..., fluxes=[{name!r}, ...]) or name it in a diagnostic")
+            parent = getattr(base, "__getattr__", None)
+            if parent is not None:
+                return parent(obj, name)
+            raise AttributeError(name)
+
+        cls = type("CudaMirrored" + base.__name__, (base,), {"__setattr__": __setattr__, "__getattr__": __getattr__,
+                                                               "_roger_b200_mirrored": True})
+        vs.__class__ = cls
+        object.__setattr__(vs, "_cuda_driver", self)
+
+    def _materialise(self, name):
+        """a read of a stale mirror: download the plane into the host array (both time levels show the step's result, i.e.
+        the state after `after_timestep`); works on a locked `vs` -- reading is not a modification"""
+        vs = self.state.variables
+        cur = np.array(self._shadow.pop(name))
+        self._stale.discard(name)
+        self.downloads += 1
+        v = self.engine.download(name).reshape(self.nx, self.ny).astype(cur.dtype)
+        if cur.ndim == 3:
+            cur[2:-2, 2:-2, : int(vs.tau) + 1] = v[:, :, None]
+        else:
+            cur[2:-2, 2:-2] = v
+        cur.flags.writeable = False  # as the reference's own arrays (roger/variables.py:6432)
+        vs.__dict__[name] = cur
+        return cur
+
+    def _mark_stale(self):
+        d = self.state.variables.__dict__
+        for name in self.pull:
+            if name in d:
+                self._shadow[name] = d.pop(name)
+            self._stale.add(name)
+        for name in self._untracked_fluxes:
+            if name in d:
+                self._shadow[name] = d.pop(name)
+
+    @staticmethod
+    def _fingerprint(values):
+        """64-bit fingerprint of a plane's bit patterns (cheap stand-in for keeping a host copy of every uploaded plane)"""
+        bits = np.ascontiguousarray(values, dtype=np.float64).view(np.uint64)
+        w = np.arange(1, bits.size + 1, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            return int(np.bitwise_xor.reduce(bits)) ^ int((bits * w).sum(dtype=np.uint64))
+
+    def _upload(self, name):
+        v = self._interior(name)
+        self.engine.upload(name, v)
+        self._uploaded_fp[name] = self._fingerprint(v)
+
+    def _upload_dirty(self):
+        for name in sorted(self._dirty):
+            v = self._interior(name)
+            fp = self._fingerprint(v)
+            if name not in self._stale and self._uploaded_fp.get(name) == fp and name not in self._device_written:
+                continue  # re-assigned with the values the device already holds (e.g. a tau -> taum1 roll of a parameter array)
+            self.engine.upload(name, v)
+            self._uploaded_fp[name] = fp
+            self.uploads += 1
+        self._dirty.clear()
 
     def _settings_struct(self, uniform):
         st = self.state.settings
@@ -116,17 +237,18 @@ class CudaStepDriver:
         zeros = np.zeros(self.C)
         for name in abi.FIELD_NAMES:
             if name == "maskRiverLake" or name in self._active:
-                self.engine.upload(name, self._interior(name))
-                if abi.FIELD_KINDS[abi.FIELD_ID[name]] == "P" and name != "maskRiverLake":
-                    self._param_ids[name] = id(getattr(vs, name))
+                self._upload(name)
             else:
                 self.engine.upload(name, zeros)
         if hasattr(self.engine, "optimize_cell_order") and os.environ.get("ROGER_B200_CELL_ORDER", "1") != "0":
             self.engine.optimize_cell_order()  # device-side only: every call keeps the setup's cell numbering
+        self._dirty.clear()
+        self._install_mirror()
 
     def push(self, name):
-        """Announce that user code changed `vs.<name>` on the host; it is uploaded before the next step."""
-        self._pushed.add(name)
+        """Kept for callers of the first version: assignments to `vs.<name>` are tracked by the mirror itself; in-place edits
+        of a (writeable copy of a) state array can still be announced here."""
+        self._dirty.add(name)
 
     # ------------------------------------------------------------------ the step
     def _scalars_to_engine(self):
@@ -179,13 +301,7 @@ class CudaStepDriver:
         if int(np.asarray(vs.time)) % DAY == 0 or self.engine is None:
             self._hand_forcing_day()
         setup.set_parameters(state)
-        for name, old in list(self._param_ids.items()):  # host-side parameter refresh (monthly land use)
-            if id(getattr(vs, name)) != old:
-                self.engine.upload(name, self._interior(name))
-                self._param_ids[name] = id(getattr(vs, name))
-        for name in self._pushed:
-            self.engine.upload(name, self._interior(name))
-        self._pushed.clear()
+        self._upload_dirty()  # whatever the hooks assigned: the monthly land-use refresh, user edits of state arrays
         pend = getattr(self, "_pending_output", None)
         if pend is not None:  # enable_output() was called before the engine existed: the accumulators start with this step
             self._pending_output = None
@@ -193,15 +309,38 @@ class CudaStepDriver:
         self._scalars_to_engine()
         self.engine.step(self._write_fluxes)
         sc = self._scalars_from_engine()
-        with vs.unlock():
-            for name in self.pull:
-                self._store(name, self.engine.download(name))
+        pulled = {}
+        if self.mirror == "eager":
+            with vs.unlock():
+                for name in self.pull:
+                    pulled[name] = self.engine.download(name)
+                    self.downloads += 1
+                    self._store(name, pulled[name])
+        else:
+            self._mark_stale()
         if not sc.sanity_ok:
             import warnings
 
             warnings.warn(f"Solution diverged at iteration {sc.itt} (numerics.sanity_check)")
         self._maybe_output(sc.time)
-        setup.after_timestep(state)
+        tail = getattr(self, "reference_tail", None)
+        if tail is not None:  # the reference's own diagnostics on the mirrors (cuda_step below)
+            tail(sc)
+        if self.call_after_timestep:
+            setup.after_timestep(state)
+            # the hook's tau -> taum1 roll re-assigns the rolled arrays: only values that really differ from what the device
+            # holds count as host-side changes
+            for name in list(self._dirty):
+                if name in pulled and np.array_equal(self._interior(name), pulled[name], equal_nan=True):
+                    self._dirty.discard(name)
+        else:
+            with vs.unlock():  # the part of every after_timestep hook that is not a roll of device-held arrays
+                for name in ("event_id", "year", "month", "doy"):
+                    if hasattr(vs, name):
+                        a = np.array(getattr(vs, name))
+                        if a.ndim == 1 and a.shape[0] >= 2:
+                            a[int(vs.taum1)] = a[int(vs.tau)]
+                            setattr(vs, name, a)
         return sc
 
     def run(self, runlen=None):
@@ -271,6 +410,52 @@ class CudaStepDriver:
         if out is not None:
             out.close()
             self._out = None
+
+
+def cuda_step(setup, state=None, **driver_kwargs):
+    """What the `cuda` branch of `RogerSetup.step` calls (integration/roger_cuda_backend.patch): one time step of `setup`
+    with the per-cell work on the GPU.  The driver is created on first use and kept on the setup object; the reference's
+    own diagnostics (`diagnostics.reset / diagnose / output`, roger/roger.py:453-466) and restart hook run unchanged on
+    the mirrors when the reference package is importable."""
+    drv = getattr(setup, "_cuda_driver", None)
+    if drv is None:
+        st = setup.state.settings
+        kw = dict(driver_kwargs)
+        if getattr(st, "enable_offline_transport", False):
+            drv = CudaTransportDriver(setup, engine_cls=kw.get("engine_cls", DEFAULT_TRANSPORT_ENGINE))
+        else:
+            kw.setdefault("engine_cls", DEFAULT_ENGINE)
+            kw.setdefault("mirror", os.environ.get("ROGER_CUDA_MIRROR", "eager"))
+            drv = CudaStepDriver(setup, **kw)
+            drv.reference_tail = _reference_tail(setup)
+        setup._cuda_driver = drv
+    return drv.step()
+
+
+def _reference_tail(setup):
+    """roger/roger.py:447-466 after the storages: the diagnostics block of the reference, on the mirrors"""
+    try:
+        from roger import diagnostics
+    except Exception:  # stand-in setups without the reference package
+        return None
+    state = setup.state
+
+    def tail(sc):
+        vs, settings = state.variables, state.settings
+        if getattr(settings, "warmup_done", False):
+            with vs.unlock():
+                if vs.time_for_diag >= settings.output_frequency:
+                    vs.time_for_diag = 0
+                diagnostics.reset(state)
+                vs.time_for_diag = vs.time_for_diag + vs.dt_secs
+            diagnostics.diagnose(state)
+            diagnostics.output(state)
+
+    return tail
+
+
+DEFAULT_ENGINE = None            # None: roger_b200.engine.CudaSvatEngine (no fallback); tests may plug the CPU oracle in here
+DEFAULT_TRANSPORT_ENGINE = None  # None: roger_b200.sas_engine.CudaSasEngine
 
 
 class CudaTransportDriver:

@@ -394,3 +394,42 @@ def test_device_cell_order_changes_nothing_but_the_placement(lateral, dist):
     models[0].engine.upload("z_gw", v)
     assert util.same_bits(models[0].get("z_gw"), v)
     assert util.same_bits(models[0].get("S_lp_ss"), models[1].get("S_lp_ss"))
+
+
+def test_lazy_mirrors_on_the_cuda_engine():
+    """mirror="lazy": the driver downloads a plane only when `vs.<name>` is read; the values read -- after a month change with
+    its land-use refresh (which itself reads vs.ta through the mirror) and a user edit of a state array -- equal the eager
+    driver's, both on the CUDA engine."""
+    from roger_b200 import synth
+    from roger_b200.integration import CudaStepDriver
+    from tests.mini_setup import MiniSvatSetup
+
+    shape = (24, 16)
+    forcing = synth.mixed_forcing(60, seed=42, start_doy=110)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, lu_choices=(10, 11, 12, 8, 5, 9), masked_fraction=0.1)
+    drivers = []
+    for mode in ("eager", "lazy"):
+        setup = MiniSvatSetup(shape, forcing, prim, th_rz, th_ss)
+        setup.setup()
+        drivers.append(CudaStepDriver(setup, engine_cls=_engine(), mirror=mode, fluxes=["q_ss"]))
+    months = set()
+    for step in range(400):
+        if step == 150:  # a user hook that edits a state array on the host: picked up by the mirror, no announcement needed
+            for d in drivers:
+                vs = d.state.variables
+                a = np.array(vs.S_dep)
+                a[2:-2, 2:-2, 1] += 0.25
+                vs.S_dep = a
+        a, b = drivers[0].step(), drivers[1].step()
+        assert (a.time, a.dt_secs, a.itt_day) == (b.time, b.dt_secs, b.itt_day)
+        months.add(int(drivers[1].state.variables.month[1]))
+        if step % 37 == 0 or step == 151:
+            for n in ("S", "theta_rz", "q_ss", "S_dep", "S_int_top_tot"):
+                x, y = np.asarray(getattr(drivers[0].state.variables, n)), np.asarray(getattr(drivers[1].state.variables, n))
+                x = x[2:-2, 2:-2, 1] if x.ndim == 3 else x[2:-2, 2:-2]
+                y = y[2:-2, 2:-2, 1] if y.ndim == 3 else y[2:-2, 2:-2]
+                assert util.same_bits(x, y), (step, n)
+    assert len(months) >= 2
+    assert drivers[1].downloads < 0.02 * drivers[0].downloads
+    with pytest.raises(RuntimeError, match="fluxes"):
+        drivers[1].state.variables.q_hof
