@@ -368,6 +368,8 @@ def run_cuda(args):
     extras = {}
     if not args.no_sweep:
         extras["sweep"], extras["strong"] = run_sweep(args, local, world, rank, dist if world > 1 else None, value, step_time / args.steps)
+    if not args.no_dropin and rank == 0:
+        extras["dropin"] = run_dropin(args, local)
     if not args.no_scenarios:
         extras["scenarios"] = {"snow_month_per_cell_forcing": run_scenario_snow_percell(args, local, world, rank, dist if world > 1 else None)}
 
@@ -486,6 +488,54 @@ def run_sweep(args, local, world, rank, dist, main_value, main_s_per_step):
     r = measure(strong_cells)  # the same tiled workload at every N, so the points of a 1/2/4/8 series are comparable
     strong = dict(r, cells_total=strong_cells * world, note=f"2^24 cells in total, {strong_cells} per GPU (fixed total work; tiled parameters, window right after warm-up)")
     return out, strong
+
+
+def run_dropin(args, local):
+    """Throughput of the reference-facing path itself: `roger_b200.integration.CudaStepDriver` stepping a setup object with the
+    reference's conventions ((nx+4, ny+4[, 2]) host arrays with ghost cells and tau / taum1 levels, the SVAT model's hooks
+    set_forcing / set_parameters / after_timestep; tests/mini_setup.py stands in for the reference package, which does not
+    travel to the GPU box).  `eager`: every state and flux plane written back into vs.* after every step and the setup's
+    after_timestep hook run on them -- what a user sees without changing anything; `lazy`: dirty-flag mirrors, planes are
+    downloaded when read (here: `S` and `theta_rz` once per simulated day, as a daily diagnostic would)."""
+    import torch
+    from roger_b200.engine import CudaSvatEngine
+    from roger_b200.integration import CudaStepDriver
+    from tests.mini_setup import MiniSvatSetup
+
+    side = args.dropin_side
+    shape = (side, side)
+    n_cells = side * side
+    forcing = synth.mixed_forcing(40, seed=42, start_doy=START_DOY)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43)
+    out = {"cells": n_cells, "setup": "tests/mini_setup.py::MiniSvatSetup (the reference's array conventions and SVAT hooks), SVAT model, uniform forcing"}
+    for mode, steps in (("eager", 4), ("lazy", 30)):
+        setup = MiniSvatSetup(shape, forcing, prim, th_rz, th_ss)
+        setup.setup()
+        drv = CudaStepDriver(setup, engine_cls=CudaSvatEngine, engine_kwargs={"device": local}, mirror=mode)
+        for _ in range(2):
+            drv.step()
+        torch.cuda.synchronize()
+        d0 = drv.downloads
+        per_step, midnight = [], []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            t1 = time.perf_counter()
+            at_midnight = int(np.asarray(setup.state.variables.time)) % 86400 == 0  # the setup's set_forcing assembles the day blocks
+            sc = drv.step()
+            if mode == "lazy" and sc.time % 86400 == 0:
+                _ = setup.state.variables.S, setup.state.variables.theta_rz
+            drv.engine.synchronize()
+            (midnight if at_midnight else per_step).append(time.perf_counter() - t1)
+        el = time.perf_counter() - t0
+        out[mode] = {"value": n_cells * steps / el, "unit": "cell-timesteps/s", "ms_per_step": 1e3 * el / steps, "steps": steps,
+                     "plane_downloads_per_step": (drv.downloads - d0) / steps,
+                     "ms_per_step_within_a_day": 1e3 * float(np.median(per_step)) if per_step else None,
+                     "ms_per_step_at_midnight": 1e3 * float(np.median(midnight)) if midnight else None,
+                     "note": "at midnight the setup's own set_forcing hook assembles three (nx+4, ny+4, 144) host arrays and the driver hands them over"}
+        drv.engine.close()
+        del drv, setup
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_scenario_snow_percell(args, local, world, rank, dist):
@@ -766,6 +816,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the grid-size sweep (2^16 .. 2^22 cells per GPU) and the strong-scaling point")
     ap.add_argument("--sweep-large", action="store_true", help="add 2^26 and 2^27 cells per GPU to the sweep")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the throughput measurement of the drop-in driver (CudaStepDriver)")
+    ap.add_argument("--dropin-side", type=int, default=1024)
     ap.add_argument("--no-scenarios", action="store_true", help="skip the snow-month / per-cell-forcing scenario")
     ap.add_argument("--scenario-side", type=int, default=2048)
     args = ap.parse_args()

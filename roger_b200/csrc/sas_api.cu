@@ -410,6 +410,7 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
         CU(cudaMemsetAsync(h->d_state[k], 0, arr, h->stream));
     }
     // the scratch arrays carry a few planes of padding: the sub-step pass prefetches ROGER_SAS_UNROLL bins ahead unguarded
+    static_assert(2 * ROGER_SAS_UNROLL <= 8, "the scratch padding below covers a look-ahead of 2 * ROGER_SAS_UNROLL planes");
     const size_t pad = sizeof(double) * (size_t)n_cells * 8;
     CU(cudaMalloc(&h->d_san, arr + pad));
     CU(cudaMalloc(&h->d_TTn, arr + pad));

@@ -1213,7 +1213,11 @@ static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int
     std::vector<StepPlan> plans;
     std::vector<int> dts;
     roger_svat_scalars sc = h->sc;  // tentative: committed once the block has run
-    const double save_prec = h->u_cur_prec, save_ta = h->u_cur_ta;
+    // the tentative planning below advances h->u_cur_*: put them back on every path that does not commit the block
+    struct Restore {
+        roger_svat* h; double prec, ta; bool commit = false;
+        ~Restore() { if (!commit) { h->u_cur_prec = prec; h->u_cur_ta = ta; } }
+    } restore{h, h->u_cur_prec, h->u_cur_ta};
     while ((int)plans.size() < max_steps && (int)plans.size() < (int)h->max_block) {
         roger_svat_scalars sc_try = sc;
         StepPlan p;
@@ -1230,10 +1234,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int
         dts.push_back((int)sc_try.dt_secs);
         if (sc.time % 86400 == 0) break;  // the next day needs a new forcing block
     }
-    if (plans.size() < 2) {  // not worth a block; undo the tentative bookkeeping
-        h->u_cur_prec = save_prec; h->u_cur_ta = save_ta;
-        return 0;
-    }
+    if (plans.size() < 2) return 0;  // not worth a block (the tentative bookkeeping is undone by `restore`)
     const int n = (int)plans.size();
     if (write_fluxes) { int r = ensure_flux_planes(h); if (r) return r; }
     if (!h->d_plans) {
@@ -1290,6 +1291,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int
     h->last_dts.insert(h->last_dts.end(), dts.begin(), dts.end());
     h->sc = sc;
     h->sc.sanity_ok = (all & FLAG_INSANE) ? 0 : 1;
+    restore.commit = true;
     *n_done = n;
     return 0;
 }
