@@ -52,6 +52,26 @@ enum roger_sas_statistic {
     RSS_COUNT
 };
 
+/* ---- nitrate (settings.solute = 2): the anion transport plus the soil nitrogen cycle on age-ranked mineral nitrogen
+ *      (roger/core/nitrate.py:68-696 calc_nitrogen_cycle_kernel and its process kernels; transport.py:948-991 with
+ *      settings.enable_nitrate, :809-824 ageing of Nmin, :3623-3657 after_substep_nitrate).  The soil temperature of
+ *      nitrate.py:6-66 is a per-cell scalar with a sine and an exponential of forcing statistics: the host side computes it
+ *      (roger_b200/nitrate.py, NumPy as the reference) and hands it over as a forcing plane. */
+enum roger_nitrate_param { /* per-cell parameter planes, roger/variables.py (km_denit_rz ... damp_soil_temp) */
+    RNP_kfix_rz = 0, RNP_kmin_rz, RNP_kmin_ss, RNP_km_nit_rz, RNP_dmax_nit_rz, RNP_kngl_rz, RNP_km_denit_rz, RNP_dmax_denit_rz,
+    RNP_km_denit_ss, RNP_dmax_denit_ss, RNP_z_soil, RNP_S_sat_rz, RNP_S_sat_ss, RNP_COUNT
+};
+enum roger_nitrate_forcing { /* per-cell daily planes besides the RSF_* ones */
+    RNF_temp_soil = 0, /* vs.temp_soil[tau] of the day (nitrate.py:6-66)                 */
+    RNF_z_root,        /* vs.z_root[tau]                                                  */
+    RNF_lu_id,         /* vs.LU_ID[:, :, itt]: nitrogen-fixing crops (nitrate.py:339-343) */
+    RNF_nup,           /* vs.nup: potential ammonium uptake                               */
+    RNF_COUNT
+};
+enum roger_nitrate_output { /* per-cell results of the nitrogen cycle of the last step */
+    RNO_nit_s = 0, RNO_denit_s, RNO_min_s, RNO_ngas_s, RNO_nfix_s, RNO_nh4_up, RNO_Nmin_s, RNO_COUNT
+};
+
 typedef struct roger_sas_settings {
     int32_t ages;          /* settings.ages (number of age bins)                       */
     int32_t substeps;      /* settings.sas_solver_substeps                              */
@@ -62,7 +82,9 @@ typedef struct roger_sas_settings {
     int32_t age_statistics; /* compute the RSS_* planes every step (settings.enable_age_statistics + numerical errors) */
     int32_t solute;         /* 0: stable isotope (oxygen-18 / deuterium: msa holds bin concentrations);
                                1: conservative anion (bromide / chloride: msa holds bin solute MASS, the *_transport_anion_kernel
-                                  family of the reference; the RSO_C_iso_* result planes then hold the solute masses M_*) */
+                                  family of the reference; the RSO_C_iso_* result planes then hold the solute masses M_*);
+                               2: nitrate = the anion transport plus the soil nitrogen cycle (two more age-ranked arrays Nmin_rz,
+                                  Nmin_ss: state 4 and 5 of roger_sas_upload_state); deterministic solver, no age statistics */
     int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day
                                (svat_transport_model_euler, transport.py:2063-2413; statistics / balance errors are those of the day's
                                last Euler step, as the reference's output shows them; the anion branch runs without statistics);
@@ -75,7 +97,7 @@ typedef struct roger_sas roger_sas; /* opaque handle */
 
 int roger_sas_create(roger_sas **out, int64_t n_cells, const roger_sas_settings *settings, int device);
 void roger_sas_destroy(roger_sas *h);
-/* age-ranked state: which = 0 sa_rz, 1 sa_ss, 2 msa_rz, 3 msa_ss; host buffers of n_cells*ages doubles */
+/* age-ranked state: which = 0 sa_rz, 1 sa_ss, 2 msa_rz, 3 msa_ss (nitrate: 4 Nmin_rz, 5 Nmin_ss); host buffers of n_cells*ages doubles */
 int roger_sas_upload_state(roger_sas *h, int which, const double *host);
 int roger_sas_download_state(roger_sas *h, int which, double *host);
 /* raw device address of the age-major array (A planes of n_cells doubles; age bin j is plane (base + j) mod A,
@@ -93,6 +115,13 @@ int roger_sas_set_parameters(roger_sas *h, const double *mask_catch, const doubl
  * n_cells doubles each */
 int roger_sas_set_anion_parameters(roger_sas *h, const double *alpha_transp, const double *alpha_q, const double *lu_id,
                                    const double *S_sat_rz);
+/* nitrate only: RNP_COUNT parameter planes of n_cells doubles, grid spacing (settings.dx, settings.dy), settings.zroot_to_zsoil_max
+ * and the time step in hours (vs.dt = 24) */
+int roger_sas_set_nitrate_parameters(roger_sas *h, const double *params, double dx, double dy, double zroot_to_zsoil_max, double dt_hours);
+/* nitrate only: the day's RNF_COUNT planes of n_cells doubles, before roger_sas_step */
+int roger_sas_set_nitrate_forcing(roger_sas *h, const double *planes);
+/* nitrate only: RNO_COUNT planes of n_cells doubles from the last step */
+int roger_sas_download_nitrate_outputs(roger_sas *h, double *host);
 /* one daily step.  forcing: RSF_COUNT planes of n_cells doubles (host memory). */
 int roger_sas_step(roger_sas *h, const double *forcing);
 /* same with forcing already on the device (raw address of RSF_COUNT * n_cells doubles) */

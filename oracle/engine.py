@@ -192,6 +192,27 @@ class OracleSasEngine:
     def set_anion_parameters(self, alpha_transp, alpha_q, lu_id, S_sat_rz):
         self._anion = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (alpha_transp, alpha_q, lu_id, S_sat_rz)]
 
+    # ---- nitrate (settings.solute = 2): roger_b200.nitrate.NitrateModel drives these
+    def set_nitrate_parameters(self, params, dx, dy, zroot_to_zsoil_max, dt_hours):
+        self._nit_params = np.ascontiguousarray(params, dtype=np.float64)
+        self._nit_scal = (float(dx), float(dy), float(zroot_to_zsoil_max), float(dt_hours))
+        self._nit_out = np.zeros((7, self.n))
+        self.state.setdefault("Nmin_rz", np.zeros((self.n, self.A)))
+        self.state.setdefault("Nmin_ss", np.zeros((self.n, self.A)))
+
+    def set_nitrate_forcing(self, planes):
+        self._nit_forcing = np.ascontiguousarray(planes, dtype=np.float64)
+
+    def download_nitrate_outputs(self):
+        return self._nit_out.copy()
+
+    def upload_state_index(self, which, arr):
+        name = (self.sas.STATE + ["Nmin_rz", "Nmin_ss"])[which]
+        self.state[name] = np.ascontiguousarray(np.asarray(arr, dtype=np.float64).reshape(self.n, self.A)).copy()
+
+    def download_state_index(self, which):
+        return self.state[(self.sas.STATE + ["Nmin_rz", "Nmin_ss"])[which]].copy()
+
     def _install_bounds(self):
         """the C oracle keeps the bounds in file-scope variables: (re)install this engine's before every step"""
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
@@ -206,6 +227,13 @@ class OracleSasEngine:
         fa.restype = None
         a = getattr(self, "_anion", None)
         fa(*([dp(x) for x in a] if a else [None] * 4))
+        fn2 = lib().sas_oracle_set_nitrate
+        fn2.argtypes = [C.POINTER(C.c_double)] * 5 + [C.c_double] * 4
+        fn2.restype = None
+        if self.settings.solute == 2:
+            fn2(dp(self._nit_params), dp(self._nit_forcing), dp(self.state["Nmin_rz"]), dp(self.state["Nmin_ss"]), dp(self._nit_out), *self._nit_scal)
+        else:
+            fn2(None, None, None, None, None, 1.0, 1.0, 0.7, 24.0)
 
     def download_statistics(self):
         return self.stats.copy()

@@ -482,6 +482,148 @@ static void anion_ageing(int A, double *sa, double *msa)
     msa[A - 1] += msam1_last;
 }
 
+/* ---- nitrate: soil nitrogen cycle on the age-ranked arrays (roger/core/nitrate.py:68-696), called between the capillary rise
+ * and the storage kernels of the anion day (transport.py:966-969) ------------------------------------------------------- */
+static struct {
+    const double *params;  /* RNP_COUNT planes */
+    const double *forcing; /* RNF_COUNT planes of the day */
+    double *nmin_rz, *nmin_ss; /* (cell, age) */
+    double *out;           /* RNO_COUNT planes */
+    double dx, dy, zmax, dt;
+} g_nit = {NULL, NULL, NULL, NULL, NULL, 1, 1, 0.7, 24};
+void sas_oracle_set_nitrate(const double *params, const double *forcing, double *nmin_rz, double *nmin_ss, double *out, double dx, double dy,
+                            double zroot_to_zsoil_max, double dt_hours)
+{
+    g_nit.params = params; g_nit.forcing = forcing; g_nit.nmin_rz = nmin_rz; g_nit.nmin_ss = nmin_ss; g_nit.out = out;
+    g_nit.dx = dx; g_nit.dy = dy; g_nit.zmax = zroot_to_zsoil_max; g_nit.dt = dt_hours;
+}
+/* soil temperature coefficient of the process kernels: T / (30 - lo) inside [lo, 30], 1 above 30, 0 below lo; "* maskCatch" twice */
+static double temp_coeff(double T, double lo, double m)
+{
+    double c = (((T >= lo) && (T <= 30)) ? T / (30 - lo) : 0) * m;
+    c = ((T > 30) ? 1 : c) * m;
+    return c;
+}
+/* nitrate.py:176-257 calc_nit_soil / :349-427 calc_gaseous_loss / :430-467 calc_ammonium_uptake share the distribution step:
+ * r[j] = (sum(w) > 0) ? (w[j] / sum(w)) * pot : 0, limited to Nmin[j] and to >= 0 (each statement "* maskCatch") */
+static void distribute(int A, const double *w, double wsum, double pot, const double *nmin, double m, double *r)
+{
+    for (int j = 0; j < A; j++) {
+        double v = ((wsum > 0) ? ((w[j] / wsum) * pot) : 0.0) * m;
+        v = ((v > nmin[j]) ? nmin[j] : v) * m;
+        v = ((v < 0) ? 0 : v) * m;
+        r[j] = v;
+    }
+}
+/* nitrate.py:68-173 calc_denit_soil: the oldest solute is removed first */
+static void denit_soil(int A, const double *msa, double km, double Dmax, const double *sa, double S_sat, double T, double m, double *mra,
+                       double *tmp)
+{
+    const double f = (g_nit.dt / (365 * 24)) * g_nit.dx * g_nit.dy * 100;
+    const double S = np_sum(sa, A) * m;
+    const double coeff = temp_coeff(T, 5, m);
+    const double ms = np_sum(msa, A) * m;
+    double mr_pot = (Dmax * (g_nit.dt / (365 * 24)) * g_nit.dx * g_nit.dy * 100 *
+                     (ms / (km * (g_nit.dt / (365 * 24)) * g_nit.dx * g_nit.dy * 100 + ms))) * coeff * m;
+    (void)f;
+    mr_pot = ((S >= 0.7 * S_sat) ? mr_pot : 0) * m;
+    /* ms_cuml = cumsum(msa[::-1])[::-1] * m */
+    double acc = 0;
+    for (int j = A - 1; j >= 0; j--) {
+        acc = (j == A - 1) ? msa[j] : acc + msa[j];
+        tmp[j] = ((acc * m < mr_pot) ? 0 : msa[j]) * m; /* msa with the bins younger-side of the potential emptied ... */
+    }
+    tmp[A - 1] += -((tmp[A - 1] >= mr_pot) ? mr_pot : 0) * m;
+    for (int j = 0; j < A; j++) {
+        double v = (msa[j] * m - tmp[j]) * m;
+        v = ((v < 0) ? 0 : v) * m;
+        mra[j] = v;
+    }
+}
+static void nitrogen_cycle_cell(int A, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss, double transp, double m,
+                                double *work)
+{
+#define NP(k) g_nit.params[(size_t)(k) * (size_t)C + (size_t)i]
+#define NF(k) g_nit.forcing[(size_t)(k) * (size_t)C + (size_t)i]
+#define NO(k) g_nit.out[(size_t)(k) * (size_t)C + (size_t)i]
+    double *n_rz = g_nit.nmin_rz + (size_t)i * A, *n_ss = g_nit.nmin_ss + (size_t)i * A;
+    double *ma = work, *r = ma + (A + 2), *mr_rz = r + (A + 2), *mr_ss = mr_rz + (A + 2), *tmp = mr_ss + (A + 2);
+    const double T = NF(RNF_temp_soil), z_root = NF(RNF_z_root), z_soil = NP(RNP_z_soil), lu = NF(RNF_lu_id);
+    const double dt = g_nit.dt, dx = g_nit.dx, dy = g_nit.dy;
+    /* calc_n_fixation :305-346, calc_min_soil :260-302 */
+    double nfix = NP(RNP_kfix_rz) * (dt / (365 * 24)) * dx * dy * 100 * temp_coeff(T, 0, m) * (z_root / (g_nit.zmax * z_soil)) * m;
+    {
+        static const double fixers[10] = {541, 577, 578, 580, 581, 583, 584, 586, 587, 588};
+        int is = 0;
+        for (int k = 0; k < 10; k++) is = is || (lu == fixers[k]);
+        nfix = is ? nfix : 0;
+    }
+    nfix = nfix * m;
+    NO(RNO_nfix_s) = nfix;
+    const double min_rz = (NP(RNP_kmin_rz) * (dt / (365 * 24)) * dx * dy * 100 * temp_coeff(T, 0, m) * m) * m;
+    const double min_ss = (NP(RNP_kmin_ss) * (dt / (365 * 24)) * dx * dy * 100 * temp_coeff(T, 0, m) * m) * m;
+    NO(RNO_min_s) = min_rz + min_ss;
+    n_rz[0] += nfix;
+    n_rz[0] += min_rz * m;
+    n_ss[0] += min_ss * m;
+    /* nitrification of the root zone :176-257 */
+    {
+        const double Ssum = np_sum(s_rz, A);
+        const double S = Ssum * m;
+        const double nsum = np_sum(n_rz, A);
+        double pot = (NP(RNP_dmax_nit_rz) * (dt / (365 * 24)) * dx * dy * 100 *
+                      (nsum / (NP(RNP_km_nit_rz) * (dt / (365 * 24)) * dx * dy * 100 + nsum))) * temp_coeff(T, 1, m) * m;
+        pot = ((S < 0.9 * NP(RNP_S_sat_rz)) ? pot : 0) * m;
+        distribute(A, s_rz, Ssum, pot, n_rz, m, ma);
+        for (int j = 0; j < A; j++) ma[j] = ma[j] * m; /* vs.ma_rz = calc_nit_soil(...) * maskCatch */
+        for (int j = 0; j < A; j++) n_rz[j] += -ma[j];
+    }
+    /* gaseous loss :349-427 */
+    {
+        const double S = np_sum(s_rz, A) * m;
+        double pot = (NP(RNP_kngl_rz) * (dt / (365 * 24)) * dx * dy * 100) * temp_coeff(T, 5, m) * m;
+        pot = ((S < 0.9 * NP(RNP_S_sat_rz)) ? pot : 0) * m;
+        const double nsum = np_sum(n_rz, A);
+        distribute(A, n_rz, nsum, pot, n_rz, m, r);
+        NO(RNO_ngas_s) = np_sum(r, A);
+        for (int j = 0; j < A; j++) n_rz[j] += -r[j] * m;
+    }
+    /* ammonium uptake :430-467 */
+    {
+        const double pot = ((transp > 0) ? NF(RNF_nup) * (z_root / (z_soil * g_nit.zmax)) : 0) * m;
+        const double nsum = np_sum(n_rz, A);
+        distribute(A, n_rz, nsum, pot, n_rz, m, r);
+        for (int j = 0; j < A; j++) tmp[j] = r[j];
+        NO(RNO_nh4_up) = np_sum(tmp, A) * m;
+        for (int j = 0; j < A; j++) n_rz[j] += -r[j] * m;
+    }
+    for (int j = 0; j < A; j++) ms_rz[j] += ma[j];
+    for (int j = 0; j < A; j++) n_ss[j] += -0.0; /* vs.ma_ss is never written by the reference: 0 */
+    /* denitrification :68-173 */
+    denit_soil(A, ms_rz, NP(RNP_km_denit_rz), NP(RNP_dmax_denit_rz), s_rz, NP(RNP_S_sat_rz), T, m, mr_rz, tmp);
+    for (int j = 0; j < A; j++) mr_rz[j] = mr_rz[j] * m;
+    for (int j = 0; j < A; j++) ms_rz[j] += -mr_rz[j];
+    denit_soil(A, ms_ss, NP(RNP_km_denit_ss), NP(RNP_dmax_denit_ss), s_ss, NP(RNP_S_sat_ss), T, m, mr_ss, tmp);
+    for (int j = 0; j < A; j++) mr_ss[j] = mr_ss[j] * m;
+    for (int j = 0; j < A; j++) ms_ss[j] += -mr_ss[j];
+    for (int j = 0; j < A; j++) tmp[j] = ma[j] + 0.0; /* ma_s = ma_rz + ma_ss */
+    NO(RNO_nit_s) = np_sum(tmp, A);
+    for (int j = 0; j < A; j++) tmp[j] = mr_rz[j] + mr_ss[j];
+    NO(RNO_denit_s) = np_sum(tmp, A);
+    NO(RNO_Nmin_s) = np_sum(n_rz, A) + np_sum(n_ss, A) * m;
+#undef NP
+#undef NF
+#undef NO
+}
+/* transport.py:655-679 calc_ageing_msa on the mineral nitrogen (:809-824) */
+static void nmin_ageing(int A, double *n)
+{
+    const double last = n[A - 1];
+    for (int j = A - 1; j >= 1; j--) n[j] = n[j - 1];
+    n[0] = 0;
+    n[A - 1] += last;
+}
+
 static void flux_age_statistics(int A, const double *tt, const double *ages, double *work, double *st5, double *avg);
 static void storage_age_statistics(int A, const double *sa, double m, const double *ages, double *work, const double *pcts, int np_, double *stp,
                                    double *avg);
@@ -579,6 +721,8 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
         }
         keep_tt(TTO(RSP_cpr_rz), tt, A);
     }
+    if (g_nit.params && g_nit.nmin_rz) /* settings.enable_nitrate: soil nitrogen cycle (transport.py:966-969) */
+        nitrogen_cycle_cell(A, C, i, s_rz, s_ss, ms_rz, ms_ss, F(RSF_transp), m, work);
     /* storage kernels */
     for (int j = 0; j < A; j++) s_rz[j] = (s_rz[j] < 1e-8) ? 0 : s_rz[j];
     for (int j = 0; j < A; j++) ms_rz[j] = (s_rz[j] <= 0) ? 0 : ms_rz[j];
@@ -639,6 +783,10 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
     }
     anion_ageing(A, s_rz, ms_rz);
     anion_ageing(A, s_ss, ms_ss);
+    if (g_nit.params && g_nit.nmin_rz) {
+        nmin_ageing(A, g_nit.nmin_rz + (size_t)i * A);
+        nmin_ageing(A, g_nit.nmin_ss + (size_t)i * A);
+    }
 #undef F
 #undef O
 #undef SP
@@ -1222,7 +1370,7 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
             const double m = mask[i];
             double *s_rz = sa_rz + (size_t)i * A, *s_ss = sa_ss + (size_t)i * A;
             double *ms_rz = msa_rz + (size_t)i * A, *ms_ss = msa_ss + (size_t)i * A;
-            if (st->solute == 1) {
+            if (st->solute == 1 || st->solute == 2) {
                 anion_day_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out, work, tmp, stats, balance_prev, ttk, ages);
                 continue;
             }

@@ -49,6 +49,10 @@ CASES = {
     # conservative anion (bromide): solute mass per age bin, partition coefficients, a crop cell whose uptake stops when wet
     "sas_bromide": dict(shape=(2, 3), ndays=26, ages=50, doy=100, solute="bromide", age_statistics=True,
                         sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
+    # nitrate: the anion transport plus the soil nitrogen cycle on age-ranked mineral nitrogen (nitrate.py), a nitrogen-fixing crop
+    # cell, a fertiliser pulse, wet cells above the denitrification threshold
+    "sas_nitrate": dict(shape=(2, 3), ndays=30, ages=50, doy=100, solute="nitrate",
+                        sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0))),
     # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
     "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
                          sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
@@ -93,7 +97,7 @@ def build(name):
         ciso = rng.uniform(-12, -5, (nx, ny, ndays + 1))
     ciso[:, :, 0] = np.nan
     case["C_ISO_IN"] = ciso
-    if c.get("solute") == "bromide":
+    if c.get("solute") in ("bromide", "nitrate"):
         # a bromide pulse dissolved in the rain of days 2..4 (mg/l), nothing afterwards
         cin = np.zeros((nx, ny, ndays + 1))
         wet = np.flatnonzero(case["PREC"][0, 0, 1:] > 0) + 1
@@ -107,7 +111,25 @@ def build(name):
         case["lu_id"] = lu
         case["S_sat_rz"] = np.full((nx, ny), 1e4)
         case["S_sat_rz"][0, 1] = case["S_RZ"][0, 1, 0] * 1.1  # ... close to saturation: uptake is switched off on wet days
-        case["solute"] = "bromide"
+        case["solute"] = c["solute"]
+    if c.get("solute") == "nitrate":
+        t = ndays + 1
+        case["TA"] = forcing["TA"][::144][:t].copy()
+        case["DOY"] = forcing["DOY"][::144][:t].astype(np.int64)
+        case["Z_ROOT"] = np.repeat(rng.uniform(300, 900, (nx, ny, 1)), t, axis=2)
+        lu_t = np.repeat(case["lu_id"][:, :, None], t, axis=2)
+        lu_t[1, 0, :] = 583  # a nitrogen-fixing crop (nitrate.py:339-343)
+        case["LU_ID"] = lu_t
+        case["NUP"] = rng.uniform(0.0, 80.0, (nx, ny, t))
+        case["z_soil"] = rng.uniform(1200, 2500, (nx, ny))
+        # storages close to the pore volume in some cells: denitrification needs S >= 0.7 S_sat, nitrification S < 0.9 S_sat
+        case["S_sat_rz"] = case["S_RZ"][:, :, 0] * rng.uniform(1.05, 1.6, (nx, ny))
+        case["S_sat_ss"] = case["S_SS"][:, :, 0] * rng.uniform(1.05, 1.6, (nx, ny))
+        for k, (lo, hi) in dict(kfix_rz=(10, 60), kmin_rz=(20, 120), kmin_ss=(5, 40), km_nit_rz=(5, 40), dmax_nit_rz=(20, 200), kngl_rz=(1, 20),
+                                km_denit_rz=(5, 40), dmax_denit_rz=(10, 150), km_denit_ss=(5, 40), dmax_denit_ss=(5, 60), damp_soil_temp=(12, 16)).items():
+            case[k] = rng.uniform(lo, hi, (nx, ny))
+        case["phi_soil_temp"] = np.full((nx, ny), 91.0)
+        case.update(C_rz0=30.0, C_ss0=15.0, NMIN_RZ0=60.0, NMIN_SS0=20.0)
     sas = {}
     for proc, tup in c["sas"].items():
         arr = np.zeros((nx, ny, 8))
@@ -123,8 +145,9 @@ SIMD_KEEP = ["sa_rz", "sa_ss", "C_rz", "C_iso_transp", "C_iso_q_ss"]
 
 def run(name, simd_out=None):
     case = build(name)
-    bromide = case.get("solute") == "bromide"
-    Setup = rh.make_bromide_setup(case) if bromide else rh.make_o18_setup(case)
+    nitrate = case.get("solute") == "nitrate"
+    bromide = case.get("solute") in ("bromide", "nitrate")
+    Setup = rh.make_nitrate_setup(case) if nitrate else (rh.make_bromide_setup(case) if bromide else rh.make_o18_setup(case))
     model = Setup()
     model.setup()
     model.warmup()
@@ -141,6 +164,10 @@ def run(name, simd_out=None):
         scal_vars = ["C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz", "C_inf_mat_rz", "C_inf_pf_rz", "C_inf_pf_ss", "C_in",
                      "M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_inf_mat_rz", "M_inf_pf_rz", "M_inf_pf_ss"]
         lvl_vars = ["C_rz", "C_ss", "C_s", "M_rz", "M_ss", "M_s"]
+    if nitrate:
+        age_vars = age_vars + ["Nmin_rz", "Nmin_ss"]
+        scal_vars = scal_vars + ["nit_s", "denit_s", "min_s", "ngas_s", "nfix_s", "nh4_up"]
+        lvl_vars = lvl_vars + ["Nmin_s", "temp_soil"]
     from roger_b200 import sas as _sas
 
     if case["age_statistics"]:
@@ -199,9 +226,19 @@ def run(name, simd_out=None):
     if case["sas_solver"] in ("Euler", "RK4"):
         out["solver"] = np.asarray({"Euler": 1, "RK4": 2}[case["sas_solver"]])
     if bromide:
-        out["solute"] = np.asarray(1)
+        out["solute"] = np.asarray(2 if nitrate else 1)
         for k in ("alpha_transp", "alpha_q", "lu_id"):
             out["par_" + k] = np.asarray(case[k], dtype=np.float64).reshape(C)
+    if nitrate:
+        for k in ("kfix_rz", "kmin_rz", "kmin_ss", "km_nit_rz", "dmax_nit_rz", "kngl_rz", "km_denit_rz", "dmax_denit_rz", "km_denit_ss",
+                  "dmax_denit_ss", "phi_soil_temp", "damp_soil_temp", "z_soil"):
+            out["par_" + k] = np.asarray(case[k], dtype=np.float64).reshape(C)
+        out["in_TA"] = case["TA"]
+        out["in_DOY"] = case["DOY"]
+        for k in ("Z_ROOT", "LU_ID", "NUP"):
+            out["in_" + k] = np.asarray(case[k], dtype=np.float64).reshape(C, -1)
+        for k in ("C_rz0", "C_ss0", "NMIN_RZ0", "NMIN_SS0"):
+            out["par_" + k] = np.asarray(case[k])
     for proc, arr in case["sas"].items():
         out["sas_" + proc] = arr.reshape(C, 8)
     for k in ("S_sat_rz", "S_sat_ss", "S_pwp_rz", "S_pwp_ss"):

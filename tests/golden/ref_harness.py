@@ -582,3 +582,78 @@ def make_bromide_setup(case):
             pass
 
     return BromideSetup
+
+
+def make_nitrate_setup(case):
+    """Offline nitrate StorAge-selection transport with the soil nitrogen cycle: the bromide setup above with
+    `settings.enable_nitrate` (transport.svat_transport_model_deterministic, roger/core/transport.py:948-991 -> nitrate.py) and the
+    nitrate-specific parameters, forcing and initial conditions of examples/plot_scale/svat_crop_nitrate_tutorial/svat_crop_nitrate.py
+    (:255-291 parameters, :337-415 initial mineral nitrogen and nitrate mass, :591-623 forcing incl. a fertiliser pulse).
+
+    case: everything make_bromide_setup takes plus TA (ndays + 1 daily air temperatures), DOY (ndays + 1), Z_ROOT, LU_ID, NUP
+    (nx, ny, ndays + 1), z_soil and the nitrate parameter planes (nx, ny): kfix_rz, kmin_rz, kmin_ss, km_nit_rz, dmax_nit_rz, kngl_rz,
+    km_denit_rz, dmax_denit_rz, km_denit_ss, dmax_denit_ss, phi_soil_temp, damp_soil_temp; C_rz0, C_ss0, NMIN_RZ0, NMIN_SS0 scalars."""
+    import_reference()
+    from roger import roger_routine
+    from roger.variables import allocate
+    from roger.core.operators import numpy as npx, update, at
+    import scipy.stats as sstx
+
+    Base = make_bromide_setup(case)
+    NIT = ("kfix_rz", "kmin_rz", "kmin_ss", "km_nit_rz", "dmax_nit_rz", "kngl_rz", "km_denit_rz", "dmax_denit_rz", "km_denit_ss",
+           "dmax_denit_ss", "phi_soil_temp", "damp_soil_temp", "z_soil")
+
+    class NitrateSetup(Base):
+        @roger_routine
+        def set_settings(self, state):
+            super().set_settings(state)
+            s = state.settings
+            s.identifier = "GOLDEN_NO3"
+            s.enable_bromide = False
+            s.enable_nitrate = True
+            s.nitt_forc = s.nitt
+
+        @roger_routine
+        def set_parameters_setup(self, state):
+            super().set_parameters_setup(state)
+            vs = state.variables
+            for k in NIT:
+                setattr(vs, k, update(getattr(vs, k), at[2:-2, 2:-2], case[k]))
+
+        @roger_routine
+        def set_initial_conditions(self, state):
+            super().set_initial_conditions(state)
+            vs = state.variables
+            settings = state.settings
+            vs.C_rz = update(vs.C_rz, at[2:-2, 2:-2, : vs.taup1], case["C_rz0"])
+            vs.C_ss = update(vs.C_ss, at[2:-2, 2:-2, : vs.taup1], case["C_ss0"])
+            p_dec = allocate(state.dimensions, ("x", "y", 2, "ages"))
+            p_dec = update(p_dec, at[:, :, : vs.taup1, :],
+                           sstx.expon.pdf(npx.linspace(sstx.expon.ppf(0.001), sstx.expon.ppf(0.999), settings.ages))[npx.newaxis, npx.newaxis, npx.newaxis, :])
+            vs.Nmin_rz = update(vs.Nmin_rz, at[2:-2, 2:-2, : vs.taup1, :], case["NMIN_RZ0"] * p_dec[2:-2, 2:-2, :, :] * settings.dx * settings.dy * 100)
+            vs.Nmin_ss = update(vs.Nmin_ss, at[2:-2, 2:-2, : vs.taup1, :], case["NMIN_SS0"] * p_dec[2:-2, 2:-2, :, :] * settings.dx * settings.dy * 100)
+            vs.msa_rz = update(vs.msa_rz, at[2:-2, 2:-2, : vs.taup1, :], vs.C_rz[2:-2, 2:-2, : vs.taup1, npx.newaxis] * vs.sa_rz[2:-2, 2:-2, : vs.taup1, :])
+            vs.msa_ss = update(vs.msa_ss, at[2:-2, 2:-2, : vs.taup1, :], vs.C_ss[2:-2, 2:-2, : vs.taup1, npx.newaxis] * vs.sa_ss[2:-2, 2:-2, : vs.taup1, :])
+            vs.msa_s = update(vs.msa_s, at[2:-2, 2:-2, :, :], vs.msa_rz[2:-2, 2:-2, :, :] + vs.msa_ss[2:-2, 2:-2, :, :])
+            vs.M_rz = update(vs.M_rz, at[2:-2, 2:-2, :], npx.sum(vs.msa_rz[2:-2, 2:-2, :, :], axis=-1))
+            vs.M_ss = update(vs.M_ss, at[2:-2, 2:-2, :], npx.sum(vs.msa_ss[2:-2, 2:-2, :, :], axis=-1))
+            vs.M_s = update(vs.M_s, at[2:-2, 2:-2, :], npx.sum(vs.msa_s[2:-2, 2:-2, :, :], axis=-1))
+
+        @roger_routine
+        def set_forcing_setup(self, state):
+            super().set_forcing_setup(state)
+            vs = state.variables
+            vs.TA = update(vs.TA, at[:], case["TA"])
+            vs.LU_ID = update(vs.LU_ID, at[2:-2, 2:-2, :], onp.asarray(case["LU_ID"]).astype(vs.LU_ID.dtype))
+
+        @roger_routine
+        def set_forcing(self, state):
+            super().set_forcing(state)
+            vs = state.variables
+            t = vs.itt
+            vs.ta = update(vs.ta, at[2:-2, 2:-2, vs.tau], vs.TA[t])
+            vs.doy = update(vs.doy, at[1], case["DOY"][t])
+            vs.z_root = update(vs.z_root, at[2:-2, 2:-2, vs.tau], case["Z_ROOT"][:, :, t])
+            vs.nup = update(vs.nup, at[2:-2, 2:-2], case["NUP"][:, :, t])
+
+    return NitrateSetup

@@ -1,0 +1,46 @@
+"""Pins the CPU oracle of the nitrate transport -- anion transport of the nitrate mass plus the soil nitrogen cycle on the
+age-ranked mineral nitrogen (roger/core/nitrate.py) -- against the reference's NumPy backend (tests/golden/sas_nitrate.npz,
+produced by tests/golden/make_sas_golden.py from the unmodified reference, settings.enable_nitrate): bit for bit."""
+import numpy as np
+
+from oracle.engine import OracleSasEngine, lib
+from roger_b200 import nitrate, sas
+from tests import util_sas as u
+
+
+def model_from_fixture(fx, engine_cls, engine_kwargs=None):
+    C, A = int(fx["nx"]) * int(fx["ny"]), int(fx["ages"])
+    daily = {k[3:]: fx[k] for k in fx if k.startswith("in_")}
+    spec = {p: fx["sas_" + p] for p in sas.PROCESSES}
+    params = {k: fx["par_" + k] for k in nitrate.PARAMS + ["phi_soil_temp", "damp_soil_temp"]}
+    anion = dict(alpha_transp=fx["par_alpha_transp"], alpha_q=fx["par_alpha_q"], lu_id=fx["par_lu_id"], S_sat_rz=fx["par_S_sat_rz"])
+    m = nitrate.NitrateModel(engine_cls, C, A, daily, spec, params, anion, nitt=int(fx["ndays"]) + 1, pi=3.14159265358979323846264338327950588, substeps=int(fx["substeps"]),
+                             store_tt=True, engine_kwargs=engine_kwargs)
+    m.setup()
+    for k, name in enumerate(nitrate.STATE):  # start from the reference's own post-setup state
+        m.engine.upload_state_index(k, fx["init_" + name])
+    # The soil temperature is a host-side NumPy expression with a sine and an exponential (nitrate.py:6-66): its last bit follows
+    # NumPy's SIMD dispatch (the fixture was generated with it switched off, see make_sas_golden.py).  The engine is pinned with
+    # the recorded temperatures; the host expression is checked against them to rounding.
+    m.temp_soil_given = np.concatenate([fx["rec_temp_soil"][:1], fx["rec_temp_soil"]])
+    return m
+
+
+def test_oracle_reproduces_reference_nitrate_bit_for_bit():
+    lib().sas_oracle_set_pow(0)
+    fx = u.load_case("sas_nitrate")
+    m = model_from_fixture(fx, OracleSasEngine)
+    for day in range(int(fx["ndays"])):
+        m.step()
+        assert u.rel_err(m.temp_soil_host, fx["rec_temp_soil"][day]) < 1e-14, f"day {day}: soil temperature (host expression)"
+        for name in nitrate.STATE:
+            assert u.same(m.state(name), fx["rec_" + name][day]), f"day {day}: {name} (max abs diff {np.nanmax(np.abs(m.state(name) - fx['rec_' + name][day]))})"
+        out = m.nitrate_outputs()
+        for k in ("nit_s", "denit_s", "min_s", "ngas_s", "nfix_s", "nh4_up", "Nmin_s"):
+            assert u.same(out[k], fx["rec_" + k][day]), f"day {day}: {k}: {out[k]} vs {fx['rec_' + k][day]}"
+        o = m.outputs()
+        for k in ("C_rz", "C_ss", "C_s", "C_transp", "C_q_ss"):
+            assert u.same(o[k], fx["rec_" + k][day]), f"day {day}: {k}"
+    # the fixture exercises every process: fixation on the crop cell, nitrification, denitrification, gaseous loss, uptake
+    for k in ("nit_s", "denit_s", "ngas_s", "nfix_s", "nh4_up", "min_s"):
+        assert np.nanmax(fx["rec_" + k]) > 0, k
