@@ -167,6 +167,24 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     anion_day<STATS>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev);
 }
 
+// One day of the nitrate transport: the anion day with the soil nitrogen cycle between the transport and the storage kernels
+__global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
+k_sas_day_nitrate(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
+                  const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap,
+                  NitrateParams np_) {
+    __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
+    __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
+    for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
+        s_log[k] = d_pow_log_tab[k];
+        s_exp[k] = d_pow_exp_tab[k];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.C) return;
+    CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    anion_day<false, true>(cx, forcing, mask[i], sas_params, ap, out, nullptr, nullptr, &np_);
+}
+
 // One day of the explicit Euler solver (`substeps` Euler steps, ageing with the last one), one thread per cell.
 #ifndef ROGER_EULER_BLOCK
 #define ROGER_EULER_BLOCK 256
@@ -312,7 +330,12 @@ struct roger_sas {
     int device = 0;
     roger_sas_settings st{};
     int base = 0;
-    double* d_state[4] = {nullptr, nullptr, nullptr, nullptr};  // sa_rz, sa_ss, msa_rz, msa_ss
+    double* d_state[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // sa_rz, sa_ss, msa_rz, msa_ss (nitrate: Nmin_rz, Nmin_ss)
+    double* d_nit_params = nullptr;   // RNP_COUNT planes
+    double* d_nit_forcing = nullptr;  // RNF_COUNT planes of the day
+    double* d_nit_out = nullptr;      // RNO_COUNT planes
+    double nit_dx = 1, nit_dy = 1, nit_zmax = 0.7, nit_dt = 24;
+    bool have_nit_params = false, have_nit_forcing = false;
     double* d_san = nullptr;
     double* d_TTn = nullptr;
     double* d_tt = nullptr;
@@ -344,6 +367,7 @@ struct roger_sas {
         Planes pl;
         pl.sa[0] = d_state[0]; pl.sa[1] = d_state[1]; pl.msa[0] = d_state[2]; pl.msa[1] = d_state[3];
         pl.san = d_san; pl.TTn = d_TTn; pl.tt = d_tt;
+        pl.nmin[0] = d_state[4]; pl.nmin[1] = d_state[5];
         return pl;
     }
 };
@@ -386,7 +410,9 @@ extern "C" {
 int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings* settings, int device) {
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_sas_create: bad argument");
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
-    if (settings->solute != 0 && settings->solute != 1) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope) or 1 (anion)");
+    if (settings->solute < 0 || settings->solute > 2) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope), 1 (anion) or 2 (nitrate)");
+    if (settings->solute == 2 && (settings->solver != 0 || settings->age_statistics))
+        return fail(ROGER_ENOTSUP, "roger_sas_create: nitrate runs with the deterministic solver and without age statistics");
     if (settings->solver != 0 && settings->solver != 1) return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic) or 1 (Euler)");
     if (settings->solver == 1 && settings->solute != 0 && settings->age_statistics)
         return fail(ROGER_ENOTSUP, "roger_sas_create: the anion branch of the explicit Euler solver runs without age statistics");
@@ -405,9 +431,15 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     h->st = *settings;
     const size_t arr = sizeof(double) * (size_t)n_cells * (size_t)settings->ages;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < (settings->solute == 2 ? 6 : 4); k++) {
         CU(cudaMalloc(&h->d_state[k], arr));
         CU(cudaMemsetAsync(h->d_state[k], 0, arr, h->stream));
+    }
+    if (settings->solute == 2) {
+        CU(cudaMalloc(&h->d_nit_params, sizeof(double) * RNP_COUNT * (size_t)n_cells));
+        CU(cudaMalloc(&h->d_nit_forcing, sizeof(double) * RNF_COUNT * (size_t)n_cells));
+        CU(cudaMalloc(&h->d_nit_out, sizeof(double) * RNO_COUNT * (size_t)n_cells));
+        CU(cudaMemsetAsync(h->d_nit_out, 0, sizeof(double) * RNO_COUNT * (size_t)n_cells, h->stream));
     }
     // the scratch arrays carry a few planes of padding: the sub-step pass prefetches ROGER_SAS_UNROLL bins ahead unguarded
     static_assert(2 * ROGER_SAS_UNROLL <= 8, "the scratch padding below covers a look-ahead of 2 * ROGER_SAS_UNROLL planes");
@@ -452,6 +484,7 @@ void roger_sas_destroy(roger_sas* h) {
     cudaStreamSynchronize(h->stream);
     for (auto p : h->d_state) cudaFree(p);
     cudaFree(h->d_stats); cudaFree(h->d_C_s_prev); cudaFree(h->d_bounds); cudaFree(h->d_anion);
+    cudaFree(h->d_nit_params); cudaFree(h->d_nit_forcing); cudaFree(h->d_nit_out);
     cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_params); cudaFree(h->d_stage); cudaFree(h->d_plan);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -460,19 +493,19 @@ void roger_sas_destroy(roger_sas* h) {
 }
 
 int roger_sas_upload_state(roger_sas* h, int which, const double* host) {
-    if (!h || !host || which < 0 || which > 3) return fail(ROGER_EINVAL, "roger_sas_upload_state: bad argument");
+    if (!h || !host || which < 0 || which > 5 || !h->d_state[which]) return fail(ROGER_EINVAL, "roger_sas_upload_state: bad argument");
     CU(cudaSetDevice(h->device));
     return transfer_state(h, h->d_state[which], h->base, const_cast<double*>(host), true);
 }
 
 int roger_sas_download_state(roger_sas* h, int which, double* host) {
-    if (!h || !host || which < 0 || which > 3) return fail(ROGER_EINVAL, "roger_sas_download_state: bad argument");
+    if (!h || !host || which < 0 || which > 5 || !h->d_state[which]) return fail(ROGER_EINVAL, "roger_sas_download_state: bad argument");
     CU(cudaSetDevice(h->device));
     return transfer_state(h, h->d_state[which], h->base, host, false);
 }
 
 uint64_t roger_sas_state_ptr(roger_sas* h, int which) {
-    if (!h || which < 0 || which > 3) return 0;
+    if (!h || which < 0 || which > 5) return 0;
     return (uint64_t)(uintptr_t)h->d_state[which];
 }
 
@@ -536,6 +569,14 @@ static int step_common(roger_sas* h, const double* d_forcing) {
         else
             k_sas_day_euler<false><<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
                                                                             h->d_out, nullptr, nullptr, nullptr, 0.0, 0.0);
+    } else if (h->st.solute == 2) {
+        if (!h->have_nit_params || !h->have_nit_forcing)
+            return fail(ROGER_EINVAL, "roger_sas_step: nitrate needs roger_sas_set_nitrate_parameters and the day's roger_sas_set_nitrate_forcing");
+        AnionParams ap{nullptr, nullptr, nullptr, nullptr};
+        if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
+        NitrateParams np_{h->d_nit_params, h->d_nit_forcing, h->d_nit_out, h->nit_dx, h->nit_dy, h->nit_zmax, h->nit_dt};
+        k_sas_day_nitrate<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out, ap, np_);
+        h->have_nit_forcing = false;
     } else if (h->st.solute == 1) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
@@ -573,6 +614,36 @@ int roger_sas_step_device(roger_sas* h, uint64_t forcing) {
     if (!h || !forcing) return fail(ROGER_EINVAL, "roger_sas_step_device: bad argument");
     CU(cudaSetDevice(h->device));
     return step_common(h, (const double*)(uintptr_t)forcing);
+}
+
+int roger_sas_set_nitrate_parameters(roger_sas* h, const double* params, double dx, double dy, double zroot_to_zsoil_max, double dt_hours) {
+    if (!h || !params) return fail(ROGER_EINVAL, "roger_sas_set_nitrate_parameters: bad argument");
+    if (h->st.solute != 2) return fail(ROGER_EINVAL, "roger_sas_set_nitrate_parameters: handle was not created with settings.solute = 2");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->d_nit_params, params, sizeof(double) * RNP_COUNT * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->nit_dx = dx; h->nit_dy = dy; h->nit_zmax = zroot_to_zsoil_max; h->nit_dt = dt_hours;
+    h->have_nit_params = true;
+    return 0;
+}
+
+int roger_sas_set_nitrate_forcing(roger_sas* h, const double* planes) {
+    if (!h || !planes) return fail(ROGER_EINVAL, "roger_sas_set_nitrate_forcing: bad argument");
+    if (h->st.solute != 2) return fail(ROGER_EINVAL, "roger_sas_set_nitrate_forcing: handle was not created with settings.solute = 2");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->d_nit_forcing, planes, sizeof(double) * RNF_COUNT * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_nit_forcing = true;
+    return 0;
+}
+
+int roger_sas_download_nitrate_outputs(roger_sas* h, double* host) {
+    if (!h || !host) return fail(ROGER_EINVAL, "roger_sas_download_nitrate_outputs: bad argument");
+    if (h->st.solute != 2) return fail(ROGER_EINVAL, "roger_sas_download_nitrate_outputs: handle was not created with settings.solute = 2");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(host, h->d_nit_out, sizeof(double) * RNO_COUNT * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 int roger_sas_download_outputs(roger_sas* h, double* host) {

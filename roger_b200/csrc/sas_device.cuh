@@ -53,6 +53,7 @@ struct Planes {  // age-major arrays
     double* san;     // scratch: StorAge inside the sub-step loop
     double* TTn;     // scratch: accumulated cumulative travel-time distribution (index j holds TTn[j + 1])
     double* tt;      // optional: RSP_COUNT x A x C
+    double* nmin[2]; // nitrate only: age-ranked mineral nitrogen of the root zone / subsoil (same ring as sa / msa)
 };
 
 // walks age bins 0..A-1 of one cell through the plane ring
@@ -819,9 +820,176 @@ struct AnionParams {  // per-cell planes (may be null: alpha = 1, no crops)
     const double* S_sat_rz;
 };
 
-template <bool STATS>
+// ================================================================================================================
+// Nitrate (settings.solute = 2): the soil nitrogen cycle on the age-ranked arrays, roger/core/nitrate.py:500-696
+// calc_nitrogen_cycle_kernel with its process kernels (:68-173 denitrification, :176-257 nitrification, :260-302
+// mineralisation, :305-346 fixation, :349-427 gaseous loss, :430-467 ammonium uptake), called between the capillary rise and
+// the storage kernels of the anion day (transport.py:966-969).  Sums over the age axis are NumPy pairwise sums
+// (stream_sums), the reversed cumulative sum of the denitrification is walked from the oldest bin down.  `msa_rz += ma_rz`
+// is applied in the nitrification pass already: nothing reads msa_rz between the two statements of the reference.
+// ================================================================================================================
+struct NitrateParams {
+    const double* params;   // RNP_COUNT planes
+    const double* forcing;  // RNF_COUNT planes of the day
+    double* out;            // RNO_COUNT planes
+    double dx, dy, zmax, dt;
+};
+
+__device__ __forceinline__ double temp_coeff(double T, double lo, double m) {
+    double c = (((T >= lo) && (T <= 30)) ? T / (30 - lo) : 0) * m;
+    c = ((T > 30) ? 1 : c) * m;
+    return c;
+}
+// r = (wsum > 0) ? (w / wsum) * pot : 0, limited to nmin and to >= 0, each statement "* maskCatch"
+__device__ __forceinline__ double distribute(double w, double wsum, double pot, double nmin, double m) {
+    double v = ((wsum > 0) ? ((w / wsum) * pot) : 0.0) * m;
+    v = ((v > nmin) ? nmin : v) * m;
+    v = ((v < 0) ? 0 : v) * m;
+    return v;
+}
+// denitrification of one layer (nitrate.py:68-173): the oldest solute is removed first; mr is left in `scratch` (unrotated)
+__device__ __noinline__ void denit_layer(const CellCtx& cx, int layer, double msum, double Ssum, double km, double Dmax, double S_sat, double T,
+                                         double m, const NitrateParams& np_, double* __restrict__ scratch) {
+    const int A = cx.P.A;
+    double* __restrict__ msa = cx.pl.msa[layer];
+    const double S = Ssum * m;
+    const double coeff = temp_coeff(T, 5, m);
+    const double ms = msum * m;
+    const double dt = np_.dt, dx = np_.dx, dy = np_.dy;
+    double mr_pot = (Dmax * (dt / (365 * 24)) * dx * dy * 100 * (ms / (km * (dt / (365 * 24)) * dx * dy * 100 + ms))) * coeff * m;
+    mr_pot = ((S >= 0.7 * S_sat) ? mr_pot : 0) * m;
+    double acc = 0;
+    for (int j = A - 1; j >= 0; j--) {
+        const int64_t o = cx.ring(j);
+        const double v = msa[o];
+        acc = (j == A - 1) ? v : acc + v;
+        double t = ((acc * m < mr_pot) ? 0 : v) * m;
+        if (j == A - 1) t += -((t >= mr_pot) ? mr_pot : 0) * m;
+        double mra = (v * m - t) * m;
+        mra = ((mra < 0) ? 0 : mra) * m;
+        const double mr = mra * m;
+        msa[o] = v + -mr;
+        scratch[cx.lin(j)] = mr;
+    }
+}
+
+__device__ __noinline__ void nitrogen_cycle(const CellCtx& cx, const NitrateParams& np_, double transp, double m) {
+    const SasParams& P = cx.P;
+    const int64_t C = P.C, i = cx.i;
+    double* __restrict__ s_rz = cx.pl.sa[0];
+    double* __restrict__ s_ss = cx.pl.sa[1];
+    double* __restrict__ m_rz = cx.pl.msa[0];
+    double* __restrict__ m_ss = cx.pl.msa[1];
+    double* __restrict__ n_rz = cx.pl.nmin[0];
+    double* __restrict__ n_ss = cx.pl.nmin[1];
+#define NP(k) np_.params[(int64_t)(k) * C + i]
+#define NF(k) np_.forcing[(int64_t)(k) * C + i]
+#define NO(k) np_.out[(int64_t)(k) * C + i]
+    const double T = NF(RNF_temp_soil), z_root = NF(RNF_z_root), z_soil = NP(RNP_z_soil), lu = NF(RNF_lu_id);
+    const double dt = np_.dt, dx = np_.dx, dy = np_.dy;
+    double nfix = NP(RNP_kfix_rz) * (dt / (365 * 24)) * dx * dy * 100 * temp_coeff(T, 0, m) * (z_root / (np_.zmax * z_soil)) * m;
+    {
+        const bool fixer = lu == 541 || lu == 577 || lu == 578 || lu == 580 || lu == 581 || lu == 583 || lu == 584 || lu == 586 ||
+                           lu == 587 || lu == 588;
+        nfix = fixer ? nfix : 0;
+    }
+    nfix = nfix * m;
+    NO(RNO_nfix_s) = nfix;
+    const double min_rz = (NP(RNP_kmin_rz) * (dt / (365 * 24)) * dx * dy * 100 * temp_coeff(T, 0, m) * m) * m;
+    const double min_ss = (NP(RNP_kmin_ss) * (dt / (365 * 24)) * dx * dy * 100 * temp_coeff(T, 0, m) * m) * m;
+    NO(RNO_min_s) = min_rz + min_ss;
+    {
+        const int64_t o0 = cx.ring(0);
+        double v = n_rz[o0];
+        v += nfix;
+        v += min_rz * m;
+        n_rz[o0] = v;
+        n_ss[o0] = n_ss[o0] + min_ss * m;
+    }
+    // sums the processes start from
+    double s0[2];
+    stream_sums<2, 2>(cx.plan,
+        [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = s_rz[o]; L[1] = n_rz[o]; },
+        [&](int, const double* L, double* v) { v[0] = L[0]; v[1] = L[1]; }, s0);
+    const double Ssum = s0[0], S = Ssum * m;
+    const double S_sat_rz = NP(RNP_S_sat_rz);
+    // nitrification of the root zone (+ msa_rz += ma_rz)
+    double sB[3];
+    {
+        const double nsum = s0[1];
+        double pot = (NP(RNP_dmax_nit_rz) * (dt / (365 * 24)) * dx * dy * 100 *
+                      (nsum / (NP(RNP_km_nit_rz) * (dt / (365 * 24)) * dx * dy * 100 + nsum))) * temp_coeff(T, 1, m) * m;
+        pot = ((S < 0.9 * S_sat_rz) ? pot : 0) * m;
+        stream_sums<3, 3>(cx.plan,
+            [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = s_rz[o]; L[1] = n_rz[o]; L[2] = m_rz[o]; },
+            [&](int j, const double* L, double* v) {
+                const int64_t o = cx.ring(j);
+                const double ma = distribute(L[0], Ssum, pot, L[1], m) * m;
+                const double nn = L[1] + -ma;
+                const double mm = L[2] + ma;
+                n_rz[o] = nn;
+                m_rz[o] = mm;
+                v[0] = ma + 0.0;  // ma_s = ma_rz + ma_ss, and vs.ma_ss is never written by the reference (0)
+                v[1] = nn;
+                v[2] = mm;
+            }, sB);
+    }
+    NO(RNO_nit_s) = sB[0];
+    // gaseous loss of ammonium
+    double sC[2];
+    {
+        double pot = (NP(RNP_kngl_rz) * (dt / (365 * 24)) * dx * dy * 100) * temp_coeff(T, 5, m) * m;
+        pot = ((S < 0.9 * S_sat_rz) ? pot : 0) * m;
+        const double nsum = sB[1];
+        stream_sums<2, 1>(cx.plan,
+            [&](int j, double* L) { L[0] = n_rz[cx.ring(j)]; },
+            [&](int j, const double* L, double* v) {
+                const double r = distribute(L[0], nsum, pot, L[0], m);
+                const double nn = L[0] + -r * m;
+                n_rz[cx.ring(j)] = nn;
+                v[0] = r;
+                v[1] = nn;
+            }, sC);
+    }
+    NO(RNO_ngas_s) = sC[0];
+    // ammonium uptake by plants
+    double sD[2];
+    {
+        const double pot = ((transp > 0) ? NF(RNF_nup) * (z_root / (z_soil * np_.zmax)) : 0) * m;
+        const double nsum = sC[1];
+        stream_sums<2, 1>(cx.plan,
+            [&](int j, double* L) { L[0] = n_rz[cx.ring(j)]; },
+            [&](int j, const double* L, double* v) {
+                const double r = distribute(L[0], nsum, pot, L[0], m);
+                const double nn = L[0] + -r * m;
+                n_rz[cx.ring(j)] = nn;
+                v[0] = r;
+                v[1] = nn;
+            }, sD);
+    }
+    NO(RNO_nh4_up) = sD[0] * m;
+    // denitrification of both layers; the subsoil's sums first
+    double sF[3];
+    stream_sums<3, 3>(cx.plan,
+        [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = s_ss[o]; L[1] = m_ss[o]; L[2] = n_ss[o]; },
+        [&](int, const double* L, double* v) { v[0] = L[0]; v[1] = L[1]; v[2] = L[2]; }, sF);
+    denit_layer(cx, 0, sB[2], Ssum, NP(RNP_km_denit_rz), NP(RNP_dmax_denit_rz), S_sat_rz, T, m, np_, cx.pl.san);
+    denit_layer(cx, 1, sF[1], sF[0], NP(RNP_km_denit_ss), NP(RNP_dmax_denit_ss), NP(RNP_S_sat_ss), T, m, np_, cx.pl.TTn);
+    double sH[1];
+    stream_sums<1, 2>(cx.plan,
+        [&](int j, double* L) { const int64_t o = cx.lin(j); L[0] = cx.pl.san[o]; L[1] = cx.pl.TTn[o]; },
+        [&](int, const double* L, double* v) { v[0] = L[0] + L[1]; }, sH);
+    NO(RNO_denit_s) = sH[0];
+    NO(RNO_Nmin_s) = sD[1] + sF[2] * m;
+#undef NP
+#undef NF
+#undef NO
+}
+
+template <bool STATS, bool NITRATE = false>
 __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
-                                          const AnionParams ap, double* __restrict__ out, double* __restrict__ stats, double* __restrict__ C_s_prev) {
+                                          const AnionParams ap, double* __restrict__ out, double* __restrict__ stats, double* __restrict__ C_s_prev,
+                                          const NitrateParams* nitrate = nullptr) {
     const SasParams& P = cx.P;
     const int A = P.A;
     const int64_t C = P.C, i = cx.i;
@@ -894,6 +1062,7 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
         O(RSO_C_cpr_rz) = ((F(RSF_cpr_rz) > 0) ? M / F(RSF_cpr_rz) : 0) * m;
         O(RSO_C_iso_cpr_rz) = M * m;
     }
+    if (NITRATE) nitrogen_cycle(cx, *nitrate, F(RSF_transp), m);  // transport.py:966-969
     {   // storage kernels (root_zone.py:219-261, subsoil.py anion, soil.py anion): clip, solute of empty bins removed, masses
         double sums[6];
         stream_sums<6, 4>(cx.plan,
@@ -962,6 +1131,11 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
             msa[(int64_t)b_last * C + i] = msa[(int64_t)b_last * C + i] + msa[(int64_t)b_new * C + i];
             sa[(int64_t)b_new * C + i] = 0;
             msa[(int64_t)b_new * C + i] = 0;
+            if (NITRATE) {  // transport.py:809-824: the mineral nitrogen ages like the solute mass
+                double* __restrict__ nm = cx.pl.nmin[L];
+                nm[(int64_t)b_last * C + i] = nm[(int64_t)b_last * C + i] + nm[(int64_t)b_new * C + i];
+                nm[(int64_t)b_new * C + i] = 0;
+            }
         }
     }
 #undef F

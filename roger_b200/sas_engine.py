@@ -34,6 +34,9 @@ def _bind(lib):
     lib.roger_sas_set_balance_reference.argtypes = [hp, dp]
     lib.roger_sas_set_sanity_bounds.argtypes = [hp, dp, dp, dp, dp, C.c_double, C.c_double]
     lib.roger_sas_set_anion_parameters.argtypes = [hp, dp, dp, dp, dp]
+    lib.roger_sas_set_nitrate_parameters.argtypes = [hp, dp, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.roger_sas_set_nitrate_forcing.argtypes = [hp, dp]
+    lib.roger_sas_download_nitrate_outputs.argtypes = [hp, dp]
     lib.roger_sas_synchronize.argtypes = [hp]
     lib.roger_sas_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
     _bound = True
@@ -139,6 +142,33 @@ class CudaSasEngine:
         if any(a.size != self.n for a in arrs):
             raise ValueError("set_anion_parameters: n_cells values expected")
         _check(self.lib, self.lib.roger_sas_set_anion_parameters(self.h, *[self._dp(a) for a in arrs]))
+
+    # ---- nitrate (settings.solute = 2): roger_b200.nitrate.NitrateModel drives these
+    def set_nitrate_parameters(self, params, dx, dy, zroot_to_zsoil_max, dt_hours):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        if p.shape != (13, self.n):
+            raise ValueError("set_nitrate_parameters: (13, n_cells) planes expected")
+        _check(self.lib, self.lib.roger_sas_set_nitrate_parameters(self.h, self._dp(p), float(dx), float(dy), float(zroot_to_zsoil_max), float(dt_hours)))
+
+    def set_nitrate_forcing(self, planes):
+        p = np.ascontiguousarray(planes, dtype=np.float64)
+        if p.shape != (4, self.n):
+            raise ValueError("set_nitrate_forcing: (4, n_cells) planes expected")
+        _check(self.lib, self.lib.roger_sas_set_nitrate_forcing(self.h, self._dp(p)))
+
+    def download_nitrate_outputs(self):
+        out = np.empty((7, self.n))
+        _check(self.lib, self.lib.roger_sas_download_nitrate_outputs(self.h, self._dp(out)))
+        return out
+
+    def upload_state_index(self, which, arr):
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64).reshape(self.n, self.A))
+        _check(self.lib, self.lib.roger_sas_upload_state(self.h, int(which), self._dp(a)))
+
+    def download_state_index(self, which):
+        out = np.empty((self.n, self.A))
+        _check(self.lib, self.lib.roger_sas_download_state(self.h, int(which), self._dp(out)))
+        return out
 
     def download_tt(self, process):
         out = np.empty((self.n, self.A))

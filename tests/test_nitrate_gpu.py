@@ -1,0 +1,105 @@
+"""GPU parity of the nitrate transport (k_sas_day_nitrate: anion transport + soil nitrogen cycle, through the C ABI): bit for bit
+against the CPU oracle evaluating the same pow, and against the reference fixture."""
+import numpy as np
+import pytest
+
+from tests import util_sas as u
+from tests.test_nitrate_oracle_golden import model_from_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    from roger_b200.sas_engine import CudaSasEngine
+
+    return CudaSasEngine
+
+
+@pytest.fixture
+def oracle_roger_pow():
+    from oracle.engine import OracleSasEngine, lib
+
+    lib().sas_oracle_set_pow(1)
+    yield OracleSasEngine
+    lib().sas_oracle_set_pow(0)
+
+
+def _compare(a, b, day, exact=True, tol=None):
+    from roger_b200 import nitrate
+
+    for name in nitrate.STATE:
+        x, y = a.state(name), b.state(name) if not isinstance(b, dict) else b[name]
+        if exact:
+            assert u.same(x, y), f"day {day}: {name} (max abs diff {np.nanmax(np.abs(x - y))})"
+        else:
+            assert u.rel_err(x, y) <= tol, (day, name, u.rel_err(x, y))
+    oa = dict(a.nitrate_outputs(), **a.outputs())
+    ob = dict(b.nitrate_outputs(), **b.outputs()) if not isinstance(b, dict) else b
+    for k in ("nit_s", "denit_s", "min_s", "ngas_s", "nfix_s", "nh4_up", "Nmin_s", "C_rz", "C_ss", "C_s", "C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz"):
+        if k not in ob:
+            continue
+        if exact:
+            assert u.same(oa[k], ob[k]), f"day {day}: {k}: {oa[k]} vs {ob[k]}"
+        else:
+            assert u.rel_err(oa[k], ob[k]) <= tol, (day, k, u.rel_err(oa[k], ob[k]))
+
+
+def test_cuda_equals_oracle_bit_for_bit_on_fixture_inputs(oracle_roger_pow):
+    fx = u.load_case("sas_nitrate")
+    a, b = model_from_fixture(fx, _cuda()), model_from_fixture(fx, oracle_roger_pow)
+    for day in range(int(fx["ndays"])):
+        a.step()
+        b.step()
+        _compare(a, b, day)
+
+
+def test_cuda_against_reference_fixture():
+    """the same run against the reference's own numbers (libm pow there, roger_pow here): 1e-10 over the first days, the
+    reference's libm envelope afterwards (tests/test_sas_gpu.py explains the power-law sensitivity)"""
+    fx = u.load_case("sas_nitrate")
+    a = model_from_fixture(fx, _cuda())
+    for day in range(int(fx["ndays"])):
+        a.step()
+        ref = {k[4:]: fx[k][day] for k in fx if k.startswith("rec_")}
+        _compare(a, ref, day, exact=False, tol=1e-10 if day < 5 else 1e-5)
+
+
+@pytest.mark.parametrize("C_,A,ndays", [(300, 96, 10), (65, 513, 4), (1, 5, 6)])
+def test_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, oracle_roger_pow):
+    from roger_b200 import nitrate, sas
+
+    rng = np.random.default_rng(100 + C_)
+    t = ndays + 1
+    wet = rng.random((C_, t)) < 0.4
+    prec = np.where(wet, rng.gamma(0.8, 6.0, (C_, t)), 0.0)
+    daily = {
+        "PREC": prec, "INF_MAT_RZ": prec * rng.uniform(0.5, 0.8, (C_, t)), "INF_PF_RZ": prec * rng.uniform(0.0, 0.15, (C_, t)),
+        "INF_PF_SS": prec * rng.uniform(0.0, 0.1, (C_, t)), "EVAP_SOIL": rng.uniform(0, 1.5, (C_, t)), "TRANSP": rng.uniform(0, 3.0, (C_, t)) * (rng.random((C_, t)) < 0.8),
+        "Q_RZ": rng.gamma(0.5, 2.0, (C_, t)), "Q_SS": rng.gamma(0.5, 1.5, (C_, t)), "CPR_RZ": rng.uniform(0, 0.5, (C_, t)) * (rng.random((C_, t)) < 0.4),
+        "S_RZ": np.repeat(rng.uniform(40, 160, (C_, 1)), t, axis=1), "S_SS": np.repeat(rng.uniform(150, 700, (C_, 1)), t, axis=1),
+        "S_SNOW": np.zeros((C_, t)), "C_IN": rng.uniform(0, 60, (C_, t)) * (rng.random((C_, t)) < 0.2),
+        "TA": rng.uniform(-5, 28, t), "DOY": np.arange(100, 100 + t), "Z_ROOT": rng.uniform(200, 900, (C_, t)),
+        "LU_ID": rng.choice([8.0, 525.0, 583.0, 541.0], (C_, t)), "NUP": rng.uniform(0, 80, (C_, t)),
+    }
+    spec = dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0))
+    params = {k: rng.uniform(lo, hi, C_) for k, (lo, hi) in dict(
+        kfix_rz=(10, 60), kmin_rz=(20, 120), kmin_ss=(5, 40), km_nit_rz=(5, 40), dmax_nit_rz=(20, 200), kngl_rz=(1, 20), km_denit_rz=(5, 40),
+        dmax_denit_rz=(10, 150), km_denit_ss=(5, 40), dmax_denit_ss=(5, 60), z_soil=(1200, 2500), damp_soil_temp=(12, 16)).items()}
+    params["phi_soil_temp"] = np.full(C_, 91.0)
+    params["S_sat_rz"] = daily["S_RZ"][:, 0] * rng.uniform(1.02, 1.7, C_)
+    params["S_sat_ss"] = daily["S_SS"][:, 0] * rng.uniform(1.02, 1.7, C_)
+    anion = dict(alpha_transp=rng.uniform(0.2, 0.9, C_), alpha_q=rng.uniform(0.4, 1.0, C_), lu_id=daily["LU_ID"][:, 0], S_sat_rz=params["S_sat_rz"])
+    mask = (rng.random(C_) > 0.05).astype(np.float64)
+    models = []
+    for eng in (_cuda(), oracle_roger_pow):
+        m = nitrate.NitrateModel(eng, C_, A, daily, spec, params, anion, nitt=t, mask=mask)
+        m.setup()
+        sa_rz, sa_ss = sas.initial_age_distribution(daily["S_RZ"][:, 0], A), sas.initial_age_distribution(daily["S_SS"][:, 0], A)
+        decay = np.exp(-np.linspace(0.001, 7, A))[None, :]
+        for k, arr in enumerate([sa_rz, sa_ss, 30.0 * sa_rz, 15.0 * sa_ss, 600.0 * decay * np.ones((C_, 1)), 200.0 * decay * np.ones((C_, 1))]):
+            m.engine.upload_state_index(k, arr)
+        models.append(m)
+    for day in range(ndays):
+        for m in models:
+            m.step()
+        _compare(models[0], models[1], day)
