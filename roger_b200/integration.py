@@ -485,13 +485,20 @@ class CudaTransportDriver:
         self.state = setup.state
         vs, st = self.state.variables, self.state.settings
         iso18, iso2 = bool(getattr(st, "enable_oxygen18", False)), bool(getattr(st, "enable_deuterium", False))
-        self.anion = bool(getattr(st, "enable_bromide", False)) or bool(getattr(st, "enable_chloride", False))
+        self.nitrate = bool(getattr(st, "enable_nitrate", False))
+        self.anion = bool(getattr(st, "enable_bromide", False)) or bool(getattr(st, "enable_chloride", False)) or self.nitrate
         if not getattr(st, "enable_offline_transport", False) or not (iso18 or iso2 or self.anion):
-            raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium / bromide / chloride transport models")
+            raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium / bromide / chloride / nitrate transport models")
         solver = getattr(st, "sas_solver", None)
         if solver not in ("deterministic", "Euler"):
             raise NotImplementedError("sas_solver = 'deterministic' and 'Euler' run on the device (DESIGN.md section 7)")
         self.euler = solver == "Euler"
+        if self.nitrate:
+            if self.euler or bool(getattr(st, "enable_age_statistics", False)):
+                raise NotImplementedError("nitrate runs with the deterministic solver and without age statistics")
+            for flag in ("enable_crop_phenology", "enable_crop_rotation", "enable_groundwater", "enable_groundwater_boundary"):
+                if getattr(st, flag, False):  # svat_crop_transport_model_deterministic: redistribution after root growth / harvesting
+                    raise NotImplementedError(f"nitrate transport with settings.{flag} is outside the CUDA hot path (DESIGN.md section 7)")
         if self.euler and self.anion and bool(getattr(st, "enable_age_statistics", False)):
             raise NotImplementedError("the anion branch of the explicit Euler solver runs without age statistics")
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
@@ -501,7 +508,7 @@ class CudaTransportDriver:
         # deuterium runs the same kernels with its own standard ratio and plausibility window (transport.py:315-340)
         vsmow, dmin, dmax = (st.VSMOW_conc2H, st.d2H_min, st.d2H_max) if iso2 else (st.VSMOW_conc18O, st.d18O_min, st.d18O_max)
         s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats),
-                            sas.ANION if self.anion else sas.ISOTOPE, sas.EULER if self.euler else sas.DETERMINISTIC)
+                            2 if self.nitrate else (sas.ANION if self.anion else sas.ISOTOPE), sas.EULER if self.euler else sas.DETERMINISTIC)
         self.settings = s
         self.engine = engine_cls(self.C, s, **(engine_kwargs or {}))
         tau = int(vs.tau)
@@ -513,6 +520,15 @@ class CudaTransportDriver:
             self.engine.set_anion_parameters(inner("alpha_transp"), inner("alpha_q"), inner("lu_id"), inner("S_sat_rz"))
         for name in sas.STATE:
             self.engine.upload_state(name, np.asarray(getattr(vs, name))[2:-2, 2:-2, tau, :].reshape(self.C, self.A))
+        if self.nitrate:
+            from . import nitrate as nit
+
+            self.nit = nit
+            inner = lambda n: np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64)  # noqa: E731
+            self.engine.set_nitrate_parameters(np.stack([inner(k) for k in nit.PARAMS]), float(st.dx), float(st.dy),
+                                               float(st.zroot_to_zsoil_max), float(np.asarray(vs.dt)))
+            for k, name in enumerate(("Nmin_rz", "Nmin_ss")):
+                self.engine.upload_state_index(4 + k, np.asarray(getattr(vs, name))[2:-2, 2:-2, tau, :].reshape(self.C, self.A))
         if self.stats:
             self.engine.set_balance_reference(np.asarray(vs.C_s)[2:-2, 2:-2, int(vs.taum1)].reshape(-1))
 
@@ -547,6 +563,16 @@ class CudaTransportDriver:
             if int(vs.time) % (24 * 60 * 60) != 0:
                 raise NotImplementedError("Euler steps that do not add up to whole days (the device ages the StorAge once per call)")
         f = np.stack([np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64) for n in self._FORCING])
+        if self.nitrate:  # nitrate.calculate_nitrogen_cycle, first half (nitrate.py:717-731): the soil temperature, on the host
+            nit, st = self.nit, state.settings
+            inner = lambda n: np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64)  # noqa: E731
+            tau = int(vs.tau)
+            S_s = np.asarray(vs.S_s)[2:-2, 2:-2, tau].reshape(-1).astype(np.float64)
+            temp = nit.soil_temperature(np.asarray(vs.TA), int(vs.itt), int(st.nitt), float(vs.doy[1]), inner("phi_soil_temp"), inner("damp_soil_temp"),
+                                        inner("z_soil"), S_s, inner("S_sat_rz"), inner("S_sat_ss"), inner("maskCatch"), float(st.pi))
+            z_root = np.asarray(vs.z_root)[2:-2, 2:-2, tau].reshape(-1).astype(np.float64)
+            lu = np.asarray(vs.LU_ID)[2:-2, 2:-2, int(vs.itt)].reshape(-1).astype(np.float64)
+            self.engine.set_nitrate_forcing(np.stack([temp, z_root, lu, inner("nup")]))
         self.engine.step(f)
         out = self.engine.download_outputs()
         tau, taum1 = int(vs.tau), int(vs.taum1)
@@ -573,6 +599,17 @@ class CudaTransportDriver:
                 for k, name in enumerate(sas.STATISTICS):
                     if name in active:
                         self._put(name, st[k])
+            if self.nitrate:
+                no = self.engine.download_nitrate_outputs()
+                for k, name in enumerate(self.nit.OUTPUTS):
+                    if name == "Nmin_s":
+                        self._put(name, no[k], level=(tau, taum1))
+                    elif name in active:
+                        self._put(name, no[k])
+                self._put("temp_soil", temp, level=(tau, taum1))
+                if self.pull_state:
+                    for k, name in enumerate(("Nmin_rz", "Nmin_ss")):
+                        self._put(name, self.engine.download_state_index(4 + k), level=(tau, taum1))
         out_w = getattr(self, "_out", None)
         if out_w is not None and int(vs.time) % self._out_freq == 0:  # roger/diagnostics/api.py:45-66
             tau = int(vs.tau)
