@@ -373,6 +373,9 @@ def run_cuda(args):
     if not args.no_scenarios:
         extras["scenarios"] = {"snow_month_per_cell_forcing": run_scenario_snow_percell(args, local, world, rank, dist if world > 1 else None)}
 
+    if not args.no_nitrate:
+        extras["nitrate"] = run_nitrate_cuda(args, local, world, rank, dist if world > 1 else None)
+
     sas_res = None
     if not args.no_sas:
         # second half of the BASELINE metric: SVAT + offline oxygen-18 SAS transport (configs[2]) on the same GPU(s)
@@ -744,6 +747,65 @@ def run_sas_cuda(args, local, world, rank, dist, steps, warmup, side, ages, samp
     }
 
 
+def run_nitrate_cuda(args, local, world, rank, dist):
+    """BASELINE configs[3]: nitrate StorAge-selection transport (anion transport + soil nitrogen cycle on age-ranked mineral
+    nitrogen) on an Eberbaechle-like grid at 5 m resolution, 400 x 265 = 106 000 cells per GPU, 1500 age bins; daily hydrologic
+    forcing from an online SVAT run of the CUDA path on a 64 x 64 tile.  No collective: every rank steps its own block."""
+    import torch
+    from roger_b200 import nitrate, sas
+    from roger_b200.engine import CudaSvatEngine
+    from roger_b200.sas_engine import CudaSasEngine
+
+    C, A = args.nitrate_cells, args.ages
+    steps, warm = min(args.steps, 6), 2
+    ndays = steps + warm + 1
+    tile = sas_daily_tile(CudaSvatEngine, ndays, engine_kwargs={"device": local})
+    nt = tile["PREC"].shape[0]
+    idx = np.arange(C) % nt
+    rng = np.random.default_rng(77 + rank)
+    t = ndays + 1
+    daily = {k: np.ascontiguousarray(v[idx]) for k, v in tile.items() if getattr(v, "ndim", 0) == 2 and v.shape[0] == nt}
+    forcing = synth.mixed_forcing(ndays + 2, seed=42, start_doy=START_DOY)
+    daily["TA"], daily["DOY"] = forcing["TA"][::144][:t].copy(), forcing["DOY"][::144][:t].astype(np.int64)
+    daily["C_IN"] = rng.uniform(0, 60, (C, t)) * (rng.random((C, t)) < 0.1)
+    daily["Z_ROOT"] = np.repeat(rng.uniform(200, 900, (C, 1)), t, axis=1)
+    daily["LU_ID"] = np.repeat(rng.choice([8.0, 525.0, 583.0, 541.0], (C, 1)), t, axis=1)
+    daily["NUP"] = rng.uniform(0, 80, (C, t))
+    params = {k: rng.uniform(lo, hi, C) for k, (lo, hi) in dict(
+        kfix_rz=(10, 60), kmin_rz=(20, 120), kmin_ss=(5, 40), km_nit_rz=(5, 40), dmax_nit_rz=(20, 200), kngl_rz=(1, 20), km_denit_rz=(5, 40),
+        dmax_denit_rz=(10, 150), km_denit_ss=(5, 40), dmax_denit_ss=(5, 60), z_soil=(1200, 2500), damp_soil_temp=(12, 16)).items()}
+    params["phi_soil_temp"] = np.full(C, 91.0)
+    params["S_sat_rz"] = daily["S_RZ"][:, 0] * rng.uniform(1.02, 1.7, C)
+    params["S_sat_ss"] = daily["S_SS"][:, 0] * rng.uniform(1.02, 1.7, C)
+    anion = dict(alpha_transp=rng.uniform(0.2, 0.9, C), alpha_q=rng.uniform(0.4, 1.0, C), lu_id=daily["LU_ID"][:, 0], S_sat_rz=params["S_sat_rz"])
+    spec = dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0))  # svat_crop_nitrate tutorial :255-268
+    m = nitrate.NitrateModel(CudaSasEngine, C, A, daily, spec, params, anion, nitt=t, engine_kwargs={"device": local})
+    m.setup()
+    sa_rz, sa_ss = sas.initial_age_distribution(daily["S_RZ"][:, 0], A), sas.initial_age_distribution(daily["S_SS"][:, 0], A)
+    decay = np.exp(-np.linspace(0.001, 7, A))[None, :]
+    for k, arr in enumerate([sa_rz, sa_ss, 30.0 * sa_rz, 15.0 * sa_ss, 600.0 * decay * np.ones((C, 1)), 200.0 * decay * np.ones((C, 1))]):
+        m.engine.upload_state_index(k, arr)
+    del sa_rz, sa_ss
+    for _ in range(warm):
+        m.step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    m.engine.kernel_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.step()  # host forcing planes in (9 + 4), scalar results read back below: the public path
+    out = m.nitrate_outputs()
+    m.engine.synchronize()
+    wall, kern = _max_over_ranks([time.perf_counter() - t0, m.engine.kernel_ms / 1e3], dist)
+    finite = float(np.isfinite(out["Nmin_s"]).mean())
+    m.engine.close()
+    return {"value": world * C * steps / wall, "unit": "cell-timesteps/s", "ms_per_step": 1e3 * wall / steps, "kernel_ms_per_step": 1e3 * kern / steps,
+            "kernel_value": world * C * steps / kern, "steps": steps, "cells_per_gpu": C, "ages": A, "finite_Nmin_s_fraction": finite,
+            "config": f"nitrate SAS transport (anion transport + soil nitrogen cycle), {C} cells per GPU (Eberbaechle-like 400 x 265 grid at 5 m), "
+                      f"{A} age bins, power-law SAS, 6 sub-steps; host forcing in, per-cell results out every day"}
+
+
 def sas_cpu_baseline(ages, cells=8192, days=4):
     from oracle.engine import OracleSasEngine, OracleSvatEngine
     from roger_b200 import sas
@@ -816,6 +878,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the grid-size sweep (2^16 .. 2^22 cells per GPU) and the strong-scaling point")
     ap.add_argument("--sweep-large", action="store_true", help="add 2^26 and 2^27 cells per GPU to the sweep")
+    ap.add_argument("--no-nitrate", action="store_true", help="skip the nitrate transport measurement (BASELINE configs[3])")
+    ap.add_argument("--nitrate-cells", type=int, default=400 * 265)
     ap.add_argument("--no-dropin", action="store_true", help="skip the throughput measurement of the drop-in driver (CudaStepDriver)")
     ap.add_argument("--dropin-side", type=int, default=1024)
     ap.add_argument("--no-scenarios", action="store_true", help="skip the snow-month / per-cell-forcing scenario")
