@@ -164,6 +164,9 @@ int roger_svat_set_block_stepping(roger_svat *h, int enabled, int max_block);
 #define ROGER_DIAG_AVERAGE 1 /* mean over the steps of the interval,        roger/diagnostics/average.py:71-97  */
 #define ROGER_DIAG_MAXIMUM 2 /* running maximum of a 2-D variable,          roger/diagnostics/maximum.py:76-92  */
 #define ROGER_DIAG_MINIMUM 3 /* running minimum of a 2-D variable,          roger/diagnostics/minimum.py        */
+#define ROGER_DIAG_MAXIMUM_T 4 /* variables with a time-step dimension ((x, y, timesteps) in the reference): the maximum of the
+                                  last two time levels, overwritten every step,  roger/diagnostics/maximum.py:60-75 */
+#define ROGER_DIAG_MINIMUM_T 5 /* likewise the minimum,                          roger/diagnostics/minimum.py        */
 int roger_svat_set_diagnostics(roger_svat *h, const int *fields, const int *modes, int n);
 int roger_svat_download_diagnostics(roger_svat *h, double *host, int reset);
 /* The same hand-over off the critical path (the reference's writer thread, io_tools/netcdf.py:145-210): the accumulators are

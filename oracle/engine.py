@@ -82,6 +82,7 @@ class OracleSvatEngine:
         self._rate_names = [n for n, _ in spec]
         self._rate_modes = [m for _, m in spec]
         self._rates = np.zeros((len(spec), self.n))
+        self._rates_prev = np.stack([self.planes[self.abi.FIELD_ID[n]].copy() for n, _ in spec]) if spec else np.zeros((0, self.n))
         self._diag_count = 0
 
     def set_rate_fields(self, names):
@@ -97,6 +98,13 @@ class OracleSvatEngine:
                     self._rates[k] = a + v
                 elif mode == "average":
                     self._rates[k] = np.where(np.isnan(a), 0, a) + v
+                elif mode in ("maximum_t", "minimum_t"):  # maximum.py:60-75: the extreme of the last two time levels
+                    p = self._rates_prev[k].copy()
+                    self._rates_prev[k] = v
+                    mx = mode == "maximum_t"
+                    d0 = np.where((p == 0) & ((v < 0) if mx else (v > 0)), np.nan, p)
+                    both = np.maximum(d0, v) if mx else np.minimum(d0, v)
+                    self._rates[k] = np.where(np.isnan(d0), v, np.where(np.isnan(v), d0, both))
                 elif mode == "maximum":
                     d0 = np.where((a == 0) & (v < 0), np.nan, a)
                     self._rates[k] = np.where(np.isnan(d0), v, np.where(np.isnan(v), d0, np.maximum(d0, v)))

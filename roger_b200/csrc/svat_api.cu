@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(256) k_forcing_to_tiles(const double* __restri
     for (int k = w; k < 144; k += 8) out[(size_t)k * kTile] = t[lane][k];
 }
 
-__global__ void k_accumulate_rates(Planes pl, double* __restrict__ acc, const int* __restrict__ fields, const int* __restrict__ modes, int n) {
+__global__ void k_accumulate_rates(Planes pl, double* __restrict__ acc, const int* __restrict__ fields, const int* __restrict__ modes, int n,
+                                   double* __restrict__ prev) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pl.C) return;
     for (int k = 0; k < n; k++) {
@@ -398,7 +399,16 @@ __global__ void k_accumulate_rates(Planes pl, double* __restrict__ acc, const in
         const int mode = modes[k];
         if (mode == ROGER_DIAG_RATE) a = a + v;
         else if (mode == ROGER_DIAG_AVERAGE) a = ((a != a) ? 0.0 : a) + v;
-        else {
+        else if (mode == ROGER_DIAG_MAXIMUM_T || mode == ROGER_DIAG_MINIMUM_T) {
+            // variables with a time-step dimension (maximum.py:60-75): the extreme of the last two time levels, not a running one
+            const bool mx = (mode == ROGER_DIAG_MAXIMUM_T);
+            double p = prev[(size_t)k * pl.C + i];  // [taum1]: the value the previous step left
+            prev[(size_t)k * pl.C + i] = v;
+            if ((p == 0) && (mx ? (v < 0) : (v > 0))) p = __longlong_as_double(0x7ff8000000000000ULL);
+            if (p != p) a = v;
+            else if (v == v) a = mx ? ((v > p) ? v : p) : ((v < p) ? v : p);
+            else a = p;
+        } else {
             const bool mx = (mode == ROGER_DIAG_MAXIMUM);
             if ((a == 0) && (mx ? (v < 0) : (v > 0))) a = __longlong_as_double(0x7ff8000000000000ULL);
             if (a != a) a = v;                    // nanmax / nanmin of (NaN, v) = v (NaN if both are)
@@ -507,6 +517,7 @@ struct roger_svat {
     std::vector<int> rate_fields, rate_modes;
     bool rates_need_flux = false;
     double* d_rates = nullptr;
+    double* d_rates_prev = nullptr;  // [taum1] planes of the MAXIMUM_T / MINIMUM_T accumulators
     int* d_rate_fields = nullptr;  // n field ids followed by n modes
     int64_t diag_count = 0;        // steps accumulated since the last reset (average_nitts)
     // day-blocked stepping (run_block)
@@ -704,7 +715,7 @@ void roger_svat_destroy(roger_svat* h) {
     for (auto p : h->snap_busy) cudaFree(p);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     for (auto& e : h->fences) if (e) cudaEventDestroy(e);
-    cudaFree(h->d_rates); cudaFree(h->d_rate_fields);
+    cudaFree(h->d_rates); cudaFree(h->d_rates_prev); cudaFree(h->d_rate_fields);
     cudaFree(h->d_plans); cudaFree(h->d_block_flags);
     if (h->h_plans) cudaFreeHost(h->h_plans);
     if (h->h_block_flags) cudaFreeHost(h->h_block_flags);
@@ -1160,7 +1171,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
     launches++;
     if (!h->rate_fields.empty()) {
         const int n = (int)h->rate_fields.size();
-        k_accumulate_rates<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(pl, h->d_rates, h->d_rate_fields, h->d_rate_fields + n, n);
+        k_accumulate_rates<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(pl, h->d_rates, h->d_rate_fields, h->d_rate_fields + n, n, h->d_rates_prev);
         CU(cudaGetLastError());
         launches++;
         h->diag_count++;
@@ -1260,7 +1271,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int
             launches++;
             if (!h->rate_fields.empty()) {
                 const int nr = (int)h->rate_fields.size();
-                k_accumulate_rates<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(pl, h->d_rates, h->d_rate_fields, h->d_rate_fields + nr, nr);
+                k_accumulate_rates<<<(int)((h->C + 255) / 256), 256, 0, h->stream>>>(pl, h->d_rates, h->d_rate_fields, h->d_rate_fields + nr, nr, h->d_rates_prev);
                 CU(cudaGetLastError());
                 launches++;
                 h->diag_count++;
@@ -1343,9 +1354,10 @@ int roger_svat_set_diagnostics(roger_svat* h, const int* fields, const int* mode
     for (int k = 0; k < n; k++) {
         if (fields[k] < 0 || fields[k] >= RF_COUNT) return fail(ROGER_EINVAL, "roger_svat_set_diagnostics: bad field id");
         const int m = modes ? modes[k] : ROGER_DIAG_RATE;
-        if (m < ROGER_DIAG_RATE || m > ROGER_DIAG_MINIMUM) return fail(ROGER_EINVAL, "roger_svat_set_diagnostics: bad mode");
+        if (m < ROGER_DIAG_RATE || m > ROGER_DIAG_MINIMUM_T) return fail(ROGER_EINVAL, "roger_svat_set_diagnostics: bad mode");
     }
     cudaFree(h->d_rates); h->d_rates = nullptr;
+    cudaFree(h->d_rates_prev); h->d_rates_prev = nullptr;
     cudaFree(h->d_rate_fields); h->d_rate_fields = nullptr;
     h->rate_fields.assign(fields, fields + n);
     h->rate_modes.assign(n, ROGER_DIAG_RATE);
@@ -1358,6 +1370,18 @@ int roger_svat_set_diagnostics(roger_svat* h, const int* fields, const int* mode
     const size_t bytes = sizeof(double) * (size_t)n * (size_t)h->C;
     CU(cudaMalloc(&h->d_rates, bytes));
     CU(cudaMemsetAsync(h->d_rates, 0, bytes, h->stream));
+    bool two_level = false;
+    for (int m : h->rate_modes) two_level = two_level || m == ROGER_DIAG_MAXIMUM_T || m == ROGER_DIAG_MINIMUM_T;
+    if (two_level) {  // [taum1] of the first accumulated step: the planes as they are now
+        CU(cudaMalloc(&h->d_rates_prev, bytes));
+        CU(cudaMemsetAsync(h->d_rates_prev, 0, bytes, h->stream));
+        for (int k = 0; k < n; k++)
+            if (h->rate_modes[k] == ROGER_DIAG_MAXIMUM_T || h->rate_modes[k] == ROGER_DIAG_MINIMUM_T) {
+                if (is_soil_kh(h->rate_fields[k])) { int r = refresh_soil_kh(h); if (r) return r; }
+                k_gather_plane<<<h->grid256(), 256, 0, h->stream>>>(h->planes(), h->rate_fields[k], h->d_rates_prev + (size_t)k * h->C, nullptr);
+            }
+        CU(cudaGetLastError());
+    }
     CU(cudaMalloc(&h->d_rate_fields, sizeof(int) * 2 * n));
     CU(cudaMemcpyAsync(h->d_rate_fields, h->rate_fields.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_rate_fields + n, h->rate_modes.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));

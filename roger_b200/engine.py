@@ -238,7 +238,9 @@ class CudaSvatEngine:
         self._timing()
         return n.value
 
-    DIAG_MODES = {"rate": 0, "average": 1, "maximum": 2, "minimum": 3}
+    # "maximum_t" / "minimum_t": variables with a time-step dimension in the reference keep the extreme of the last two time
+    # levels instead of a running one (roger/diagnostics/maximum.py:60-75)
+    DIAG_MODES = {"rate": 0, "average": 1, "maximum": 2, "minimum": 3, "maximum_t": 4, "minimum_t": 5}
 
     def set_diagnostics(self, spec):
         """spec: list of (field name, "rate" | "average" | "maximum" | "minimum"); accumulated on the device after every step

@@ -373,7 +373,11 @@ class CudaStepDriver:
                 raise NotImplementedError(f"diagnostic {name!r}: {unknown} are not planes of the CUDA engine")
             if any((v, m) for v, m in spec if v in d.output_variables):
                 raise NotImplementedError("a variable in more than one diagnostic")
-            spec += [(v, name) for v in d.output_variables]
+            for v in d.output_variables:
+                mode = name
+                if name in ("maximum", "minimum") and np.asarray(getattr(self.state.variables, v)).ndim == 3:
+                    mode = name + "_t"  # (x, y, timesteps) variables: the extreme of the last two time levels (maximum.py:60-75)
+                spec.append((v, mode))
             fname = d.output_path.format(identifier=st.identifier)
             files[os.path.join(str(getattr(d, "base_output_path", None) or base_path), fname)] = list(d.output_variables)
         if not spec:
@@ -531,6 +535,11 @@ class CudaTransportDriver:
                 self.engine.upload_state_index(4 + k, np.asarray(getattr(vs, name))[2:-2, 2:-2, tau, :].reshape(self.C, self.A))
         if self.stats:
             self.engine.set_balance_reference(np.asarray(vs.C_s)[2:-2, 2:-2, int(vs.taum1)].reshape(-1))
+            # storage-bound part of numerics.sanity_check (numerics.py:1051-1122) and its tolerances
+            inner = lambda n: np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64)  # noqa: E731
+            if all(hasattr(vs, n) for n in ("S_sat_rz", "S_sat_ss", "S_pwp_rz", "S_pwp_ss")):
+                self.engine.set_sanity_bounds(inner("S_sat_rz"), inner("S_sat_ss"), inner("S_pwp_rz"), inner("S_pwp_ss"),
+                                              float(getattr(st, "atol", 1e-2)), float(getattr(st, "rtol", 1e-2)))
 
     def _put(self, name, values, level=None):
         vs = self.state.variables
@@ -547,6 +556,10 @@ class CudaTransportDriver:
         setup, state, sas = self.setup, self.state, self.sas
         vs = state.variables
         setup._ensure_setup_done()
+        if self.euler:  # validate before touching vs: the device ages the StorAge once per call, i.e. the Euler steps must fill whole days
+            n = int(self.settings.substeps)
+            if (n * int(int(np.asarray(vs.dt_secs)) / n)) % (24 * 60 * 60) != 0:
+                raise NotImplementedError("Euler steps that do not add up to whole days (the device ages the StorAge once per call)")
         with vs.unlock():
             vs.itt = vs.itt + 1
             if not self.euler:  # roger.py:470-471
@@ -560,8 +573,6 @@ class CudaTransportDriver:
             with vs.unlock():
                 vs.time = vs.time + n * int(vs.dt_secs / n)
                 vs.itt_substep = n - 1
-            if int(vs.time) % (24 * 60 * 60) != 0:
-                raise NotImplementedError("Euler steps that do not add up to whole days (the device ages the StorAge once per call)")
         f = np.stack([np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64) for n in self._FORCING])
         if self.nitrate:  # nitrate.calculate_nitrogen_cycle, first half (nitrate.py:717-731): the soil temperature, on the host
             nit, st = self.nit, state.settings
@@ -599,6 +610,11 @@ class CudaTransportDriver:
                 for k, name in enumerate(sas.STATISTICS):
                     if name in active:
                         self._put(name, st[k])
+                ok = st[sas.STATISTICS.index("sanity_ok")]
+                if np.any(ok == 0.0):  # the reference's scalar is the AND over all cells (roger.py:453-456: a warning, not an error)
+                    import warnings
+
+                    warnings.warn(f"Solution diverged at iteration {int(np.asarray(vs.itt))} (numerics.sanity_check, {int((ok == 0.0).sum())} cells)")
             if self.nitrate:
                 no = self.engine.download_nitrate_outputs()
                 for k, name in enumerate(self.nit.OUTPUTS):

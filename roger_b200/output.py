@@ -24,7 +24,7 @@ import numpy as np
 from .field_meta import FIELD_META
 
 FLOAT_FILL_VALUE = -9999  # roger/variables.py:57
-MODES = ("rate", "average", "maximum", "minimum", "collect")
+MODES = ("rate", "average", "maximum", "minimum", "maximum_t", "minimum_t", "collect")
 
 
 class DiagnosticFile:

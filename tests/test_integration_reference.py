@@ -164,7 +164,10 @@ def test_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
 
     case = _case("svat_rain")
     Setup = rh.make_svat_setup(case)
-    want = {"rate": ["q_ss", "aet", "prec"], "average": ["theta_rz"], "collect": ["S_s"]}
+    # maximum / minimum: theta_ss and S carry a time-step dimension in the reference (their record is the extreme of the last two
+    # time levels, maximum.py:60-75), inf_mat and aet_soil are plain (x, y) variables (running extremes)
+    want = {"rate": ["q_ss", "aet", "prec"], "average": ["theta_rz"], "collect": ["S_s"], "maximum": ["theta_ss", "inf_mat"],
+            "minimum": ["S", "aet_soil"]}
 
     def configure(model):
         for name, vars_ in want.items():
@@ -182,6 +185,17 @@ def test_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
     configure(dut)
     driver = CudaStepDriver(dut, engine_cls=OracleSvatEngine)
     driver.enable_output(base_path=str(tmp_path), force_overwrite=True)
+    # Maximum / Minimum zero their arrays right after writing (maximum.py:94-113): catch what they hand to write_output
+    written = {}
+    for name in ("maximum", "minimum"):
+        d = ref.state.diagnostics[name]
+
+        def spy(state, _d=d, _orig=d.write_output):
+            for v in _d.output_variables:
+                written[v] = np.asarray(getattr(_d.variables, v))[2:-2, 2:-2].copy()
+            return _orig(state)
+
+        d.write_output = spy
     records = []
     for step in range(400):
         ref.step(ref.state)
@@ -192,6 +206,9 @@ def test_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
             for name, vars_ in want.items():
                 dv = ref.state.diagnostics[name].variables
                 for v in vars_:
+                    if name in ("maximum", "minimum"):
+                        rec[v] = written[v]
+                        continue
                     a = np.asarray(getattr(dv, v))
                     rec[v] = a[2:-2, 2:-2].copy() if a.ndim == 2 else a[2:-2, 2:-2, int(ref.state.variables.tau)].copy()
             records.append((t, rec))
@@ -209,7 +226,7 @@ def test_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
                 got = f.variables[v][k].T
                 ref_v = records[k][1][v]
                 # (Average.output has already divided the in-memory sums by the step count, average.py:93-97)
-                assert v == "prec" or k == 0 or np.abs(ref_v[mask]).sum() > 0, (name, v)  # (the second day of this case is dry)
+                assert v in ("prec", "inf_mat", "aet_soil") or k == 0 or np.abs(ref_v[mask]).sum() > 0, (name, v)  # (the second day of this case is dry)
                 assert normalised_max_error(np.where(mask, ref_v, 0), np.where(mask, got, 0)) < 1e-10, (name, v)
 
 

@@ -234,7 +234,8 @@ def test_average_maximum_minimum_diagnostics_on_the_device():
     shape = (12, 9)
     forcing = synth.mixed_forcing(8, seed=42, start_doy=121)
     prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, masked_fraction=0.1)
-    spec = [("theta_rz", "average"), ("q_ss", "maximum"), ("dS", "minimum"), ("aet", "rate"), ("q_sur", "maximum"), ("z_sat", "average")]
+    spec = [("theta_rz", "average"), ("q_ss", "maximum"), ("dS", "minimum"), ("aet", "rate"), ("q_sur", "maximum"), ("z_sat", "average"),
+            ("S", "maximum_t"), ("theta_ss", "minimum_t")]  # (x, y, timesteps) variables of the reference: extreme of the last two levels
     lib().roger_oracle_set_pow(1)
     try:
         models = [SvatModel(e, shape, forcing, prim, th_rz, th_ss) for e in (_engine(), OracleSvatEngine)]
