@@ -82,6 +82,10 @@ int roger_svat_download(roger_svat *h, int field, double *host);
  * second stream while later steps run.  The buffer is valid after roger_svat_download_wait(). */
 int roger_svat_download_async(roger_svat *h, int field, double *host_pinned);
 int roger_svat_download_wait(roger_svat *h);
+/* how a snapshot leaves the device: 1 (default) an SM copy kernel writing into the caller's page-locked buffer through its mapped
+ * device pointer, on a high-priority stream beside the step kernels (the copy engine's transfer is starved by a DRAM-saturating
+ * kernel: 3 GB/s measured against 33 GB/s idle); 0 the copy engine (also the automatic fallback for buffers that are not mapped) */
+int roger_svat_set_d2h_mode(roger_svat *h, int mode);
 /* Makes sure `n` device snapshot planes exist so that roger_svat_download_async / _diagnostics_async never allocate inside
  * a stepping loop; a driver calls it once when it configures its output (n = planes handed over per output time).  The
  * copy stream, its events and the fence ring are created by roger_svat_create. */

@@ -322,6 +322,15 @@ __global__ void k_gather_linear(const double* __restrict__ src, double* __restri
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d < C) dst[order ? order[d] : d] = src[d];
 }
+// Snapshot plane -> page-locked host memory, written by the SMs (16-byte stores over PCIe through the mapped host pointer).
+// The copy engine's device-to-host transfer of a snapshot is starved by the DRAM-saturating step kernel running beside it
+// (measured on B200: 33 GB/s with the GPU idle, 3 GB/s beside k_svat_step); SM-issued loads take part in the same
+// arbitration as the step kernel's own.  Runs on the high-priority copy stream: its blocks slip in as step blocks retire.
+__global__ void __launch_bounds__(256) k_copy_to_host(const double2* __restrict__ src, double2* __restrict__ dst, int64_t n2,
+                                                       const double* __restrict__ src_tail, double* __restrict__ dst_tail, int tail) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
 __global__ void k_copy_plane(Planes pl, int dst_field, int src_field) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < pl.C) *pl.at(dst_field, i) = *pl.at(src_field, i);
@@ -530,7 +539,8 @@ struct roger_svat {
     unsigned* d_block_flags = nullptr;
     unsigned* h_block_flags = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;          // asynchronous diagnostic read-back (roger_svat_download_async)
+    cudaStream_t copy_stream = nullptr;          // asynchronous diagnostic read-back (roger_svat_download_async), high priority
+    int d2h_mode = 1;                            // 1: SM copy kernel into mapped host memory where possible, 0: copy engine
     std::vector<double*> snap_free, snap_busy;   // device snapshot planes
     cudaEvent_t ev_snap = nullptr;
     static constexpr int kFences = 64;           // ring of copy-stream fences (roger_svat_download_fence)
@@ -653,6 +663,7 @@ const char* roger_svat_field_name(int f) { return (f >= 0 && f < RF_COUNT) ? kFi
 int roger_svat_field_kind(int f) { return (f >= 0 && f < RF_COUNT) ? kFieldKind[f] : -1; }
 
 static int ensure_copy_stream(roger_svat* h);
+static int copy_plane_to_host(roger_svat* h, const double* snap, double* host_pinned);
 
 int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settings* settings, int device) {
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_svat_create: bad argument");
@@ -792,13 +803,31 @@ int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_snap, h->stream));
     CU(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    return copy_plane_to_host(h, snap, host_pinned);
+}
+
+// snapshot plane (device) -> caller's page-locked buffer, on the copy stream
+static int copy_plane_to_host(roger_svat* h, const double* snap, double* host_pinned) {
+    const size_t plane = sizeof(double) * (size_t)h->C;
+    void* mapped = nullptr;
+    if (h->d2h_mode == 1 && ((uintptr_t)host_pinned % 16 == 0) && cudaHostGetDevicePointer(&mapped, host_pinned, 0) == cudaSuccess && mapped) {
+        const int64_t n2 = h->C / 2;
+        const int tail = (int)(h->C - 2 * n2);
+        k_copy_to_host<<<148 * 4, 256, 0, h->copy_stream>>>(reinterpret_cast<const double2*>(snap), reinterpret_cast<double2*>(mapped), n2,
+                                                             snap + 2 * n2, reinterpret_cast<double*>(mapped) + 2 * n2, tail);
+        CU(cudaGetLastError());
+        return 0;
+    }
+    cudaGetLastError();  // (a buffer that is not mapped: clear the sticky-free error of the query and use the copy engine)
     CU(cudaMemcpyAsync(host_pinned, snap, plane, cudaMemcpyDeviceToHost, h->copy_stream));
     return 0;
 }
 
 static int ensure_copy_stream(roger_svat* h) {
     if (!h->copy_stream) {
-        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = greatest priority
+        CU(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi));
         CU(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
     }
     return 0;
@@ -821,8 +850,7 @@ int roger_svat_download_diagnostics_async(roger_svat* h, double* host_pinned, in
     if (reset) CU(cudaMemsetAsync(h->d_rates, 0, plane * n, h->stream));
     CU(cudaEventRecord(h->ev_snap, h->stream));
     CU(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
-    for (size_t k = 0; k < n; k++)
-        CU(cudaMemcpyAsync(host_pinned + k * (size_t)h->C, snaps[k], plane, cudaMemcpyDeviceToHost, h->copy_stream));
+    for (size_t k = 0; k < n; k++) { int r = copy_plane_to_host(h, snaps[k], host_pinned + k * (size_t)h->C); if (r) return r; }
     if (count) *count = h->diag_count;
     if (reset) h->diag_count = 0;
     return 0;
@@ -840,6 +868,12 @@ int roger_svat_download_fence(roger_svat* h) {
 int roger_svat_fence_wait(roger_svat* h, int token) {
     if (!h || token < 0 || token >= roger_svat::kFences || !h->fences[token]) return fail(ROGER_EINVAL, "roger_svat_fence_wait: bad token");
     CU(cudaEventSynchronize(h->fences[token]));
+    return 0;
+}
+
+int roger_svat_set_d2h_mode(roger_svat* h, int mode) {
+    if (!h || mode < 0 || mode > 1) return fail(ROGER_EINVAL, "roger_svat_set_d2h_mode: 0 (copy engine) or 1 (SM copy kernel into mapped host memory)");
+    h->d2h_mode = mode;
     return 0;
 }
 

@@ -47,6 +47,7 @@ def load_library():
     lib.roger_svat_download_fence.argtypes = [hp]
     lib.roger_svat_fence_wait.argtypes = [hp, C.c_int]
     lib.roger_svat_download_wait.argtypes = [hp]
+    lib.roger_svat_set_d2h_mode.argtypes = [hp, C.c_int]
     lib.roger_svat_reserve_snapshots.argtypes = [hp, C.c_int]
     lib.roger_svat_tile_layout.argtypes = [hp, C.POINTER(abi.SvatLayout)]
     lib.roger_svat_field_slot.argtypes = [C.c_int]
@@ -143,6 +144,10 @@ class CudaSvatEngine:
 
     def download_wait(self):
         _check(self.lib, self.lib.roger_svat_download_wait(self.h))
+
+    def set_d2h_mode(self, mode):
+        """1: snapshots leave the device through an SM copy kernel into the mapped page-locked buffer (default), 0: copy engine"""
+        _check(self.lib, self.lib.roger_svat_set_d2h_mode(self.h, int(mode)))
 
     def download_diagnostics_async(self, host_pinned, reset=True):
         """Hands the accumulators (len(spec), n_cells) to `host_pinned` off the critical path; returns the number of accumulated

@@ -15,9 +15,13 @@ eng.reserve_snapshots(2)
 for _ in range(8):
     m.run_steps(1)
 eng.synchronize()
-for label, steps in (("idle", 0), ("under load", 24)):
+for label, steps, mode in (("idle, copy engine", 0, 0), ("under load, copy engine", 24, 0), ("idle, SM copy kernel", 0, 1), ("under load, SM copy kernel", 24, 1),
+                           ("under load, no copy", 24, -1)):
+    if mode >= 0:
+        eng.set_d2h_mode(mode)
     t0 = time.perf_counter()
-    eng.download_async("theta_rz", pin[0]); eng.download_async("S", pin[1])
+    if mode >= 0:
+        eng.download_async("theta_rz", pin[0]); eng.download_async("S", pin[1])
     t1 = time.perf_counter()
     left = steps
     while left > 0:
