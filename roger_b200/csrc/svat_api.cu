@@ -326,6 +326,7 @@ __global__ void k_gather_linear(const double* __restrict__ src, double* __restri
 // The copy engine's device-to-host transfer of a snapshot is starved by the DRAM-saturating step kernel running beside it
 // (measured on B200: 33 GB/s with the GPU idle, 3 GB/s beside k_svat_step); SM-issued loads take part in the same
 // arbitration as the step kernel's own.  Runs on the high-priority copy stream: its blocks slip in as step blocks retire.
+constexpr int kD2HBlocks = 16;
 __global__ void __launch_bounds__(256) k_copy_to_host(const double2* __restrict__ src, double2* __restrict__ dst, int64_t n2,
                                                        const double* __restrict__ src_tail, double* __restrict__ dst_tail, int tail) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
@@ -540,7 +541,8 @@ struct roger_svat {
     unsigned* h_block_flags = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // asynchronous diagnostic read-back (roger_svat_download_async), high priority
-    int d2h_mode = 1;                            // 1: SM copy kernel into mapped host memory where possible, 0: copy engine
+    int d2h_mode = 1;                            // >= 1: SM copy kernel into mapped host memory where possible (1: default grid,
+                                                 // n > 1: n blocks), 0: copy engine
     std::vector<double*> snap_free, snap_busy;   // device snapshot planes
     cudaEvent_t ev_snap = nullptr;
     static constexpr int kFences = 64;           // ring of copy-stream fences (roger_svat_download_fence)
@@ -810,10 +812,13 @@ int roger_svat_download_async(roger_svat* h, int field, double* host_pinned) {
 static int copy_plane_to_host(roger_svat* h, const double* snap, double* host_pinned) {
     const size_t plane = sizeof(double) * (size_t)h->C;
     void* mapped = nullptr;
-    if (h->d2h_mode == 1 && ((uintptr_t)host_pinned % 16 == 0) && cudaHostGetDevicePointer(&mapped, host_pinned, 0) == cudaSuccess && mapped) {
+    if (h->d2h_mode >= 1 && ((uintptr_t)host_pinned % 16 == 0) && cudaHostGetDevicePointer(&mapped, host_pinned, 0) == cudaSuccess && mapped) {
         const int64_t n2 = h->C / 2;
         const int tail = (int)(h->C - 2 * n2);
-        k_copy_to_host<<<148 * 4, 256, 0, h->copy_stream>>>(reinterpret_cast<const double2*>(snap), reinterpret_cast<double2*>(mapped), n2,
+        // A FEW blocks only: two step blocks fill an SM's register file, so every SM that hosts a copy block runs the step at
+        // half rate for as long as the PCIe writes take; a dozen SMs issue more stores than the link absorbs.
+        const int blocks = (h->d2h_mode == 1) ? kD2HBlocks : h->d2h_mode;
+        k_copy_to_host<<<blocks, 256, 0, h->copy_stream>>>(reinterpret_cast<const double2*>(snap), reinterpret_cast<double2*>(mapped), n2,
                                                              snap + 2 * n2, reinterpret_cast<double*>(mapped) + 2 * n2, tail);
         CU(cudaGetLastError());
         return 0;
@@ -872,7 +877,7 @@ int roger_svat_fence_wait(roger_svat* h, int token) {
 }
 
 int roger_svat_set_d2h_mode(roger_svat* h, int mode) {
-    if (!h || mode < 0 || mode > 1) return fail(ROGER_EINVAL, "roger_svat_set_d2h_mode: 0 (copy engine) or 1 (SM copy kernel into mapped host memory)");
+    if (!h || mode < 0 || mode > 65535) return fail(ROGER_EINVAL, "roger_svat_set_d2h_mode: 0 (copy engine), 1 (SM copy kernel, default grid) or the number of copy blocks");
     h->d2h_mode = mode;
     return 0;
 }

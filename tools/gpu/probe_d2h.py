@@ -15,8 +15,11 @@ eng.reserve_snapshots(2)
 for _ in range(8):
     m.run_steps(1)
 eng.synchronize()
-for label, steps, mode in (("idle, copy engine", 0, 0), ("under load, copy engine", 24, 0), ("idle, SM copy kernel", 0, 1), ("under load, SM copy kernel", 24, 1),
-                           ("under load, no copy", 24, -1)):
+cases = [("under load, no copy", 24, -1), ("idle, copy engine", 0, 0), ("under load, copy engine", 24, 0)]
+for nb in (4, 8, 16, 32, 64, 592):
+    cases += [(f"idle, SM copy kernel x{nb} blocks", 0, nb), (f"under load, SM copy kernel x{nb} blocks", 24, nb)]
+cases.append(("under load, no copy", 24, -1))
+for label, steps, mode in cases:
     if mode >= 0:
         eng.set_d2h_mode(mode)
     t0 = time.perf_counter()
