@@ -153,6 +153,24 @@ def build_model(engine_cls, shape, workload, seed, engine_kwargs=None, ndays=40)
     return m
 
 
+def place_window(m):
+    """Untimed steps up to the midnight that opens the first day stepped hourly -- the day the first rain event of the synthetic
+    series arrives -- so that the timed window holds rain steps as well as dry ones (both arms use it).  Whether a day is
+    stepped hourly is only known after its first step, hence the engine's in-memory checkpoint / rollback.  Returns the day."""
+    eng = m.engine
+    for _ in range(40):
+        while eng.get_scalars().time % 86400 != 0:
+            m.run_steps(144)
+        m.checkpoint()
+        m.run_steps(1)
+        hourly = eng.get_scalars().dt_secs == 3600
+        m.rollback()
+        if hourly:
+            break
+        m.run_steps(1)
+    return int(eng.get_scalars().time // 86400)
+
+
 def run_reference(args):
     """The reference arm: the reference's CPU algorithm (oracle port, all host threads) on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -194,6 +212,7 @@ def run_reference(args):
     m = build_model(OracleSvatEngine, shape, args.workload, seed=43)
     for _ in range(args.warmup):
         m.step(False)
+    day = place_window(m)  # the same simulated window as the CUDA arm
     t0 = time.perf_counter()
     for _ in range(args.steps):
         m.step(False)
@@ -205,7 +224,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload} {args.side}x{args.side} cells per GPU (oneD_benchmark.py), uniform synthetic forcing from 1 May",
-                   "sample": f"timed on a {side}x{side}-cell sample of that workload (same parameter and forcing generators), {cores} host threads"},
+                   "sample": f"timed on a {side}x{side}-cell sample of that workload (same parameter and forcing generators), {cores} host threads",
+                   "window": "starts at the midnight opening simulated day %d (first rain event of the series)" % day},
         "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port",
                          "sample": f"{side}x{side} cells of the same workload, {args.steps} adaptive steps, OpenMP over cells",
                          "numpy_reference": numpy_reference_record(args.workload)},
@@ -286,22 +306,10 @@ def run_cuda(args):
     sampler = ClockSampler(local)
     sampler.start()
     advance(args.warmup)
-    # Placement of the timed window (untimed steps): it starts at the midnight that opens the first day stepped hourly -- the
-    # day the first rain event of the synthetic series arrives -- so that it holds rain steps as well as dry ones.  In `e2e`
-    # the daily output of the day that just ended is issued at that midnight, inside the timed region, and its copy to the
-    # host overlaps the day's steps: the steady state of a long run (one output per simulated day).  Whether a day is
-    # stepped hourly is only known after its first step, hence the device-resident checkpoint / rollback.
-    for _ in range(40):
-        while eng.get_scalars().time % 86400 != 0:
-            m.run_steps(144)
-        m.checkpoint()
-        m.run_steps(1)
-        hourly = eng.get_scalars().dt_secs == 3600
-        m.rollback()
-        if hourly:
-            break
-        m.run_steps(1)
-    window_start_day = eng.get_scalars().time // 86400
+    # Placement of the timed window (untimed steps, place_window()): the midnight that opens the first day stepped hourly.  In
+    # `e2e` the daily output of the day that just ended is issued at that midnight, inside the timed region, and its copy to the
+    # host overlaps the day's steps: the steady state of a long run (one output per simulated day).
+    window_start_day = place_window(m)
     ms_by_dt.clear()
     n_by_dt.clear()
     m.checkpoint()  # `e2e` below repeats exactly this simulated window (same state, same forcing days, same step mix)
@@ -834,6 +842,7 @@ def cpu_baseline(args):
     m = build_model(OracleSvatEngine, (side, side), args.workload, seed=43)
     for _ in range(2):
         m.step(False)
+    place_window(m)  # the same simulated window as the CUDA measurement
     n = max(10, min(args.steps, 40))
     t0 = time.perf_counter()
     for _ in range(n):

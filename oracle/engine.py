@@ -70,6 +70,18 @@ class OracleSvatEngine:
     def set_forcing_day(self, prec, ta, pet):
         self.forcing = [np.ascontiguousarray(a, dtype=np.float64) for a in (prec, ta, pet)]
 
+    def checkpoint(self):
+        """the in-memory checkpoint of roger_b200.engine.CudaSvatEngine (roger_svat_checkpoint)"""
+        sc = self.abi.SvatScalars()
+        C.memmove(C.byref(sc), C.byref(self.scalars), C.sizeof(sc))
+        self._ckpt = (self.planes.copy(), sc, None if self.forcing is None else [a.copy() for a in self.forcing])
+
+    def rollback(self):
+        planes, sc, forcing = self._ckpt
+        self.planes[:] = planes
+        C.memmove(C.byref(self.scalars), C.byref(sc), C.sizeof(sc))
+        self.forcing = None if forcing is None else [a.copy() for a in forcing]
+
     def step(self, write_fluxes=True):
         p, t, e = self.forcing
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731

@@ -265,7 +265,7 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
             for (unsigned k = 0; k < sizeof(Cell) / sizeof(double); k++) raw[k] = __longlong_as_double(0x7ff8000000000000ULL);
         }
 #endif
-        const Io io{pl.ps, pl.fl, i};
+        const Io io{pl.ps, pl.fl, i, p.flux_mask[0], p.flux_mask[1]};
         c.maskCatch = io.ldp(RF_maskCatch);
         c.m = c.maskCatch;
         // ---- adaptive_time_stepping.py:130-189 / :256-360: forcing for this cell ----
@@ -1165,9 +1165,20 @@ static int ensure_uniform_current(roger_svat* h) {  // the "keep" class reads pr
 }
 
 // One adaptive time step: host scheduler + one launch of the fused per-cell kernel.
+// which flux planes a flux-storing step writes: all of them when the caller asked for fluxes (parity / diagnostics mode), only the
+// accumulated ones when a diagnostics accumulator is the reason the flux kernel runs
+static void set_flux_mask(const roger_svat* h, bool caller_wants_all, StepPlan& p) {
+    p.flux_mask[0] = p.flux_mask[1] = ~0ULL;
+    if (caller_wants_all) return;
+    p.flux_mask[0] = p.flux_mask[1] = 0;
+    for (int f : h->rate_fields)
+        if (kind_is_F(f)) p.flux_mask[(f - kNumPS) >> 6] |= 1ULL << ((f - kNumPS) & 63);
+}
+
 static int step_impl(roger_svat* h, int write_fluxes) {
     if (!h->have_forcing) return fail(ROGER_EINVAL, "roger_svat_step: no forcing day set");
     CU(cudaSetDevice(h->device));
+    const bool caller_wants_fluxes = write_fluxes != 0;
     if (h->rates_need_flux) write_fluxes = 1;  // flux rates are accumulated from the flux planes
     if (write_fluxes) { int r = ensure_flux_planes(h); if (r) return r; }
     const roger_svat_settings& st = h->st;
@@ -1197,6 +1208,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
         ev = w;
     }
     schedule_second_half(h, ev, a, sc, p);
+    set_flux_mask(h, caller_wants_fluxes, p);
 
     CU(cudaMemsetAsync(h->d_flags, 0, sizeof(unsigned), h->stream));
     const Planes pl = h->planes();
@@ -1248,7 +1260,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
 // runs them in ONE launch of k_svat_steps (the state comes back from L2: right for catchment-scale grids), `queued` = true
 // launches the ordinary step kernel once per step, back to back, and reads all flag words back once -- no launch gap, no
 // read-back latency and, on several GPUs, one flag exchange per batch instead of one per step.
-static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int write_fluxes) {
+static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int write_fluxes, bool caller_wants_fluxes) {
     *n_done = 0;
     const roger_svat_settings& st = h->st;
     if (!st.forcing_uniform || !h->ks_ss_synced || !h->have_forcing || max_steps < 2) return 0;
@@ -1280,6 +1292,7 @@ static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int
         if (!(ta_seen_a > st.ta_fm) || !(ta_final > st.ta_fm)) break;       // a cold step: snow may accrue, stop before it
         finish_step_scalars(h, p, sc_try);
         sc = sc_try;
+        set_flux_mask(h, caller_wants_fluxes, p);
         plans.push_back(p);
         dts.push_back((int)sc_try.dt_secs);
         if (sc.time % 86400 == 0) break;  // the next day needs a new forcing block
@@ -1365,10 +1378,10 @@ int roger_svat_run_steps(roger_svat* h, int write_fluxes, int max_steps, int* n_
     do {
         int nb = 0;
         if (h->step_batching == 1 && !write_fluxes && h->rate_fields.empty() && !h->rates_need_flux) {
-            int r = run_block(h, max_steps - n, &nb, false, 0);
+            int r = run_block(h, max_steps - n, &nb, false, 0, false);
             if (r) return r;
         } else if (h->step_batching == 2) {
-            int r = run_block(h, max_steps - n, &nb, true, (write_fluxes || h->rates_need_flux) ? 1 : 0);
+            int r = run_block(h, max_steps - n, &nb, true, (write_fluxes || h->rates_need_flux) ? 1 : 0, write_fluxes != 0);
             if (r) return r;
         }
         if (nb == 0) {

@@ -41,6 +41,8 @@ struct StepPlan {
     int uniform;          // forcing shared by all cells
     int lbc;              // settings.enable_macropore_lower_boundary_condition
     int clamp;            // after_timestep clamp of tiny negative storages (SVAT setups)
+    unsigned long long flux_mask[2];  // FLUX kernels: which flux planes are stored (bit f - first flux id); all ones in parity mode,
+                                      // only the accumulated ones when a diagnostics accumulator is what asked for the flux kernel
 };
 
 #define RD __device__ __forceinline__
@@ -187,16 +189,21 @@ static_assert(ps_order_is_permutation(), "ROGER_SVAT_PS_ORDER: a field is missin
 struct Io {
     char* __restrict__ ps;  // this thread's cell in plane 0 of its tile (parameter + state planes)
     char* __restrict__ fl;  // likewise in the flux planes (FLUX kernels only)
-    RD Io(double* ps_, double* fl_, int64_t i)
+    unsigned long long fm0, fm1;  // which flux planes are stored
+    RD Io(double* ps_, double* fl_, int64_t i, unsigned long long fm0_ = ~0ULL, unsigned long long fm1_ = ~0ULL)
         : ps(reinterpret_cast<char*>(ps_) + (size_t)(i >> kTileShift) * kTileBytesPS + (size_t)(i & kTileMask) * sizeof(double)),
-          fl(fl_ ? reinterpret_cast<char*>(fl_) + (size_t)(i >> kTileShift) * kTileBytesF + (size_t)(i & kTileMask) * sizeof(double) : nullptr) {}
+          fl(fl_ ? reinterpret_cast<char*>(fl_) + (size_t)(i >> kTileShift) * kTileBytesF + (size_t)(i & kTileMask) * sizeof(double) : nullptr),
+          fm0(fm0_), fm1(fm1_) {}
     RD double* at(int id) const { return reinterpret_cast<double*>(ps + (size_t)ps_slot(id) * (kTile * sizeof(double))); }
     RD double ldp(int id) const { return __ldg(at(id)); }
     RD double lds(int id) const { return *at(id); }
     RD void sts(int id, double v) const { *at(id) = v; }
     template <bool FLUX>
     RD void stf(int id, double v) const {
-        if (FLUX) *reinterpret_cast<double*>(fl + (size_t)(id - kFirstFlux) * (kTile * sizeof(double))) = v;
+        if (FLUX) {
+            const int b = id - kFirstFlux;
+            if (((b < 64 ? fm0 : fm1) >> (b & 63)) & 1ULL) *reinterpret_cast<double*>(fl + (size_t)b * (kTile * sizeof(double))) = v;
+        }
     }
     RD void pf(int id) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(at(id))); }
 };

@@ -22,7 +22,7 @@ def daily_fluxes_from_svat(model, ndays):
     names = sorted({f for fields in SUMS.values() for f in fields})
     model.engine.set_rate_fields(names)
     while day <= ndays:
-        sc = model.step(write_fluxes=True)
+        sc = model.step(write_fluxes=False)  # the accumulators themselves make the step store the flux planes they read -- and only those
         if sc.time % 86400 == 0:
             rates = model.engine.download_rates(reset=True)
             for k, fields in SUMS.items():
