@@ -406,7 +406,7 @@ def test_lazy_mirrors_on_the_cuda_engine():
     from tests.mini_setup import MiniSvatSetup
 
     shape = (24, 16)
-    forcing = synth.mixed_forcing(60, seed=42, start_doy=110)
+    forcing = synth.mixed_forcing(200, seed=42, start_doy=110)
     prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=43, lu_choices=(10, 11, 12, 8, 5, 9), masked_fraction=0.1)
     drivers = []
     for mode in ("eager", "lazy"):
