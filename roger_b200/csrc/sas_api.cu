@@ -338,6 +338,7 @@ struct roger_sas {
     bool have_nit_params = false, have_nit_forcing = false;
     double* d_san = nullptr;
     double* d_TTn = nullptr;
+    double* d_om = nullptr;   // ROGER_SAS_SPLIT: SAS function values between the two walks of a sub-step pass
     double* d_tt = nullptr;
     double* d_forcing = nullptr;
     double* d_out = nullptr;
@@ -368,6 +369,7 @@ struct roger_sas {
         pl.sa[0] = d_state[0]; pl.sa[1] = d_state[1]; pl.msa[0] = d_state[2]; pl.msa[1] = d_state[3];
         pl.san = d_san; pl.TTn = d_TTn; pl.tt = d_tt;
         pl.nmin[0] = d_state[4]; pl.nmin[1] = d_state[5];
+        pl.om = d_om;
         return pl;
     }
 };
@@ -448,6 +450,11 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     CU(cudaMalloc(&h->d_TTn, arr + pad));
     CU(cudaMemsetAsync(h->d_san, 0, arr + pad, h->stream));
     CU(cudaMemsetAsync(h->d_TTn, 0, arr + pad, h->stream));
+#if ROGER_SAS_SPLIT
+    static_assert(2 * ROGER_SAS_SPLIT_UNROLL <= 8, "scratch padding vs. the look-ahead of the split pass");
+    CU(cudaMalloc(&h->d_om, arr + pad));
+    CU(cudaMemsetAsync(h->d_om, 0, arr + pad, h->stream));
+#endif
     if (settings->store_tt) {
         CU(cudaMalloc(&h->d_tt, arr * RSP_COUNT));
         CU(cudaMemsetAsync(h->d_tt, 0, arr * RSP_COUNT, h->stream));
@@ -485,7 +492,7 @@ void roger_sas_destroy(roger_sas* h) {
     for (auto p : h->d_state) cudaFree(p);
     cudaFree(h->d_stats); cudaFree(h->d_C_s_prev); cudaFree(h->d_bounds); cudaFree(h->d_anion);
     cudaFree(h->d_nit_params); cudaFree(h->d_nit_forcing); cudaFree(h->d_nit_out);
-    cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
+    cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_om); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_params); cudaFree(h->d_stage); cudaFree(h->d_plan);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);

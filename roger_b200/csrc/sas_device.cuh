@@ -54,6 +54,7 @@ struct Planes {  // age-major arrays
     double* TTn;     // scratch: accumulated cumulative travel-time distribution (index j holds TTn[j + 1])
     double* tt;      // optional: RSP_COUNT x A x C
     double* nmin[2]; // nitrate only: age-ranked mineral nitrogen of the root zone / subsoil (same ring as sa / msa)
+    double* om;      // scratch of the split sub-step pass (ROGER_SAS_SPLIT): the SAS function value of every bin
 };
 
 // walks age bins 0..A-1 of one cell through the plane ring
@@ -552,6 +553,130 @@ __device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, 
     return c.anynan ? __longlong_as_double(0x7ff8000000000000LL) : c.mxv;
 }
 
+// The same pass split in two walks (ROGER_SAS_SPLIT): (1) cumulative StorAge -> SAS function value of every bin, stored to the
+// scratch array `om`; (2) the sequential bookkeeping from the stored values.  Walk 1 carries one accumulator and no travel-time
+// state, so four power evaluations fit into the register budget that holds two in the fused pass: the FP64 pipe sees twice the
+// independent work per warp (the fused pass keeps it 40 % busy at 4 warps per scheduler).  Price: 16 B more traffic per bin
+// and sub-step.  Same operations on the same values, hence the same bits.
+#ifndef ROGER_SAS_SPLIT
+#define ROGER_SAS_SPLIT 0
+#endif
+#ifndef ROGER_SAS_SPLIT_UNROLL
+#define ROGER_SAS_SPLIT_UNROLL 4
+#endif
+template <bool FIRST>
+__device__ __forceinline__ double substep_pass_pow_split(const CellCtx& cx, double S, double y, double flux, double h, double fh,
+                                                         double* __restrict__ san, double* __restrict__ TTn, double* __restrict__ omv) {
+    constexpr int U = ROGER_SAS_SPLIT_UNROLL;
+    const int A = cx.P.A;
+    const int64_t C = cx.P.C;
+    const PowPassConst k{S, 1.0 / S, y, flux, h, fh, 1.0 / fh};
+    const roger_pow_tables tabs = cx.tabs;
+    {   // walk 1: omega
+        const double* __restrict__ ps = san + cx.i;
+        double* __restrict__ po = omv + cx.i;
+        double acc_in = 0, om_prev = 0.0;
+        const int nfull = A / U;
+        double xn_[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) xn_[u] = ps[u * C];
+        for (int b = 0; b < nfull; b++) {
+            double xb[U], SAv[U], om[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) xb[u] = xn_[u];
+#pragma unroll
+            for (int u = 0; u < U; u++) xn_[u] = ps[(U + u) * C];  // look-ahead into the padding at the end
+#pragma unroll
+            for (int u = 0; u < U; u++) { acc_in += xb[u]; SAv[u] = acc_in; }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const double SA = SAv[u];
+                const bool in = (SA > 0) && (SA <= k.S);
+                const bool easy = in && (SA >= 0x1p-500);
+                const double xr = div_by(SA, k.S, k.rS);
+                double p = roger_pow_core(easy ? roger_pow_asu(xr) : 0x3fe0000000000000ULL, k.y, tabs);
+                if (in && !easy) p = roger_pow(SA / k.S, k.y, tabs);
+                om[u] = (SA > 0) ? ((SA <= k.S) ? p : 1.) : 0.;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {  // an empty bin repeats its predecessor's value bit for bit (same SA)
+                if (xb[u] == 0) om[u] = (u == 0) ? om_prev : om[u - 1];
+                po[u * C] = om[u];
+            }
+            om_prev = om[U - 1];
+            ps += U * C;
+            po += U * C;
+        }
+        for (int j = nfull * U; j < A; j++) {
+            const double x = ps[0];
+            acc_in += x;
+            const double SA = acc_in;
+            double o;
+            if (x == 0) o = om_prev;
+            else {
+                const bool in = (SA > 0) && (SA <= k.S);
+                const bool easy = in && (SA >= 0x1p-500);
+                const double xr = div_by(SA, k.S, k.rS);
+                double p = roger_pow_core(easy ? roger_pow_asu(xr) : 0x3fe0000000000000ULL, k.y, tabs);
+                if (in && !easy) p = roger_pow(SA / k.S, k.y, tabs);
+                o = (SA > 0) ? ((SA <= k.S) ? p : 1.) : 0.;
+            }
+            po[0] = o;
+            om_prev = o;
+            ps += C;
+            po += C;
+        }
+    }
+    // walk 2: travel-time bookkeeping
+    double* __restrict__ ps = san + cx.i;
+    double* __restrict__ pt = TTn + cx.i;
+    const double* __restrict__ po = omv + cx.i;
+    PowPassCarry c{0, 0, 0, 0.0, 0.0, false};
+    constexpr int V = 4;
+    int j = 0;
+    for (; j + V <= A; j += V) {
+        double xb[V], tb[V], om[V];
+#pragma unroll
+        for (int u = 0; u < V; u++) { xb[u] = ps[u * C]; tb[u] = FIRST ? 0.0 : pt[u * C]; om[u] = po[u * C]; }
+#pragma unroll
+        for (int u = 0; u < V; u++) {
+            const double x = xb[u];
+            const double d = om[u] - c.om_prev;
+            c.om_prev = om[u];
+            double tti = (d >= 0) ? d : 0;
+            const double q = k.flux * tti * k.h;
+            const double ttqi = (q > x) ? x : q;
+            tti = (ttqi == 0 || div_range_ok(ttqi)) ? div_by(ttqi, k.fh, k.rfh) : ttqi / k.fh;
+            const double xn = x + -tti * k.flux * k.h;
+            ps[u * C] = xn;
+            c.acc_new += xn;
+            c.anynan = c.anynan || isnan_d(c.acc_new);
+            c.mxv = (c.acc_new > c.mxv) ? c.acc_new : c.mxv;
+            c.acc_t += tti;
+            pt[u * C] = tb[u] + c.acc_t;
+        }
+        ps += V * C; pt += V * C; po += V * C;
+    }
+    for (; j < A; j++) {
+        const double x = ps[0], tb = FIRST ? 0.0 : pt[0], o = po[0];
+        const double d = o - c.om_prev;
+        c.om_prev = o;
+        double tti = (d >= 0) ? d : 0;
+        const double q = k.flux * tti * k.h;
+        const double ttqi = (q > x) ? x : q;
+        tti = (ttqi == 0 || div_range_ok(ttqi)) ? div_by(ttqi, k.fh, k.rfh) : ttqi / k.fh;
+        const double xn = x + -tti * k.flux * k.h;
+        ps[0] = xn;
+        c.acc_new += xn;
+        c.anynan = c.anynan || isnan_d(c.acc_new);
+        c.mxv = (c.acc_new > c.mxv) ? c.acc_new : c.mxv;
+        c.acc_t += tti;
+        pt[0] = tb + c.acc_t;
+        ps += C; pt += C; po += C;
+    }
+    return c.anynan ? __longlong_as_double(0x7ff8000000000000LL) : c.mxv;
+}
+
 // ---- one SAS-controlled withdrawal from layer `src`, optionally received by layer `dst` (dst < 0: leaves the
 // soil).  evapotranspiration.py:653-716, :831-895; subsurface_runoff.py:1531-1625, :1753-1815;
 // capillary_rise.py:404-500.
@@ -600,8 +725,13 @@ __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double f
         family_prepare(fam, mx.get());
         const bool first = (s == 0);
         if (fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh)) {
+#if ROGER_SAS_SPLIT
+            const double S_next = first ? substep_pass_pow_split<true>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn, cx.pl.om)
+                                        : substep_pass_pow_split<false>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn, cx.pl.om);
+#else
             const double S_next = first ? substep_pass_pow<U, true>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn)
                                         : substep_pass_pow<U, false>(cx, fam.S, fam.sp[1], flux, h, fh, san, TTn);
+#endif
             mx.init(S_next);
             continue;
         }
