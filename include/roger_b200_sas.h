@@ -88,12 +88,14 @@ typedef struct roger_sas_settings {
     int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day
                                (svat_transport_model_euler, transport.py:2063-2413; statistics / balance errors are those of the day's
                                last Euler step, as the reference's output shows them; the anion branch runs without statistics);
-                               2: RK4 (transport.py:1138-2047) is restated in the CPU oracle only -- roger_sas_create rejects it */
+                               2: RK4 (svat_transport_model_rk4, transport.py:1138-2047), isotope branch only: four stages of the Euler
+                               building blocks per step on stage copies of the StorAge (nine more scratch arrays of cells x ages) */
 } roger_sas_settings;
 
 typedef struct roger_sas roger_sas; /* opaque handle */
 
-#define ROGER_ENOTSUP 95 /* a SAS function id this backend does not implement (gamma = 4, reversed exponential = 52) */
+#define ROGER_ENOTSUP 95 /* a combination this backend does not evaluate: an unknown SAS function id, gamma parameters outside
+                            0 < a <= 170, 0 <= b <= 50, RK4 with a solute other than the isotope, ... (the message says which) */
 
 int roger_sas_create(roger_sas **out, int64_t n_cells, const roger_sas_settings *settings, int device);
 void roger_sas_destroy(roger_sas *h);
@@ -108,7 +110,8 @@ int roger_sas_age_base(roger_sas *h);
  * roger/models/svat_oxygen18 set_initial_conditions): sa[1:] = diff(linspace(0, S, ages)), sa[0] = 0, msa = conc0, msa[0] = 0.
  * S_rz, S_ss: n_cells doubles (host). */
 int roger_sas_init_linear(roger_sas *h, const double *S_rz, const double *S_ss, double conc0);
-/* maskCatch (n_cells) and SAS parameters (RSP_COUNT * n_cells * 8), roger/variables.py:4275 */
+/* maskCatch (n_cells) and SAS parameters (RSP_COUNT * n_cells * 8), roger/variables.py:4275.  Every family of roger/core/sas.py:
+ * uniform 1, dirac 2, Kumaraswamy 3 / 31-37, gamma 4 (0 < a <= 170, 0 <= b <= 50), exponential 51 / 52, power 6 / 61 / 62. */
 int roger_sas_set_parameters(roger_sas *h, const double *mask_catch, const double *sas_params);
 /* anion transport only: partition coefficients of transpiration and percolation (vs.alpha_transp, vs.alpha_q), land use
  * and root-zone saturation storage (crop nutrient uptake stops above 80 % saturation, evapotranspiration.py:931-938);
@@ -143,6 +146,9 @@ int roger_sas_download_tt(roger_sas *h, int process, double *host);
  * roger_b200/csrc/roger_pow.h (host pointers, n doubles each): the parity tests use it to prove that the device and
  * the host evaluate the shared power function to identical bits. */
 int roger_pow_device(const double *x, const double *y, double *out, int64_t n, int device);
+/* out[i] = P(a[i], x[i]), the regularised lower incomplete gamma function of the gamma SAS family (sas.py:153,
+ * scipy.special.gammainc), evaluated by the device build of roger_b200/csrc/roger_gamma.h (host pointers, n doubles each) */
+int roger_gammainc_device(const double *a, const double *x, double *out, int64_t n, int device);
 /* self-test of the kernel's hoisted-reciprocal division (sas_device.cuh div_by) against the division instruction on n
  * pseudo-random operand pairs; *mismatches must come back 0 */
 int roger_selftest_division(int64_t n, uint64_t seed, int device, int64_t *mismatches);

@@ -12,6 +12,7 @@ LIB = os.path.join(HERE, "_build", "libroger_oracle.so")
 
 def build(force=False):
     deps = ("svat_oracle.c", "sas_oracle.c", "Makefile", os.path.join("..", "roger_b200", "csrc", "roger_pow.h"),
+            os.path.join("..", "roger_b200", "csrc", "roger_gamma.h"),
             os.path.join("..", "roger_b200", "csrc", "roger_pow_tables.h"), os.path.join("..", "include", "roger_b200_sas.h"),
             os.path.join("..", "include", "roger_b200_fields.h"))
     if force or not os.path.exists(LIB) or any(os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(LIB) for f in deps):

@@ -4,8 +4,10 @@
  * TEST INFRASTRUCTURE (see svat_oracle.c): only tests/, __graft_entry__.smoke() and bench.py's CPU legs use it.
  * Parity status: PINNED against outputs of the reference's own NumPy backend (tests/golden/sas_*.npz produced
  * by tests/golden/make_sas_golden.py).  SAS families restated: uniform (1), dirac (2), Kumaraswamy (3, 31-37),
- * exponential (51, 52), power (6, 61, 62); the gamma family (4, scipy.special.gammainc) is not restated and
- * is not used by any benchmark configuration.
+ * gamma (4), exponential (51, 52), power (6, 61, 62).  The gamma family calls scipy.special.gammainc in the reference;
+ * roger_gamma.h restates the published series / continued fraction it is built on (not scipy's Lanczos prefactor and
+ * asymptotic branch) and is pinned by tolerance: a table of scipy outputs (tests/golden/gammainc_table.npz, 4e-15) and
+ * the reference fixtures sas_gamma52 / sas_euler_gamma52 (1e-10).
  */
 #include <math.h>
 #include <stdint.h>
@@ -13,6 +15,7 @@
 #include <string.h>
 #include "../include/roger_b200_sas.h"
 #include "../roger_b200/csrc/roger_pow.h"
+#include "../roger_b200/csrc/roger_gamma.h"
 
 /* Which pow the SAS functions call.  0: the C library's pow -- what NumPy's float64 `power` loop calls when its
  * AVX512 SVML dispatch is off; the mode the oracle is PINNED in against the reference fixtures.  1: roger_pow()
@@ -139,6 +142,35 @@ static void sas_kumaraswami(const sas_ctx *c, const double *SA, double *sp, doub
     }
     for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
 }
+/* scipy.special.gammainc(a, x): argument rules of cephes igam, then series / continued fraction on the prefactor */
+double sas_oracle_gammainc(double a, double x)
+{
+    const double G = exp(lgamma(a));
+    if (g_pow_mode) {
+        const roger_pow_tables t = {roger_pow_log_tab_h, roger_pow_exp_tab_h};
+        return roger_gammainc(a, x, G, t);
+    }
+    if (!(x >= 0) || !(a >= 0)) return NAN;
+    if (a == 0) return (x > 0) ? 1.0 : NAN;
+    if (x == 0) return 0.0;
+    if (isinf(a)) return isinf(x) ? NAN : 0.0;
+    if (isinf(x)) return 1.0;
+    return roger_gammainc_from_fac(a, x, pow(x, a) * exp(-x) / G);
+}
+static void sas_gamma(const sas_ctx *c, const double *SA, const double *sp, double m, double *Om)
+{ /* sas.py:137-160: S carries the family mask, so every other id selects the constant 0; the quotient by
+   * exp(gammaln(a)) on top of the already regularised gammainc is the reference's */
+    const int N = c->A + 1;
+    const double mask = (sp[0] == 4) ? 1.0 : 0.0;
+    const double S = np_max(SA, N) * mask * m;
+    const double G = (mask != 0) ? exp(lgamma(sp[1])) : 1.0;
+    for (int j = 0; j < N; j++) {
+        double v = 0.;
+        if ((SA[j] > 0) && (SA[j] < S)) v = sas_oracle_gammainc(sp[1], sp[2] * SA[j] / S) / G;
+        Om[j] = v * mask * m;
+    }
+    for (int j = 0; j < N; j++) Om[j] = ((S <= 0) ? 0 : Om[j]) * m;
+}
 static void sas_exponential(const sas_ctx *c, const double *SA, const double *sp, double m, double *Om)
 { /* sas.py:163-191 */
     const int N = c->A + 1;
@@ -176,7 +208,8 @@ static void sas_sum_families(const sas_ctx *c, const double *SA, double *sp, dou
     for (int j = 0; j < N; j++) TT[j] += Om[j];
     sas_kumaraswami(c, SA, sp, m, Om);
     for (int j = 0; j < N; j++) TT[j] += Om[j];
-    /* gamma family (id 4) not restated: contributes 0 for every other id */
+    sas_gamma(c, SA, sp, m, Om);
+    for (int j = 0; j < N; j++) TT[j] += Om[j];
     sas_exponential(c, SA, sp, m, Om);
     for (int j = 0; j < N; j++) TT[j] += Om[j];
     sas_power(c, SA, sp, m, Om);

@@ -17,7 +17,7 @@ COMMON_HEADERS = ["roger_pow.h", "roger_pow_tables.h", os.path.join(INC, "roger_
                   os.path.join(INC, "roger_b200_sas.h")]
 SOURCES = {  # source -> headers of its own
     "svat_api.cu": ["svat_device.cuh"],
-    "sas_api.cu": ["sas_device.cuh", "sas_cta.cuh"],
+    "sas_api.cu": ["sas_device.cuh", "roger_gamma.h"],
 }
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -192,7 +192,7 @@ k_sas_day_nitrate(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const
 #ifndef ROGER_EULER_MIN_BLOCKS
 #define ROGER_EULER_MIN_BLOCKS 1
 #endif
-template <bool STATS>
+template <bool STATS, bool RK4>
 __global__ void __launch_bounds__(ROGER_EULER_BLOCK, ROGER_EULER_MIN_BLOCKS)
 k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
                 const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out,
@@ -207,7 +207,7 @@ k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
-    euler_day<STATS>(cx, forcing, mask[i], sas_params, out, stats, C_s_prev, bounds, atol, rtol);
+    euler_day<STATS, RK4>(cx, forcing, mask[i], sas_params, out, stats, C_s_prev, bounds, atol, rtol);
 }
 
 __global__ void __launch_bounds__(ROGER_EULER_BLOCK, ROGER_EULER_MIN_BLOCKS)
@@ -297,6 +297,20 @@ __global__ void k_pow_array(const double* __restrict__ x, const double* __restri
         out[i] = use_exp ? roger_exp(x[i], tabs) : roger_pow(x[i], y[i], tabs);
 }
 
+__global__ void k_gammainc_array(const double* __restrict__ a, const double* __restrict__ x, const double* __restrict__ G, double* __restrict__ out,
+                                 int64_t n) {
+    __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
+    __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
+    for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
+        s_log[k] = d_pow_log_tab[k];
+        s_exp[k] = d_pow_exp_tab[k];
+    }
+    __syncthreads();
+    const roger_pow_tables tabs{s_log, s_exp};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = roger_gammainc(a[i], x[i], G[i], tabs);
+}
+
 // div_by() against the division instruction on pseudo-random operand pairs (splitmix64 bits -> doubles with
 // exponents inside the guarded range, quotients on both sides of one)
 __global__ void k_div_selftest(uint64_t seed, int64_t n, unsigned long long* mismatches) {
@@ -338,7 +352,9 @@ struct roger_sas {
     bool have_nit_params = false, have_nit_forcing = false;
     double* d_san = nullptr;
     double* d_TTn = nullptr;
-    double* d_om = nullptr;   // ROGER_SAS_SPLIT: SAS function values between the two walks of a sub-step pass
+    double* d_om = nullptr;   // ROGER_SAS_SPLIT: SAS function values between the two walks of a sub-step pass; RK4: a stage array
+    double* d_rev[2] = {nullptr, nullptr};  // SAS family 52: cumulative StorAge read backwards (allocated by roger_sas_set_parameters)
+    double* d_rk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // RK4: stage array + accumulated travel-time distributions
     double* d_tt = nullptr;
     double* d_forcing = nullptr;
     double* d_out = nullptr;
@@ -370,6 +386,8 @@ struct roger_sas {
         pl.san = d_san; pl.TTn = d_TTn; pl.tt = d_tt;
         pl.nmin[0] = d_state[4]; pl.nmin[1] = d_state[5];
         pl.om = d_om;
+        for (int k = 0; k < 6; k++) pl.rk[k] = d_rk[k];
+        pl.rev[0] = d_rev[0]; pl.rev[1] = d_rev[1];
         return pl;
     }
 };
@@ -415,7 +433,10 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     if (settings->solute < 0 || settings->solute > 2) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope), 1 (anion) or 2 (nitrate)");
     if (settings->solute == 2 && (settings->solver != 0 || settings->age_statistics))
         return fail(ROGER_ENOTSUP, "roger_sas_create: nitrate runs with the deterministic solver and without age statistics");
-    if (settings->solver != 0 && settings->solver != 1) return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic) or 1 (Euler)");
+    if (settings->solver < 0 || settings->solver > 2)
+        return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic), 1 (Euler) or 2 (RK4)");
+    if (settings->solver == 2 && settings->solute != 0)
+        return fail(ROGER_ENOTSUP, "roger_sas_create: the RK4 solver runs the isotope branch only");
     if (settings->solver == 1 && settings->solute != 0 && settings->age_statistics)
         return fail(ROGER_ENOTSUP, "roger_sas_create: the anion branch of the explicit Euler solver runs without age statistics");
     int ndev = 0;
@@ -455,6 +476,16 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     CU(cudaMalloc(&h->d_om, arr + pad));
     CU(cudaMemsetAsync(h->d_om, 0, arr + pad, h->stream));
 #endif
+    if (settings->solver == 2) {  // stage copies and the accumulated stage distributions of the Runge-Kutta solver
+        if (!h->d_om) {
+            CU(cudaMalloc(&h->d_om, arr + pad));
+            CU(cudaMemsetAsync(h->d_om, 0, arr + pad, h->stream));
+        }
+        for (int k = 0; k < 6; k++) {
+            CU(cudaMalloc(&h->d_rk[k], arr));
+            CU(cudaMemsetAsync(h->d_rk[k], 0, arr, h->stream));
+        }
+    }
     if (settings->store_tt) {
         CU(cudaMalloc(&h->d_tt, arr * RSP_COUNT));
         CU(cudaMemsetAsync(h->d_tt, 0, arr * RSP_COUNT, h->stream));
@@ -492,6 +523,8 @@ void roger_sas_destroy(roger_sas* h) {
     for (auto p : h->d_state) cudaFree(p);
     cudaFree(h->d_stats); cudaFree(h->d_C_s_prev); cudaFree(h->d_bounds); cudaFree(h->d_anion);
     cudaFree(h->d_nit_params); cudaFree(h->d_nit_forcing); cudaFree(h->d_nit_out);
+    for (int k = 0; k < 6; k++) cudaFree(h->d_rk[k]);
+    cudaFree(h->d_rev[0]); cudaFree(h->d_rev[1]);
     cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_om); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_params); cudaFree(h->d_stage); cudaFree(h->d_plan);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -537,20 +570,38 @@ int roger_sas_set_parameters(roger_sas* h, const double* mask_catch, const doubl
     CU(cudaSetDevice(h->device));
     const int64_t C = h->C;
     std::vector<double> t((size_t)RSP_COUNT * 8 * (size_t)C);
+    bool any52 = false;
     for (int p = 0; p < RSP_COUNT; p++)
         for (int64_t i = 0; i < C; i++) {
             const double* row = sas_params + ((size_t)p * (size_t)C + (size_t)i) * 8;
             const double id = row[0];
-            const bool ok = id == 0 || id == 1 || id == 2 || id == 3 || (id >= 31 && id <= 37 && id == std::floor(id)) || id == 51 ||
-                            id == 6 || id == 61 || id == 62;
+            const bool ok = id == 0 || id == 1 || id == 2 || id == 3 || (id >= 31 && id <= 37 && id == std::floor(id)) || id == 4 ||
+                            id == 51 || id == 52 || id == 6 || id == 61 || id == 62;
             if (!ok) {
                 char buf[320];
-                snprintf(buf, sizeof buf, "roger_sas_set_parameters: SAS function id %g (process %d, cell %lld) is not implemented on the device "
-                         "(gamma = 4 and time-reversed exponential = 52 are outside this backend)", id, p, (long long)i);
+                snprintf(buf, sizeof buf, "roger_sas_set_parameters: SAS function id %g (process %d, cell %lld) is not one of the reference's "
+                         "(roger/core/sas.py: 1, 2, 3, 31-37, 4, 51, 52, 6, 61, 62)", id, p, (long long)i);
                 return fail(ROGER_ENOTSUP, buf);
             }
             for (int k = 0; k < 8; k++) t[((size_t)p * 8 + (size_t)k) * (size_t)C + (size_t)i] = row[k];
+            if (id == 4) {  // gamma family (sas.py:137-160): Gamma(a) = exp(gammaln(a)) is a per-flux constant, computed here once
+                if (!(row[1] > 0 && row[1] <= ROGER_GAMMA_A_MAX && row[2] >= 0 && row[2] <= ROGER_GAMMA_B_MAX)) {
+                    char buf[320];
+                    snprintf(buf, sizeof buf, "roger_sas_set_parameters: gamma SAS function (process %d, cell %lld) with a = %g, b = %g: this backend "
+                             "evaluates 0 < a <= %g, 0 <= b <= %g", p, (long long)i, row[1], row[2], ROGER_GAMMA_A_MAX, ROGER_GAMMA_B_MAX);
+                    return fail(ROGER_ENOTSUP, buf);
+                }
+                t[((size_t)p * 8 + 3) * (size_t)C + (size_t)i] = std::exp(std::lgamma(row[1]));
+            }
+            if (id == 52) any52 = true;
         }
+    if (any52 && !h->d_rev[0]) {  // the backwards-read cumulative StorAge of family 52 (two scratch arrays of cells x ages)
+        const size_t arr = sizeof(double) * (size_t)C * (size_t)h->st.ages;
+        for (int k = 0; k < 2; k++) {
+            CU(cudaMalloc(&h->d_rev[k], arr));
+            CU(cudaMemsetAsync(h->d_rev[k], 0, arr, h->stream));
+        }
+    }
     CU(cudaMemcpyAsync(h->d_params, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_mask, mask_catch, sizeof(double) * (size_t)C, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -563,19 +614,30 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     CU(cudaEventRecord(h->ev0, h->stream));
     const int threads = ROGER_SAS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
-    if (h->st.solver == 1) {
+    if (h->st.solver != 0) {
         const int eb = (int)((h->C + ROGER_EULER_BLOCK - 1) / ROGER_EULER_BLOCK);
         if (h->st.solute == 1) {
             AnionParams ap{nullptr, nullptr, nullptr, nullptr};
             if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
             k_sas_day_euler_anion<<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
                                                                            h->d_out, ap);
-        } else if (h->st.age_statistics)
-            k_sas_day_euler<true><<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
-                                                                           h->d_out, h->d_stats, h->d_C_s_prev, h->d_bounds, h->atol, h->rtol);
-        else
-            k_sas_day_euler<false><<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
-                                                                            h->d_out, nullptr, nullptr, nullptr, 0.0, 0.0);
+        } else {
+            auto launch = [&](auto kernel) {
+                if (h->st.age_statistics)
+                    kernel<<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+                                                                    h->d_stats, h->d_C_s_prev, h->d_bounds, h->atol, h->rtol);
+                else
+                    kernel<<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+                                                                    nullptr, nullptr, nullptr, 0.0, 0.0);
+            };
+            if (h->st.solver == 2) {
+                if (h->st.age_statistics) launch(k_sas_day_euler<true, true>);
+                else launch(k_sas_day_euler<false, true>);
+            } else {
+                if (h->st.age_statistics) launch(k_sas_day_euler<true, false>);
+                else launch(k_sas_day_euler<false, false>);
+            }
+        }
     } else if (h->st.solute == 2) {
         if (!h->have_nit_params || !h->have_nit_forcing)
             return fail(ROGER_EINVAL, "roger_sas_step: nitrate needs roger_sas_set_nitrate_parameters and the day's roger_sas_set_nitrate_forcing");
@@ -732,6 +794,32 @@ int roger_pow_device(const double* x, const double* y, double* out, int64_t n, i
     CU(cudaGetLastError());
     CU(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return 0;
+}
+
+// out[i] = roger_gammainc(a[i], x[i]) evaluated by the device build of roger_gamma.h, Gamma(a) = exp(lgamma(a)) computed here on the host
+// as roger_sas_set_parameters does.  Host pointers.
+int roger_gammainc_device(const double* a, const double* x, double* out, int64_t n, int device) {
+    if (!a || !x || !out || n <= 0) return fail(ROGER_EINVAL, "roger_gammainc_device: bad argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(ROGER_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    CU(cudaSetDevice(device));
+    std::vector<double> G((size_t)n);
+    for (int64_t i = 0; i < n; i++) G[(size_t)i] = std::exp(std::lgamma(a[i]));
+    double *da = nullptr, *dx = nullptr, *dG = nullptr, *dout = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    CU(cudaMalloc(&da, bytes));
+    CU(cudaMalloc(&dx, bytes));
+    CU(cudaMalloc(&dG, bytes));
+    CU(cudaMalloc(&dout, bytes));
+    CU(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dG, G.data(), bytes, cudaMemcpyHostToDevice));
+    k_gammainc_array<<<148 * 8, 256>>>(da, dx, dG, dout, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(dx); cudaFree(dG); cudaFree(dout);
     return 0;
 }
 

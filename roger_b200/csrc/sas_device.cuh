@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "roger_pow.h"
+#include "roger_gamma.h"
 #include "../../include/roger_b200_sas.h"
 
 #ifndef ROGER_SAS_LOADGROUP
@@ -55,6 +56,8 @@ struct Planes {  // age-major arrays
     double* tt;      // optional: RSP_COUNT x A x C
     double* nmin[2]; // nitrate only: age-ranked mineral nitrogen of the root zone / subsoil (same ring as sa / msa)
     double* om;      // scratch of the split sub-step pass (ROGER_SAS_SPLIT): the SAS function value of every bin
+    double* rev[2];  // SAS family 52 only: masked cumulative StorAge of the root zone / subsoil (bin-major), read backwards by omega()
+    double* rk[6];   // RK4 solver only: the fourth stage array and the five accumulated travel-time distributions (bin-major like TTn)
 };
 
 // walks age bins 0..A-1 of one cell through the plane ring
@@ -118,8 +121,12 @@ struct Family {
     // per sub-step
     double S;          // max(SA) * m
     double uS, ulam, umask;
-    bool is_uniform, is_dirac, is_kum, is_exp51, is_pow;
+    bool is_uniform, is_dirac, is_kum, is_gamma, is_exp51, is_exp52, is_pow;
     bool fast;         // every inactive family provably contributes +0.0
+    // id 52 (the exponential family read backwards along the age axis, sas.py:183): the masked cumulative StorAge of the layer,
+    // written by the caller before the pass -- element k * rev_stride holds SA[k + 1]
+    const double* rev;
+    int64_t rev_stride;
 };
 
 __device__ __forceinline__ double s_rel(double S, const double* sp, double m) {
@@ -133,6 +140,8 @@ __device__ __forceinline__ void family_begin(Family& f, const double* sp_global,
 #pragma unroll
     for (int k = 0; k < 8; k++) f.sp[k] = sp_global[k * stride];
     f.m = m;
+    f.rev = nullptr;
+    f.rev_stride = 0;
 }
 
 // per sub-step preparation: everything that depends on max(SA) only
@@ -157,7 +166,9 @@ __device__ __forceinline__ void family_prepare(Family& f, double mx) {
         if (id == 36) { sp[1] = sp[3] + ((1 - r) * sp[4]); }
         if (id == 37) { sp[2] = sp[3] + (r * sp[4]); }
     }
+    f.is_gamma = (id == 4);   // sp[3] carries Gamma(sp[1]) = exp(lgamma(sp[1])), put there by roger_sas_set_parameters
     f.is_exp51 = (id == 51);
+    f.is_exp52 = (id == 52);
     f.is_pow = (id == 6 || id == 61 || id == 62);
     {   // sas.py:209-229
         const double r = s_rel(f.S, f.sp, m);
@@ -171,8 +182,7 @@ __device__ __forceinline__ void family_prepare(Family& f, double mx) {
 }
 
 // cumulative SAS distribution at age index jj (0..A) where the cumulative StorAge is SA: the sum of the five
-// families in the reference's order (transport.py:399-428; the gamma family and the time-reversed exponential,
-// ids 4 and 52, are rejected by roger_sas_set_parameters)
+// families in the reference's order (transport.py:399-428)
 __device__ __forceinline__ double omega(const Family& f, const SasParams& P, const roger_pow_tables tabs, int jj, double SA) {
     const double m = f.m;
     double t = 0.0;
@@ -197,12 +207,25 @@ __device__ __forceinline__ double omega(const Family& f, const SasParams& P, con
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
     }
-    if (f.is_exp51 || !f.fast) {  // sas.py:163-191
+    if (f.is_gamma) {  // sas.py:137-160; S carries the family mask there, so every other id selects the constant 0 (skipped: + 0.0)
+        const double S = f.S;
+        double v = 0.;
+        if ((SA > 0) && (SA < S)) v = roger_gammainc(f.sp[1], f.sp[2] * SA / S, f.sp[3], tabs) / f.sp[3];
+        double o = v * 1.0 * m;
+        o = ((S <= 0) ? 0 : o) * m;
+        t += o;
+    }
+    if (f.is_exp51 || f.is_exp52 || !f.fast) {  // sas.py:163-191
         const double S = f.S;
         double o = 0.0;
         if (f.is_exp51) o = (SA > 0) ? ((SA < S) ? 1 - roger_exp(f.sp[1] * (-1) * (SA / S), tabs) : 1.) : 0.;
         o = o * m;
-        o = o * m;  // the id-52 select of sas.py:183 multiplies by maskCatch once more
+        if (f.is_exp52) {  // [..., ::-1]: age index jj takes the value at nages - 1 - jj
+            const int k = P.A - jj;
+            const double SAr = (k == 0) ? 0.0 * m : f.rev[(int64_t)(k - 1) * f.rev_stride];
+            o = (SAr > 0) ? ((SAr < S) ? 1 - roger_exp(f.sp[1] * (-1) * (SAr / S), tabs) : 1.) : 0.;
+        }
+        o = o * m;
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
     }
@@ -418,7 +441,7 @@ struct SubstepCarry {
 template <int U>
 __device__ __forceinline__ void substep_block(const CellCtx& cx, const Family& fam, SubstepCarry& k, int j0, int n, const double* xb,
                                               const double* tb, bool first, double flux, double h, double fh, double m,
-                                              double* __restrict__ san, double* __restrict__ TTn) {
+                                              double* __restrict__ san, double* __restrict__ TTn, double* __restrict__ rev_next = nullptr) {
     double om[U];
     double SAv[U];
 #pragma unroll
@@ -445,6 +468,7 @@ __device__ __forceinline__ void substep_block(const CellCtx& cx, const Family& f
             san[o] = xn;
             k.acc_new += xn;
             k.mxn.push(k.acc_new);
+            if (rev_next) rev_next[o] = k.acc_new;
             k.acc_t += tti;
             TTn[o] = (first ? 0.0 : tb[u]) + k.acc_t;
         }
@@ -697,6 +721,9 @@ __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double f
     NpMax mx;
     const double SA0 = 0. * m;
     mx.init(SA0);
+    // family 52 reads the cumulative StorAge backwards: two scratch planes take it in turns (this sub-step's, the next one's)
+    const bool is52 = (sp_global[0] == 52);
+    double* const rv[2] = {cx.pl.rev[0], cx.pl.rev[1]};
     {
         double acc = 0;
         int j = 0;
@@ -709,6 +736,7 @@ __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double f
                 san[cx.lin(j + q)] = v[q];
                 acc += v[q];
                 mx.push(acc * m);
+                if (is52) rv[0][cx.lin(j + q)] = acc * m;
             }
         }
         for (; j < A; j++) {
@@ -716,12 +744,19 @@ __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double f
             san[cx.lin(j)] = v;
             acc += v;
             mx.push(acc * m);
+            if (is52) rv[0][cx.lin(j)] = acc * m;
         }
     }
     Family fam;
     family_begin(fam, sp_global, sp_stride, m);
     const double fh = flux * h;
     for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
+        double* rev_next = nullptr;
+        if (is52) {
+            fam.rev = rv[s & 1] + cx.i;
+            fam.rev_stride = P.C;
+            rev_next = rv[(s + 1) & 1];
+        }
         family_prepare(fam, mx.get());
         const bool first = (s == 0);
         if (fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh)) {
@@ -757,9 +792,9 @@ __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double f
                 xn_[u] = (jn < A) ? san[cx.lin(jn)] : 0.0;
                 tn_[u] = (!first && jn < A) ? TTn[cx.lin(jn)] : 0.0;
             }
-            substep_block<U>(cx, fam, k, j0, U, xb, tb, first, flux, h, fh, m, san, TTn);
+            substep_block<U>(cx, fam, k, j0, U, xb, tb, first, flux, h, fh, m, san, TTn, rev_next);
         }
-        if (j0 < A) substep_block<U>(cx, fam, k, j0, A - j0, xn_, tn_, first, flux, h, fh, m, san, TTn);
+        if (j0 < A) substep_block<U>(cx, fam, k, j0, A - j0, xn_, tn_, first, flux, h, fh, m, san, TTn, rev_next);
         mx = k.mxn;
     }
     return true;
@@ -1506,7 +1541,7 @@ struct EulerStats {  // diagnostics of the day's last Euler step (STATS kernels)
 // ANION: the conservative-solute branch (bromide / chloride; transport.py:2144-2156, :2320-2343, :2378-2407): msa holds solute
 // mass, calc_mtt (:582-596) with the partition coefficients alpha_transp / alpha_q, no mixing statements, the anion storage
 // kernels' `msa = 0 where sa <= 0` fused into the store.
-template <bool LAST, bool STATS, bool ANION>
+template <bool LAST, bool STATS, bool ANION, bool RK4 = false>
 __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
                                         double* __restrict__ out, EulerStats* es, double alpha_t, double alpha_q) {
     const SasParams& P = cx.P;
@@ -1561,45 +1596,45 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
     };
     auto clean_rz = [&](double ms, double s) { return ((s > 0) && (ms > 0)) ? ms * self_ratio(s) + 0.0 : 0.0; };
     auto clean_ss = [&](double ms, double s) { return (s > 0) ? ms * self_ratio(s) + 0.0 : 0.0; };
-    // P1: S of both layers (calc_SA :343-359 times maskCatch, np.max over nages points)
-    NpMax mx_rz, mx_ss;
-    mx_rz.init(0.0 * m);
-    mx_ss.init(0.0 * m);
-    {
-        double acc_a = 0, acc_b = 0;
-        Cursor c(P, i);
-        for (int j = 0; j < A; j++, c.next()) {
-            acc_a += s_rz[c.off];
-            acc_b += s_ss[c.off];
-            mx_rz.push(acc_a * m);
-            mx_ss.push(acc_b * m);
-        }
-    }
     EulerFlux fx[5];  // evap_soil, transp, q_rz (root zone); cpr_rz, q_ss (subsoil)
     Family fams[5];
+    const double flx[5] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_rz), F(RSF_cpr_rz), F(RSF_q_ss)};
     {
         const int procs[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
-        const double flx[5] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_rz), F(RSF_cpr_rz), F(RSF_q_ss)};
-        const double mxa = mx_rz.get(), mxb = mx_ss.get();
+#pragma unroll
+        for (int k = 0; k < 5; k++) family_begin(fams[k], SP(procs[k]), C, m);
+    }
+    bool any52 = false;  // family 52 reads the layer's cumulative StorAge backwards: the S passes below leave it in scratch planes
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (fams[k].sp[0] == 52) {
+            any52 = true;
+            fams[k].rev = cx.pl.rev[(k < 3) ? 0 : 1] + i;
+            fams[k].rev_stride = C;
+        }
+    }
+    // one logarithm per layer and bin serves every power-law flux of the layer (skipped for empty bins)
+    bool logs_a = false, logs_b = false;
+    double S_a = 0, rS_a = 0, S_b = 0, rS_b = 0;
+    // per-flux scalars from S = max(SA) of the two layers; `half`: the RK4 stages 2 and 3 advance by h / 2 (:1433-1449, :1583-1599)
+    auto prepare = [&](double mxa, double mxb, bool half) {
 #pragma unroll
         for (int k = 0; k < 5; k++) {
-            family_begin(fams[k], SP(procs[k]), C, m);
             family_prepare(fams[k], (k < 3) ? mxa : mxb);
             fx[k].flux = flx[k];
-            fx[k].fh = flx[k] * h;
+            fx[k].fh = half ? flx[k] * h / 2 : flx[k] * h;
             fx[k].active = !(fx[k].fh <= 0);
             const Family& f = fams[k];
-            fx[k].sa_only = f.fast && !f.is_uniform && !f.is_dirac;
+            fx[k].sa_only = f.fast && !f.is_uniform && !f.is_dirac && !f.is_exp52;
             fx[k].powfast = f.fast && f.is_pow && (f.S > 0) && div_range_ok(f.S) && (f.sp[1] - f.sp[1] == 0.0);
             fx[k].S = f.S;
             fx[k].y = f.sp[1];
             fx[k].rS = 1.0 / f.S;
         }
-    }
-    // one logarithm per layer and bin serves every power-law flux of the layer (skipped for empty bins)
-    const bool logs_a = (fx[0].active && fx[0].powfast) || (fx[1].active && fx[1].powfast) || (fx[2].active && fx[2].powfast);
-    const bool logs_b = (fx[3].active && fx[3].powfast) || (fx[4].active && fx[4].powfast);
-    const double S_a = fx[0].S, rS_a = fx[0].rS, S_b = fx[3].S, rS_b = fx[3].rS;
+        logs_a = (fx[0].active && fx[0].powfast) || (fx[1].active && fx[1].powfast) || (fx[2].active && fx[2].powfast);
+        logs_b = (fx[3].active && fx[3].powfast) || (fx[4].active && fx[4].powfast);
+        S_a = fx[0].S; rS_a = fx[0].rS; S_b = fx[3].S; rS_b = fx[3].rS;
+    };
     auto layer_log = [&](int layer, double SA, double sa_d) {
         EulerLog g{0.0, 0.0, false, false};
         if ((layer == 0 ? logs_a : logs_b) && !(sa_d == 0)) g = euler_log(cx, SA, layer == 0 ? S_a : S_b, layer == 0 ? rS_a : rS_b);
@@ -1609,8 +1644,51 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
 #pragma unroll
         for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega(fams[k], P, cx.tabs, 0, 0.0 * m) : 0.0;
     };
+    auto set_sums = [&](const double* sums) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            fx[k].ssum = sums[k];
+            fx[k].ssum_ok = (sums[k] > 0) && div_range_ok(sums[k]);
+            fx[k].rssum = 1.0 / sums[k];
+        }
+    };
+    // backward travel-time distributions of bin j (calc_TT_num / calc_tt_num, transport.py:859-945) from the masked cumulative StorAge
+    // at the bin's upper edge (na, nb) and its increment over the bin (da, db)
+    auto tt_of_bin = [&](int j, double na, double nb, double da, double db, double* tt) {
+        const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const double q = euler_q(fx[k], fams[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
+            const double p = (q > 0) ? ((fx[k].ssum_ok && div_range_ok(q)) ? div_by(q, fx[k].ssum, fx[k].rssum) : q / fx[k].ssum) : 0;
+            fx[k].accT = (j == 0) ? p : fx[k].accT + p;  // np.cumsum starts from the first element
+            const double d = fx[k].accT - fx[k].Tprev;
+            fx[k].Tprev = fx[k].accT;
+            tt[k] = (d >= 0) ? d : 0;
+        }
+    };
+    if (!RK4) {
+        // P1: S of both layers (calc_SA :343-359 times maskCatch, np.max over nages points)
+        NpMax mx_rz, mx_ss;
+        mx_rz.init(0.0 * m);
+        mx_ss.init(0.0 * m);
+        {
+            double acc_a = 0, acc_b = 0;
+            Cursor c(P, i);
+            for (int j = 0; j < A; j++, c.next()) {
+                acc_a += s_rz[c.off];
+                acc_b += s_ss[c.off];
+                mx_rz.push(acc_a * m);
+                mx_ss.push(acc_b * m);
+                if (any52) {
+                    cx.pl.rev[0][cx.lin(j)] = acc_a * m;
+                    cx.pl.rev[1][cx.lin(j)] = acc_b * m;
+                }
+            }
+        }
+        prepare(mx_rz.get(), mx_ss.get(), false);
+    }
     // P2: normalisation constants
-    {
+    if (!RK4) {
         reset();
         double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
         double sums[5];
@@ -1627,11 +1705,155 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
 #pragma unroll
                 for (int k = 0; k < 5; k++) v[k] = euler_q(fx[k], fams[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
             }, sums);
+        set_sums(sums);
+    }
+    // Runge-Kutta solver (settings.sas_solver = "RK4", svat_transport_model_rk4 transport.py:1138-2047): four stages of the Euler
+    // building blocks on stage copies of the StorAge (scratch planes, bin-major like TTn); stage 1 advances by h, stages 2 and 3 by
+    // h / 2 with mass-like bookkeeping of the stage concentrations, stage 3 tests sarkn - dsarkn < 0, dsarkn_ss1 of stage 1 lacks
+    // the flux -- all as written in the reference.  k1 + 2 k2 + 2 k3 + k4 accumulates in the reference's order in five more scratch
+    // planes; P3 below divides by 6 and performs the Euler solver's update with the combined distributions (:1836-1945).
+    if (RK4) {
+        double* __restrict__ sr = cx.pl.san;
+        double* __restrict__ ss = cx.pl.TTn;
+        double* __restrict__ mr = cx.pl.om;
+        double* __restrict__ mss = cx.pl.rk[0];
+        double* __restrict__ k0 = cx.pl.rk[1];
+        double* __restrict__ k1 = cx.pl.rk[2];
+        double* __restrict__ k2 = cx.pl.rk[3];
+        double* __restrict__ k3 = cx.pl.rk[4];
+        double* __restrict__ k4 = cx.pl.rk[5];
+        for (int j = 0; j < A; j++) {  // sarkn = sa, msarkn = msa after the boundary condition (:1224-1240)
+            const int64_t o = cx.ring(j), l = cx.lin(j);
+            const double a = s_rz[o], b = s_ss[o];
+            sr[l] = a;
+            ss[l] = b;
+            mr[l] = (j == 0) ? m_rz[o] : clean_rz(m_rz[o], a);
+            mss[l] = (j == 0) ? m_ss[o] : clean_ss(m_ss[o], b);
+        }
+        const double evap = flx[0], transp = flx[1], q_rz = flx[2], cpr = flx[3], q_ss = flx[4];
+        for (int st = 0; st < 4; st++) {
+            const bool half = (st == 1 || st == 2);
+            // cumulative StorAge of the stage: calc_SA * maskCatch for the first stage, SArkn[1:] = cumsum(sarkn) afterwards
+            double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
+            auto advance = [&](int j, double a, double b, double& na, double& nb) {
+                if (st == 0) {
+                    acc_a += a;
+                    acc_b += b;
+                    na = acc_a * m;
+                    nb = acc_b * m;
+                } else {
+                    acc_a = (j == 0) ? a : acc_a + a;
+                    acc_b = (j == 0) ? b : acc_b + b;
+                    na = acc_a;
+                    nb = acc_b;
+                }
+            };
+            {
+                NpMax mx_rz, mx_ss;
+                mx_rz.init(0.0 * m);
+                mx_ss.init(0.0 * m);
+                for (int j = 0; j < A; j++) {
+                    const int64_t l = cx.lin(j);
+                    double na, nb;
+                    advance(j, sr[l], ss[l], na, nb);
+                    mx_rz.push(na);
+                    mx_ss.push(nb);
+                    if (any52) {
+                        cx.pl.rev[0][l] = na;
+                        cx.pl.rev[1][l] = nb;
+                    }
+                }
+                prepare(mx_rz.get(), mx_ss.get(), half);
+            }
+            {   // normalisation constants of the stage
+                reset();
+                acc_a = 0; acc_b = 0;
+                double sums[5];
+                EULER_SUMS<5, 2>(cx.plan, EULER_SUMS_ARG
+                    [&](int j, double* L) { const int64_t l = cx.lin(j); L[0] = sr[l]; L[1] = ss[l]; },
+                    [&](int j, const double* L, double* v) {
+                        double na, nb;
+                        advance(j, L[0], L[1], na, nb);
+                        const double da = na - SAa, db = nb - SAb;
+                        SAa = na;
+                        SAb = nb;
+                        const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            fx[k].ssum = sums[k];
-            fx[k].ssum_ok = (sums[k] > 0) && div_range_ok(sums[k]);
-            fx[k].rssum = 1.0 / sums[k];
+                        for (int k = 0; k < 5; k++) v[k] = euler_q(fx[k], fams[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
+                    }, sums);
+                set_sums(sums);
+            }
+            reset();
+#pragma unroll
+            for (int k = 0; k < 5; k++) { fx[k].accT = 0; fx[k].Tprev = 0; }
+            acc_a = 0; acc_b = 0; SAa = 0.0 * m; SAb = 0.0 * m;
+            for (int j = 0; j < A; j++) {
+                const int64_t l = cx.lin(j);
+                double a = sr[l], b = ss[l], ma = mr[l], mb = mss[l];
+                double na, nb;
+                advance(j, a, b, na, nb);
+                const double da = na - SAa, db = nb - SAb;
+                SAa = na;
+                SAb = nb;
+                double tt[5];
+                tt_of_bin(j, na, nb, da, db, tt);
+                const double tt_e = tt[0], tt_t = tt[1], tt_q = tt[2], tt_c = tt[3], tt_s = tt[4];
+                if (st == 0) {
+                    k0[l] = tt_e; k1[l] = tt_t; k2[l] = tt_q; k3[l] = tt_c; k4[l] = tt_s;
+                } else {
+                    const double w = half ? 2. : 1.;
+                    k0[l] = k0[l] + w * tt_e; k1[l] = k1[l] + w * tt_t; k2[l] = k2[l] + w * tt_q; k3[l] = k3[l] + w * tt_c;
+                    k4[l] = k4[l] + w * tt_s;
+                }
+                // solute travel-time distributions of the stage: mtt = where(tt > 0, msarkn, 0) (calc_mtt, isotope branch :575-580)
+                const double mtt_e = (tt_e > 0) ? ma : 0, mtt_t = (tt_t > 0) ? ma : 0, mtt_q = (tt_q > 0) ? ma : 0;
+                const double mtt_c = (tt_c > 0) ? mb : 0, mtt_s = (tt_s > 0) ? mb : 0;
+                if (st == 0) {  // :1388-1431
+                    double dsa_rz = (cpr * tt_c - evap * tt_e - transp * tt_t - q_rz * tt_q) * h;
+                    dsa_rz = (a + dsa_rz < 0) ? -a : dsa_rz;
+                    double dsa_ss = (q_rz * tt_q - cpr * tt_c - q_ss * tt_s) * h;
+                    dsa_ss = (b + dsa_ss < 0) ? -b : dsa_ss;
+                    const double dsa_rz1 = (cpr * tt_c) * h;
+                    const double dmsa_rz1 = nan0(mtt_c) * ((dsa_rz1 > 0) ? ((cpr * tt_c * h) / dsa_rz1) : 0);
+                    const double dsa_ss1 = (tt_q) * h;
+                    const double dmsa_ss1 = nan0(mtt_q) * ((dsa_ss1 > 0) ? ((q_rz * tt_q * h) / dsa_ss1) : 0);
+                    ma = euler_mix(ma, a, dsa_rz1, dmsa_rz1, true);
+                    mb = euler_mix(mb, b, dsa_ss1, dmsa_ss1, false);
+                    a += dsa_rz;
+                    b += dsa_ss;
+                    ma = (a <= 0) ? 0 : ma;
+                    mb = (b <= 0) ? 0 : mb;
+                } else if (half) {  // :1551-1581, :1699-1729
+                    double dsa_rz = (cpr * tt_c - evap * tt_e - transp * tt_t - q_rz * tt_q) * h / 2;
+                    double dsa_ss = (q_rz * tt_q - cpr * tt_c - q_ss * tt_s) * h / 2;
+                    if (st == 1) {
+                        dsa_rz = (a + dsa_rz < 0) ? -a : dsa_rz;
+                        dsa_ss = (b + dsa_ss < 0) ? -b : dsa_ss;
+                    } else {
+                        dsa_rz = (a - dsa_rz < 0) ? -a : dsa_rz;
+                        dsa_ss = (b - dsa_ss < 0) ? -b : dsa_ss;
+                    }
+                    a += dsa_rz;
+                    b += dsa_ss;
+                    const double r1 = nan0(mtt_c);
+                    const double r2 = nan0(mtt_e) + nan0(mtt_t) + nan0(mtt_q);
+                    double s1 = nan0(mtt_q);
+                    double s2 = nan0(mtt_c) + nan0(mtt_s);
+                    if (st == 1) { s1 = s1 * h / 2; s2 = s2 * h / 2; }
+                    double dr = ((r1 < 0) && (r2 >= 0)) ? r1 + r2 : r1 - r2;
+                    double ds = ((s1 < 0) && (s2 >= 0)) ? s1 + s2 : s1 - s2;
+                    dr = (dr > 0) ? ((ma + dr > 0) ? -ma : dr) : dr;
+                    ds = (ds > 0) ? ((mb + ds > 0) ? -mb : ds) : ds;
+                    ma += dr;
+                    mb += ds;
+                }
+                if (st < 3) {
+                    sr[l] = a;
+                    ss[l] = b;
+                    mr[l] = ma;
+                    mss[l] = mb;
+                }
+            }
         }
     }
     // P3: travel-time distributions, mixing, update
@@ -1655,22 +1877,18 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             const double a = L[0], b = L[1];
             const double ma = (ANION || j == 0) ? L[2] : clean_rz(L[2], a);
             const double mb = (ANION || j == 0) ? L[3] : clean_ss(L[3], b);
-            acc_a += a;
-            acc_b += b;
-            const double na = acc_a * m, nb = acc_b * m;
-            const double da = na - SAa, db = nb - SAb;
-            SAa = na;
-            SAb = nb;
             double tt[5];
-            const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
+            if (RK4) {  // tt = (k1 + 2 k2 + 2 k3 + k4) / 6 (:1836-1856)
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const double q = euler_q(fx[k], fams[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
-                const double p = (q > 0) ? ((fx[k].ssum_ok && div_range_ok(q)) ? div_by(q, fx[k].ssum, fx[k].rssum) : q / fx[k].ssum) : 0;
-                fx[k].accT = (j == 0) ? p : fx[k].accT + p;  // np.cumsum starts from the first element
-                const double d = fx[k].accT - fx[k].Tprev;
-                fx[k].Tprev = fx[k].accT;
-                tt[k] = (d >= 0) ? d : 0;
+                for (int k = 0; k < 5; k++) tt[k] = L[4 + k] / 6.;
+            } else {
+                acc_a += a;
+                acc_b += b;
+                const double na = acc_a * m, nb = acc_b * m;
+                const double da = na - SAa, db = nb - SAb;
+                SAa = na;
+                SAb = nb;
+                tt_of_bin(j, na, nb, da, db, tt);
             }
             const double tt_e = tt[0], tt_t = tt[1], tt_q = tt[2], tt_c = tt[3], tt_s = tt[4];
             if (ANION) {
@@ -1760,14 +1978,20 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             m_rz[o] = ma2;
             m_ss[o] = mb2;
         };
+        constexpr int NL = RK4 ? 9 : 4;
         auto load = [&](int j, double* L) {
             const int64_t o = cx.ring(j);
             L[0] = s_rz[o]; L[1] = s_ss[o]; L[2] = m_rz[o]; L[3] = m_ss[o];
+            if (RK4) {
+                const int64_t l = cx.lin(j);
+#pragma unroll
+                for (int k = 0; k < 5; k++) L[(RK4 ? 4 : 0) + k] = cx.pl.rk[1 + k][l];
+            }
         };
         if (LAST) {
             constexpr int NS = ANION ? 4 : (STATS ? 15 : 10);
             double sums[NS];
-            EULER_SUMS<NS, 4>(cx.plan, EULER_SUMS_ARG load, bin, sums);
+            EULER_SUMS<NS, NL>(cx.plan, EULER_SUMS_ARG load, bin, sums);
             if (ANION) {  // :2378-2407; C_evap_soil and the M_* flux planes are not touched by the Euler solver
                 O(RSO_C_inf_mat_rz) = ((inf_mat * h > 0) ? C_in : 0) * m;
                 O(RSO_C_inf_pf_rz) = ((inf_pf * h > 0) ? C_in : 0) * m;
@@ -1802,13 +2026,13 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             O(RSO_C_inf_pf_rz) = c2; O(RSO_C_iso_inf_pf_rz) = conc_to_delta(P, c2) * m;
             O(RSO_C_inf_pf_ss) = c3; O(RSO_C_iso_inf_pf_ss) = conc_to_delta(P, c3) * m;
         } else {
-            double Lc[4], Ln[4], v[1];
+            double Lc[NL], Ln[NL], v[1];
             load(0, Lc);
             for (int j = 0; j < A; j++) {  // next bin's loads in flight while this bin computes
                 if (j + 1 < A) load(j + 1, Ln);
                 bin(j, Lc, v);
 #pragma unroll
-                for (int q = 0; q < 4; q++) Lc[q] = Ln[q];
+                for (int q = 0; q < NL; q++) Lc[q] = Ln[q];
             }
         }
     }
@@ -1881,15 +2105,15 @@ __device__ __forceinline__ void euler_day_anion(const CellCtx& cx, const double*
     anion_ageing(cx);
 }
 
-template <bool STATS>
+template <bool STATS, bool RK4 = false>
 __device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
                                           double* __restrict__ out, double* __restrict__ stats, double* __restrict__ C_s_prev,
                                           const double* __restrict__ bounds, double atol, double rtol) {
     const SasParams& P = cx.P;
     const int64_t C = P.C, i = cx.i;
     const int n = P.substeps;
-    for (int s = 0; s + 2 < n; s++) euler_step<false, false, false>(cx, forcing, m, sas_params, out, nullptr, 1.0, 1.0);
-    if (n > 1) euler_step<false, false, false>(cx, forcing, m, sas_params, out, nullptr, 1.0, 1.0);
+    for (int s = 0; s + 2 < n; s++) euler_step<false, false, false, RK4>(cx, forcing, m, sas_params, out, nullptr, 1.0, 1.0);
+    if (n > 1) euler_step<false, false, false, RK4>(cx, forcing, m, sas_params, out, nullptr, 1.0, 1.0);
     double sum_sa_s, C_s, sum_sa_rz, sum_sa_ss;
     double sum_sa_s_m1 = 0, Cp = 0;
     if (STATS) {  // [taum1] of the last Euler step: what its predecessor left (after_substep_iso, transport.py:3421-3520)
@@ -1904,7 +2128,7 @@ __device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __res
         sum_sa_s_m1 = sm[0];
     }
     EulerStats es;
-    euler_step<true, STATS, false>(cx, forcing, m, sas_params, out, &es, 1.0, 1.0);
+    euler_step<true, STATS, false, RK4>(cx, forcing, m, sas_params, out, &es, 1.0, 1.0);
     storage_concentrations(cx, m, out, C, &sum_sa_s, &C_s, &sum_sa_rz, &sum_sa_ss);
     if (STATS) {
 #define F(k) forcing[(int64_t)(k) * C + i]

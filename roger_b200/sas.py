@@ -32,7 +32,7 @@ class SasSettings(C.Structure):
 
 
 ISOTOPE, ANION = 0, 1
-DETERMINISTIC, EULER, RK4 = 0, 1, 2  # settings.sas_solver of the reference (roger/settings.py); RK4: CPU oracle only so far
+DETERMINISTIC, EULER, RK4 = 0, 1, 2  # settings.sas_solver of the reference (roger/settings.py); RK4: isotope branch
 
 
 def default_settings(ages, substeps=6, store_tt=False, age_statistics=False, solute=ISOTOPE, solver=DETERMINISTIC):

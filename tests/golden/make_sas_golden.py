@@ -63,11 +63,21 @@ CASES = {
                             sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     "sas_euler_bromide": dict(shape=(2, 3), ndays=20, ages=50, doy=100, solute="bromide", sas_solver="Euler",
                               sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
-    # Runge-Kutta solver (settings.sas_solver = "RK4"): oracle only so far
+    # Runge-Kutta solver (settings.sas_solver = "RK4")
     "sas_rk4": dict(shape=(2, 2), ndays=12, ages=40, doy=100, sas_solver="RK4",
                     sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     "sas_rk4_stats": dict(shape=(2, 2), ndays=10, ages=36, doy=105, sas_solver="RK4", age_statistics=True, var_input=True,
                           sas=dict(evap_soil=(6, 0.2), cpr_rz=(3, 0.7, 1.6), transp=(6, 0.5), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(6, 1.5))),
+    # the gamma family (id 4, scipy.special.gammainc) and the exponential family read backwards along the age axis (id 52), with
+    # each of the three solvers
+    "sas_gamma52": dict(shape=(2, 2), ndays=16, ages=45, doy=110, var_input=True,
+                        sas=dict(evap_soil=(52, 2.0), cpr_rz=(4, 2.0, 3.0), transp=(4, 1.5, 4.0), q_rz=(52, 1.0), q_ss=(4, 0.8, 2.5))),
+    # (under the Euler / RK4 schemes the gamma family makes the reference divide by a rounding residue -- its cumulative function
+    # returns to 0 at S, the normalising sum telescopes to ~0, "Solution of SAS diverged" -- so only family 52 is pinned there)
+    "sas_euler_52": dict(shape=(2, 2), ndays=14, ages=40, doy=110, sas_solver="Euler", var_input=True,
+                         sas=dict(evap_soil=(52, 2.0), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(52, 1.0), q_ss=(6, 1.5))),
+    "sas_rk4_52": dict(shape=(2, 2), ndays=8, ages=36, doy=110, sas_solver="RK4",
+                       sas=dict(evap_soil=(6, 0.2), cpr_rz=(52, 2.0), transp=(52, 1.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     "sas_euler_families": dict(shape=(2, 2), ndays=22, ages=45, doy=20, sas_solver="Euler", var_input=True,
                                sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0),
                                         q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),

@@ -125,6 +125,8 @@ def _random_case(C_, A, ndays, seed, families=False):
     spec = {}
     if families:
         ids = {"evap_soil": [1, 6, 3], "cpr_rz": [51, 6, 2], "transp": [3, 32, 6], "q_rz": [61, 62, 35], "q_ss": [35, 31, 6]}
+        if families == "all":  # plus the gamma family and the backwards-read exponential
+            ids = {"evap_soil": [1, 6, 3, 52], "cpr_rz": [51, 6, 2, 4], "transp": [3, 32, 6, 4, 52], "q_rz": [61, 62, 35, 4], "q_ss": [35, 31, 6, 52, 4]}
         for p, choices in ids.items():
             arr = np.zeros((C_, 8))
             arr[:, 0] = rng.choice(choices, C_)
@@ -229,8 +231,8 @@ def test_unsupported_sas_function_is_rejected():
     from roger_b200.engine import RogerCudaError
 
     eng = _cuda()(8, sas.default_settings(10))
-    spec = dict(evap_soil=(4, 1.0, 1.0), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))
-    with pytest.raises(RogerCudaError, match="not implemented"):
+    spec = dict(evap_soil=(7, 1.0, 1.0), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))
+    with pytest.raises(RogerCudaError, match="not one of the reference's"):
         eng.set_parameters(np.ones(8), sas.sas_parameter_block(8, spec))
     with pytest.raises(RogerCudaError, match="set_parameters"):
         eng.step(np.zeros((9, 8)))
@@ -312,6 +314,48 @@ def test_anion_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, ora
     assert float(np.nansum(models[0].state("msa_ss"))) > 0
 
 
+# ---- gamma family (id 4) and backwards-read exponential (id 52) --------------------------------------------------------
+@pytest.mark.parametrize("case", u.GAMMA_CASES)
+def test_gamma_cuda_equals_oracle_bit_for_bit_and_reference_to_1e10(case, oracle_roger_pow):
+    fx = u.load_case(case)
+    a = u.model_from_fixture(fx, _cuda())
+    b = u.model_from_fixture(fx, oracle_roger_pow)
+    u.replay_pair(a, b, int(fx["ndays"]), exact=True)
+    m = u.model_from_fixture(fx, _cuda())
+    worst = u.replay_against_fixture(fx, m, exact=False)
+    bad = {k: v for k, v in worst.items() if v[0] > (1e-9 if k.startswith("C_iso") else 1e-10)}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("solver,C_,A,ndays,substeps", [(0, 300, 96, 6, 6), (0, 33, 257, 3, 3), (0, 5, 9, 5, 1), (1, 300, 77, 5, 6), (1, 3, 130, 3, 2),
+                                                        (2, 200, 64, 4, 4), (2, 2, 9, 4, 1)])
+def test_all_families_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(solver, C_, A, ndays, substeps, oracle_roger_pow):
+    """every SAS function id of roger/core/sas.py drawn per cell and flux, each of the three solvers, masked cells.  Under the Euler / RK4
+    schemes the gamma family makes the reference (and therefore both sides here) divide by rounding residues -- NaN and inf patterns
+    included, the two sides must still agree bit for bit"""
+    from roger_b200 import sas
+
+    daily, spec = _random_case(C_, A, ndays, seed=4200 + A + solver, families="all")
+    mask = np.ones(C_)
+    mask[4::13] = 0.0
+    models = [sas.SasModel(e, C_, A, daily, spec, store_tt=True, mask=mask, substeps=substeps, solver=solver) for e in (_cuda(), oracle_roger_pow)]
+    for m in models:
+        m.setup()
+    u.replay_pair(models[0], models[1], ndays, exact=True)
+
+
+def test_gamma_parameters_outside_the_evaluated_range_are_rejected():
+    from roger_b200 import sas
+    from roger_b200.engine import RogerCudaError
+
+    daily, _ = _random_case(4, 8, 2, seed=1)
+    for bad in [(4, 0.0, 1.0), (4, 171.0, 1.0), (4, 2.0, 51.0), (4, 2.0, -1.0), (7,)]:
+        spec = dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=bad, q_rz=(6, 1.5), q_ss=(6, 1.5))
+        m = sas.SasModel(_cuda(), 4, 8, daily, spec)
+        with pytest.raises(RogerCudaError):
+            m.setup()
+
+
 # ---- explicit Euler solver (settings.sas_solver = "Euler", transport.py:2063-2413) ---------------------------------
 @pytest.mark.parametrize("case", u.EULER_CASES)
 def test_euler_cuda_equals_oracle_bit_for_bit_on_fixture_inputs(case, oracle_roger_pow):
@@ -382,11 +426,49 @@ def test_euler_anion_with_statistics_is_rejected():
         sas.SasModel(_cuda(), 4, 8, daily, spec, solver=sas.EULER, solute=sas.ANION, age_statistics=True)
 
 
-def test_rk4_solver_is_rejected_on_the_device():
-    """the RK4 solver is restated in the CPU oracle only: the device says so instead of computing something else"""
+# ---- Runge-Kutta solver (settings.sas_solver = "RK4", transport.py:1138-2047) ---------------------------------------
+@pytest.mark.parametrize("case", u.RK4_CASES)
+def test_rk4_cuda_equals_oracle_bit_for_bit_on_fixture_inputs(case, oracle_roger_pow):
+    fx = u.load_case(case)
+    a = u.model_from_fixture(fx, _cuda())
+    b = u.model_from_fixture(fx, oracle_roger_pow)
+    assert a.settings.solver == 2
+    u.replay_pair(a, b, int(fx["ndays"]), exact=True)
+
+
+def test_rk4_cuda_against_reference_fixtures():
+    """like the Euler scheme: normalised pdfs, no clamp decided by the last bit of a pow -- 1e-10 against the reference directly"""
+    for case in u.RK4_CASES:
+        fx = u.load_case(case)
+        m = u.model_from_fixture(fx, _cuda())
+        worst = u.replay_against_fixture(fx, m, exact=False)
+        bad = {k: v for k, v in worst.items() if "num_error" not in k and v[0] > (1e-9 if k.startswith("C_iso") else 1e-10)}
+        assert not bad, (case, bad)
+
+
+@pytest.mark.parametrize("C_,A,ndays,families,substeps", [(400, 136, 6, False, 6), (333, 77, 6, True, 6), (40, 1000, 2, False, 2), (1, 2, 5, False, 6),
+                                                          (5, 9, 5, True, 1), (257, 129, 3, False, 3)])
+def test_rk4_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, families, substeps, oracle_roger_pow):
+    """seeded grids with masked cells, all SAS families, the stage clamps, 1 to 6 Runge-Kutta steps per day, sizes around the block /
+    summation-tree boundaries; age statistics and stored travel-time distributions on most cases"""
+    from roger_b200 import sas
+
+    daily, spec = _random_case(C_, A, ndays, seed=1300 + A, families=families)
+    mask = np.ones(C_)
+    mask[5::17] = 0.0
+    models = [sas.SasModel(e, C_, A, daily, spec, store_tt=(A != 136), mask=mask, substeps=substeps, solver=sas.RK4, age_statistics=(A != 1000))
+              for e in (_cuda(), oracle_roger_pow)]
+    for m in models:
+        m.setup()
+    u.replay_pair(models[0], models[1], ndays, exact=True)
+
+
+def test_rk4_anion_is_rejected_on_the_device():
+    """the reference's RK4 solver has no working anion branch: the device says so instead of computing something else"""
     from roger_b200 import sas
     from roger_b200.engine import RogerCudaError
 
     daily, spec = _random_case(4, 8, 2, seed=1)
+    daily["C_IN"] = daily["C_ISO_IN"] * 0
     with pytest.raises(RogerCudaError):
-        sas.SasModel(_cuda(), 4, 8, daily, spec, solver=sas.RK4)
+        sas.SasModel(_cuda(), 4, 8, daily, spec, solver=sas.RK4, solute=sas.ANION)
