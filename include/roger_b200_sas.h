@@ -72,6 +72,11 @@ enum roger_nitrate_output { /* per-cell results of the nitrogen cycle of the las
     RNO_nit_s = 0, RNO_denit_s, RNO_min_s, RNO_ngas_s, RNO_nfix_s, RNO_nh4_up, RNO_Nmin_s, RNO_COUNT
 };
 
+enum roger_crop_output { /* crop variant: the redistribution fluxes as applied (clamped to the source layer's water), their solute
+                            concentration and mass (vs.re_rg, vs.C_re_rg, vs.M_re_rg, ... of roger/core/crop.py:2461-2828) */
+    RCO_re_rg = 0, RCO_re_rl, RCO_C_re_rg, RCO_C_re_rl, RCO_M_re_rg, RCO_M_re_rl, RCO_COUNT
+};
+
 typedef struct roger_sas_settings {
     int32_t ages;          /* settings.ages (number of age bins)                       */
     int32_t substeps;      /* settings.sas_solver_substeps                              */
@@ -125,6 +130,17 @@ int roger_sas_set_nitrate_parameters(roger_sas *h, const double *params, double 
 int roger_sas_set_nitrate_forcing(roger_sas *h, const double *planes);
 /* nitrate only: RNO_COUNT planes of n_cells doubles from the last step */
 int roger_sas_download_nitrate_outputs(roger_sas *h, double *host);
+/* Crop variant of the offline model (settings.enable_crop_phenology: svat_crop_transport_model_deterministic,
+ * roger/core/transport.py:1042-1087): every day then opens with crop.calculate_redistribution_transport (roger/core/crop.py:2829-2867,
+ * anion kernels :2461-2558 and :2729-2828) -- water and solute move from the subsoil to the root zone after root growth (re_rg) and
+ * back after root loss (re_rl), each a SAS-controlled withdrawal with its own parameter row (vs.sas_params_re_rg / _re_rl,
+ * n_cells * 8 doubles each, same row layout as roger_sas_set_parameters).  Anion and nitrate solutes, deterministic solver, no age
+ * statistics (ROGER_ENOTSUP otherwise).  The day's fluxes vs.re_rg, vs.re_rl (n_cells doubles each, host; an input of the offline
+ * model, read from the SVAT-CROP output by the reference's setups) must be set before every roger_sas_step*. */
+int roger_sas_set_crop_parameters(roger_sas *h, const double *sas_params_re_rg, const double *sas_params_re_rl);
+int roger_sas_set_redistribution(roger_sas *h, const double *re_rg, const double *re_rl);
+/* RCO_COUNT planes of n_cells doubles from the last step */
+int roger_sas_download_redistribution(roger_sas *h, double *host);
 /* one daily step.  forcing: RSF_COUNT planes of n_cells doubles (host memory). */
 int roger_sas_step(roger_sas *h, const double *forcing);
 /* same with forcing already on the device (raw address of RSF_COUNT * n_cells doubles) */

@@ -227,6 +227,20 @@ class OracleSasEngine:
     def download_nitrate_outputs(self):
         return self._nit_out.copy()
 
+    # ---- crop variant (redistribution after root growth / root loss opens the day)
+    def set_crop_parameters(self, sas_params_re_rg, sas_params_re_rl):
+        if self.settings.solute == 0 or self.settings.solver != 0 or self.settings.age_statistics:
+            raise NotImplementedError("crop variant: anion / nitrate solutes, deterministic solver, no age statistics")
+        self._crop_sp = [np.ascontiguousarray(a, dtype=np.float64).reshape(self.n, 8) for a in (sas_params_re_rg, sas_params_re_rl)]
+        self._crop_out = np.zeros((6, self.n))
+        self._crop_re = None
+
+    def set_redistribution(self, re_rg, re_rl):
+        self._crop_re = np.ascontiguousarray(np.stack([np.asarray(re_rg, dtype=np.float64).reshape(-1), np.asarray(re_rl, dtype=np.float64).reshape(-1)]))
+
+    def download_redistribution(self):
+        return self._crop_out.copy()
+
     def upload_state_index(self, which, arr):
         name = (self.sas.STATE + ["Nmin_rz", "Nmin_ss"])[which]
         self.state[name] = np.ascontiguousarray(np.asarray(arr, dtype=np.float64).reshape(self.n, self.A)).copy()
@@ -255,6 +269,17 @@ class OracleSasEngine:
             fn2(dp(self._nit_params), dp(self._nit_forcing), dp(self.state["Nmin_rz"]), dp(self.state["Nmin_ss"]), dp(self._nit_out), *self._nit_scal)
         else:
             fn2(None, None, None, None, None, 1.0, 1.0, 0.7, 24.0)
+
+        fc = lib().sas_oracle_set_crop
+        fc.argtypes = [C.POINTER(C.c_double)] * 4
+        fc.restype = None
+        if getattr(self, "_crop_sp", None) is not None:
+            if self._crop_re is None:
+                raise RuntimeError("crop variant: set_redistribution has not been called for this day")
+            fc(dp(self._crop_sp[0]), dp(self._crop_sp[1]), dp(self._crop_re), dp(self._crop_out))
+            self._crop_re_used, self._crop_re = self._crop_re, None  # keep the buffer alive through the step
+        else:
+            fc(None, None, None, None)
 
     def download_statistics(self):
         return self.stats.copy()

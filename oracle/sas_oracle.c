@@ -662,6 +662,37 @@ static void storage_age_statistics(int A, const double *sa, double m, const doub
                                    double *avg);
 static double nan0(double x);
 
+/* crop variant of the offline model (svat_crop_transport_model_deterministic, transport.py:1042-1087): the day opens with the
+ * redistribution after root growth (subsoil -> root zone) and root loss (root zone -> subsoil), crop.py:2461-2558, :2729-2828 */
+static struct {
+    const double *sp_rg, *sp_rl; /* (C, 8) SAS parameters */
+    const double *re;            /* (2, C): today's re_rg, re_rl */
+    double *out;                 /* (6, C): RCO_* */
+} g_crop = {NULL, NULL, NULL, NULL};
+void sas_oracle_set_crop(const double *sp_rg, const double *sp_rl, const double *re, double *out)
+{
+    g_crop.sp_rg = sp_rg; g_crop.sp_rl = sp_rl; g_crop.re = re; g_crop.out = out;
+}
+static void redistribution(const sas_ctx *c, double *s_src, double *ms_src, double *s_dst, double *ms_dst, double re_in, const double *sp, double m,
+                           double *tt, double *mtt, double *w2, double *re_out, double *C_out, double *M_out)
+{
+    const int A = c->A;
+    const double tot = np_sum(s_src, A);
+    const double re = ((re_in > tot) ? tot : re_in) * m;
+    anion_tt(c, s_src, re, sp, m, tt, w2);
+    anion_mtt(A, s_src, tt, re, ms_src, 1.0, m, mtt);
+    const double M = np_sum(mtt, A);
+    *re_out = re;
+    *C_out = ((re > 0) ? M / re : 0) * m;
+    *M_out = M * m;
+    update_sa(A, s_src, tt, re, m);
+    for (int j = 0; j < A; j++) {
+        s_dst[j] += tt[j] * re * m;
+        ms_dst[j] += mtt[j] * m;
+        ms_src[j] += -mtt[j] * m;
+    }
+}
+
 static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz, double *s_ss, double *ms_rz, double *ms_ss,
                            const double *forcing, double m, const double *sas_params, double *out, double *tt_out, double *work, double *tmp,
                            double *stats, double *balance_prev, double *ttk, const double *ages)
@@ -681,6 +712,14 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
     double *tt = work, *mtt = tt + (A + 2), *w2 = mtt + (A + 2);
     const double C_in = F(RSF_C_in);
     const double alpha_q = g_anion[1] ? g_anion[1][i] : 1.0;
+    if (g_crop.re) {
+#define CO(k) g_crop.out[(size_t)(k) * (size_t)C + (size_t)i]
+        redistribution(c, s_ss, ms_ss, s_rz, ms_rz, g_crop.re[i], g_crop.sp_rg + (size_t)i * 8, m, tt, mtt, w2, &CO(RCO_re_rg), &CO(RCO_C_re_rg),
+                       &CO(RCO_M_re_rg));
+        redistribution(c, s_rz, ms_rz, s_ss, ms_ss, g_crop.re[(size_t)C + (size_t)i], g_crop.sp_rl + (size_t)i * 8, m, tt, mtt, w2, &CO(RCO_re_rl),
+                       &CO(RCO_C_re_rl), &CO(RCO_M_re_rl));
+#undef CO
+    }
     /* infiltration into the root zone */
     O(RSO_C_inf_mat_rz) = ((F(RSF_inf_mat_rz) > 0) ? C_in : 0) * m;
     O(RSO_C_inf_pf_rz) = ((F(RSF_inf_pf_rz) > 0) ? C_in : 0) * m;

@@ -153,7 +153,7 @@ template <bool STATS>
 __global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
 k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
                 const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap,
-                double* __restrict__ stats, double* __restrict__ C_s_prev) {
+                double* __restrict__ stats, double* __restrict__ C_s_prev, CropParams crop) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
     __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
     for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
@@ -164,14 +164,14 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
-    anion_day<STATS>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev);
+    anion_day<STATS>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev, nullptr, crop);
 }
 
 // One day of the nitrate transport: the anion day with the soil nitrogen cycle between the transport and the storage kernels
 __global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
 k_sas_day_nitrate(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
                   const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap,
-                  NitrateParams np_) {
+                  NitrateParams np_, CropParams crop) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
     __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
     for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
@@ -182,7 +182,7 @@ k_sas_day_nitrate(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
-    anion_day<false, true>(cx, forcing, mask[i], sas_params, ap, out, nullptr, nullptr, &np_);
+    anion_day<false, true>(cx, forcing, mask[i], sas_params, ap, out, nullptr, nullptr, &np_, crop);
 }
 
 // One day of the explicit Euler solver (`substeps` Euler steps, ageing with the last one), one thread per cell.
@@ -350,6 +350,14 @@ struct roger_sas {
     double* d_nit_out = nullptr;      // RNO_COUNT planes
     double nit_dx = 1, nit_dy = 1, nit_zmax = 0.7, nit_dt = 24;
     bool have_nit_params = false, have_nit_forcing = false;
+    double* d_crop_params = nullptr;  // crop variant: SAS parameter rows of re_rg and re_rl, [2][8][C]
+    double* d_crop_re = nullptr;      // today's re_rg, re_rl, [2][C]
+    double* d_crop_out = nullptr;     // RCO_COUNT planes
+    bool have_crop_re = false;
+    CropParams crop() const {
+        if (!d_crop_params) return CropParams{nullptr, nullptr, nullptr, nullptr};
+        return CropParams{d_crop_params, d_crop_params + 8 * C, d_crop_re, d_crop_out};
+    }
     double* d_san = nullptr;
     double* d_TTn = nullptr;
     double* d_om = nullptr;   // ROGER_SAS_SPLIT: SAS function values between the two walks of a sub-step pass; RK4: a stage array
@@ -525,6 +533,7 @@ void roger_sas_destroy(roger_sas* h) {
     cudaFree(h->d_nit_params); cudaFree(h->d_nit_forcing); cudaFree(h->d_nit_out);
     for (int k = 0; k < 6; k++) cudaFree(h->d_rk[k]);
     cudaFree(h->d_rev[0]); cudaFree(h->d_rev[1]);
+    cudaFree(h->d_crop_params); cudaFree(h->d_crop_re); cudaFree(h->d_crop_out);
     cudaFree(h->d_san); cudaFree(h->d_TTn); cudaFree(h->d_om); cudaFree(h->d_tt); cudaFree(h->d_forcing); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_params); cudaFree(h->d_stage); cudaFree(h->d_plan);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -565,30 +574,29 @@ int roger_sas_init_linear(roger_sas* h, const double* S_rz, const double* S_ss, 
     return 0;
 }
 
-int roger_sas_set_parameters(roger_sas* h, const double* mask_catch, const double* sas_params) {
-    if (!h || !mask_catch || !sas_params) return fail(ROGER_EINVAL, "roger_sas_set_parameters: bad argument");
-    CU(cudaSetDevice(h->device));
+// Validates `nproc` blocks of (C, 8) SAS parameter rows and packs them plane-major ([proc][8][C]) for the device.
+static int pack_sas_rows(roger_sas* h, const double* rows, int nproc, std::vector<double>& t, const char* who) {
     const int64_t C = h->C;
-    std::vector<double> t((size_t)RSP_COUNT * 8 * (size_t)C);
+    t.resize((size_t)nproc * 8 * (size_t)C);
     bool any52 = false;
-    for (int p = 0; p < RSP_COUNT; p++)
+    for (int p = 0; p < nproc; p++)
         for (int64_t i = 0; i < C; i++) {
-            const double* row = sas_params + ((size_t)p * (size_t)C + (size_t)i) * 8;
+            const double* row = rows + ((size_t)p * (size_t)C + (size_t)i) * 8;
             const double id = row[0];
             const bool ok = id == 0 || id == 1 || id == 2 || id == 3 || (id >= 31 && id <= 37 && id == std::floor(id)) || id == 4 ||
                             id == 51 || id == 52 || id == 6 || id == 61 || id == 62;
             if (!ok) {
                 char buf[320];
-                snprintf(buf, sizeof buf, "roger_sas_set_parameters: SAS function id %g (process %d, cell %lld) is not one of the reference's "
-                         "(roger/core/sas.py: 1, 2, 3, 31-37, 4, 51, 52, 6, 61, 62)", id, p, (long long)i);
+                snprintf(buf, sizeof buf, "%s: SAS function id %g (process %d, cell %lld) is not one of the reference's "
+                         "(roger/core/sas.py: 1, 2, 3, 31-37, 4, 51, 52, 6, 61, 62)", who, id, p, (long long)i);
                 return fail(ROGER_ENOTSUP, buf);
             }
             for (int k = 0; k < 8; k++) t[((size_t)p * 8 + (size_t)k) * (size_t)C + (size_t)i] = row[k];
             if (id == 4) {  // gamma family (sas.py:137-160): Gamma(a) = exp(gammaln(a)) is a per-flux constant, computed here once
                 if (!(row[1] > 0 && row[1] <= ROGER_GAMMA_A_MAX && row[2] >= 0 && row[2] <= ROGER_GAMMA_B_MAX)) {
                     char buf[320];
-                    snprintf(buf, sizeof buf, "roger_sas_set_parameters: gamma SAS function (process %d, cell %lld) with a = %g, b = %g: this backend "
-                             "evaluates 0 < a <= %g, 0 <= b <= %g", p, (long long)i, row[1], row[2], ROGER_GAMMA_A_MAX, ROGER_GAMMA_B_MAX);
+                    snprintf(buf, sizeof buf, "%s: gamma SAS function (process %d, cell %lld) with a = %g, b = %g: this backend "
+                             "evaluates 0 < a <= %g, 0 <= b <= %g", who, p, (long long)i, row[1], row[2], ROGER_GAMMA_A_MAX, ROGER_GAMMA_B_MAX);
                     return fail(ROGER_ENOTSUP, buf);
                 }
                 t[((size_t)p * 8 + 3) * (size_t)C + (size_t)i] = std::exp(std::lgamma(row[1]));
@@ -602,6 +610,15 @@ int roger_sas_set_parameters(roger_sas* h, const double* mask_catch, const doubl
             CU(cudaMemsetAsync(h->d_rev[k], 0, arr, h->stream));
         }
     }
+    return 0;
+}
+
+int roger_sas_set_parameters(roger_sas* h, const double* mask_catch, const double* sas_params) {
+    if (!h || !mask_catch || !sas_params) return fail(ROGER_EINVAL, "roger_sas_set_parameters: bad argument");
+    CU(cudaSetDevice(h->device));
+    const int64_t C = h->C;
+    std::vector<double> t;
+    if (int rc = pack_sas_rows(h, sas_params, RSP_COUNT, t, "roger_sas_set_parameters")) return rc;
     CU(cudaMemcpyAsync(h->d_params, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_mask, mask_catch, sizeof(double) * (size_t)C, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -609,8 +626,52 @@ int roger_sas_set_parameters(roger_sas* h, const double* mask_catch, const doubl
     return 0;
 }
 
+int roger_sas_set_crop_parameters(roger_sas* h, const double* sas_params_re_rg, const double* sas_params_re_rl) {
+    if (!h || !sas_params_re_rg || !sas_params_re_rl) return fail(ROGER_EINVAL, "roger_sas_set_crop_parameters: bad argument");
+    if (h->st.solute == 0 || h->st.solver != 0 || h->st.age_statistics)
+        return fail(ROGER_ENOTSUP, "roger_sas_set_crop_parameters: the crop variant runs anion / nitrate solutes with the deterministic solver "
+                                   "and without age statistics");
+    CU(cudaSetDevice(h->device));
+    const int64_t C = h->C;
+    std::vector<double> rows((size_t)2 * 8 * (size_t)C), t;
+    std::memcpy(rows.data(), sas_params_re_rg, sizeof(double) * 8 * (size_t)C);
+    std::memcpy(rows.data() + 8 * (size_t)C, sas_params_re_rl, sizeof(double) * 8 * (size_t)C);
+    if (int rc = pack_sas_rows(h, rows.data(), 2, t, "roger_sas_set_crop_parameters")) return rc;
+    if (!h->d_crop_params) {
+        CU(cudaMalloc(&h->d_crop_params, sizeof(double) * 16 * (size_t)C));
+        CU(cudaMalloc(&h->d_crop_re, sizeof(double) * 2 * (size_t)C));
+        CU(cudaMalloc(&h->d_crop_out, sizeof(double) * RCO_COUNT * (size_t)C));
+        CU(cudaMemsetAsync(h->d_crop_out, 0, sizeof(double) * RCO_COUNT * (size_t)C, h->stream));
+    }
+    CU(cudaMemcpyAsync(h->d_crop_params, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int roger_sas_set_redistribution(roger_sas* h, const double* re_rg, const double* re_rl) {
+    if (!h || !re_rg || !re_rl) return fail(ROGER_EINVAL, "roger_sas_set_redistribution: bad argument");
+    if (!h->d_crop_params) return fail(ROGER_EINVAL, "roger_sas_set_redistribution: roger_sas_set_crop_parameters has not been called");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->d_crop_re, re_rg, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_crop_re + h->C, re_rl, sizeof(double) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));  // the host buffers are the caller's
+    h->have_crop_re = true;
+    return 0;
+}
+
+int roger_sas_download_redistribution(roger_sas* h, double* host) {
+    if (!h || !host) return fail(ROGER_EINVAL, "roger_sas_download_redistribution: bad argument");
+    if (!h->d_crop_out) return fail(ROGER_EINVAL, "roger_sas_download_redistribution: roger_sas_set_crop_parameters has not been called");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(host, h->d_crop_out, sizeof(double) * RCO_COUNT * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 static int step_common(roger_sas* h, const double* d_forcing) {
     if (!h->have_params) return fail(ROGER_EINVAL, "roger_sas_step: roger_sas_set_parameters has not been called");
+    if (h->d_crop_params && !h->have_crop_re)
+        return fail(ROGER_EINVAL, "roger_sas_step: the crop variant needs the day's roger_sas_set_redistribution");
     CU(cudaEventRecord(h->ev0, h->stream));
     const int threads = ROGER_SAS_BLOCK;
     const int blocks = (int)((h->C + threads - 1) / threads);
@@ -644,17 +705,20 @@ static int step_common(roger_sas* h, const double* d_forcing) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
         NitrateParams np_{h->d_nit_params, h->d_nit_forcing, h->d_nit_out, h->nit_dx, h->nit_dy, h->nit_zmax, h->nit_dt};
-        k_sas_day_nitrate<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out, ap, np_);
+        k_sas_day_nitrate<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out, ap, np_,
+                                                             h->crop());
         h->have_nit_forcing = false;
+        h->have_crop_re = false;
     } else if (h->st.solute == 1) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
         if (h->st.age_statistics)
             k_sas_day_anion<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
-                                                                     h->d_out, ap, h->d_stats, h->d_C_s_prev);
+                                                                     h->d_out, ap, h->d_stats, h->d_C_s_prev, h->crop());
         else
             k_sas_day_anion<false><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
-                                                                      h->d_out, ap, nullptr, nullptr);
+                                                                      h->d_out, ap, nullptr, nullptr, h->crop());
+        h->have_crop_re = false;
     } else if (h->st.age_statistics)
         k_sas_day<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
                                                            h->d_stats, h->d_C_s_prev, h->d_bounds, h->atol, h->rtol);

@@ -906,7 +906,7 @@ __device__ __noinline__ double anion_withdrawal(const CellCtx& cx, int src, int 
     const bool active = solve_substeps(cx, src, flux, sp_global, sp_stride, m);
     double* __restrict__ sa_d = (dst >= 0) ? cx.pl.sa[dst] : nullptr;
     double* __restrict__ msa_d = (dst >= 0) ? cx.pl.msa[dst] : nullptr;
-    double* __restrict__ tt_out = (P.store_tt && cx.pl.tt) ? cx.pl.tt + (size_t)process * (size_t)A * (size_t)C : nullptr;
+    double* __restrict__ tt_out = (P.store_tt && cx.pl.tt && process >= 0) ? cx.pl.tt + (size_t)process * (size_t)A * (size_t)C : nullptr;
     const double nsub = (double)P.substeps;
     double prev = 0. / nsub;
     constexpr int NS = STATS ? 4 : 1;
@@ -993,6 +993,13 @@ struct AnionParams {  // per-cell planes (may be null: alpha = 1, no crops)
 // (stream_sums), the reversed cumulative sum of the denitrification is walked from the oldest bin down.  `msa_rz += ma_rz`
 // is applied in the nitrification pass already: nothing reads msa_rz between the two statements of the reference.
 // ================================================================================================================
+struct CropParams {  // crop variant of the offline model: redistribution after root growth / root loss (null pointers: no crop model)
+    const double* sp_rg;  // SAS parameter rows, [8][C]
+    const double* sp_rl;
+    const double* re;     // [2][C]: today's re_rg, re_rl
+    double* out;          // [RCO_COUNT][C]
+};
+
 struct NitrateParams {
     const double* params;   // RNP_COUNT planes
     const double* forcing;  // RNF_COUNT planes of the day
@@ -1154,7 +1161,7 @@ __device__ __noinline__ void nitrogen_cycle(const CellCtx& cx, const NitratePara
 template <bool STATS, bool NITRATE = false>
 __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
                                           const AnionParams ap, double* __restrict__ out, double* __restrict__ stats, double* __restrict__ C_s_prev,
-                                          const NitrateParams* nitrate = nullptr) {
+                                          const NitrateParams* nitrate = nullptr, const CropParams crop = CropParams{nullptr, nullptr, nullptr, nullptr}) {
     const SasParams& P = cx.P;
     const int A = P.A;
     const int64_t C = P.C, i = cx.i;
@@ -1178,6 +1185,22 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
     }
     FluxStats fs_evap, fs_transp, fs_qss;
     double C_transp_v = 0, C_q_ss_v = 0, C_inf1 = 0, C_inf2 = 0, C_inf3 = 0;
+    if (!STATS && crop.re) {  // svat_crop_transport_model_deterministic (transport.py:1042-1051): redistribution opens the day
+        // crop.py:2461-2558 (root growth: subsoil -> root zone), :2729-2828 (root loss: root zone -> subsoil): the flux is limited to the
+        // water the source layer holds, the solute leaves with partition coefficient 1
+        auto redistribute = [&](int src, int dst, double re_in, const double* sp, int k_re, int k_C, int k_M) {
+            double sm[1];
+            double* __restrict__ s_src = cx.pl.sa[src];
+            stream_sums<1, 1>(cx.plan, [&](int j, double* L) { L[0] = s_src[cx.ring(j)]; }, [&](int, const double* L, double* v) { v[0] = L[0]; }, sm);
+            const double re = ((re_in > sm[0]) ? sm[0] : re_in) * m;
+            const double M = anion_withdrawal<false>(cx, src, dst, re, sp + i, C, m, 1.0, true, -1, nullptr);
+            crop.out[(int64_t)k_re * C + i] = re;
+            crop.out[(int64_t)k_C * C + i] = ((re > 0) ? M / re : 0) * m;
+            crop.out[(int64_t)k_M * C + i] = M * m;
+        };
+        redistribute(1, 0, crop.re[i], crop.sp_rg, RCO_re_rg, RCO_C_re_rg, RCO_M_re_rg);
+        redistribute(0, 1, crop.re[C + i], crop.sp_rl, RCO_re_rl, RCO_C_re_rl, RCO_M_re_rl);
+    }
     {   // infiltration into the root zone
         const double c1 = ((F(RSF_inf_mat_rz) > 0) ? C_in : 0) * m, c2 = ((F(RSF_inf_pf_rz) > 0) ? C_in : 0) * m;
         const double M1 = c1 * F(RSF_inf_mat_rz) * m, M2 = c2 * F(RSF_inf_pf_rz) * m;

@@ -53,10 +53,12 @@ def conc_to_delta(conc):
         return np.where((d < D18O_MIN) | (d > D18O_MAX), np.nan, d)
 
 
-def sas_parameter_block(n_cells, spec):
-    """spec: process -> tuple (id, p1, p2, ...) or (n_cells, 8) array.  Returns (5, n_cells, 8)."""
-    out = np.zeros((len(PROCESSES), n_cells, 8))
-    for k, proc in enumerate(PROCESSES):
+def sas_parameter_block(n_cells, spec, processes=None):
+    """spec: process -> tuple (id, p1, p2, ...) or (n_cells, 8) array.  Returns (len(processes), n_cells, 8), by default for
+    the five fluxes of PROCESSES."""
+    processes = PROCESSES if processes is None else list(processes)
+    out = np.zeros((len(processes), n_cells, 8))
+    for k, proc in enumerate(processes):
         v = spec[proc]
         a = np.asarray(v, dtype=np.float64)
         if a.ndim == 1:
@@ -75,11 +77,17 @@ def initial_age_distribution(S, ages):
     return sa
 
 
+REDISTRIBUTION = ["re_rg", "re_rl", "C_re_rg", "C_re_rl", "M_re_rg", "M_re_rl"]  # enum roger_crop_output
+
+
 class SasModel:
     def __init__(self, engine_cls, n_cells, ages, daily, sas_spec, d18O_soil=-10.0, mask=None, substeps=6, store_tt=False,
-                 engine_kwargs=None, age_statistics=False, solute=ISOTOPE, anion_parameters=None, solver=DETERMINISTIC):
+                 engine_kwargs=None, age_statistics=False, solute=ISOTOPE, anion_parameters=None, solver=DETERMINISTIC, crop=False):
         """daily: dict of (n_cells, ndays + 1) arrays PREC, INF_MAT_RZ, INF_PF_RZ, INF_PF_SS, TRANSP, EVAP_SOIL, CPR_RZ,
-        Q_RZ, Q_SS, S_RZ, S_SS, S_SNOW, C_ISO_IN (index 0 = initial state, as in the reference's SVAT.nc)."""
+        Q_RZ, Q_SS, S_RZ, S_SS, S_SNOW, C_ISO_IN (index 0 = initial state, as in the reference's SVAT.nc).
+        crop: the crop variant of the offline model (settings.enable_crop_phenology, svat_crop_transport_model_deterministic): `daily`
+        then carries RE_RG, RE_RL (the redistribution fluxes of the SVAT-CROP run) and `sas_spec` the rows re_rg, re_rl."""
+        self.crop = bool(crop)
         self.C = int(n_cells)
         self.ages = int(ages)
         self.daily = {k: np.asarray(v, dtype=np.float64) for k, v in daily.items()}
@@ -90,6 +98,7 @@ class SasModel:
         self.engine = engine_cls(self.C, self.settings, **(engine_kwargs or {}))
         self.mask = np.ones(self.C) if mask is None else np.asarray(mask, dtype=np.float64)
         self.sas_params = sas_parameter_block(self.C, sas_spec)
+        self.sas_spec = sas_spec
         self.d18O_soil = d18O_soil
         self.itt = 0
         self.C_IN = delta_to_conc(self.daily["C_ISO_IN"]) if self.solute == ISOTOPE else self.daily["C_IN"]
@@ -112,6 +121,9 @@ class SasModel:
             self.engine.set_anion_parameters(p.get("alpha_transp", one), p.get("alpha_q", one), p.get("lu_id", 0 * one),
                                              p.get("S_sat_rz", np.inf * one))
         self.engine.set_parameters(self.mask, self.sas_params)
+        if self.crop:
+            rows = sas_parameter_block(self.C, self.sas_spec, processes=("re_rg", "re_rl"))
+            self.engine.set_crop_parameters(rows[0], rows[1])
         self.engine.upload_state("sa_rz", sa_rz)
         self.engine.upload_state("sa_ss", sa_ss)
         self.engine.upload_state("msa_rz", msa)
@@ -152,6 +164,8 @@ class SasModel:
         """RogerSetup.step, offline-transport branch (roger/roger.py:467-485)."""
         self.itt += 1
         f = self._set_forcing()
+        if self.crop:  # svat_crop_nitrate.py:603-604
+            self.engine.set_redistribution(self.daily["RE_RG"][:, self.itt], self.daily["RE_RL"][:, self.itt])
         self.engine.step(f)
         self.C_snow[:, 0] = self.C_snow[:, 1]  # after_timestep
         return self.itt
@@ -159,6 +173,10 @@ class SasModel:
     def outputs(self):
         o = self.engine.download_outputs()
         return {n: o[k] for k, n in enumerate(OUTPUTS)}
+
+    def redistribution(self):
+        o = self.engine.download_redistribution()
+        return {n: o[k] for k, n in enumerate(REDISTRIBUTION)}
 
     def statistics(self):
         o = self.engine.download_statistics()

@@ -37,6 +37,9 @@ def _bind(lib):
     lib.roger_sas_set_nitrate_parameters.argtypes = [hp, dp, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.roger_sas_set_nitrate_forcing.argtypes = [hp, dp]
     lib.roger_sas_download_nitrate_outputs.argtypes = [hp, dp]
+    lib.roger_sas_set_crop_parameters.argtypes = [hp, dp, dp]
+    lib.roger_sas_set_redistribution.argtypes = [hp, dp, dp]
+    lib.roger_sas_download_redistribution.argtypes = [hp, dp]
     lib.roger_sas_synchronize.argtypes = [hp]
     lib.roger_sas_last_timing.argtypes = [hp, dp, C.POINTER(C.c_int64)]
     _bound = True
@@ -159,6 +162,22 @@ class CudaSasEngine:
     def download_nitrate_outputs(self):
         out = np.empty((7, self.n))
         _check(self.lib, self.lib.roger_sas_download_nitrate_outputs(self.h, self._dp(out)))
+        return out
+
+    # ---- crop variant (svat_crop_transport_model_deterministic): redistribution after root growth / root loss opens the day
+    def set_crop_parameters(self, sas_params_re_rg, sas_params_re_rl):
+        a = [np.ascontiguousarray(x, dtype=np.float64).reshape(self.n, 8) for x in (sas_params_re_rg, sas_params_re_rl)]
+        _check(self.lib, self.lib.roger_sas_set_crop_parameters(self.h, self._dp(a[0]), self._dp(a[1])))
+
+    def set_redistribution(self, re_rg, re_rl):
+        a = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1) for x in (re_rg, re_rl)]
+        if a[0].size != self.n or a[1].size != self.n:
+            raise ValueError("set_redistribution: n_cells values each expected")
+        _check(self.lib, self.lib.roger_sas_set_redistribution(self.h, self._dp(a[0]), self._dp(a[1])))
+
+    def download_redistribution(self):
+        out = np.empty((6, self.n))
+        _check(self.lib, self.lib.roger_sas_download_redistribution(self.h, self._dp(out)))
         return out
 
     def upload_state_index(self, which, arr):

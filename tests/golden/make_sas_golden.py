@@ -53,6 +53,14 @@ CASES = {
     # cell, a fertiliser pulse, wet cells above the denitrification threshold
     "sas_nitrate": dict(shape=(2, 3), ndays=30, ages=50, doy=100, solute="nitrate",
                         sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0))),
+    # the crop variant of the offline model (svat_crop_transport_model_deterministic): redistribution between subsoil and root zone
+    # after root growth (re_rg) / root loss (re_rl) opens the day; a harvest pulse larger than the root zone holds is clamped
+    "sas_nitrate_crop": dict(shape=(2, 3), ndays=24, ages=50, doy=100, solute="nitrate", crop=True,
+                             sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0),
+                                      re_rg=(6, 0.5), re_rl=(6, 10.0))),
+    "sas_bromide_crop": dict(shape=(2, 2), ndays=16, ages=40, doy=100, solute="bromide", crop=True,
+                             sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0),
+                                      re_rg=(3, 0.7, 1.6), re_rl=(1,))),
     # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
     "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
                          sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
@@ -140,6 +148,17 @@ def build(name):
             case[k] = rng.uniform(lo, hi, (nx, ny))
         case["phi_soil_temp"] = np.full((nx, ny), 91.0)
         case.update(C_rz0=30.0, C_ss0=15.0, NMIN_RZ0=60.0, NMIN_SS0=20.0)
+    if c.get("crop"):
+        t = ndays + 1
+        rg = np.zeros((nx, ny, t))
+        rl = np.zeros((nx, ny, t))
+        rg[:, :, 2:9] = rng.uniform(0.2, 3.0, (nx, ny, 7)) * (rng.random((nx, ny, 7)) < 0.8)  # roots grow for a week ...
+        rl[:, :, 12] = rng.uniform(2.0, 25.0, (nx, ny))                                         # ... and are lost at harvest
+        rl[0, 0, 12] = 1e4                                                                      # more than the root zone holds
+        rg[1, 0, 14] = 1e4                                                                      # more than the subsoil holds
+        rl[:, :, 15:18] = rng.uniform(0.0, 1.0, rl[:, :, 15:18].shape)
+        case["RE_RG"], case["RE_RL"] = rg, rl
+        case["crop"] = True
     sas = {}
     for proc, tup in c["sas"].items():
         arr = np.zeros((nx, ny, 8))
@@ -158,6 +177,9 @@ def run(name, simd_out=None):
     nitrate = case.get("solute") == "nitrate"
     bromide = case.get("solute") in ("bromide", "nitrate")
     Setup = rh.make_nitrate_setup(case) if nitrate else (rh.make_bromide_setup(case) if bromide else rh.make_o18_setup(case))
+    crop = bool(case.get("crop"))
+    if crop:
+        Setup = rh.with_crop_redistribution(Setup, case)
     model = Setup()
     model.setup()
     model.warmup()
@@ -178,6 +200,9 @@ def run(name, simd_out=None):
         age_vars = age_vars + ["Nmin_rz", "Nmin_ss"]
         scal_vars = scal_vars + ["nit_s", "denit_s", "min_s", "ngas_s", "nfix_s", "nh4_up"]
         lvl_vars = lvl_vars + ["Nmin_s", "temp_soil"]
+    if crop:
+        tt_vars = tt_vars + ["tt_re_rg", "tt_re_rl"]
+        scal_vars = scal_vars + ["re_rg", "re_rl", "C_re_rg", "C_re_rl", "M_re_rg", "M_re_rl"]
     from roger_b200 import sas as _sas
 
     if case["age_statistics"]:
@@ -249,6 +274,9 @@ def run(name, simd_out=None):
             out["in_" + k] = np.asarray(case[k], dtype=np.float64).reshape(C, -1)
         for k in ("C_rz0", "C_ss0", "NMIN_RZ0", "NMIN_SS0"):
             out["par_" + k] = np.asarray(case[k])
+    if crop:
+        out["in_RE_RG"] = case["RE_RG"].reshape(C, -1)
+        out["in_RE_RL"] = case["RE_RL"].reshape(C, -1)
     for proc, arr in case["sas"].items():
         out["sas_" + proc] = arr.reshape(C, 8)
     for k in ("S_sat_rz", "S_sat_ss", "S_pwp_rz", "S_pwp_ss"):

@@ -657,3 +657,40 @@ def make_nitrate_setup(case):
             vs.nup = update(vs.nup, at[2:-2, 2:-2], case["NUP"][:, :, t])
 
     return NitrateSetup
+
+
+def with_crop_redistribution(Base, case):
+    """The offline transport setups above with `settings.enable_crop_phenology`: calculate_storage_selection then runs
+    svat_crop_transport_model_deterministic (roger/core/transport.py:1042-1087), i.e. the day starts with the redistribution of
+    water and solute between subsoil and root zone after root growth / root loss (crop.calculate_redistribution_transport,
+    roger/core/crop.py:2461-2867).  The redistribution fluxes are an INPUT of the offline model (the tutorial setup reads them from the
+    SVAT-CROP output, examples/plot_scale/svat_crop_nitrate_tutorial/svat_crop_nitrate.py:525-537, :603-604).
+
+    case: plus RE_RG, RE_RL (nx, ny, ndays + 1) and case["sas"]["re_rg"], case["sas"]["re_rl"] (nx, ny, 8)."""
+    import_reference()
+    from roger import roger_routine
+    from roger.core.operators import update, at
+
+    class CropSetup(Base):
+        @roger_routine
+        def set_settings(self, state):
+            super().set_settings(state)
+            state.settings.enable_crop_phenology = True
+            state.settings.identifier = state.settings.identifier + "_CROP"
+
+        @roger_routine
+        def set_parameters_setup(self, state):
+            super().set_parameters_setup(state)
+            vs = state.variables
+            vs.sas_params_re_rg = update(vs.sas_params_re_rg, at[2:-2, 2:-2, :], case["sas"]["re_rg"])
+            vs.sas_params_re_rl = update(vs.sas_params_re_rl, at[2:-2, 2:-2, :], case["sas"]["re_rl"])
+
+        @roger_routine
+        def set_forcing(self, state):
+            super().set_forcing(state)
+            vs = state.variables
+            t = vs.itt
+            vs.re_rg = update(vs.re_rg, at[2:-2, 2:-2], case["RE_RG"][:, :, t])
+            vs.re_rl = update(vs.re_rl, at[2:-2, 2:-2], case["RE_RL"][:, :, t])
+
+    return CropSetup
