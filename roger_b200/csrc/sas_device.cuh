@@ -176,9 +176,12 @@ __device__ __forceinline__ void family_prepare(Family& f, double mx) {
         if (id == 62) f.sp[1] = f.sp[3] + (r * f.sp[4]);
     }
     // An inactive Kumaraswamy / power term is `value * 0`; it is +0.0 unless value is NaN or infinite, which needs a
-    // negative or non-finite shape parameter.  With both shape parameters finite and >= 0 the skipped terms are
-    // exactly +0.0 and skipping them changes nothing.
-    f.fast = (f.sp[1] >= 0) && (f.sp[2] >= 0) && (f.sp[1] <= 1.7e308) && (f.sp[2] <= 1.7e308) && (m == 1.0);
+    // negative or non-finite shape parameter -- or a non-finite S = max(SA) (inf / inf in the power law; a StorAge that a
+    // diverged Euler / RK4 solution has driven to infinity poisons every family's sum there, and here).  With both shape
+    // parameters finite and >= 0 and S finite (hence no SA above S, none NaN) the skipped terms are exactly +0.0 and skipping
+    // them changes nothing.
+    f.fast = (f.sp[1] >= 0) && (f.sp[2] >= 0) && (f.sp[1] <= 1.7e308) && (f.sp[2] <= 1.7e308) && (m == 1.0) && (f.S <= 1.7e308) &&
+             (f.S >= -1.7e308);
 }
 
 // cumulative SAS distribution at age index jj (0..A) where the cumulative StorAge is SA: the sum of the five
