@@ -465,9 +465,11 @@ DEFAULT_TRANSPORT_ENGINE = None  # None: roger_b200.sas_engine.CudaSasEngine
 class CudaTransportDriver:
     """Drop-in for the offline oxygen-18 transport branch of `RogerSetup.step` (roger/roger.py:467-483): the setup's own
     hooks feed `vs.inf_mat_rz, vs.transp, ... vs.C_in` for the day, the engine runs
-    `transport.svat_transport_model_deterministic` (core/transport.py:948-991) -- or, with `settings.sas_solver = "Euler"`,
-    the day's explicit Euler steps (`svat_transport_model_euler`, :2063-2413, driven by :3221-3258) -- for every cell, and the results are written
-    back into `vs` with both time levels as `after_substep_iso` (:3421-3520) leaves them.
+    `transport.svat_transport_model_deterministic` (core/transport.py:948-991) -- or, with `settings.sas_solver = "Euler"` / `"RK4"`,
+    the day's explicit steps (`svat_transport_model_euler`, :2063-2413, `svat_transport_model_rk4`, :1138-2047, driven by :3221-3302) -- for
+    every cell, and the results are written back into `vs` with both time levels as `after_substep_iso` (:3421-3520) leaves them.
+    Variants: `settings.enable_crop_phenology` (anion / nitrate: redistribution after root growth / root loss opens the day),
+    `settings.enable_groundwater_boundary` (same transport; the reference computes no balance errors then).
 
         model = MyOxygen18Setup(); model.setup(); model.warmup()
         driver = CudaTransportDriver(model)
@@ -494,16 +496,29 @@ class CudaTransportDriver:
         if not getattr(st, "enable_offline_transport", False) or not (iso18 or iso2 or self.anion):
             raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium / bromide / chloride / nitrate transport models")
         solver = getattr(st, "sas_solver", None)
-        if solver not in ("deterministic", "Euler"):
-            raise NotImplementedError("sas_solver = 'deterministic' and 'Euler' run on the device (DESIGN.md section 7)")
-        self.euler = solver == "Euler"
-        if self.nitrate:
-            if self.euler or bool(getattr(st, "enable_age_statistics", False)):
-                raise NotImplementedError("nitrate runs with the deterministic solver and without age statistics")
-            for flag in ("enable_crop_phenology", "enable_crop_rotation", "enable_groundwater", "enable_groundwater_boundary"):
-                if getattr(st, flag, False):  # svat_crop_transport_model_deterministic: redistribution after root growth / harvesting
-                    raise NotImplementedError(f"nitrate transport with settings.{flag} is outside the CUDA hot path (DESIGN.md section 7)")
-        if self.euler and self.anion and bool(getattr(st, "enable_age_statistics", False)):
+        if solver not in ("deterministic", "Euler", "RK4"):
+            raise NotImplementedError(f"sas_solver = {solver!r}: 'deterministic', 'Euler' and 'RK4' run on the device")
+        self.euler = solver in ("Euler", "RK4")  # the schemes that take `sas_solver_substeps` steps per day (transport.py:3221-3302)
+        if solver == "RK4" and self.anion:
+            raise NotImplementedError("the RK4 solver runs the isotope branch only (the reference's RK4 kernels have no anion branch that runs)")
+        stats = bool(getattr(st, "enable_age_statistics", False))
+        # variants of the offline model (calculate_storage_selection, transport.py:3135-3396).  crop: redistribution after root growth
+        # / root loss opens the day (svat_crop_transport_model_deterministic :1042-1087); groundwater boundary: svat_lbc_transport_model_
+        # deterministic (:995-1040) adds the capillary rise into the subsoil, whose transport kernels are empty stubs
+        # (capillary_rise.py:590-611), and the reference then computes no balance errors (numerics.py:423-428, :1380-1387)
+        self.crop = bool(getattr(st, "enable_crop_phenology", False))
+        self.lbc = bool(getattr(st, "enable_groundwater_boundary", False))
+        for flag in ("enable_groundwater", "enable_routing_1D", "enable_routing_2D", "enable_virtualtracer"):
+            if getattr(st, flag, False):
+                raise NotImplementedError(f"offline transport with settings.{flag} is outside the CUDA hot path (DESIGN.md section 7)")
+        if self.crop and (not self.anion or self.euler or stats or self.lbc):
+            raise NotImplementedError("settings.enable_crop_phenology: anion / nitrate transport with the deterministic solver, without age "
+                                      "statistics and without the groundwater boundary")
+        if self.lbc and self.euler:
+            raise NotImplementedError("settings.enable_groundwater_boundary runs with the deterministic solver")
+        if self.nitrate and (self.euler or stats):
+            raise NotImplementedError("nitrate runs with the deterministic solver and without age statistics")
+        if self.euler and self.anion and stats:
             raise NotImplementedError("the anion branch of the explicit Euler solver runs without age statistics")
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
         self.C = self.nx * self.ny
@@ -512,7 +527,8 @@ class CudaTransportDriver:
         # deuterium runs the same kernels with its own standard ratio and plausibility window (transport.py:315-340)
         vsmow, dmin, dmax = (st.VSMOW_conc2H, st.d2H_min, st.d2H_max) if iso2 else (st.VSMOW_conc18O, st.d18O_min, st.d18O_max)
         s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats),
-                            2 if self.nitrate else (sas.ANION if self.anion else sas.ISOTOPE), sas.EULER if self.euler else sas.DETERMINISTIC)
+                            2 if self.nitrate else (sas.ANION if self.anion else sas.ISOTOPE),
+                            {"deterministic": sas.DETERMINISTIC, "Euler": sas.EULER, "RK4": sas.RK4}[solver])
         self.settings = s
         self.engine = engine_cls(self.C, s, **(engine_kwargs or {}))
         tau = int(vs.tau)
@@ -522,6 +538,9 @@ class CudaTransportDriver:
         if self.anion:
             inner = lambda n: np.asarray(getattr(vs, n))[2:-2, 2:-2].reshape(-1).astype(np.float64)  # noqa: E731
             self.engine.set_anion_parameters(inner("alpha_transp"), inner("alpha_q"), inner("lu_id"), inner("S_sat_rz"))
+        if self.crop:
+            rows = [np.asarray(getattr(vs, "sas_params_" + p))[2:-2, 2:-2, :].reshape(self.C, 8).astype(np.float64) for p in ("re_rg", "re_rl")]
+            self.engine.set_crop_parameters(rows[0], rows[1])
         for name in sas.STATE:
             self.engine.upload_state(name, np.asarray(getattr(vs, name))[2:-2, 2:-2, tau, :].reshape(self.C, self.A))
         if self.nitrate:
@@ -584,6 +603,8 @@ class CudaTransportDriver:
             z_root = np.asarray(vs.z_root)[2:-2, 2:-2, tau].reshape(-1).astype(np.float64)
             lu = np.asarray(vs.LU_ID)[2:-2, 2:-2, int(vs.itt)].reshape(-1).astype(np.float64)
             self.engine.set_nitrate_forcing(np.stack([temp, z_root, lu, inner("nup")]))
+        if self.crop:  # the setup's set_forcing has put the day's redistribution fluxes into vs.re_rg, vs.re_rl
+            self.engine.set_redistribution(np.asarray(vs.re_rg)[2:-2, 2:-2].reshape(-1), np.asarray(vs.re_rl)[2:-2, 2:-2].reshape(-1))
         self.engine.step(f)
         out = self.engine.download_outputs()
         tau, taum1 = int(vs.tau), int(vs.taum1)
@@ -605,13 +626,20 @@ class CudaTransportDriver:
                 for p in sas.PROCESSES:
                     if "tt_" + p in active:
                         self._put("tt_" + p, self.engine.download_tt(p))
+            if self.crop:
+                ro = self.engine.download_redistribution()
+                for k, name in enumerate(sas.REDISTRIBUTION):
+                    if name in active:
+                        self._put(name, ro[k])
             if self.stats:
                 st = self.engine.download_statistics()
                 for k, name in enumerate(sas.STATISTICS):
+                    if self.lbc and name in ("dS_num_error", "dC_num_error", "sanity_ok"):
+                        continue  # not computed by the reference under the groundwater boundary: the planes keep their initial 0
                     if name in active:
                         self._put(name, st[k])
                 ok = st[sas.STATISTICS.index("sanity_ok")]
-                if np.any(ok == 0.0):  # the reference's scalar is the AND over all cells (roger.py:453-456: a warning, not an error)
+                if np.any(ok == 0.0) and not self.lbc:  # the reference's scalar is the AND over all cells (roger.py:453-456: a warning, not an error)
                     import warnings
 
                     warnings.warn(f"Solution diverged at iteration {int(np.asarray(vs.itt))} (numerics.sanity_check, {int((ok == 0.0).sum())} cells)")

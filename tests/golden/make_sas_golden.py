@@ -46,6 +46,9 @@ CASES = {
                           sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     "sas_power_1500": dict(shape=(1, 2), ndays=4, ages=1500, doy=100,
                            sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
+    # groundwater boundary condition (settings.enable_groundwater_boundary): svat_lbc_transport_model_deterministic
+    "sas_power_lbc": dict(shape=(2, 2), ndays=12, ages=40, doy=100, groundwater_boundary=True, age_statistics=True,
+                          sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     # conservative anion (bromide): solute mass per age bin, partition coefficients, a crop cell whose uptake stops when wet
     "sas_bromide": dict(shape=(2, 3), ndays=26, ages=50, doy=100, solute="bromide", age_statistics=True,
                         sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
@@ -102,7 +105,7 @@ def build(name):
     svat.setup()
     daily = sas_inputs.daily_fluxes_from_svat(svat, ndays)
     case = dict(nx=nx, ny=ny, ndays=ndays, ages=ages, age_statistics=bool(c.get("age_statistics", False)),
-                sas_solver=c.get("sas_solver", "deterministic"))
+                sas_solver=c.get("sas_solver", "deterministic"), groundwater_boundary=bool(c.get("groundwater_boundary", False)))
     for k in list(sas_inputs.SUMS) + list(sas_inputs.STATES):
         case[k] = daily[k].reshape(nx, ny, ndays + 1)
     for k in ("S_pwp_rz", "S_pwp_ss"):

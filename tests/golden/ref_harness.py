@@ -283,6 +283,10 @@ def make_o18_setup(case):
             s.enable_oxygen18 = True
             s.tm_structure = "power"
             s.enable_age_statistics = bool(case.get("age_statistics", False))
+            # groundwater boundary: calculate_storage_selection then runs svat_lbc_transport_model_deterministic
+            # (transport.py:995-1040, :3304-3349), whose extra kernel -- capillary rise into the subsoil -- is an empty stub
+            # (capillary_rise.py:590-611)
+            s.enable_groundwater_boundary = bool(case.get("groundwater_boundary", False))
 
         @roger_routine
         def read_data(self, state):

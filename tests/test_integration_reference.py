@@ -152,6 +152,77 @@ def test_transport_driver_reproduces_reference_nitrate_step():
             assert rel_err(y, x) < (1e-10 if day < 10 else 1e-3), (day, n, rel_err(y, x))
 
 
+@pytest.mark.parametrize("name,ndays,tight", [("sas_rk4_stats", 8, 8), ("sas_power_lbc", 5, 5), ("sas_nitrate_crop", 10, 10), ("sas_bromide_crop", 11, 4)])
+def test_transport_driver_variants_reproduce_reference_step(name, ndays, tight):
+    """RK4 solver (with age statistics); groundwater boundary (svat_lbc_transport_model_deterministic: same transport, balance errors
+    left at 0); crop variant (redistribution after root growth / root loss) for nitrate and bromide.  The reference runs on NumPy's
+    SVML `power` in this process (see above): 1e-10 over the `tight` days before a rounding-decided clamp, the reference's own libm
+    envelope (1e-3 for the bromide exponents 0.1) afterwards -- up to the harvest pulse that empties a root zone, after which that
+    cell's concentrations are quotients of rounding residues; the bit-for-bit pins are the oracle tests on the fixtures."""
+    import make_sas_golden as mg
+    import ref_harness as rh
+    from oracle.engine import OracleSasEngine, lib
+    from roger_b200 import sas
+    from roger_b200.integration import CudaTransportDriver
+    from tests.util_sas import rel_err
+
+    lib().roger_oracle_set_pow(0)
+    case = mg.build(name)
+    solute = case.get("solute")
+    Setup = rh.make_nitrate_setup(case) if solute == "nitrate" else (rh.make_bromide_setup(case) if solute == "bromide" else rh.make_o18_setup(case))
+    if case.get("crop"):
+        Setup = rh.with_crop_redistribution(Setup, case)
+    ref, dut = Setup(), Setup()
+    for m in (ref, dut):
+        m.setup()
+        m.warmup()
+    driver = CudaTransportDriver(dut, engine_cls=OracleSasEngine)
+    a, b = ref.state.variables, dut.state.variables
+    meta = ref.state.var_meta
+    names = list(sas.STATE) + [n for n in sas.OUTPUTS if n in meta and meta[n].active and n != "C_evap_soil"]
+    if solute:
+        names += ["M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_rz", "M_ss", "M_s"]
+    if solute == "nitrate":
+        names += ["Nmin_rz", "Nmin_ss", "Nmin_s", "nit_s", "denit_s", "min_s"]
+    if case.get("crop"):
+        names += list(sas.REDISTRIBUTION)
+    if case["age_statistics"]:
+        names += [n for n in sas.STATISTICS if n != "sanity_ok"]
+    moved = 0.0
+    for day in range(ndays):
+        ref.step(ref.state)
+        driver.step()
+        assert int(a.itt) == int(b.itt) and int(a.time) == int(b.time)
+        for n in names:
+            x, y = np.asarray(getattr(a, n))[2:-2, 2:-2], np.asarray(getattr(b, n))[2:-2, 2:-2]
+            assert x.shape == y.shape
+            if "num_error" in n:  # rounding residues (1e-14 mm): compared absolutely
+                assert np.nanmax(np.abs(x - y)) < 1e-9, (day, n)
+                continue
+            lim = (1e-9 if n.startswith("C_iso") else 1e-10) if day < tight else 1e-3
+            assert rel_err(y, x) < lim, (day, n, rel_err(y, x))
+        if case.get("crop"):
+            moved += float(np.asarray(b.re_rg).sum() + np.asarray(b.re_rl).sum())  # water moved between the layers
+    if case.get("crop"):
+        assert moved > 0
+    if name == "sas_power_lbc":  # the reference leaves the balance errors at 0 under the groundwater boundary, and so does the driver
+        assert float(np.abs(np.asarray(b.dS_num_error)).max()) == 0.0 and float(np.abs(np.asarray(a.dS_num_error)).max()) == 0.0
+
+
+def test_transport_driver_refuses_what_the_reference_has_no_working_branch_for():
+    import make_sas_golden as mg
+    import ref_harness as rh
+    from oracle.engine import OracleSasEngine
+    from roger_b200.integration import CudaTransportDriver
+
+    case = mg.build("sas_bromide")
+    case["sas_solver"] = "RK4"
+    m = rh.make_bromide_setup(case)()
+    m.setup()
+    with pytest.raises(NotImplementedError, match="isotope branch only"):
+        CudaTransportDriver(m, engine_cls=OracleSasEngine)
+
+
 def test_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
     """`CudaStepDriver.enable_output`: the setup's own `state.diagnostics` configuration (rate / average / collect with their
     output variables, frequency and path) produces files whose records equal what the reference's diagnostics hold in memory at

@@ -37,6 +37,18 @@ def test_oracle_reproduces_reference_with_the_gamma_family(case):
     assert float(np.abs(fx["rec_tt_transp"]).max()) > 0  # the gamma-controlled flux withdraws water
 
 
+def test_groundwater_boundary_variant_is_the_same_transport():
+    """settings.enable_groundwater_boundary: svat_lbc_transport_model_deterministic (transport.py:995-1040) adds the capillary rise into
+    the subsoil, whose transport kernels are empty stubs (capillary_rise.py:590-611) -- bit for bit the plain model; the reference
+    then computes no balance errors (numerics.py:423-428: the planes stay 0)"""
+    fx = u.load_case("sas_power_lbc")
+    assert float(np.abs(fx["rec_dS_num_error"]).max()) == 0.0 and float(np.abs(fx["rec_dC_num_error"]).max()) == 0.0
+    for k in ("rec_dS_num_error", "rec_dC_num_error"):
+        fx.pop(k)
+    m = u.model_from_fixture(fx, OracleSasEngine)
+    u.replay_against_fixture(fx, m, exact=True)
+
+
 def test_host_side_setup_matches_reference_initial_state():
     """roger_b200.sas.SasModel.setup (initial age distributions) against the reference's set_initial_conditions."""
     fx = u.load_case("sas_power")
