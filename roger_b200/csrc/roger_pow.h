@@ -10,10 +10,18 @@
  * removes the libm from the comparison: the CUDA kernels and the CPU oracle (when told to) evaluate exactly the
  * same operation sequence and their results can be compared bit for bit.
  *
- * Algorithm (table-driven, in the style published with the ARM optimized routines):
+ * Algorithm: the table-driven pow published with the ARM optimized routines (math/pow.c, MIT licence) and shipped as the
+ * C library's pow since glibc 2.28 (pinned here: glibc 2.39, x86-64, the FMA build the dynamic loader selects on any
+ * FMA-capable CPU):
  *   log(x) = k ln2 + log(c_i) + log1p(r),  r = z / c_i - 1 exact by fma, carried as hi + lo (~2^-66 relative);
  *   exp(y hi + y lo) = 2^(k/N) e^r with 2^(i/N) from a table as scale bits + relative tail.
- * Error against the exactly rounded result: < 0.53 ulp over the domain the tests sweep (tests/test_pow.py).
+ * The operation sequence below -- which products are fused with the following sum and which are rounded separately -- is
+ * that of the library's FMA build (read off its compiled code), the constants are the published ones
+ * (tools/gen_pow_tables.py): roger_pow(x, y) and roger_exp(x) return the BITS of the C library's pow(x, y) and exp(x)
+ * for results in the normal range (tests/test_pow.py: 4e7 arguments each, no difference).  That is the function NumPy's
+ * float64 `power` / `exp` loops call when its SIMD dispatch is off -- what the reference fixtures were produced with --
+ * so the CUDA kernels reproduce those fixtures bit for bit, not only the CPU oracle.
+ * Error against the exactly rounded result: < 0.52 ulp.
  *
  * Domain: the general real power for x >= 0: x^0 = 1, 0^y = 0 / 1 / +inf, results above DBL_MAX -> +inf, results
  * below 2^-1022 are flushed to 0 (not gradual), negative or NaN base -> NaN (the SAS functions never raise a
@@ -136,8 +144,7 @@ ROGER_POW_FN double roger_pow_log(uint64_t ix, double *tail, const roger_pow_log
     const double q2 = roger_pow_fma(r, RPK(a6, ROGER_POW_A6), RPK(a5, ROGER_POW_A5));
     const double q1 = roger_pow_fma(ar2, q2, roger_pow_fma(r, RPK(a4, ROGER_POW_A4), RPK(a3, ROGER_POW_A3)));
     const double q0 = roger_pow_fma(ar2, q1, roger_pow_fma(r, RPK(a2, ROGER_POW_A2), RPK(a1, ROGER_POW_A1)));
-    const double p = roger_pow_mul(ar3, q0);
-    const double lo = roger_pow_add(roger_pow_add(roger_pow_add(roger_pow_add(lo1, lo2), lo3), lo4), p);
+    const double lo = roger_pow_fma(ar3, q0, roger_pow_add(roger_pow_add(roger_pow_add(lo1, lo2), lo3), lo4));
     const double y = roger_pow_add(hi, lo);
     *tail = roger_pow_add(roger_pow_add(hi, -y), lo);
     return y;
@@ -147,8 +154,7 @@ ROGER_POW_FN double roger_pow_log(uint64_t ix, double *tail, const roger_pow_log
 ROGER_POW_FN double roger_pow_exp(double x, double xtail, const roger_pow_exp_entry *T)
 {
     const double shift = RPK(shift, 0x1.8p52);
-    const double z = roger_pow_mul(RPK(invln2n, ROGER_POW_INVLN2N), x);
-    double kd = roger_pow_add(z, shift);
+    double kd = roger_pow_fma(RPK(invln2n, ROGER_POW_INVLN2N), x, shift);
     const uint64_t ki = roger_pow_asu(kd);
     kd = roger_pow_add(kd, -shift);
     double r = roger_pow_fma(kd, RPK(negln2hin, ROGER_POW_NEGLN2HIN), x); /* exact product, one rounding of the sum */
@@ -184,7 +190,7 @@ ROGER_POW_FN double roger_pow_core(uint64_t ix, double y, const roger_pow_tables
 ROGER_POW_FN double roger_pow_from_log(double hi, double lo, double y, const roger_pow_tables tabs)
 {
     const double ehi = roger_pow_mul(y, hi);
-    const double elo = roger_pow_add(roger_pow_mul(y, lo), roger_pow_fma(y, hi, -ehi));
+    const double elo = roger_pow_fma(y, lo, roger_pow_fma(y, hi, -ehi));
     const int ovf = !(ehi < RPK(ovf, 0x1.62e42fefa39efp+9)); /* >= 1024 ln2: overflow              */
     const int unf = ehi < RPK(unf, -0x1.6232bdd7abcd2p+9); /* result below 2^-1022: flushed to 0 */
     const int out = ovf | unf;

@@ -161,3 +161,28 @@ def test_crop_variant_needs_the_days_fluxes_and_rejects_other_configurations():
     for kw in (dict(), dict(solute=sas.ANION, age_statistics=True), dict(solute=sas.ANION, solver=sas.EULER)):
         with pytest.raises(RogerCudaError, match="crop variant"):
             _cuda()(4, sas.default_settings(8, **kw)).set_crop_parameters(rows[0], rows[1])
+
+
+@pytest.mark.parametrize("case", ["sas_nitrate", "sas_nitrate_crop", "sas_bromide_crop"])
+def test_cuda_reproduces_reference_fixture_bit_for_bit(case):
+    """nitrate (anion transport + soil nitrogen cycle) and the crop variants against the reference's own numbers, bit for bit on every
+    day (the soil temperature, a host-side expression, is taken from the fixture as in the oracle pin)"""
+    from roger_b200 import nitrate
+    from tests.test_nitrate_oracle_golden import crop_model_from_fixture, crop_snapshot
+
+    fx = u.load_case(case)
+    if case == "sas_nitrate":
+        m = model_from_fixture(fx, _cuda())
+        for day in range(int(fx["ndays"])):
+            m.step()
+            for name in nitrate.STATE:
+                assert u.same(m.state(name), fx["rec_" + name][day]), (day, name)
+            out = dict(m.nitrate_outputs(), **m.outputs())
+            for k in ("nit_s", "denit_s", "min_s", "ngas_s", "nfix_s", "nh4_up", "Nmin_s", "C_rz", "C_ss", "C_s", "C_transp", "C_q_ss"):
+                assert u.same(out[k], fx["rec_" + k][day]), (day, k)
+        return
+    m = crop_model_from_fixture(fx, _cuda())
+    for day in range(int(fx["ndays"])):
+        m.step()
+        for k, v in crop_snapshot(m, fx).items():
+            assert u.same(v, fx["rec_" + k][day]), (day, k)

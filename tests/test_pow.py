@@ -20,6 +20,20 @@ def host_pow(x, y):
     return out
 
 
+def test_bit_identical_to_the_c_librarys_pow_and_exp():
+    """roger_pow.h restates the algorithm of the C library's pow / exp (glibc >= 2.28, the FMA build the loader selects on an
+    FMA-capable x86-64 CPU) operation by operation with the published constants: for |y log x| < 511 (results between 2^-737
+    and 2^737) the bits are the library's.  NumPy's float64 `power` / `exp` loops call exactly these functions when its SIMD
+    dispatch is off, which is how the reference fixtures were produced -- so results computed with roger_pow can be compared
+    with those fixtures bit for bit."""
+    L = lib()
+    L.roger_pow_compare_libm.restype = C.c_int64
+    L.roger_pow_compare_libm.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
+    bade = C.c_int64(-1)
+    bad = L.roger_pow_compare_libm(40_000_000, 12345, C.byref(bade))
+    assert (bad, bade.value) == (0, 0), f"{bad} pow and {bade.value} exp results differ from the C library's (glibc version / non-FMA CPU?)"
+
+
 def test_within_one_ulp_of_libm_and_mostly_identical():
     rng = np.random.default_rng(1)
     x = np.concatenate([rng.uniform(0, 1, 100000), np.exp(rng.uniform(-200, 200, 100000))])

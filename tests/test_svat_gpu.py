@@ -25,6 +25,16 @@ def test_cuda_matches_reference_fixture(case):
     print(case, sorted(worst.items(), key=lambda kv: -kv[1][0])[:4])
 
 
+@pytest.mark.parametrize("case", util.SVAT_CASES + util.ONED_CASES)
+def test_cuda_reproduces_reference_fixture_bit_for_bit(case):
+    """The kernel evaluates the C library's pow (roger_pow.h returns its bits, tests/test_pow.py) and otherwise the reference's own
+    operation order: every recorded plane of every fixture -- and, for the two 256-cell fixtures, the digest of every field after
+    EVERY step -- equals the numbers the unmodified reference's NumPy backend produced, bit for bit."""
+    fx = util.load_case(case)
+    model = util.model_from_fixture(fx, _engine(), from_reference_setup=True)
+    util.replay_and_compare(fx, model, 0.0, write_fluxes=True, exact=True)
+
+
 @pytest.mark.parametrize("lateral,doy,dist,nsteps", [(True, 121, False, 70), (False, 40, False, 90), (False, 150, True, 60), (True, 330, True, 50)])
 def test_cuda_equals_oracle_bit_for_bit(lateral, doy, dist, nsteps):
     """Kernel and oracle evaluate the same pow (roger_pow.h): every parameter, state and flux plane of 1024 heterogeneous
