@@ -20,7 +20,8 @@
 /* Which pow the SAS functions call.  0: the C library's pow -- what NumPy's float64 `power` loop calls when its
  * AVX512 SVML dispatch is off; the mode the oracle is PINNED in against the reference fixtures.  1: roger_pow()
  * (roger_b200/csrc/roger_pow.h), the fixed IEEE operation sequence the CUDA kernels also evaluate, so that GPU
- * results can be compared with this oracle bit for bit (the two modes differ by at most 1 ulp per call). */
+ * results can be compared with this oracle bit for bit.  Since round 2 roger_pow restates the C library's own algorithm
+ * with the published constants: the two modes return the same bits (tests/test_pow.py), and both reproduce the fixtures. */
 ROGER_POW_DEFINE_HOST_TABLES(static const)
 int g_roger_oracle_pow_mode = 0; /* shared with svat_oracle.c */
 #define g_pow_mode g_roger_oracle_pow_mode
