@@ -46,6 +46,14 @@ typedef struct roger_svat_settings {
                                              models/svat/svat.py:333-352 (SVAT yes, oneD no) */
     int32_t forcing_uniform;    /* 1: prec/ta/pet day blocks are 144 values shared by all cells
                                    (benchmarks/SVAT_benchmark.py:162-170); 0: (C,144) per cell   */
+    int32_t enable_groundwater_boundary; /* settings.enable_groundwater_boundary (roger/roger.py:425-438): the water table
+                                   z_gw is a boundary condition the host sets (plane z_gw, m below the surface); a step then
+                                   adds the capillary rise into the subsoil (calc_cpr_ss, capillary_rise.py:176-324), the
+                                   groundwater recharge through the vadose-zone reservoir (calc_q_re,
+                                   groundwater_flow.py:99-160) and the balance terms of numerics.py:271-290, :396-420;
+                                   single steps only (no day-blocked stepping) */
+    int32_t reserved_;
+    double kf_max;              /* settings.kf_max (mm/h), groundwater boundary only          */
 } roger_svat_settings;
 
 /* Global (grid-wide) scalars of the adaptive time stepping, roger/variables.py:198-460.

@@ -35,6 +35,8 @@
     X(P, dmph) X(P, slope) \
     X(P, v_mp_layer_1) X(P, v_mp_layer_2) X(P, v_mp_layer_3) X(P, v_mp_layer_4) \
     X(P, v_mp_layer_5) X(P, v_mp_layer_6) X(P, v_mp_layer_7) X(P, v_mp_layer_8) \
+    /* groundwater boundary (settings.enable_groundwater_boundary): drainable porosity of the vadose zone below the soil */ \
+    X(P, n0) \
     /* ---- state ---------------------------------------------------------- */ \
     X(S, prec) X(S, ta) X(S, pet) \
     X(S, S_int_top) X(S, S_int_ground) X(S, swe_top) X(S, swe_ground) X(S, swe_top_tot) \
@@ -49,6 +51,9 @@
     X(S, theta_rz) X(S, theta_ss) X(S, theta) \
     X(S, k_rz) X(S, k_ss) X(S, k) X(S, h_rz) X(S, h_ss) X(S, h) \
     X(S, S_sur) X(S, S_rz) X(S, S_ss) X(S, S_s) X(S, S) \
+    /* groundwater boundary: vadose-zone reservoir below the soil and its capacity (groundwater_flow.py:99-160); z_gw_m1 is \
+       vs.z_gw[taum1], the depth of the water table of the previous step (capillary_rise.py:262-272) */ \
+    X(S, S_vad) X(S, S_vad_tot) X(S, z_gw_m1) \
     /* ---- fluxes / diagnostics ------------------------------------------ */ \
     X(F, pet_res) \
     X(F, rain_top) X(F, int_rain_top) X(F, rain_ground) X(F, int_rain_ground) \
@@ -76,7 +81,9 @@
     X(F, q_sub_ss) X(F, q_sub_mat_ss) X(F, q_sub_mp_ss) \
     X(F, q_sub_mat) X(F, q_sub_mp) X(F, q_sub) \
     X(F, z_sat_layer_1) X(F, z_sat_layer_2) X(F, z_sat_layer_3) X(F, z_sat_layer_4) \
-    X(F, z_sat_layer_5) X(F, z_sat_layer_6) X(F, z_sat_layer_7) X(F, z_sat_layer_8)
+    X(F, z_sat_layer_5) X(F, z_sat_layer_6) X(F, z_sat_layer_7) X(F, z_sat_layer_8) \
+    /* groundwater boundary: capillary rise from the water table into the subsoil, groundwater recharge */ \
+    X(F, cpr_ss) X(F, q_re)
 
 #define ROGER_FIELD_ENUM(kind, name) RF_##name,
 enum roger_svat_field { ROGER_SVAT_FIELDS(ROGER_FIELD_ENUM) RF_COUNT };

@@ -1095,6 +1095,52 @@ static void calc_cpr_rz(double *f, const step_ctx *c) /* capillary_rise.py:7-173
     V(S_fp_rz) = (mask4 ? V(S_ufc_rz) : V(S_fp_rz)) * m;
 }
 
+/* groundwater boundary (settings.enable_groundwater_boundary): capillary rise from the water table into the subsoil */
+static void calc_cpr_ss(double *f, const step_ctx *c) /* capillary_rise.py:176-324 (no film flow) */
+{
+    const double m = V(maskCatch), dt = c->dt;
+    const int mask1 = (V(z_sat) > 0) && (V(z_gw) * 1000 < V(z_soil));
+    const int mask2 = V(z_gw) * 1000 < V(z_soil);
+    const double z = (V(z_gw) * 1000 - V(z_soil)) + ((V(z_soil) - V(z_root)) / 2) * m;
+    const double pa = opow(z / (-V(ha) * 10.2), -V(n_salv));
+    const double pb = opow(-V(h_ss) / -V(ha), -V(n_salv));
+    double cpr = (pa - pb) / (1 + pb + (V(n_salv) - 1) * pa) * dt * V(ks_ss) * m;
+    cpr = ((cpr < 0) ? 0 : cpr) * m;
+    cpr = (isnan(cpr) ? 0 : cpr) * m;
+    cpr = ((cpr < 0) ? 0 : cpr) * m;
+    cpr = ((cpr > (V(S_ufc_ss) - V(S_fp_ss))) ? V(S_ufc_ss) - V(S_fp_ss) : cpr) * m; /* room in the fine pores */
+    cpr = (mask1 ? 0 : cpr) * m;                                                      /* saturated subsoil */
+    cpr = ((cpr > V(S_lp_ss)) ? cpr - V(S_lp_ss) : cpr) * m;                           /* water in the large pores */
+    cpr = ((V(z_gw) * 1000 - V(z_soil) > 10000) ? 0 : cpr) * m;                        /* water table deeper than 10 m */
+    /* the water table rises into the subsoil */
+    const double zgw_soil = (((V(z_gw) * 1000 < V(z_soil)) && (V(z_gw_m1) * 1000 >= V(z_soil))) ? V(z_soil) : V(z_gw_m1) * 1000) * m;
+    double gw_rise = -(V(z_gw) * 1000 - zgw_soil) * V(theta_ac) * m;
+    gw_rise = ((gw_rise < 0) ? 0 : gw_rise) * m;
+    gw_rise = (mask2 ? gw_rise : 0) * m;
+    cpr += gw_rise * m;
+    V(cpr_ss) = cpr;
+    V(S_fp_ss) += V(cpr_ss) * m;
+    const int mask3 = V(S_fp_ss) > V(S_ufc_ss);
+    V(S_lp_ss) += (mask3 ? (V(S_fp_ss) - V(S_ufc_ss)) : 0) * m;
+    V(S_fp_ss) = (mask3 ? V(S_ufc_ss) : V(S_fp_ss)) * m;
+}
+
+/* groundwater boundary: recharge through the vadose zone below the soil, a linear reservoir that spills when full */
+static void calc_q_re(double *f, const step_ctx *c) /* groundwater_flow.py:99-160 */
+{
+    const double m = V(maskCatch);
+    const int mask1 = V(z_gw) * 1000 > V(z_soil);
+    V(S_vad_tot) = (mask1 ? (V(z_gw) * 1000 - V(z_soil)) * V(n0) : 0) * m;
+    V(S_vad) += V(q_ss) * m;
+    const double k = (V(kf) / c->st->kf_max) * m;
+    V(q_re) = k * V(S_vad) * m;
+    V(S_vad) += -V(q_re) * m;
+    const int mask2 = V(S_vad) > V(S_vad_tot);
+    const double spill = (mask2 ? (V(S_vad) - V(S_vad_tot)) : 0) * m;
+    V(q_re) += spill * m;
+    V(S_vad) += -spill * m;
+}
+
 /* ================================================================================== */
 /* storages: surface.py:8-28, root_zone.py:36-163, subsoil.py:6-130, soil.py:9-140,     */
 /* numerics.py:125-152, :217-346                                                      */
@@ -1140,7 +1186,17 @@ static int calc_num_error_and_check(double *f, const step_ctx *c, const cell_m1 
 {
     const double atol = c->st->atol, rtol = c->st->rtol;
     double lhs = V(S) - p->S, rhs;
-    if (c->st->enable_lateral_flow) { /* numerics.py:224-246 */
+    if (c->st->enable_groundwater_boundary) {
+        /* the balance error (numerics.py:271-290 with lateral flow, :396-420 without) and the closure the sanity check tests
+         * (:822-841, :902-918) are different expressions when lateral flow is on: q_re there, q_ss here */
+        if (c->st->enable_lateral_flow) {
+            V(dS_num_error) = fabs(lhs - (V(prec) - V(q_sur) - V(aet) - V(q_re) - V(q_sub) + V(cpr_ss)));
+            rhs = V(prec) - V(q_sur) - V(aet) - V(q_ss) - V(q_sub) + V(cpr_ss);
+        } else {
+            rhs = V(prec) - V(q_sur) - V(aet) - V(q_ss) + V(cpr_ss);
+            V(dS_num_error) = fabs(lhs - rhs);
+        }
+    } else if (c->st->enable_lateral_flow) { /* numerics.py:224-246 */
         rhs = V(prec) - V(q_sur) - V(aet) - V(q_ss) - V(q_sub);
         V(dS_num_error) = fabs(lhs - rhs);
     } else { /* numerics.py:303-346 */
@@ -1359,8 +1415,11 @@ void svat_oracle_step(int64_t C, double *planes, const double *prec_day, const d
             calc_percolation_ss(f);
         }
         calc_cpr_rz(f, &ctx);
+        if (st->enable_groundwater_boundary) calc_cpr_ss(f, &ctx); /* capillary_rise.py:346-358 */
         calc_storages(f, &ctx, &p);
+        if (st->enable_groundwater_boundary) calc_q_re(f, &ctx);   /* roger.py:436-438 */
         int ok = calc_num_error_and_check(f, &ctx, &p);
+        if (st->enable_groundwater_boundary) V(z_gw_m1) = V(z_gw); /* after_timestep of the setups: vs.z_gw[taum1] = vs.z_gw[tau] */
         all_ok = all_ok && ok;
         /* after_timestep: clamp tiny negatives (models/svat/svat.py:333-352) */
         if (st->clamp_small_negative_storage) {

@@ -28,6 +28,7 @@ class SvatSettings(C.Structure):
         ("transp_water_stress", C.c_double), ("dx", C.c_double), ("atol", C.c_double), ("rtol", C.c_double),
         ("enable_lateral_flow", C.c_int32), ("enable_macropore_lower_boundary_condition", C.c_int32),
         ("clamp_small_negative_storage", C.c_int32), ("forcing_uniform", C.c_int32),
+        ("enable_groundwater_boundary", C.c_int32), ("reserved_", C.c_int32), ("kf_max", C.c_double),
     ]
 
 
@@ -54,6 +55,7 @@ def default_settings(lateral=False, forcing_uniform=True, **over):
         l_sc=D["l_sc"], pi=D["pi"], transp_water_stress=D["transp_water_stress"], dx=D["dx"], atol=D["atol"],
         rtol=D["rtol"], enable_lateral_flow=int(lateral), enable_macropore_lower_boundary_condition=0,
         clamp_small_negative_storage=int(not lateral), forcing_uniform=int(forcing_uniform),
+        enable_groundwater_boundary=0, reserved_=0, kf_max=D.get("kf_max", 3600.0),
     )
     for k, v in over.items():
         setattr(s, k, v)

@@ -236,7 +236,7 @@ __host__ __device__ constexpr unsigned kPrefetchEnd() {  // the head of the tile
     return (unsigned)((LAT ? kHotOned : kHotSvat) * kTile * sizeof(double));
 }
 static_assert(ROGER_BLOCK == kTile, "one k_svat_step block per tile");
-template <bool LAT, bool FLUX>
+template <bool LAT, bool FLUX, bool GWB = false>
 __global__ void __launch_bounds__(ROGER_BLOCK, ROGER_MIN_BLOCKS)
 k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* __restrict__ ta_day,
             const double* __restrict__ pet_day, StepPlan p, unsigned* flags) {
@@ -283,7 +283,7 @@ k_svat_step(Planes pl, const double* __restrict__ prec_m1_plane, const double* _
         }
         io.sts(RF_prec, c.prec); io.sts(RF_ta, c.ta); io.sts(RF_pet, c.pet);
 
-        const bool ok = (c.m == 1.0) ? cell_step<LAT, FLUX, true>(c, p, io) : cell_step<LAT, FLUX, false>(c, p, io);
+        const bool ok = (c.m == 1.0) ? cell_step<LAT, FLUX, true, GWB>(c, p, io) : cell_step<LAT, FLUX, false, GWB>(c, p, io);
 
         bits |= (c.swe > 0) ? FLAG_SWE_GT0 : 0;
         bits |= !(c.swe <= 0) ? FLAG_SWE_NOT_LE0 : 0;
@@ -670,6 +670,8 @@ static int copy_plane_to_host(roger_svat* h, const double* snap, double* host_pi
 int roger_svat_create(roger_svat** out, int64_t n_cells, const roger_svat_settings* settings, int device) {
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_svat_create: bad argument");
     if (n_cells >= (int64_t(1) << 31)) return fail(ROGER_EINVAL, "roger_svat_create: at most 2^31 - 1 cells per handle; shard the grid");
+    if (settings->enable_groundwater_boundary && !(settings->kf_max > 0))
+        return fail(ROGER_EINVAL, "roger_svat_create: settings.kf_max must be positive with enable_groundwater_boundary");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -1129,6 +1131,7 @@ static void schedule_second_half(roger_svat* h, unsigned ev, const SchedA& a, ro
     p.uniform = st.forcing_uniform;
     p.lbc = st.enable_macropore_lower_boundary_condition;
     p.clamp = st.clamp_small_negative_storage;
+    p.kf_max = st.kf_max;
 }
 
 // bookkeeping at the end of a step (roger.py:447-448 and the after_timestep roll)
@@ -1212,10 +1215,13 @@ static int step_impl(roger_svat* h, int write_fluxes) {
 
     CU(cudaMemsetAsync(h->d_flags, 0, sizeof(unsigned), h->stream));
     const Planes pl = h->planes();
-#define LAUNCH(LAT, FLUX) \
-    k_svat_step<LAT, FLUX><<<blocks, threads, 0, h->stream>>>(pl, h->d_prec_m1, h->forc[1], h->forc[2], p, h->d_flags)
-    if (st.enable_lateral_flow) { if (write_fluxes) LAUNCH(true, true); else LAUNCH(true, false); }
-    else { if (write_fluxes) LAUNCH(false, true); else LAUNCH(false, false); }
+#define LAUNCH(LAT, FLUX, GWB) \
+    k_svat_step<LAT, FLUX, GWB><<<blocks, threads, 0, h->stream>>>(pl, h->d_prec_m1, h->forc[1], h->forc[2], p, h->d_flags)
+    if (st.enable_groundwater_boundary) {  // the water table as a boundary condition: capillary rise into the subsoil, recharge
+        if (st.enable_lateral_flow) { if (write_fluxes) LAUNCH(true, true, true); else LAUNCH(true, false, true); }
+        else { if (write_fluxes) LAUNCH(false, true, true); else LAUNCH(false, false, true); }
+    } else if (st.enable_lateral_flow) { if (write_fluxes) LAUNCH(true, true, false); else LAUNCH(true, false, false); }
+    else { if (write_fluxes) LAUNCH(false, true, false); else LAUNCH(false, false, false); }
 #undef LAUNCH
     h->soil_kh_stale = !write_fluxes;
     CU(cudaGetLastError());
@@ -1262,6 +1268,7 @@ static int step_impl(roger_svat* h, int write_fluxes) {
 // read-back latency and, on several GPUs, one flag exchange per batch instead of one per step.
 static int run_block(roger_svat* h, int max_steps, int* n_done, bool queued, int write_fluxes, bool caller_wants_fluxes) {
     *n_done = 0;
+    if (h->st.enable_groundwater_boundary) return 0;  // single steps only (the batched kernels are built without that variant)
     const roger_svat_settings& st = h->st;
     if (!st.forcing_uniform || !h->ks_ss_synced || !h->have_forcing || max_steps < 2) return 0;
     CU(cudaSetDevice(h->device));

@@ -41,6 +41,7 @@ struct StepPlan {
     int uniform;          // forcing shared by all cells
     int lbc;              // settings.enable_macropore_lower_boundary_condition
     int clamp;            // after_timestep clamp of tiny negative storages (SVAT setups)
+    double kf_max;        // settings.kf_max (groundwater boundary: calc_q_re)
     unsigned long long flux_mask[2];  // FLUX kernels: which flux planes are stored (bit f - first flux id); all ones in parity mode,
                                       // only the accumulated ones when a diagnostics accumulator is what asked for the flux kernel
 };
@@ -162,7 +163,9 @@ constexpr size_t kTileBytesF = (size_t)kNumFPlanes * kTile * sizeof(double);
     /* ---- end of the planes every state-only oneD step reads (kHotOned) ---- */ \
     X(theta_4) X(theta_27) X(z_sc_max) X(k_stress_transp) X(k_ss) X(S_rz) X(S_ss) X(S_s) X(theta) \
     X(k_stress_evap) X(theta_ss) X(k) X(h) X(S_sur) \
-    X(theta_sat) X(theta_fc) X(S_ac_rz) X(S_ufc_rz) X(S_pwp_rz) X(S_ac_ss) X(S_ufc_ss) X(S_pwp_ss) X(S_pwp_s)
+    X(theta_sat) X(theta_fc) X(S_ac_rz) X(S_ufc_rz) X(S_pwp_rz) X(S_ac_ss) X(S_ufc_ss) X(S_pwp_ss) X(S_pwp_s) \
+    /* groundwater boundary only (k_svat_step<.., GWB = true>) */ \
+    X(n0) X(S_vad) X(S_vad_tot) X(z_gw_m1)
 #define ROGER_SLOT_ENUM(name) SLOT_##name,
 enum roger_svat_slot { ROGER_SVAT_PS_ORDER(ROGER_SLOT_ENUM) SLOT_COUNT };
 #undef ROGER_SLOT_ENUM
@@ -1195,6 +1198,60 @@ RD void subsurface(Cell& c, const StepPlan& p, const Io& io) {
     }
 }
 
+// ---- groundwater boundary condition (settings.enable_groundwater_boundary) ----------------------------------------
+// calc_cpr_ss capillary_rise.py:176-324 (no film flow): capillary rise from the water table into the subsoil plus the water a
+// rising water table brings into it; runs right after calc_cpr_rz (capillary_rise.py:346-358)
+template <bool FLUX, bool MASK1>
+RD void capillary_rise_subsoil(Cell& c, const StepPlan& p, const Io& io) {
+    LDS(z_gw_m1);
+    const double dt = p.dt;
+    const bool mask1 = (c.z_sat > 0) && (c.z_gw * 1000 < c.z_soil);
+    const bool mask2 = c.z_gw * 1000 < c.z_soil;
+    const double z = (c.z_gw * 1000 - c.z_soil) + M((c.z_soil - c.z_root) / 2);
+    const double mn = -c.n_salv;
+    const double pa = powr(z / (-c.ha * 10.2), mn);
+    const double pb = powr(-c.h_ss / -c.ha, mn);
+    double cpr = M((pa - pb) / (1 + pb + (c.n_salv - 1) * pa) * dt * c.ks_ss);
+    cpr = M((cpr < 0) ? 0.0 : cpr);
+    cpr = M(isnan(cpr) ? 0.0 : cpr);
+    cpr = M((cpr < 0) ? 0.0 : cpr);
+    const double S_ufc_ss = c.S_ufc_ss;
+    cpr = M((cpr > (S_ufc_ss - c.S_fp_ss)) ? S_ufc_ss - c.S_fp_ss : cpr);
+    cpr = M(mask1 ? 0.0 : cpr);
+    cpr = M((cpr > c.S_lp_ss) ? cpr - c.S_lp_ss : cpr);
+    cpr = M((c.z_gw * 1000 - c.z_soil > 10000) ? 0.0 : cpr);
+    const double zgw_soil = M(((c.z_gw * 1000 < c.z_soil) && (c.z_gw_m1 * 1000 >= c.z_soil)) ? c.z_soil : c.z_gw_m1 * 1000);
+    double gw_rise = M(-(c.z_gw * 1000 - zgw_soil) * c.theta_ac);
+    gw_rise = M((gw_rise < 0) ? 0.0 : gw_rise);
+    gw_rise = M(mask2 ? gw_rise : 0.0);
+    cpr += M(gw_rise);
+    c.cpr_ss = cpr;
+    c.S_fp_ss += M(c.cpr_ss);
+    const bool ex = c.S_fp_ss > S_ufc_ss;
+    c.S_lp_ss += M(ex ? (c.S_fp_ss - S_ufc_ss) : 0.0);
+    c.S_fp_ss = M(ex ? S_ufc_ss : c.S_fp_ss);
+    STF(cpr_ss);
+}
+
+// calc_q_re groundwater_flow.py:99-160: recharge through the vadose zone below the soil, a linear reservoir that spills when full;
+// runs after the storage kernels (roger.py:436-438).  Then vs.z_gw[taum1] = vs.z_gw[tau] (the setups' after_timestep).
+template <bool FLUX, bool MASK1>
+RD void groundwater_recharge(Cell& c, const StepPlan& p, const Io& io) {
+    LDP(n0);
+    LDS(S_vad);
+    c.S_vad_tot = M((c.z_gw * 1000 > c.z_soil) ? (c.z_gw * 1000 - c.z_soil) * c.n0 : 0.0);
+    c.S_vad += M(c.q_ss);
+    const double k = M(c.kf / p.kf_max);
+    c.q_re = M(k * c.S_vad);
+    c.S_vad += M(-c.q_re);
+    const double spill = M((c.S_vad > c.S_vad_tot) ? (c.S_vad - c.S_vad_tot) : 0.0);
+    c.q_re += M(spill);
+    c.S_vad += M(-spill);
+    c.z_gw_m1 = c.z_gw;
+    STS(S_vad); STS(S_vad_tot); STS(z_gw_m1);
+    STF(q_re);
+}
+
 // Brooks-Corey conductivity and matric potential of one layer (root_zone.py:36-60, subsoil.py:22-48,
 // soil.py:9-42): k = ks / (1 + r**-m), h = ha / r**(1/lambda) with r = theta / theta_sat.
 template <bool MASK1>
@@ -1264,11 +1321,21 @@ RD void soil_kh_refresh(const Io& io) {
 }
 
 // numerics.py:217-346 calc_dS_num_error and :742-800 / :978-1016 sanity_check; returns the cell's verdict
-template <bool LAT, bool FLUX>
+template <bool LAT, bool FLUX, bool GWB = false>
 RD bool balance_check(Cell& c, const StepPlan& p, const Io& io) {
     const double lhs = c.S - c.S_m1;
     double rhs;
-    if (LAT) {
+    if (GWB) {
+        // the balance error (numerics.py:271-290 with lateral flow, :396-420 without) and the closure the sanity check tests
+        // (:822-841, :902-918) are different expressions when lateral flow is on: q_re there, q_ss here
+        if (LAT) {
+            c.dS_num_error = fabs(lhs - (c.prec - c.q_sur - c.aet - c.q_re - c.q_sub + c.cpr_ss));
+            rhs = c.prec - c.q_sur - c.aet - c.q_ss - c.q_sub + c.cpr_ss;
+        } else {
+            rhs = c.prec - c.q_sur - c.aet - c.q_ss + c.cpr_ss;
+            c.dS_num_error = fabs(lhs - rhs);
+        }
+    } else if (LAT) {
         rhs = c.prec - c.q_sur - c.aet - c.q_ss - c.q_sub;
         c.dS_num_error = fabs(lhs - rhs);
     } else {
@@ -1290,7 +1357,7 @@ RD bool balance_check(Cell& c, const StepPlan& p, const Io& io) {
     ok = ok && (nz(c.S_fp_rz) - a <= nz(c.S_ufc_rz)) && (nz(c.S_lp_rz) - a <= nz(c.S_ac_rz)) &&
          (nz(c.S_fp_ss) - a <= nz(c.S_ufc_ss)) && (nz(c.S_lp_ss) - a <= nz(c.S_ac_ss));
     STF(dS_num_error);
-    if (!LAT) { STF(dS_rz_num_error); STF(dS_ss_num_error); }
+    if (!LAT && !GWB) { STF(dS_rz_num_error); STF(dS_ss_num_error); }
     return ok;
 }
 
@@ -1379,7 +1446,7 @@ RD void prefetch_later_groups(const StepPlan& p, const Io& io) {
 #undef PF
 }
 
-template <bool LAT, bool FLUX, bool MASK1>
+template <bool LAT, bool FLUX, bool MASK1, bool GWB = false>
 RD bool cell_step(Cell& c, const StepPlan& p, const Io& io) {
     derived_parameters<MASK1>(c, io);
     c.pet_res = c.pet;  // adaptive_time_stepping.py:367-368
@@ -1403,9 +1470,11 @@ RD bool cell_step(Cell& c, const StepPlan& p, const Io& io) {
     if (!ROGER_PREFETCH) load_subsurface<LAT>(c, io);
     if (ROGER_PREFETCH) load_storages<FLUX>(c, io);
     subsurface<LAT, FLUX, MASK1>(c, p, io);
+    if (GWB) capillary_rise_subsoil<FLUX, MASK1>(c, p, io);
     if (!ROGER_PREFETCH) load_storages<FLUX>(c, io);
     storages<FLUX, MASK1>(c, p, io);
-    bool ok = balance_check<LAT, FLUX>(c, p, io);
+    if (GWB) groundwater_recharge<FLUX, MASK1>(c, p, io);
+    bool ok = balance_check<LAT, FLUX, GWB>(c, p, io);
     if (p.clamp) {  // models/svat/svat.py:333-352
         c.S_fp_rz = ((c.S_fp_rz > -1e-6) && (c.S_fp_rz < 0)) ? 0.0 : c.S_fp_rz;
         c.S_lp_rz = ((c.S_lp_rz > -1e-6) && (c.S_lp_rz < 0)) ? 0.0 : c.S_lp_rz;

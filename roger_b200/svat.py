@@ -18,7 +18,7 @@ DAY = 24 * 60 * 60
 
 class SvatModel:
     def __init__(self, engine_cls, shape, forcing, primary, theta_rz0, theta_ss0, lateral=False, weights=None,
-                 settings=None, engine_kwargs=None, cell_order=None):
+                 settings=None, engine_kwargs=None, cell_order=None, z_gw_daily=None):
         self.shape = tuple(shape)
         self.C = int(np.prod(self.shape))
         self.lateral = bool(lateral)
@@ -27,7 +27,14 @@ class SvatModel:
         self.theta_rz0 = np.asarray(theta_rz0, dtype=np.float64).reshape(-1)
         self.theta_ss0 = np.asarray(theta_ss0, dtype=np.float64).reshape(-1)
         self.weights = None if weights is None else {k: np.asarray(v, dtype=np.float64).reshape(-1) for k, v in weights.items()}
-        self.settings = abi.default_settings(lateral=self.lateral, forcing_uniform=self.weights is None, **(settings or {}))
+        # groundwater boundary (settings.enable_groundwater_boundary): z_gw_daily holds the depth of the water table (m) per cell and
+        # day, (n_cells, ndays + 1) with column 0 the initial state -- the boundary condition the setups read from their forcing file
+        # (examples/hillslope_scale/oneD_with_groundwater_boundary_condition_distributed_tutorial/oneD.py:317-361)
+        self.z_gw_daily = None if z_gw_daily is None else np.asarray(z_gw_daily, dtype=np.float64).reshape(self.C, -1)
+        settings = dict(settings or {})
+        if self.z_gw_daily is not None:
+            settings.setdefault("enable_groundwater_boundary", 1)
+        self.settings = abi.default_settings(lateral=self.lateral, forcing_uniform=self.weights is None, **settings)
         self.engine = engine_cls(self.C, self.settings, **(engine_kwargs or {}))
         # device-side cell ordering by infiltration capacity (engine.optimize_cell_order); ROGER_B200_CELL_ORDER=0 switches it off
         self.cell_order = (os.environ.get("ROGER_B200_CELL_ORDER", "1") != "0") if cell_order is None else bool(cell_order)
@@ -48,10 +55,13 @@ class SvatModel:
         planes.update({k: v for k, v in d.items() if k in abi.FIELD_ID})
         planes.update({k: v for k, v in ic.items() if k in abi.FIELD_ID})
         planes.update({k: v for k, v in sp.items() if k in abi.FIELD_ID})
-        for k in ("lu_id", "z_soil", "dmpv", "lmpv", "theta_ac", "theta_ufc", "theta_pwp", "ks", "kf", "sealing", "dmph", "slope"):
+        for k in ("lu_id", "z_soil", "dmpv", "lmpv", "theta_ac", "theta_ufc", "theta_pwp", "ks", "kf", "sealing", "dmph", "slope", "n0"):
             if k in p:
                 planes[k] = p[k].astype(np.float64)
         planes["z_gw"] = np.full(self.C, 1000.0)  # vs.z_gw initial value (roger/variables.py:3248)
+        if self.z_gw_daily is not None:
+            planes["z_gw"] = self.z_gw_daily[:, 0].copy()
+        planes["z_gw_m1"] = planes["z_gw"]
         if override_planes:
             planes.update(override_planes)
         for n in abi.FIELD_NAMES:
@@ -79,6 +89,8 @@ class SvatModel:
             ta = ta[None, :] + w["ta_offset"][:, None]
             pet = pet[None, :] * w["pet_weight"][:, None]
         self.engine.set_forcing_day(prec, ta, pet)
+        if self.z_gw_daily is not None:  # vs.z_gw[tau] of the day that begins
+            self.engine.upload("z_gw", self.z_gw_daily[:, min(i0 // abi.SLOTS_PER_DAY + 1, self.z_gw_daily.shape[1] - 1)])
         self.itt_forc += abi.SLOTS_PER_DAY
 
     def _set_parameters(self, sc):

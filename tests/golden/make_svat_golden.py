@@ -58,6 +58,10 @@ CASES = {
                            masked=0.05, sealed=0.3, lu=(5, 6, 7, 8, 9, 10, 11, 12, 13), full_records=(1, 2, 100, 200), digest=True),
     "oned_hetero256": dict(event="mixed", ndays=25, shape=(16, 16), hetero=True, dist=True, lateral=True, doy=95, every=10 ** 9,
                            masked=0.05, sealed=0.3, full_records=(1, 2, 100, 200), digest=True),
+    # groundwater boundary condition (settings.enable_groundwater_boundary): a water table that moves with time -- in some cells up
+    # into the subsoil and back -- capillary rise from it, recharge through the vadose-zone reservoir
+    "svat_gwb": dict(event="mixed", ndays=24, shape=(4, 4), hetero=True, dist=True, lateral=False, doy=100, every=4, masked=0.1, gwb=True),
+    "oned_gwb": dict(event="mixed", ndays=20, shape=(3, 4), hetero=True, dist=False, lateral=True, doy=95, every=4, gwb=True),
 }
 
 
@@ -80,6 +84,17 @@ def build_case(name):
         rng = np.random.default_rng(46)
         params["sealing"] = np.where(rng.uniform(size=(nx, ny)) < c["sealed"], np.round(rng.uniform(0.05, 0.6, (nx, ny)), 2), 0.0)
     case = dict(nx=nx, ny=ny, ndays=c["ndays"], params=params, theta_rz0=th_rz, theta_ss0=th_ss, lateral=c["lateral"], **forc)
+    if c.get("gwb"):
+        rng = np.random.default_rng(47)
+        params["n0"] = rng.uniform(0.05, 0.3, (nx, ny))
+        params["kf"] = rng.uniform(5, 2500, (nx, ny))
+        base = np.asarray(params["z_soil"]) / 1000 + np.where(rng.random((nx, ny)) < 0.5, rng.uniform(0.02, 0.4, (nx, ny)), rng.uniform(0.4, 4.0, (nx, ny)))
+        base.reshape(-1)[0] += 11.0  # one cell with the water table more than 10 m below the soil
+        t = np.arange(c["ndays"] + 1)
+        amp = rng.uniform(0.1, 0.6, (nx, ny))
+        z = base[:, :, None] - amp[:, :, None] * np.sin(t / 3.0)[None, None, :]
+        z[:, :, 0] = base  # numerics.validate_parameters wants the initial water table below the soil
+        case["Z_GW"] = z
     if c["dist"]:
         case.update(synth.distributed_weights((nx, ny), seed=44))
     return case, c
@@ -169,7 +184,7 @@ def run(name):
         out["digest_valid"] = ~np.isnan(init_fields).all(axis=1)
     for k, v in case["params"].items():
         out["param_" + k] = np.asarray(v)
-    for k in ("prec_weight", "ta_offset", "pet_weight"):
+    for k in ("prec_weight", "ta_offset", "pet_weight", "Z_GW"):
         if k in case:
             out[k] = case[k]
     # every derived per-cell variable after setup (for the host-side parameter derivation tests)

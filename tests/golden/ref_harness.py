@@ -56,12 +56,17 @@ def make_svat_setup(case):
     nx, ny, ndays = case["nx"], case["ny"], case["ndays"]
     P = case["params"]
     lateral = bool(case.get("lateral", False))
+    # groundwater boundary condition: case["Z_GW"] (nx, ny, ndays + 1) is the depth of the water table (m), column 0 the initial
+    # state (examples/hillslope_scale/oneD_with_groundwater_boundary_condition_distributed_tutorial/oneD.py:266, :317-361)
+    gwb = case.get("Z_GW") is not None
 
     copy_tau = [
         "ta", "z_root", "ground_cover", "S_sur", "S_int_top", "S_int_ground", "S_dep", "S_snow", "swe",
         "S_rz", "S_ss", "S_s", "S", "z_sat", "z_wf", "z_wf_t0", "z_wf_t1", "y_mp", "y_sc", "theta_rz",
         "theta_ss", "theta", "k_rz", "k_ss", "k", "h_rz", "h_ss", "h", "z0", "prec",
     ]
+    if gwb:
+        copy_tau = copy_tau + ["z_gw", "S_vad"]
 
     class GoldenSetup(RogerSetup):
         @roger_routine
@@ -76,7 +81,7 @@ def make_svat_setup(case):
             s.x_origin = 0.0
             s.y_origin = 0.0
             s.time_origin = "2017-12-31 00:00:00"
-            s.enable_groundwater_boundary = False
+            s.enable_groundwater_boundary = gwb
             s.enable_adaptive_time_stepping = True
             if lateral:
                 s.enable_lateral_flow = True
@@ -136,6 +141,8 @@ def make_svat_setup(case):
             th_ss = onp.asarray(case["theta_ss0"])[:, :, None]
             vs.theta_rz = update(vs.theta_rz, at[2:-2, 2:-2, : vs.taup1], th_rz)
             vs.theta_ss = update(vs.theta_ss, at[2:-2, 2:-2, : vs.taup1], th_ss)
+            if gwb:
+                vs.z_gw = update(vs.z_gw, at[2:-2, 2:-2, : vs.taup1], onp.asarray(case["Z_GW"])[:, :, 0][:, :, None])
 
         @roger_routine
         def set_boundary_conditions_setup(self, state):
@@ -183,6 +190,9 @@ def make_svat_setup(case):
                     vs.prec_day = update(vs.prec_day, at[:, :, :], prec)
                     vs.ta_day = update(vs.ta_day, at[:, :, :], ta)
                     vs.pet_day = update(vs.pet_day, at[:, :, :], pet)
+                if gwb:
+                    day = min(int(vs.itt_forc) // (6 * 24) + 1, onp.asarray(case["Z_GW"]).shape[2] - 1)
+                    vs.z_gw = update(vs.z_gw, at[2:-2, 2:-2, vs.tau], onp.asarray(case["Z_GW"])[:, :, day])
                 vs.itt_forc = vs.itt_forc + 6 * 24
 
         @roger_routine

@@ -8,8 +8,8 @@ from roger_b200.svat import SvatModel
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-SVAT_CASES = ["svat_rain", "svat_heavyrain", "svat_snowrain", "svat_snow", "svat_mixed_dist", "svat_hetero256"]
-ONED_CASES = ["oned_rain", "oned_mixed", "oned_hetero256"]
+SVAT_CASES = ["svat_rain", "svat_heavyrain", "svat_snowrain", "svat_snow", "svat_mixed_dist", "svat_hetero256", "svat_gwb"]
+ONED_CASES = ["oned_rain", "oned_mixed", "oned_hetero256", "oned_gwb"]
 
 
 def field_digest(row):
@@ -38,8 +38,9 @@ def model_from_fixture(fx, engine_cls, from_reference_setup=True, engine_kwargs=
     weights = None
     if "prec_weight" in fx:
         weights = {k: fx[k] for k in ("prec_weight", "ta_offset", "pet_weight")}
+    z_gw = fx["Z_GW"].reshape(shape[0] * shape[1], -1) if "Z_GW" in fx else None  # groundwater boundary condition
     m = SvatModel(engine_cls, shape, forcing, primary, fx["theta_rz0"], fx["theta_ss0"], lateral=bool(fx["lateral"]),
-                  weights=weights, engine_kwargs=engine_kwargs)
+                  weights=weights, engine_kwargs=engine_kwargs, z_gw_daily=z_gw)
     over = None
     if from_reference_setup:
         names = [str(n) for n in fx["field_names"]]
