@@ -43,7 +43,7 @@ _SCALARS = ("time", "itt", "dt_secs", "itt_day", "event_id_counter", "time_event
 # settings (roger/settings.py:86-113) whose branches of RogerSetup.step the CUDA engine does not implement: a setup that
 # switches one of them on is refused instead of being run without it
 UNSUPPORTED_SETTINGS = (
-    "enable_groundwater", "enable_groundwater_boundary", "enable_film_flow", "enable_routing_1D", "enable_routing_2D",
+    "enable_groundwater", "enable_film_flow", "enable_routing_1D", "enable_routing_2D",
     "enable_runon_infiltration", "enable_urban", "enable_soil_compaction", "enable_time_variant_macropores",
     "enable_irrigation", "enable_net_irrigation", "enable_crop_phenology", "enable_crop_rotation",
     "enable_crop_specific_irrigation_demand", "enable_crop_partitioning", "enable_crop_water_stress", "enable_crop_optimization",
@@ -113,6 +113,10 @@ class CudaStepDriver:
         vs = self.state.variables
         if name == "maskRiverLake":
             a = np.asarray(vs.maskRiver) | np.asarray(vs.maskLake)
+            return a[2:-2, 2:-2].reshape(-1).astype(np.float64)
+        if name == "z_gw_m1":  # the previous step's water table (groundwater boundary): vs.z_gw[taum1]
+            a = np.asarray(vs.z_gw)
+            a = a[:, :, int(vs.taum1)] if a.ndim == 3 else a
             return a[2:-2, 2:-2].reshape(-1).astype(np.float64)
         a = np.asarray(getattr(vs, name))
         if a.ndim == 3:
@@ -229,6 +233,8 @@ class CudaStepDriver:
         s = abi.default_settings(lateral=self.lateral, forcing_uniform=uniform, **over)
         s.enable_macropore_lower_boundary_condition = int(bool(getattr(st, "enable_macropore_lower_boundary_condition", False)))
         s.clamp_small_negative_storage = int(self._clamp)
+        s.enable_groundwater_boundary = int(bool(getattr(st, "enable_groundwater_boundary", False)))
+        s.kf_max = float(getattr(st, "kf_max", 3600.0))
         return s
 
     def _create_engine(self, uniform):
@@ -236,7 +242,7 @@ class CudaStepDriver:
         vs = self.state.variables
         zeros = np.zeros(self.C)
         for name in abi.FIELD_NAMES:
-            if name == "maskRiverLake" or name in self._active:
+            if name == "maskRiverLake" or name in self._active or (name == "z_gw_m1" and "z_gw" in self._active):
                 self._upload(name)
             else:
                 self.engine.upload(name, zeros)

@@ -23,7 +23,7 @@ def _case(name):
     return case
 
 
-@pytest.mark.parametrize("name,nsteps", [("svat_mixed_dist", 260), ("oned_rain", 50), ("svat_snowrain", 50)])
+@pytest.mark.parametrize("name,nsteps", [("svat_mixed_dist", 260), ("oned_rain", 50), ("svat_snowrain", 50), ("svat_gwb", 120), ("oned_gwb", 120)])
 def test_driver_reproduces_reference_step(name, nsteps):
     import ref_harness as rh
     from oracle.engine import OracleSvatEngine

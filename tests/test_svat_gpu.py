@@ -64,6 +64,47 @@ def test_cuda_equals_oracle_bit_for_bit(lateral, doy, dist, nsteps):
         lib().roger_oracle_set_pow(0)
 
 
+@pytest.mark.parametrize("lateral,doy,nsteps", [(False, 100, 80), (True, 300, 60)])
+def test_groundwater_boundary_cuda_equals_oracle_bit_for_bit(lateral, doy, nsteps):
+    """settings.enable_groundwater_boundary on 1024 heterogeneous cells: a water table that moves every day -- in a third of the
+    cells up into the subsoil and back --, capillary rise into the subsoil, recharge through the vadose-zone reservoir; every plane
+    every third step, state-only steps in between (the production mode)"""
+    from oracle.engine import OracleSvatEngine, lib
+    from roger_b200 import abi, synth
+    from roger_b200.svat import SvatModel
+
+    shape = (32, 32)
+    ndays = 30
+    forcing = synth.mixed_forcing(ndays, seed=52, start_doy=doy)
+    prim, th_rz, th_ss = synth.heterogeneous_parameters(shape, seed=53, lateral=lateral, masked_fraction=0.05)
+    rng = np.random.default_rng(54)
+    prim["n0"] = rng.uniform(0.05, 0.3, shape)
+    base = np.asarray(prim["z_soil"]) / 1000 + np.where(rng.random(shape) < 0.35, rng.uniform(0.02, 0.4, shape), rng.uniform(0.4, 12.0, shape))
+    z_gw = base[:, :, None] - rng.uniform(0.1, 0.6, shape)[:, :, None] * np.sin(np.arange(ndays + 1) / 3.0)[None, None, :]
+    z_gw[:, :, 0] = base
+    lib().roger_oracle_set_pow(1)
+    try:
+        models = [SvatModel(e, shape, forcing, prim, th_rz, th_ss, lateral=lateral, z_gw_daily=z_gw.reshape(-1, ndays + 1))
+                  for e in (_engine(), OracleSvatEngine)]
+        for m in models:
+            m.setup()
+        moved = 0.0
+        for step in range(nsteps):
+            full = step % 3 == 0 or step == nsteps - 1
+            a, b = models[0].step(full), models[1].step(True)
+            for k in ("time", "itt", "dt_secs", "itt_day", "event_id_counter", "time_event0", "dt", "sanity_ok"):
+                assert getattr(a, k) == getattr(b, k), (step, k)
+            kinds = dict(zip(abi.FIELD_NAMES, abi.FIELD_KINDS))
+            for n in abi.FIELD_NAMES:
+                if full or (kinds[n] != "F" and n not in ("k", "h")):
+                    assert util.same_bits(models[0].get(n), models[1].get(n)), (step, n)
+            if full:
+                moved += float(models[0].get("cpr_ss").sum() + models[0].get("q_re").sum())
+        assert moved > 0
+    finally:
+        lib().roger_oracle_set_pow(0)
+
+
 @pytest.mark.parametrize("case", ["svat_rain", "svat_mixed_dist", "oned_mixed"])
 def test_cuda_state_only_mode_matches(case):
     """write_fluxes=0 (the production mode) must give the same state as the diagnostics mode."""
