@@ -179,8 +179,6 @@ class OracleSasEngine:
         self.balance_prev = np.zeros(self.n)
         if settings.solver == 2 and settings.solute != 0:
             raise NotImplementedError("RK4 solver: isotope branch only")
-        if settings.solver == 1 and settings.solute != 0 and settings.age_statistics:
-            raise NotImplementedError("explicit Euler solver, anion branch: without age statistics")
         self._fn = lib().sas_oracle_day_stats
         self._fn.restype = None
 

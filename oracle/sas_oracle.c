@@ -1352,7 +1352,7 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
                 }
                 if (st->solute == 1) {
                     euler_substep_cell_anion(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out,
-                                             tt_out ? tt_out + (size_t)i * A : NULL, (size_t)C * A, work);
+                                             tt_out ? tt_out + (size_t)i * A : ((stats && last) ? ttk : NULL), tt_out ? (size_t)C * A : (size_t)A, work);
                     storage_kernels_anion(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
                     continue;
                 }
@@ -1367,6 +1367,44 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
                 storage_kernels_iso(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
             }
             if (st->solute == 1) {
+                if (stats) { /* age statistics (water only, transport.py:59-312) and the balance errors of the day's last Euler step:
+                              * numerics.py:424-445 (water), :642-672 (bromide / chloride), both carrying settings.h */
+                    const double h = 1.0 / ctx.substeps;
+                    const double *TT[RSP_COUNT];
+                    for (int p = 0; p < RSP_COUNT; p++) TT[p] = tt_out ? tt_out + ((size_t)p * (size_t)C + (size_t)i) * A : ttk + (size_t)p * A;
+                    const double p5[5] = {0.1, 0.25, 0.5, 0.75, 0.9}, p3[3] = {0.25, 0.5, 0.75};
+                    double s5[5], s3[3], avg, w[3];
+                    double *sa_s = tmp + (A + 2);
+                    for (int j = 0; j < A; j++) sa_s[j] = s_rz[j] + s_ss[j] * m;
+                    const int procs[3] = {RSP_evap_soil, RSP_transp, RSP_q_ss};
+                    const double flx[3] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_ss)};
+                    for (int k = 0; k < 3; k++) {
+                        for (int j = 0; j < A; j++) tmp[j] = flx[k] * TT[procs[k]][j];
+                        w[k] = np_sum(tmp, A);
+                    }
+                    flux_age_statistics(A, TT[RSP_transp], ages, work, s5, &avg);
+                    for (int k = 0; k < 5; k++) ST(RSS_tt10_transp + k) = s5[k];
+                    ST(RSS_ttavg_transp) = avg;
+                    flux_age_statistics(A, TT[RSP_q_ss], ages, work, s5, &avg);
+                    for (int k = 0; k < 5; k++) ST(RSS_tt10_q_ss + k) = s5[k];
+                    ST(RSS_ttavg_q_ss) = avg;
+                    storage_age_statistics(A, s_rz, m, ages, work, p3, 3, s3, &avg);
+                    for (int k = 0; k < 3; k++) ST(RSS_rt25_rz + k) = s3[k];
+                    ST(RSS_rtavg_rz) = avg;
+                    storage_age_statistics(A, s_ss, m, ages, work, p3, 3, s3, &avg);
+                    for (int k = 0; k < 3; k++) ST(RSS_rt25_ss + k) = s3[k];
+                    ST(RSS_rtavg_ss) = avg;
+                    storage_age_statistics(A, sa_s, m, ages, work, p5, 5, s5, &avg);
+                    for (int k = 0; k < 5; k++) ST(RSS_rt10_s + k) = s5[k];
+                    ST(RSS_rtavg_s) = avg;
+                    const double S = np_sum(sa_s, A);
+                    ST(RSS_dS_num_error) = fabs((S - sum_sa_s_m1) - (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - w[0] - w[1] - w[2]) * h);
+                    ST(RSS_dC_num_error) = fabs((S * O(RSO_C_s) - sum_sa_s_m1 * Cp) -
+                                                (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                                                 F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss))) * h);
+                    ST(RSS_sanity_ok) = NAN; /* the anion branch of numerics.sanity_check is not restated */
+                    balance_prev[i] = O(RSO_C_s);
+                }
                 anion_ageing(A, s_rz, ms_rz);
                 anion_ageing(A, s_ss, ms_ss);
                 continue;

@@ -210,9 +210,11 @@ k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     euler_day<STATS, RK4>(cx, forcing, mask[i], sas_params, out, stats, C_s_prev, bounds, atol, rtol);
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(ROGER_EULER_BLOCK, ROGER_EULER_MIN_BLOCKS)
 k_sas_day_euler_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
-                      const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap) {
+                      const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap,
+                      double* __restrict__ stats, double* __restrict__ C_s_prev) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
     __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
     for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
@@ -223,7 +225,7 @@ k_sas_day_euler_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, c
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
-    euler_day_anion(cx, forcing, mask[i], sas_params, ap, out);
+    euler_day_anion<STATS>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev);
 }
 
 // (cells, A) row-major staging block <-> age-major planes, 32 x 32 tiles through shared memory
@@ -445,8 +447,6 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
         return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic), 1 (Euler) or 2 (RK4)");
     if (settings->solver == 2 && settings->solute != 0)
         return fail(ROGER_ENOTSUP, "roger_sas_create: the RK4 solver runs the isotope branch only");
-    if (settings->solver == 1 && settings->solute != 0 && settings->age_statistics)
-        return fail(ROGER_ENOTSUP, "roger_sas_create: the anion branch of the explicit Euler solver runs without age statistics");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -680,8 +680,12 @@ static int step_common(roger_sas* h, const double* d_forcing) {
         if (h->st.solute == 1) {
             AnionParams ap{nullptr, nullptr, nullptr, nullptr};
             if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
-            k_sas_day_euler_anion<<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
-                                                                           h->d_out, ap);
+            if (h->st.age_statistics)
+                k_sas_day_euler_anion<true><<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask,
+                                                                                     h->d_params, h->d_out, ap, h->d_stats, h->d_C_s_prev);
+            else
+                k_sas_day_euler_anion<false><<<eb, ROGER_EULER_BLOCK, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask,
+                                                                                      h->d_params, h->d_out, ap, nullptr, nullptr);
         } else {
             auto launch = [&](auto kernel) {
                 if (h->st.age_statistics)

@@ -1927,6 +1927,16 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
                 const double mc = amtt(b, mb, alpha_q, tt_c, fx[3].fh), msq = amtt(b, mb, alpha_q, tt_s, fx[4].fh);
                 if (LAST) {
                     v[0] = mt; v[1] = mq; v[2] = mc; v[3] = msq;
+                    if (STATS) {  // water-age statistics of the day's last step (transport.py:59-152), numerics.py:437-439
+                        v[4] = evap * tt_e; v[5] = transp * tt_t; v[6] = q_ss * tt_s;
+                        v[STATS ? 7 : 0] = tt_t; v[STATS ? 8 : 0] = tt_s;
+                        v[STATS ? 9 : 0] = (double)(j + 1) * tt_t; v[STATS ? 10 : 0] = (double)(j + 1) * tt_s;
+                        cdf_t += tt_t;
+                        cdf_s += tt_s;
+                        if (j == 0) { cmax_t.init(cdf_t); cmax_s.init(cdf_s); } else { cmax_t.push(cdf_t); cmax_s.push(cdf_s); }
+#pragma unroll
+                        for (int k = 0; k < 5; k++) { trk[k].push(j, cdf_t); trk[(STATS ? 5 : 0) + k].push(j, cdf_s); }
+                    }
                     if (tt_base) {
                         const int64_t span = (int64_t)A * C, l = cx.lin(j);
                         tt_base[RSP_evap_soil * span + l] = tt_e;
@@ -2015,9 +2025,17 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
             }
         };
         if (LAST) {
-            constexpr int NS = ANION ? 4 : (STATS ? 15 : 10);
+            constexpr int NS = ANION ? (STATS ? 11 : 4) : (STATS ? 15 : 10);
             double sums[NS];
             EULER_SUMS<NS, NL>(cx.plan, EULER_SUMS_ARG load, bin, sums);
+            if (ANION && STATS && es) {
+                const double qn = __longlong_as_double(0x7ff8000000000000LL);
+                es->wsum[0] = sums[STATS ? 4 : 0]; es->wsum[1] = sums[STATS ? 5 : 0]; es->wsum[2] = sums[STATS ? 6 : 0];
+#pragma unroll
+                for (int k = 0; k < 5; k++) { es->pct[0][k] = trk[k].result(A, cmax_t.get()); es->pct[1][k] = trk[(STATS ? 5 : 0) + k].result(A, cmax_s.get()); }
+                es->avg[0] = (sums[STATS ? 7 : 0] > 0) ? sums[STATS ? 9 : 0] : qn;
+                es->avg[1] = (sums[STATS ? 8 : 0] > 0) ? sums[STATS ? 10 : 0] : qn;
+            }
             if (ANION) {  // :2378-2407; C_evap_soil and the M_* flux planes are not touched by the Euler solver
                 O(RSO_C_inf_mat_rz) = ((inf_mat * h > 0) ? C_in : 0) * m;
                 O(RSO_C_inf_pf_rz) = ((inf_pf * h > 0) ? C_in : 0) * m;
@@ -2069,7 +2087,7 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
 
 // anion storage kernels (root_zone.py:219-261, subsoil.py / soil.py anion kernels) and ageing (transport.py:622-679) as used
 // by anion_day<>, for the Euler solver
-__device__ __forceinline__ void anion_storage(const CellCtx& cx, double m, double* __restrict__ out) {
+__device__ __forceinline__ void anion_storage(const CellCtx& cx, double m, double* __restrict__ out, double* sum_sa_s = nullptr) {
     const int64_t C = cx.P.C, i = cx.i;
     double* __restrict__ s_rz = cx.pl.sa[0];
     double* __restrict__ s_ss = cx.pl.sa[1];
@@ -2102,6 +2120,7 @@ __device__ __forceinline__ void anion_storage(const CellCtx& cx, double m, doubl
     O(RSO_C_iso_rz) = M_rz; O(RSO_C_rz) = (sums[1] > 0) ? M_rz / sums[1] : 0;
     O(RSO_C_iso_ss) = M_ss; O(RSO_C_ss) = (sums[3] > 0) ? M_ss / sums[3] : 0;
     O(RSO_C_iso_s) = M_s;   O(RSO_C_s) = (sums[5] > 0) ? M_s / sums[5] : 0;
+    if (sum_sa_s) *sum_sa_s = sums[5];
 #undef O
 }
 __device__ __forceinline__ void anion_ageing(const CellCtx& cx) {
@@ -2122,12 +2141,64 @@ __device__ __forceinline__ void anion_ageing(const CellCtx& cx) {
     }
 }
 
+template <bool STATS>
 __device__ __forceinline__ void euler_day_anion(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
-                                                const AnionParams ap, double* __restrict__ out) {
+                                                const AnionParams ap, double* __restrict__ out, double* __restrict__ stats,
+                                                double* __restrict__ C_s_prev) {
     const double alpha_t = ap.alpha_transp ? ap.alpha_transp[cx.i] : 1.0, alpha_q = ap.alpha_q ? ap.alpha_q[cx.i] : 1.0;
-    for (int s = 0; s + 1 < cx.P.substeps; s++) euler_step<false, false, true>(cx, forcing, m, sas_params, out, nullptr, alpha_t, alpha_q);
-    euler_step<true, false, true>(cx, forcing, m, sas_params, out, nullptr, alpha_t, alpha_q);
-    anion_storage(cx, m, out);
+    const int n = cx.P.substeps;
+    const int64_t C = cx.P.C, i = cx.i;
+    for (int s = 0; s + 1 < n; s++) euler_step<false, false, true>(cx, forcing, m, sas_params, out, nullptr, alpha_t, alpha_q);
+    double sum_sa_s_m1 = 0, Cp = 0;
+    if (STATS) {  // [taum1] of the last Euler step: what its predecessor left (after_substep_anion)
+        if (n > 1) {  // the storage kernels after that step (idempotent on the state: the step applied their thresholds itself)
+            anion_storage(cx, m, out, &sum_sa_s_m1);
+            Cp = out[(int64_t)RSO_C_s * C + i];
+        } else {
+            Cp = C_s_prev[i];
+            double sm[1];
+            stream_sums<1, 2>(cx.plan,
+                [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = cx.pl.sa[0][o]; L[1] = cx.pl.sa[1][o]; },
+                [&](int, const double* L, double* v) { v[0] = L[0] + L[1] * m; }, sm);
+            sum_sa_s_m1 = sm[0];
+        }
+    }
+    EulerStats es;
+    euler_step<true, STATS, true>(cx, forcing, m, sas_params, out, &es, alpha_t, alpha_q);
+    double sum_sa_s = 0;
+    anion_storage(cx, m, out, &sum_sa_s);
+    if (STATS) {  // age statistics of the water (transport.py:59-312), balance errors numerics.py:424-445 and :642-672 with settings.h
+#define F(k) forcing[(int64_t)(k) * C + i]
+#define O(k) out[(int64_t)(k) * C + i]
+#define ST(k) stats[(int64_t)(k) * C + i]
+        for (int k = 0; k < 5; k++) { ST(RSS_tt10_transp + k) = es.pct[0][k]; ST(RSS_tt10_q_ss + k) = es.pct[1][k]; }
+        ST(RSS_ttavg_transp) = es.avg[0];
+        ST(RSS_ttavg_q_ss) = es.avg[1];
+        const double p5[5] = {0.1, 0.25, 0.5, 0.75, 0.9}, p3[3] = {0.25, 0.5, 0.75};
+        double pc[5], avg;
+        storage_age_statistics(cx, 0, m, 3, p3, pc, &avg);
+        for (int k = 0; k < 3; k++) ST(RSS_rt25_rz + k) = pc[k];
+        ST(RSS_rtavg_rz) = avg;
+        storage_age_statistics(cx, 1, m, 3, p3, pc, &avg);
+        for (int k = 0; k < 3; k++) ST(RSS_rt25_ss + k) = pc[k];
+        ST(RSS_rtavg_ss) = avg;
+        storage_age_statistics(cx, 2, m, 5, p5, pc, &avg);
+        for (int k = 0; k < 5; k++) ST(RSS_rt10_s + k) = pc[k];
+        ST(RSS_rtavg_s) = avg;
+        auto nan0 = [](double x) { return (x != x) ? 0.0 : x; };
+        const double h = 1.0 / (double)n;
+        const double C_s = O(RSO_C_s);
+        ST(RSS_dS_num_error) = fabs((sum_sa_s - sum_sa_s_m1) - (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - es.wsum[0] - es.wsum[1] - es.wsum[2]) * h);
+        ST(RSS_dC_num_error) = fabs((sum_sa_s * C_s - sum_sa_s_m1 * Cp) -
+                                    (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                                     F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - es.wsum[1] * nan0(O(RSO_C_transp)) -
+                                     es.wsum[2] * nan0(O(RSO_C_q_ss))) * h);
+        ST(RSS_sanity_ok) = __longlong_as_double(0x7ff8000000000000LL);  // the anion branch of numerics.sanity_check is not restated
+        C_s_prev[i] = C_s;
+#undef F
+#undef O
+#undef ST
+    }
     anion_ageing(cx);
 }
 

@@ -524,8 +524,7 @@ class CudaTransportDriver:
             raise NotImplementedError("settings.enable_groundwater_boundary runs with the deterministic solver")
         if self.nitrate and (self.euler or stats):
             raise NotImplementedError("nitrate runs with the deterministic solver and without age statistics")
-        if self.euler and self.anion and stats:
-            raise NotImplementedError("the anion branch of the explicit Euler solver runs without age statistics")
+
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
         self.C = self.nx * self.ny
         self.pull_state = bool(pull_state)

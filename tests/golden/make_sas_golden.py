@@ -74,6 +74,8 @@ CASES = {
                             sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),
     "sas_euler_bromide": dict(shape=(2, 3), ndays=20, ages=50, doy=100, solute="bromide", sas_solver="Euler",
                               sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
+    "sas_euler_bromide_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=100, solute="bromide", sas_solver="Euler", age_statistics=True,
+                                    sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
     # Runge-Kutta solver (settings.sas_solver = "RK4")
     "sas_rk4": dict(shape=(2, 2), ndays=12, ages=40, doy=100, sas_solver="RK4",
                     sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),

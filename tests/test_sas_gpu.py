@@ -402,14 +402,28 @@ def test_euler_anion_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, nday
     u.replay_pair(models[0], models[1], ndays, exact=True)
 
 
-def test_euler_anion_with_statistics_is_rejected():
+def test_euler_anion_with_age_statistics(oracle_roger_pow):
+    """the anion branch of the Euler solver with settings.enable_age_statistics: water-age percentiles of the day's last step and the
+    balance errors of numerics.py:424-445 / :642-672 (carrying settings.h): the reference fixture bit for bit, and seeded inputs
+    against the oracle"""
     from roger_b200 import sas
-    from roger_b200.engine import RogerCudaError
 
-    daily, spec = _random_case(4, 8, 2, seed=1)
-    daily["C_IN"] = daily["C_ISO_IN"] * 0
-    with pytest.raises(RogerCudaError):
-        sas.SasModel(_cuda(), 4, 8, daily, spec, solver=sas.EULER, solute=sas.ANION, age_statistics=True)
+    fx = u.load_case("sas_euler_bromide_stats")
+    m = u.model_from_fixture(fx, _cuda())
+    assert m.settings.solver == 1 and m.settings.solute == 1 and m.settings.age_statistics == 1
+    u.replay_against_fixture(fx, m, exact=True)
+    for C_, A, ndays, substeps in [(200, 96, 5, 6), (3, 130, 3, 1)]:
+        daily, spec = _random_case(C_, A, ndays, seed=800 + A)
+        rng = np.random.default_rng(A)
+        daily["C_IN"] = np.where(rng.random(daily["PREC"].shape) < 0.3, rng.uniform(5, 80, daily["PREC"].shape), 0.0) * (daily["PREC"] > 0)
+        ap = dict(alpha_transp=rng.uniform(0.1, 1.0, C_), alpha_q=rng.uniform(0.3, 1.0, C_), lu_id=np.full(C_, 8.0), S_sat_rz=np.full(C_, 1e4))
+        mask = np.ones(C_)
+        mask[3::11] = 0.0
+        models = [sas.SasModel(e, C_, A, daily, spec, store_tt=(A != 96), mask=mask, substeps=substeps, solver=sas.EULER, solute=sas.ANION,
+                               anion_parameters=ap, age_statistics=True) for e in (_cuda(), oracle_roger_pow)]
+        for mm in models:
+            mm.setup()
+        u.replay_pair(models[0], models[1], ndays, exact=True)
 
 
 # ---- Runge-Kutta solver (settings.sas_solver = "RK4", transport.py:1138-2047) ---------------------------------------
