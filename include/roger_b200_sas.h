@@ -92,7 +92,7 @@ typedef struct roger_sas_settings {
                                   Nmin_ss: state 4 and 5 of roger_sas_upload_state); deterministic solver, no age statistics */
     int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day
                                (svat_transport_model_euler, transport.py:2063-2413; statistics / balance errors are those of the day's
-                               last Euler step, as the reference's output shows them; the anion branch runs without statistics);
+                               last Euler step, as the reference's output shows them -- isotope and anion branch alike);
                                2: RK4 (svat_transport_model_rk4, transport.py:1138-2047), isotope branch only: four stages of the Euler
                                building blocks per step on stage copies of the StorAge (nine more scratch arrays of cells x ages) */
 } roger_sas_settings;
