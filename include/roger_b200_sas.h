@@ -89,7 +89,7 @@ typedef struct roger_sas_settings {
                                1: conservative anion (bromide / chloride: msa holds bin solute MASS, the *_transport_anion_kernel
                                   family of the reference; the RSO_C_iso_* result planes then hold the solute masses M_*);
                                2: nitrate = the anion transport plus the soil nitrogen cycle (two more age-ranked arrays Nmin_rz,
-                                  Nmin_ss: state 4 and 5 of roger_sas_upload_state); deterministic solver, no age statistics */
+                                  Nmin_ss: state 4 and 5 of roger_sas_upload_state); deterministic solver */
     int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day
                                (svat_transport_model_euler, transport.py:2063-2413; statistics / balance errors are those of the day's
                                last Euler step, as the reference's output shows them -- isotope and anion branch alike);

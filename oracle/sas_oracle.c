@@ -873,6 +873,12 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
             ST(RSS_rtavg_s) = avg;
             double *bp_C = balance_prev + i;
             ST(RSS_dS_num_error) = fabs((S - sum_sa_s_m1) - (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - w[0] - w[1] - w[2]) * 1.0);
+            if (g_nit.params && g_nit.nmin_rz) /* nitrate (numerics.py:673-705): the denitrified and the nitrified mass of the day as well */
+                ST(RSS_dC_num_error) = fabs((S * O(RSO_C_s) - sum_sa_s_m1 * *bp_C) -
+                                            (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                                             F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss)) -
+                                             g_nit.out[(size_t)RNO_denit_s * (size_t)C + (size_t)i] + g_nit.out[(size_t)RNO_nit_s * (size_t)C + (size_t)i]) * 1.0);
+            else
             ST(RSS_dC_num_error) = fabs((S * O(RSO_C_s) - sum_sa_s_m1 * *bp_C) -
                                         (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
                                          F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss))) * 1.0);

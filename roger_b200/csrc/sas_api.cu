@@ -168,10 +168,11 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
 }
 
 // One day of the nitrate transport: the anion day with the soil nitrogen cycle between the transport and the storage kernels
+template <bool STATS>
 __global__ void __launch_bounds__(ROGER_SAS_BLOCK, ROGER_SAS_MIN_BLOCKS)
 k_sas_day_nitrate(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double* __restrict__ forcing,
                   const double* __restrict__ mask, const double* __restrict__ sas_params, double* __restrict__ out, AnionParams ap,
-                  NitrateParams np_, CropParams crop) {
+                  NitrateParams np_, CropParams crop, double* __restrict__ stats, double* __restrict__ C_s_prev) {
     __shared__ roger_pow_log_entry s_log[ROGER_POW_N];
     __shared__ roger_pow_exp_entry s_exp[ROGER_POW_N];
     for (int k = threadIdx.x; k < ROGER_POW_N; k += blockDim.x) {
@@ -182,7 +183,7 @@ k_sas_day_nitrate(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
-    anion_day<false, true>(cx, forcing, mask[i], sas_params, ap, out, nullptr, nullptr, &np_, crop);
+    anion_day<STATS, true>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev, &np_, crop);
 }
 
 // One day of the explicit Euler solver (`substeps` Euler steps, ageing with the last one), one thread per cell.
@@ -441,8 +442,8 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_sas_create: bad argument");
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
     if (settings->solute < 0 || settings->solute > 2) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope), 1 (anion) or 2 (nitrate)");
-    if (settings->solute == 2 && (settings->solver != 0 || settings->age_statistics))
-        return fail(ROGER_ENOTSUP, "roger_sas_create: nitrate runs with the deterministic solver and without age statistics");
+    if (settings->solute == 2 && settings->solver != 0)
+        return fail(ROGER_ENOTSUP, "roger_sas_create: nitrate runs with the deterministic solver");
     if (settings->solver < 0 || settings->solver > 2)
         return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic), 1 (Euler) or 2 (RK4)");
     if (settings->solver == 2 && settings->solute != 0)
@@ -709,8 +710,12 @@ static int step_common(roger_sas* h, const double* d_forcing) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
         NitrateParams np_{h->d_nit_params, h->d_nit_forcing, h->d_nit_out, h->nit_dx, h->nit_dy, h->nit_zmax, h->nit_dt};
-        k_sas_day_nitrate<<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out, ap, np_,
-                                                             h->crop());
+        if (h->st.age_statistics)
+            k_sas_day_nitrate<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+                                                                       ap, np_, h->crop(), h->d_stats, h->d_C_s_prev);
+        else
+            k_sas_day_nitrate<false><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params, h->d_out,
+                                                                        ap, np_, h->crop(), nullptr, nullptr);
         h->have_nit_forcing = false;
         h->have_crop_re = false;
     } else if (h->st.solute == 1) {

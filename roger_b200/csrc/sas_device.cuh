@@ -1302,9 +1302,15 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
             const double Cp = C_s_prev[i];
             ST(RSS_dS_num_error) = fabs((sums[5] - sum_sa_s_m1) -
                                         (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) + F(RSF_inf_pf_ss) - fs_evap.wsum - fs_transp.wsum - fs_qss.wsum) * 1.0);
-            ST(RSS_dC_num_error) = fabs((sums[5] * C_s - sum_sa_s_m1 * Cp) -
-                                        (F(RSF_inf_mat_rz) * nan0(C_inf1) + F(RSF_inf_pf_rz) * nan0(C_inf2) + F(RSF_inf_pf_ss) * nan0(C_inf3) -
-                                         fs_transp.wsum * nan0(C_transp_v) - fs_qss.wsum * nan0(C_q_ss_v)) * 1.0);
+            if (NITRATE)  // numerics.py:673-705: the denitrified and the nitrified mass of the day as well
+                ST(RSS_dC_num_error) = fabs((sums[5] * C_s - sum_sa_s_m1 * Cp) -
+                                            (F(RSF_inf_mat_rz) * nan0(C_inf1) + F(RSF_inf_pf_rz) * nan0(C_inf2) + F(RSF_inf_pf_ss) * nan0(C_inf3) -
+                                             fs_transp.wsum * nan0(C_transp_v) - fs_qss.wsum * nan0(C_q_ss_v) -
+                                             nitrate->out[(int64_t)RNO_denit_s * C + i] + nitrate->out[(int64_t)RNO_nit_s * C + i]) * 1.0);
+            else
+                ST(RSS_dC_num_error) = fabs((sums[5] * C_s - sum_sa_s_m1 * Cp) -
+                                            (F(RSF_inf_mat_rz) * nan0(C_inf1) + F(RSF_inf_pf_rz) * nan0(C_inf2) + F(RSF_inf_pf_ss) * nan0(C_inf3) -
+                                             fs_transp.wsum * nan0(C_transp_v) - fs_qss.wsum * nan0(C_q_ss_v)) * 1.0);
             ST(RSS_sanity_ok) = __longlong_as_double(0x7ff8000000000000LL);  // the anion branch of sanity_check is not evaluated
             C_s_prev[i] = C_s;
 #undef ST

@@ -56,6 +56,8 @@ CASES = {
     # cell, a fertiliser pulse, wet cells above the denitrification threshold
     "sas_nitrate": dict(shape=(2, 3), ndays=30, ages=50, doy=100, solute="nitrate",
                         sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0))),
+    "sas_nitrate_stats": dict(shape=(2, 2), ndays=14, ages=40, doy=100, solute="nitrate", age_statistics=True,
+                              sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0))),
     # the crop variant of the offline model (svat_crop_transport_model_deterministic): redistribution between subsoil and root zone
     # after root growth (re_rg) / root loss (re_rl) opens the day; a harvest pulse larger than the root zone holds is clamped
     "sas_nitrate_crop": dict(shape=(2, 3), ndays=24, ages=50, doy=100, solute="nitrate", crop=True,

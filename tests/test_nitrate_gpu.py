@@ -186,3 +186,18 @@ def test_cuda_reproduces_reference_fixture_bit_for_bit(case):
         m.step()
         for k, v in crop_snapshot(m, fx).items():
             assert u.same(v, fx["rec_" + k][day]), (day, k)
+
+
+def test_nitrate_age_statistics_cuda_equals_reference_fixture_and_oracle(oracle_roger_pow):
+    """settings.enable_age_statistics with nitrate (k_sas_day_nitrate<STATS = true>): the reference fixture bit for bit, the oracle too"""
+    from tests.test_nitrate_oracle_golden import nitrate_stats_snapshot
+
+    fx = u.load_case("sas_nitrate_stats")
+    a, b = model_from_fixture(fx, _cuda()), model_from_fixture(fx, oracle_roger_pow)
+    for day in range(int(fx["ndays"])):
+        a.step()
+        b.step()
+        sa, sb = nitrate_stats_snapshot(a), nitrate_stats_snapshot(b)
+        for k in sa:
+            assert u.same(sa[k], sb[k]), (day, k, "oracle")
+            assert u.same(sa[k], fx["rec_" + k][day]), (day, k, "reference fixture")

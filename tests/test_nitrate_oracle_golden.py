@@ -9,16 +9,20 @@ from tests import util_sas as u
 
 
 def model_from_fixture(fx, engine_cls, engine_kwargs=None):
+    """fixtures sas_nitrate and sas_nitrate_stats (the latter with settings.enable_age_statistics)"""
     C, A = int(fx["nx"]) * int(fx["ny"]), int(fx["ages"])
+    stats = "rec_dC_num_error" in fx
     daily = {k[3:]: fx[k] for k in fx if k.startswith("in_")}
     spec = {p: fx["sas_" + p] for p in sas.PROCESSES}
     params = {k: fx["par_" + k] for k in nitrate.PARAMS + ["phi_soil_temp", "damp_soil_temp"]}
     anion = dict(alpha_transp=fx["par_alpha_transp"], alpha_q=fx["par_alpha_q"], lu_id=fx["par_lu_id"], S_sat_rz=fx["par_S_sat_rz"])
     m = nitrate.NitrateModel(engine_cls, C, A, daily, spec, params, anion, nitt=int(fx["ndays"]) + 1, pi=3.14159265358979323846264338327950588, substeps=int(fx["substeps"]),
-                             store_tt=True, engine_kwargs=engine_kwargs)
+                             store_tt=True, engine_kwargs=engine_kwargs, age_statistics=stats)
     m.setup()
     for k, name in enumerate(nitrate.STATE):  # start from the reference's own post-setup state
         m.engine.upload_state_index(k, fx["init_" + name])
+    if stats:
+        m.engine.set_balance_reference(fx["init_C_s"])
     # The soil temperature is a host-side NumPy expression with a sine and an exponential (nitrate.py:6-66): its last bit follows
     # NumPy's SIMD dispatch (the fixture was generated with it switched off, see make_sas_golden.py).  The engine is pinned with
     # the recorded temperatures; the host expression is checked against them to rounding.
@@ -44,6 +48,29 @@ def test_oracle_reproduces_reference_nitrate_bit_for_bit():
     # the fixture exercises every process: fixation on the crop cell, nitrification, denitrification, gaseous loss, uptake
     for k in ("nit_s", "denit_s", "ngas_s", "nfix_s", "nh4_up", "min_s"):
         assert np.nanmax(fx["rec_" + k]) > 0, k
+
+
+def nitrate_stats_snapshot(m):
+    snap = {name: m.state(name) for name in nitrate.STATE}
+    snap.update(m.nitrate_outputs())
+    snap.update({k: v for k, v in m.statistics().items() if k != "sanity_ok"})
+    o = m.outputs()
+    for k in ("C_rz", "C_ss", "C_s", "C_transp", "C_q_ss"):
+        snap[k] = o[k]
+    return snap
+
+
+def test_oracle_reproduces_reference_nitrate_age_statistics_bit_for_bit():
+    """settings.enable_age_statistics with nitrate: water-age percentiles and mean ages of the fluxes and storages, the water balance
+    error and the nitrate balance error, which carries the day's denitrified and nitrified mass (numerics.py:673-705)"""
+    lib().sas_oracle_set_pow(0)
+    fx = u.load_case("sas_nitrate_stats")
+    m = model_from_fixture(fx, OracleSasEngine)
+    for day in range(int(fx["ndays"])):
+        m.step()
+        for k, v in nitrate_stats_snapshot(m).items():
+            assert u.same(v, fx["rec_" + k][day]), f"day {day}: {k}"
+    assert np.nanmax(fx["rec_dC_num_error"]) > 0 and np.nanmax(fx["rec_denit_s"]) > 0 and np.nanmax(fx["rec_nit_s"]) > 0
 
 
 # ---- crop variant of the offline model: redistribution after root growth / root loss opens the day ----------------------------
