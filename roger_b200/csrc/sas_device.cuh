@@ -433,6 +433,9 @@ struct CellCtx {
 #ifndef ROGER_SAS_UNROLL
 #define ROGER_SAS_UNROLL 2
 #endif
+#ifndef ROGER_SAS_PF
+#define ROGER_SAS_PF 0
+#endif
 
 // One sub-step of the deterministic solver for `n` consecutive bins starting at j0 (transport.py:388-470).  The n values
 // of san / TTn were loaded by the caller (xb, tb); the cumulative SAS function of the n bins is evaluated first --
@@ -571,6 +574,11 @@ __device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, 
         for (int u = 0; u < U; u++) {
             xn_[u] = ps[(U + u) * C];
             tn_[u] = FIRST ? 0.0 : pt[(U + u) * C];
+#if ROGER_SAS_PF  // experiment (measured 2.5 % SLOWER, profiles/r2_ncu_summary.md): L2 prefetch hint ROGER_SAS_PF bins beyond the register look-ahead
+            static_assert(ROGER_SAS_PF + 2 * ROGER_SAS_UNROLL <= 8 + ROGER_SAS_UNROLL, "prefetch distance vs. scratch padding");
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (size_t)(U + u + ROGER_SAS_PF) * C));
+            if (!FIRST) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + (size_t)(U + u + ROGER_SAS_PF) * C));
+#endif
         }
         pow_pass_bins<U, FIRST>(k, c, tabs, xb, tb, ps, pt, C);
         ps += U * C;
