@@ -58,6 +58,7 @@ k_sas_day(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const double*
     const int64_t C = P.C;
     if (i >= C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    cx.assume_spaces();
     const double m = mask[i];
 #define F(k) forcing[(int64_t)(k) * C + i]
 #define O(k) out[(int64_t)(k) * C + i]
@@ -164,6 +165,7 @@ k_sas_day_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    cx.assume_spaces();
     anion_day<STATS>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev, nullptr, crop);
 }
 
@@ -183,6 +185,7 @@ k_sas_day_nitrate(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    cx.assume_spaces();
     anion_day<STATS, true>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev, &np_, crop);
 }
 
@@ -208,6 +211,7 @@ k_sas_day_euler(SasParams P, Planes pl, const PwPlan* __restrict__ plan, const d
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    cx.assume_spaces();
     euler_day<STATS, RK4>(cx, forcing, mask[i], sas_params, out, stats, C_s_prev, bounds, atol, rtol);
 }
 
@@ -226,6 +230,7 @@ k_sas_day_euler_anion(SasParams P, Planes pl, const PwPlan* __restrict__ plan, c
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.C) return;
     CellCtx cx{P, pl, plan, roger_pow_tables{s_log, s_exp}, i};
+    cx.assume_spaces();
     euler_day_anion<STATS>(cx, forcing, mask[i], sas_params, ap, out, stats, C_s_prev);
 }
 

@@ -19,9 +19,21 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "roger_pow.h"
 #include "roger_gamma.h"
 #include "../../include/roger_b200_sas.h"
+
+// Pointers that reach a __noinline__ function through CellCtx (a struct passed by reference) have lost their address space: the
+// compiler then emits generic LD / ST with a descriptor it re-materialises through R2UR for every access (6 % of the day kernel's
+// instructions in the ncu source view, and generic-load latency on the shared-memory pow tables).  These hints give it back.
+#if defined(__CUDA_ARCH__) && !defined(ROGER_NO_HINTS)
+#define ROGER_IS_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#define ROGER_IS_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define ROGER_IS_GLOBAL(p) ((void)0)
+#define ROGER_IS_SHARED(p) ((void)0)
+#endif
 
 #ifndef ROGER_SAS_LOADGROUP
 #define ROGER_SAS_LOADGROUP 2
@@ -125,8 +137,10 @@ struct Family {
     bool fast;         // every inactive family provably contributes +0.0
     // id 52 (the exponential family read backwards along the age axis, sas.py:183): the masked cumulative StorAge of the layer,
     // written by the caller before the pass -- element k * rev_stride holds SA[k + 1]
+#ifndef ROGER_NO_FAMILY_FIELDS
     const double* rev;
     int64_t rev_stride;
+#endif
 };
 
 __device__ __forceinline__ double s_rel(double S, const double* sp, double m) {
@@ -140,8 +154,10 @@ __device__ __forceinline__ void family_begin(Family& f, const double* sp_global,
 #pragma unroll
     for (int k = 0; k < 8; k++) f.sp[k] = sp_global[k * stride];
     f.m = m;
+#ifndef ROGER_NO_FAMILY_FIELDS
     f.rev = nullptr;
     f.rev_stride = 0;
+#endif
 }
 
 // per sub-step preparation: everything that depends on max(SA) only
@@ -210,6 +226,7 @@ __device__ __forceinline__ double omega(const Family& f, const SasParams& P, con
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
     }
+#ifndef ROGER_NO_GAMMA52  // (diagnostic builds only)
     if (f.is_gamma) {  // sas.py:137-160; S carries the family mask there, so every other id selects the constant 0 (skipped: + 0.0)
         const double S = f.S;
         double v = 0.;
@@ -218,16 +235,19 @@ __device__ __forceinline__ double omega(const Family& f, const SasParams& P, con
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
     }
+#endif
     if (f.is_exp51 || f.is_exp52 || !f.fast) {  // sas.py:163-191
         const double S = f.S;
         double o = 0.0;
         if (f.is_exp51) o = (SA > 0) ? ((SA < S) ? 1 - roger_exp(f.sp[1] * (-1) * (SA / S), tabs) : 1.) : 0.;
         o = o * m;
+#ifndef ROGER_NO_GAMMA52
         if (f.is_exp52) {  // [..., ::-1]: age index jj takes the value at nages - 1 - jj
             const int k = P.A - jj;
             const double SAr = (k == 0) ? 0.0 * m : f.rev[(int64_t)(k - 1) * f.rev_stride];
             o = (SAr > 0) ? ((SAr < S) ? 1 - roger_exp(f.sp[1] * (-1) * (SAr / S), tabs) : 1.) : 0.;
         }
+#endif
         o = o * m;
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
@@ -428,6 +448,12 @@ struct CellCtx {
         return (int64_t)p * P.C + i;
     }
     __device__ __forceinline__ int64_t lin(int j) const { return (int64_t)j * P.C + i; }
+    // address spaces of the pointers that are never null (see ROGER_IS_GLOBAL above); call at the top of a __noinline__ function
+    __device__ __forceinline__ void assume_spaces() const {
+        ROGER_IS_GLOBAL(pl.sa[0]); ROGER_IS_GLOBAL(pl.sa[1]); ROGER_IS_GLOBAL(pl.msa[0]); ROGER_IS_GLOBAL(pl.msa[1]);
+        ROGER_IS_GLOBAL(pl.san); ROGER_IS_GLOBAL(pl.TTn); ROGER_IS_GLOBAL(plan);
+        ROGER_IS_SHARED(tabs.log_tab); ROGER_IS_SHARED(tabs.exp_tab);
+    }
 };
 
 #ifndef ROGER_SAS_UNROLL
@@ -539,6 +565,7 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
 template <bool FIRST>
 __device__ __noinline__ void pow_pass_tail(const PowPassConst& k, PowPassCarry& c, const roger_pow_tables tabs, double* __restrict__ san_o,
                                            double* __restrict__ TTn_o, int64_t C, int n) {
+    ROGER_IS_GLOBAL(san_o); ROGER_IS_GLOBAL(TTn_o); ROGER_IS_SHARED(tabs.log_tab); ROGER_IS_SHARED(tabs.exp_tab);
     for (int u = 0; u < n; u++) {
         const double xb = san_o[u * C];
         const double tb = FIRST ? 0.0 : TTn_o[u * C];
@@ -555,8 +582,10 @@ __device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, 
     PowPassConst k{S, 1.0 / S, y, flux, h, fh, 1.0 / fh};
     PowPassCarry c{0, 0, 0, 0.0, 0.0, false};  // om_prev = omega(SA[0] = 0) = 0, running max starts at SA[0] = 0
     const roger_pow_tables tabs = cx.tabs;
+    ROGER_IS_SHARED(tabs.log_tab); ROGER_IS_SHARED(tabs.exp_tab);
     double* __restrict__ ps = san + cx.i;
     double* __restrict__ pt = TTn + cx.i;
+    ROGER_IS_GLOBAL(ps); ROGER_IS_GLOBAL(pt);
     const int nfull = A / U;
     // register double buffer: the loads of block b + 1 are in flight while block b is computed.  The scratch arrays carry
     // U planes of padding, so the look-ahead of the last block needs no guard.
@@ -719,12 +748,15 @@ __device__ __forceinline__ double substep_pass_pow_split(const CellCtx& cx, doub
 // the layer `src` in the scratch array TTn (index j holds TTn[j + 1]).  Returns false when flux * h <= 0: every sub-step
 // then leaves StorAge and TTn untouched and TTn counts as zero.
 __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double flux, const double* sp_global, int64_t sp_stride, double m) {
+    cx.assume_spaces();
     constexpr int U = ROGER_SAS_UNROLL;
     const SasParams& P = cx.P;
     const int A = P.A;
     double* __restrict__ sa = cx.pl.sa[src];
     double* __restrict__ san = cx.pl.san;
     double* __restrict__ TTn = cx.pl.TTn;
+    ROGER_IS_GLOBAL(sa); ROGER_IS_GLOBAL(san); ROGER_IS_GLOBAL(TTn); ROGER_IS_GLOBAL(sp_global); ROGER_IS_GLOBAL(cx.plan);
+    ROGER_IS_SHARED(cx.tabs.log_tab); ROGER_IS_SHARED(cx.tabs.exp_tab);
     const double h = 1.0 / P.substeps;
     if (!(flux * h > 0)) return false;
     // cumulative StorAge of the layer (transport.py:343-359) -> S = max(SA); the layer's StorAge is copied into the
@@ -763,11 +795,13 @@ __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double f
     const double fh = flux * h;
     for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
         double* rev_next = nullptr;
+#ifndef ROGER_NO_GAMMA52
         if (is52) {
             fam.rev = rv[s & 1] + cx.i;
             fam.rev_stride = P.C;
             rev_next = rv[(s + 1) & 1];
         }
+#endif
         family_prepare(fam, mx.get());
         const bool first = (s == 0);
         if (fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh)) {
@@ -814,19 +848,22 @@ __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double f
 template <bool STATS>
 __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
                                         double m, double* C_flux, double* C_iso_flux, int process, FluxStats* fs) {
+    cx.assume_spaces();
     const SasParams& P = cx.P;
     const int A = P.A;
     double* __restrict__ sa = cx.pl.sa[src];
     double* __restrict__ msa = cx.pl.msa[src];
     double* __restrict__ TTn = cx.pl.TTn;
+    ROGER_IS_GLOBAL(sa); ROGER_IS_GLOBAL(msa); ROGER_IS_GLOBAL(TTn); ROGER_IS_GLOBAL(cx.plan);
     const int64_t C = P.C;
     const bool active = solve_substeps(cx, src, flux, sp_global, sp_stride, m);
 
     // aggregate (transport.py:472-496), flux concentration (:512-535), isotope mixing into the receiving layer,
     // StorAge update (:599-619)
-    double* __restrict__ sa_d = (dst >= 0) ? cx.pl.sa[dst] : nullptr;
-    double* __restrict__ msa_d = (dst >= 0) ? cx.pl.msa[dst] : nullptr;
+    double* __restrict__ sa_d = (dst >= 0) ? cx.pl.sa[dst] : sa;  // (never dereferenced when dst < 0)
+    double* __restrict__ msa_d = (dst >= 0) ? cx.pl.msa[dst] : msa;
     double* __restrict__ tt_out = (P.store_tt && cx.pl.tt) ? cx.pl.tt + (size_t)process * (size_t)A * (size_t)C : nullptr;
+    ROGER_IS_GLOBAL(sa_d); ROGER_IS_GLOBAL(msa_d);
     const double nsub = (double)P.substeps;
     double prev = 0. / nsub;
     constexpr int NS = STATS ? 4 : 2;
@@ -908,6 +945,7 @@ __device__ __noinline__ void withdrawal(const CellCtx& cx, int src, int dst, dou
 template <bool STATS>
 __device__ __noinline__ double anion_withdrawal(const CellCtx& cx, int src, int dst, double flux, const double* sp_global, int64_t sp_stride,
                                                 double m, double alpha, bool with_solute, int process, FluxStats* fs) {
+    cx.assume_spaces();
     const SasParams& P = cx.P;
     const int A = P.A;
     double* __restrict__ sa = cx.pl.sa[src];
@@ -1033,6 +1071,7 @@ __device__ __forceinline__ double distribute(double w, double wsum, double pot, 
 // denitrification of one layer (nitrate.py:68-173): the oldest solute is removed first; mr is left in `scratch` (unrotated)
 __device__ __noinline__ void denit_layer(const CellCtx& cx, int layer, double msum, double Ssum, double km, double Dmax, double S_sat, double T,
                                          double m, const NitrateParams& np_, double* __restrict__ scratch) {
+    cx.assume_spaces();
     const int A = cx.P.A;
     double* __restrict__ msa = cx.pl.msa[layer];
     const double S = Ssum * m;
@@ -1057,6 +1096,7 @@ __device__ __noinline__ void denit_layer(const CellCtx& cx, int layer, double ms
 }
 
 __device__ __noinline__ void nitrogen_cycle(const CellCtx& cx, const NitrateParams& np_, double transp, double m) {
+    cx.assume_spaces();
     const SasParams& P = cx.P;
     const int64_t C = P.C, i = cx.i;
     double* __restrict__ s_rz = cx.pl.sa[0];
@@ -1375,6 +1415,7 @@ __device__ __forceinline__ void inflow(const CellCtx& cx, int layer, double inf,
 // (which 0: root zone, 1: subsoil, 2: soil = root zone + subsoil * m), percentile ages and the mean residence time
 __device__ __noinline__ void storage_age_statistics(const CellCtx& cx, int which, double m, int n_pct, const double* pcts, double* pct_out,
                                                     double* avg_out) {
+    cx.assume_spaces();
     const SasParams& P = cx.P;
     const int A = P.A;
     const double* __restrict__ s_rz = cx.pl.sa[0];
@@ -1581,7 +1622,7 @@ struct EulerStats {  // diagnostics of the day's last Euler step (STATS kernels)
 // ANION: the conservative-solute branch (bromide / chloride; transport.py:2144-2156, :2320-2343, :2378-2407): msa holds solute
 // mass, calc_mtt (:582-596) with the partition coefficients alpha_transp / alpha_q, no mixing statements, the anion storage
 // kernels' `msa = 0 where sa <= 0` fused into the store.
-template <bool LAST, bool STATS, bool ANION, bool RK4 = false>
+template <bool LAST, bool STATS, bool ANION>
 __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
                                         double* __restrict__ out, EulerStats* es, double alpha_t, double alpha_q) {
     const SasParams& P = cx.P;
@@ -1591,6 +1632,364 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
     double* __restrict__ s_ss = cx.pl.sa[1];
     double* __restrict__ m_rz = cx.pl.msa[0];
     double* __restrict__ m_ss = cx.pl.msa[1];
+    cx.assume_spaces();
+    auto nan0 = [](double x) { return (x != x) ? 0.0 : x; };
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#define F(k) forcing[(int64_t)(k) * C + i]
+#define O(k) out[(int64_t)(k) * C + i]
+#define SP(p) (sas_params + (int64_t)(p) * 8 * C + i)
+    const double h = 1.0 / (double)P.substeps;
+    const double inf_mat = F(RSF_inf_mat_rz), inf_pf = F(RSF_inf_pf_rz), inf_ss = F(RSF_inf_pf_ss), C_in = F(RSF_C_in);
+    {   // upper boundary condition :2071-2143: infiltration enters age bin 0 (bins j > 0: see clean_* below)
+        const int64_t o = cx.ring(0);
+        const double tt_im = ((inf_mat > 0) ? 1 : 0) * m, tt_ip = ((inf_pf > 0) ? 1 : 0) * m, tt_is = ((inf_ss > 0) ? 1 : 0) * m;
+        const double mtt_im = ((inf_mat > 0) ? C_in : 0) * m, mtt_ip = ((inf_pf > 0) ? C_in : 0) * m, mtt_is = ((inf_ss > 0) ? C_in : 0) * m;
+        const double dsa_rz = (inf_mat * tt_im + inf_pf * tt_ip) * h;
+        const double dsa_ss = (inf_ss * tt_is) * h;
+        const double dmsa_rz1 = nan0(mtt_im) * ((dsa_rz > 0) ? ((inf_mat * tt_im * h) / dsa_rz) : 0) +
+                                nan0(mtt_ip) * ((dsa_rz > 0) ? ((inf_pf * tt_ip * h) / dsa_rz) : 0);
+        const double dmsa_ss1 = nan0(mtt_is) * ((dsa_ss > 0) ? ((inf_ss * tt_is * h) / dsa_ss) : 0);
+        double a = s_rz[o], b = s_ss[o];
+        if (ANION) {  // solute enters as mtt_inf * h with mtt_inf[0] = C_in * mask in all three infiltration arrays (:2089-2101, :2150-2156)
+            const double mi = nan0(C_in * m);
+            s_rz[o] = a + dsa_rz;
+            s_ss[o] = b + dsa_ss;
+            m_rz[o] = m_rz[o] + (mi * h + mi * h);
+            m_ss[o] = m_ss[o] + mi * h;
+        } else {
+            double ma = euler_mix(m_rz[o], a, dsa_rz, dmsa_rz1, true);
+            double mb = euler_mix(m_ss[o], b, dsa_ss, dmsa_ss1, false);
+            a += dsa_rz;
+            b += dsa_ss;
+            s_rz[o] = a;
+            s_ss[o] = b;
+            m_rz[o] = (a <= 0) ? 0 : ma;
+            m_ss[o] = (b <= 0) ? 0 : mb;
+        }
+    }
+    // what the boundary-condition statements do to a bin that receives nothing (dsa1 = 0, dmsa1 = 0):
+    //   msa*(sa/(0 + sa)) + 0*(0/sa) under the statements' conditions, then msa = 0 where sa <= 0
+    // (the rare sides of these shortcuts sit behind `asm volatile("")`: without it the compiler if-converts the selects and
+    // executes the divisions anyway -- 5 of the 8 divisions per bin and step in the first capture)
+    auto self_ratio = [](double x) {  // x / x: exactly 1 for a finite non-zero x
+        double one = 1.0;
+        if (!(x < 1.7976931348623157e308)) { asm volatile(""); one = x / x; }
+        return one;
+    };
+    auto clean_rz = [&](double ms, double s) { return ((s > 0) && (ms > 0)) ? ms * self_ratio(s) + 0.0 : 0.0; };
+    auto clean_ss = [&](double ms, double s) { return (s > 0) ? ms * self_ratio(s) + 0.0 : 0.0; };
+    // P1: S of both layers (calc_SA :343-359 times maskCatch, np.max over nages points)
+    NpMax mx_rz, mx_ss;
+    mx_rz.init(0.0 * m);
+    mx_ss.init(0.0 * m);
+    {
+        double acc_a = 0, acc_b = 0;
+        Cursor c(P, i);
+        // SAS family 52 (allocated by roger_sas_set_parameters when some cell uses it) reads the masked cumulative StorAge backwards:
+        // a second copy of the walk leaves it in the scratch planes, so that the plain walk keeps its loads free of aliasing stores
+#ifndef ROGER_NO_GAMMA52
+        if (cx.pl.rev[0] != nullptr) {
+            double* __restrict__ rev_a = cx.pl.rev[0];
+            double* __restrict__ rev_b = cx.pl.rev[1];
+            for (int j = 0; j < A; j++, c.next()) {
+                acc_a += s_rz[c.off];
+                acc_b += s_ss[c.off];
+                mx_rz.push(acc_a * m);
+                mx_ss.push(acc_b * m);
+                rev_a[cx.lin(j)] = acc_a * m;
+                rev_b[cx.lin(j)] = acc_b * m;
+            }
+        } else
+#endif
+        for (int j = 0; j < A; j++, c.next()) {
+            acc_a += s_rz[c.off];
+            acc_b += s_ss[c.off];
+            mx_rz.push(acc_a * m);
+            mx_ss.push(acc_b * m);
+        }
+    }
+    EulerFlux fx[5];  // evap_soil, transp, q_rz (root zone); cpr_rz, q_ss (subsoil)
+    Family fams[5];
+    {
+        const int procs[5] = {RSP_evap_soil, RSP_transp, RSP_q_rz, RSP_cpr_rz, RSP_q_ss};
+        const double flx[5] = {F(RSF_evap_soil), F(RSF_transp), F(RSF_q_rz), F(RSF_cpr_rz), F(RSF_q_ss)};
+        const double mxa = mx_rz.get(), mxb = mx_ss.get();
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            family_begin(fams[k], SP(procs[k]), C, m);
+#ifndef ROGER_NO_GAMMA52
+            if (fams[k].sp[0] == 52) {  // read backwards by omega(): the masked cumulative StorAge P1 left in the scratch planes
+                fams[k].rev = cx.pl.rev[(k < 3) ? 0 : 1] + i;
+                fams[k].rev_stride = C;
+            }
+#endif
+            family_prepare(fams[k], (k < 3) ? mxa : mxb);
+            fx[k].flux = flx[k];
+            fx[k].fh = flx[k] * h;
+            fx[k].active = !(fx[k].fh <= 0);
+            const Family& f = fams[k];
+            fx[k].sa_only = f.fast && !f.is_uniform && !f.is_dirac && !f.is_exp52;
+            fx[k].powfast = f.fast && f.is_pow && (f.S > 0) && div_range_ok(f.S) && (f.sp[1] - f.sp[1] == 0.0);
+            fx[k].S = f.S;
+            fx[k].y = f.sp[1];
+            fx[k].rS = 1.0 / f.S;
+        }
+    }
+    // one logarithm per layer and bin serves every power-law flux of the layer (skipped for empty bins)
+    const bool logs_a = (fx[0].active && fx[0].powfast) || (fx[1].active && fx[1].powfast) || (fx[2].active && fx[2].powfast);
+    const bool logs_b = (fx[3].active && fx[3].powfast) || (fx[4].active && fx[4].powfast);
+    const double S_a = fx[0].S, rS_a = fx[0].rS, S_b = fx[3].S, rS_b = fx[3].rS;
+    auto layer_log = [&](int layer, double SA, double sa_d) {
+        EulerLog g{0.0, 0.0, false, false};
+        if ((layer == 0 ? logs_a : logs_b) && !(sa_d == 0)) g = euler_log(cx, SA, layer == 0 ? S_a : S_b, layer == 0 ? rS_a : rS_b);
+        return g;
+    };
+    auto reset = [&]() {
+#pragma unroll
+        for (int k = 0; k < 5; k++) fx[k].om_prev = fx[k].active ? omega(fams[k], P, cx.tabs, 0, 0.0 * m) : 0.0;
+    };
+    // P2: normalisation constants
+    {
+        reset();
+        double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
+        double sums[5];
+        EULER_SUMS<5, 2>(cx.plan, EULER_SUMS_ARG
+            [&](int j, double* L) { const int64_t o = cx.ring(j); L[0] = s_rz[o]; L[1] = s_ss[o]; },
+            [&](int j, const double* L, double* v) {
+                acc_a += L[0];
+                acc_b += L[1];
+                const double na = acc_a * m, nb = acc_b * m;
+                const double da = na - SAa, db = nb - SAb;
+                SAa = na;
+                SAb = nb;
+                const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
+#pragma unroll
+                for (int k = 0; k < 5; k++) v[k] = euler_q(fx[k], fams[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
+            }, sums);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            fx[k].ssum = sums[k];
+            fx[k].ssum_ok = (sums[k] > 0) && div_range_ok(sums[k]);
+            fx[k].rssum = 1.0 / sums[k];
+        }
+    }
+    // P3: travel-time distributions, mixing, update
+    {
+        reset();
+#pragma unroll
+        for (int k = 0; k < 5; k++) { fx[k].accT = 0; fx[k].Tprev = 0; }
+        double acc_a = 0, acc_b = 0, SAa = 0.0 * m, SAb = 0.0 * m;
+        const double evap = fx[0].flux, transp = fx[1].flux, q_rz = fx[2].flux, cpr = fx[3].flux, q_ss = fx[4].flux;
+        double* __restrict__ tt_base = (LAST && P.store_tt && cx.pl.tt) ? cx.pl.tt : nullptr;
+        PctTracker trk[(LAST && STATS) ? 10 : 1];
+        double cdf_t = 0, cdf_s = 0;
+        NpMax cmax_t, cmax_s;
+        if (LAST && STATS) {
+            const double pcts[5] = {0.1, 0.25, 0.5, 0.75, 0.9};
+#pragma unroll
+            for (int k = 0; k < 5; k++) { trk[k].init(pcts[k]); trk[5 + k].init(pcts[k]); }
+        }
+        auto bin = [&](int j, const double* L, double* v) {
+            const int64_t o = cx.ring(j);
+            const double a = L[0], b = L[1];
+            const double ma = (ANION || j == 0) ? L[2] : clean_rz(L[2], a);
+            const double mb = (ANION || j == 0) ? L[3] : clean_ss(L[3], b);
+            acc_a += a;
+            acc_b += b;
+            const double na = acc_a * m, nb = acc_b * m;
+            const double da = na - SAa, db = nb - SAb;
+            SAa = na;
+            SAb = nb;
+            double tt[5];
+            const EulerLog ga = layer_log(0, na, da), gb = layer_log(1, nb, db);
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const double q = euler_q(fx[k], fams[k], cx, j, (k < 3) ? na : nb, (k < 3) ? da : db, (k < 3) ? ga : gb);
+                const double p = (q > 0) ? ((fx[k].ssum_ok && div_range_ok(q)) ? div_by(q, fx[k].ssum, fx[k].rssum) : q / fx[k].ssum) : 0;
+                fx[k].accT = (j == 0) ? p : fx[k].accT + p;  // np.cumsum starts from the first element
+                const double d = fx[k].accT - fx[k].Tprev;
+                fx[k].Tprev = fx[k].accT;
+                tt[k] = (d >= 0) ? d : 0;
+            }
+            const double tt_e = tt[0], tt_t = tt[1], tt_q = tt[2], tt_c = tt[3], tt_s = tt[4];
+            if (ANION) {
+                auto amtt = [](double sa_, double msa_, double alpha, double t, double fh) {  // calc_mtt, transport.py:582-596
+                    double w = ((sa_ > 0) ? (msa_ / sa_) : 0) * alpha * t * fh;
+                    w = (w <= 0) ? 0 : w;
+                    return (w > msa_) ? msa_ : w;
+                };
+                const double mt = amtt(a, ma, alpha_t, tt_t, fx[1].fh), mq = amtt(a, ma, alpha_q, tt_q, fx[2].fh);
+                const double mc = amtt(b, mb, alpha_q, tt_c, fx[3].fh), msq = amtt(b, mb, alpha_q, tt_s, fx[4].fh);
+                if (LAST) {
+                    v[0] = mt; v[1] = mq; v[2] = mc; v[3] = msq;
+                    if (STATS) {  // water-age statistics of the day's last step (transport.py:59-152), numerics.py:437-439
+                        v[4] = evap * tt_e; v[5] = transp * tt_t; v[6] = q_ss * tt_s;
+                        v[STATS ? 7 : 0] = tt_t; v[STATS ? 8 : 0] = tt_s;
+                        v[STATS ? 9 : 0] = (double)(j + 1) * tt_t; v[STATS ? 10 : 0] = (double)(j + 1) * tt_s;
+                        cdf_t += tt_t;
+                        cdf_s += tt_s;
+                        if (j == 0) { cmax_t.init(cdf_t); cmax_s.init(cdf_s); } else { cmax_t.push(cdf_t); cmax_s.push(cdf_s); }
+#pragma unroll
+                        for (int k = 0; k < 5; k++) { trk[k].push(j, cdf_t); trk[(STATS ? 5 : 0) + k].push(j, cdf_s); }
+                    }
+                    if (tt_base) {
+                        const int64_t span = (int64_t)A * C, l = cx.lin(j);
+                        tt_base[RSP_evap_soil * span + l] = tt_e;
+                        tt_base[RSP_transp * span + l] = tt_t;
+                        tt_base[RSP_q_rz * span + l] = tt_q;
+                        tt_base[RSP_cpr_rz * span + l] = tt_c;
+                        tt_base[RSP_q_ss * span + l] = tt_s;
+                    }
+                }
+                double dsa_rz = (cpr * tt_c - evap * tt_e - transp * tt_t - q_rz * tt_q) * h;
+                dsa_rz = (a + dsa_rz < 0) ? -a : dsa_rz;
+                double dsa_ss = (q_rz * tt_q - cpr * tt_c - q_ss * tt_s) * h;
+                dsa_ss = (b + dsa_ss < 0) ? -b : dsa_ss;
+                double a2 = a + dsa_rz, b2 = b + dsa_ss;
+                double dma = nan0(mc) - nan0(mt) - nan0(mq);
+                double dmb = nan0(mq) - nan0(mc) - nan0(msq);
+                dma = (ma + dma < 0) ? 0 : dma;
+                dmb = (mb + dmb < 0) ? 0 : dmb;
+                double ma2 = ma + dma, mb2 = mb + dmb;
+                a2 = (a2 < 1e-8) ? 0 : a2;   // anion storage kernels (root_zone.py:219-240, subsoil.py), run after every Euler step
+                b2 = (b2 < 1e-8) ? 0 : b2;
+                ma2 = (a2 <= 0) ? 0 : ma2;
+                mb2 = (b2 <= 0) ? 0 : mb2;
+                s_rz[o] = a2;
+                s_ss[o] = b2;
+                m_rz[o] = ma2;
+                m_ss[o] = mb2;
+                return;
+            }
+            const double mtt_c = (tt_c > 0) ? mb : 0, mtt_q = (tt_q > 0) ? ma : 0;
+            if (LAST) {
+                v[0] = tt_e; v[1] = ((tt_e > 0) ? ma : 0) * tt_e;
+                v[2] = tt_t; v[3] = ((tt_t > 0) ? ma : 0) * tt_t;
+                v[4] = tt_q; v[5] = mtt_q * tt_q;
+                v[6] = tt_c; v[7] = mtt_c * tt_c;
+                v[8] = tt_s; v[9] = ((tt_s > 0) ? mb : 0) * tt_s;
+                if (STATS) {  // transport.py:59-152 (TT[1:] = cumsum(tt)), numerics.py:437-439
+                    v[10] = evap * tt_e; v[11] = transp * tt_t; v[12] = q_ss * tt_s;
+                    v[13] = (double)(j + 1) * tt_t; v[14] = (double)(j + 1) * tt_s;
+                    cdf_t += tt_t;
+                    cdf_s += tt_s;
+                    if (j == 0) { cmax_t.init(cdf_t); cmax_s.init(cdf_s); } else { cmax_t.push(cdf_t); cmax_s.push(cdf_s); }
+#pragma unroll
+                    for (int k = 0; k < 5; k++) { trk[k].push(j, cdf_t); trk[5 + k].push(j, cdf_s); }
+                }
+                if (tt_base) {
+                    const int64_t span = (int64_t)A * C, l = cx.lin(j);
+                    tt_base[RSP_evap_soil * span + l] = tt_e;
+                    tt_base[RSP_transp * span + l] = tt_t;
+                    tt_base[RSP_q_rz * span + l] = tt_q;
+                    tt_base[RSP_cpr_rz * span + l] = tt_c;
+                    tt_base[RSP_q_ss * span + l] = tt_s;
+                }
+            }
+            double dsa_rz = (cpr * tt_c - evap * tt_e - transp * tt_t - q_rz * tt_q) * h;
+            dsa_rz = (a + dsa_rz < 0) ? -a : dsa_rz;
+            double dsa_ss = (q_rz * tt_q - cpr * tt_c - q_ss * tt_s) * h;
+            dsa_ss = (b + dsa_ss < 0) ? -b : dsa_ss;
+            const double dsa_rz1 = (cpr * tt_c) * h;
+            // (cpr * tt_c * h) / dsa_rz1 divides a value by itself: exactly 1 for a finite positive value
+            const double dmsa_rz1 = nan0(mtt_c) * ((dsa_rz1 > 0) ? self_ratio(dsa_rz1) : 0);
+            const double dsa_ss1 = (q_rz * tt_q) * h;
+            const double dmsa_ss1 = nan0(mtt_q) * ((dsa_ss1 > 0) ? self_ratio(dsa_ss1) : 0);
+            // a bin that receives nothing keeps its concentration: the general expression reduces to clean_*()
+            double ma2 = ma, mb2 = mb;
+            if (!(dsa_rz1 == 0 && dmsa_rz1 == 0 && j > 0)) { asm volatile(""); ma2 = euler_mix(ma, a, dsa_rz1, dmsa_rz1, true); }
+            if (!(dsa_ss1 == 0 && dmsa_ss1 == 0 && j > 0)) { asm volatile(""); mb2 = euler_mix(mb, b, dsa_ss1, dmsa_ss1, false); }
+            double a2 = a + dsa_rz, b2 = b + dsa_ss;
+            ma2 = (a2 <= 0) ? 0 : ma2;
+            mb2 = (b2 <= 0) ? 0 : mb2;
+            a2 = (a2 < 1e-8) ? 0 : a2;  // root_zone.py:196-199, subsoil.py:160-163 (run after every Euler step)
+            b2 = (b2 < 1e-8) ? 0 : b2;
+            s_rz[o] = a2;
+            s_ss[o] = b2;
+            m_rz[o] = ma2;
+            m_ss[o] = mb2;
+        };
+        auto load = [&](int j, double* L) {
+            const int64_t o = cx.ring(j);
+            L[0] = s_rz[o]; L[1] = s_ss[o]; L[2] = m_rz[o]; L[3] = m_ss[o];
+        };
+        if (LAST) {
+            constexpr int NS = ANION ? (STATS ? 11 : 4) : (STATS ? 15 : 10);
+            double sums[NS];
+            EULER_SUMS<NS, 4>(cx.plan, EULER_SUMS_ARG load, bin, sums);
+            if (ANION && STATS && es) {
+                const double qn = __longlong_as_double(0x7ff8000000000000LL);
+                es->wsum[0] = sums[STATS ? 4 : 0]; es->wsum[1] = sums[STATS ? 5 : 0]; es->wsum[2] = sums[STATS ? 6 : 0];
+#pragma unroll
+                for (int k = 0; k < 5; k++) { es->pct[0][k] = trk[k].result(A, cmax_t.get()); es->pct[1][k] = trk[(STATS ? 5 : 0) + k].result(A, cmax_s.get()); }
+                es->avg[0] = (sums[STATS ? 7 : 0] > 0) ? sums[STATS ? 9 : 0] : qn;
+                es->avg[1] = (sums[STATS ? 8 : 0] > 0) ? sums[STATS ? 10 : 0] : qn;
+            }
+            if (ANION) {  // :2378-2407; C_evap_soil and the M_* flux planes are not touched by the Euler solver
+                O(RSO_C_inf_mat_rz) = ((inf_mat * h > 0) ? C_in : 0) * m;
+                O(RSO_C_inf_pf_rz) = ((inf_pf * h > 0) ? C_in : 0) * m;
+                O(RSO_C_inf_pf_ss) = ((inf_ss * h > 0) ? C_in : 0) * m;
+                O(RSO_C_transp) = ((transp > 0) ? sums[0] / fx[1].fh : 0) * m;
+                O(RSO_C_q_rz) = ((q_rz > 0) ? sums[1] / fx[2].fh : 0) * m;
+                O(RSO_C_cpr_rz) = ((cpr > 0) ? sums[2] / fx[3].fh : 0) * m;
+                O(RSO_C_q_ss) = ((q_ss > 0) ? sums[3] / fx[4].fh : 0) * m;
+                return;
+            }
+            if (STATS && es) {
+                const double qn = __longlong_as_double(0x7ff8000000000000LL);
+                es->wsum[0] = sums[NS - 5]; es->wsum[1] = sums[NS - 4]; es->wsum[2] = sums[NS - 3];
+#pragma unroll
+                for (int k = 0; k < 5; k++) { es->pct[0][k] = trk[k].result(A, cmax_t.get()); es->pct[1][k] = trk[(STATS ? 5 : 0) + k].result(A, cmax_s.get()); }
+                es->avg[0] = (sums[2] > 0) ? sums[NS - 2] : qn;
+                es->avg[1] = (sums[8] > 0) ? sums[NS - 1] : qn;
+            }
+            // calc_conc_iso_flux :512-535, delta_fluxes_svat :3659-3697
+            const int oc[5] = {RSO_C_evap_soil, RSO_C_transp, RSO_C_q_rz, RSO_C_cpr_rz, RSO_C_q_ss};
+            const int oi[5] = {RSO_C_iso_evap_soil, RSO_C_iso_transp, RSO_C_iso_q_rz, RSO_C_iso_cpr_rz, RSO_C_iso_q_ss};
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                double conc = (sums[2 * k] > 0) ? sums[2 * k + 1] / sums[2 * k] : qnan;
+                conc = (conc != 0) ? conc : qnan;
+                conc = conc * m;
+                O(oc[k]) = conc;
+                O(oi[k]) = conc_to_delta(P, conc) * m;
+            }
+            const double c1 = ((inf_mat > 0) ? C_in : qnan) * m, c2 = ((inf_pf > 0) ? C_in : qnan) * m, c3 = ((inf_ss > 0) ? C_in : qnan) * m;
+            O(RSO_C_inf_mat_rz) = c1; O(RSO_C_iso_inf_mat_rz) = conc_to_delta(P, c1) * m;
+            O(RSO_C_inf_pf_rz) = c2; O(RSO_C_iso_inf_pf_rz) = conc_to_delta(P, c2) * m;
+            O(RSO_C_inf_pf_ss) = c3; O(RSO_C_iso_inf_pf_ss) = conc_to_delta(P, c3) * m;
+        } else {
+            double Lc[4], Ln[4], v[1];
+            load(0, Lc);
+            for (int j = 0; j < A; j++) {  // next bin's loads in flight while this bin computes
+                if (j + 1 < A) load(j + 1, Ln);
+                bin(j, Lc, v);
+#pragma unroll
+                for (int q = 0; q < 4; q++) Lc[q] = Ln[q];
+            }
+        }
+    }
+#undef F
+#undef O
+#undef SP
+}
+
+// The Runge-Kutta step (see the RK4 block below): the Euler step's building blocks as lambdas (`prepare`, `tt_of_bin`) so that the
+// four stages can re-evaluate them.  A function of its own: folding it into euler_step<> cost the Euler solver 14 % (measured,
+// 315 vs 276 ms per day at 262144 x 1000 -- the lambdas' captured state no longer stays in registers).
+template <bool LAST, bool STATS, bool ANION, bool RK4 = true>
+__device__ __noinline__ void rk4_step(const CellCtx& cx, const double* __restrict__ forcing, double m, const double* __restrict__ sas_params,
+                                        double* __restrict__ out, EulerStats* es, double alpha_t, double alpha_q) {
+    cx.assume_spaces();
+    const SasParams& P = cx.P;
+    const int A = P.A;
+    const int64_t C = P.C, i = cx.i;
+    double* __restrict__ s_rz = cx.pl.sa[0];
+    double* __restrict__ s_ss = cx.pl.sa[1];
+    double* __restrict__ m_rz = cx.pl.msa[0];
+    double* __restrict__ m_ss = cx.pl.msa[1];
+    ROGER_IS_GLOBAL(s_rz); ROGER_IS_GLOBAL(s_ss); ROGER_IS_GLOBAL(m_rz); ROGER_IS_GLOBAL(m_ss);
+    ROGER_IS_GLOBAL(forcing); ROGER_IS_GLOBAL(sas_params); ROGER_IS_GLOBAL(out);
     auto nan0 = [](double x) { return (x != x) ? 0.0 : x; };
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #define F(k) forcing[(int64_t)(k) * C + i]
@@ -1647,11 +2046,13 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
     bool any52 = false;  // family 52 reads the layer's cumulative StorAge backwards: the S passes below leave it in scratch planes
 #pragma unroll
     for (int k = 0; k < 5; k++) {
+#ifndef ROGER_NO_GAMMA52
         if (fams[k].sp[0] == 52) {
             any52 = true;
             fams[k].rev = cx.pl.rev[(k < 3) ? 0 : 1] + i;
             fams[k].rev_stride = C;
         }
+#endif
     }
     // one logarithm per layer and bin serves every power-law flux of the layer (skipped for empty bins)
     bool logs_a = false, logs_b = false;
@@ -2223,8 +2624,13 @@ __device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __res
     const SasParams& P = cx.P;
     const int64_t C = P.C, i = cx.i;
     const int n = P.substeps;
-    for (int s = 0; s + 2 < n; s++) euler_step<false, false, false, RK4>(cx, forcing, m, sas_params, out, nullptr, 1.0, 1.0);
-    if (n > 1) euler_step<false, false, false, RK4>(cx, forcing, m, sas_params, out, nullptr, 1.0, 1.0);
+    auto step = [&](auto last, EulerStats* es) {
+        constexpr bool L = decltype(last)::value;
+        if (RK4) rk4_step<L, L && STATS, false, true>(cx, forcing, m, sas_params, out, es, 1.0, 1.0);
+        else euler_step<L, L && STATS, false>(cx, forcing, m, sas_params, out, es, 1.0, 1.0);
+    };
+    for (int s = 0; s + 2 < n; s++) step(std::false_type{}, nullptr);
+    if (n > 1) step(std::false_type{}, nullptr);
     double sum_sa_s, C_s, sum_sa_rz, sum_sa_ss;
     double sum_sa_s_m1 = 0, Cp = 0;
     if (STATS) {  // [taum1] of the last Euler step: what its predecessor left (after_substep_iso, transport.py:3421-3520)
@@ -2239,7 +2645,7 @@ __device__ __forceinline__ void euler_day(const CellCtx& cx, const double* __res
         sum_sa_s_m1 = sm[0];
     }
     EulerStats es;
-    euler_step<true, STATS, false, RK4>(cx, forcing, m, sas_params, out, &es, 1.0, 1.0);
+    step(std::true_type{}, &es);
     storage_concentrations(cx, m, out, C, &sum_sa_s, &C_s, &sum_sa_rz, &sum_sa_ss);
     if (STATS) {
 #define F(k) forcing[(int64_t)(k) * C + i]
