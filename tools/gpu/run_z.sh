@@ -11,4 +11,4 @@ import json
 l=json.load(open('gpurun_out/r2z_bench.json'))
 print('value', l['value'], 'frac', l['roofline']['frac'], 'e2e', l['e2e']['value'], 'sas', l.get('sas',{}).get('value'), 'nitrate', l.get('nitrate',{}).get('value'))
 r=json.load(open('gpurun_out/r2z_bench_reference.json'))
-print('reference arm', r.get('value'), r.get('unit'), r.get('cpu_baseline'))"
+print('reference arm', r.get('value'), r.get('unit'))"
