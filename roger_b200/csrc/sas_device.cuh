@@ -137,10 +137,8 @@ struct Family {
     bool fast;         // every inactive family provably contributes +0.0
     // id 52 (the exponential family read backwards along the age axis, sas.py:183): the masked cumulative StorAge of the layer,
     // written by the caller before the pass -- element k * rev_stride holds SA[k + 1]
-#ifndef ROGER_NO_FAMILY_FIELDS
     const double* rev;
     int64_t rev_stride;
-#endif
 };
 
 __device__ __forceinline__ double s_rel(double S, const double* sp, double m) {
@@ -154,10 +152,8 @@ __device__ __forceinline__ void family_begin(Family& f, const double* sp_global,
 #pragma unroll
     for (int k = 0; k < 8; k++) f.sp[k] = sp_global[k * stride];
     f.m = m;
-#ifndef ROGER_NO_FAMILY_FIELDS
     f.rev = nullptr;
     f.rev_stride = 0;
-#endif
 }
 
 // per sub-step preparation: everything that depends on max(SA) only
@@ -226,7 +222,6 @@ __device__ __forceinline__ double omega(const Family& f, const SasParams& P, con
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
     }
-#ifndef ROGER_NO_GAMMA52  // (diagnostic builds only)
     if (f.is_gamma) {  // sas.py:137-160; S carries the family mask there, so every other id selects the constant 0 (skipped: + 0.0)
         const double S = f.S;
         double v = 0.;
@@ -235,19 +230,16 @@ __device__ __forceinline__ double omega(const Family& f, const SasParams& P, con
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
     }
-#endif
     if (f.is_exp51 || f.is_exp52 || !f.fast) {  // sas.py:163-191
         const double S = f.S;
         double o = 0.0;
         if (f.is_exp51) o = (SA > 0) ? ((SA < S) ? 1 - roger_exp(f.sp[1] * (-1) * (SA / S), tabs) : 1.) : 0.;
         o = o * m;
-#ifndef ROGER_NO_GAMMA52
         if (f.is_exp52) {  // [..., ::-1]: age index jj takes the value at nages - 1 - jj
             const int k = P.A - jj;
             const double SAr = (k == 0) ? 0.0 * m : f.rev[(int64_t)(k - 1) * f.rev_stride];
             o = (SAr > 0) ? ((SAr < S) ? 1 - roger_exp(f.sp[1] * (-1) * (SAr / S), tabs) : 1.) : 0.;
         }
-#endif
         o = o * m;
         o = ((S <= 0) ? 0 : o) * m;
         t += o;
@@ -795,13 +787,11 @@ __device__ __noinline__ bool solve_substeps(const CellCtx& cx, int src, double f
     const double fh = flux * h;
     for (int s = 0; s < P.substeps; s++) {  // transport.py:388-470
         double* rev_next = nullptr;
-#ifndef ROGER_NO_GAMMA52
         if (is52) {
             fam.rev = rv[s & 1] + cx.i;
             fam.rev_stride = P.C;
             rev_next = rv[(s + 1) & 1];
         }
-#endif
         family_prepare(fam, mx.get());
         const bool first = (s == 0);
         if (fam.fast && fam.is_pow && fam.S > 0 && div_range_ok(fam.S) && div_range_ok(fh)) {
@@ -1687,7 +1677,6 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
         Cursor c(P, i);
         // SAS family 52 (allocated by roger_sas_set_parameters when some cell uses it) reads the masked cumulative StorAge backwards:
         // a second copy of the walk leaves it in the scratch planes, so that the plain walk keeps its loads free of aliasing stores
-#ifndef ROGER_NO_GAMMA52
         if (cx.pl.rev[0] != nullptr) {
             double* __restrict__ rev_a = cx.pl.rev[0];
             double* __restrict__ rev_b = cx.pl.rev[1];
@@ -1700,7 +1689,6 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
                 rev_b[cx.lin(j)] = acc_b * m;
             }
         } else
-#endif
         for (int j = 0; j < A; j++, c.next()) {
             acc_a += s_rz[c.off];
             acc_b += s_ss[c.off];
@@ -1717,12 +1705,10 @@ __device__ __noinline__ void euler_step(const CellCtx& cx, const double* __restr
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             family_begin(fams[k], SP(procs[k]), C, m);
-#ifndef ROGER_NO_GAMMA52
             if (fams[k].sp[0] == 52) {  // read backwards by omega(): the masked cumulative StorAge P1 left in the scratch planes
                 fams[k].rev = cx.pl.rev[(k < 3) ? 0 : 1] + i;
                 fams[k].rev_stride = C;
             }
-#endif
             family_prepare(fams[k], (k < 3) ? mxa : mxb);
             fx[k].flux = flx[k];
             fx[k].fh = flx[k] * h;
@@ -2046,13 +2032,11 @@ __device__ __noinline__ void rk4_step(const CellCtx& cx, const double* __restric
     bool any52 = false;  // family 52 reads the layer's cumulative StorAge backwards: the S passes below leave it in scratch planes
 #pragma unroll
     for (int k = 0; k < 5; k++) {
-#ifndef ROGER_NO_GAMMA52
         if (fams[k].sp[0] == 52) {
             any52 = true;
             fams[k].rev = cx.pl.rev[(k < 3) ? 0 : 1] + i;
             fams[k].rev_stride = C;
         }
-#endif
     }
     // one logarithm per layer and bin serves every power-law flux of the layer (skipped for empty bins)
     bool logs_a = false, logs_b = false;
