@@ -547,7 +547,6 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
         const double xn = x + -tti * k.flux * k.h;
         san_o[u * C] = xn;
         c.acc_new += xn;
-        c.anynan = c.anynan || isnan_d(c.acc_new);
         c.mxv = (c.acc_new > c.mxv) ? c.acc_new : c.mxv;
         c.acc_t += tti;
         TTn_o[u * C] = (FIRST ? 0.0 : tb[u]) + c.acc_t;
@@ -606,7 +605,8 @@ __device__ __forceinline__ double substep_pass_pow(const CellCtx& cx, double S, 
         pt += U * C;
     }
     if (nfull * U < A) pow_pass_tail<FIRST>(k, c, tabs, ps, pt, C, A - nfull * U);
-    return c.anynan ? __longlong_as_double(0x7ff8000000000000LL) : c.mxv;
+    // np.max returns NaN when any cumulative sum is NaN; a NaN in the running sum stays (NaN + x = NaN), so its final value tells
+    return isnan_d(c.acc_new) ? __longlong_as_double(0x7ff8000000000000LL) : c.mxv;
 }
 
 // The same pass split in two walks (ROGER_SAS_SPLIT): (1) cumulative StorAge -> SAS function value of every bin, stored to the
