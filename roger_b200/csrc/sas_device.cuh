@@ -531,7 +531,8 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
         // SA >= 2^-500 and S <= 2^500 (checked by the caller) keep the quotient normal and div_by() exact
         const bool easy = in && (SA >= 0x1p-500);
         const double xr = div_by(SA, k.S, k.rS);
-        double p = roger_pow_core(easy ? roger_pow_asu(xr) : 0x3fe0000000000000ULL, k.y, tabs);
+        // outside `easy` the core runs on whatever bits xr has (arithmetic and a masked table index only) and its result is replaced
+        double p = roger_pow_core(roger_pow_asu(xr), k.y, tabs);
         if (in && !easy) p = roger_pow(SA / k.S, k.y, tabs);
         om[u] = (SA > 0) ? ((SA <= k.S) ? p : 1.) : 0.;
     }
@@ -543,7 +544,8 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
         double tti = (d >= 0) ? d : 0;
         const double q = k.flux * tti * k.h;
         const double ttqi = (q > x) ? x : q;
-        tti = (ttqi == 0 || div_range_ok(ttqi)) ? div_by(ttqi, k.fh, k.rfh) : ttqi / k.fh;
+        // div_by() is exact for ttqi = 0 and for 2^-500 <= ttqi <= 2^500; ttqi <= flux * h * tti <= fh <= 2^500 (checked by the caller)
+        tti = (ttqi == 0 || ttqi >= 0x1p-500) ? div_by(ttqi, k.fh, k.rfh) : ttqi / k.fh;
         const double xn = x + -tti * k.flux * k.h;
         san_o[u * C] = xn;
         c.acc_new += xn;
