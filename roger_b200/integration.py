@@ -281,10 +281,25 @@ class CudaStepDriver:
             vs.event_id = ev
         return sc
 
+    @staticmethod
+    def _is_uniform(a):
+        """every cell of the (nx, ny, slots) day block holds the row of cell (0, 0) (NaN == NaN, -0.0 == 0.0).  One chunked pass over the
+        bit patterns, no copy of the block: 0.3 s instead of 5 s per variable at 1024 x 1024 cells (the setups' `update(vs.prec_day, ...)`
+        materialises the block even when all cells share one series)."""
+        if a.dtype == np.float64 and a.strides[-1] == a.itemsize:
+            ai = a.view(np.int64)
+            ref = ai[0, 0, :]
+            if all(bool((ai[i0:i0 + 64] == ref).all()) for i0 in range(0, ai.shape[0], 64)):
+                return True
+        ref = a[0, 0, :]
+        return bool(np.all((a == ref) | (np.isnan(a) & np.isnan(ref))))
+
     def _hand_forcing_day(self):
         vs = self.state.variables
-        blocks = [np.asarray(getattr(vs, n))[2:-2, 2:-2, :].reshape(self.C, abi.SLOTS_PER_DAY) for n in ("prec_day", "ta_day", "pet_day")]
-        uniform_today = all(np.array_equal(b, np.broadcast_to(b[0], b.shape), equal_nan=True) for b in blocks)
+        views = [np.asarray(getattr(vs, n))[2:-2, 2:-2, :] for n in ("prec_day", "ta_day", "pet_day")]
+        uniform_today = None
+        if self.engine is None or self._uniform:  # (an engine built for per-cell forcing takes whatever comes)
+            uniform_today = all(self._is_uniform(a) for a in views)
         if self.engine is None:
             uniform = uniform_today if self._uniform is None else bool(self._uniform)
             self._create_engine(uniform)
@@ -293,9 +308,9 @@ class CudaStepDriver:
             if not uniform_today:
                 raise RuntimeError("forcing differs between cells but the engine was created for spatially uniform forcing; "
                                    "construct CudaStepDriver(..., forcing_uniform=False)")
-            self.engine.set_forcing_day(*[b[0].copy() for b in blocks])
+            self.engine.set_forcing_day(*[np.array(a[0, 0, :], dtype=np.float64) for a in views])
         else:
-            self.engine.set_forcing_day(*[np.ascontiguousarray(b, dtype=np.float64) for b in blocks])
+            self.engine.set_forcing_day(*[np.ascontiguousarray(a.reshape(self.C, abi.SLOTS_PER_DAY), dtype=np.float64) for a in views])
 
     def step(self):
         setup, state = self.setup, self.state

@@ -40,3 +40,24 @@ def test_offline_transport_setups_are_sent_to_the_transport_driver():
 
 def test_supported_setup_is_accepted():
     integration.CudaStepDriver(_setup(), engine_cls=OracleSvatEngine)
+
+
+def test_uniform_forcing_detection_handles_nan_slots_and_signed_zeros():
+    """day blocks of (nx, ny, 144): one series shared by all cells -- with gaps (NaN slots, which nanmean tolerates) and a -0.0 written
+    where another cell holds +0.0 -- counts as uniform; a single deviating cell does not"""
+    import numpy as np
+
+    from roger_b200.integration import CudaStepDriver
+
+    rng = np.random.default_rng(0)
+    full = np.empty((70, 5, 144))
+    full[:] = rng.random(144)
+    full[:, :, 7] = np.nan
+    a = full[2:-2, 1:-1, :]  # a strided interior view, as the driver sees it
+    assert CudaStepDriver._is_uniform(a)
+    full[40, 2, 9] = -0.0
+    full[:, :, 9] = np.where(np.arange(70)[:, None] == 40, -0.0, 0.0)
+    assert CudaStepDriver._is_uniform(a)
+    full[66, 3, 100] += 1e-9
+    assert not CudaStepDriver._is_uniform(a)
+    assert CudaStepDriver._is_uniform(full[2:-2, 1:-1, :].astype(np.float32)[:, :, :99])  # other dtypes take the value comparison
