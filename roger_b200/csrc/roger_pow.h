@@ -193,9 +193,15 @@ ROGER_POW_FN double roger_pow_from_log(double hi, double lo, double y, const rog
     const double elo = roger_pow_fma(y, lo, roger_pow_fma(y, hi, -ehi));
     const int ovf = !(ehi < RPK(ovf, 0x1.62e42fefa39efp+9)); /* >= 1024 ln2: overflow              */
     const int unf = ehi < RPK(unf, -0x1.6232bdd7abcd2p+9); /* result below 2^-1022: flushed to 0 */
+#if defined(ROGER_POW_CLEAN_INPUTS) && ROGER_POW_CLEAN_INPUTS
+    /* (the form the SVAT step kernel keeps: same bits, and the register allocation its 128-register budget was tuned with) */
+    const int out = ovf | unf;
+    const double res = roger_pow_exp(out ? 0.0 : ehi, out ? 0.0 : elo, tabs.exp_tab);
+#else
     /* out of range (or NaN) the reduction below runs on whatever ehi holds -- integer and floating-point operations only, the
      * table index is masked -- and its result is discarded by the selects: four selects fewer than cleaning the inputs first */
     const double res = roger_pow_exp(ehi, elo, tabs.exp_tab);
+#endif
     return ovf ? roger_pow_asd(0x7ff0000000000000ULL) : (unf ? 0.0 : res);
 }
 

@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "../../include/roger_b200.h"
+#define ROGER_POW_CLEAN_INPUTS 1  // see roger_pow_from_log: 1 % on the step kernel (4.78e9 vs 4.73e9 cell-timesteps/s)
 #include "roger_pow.h"
 
 namespace roger {
