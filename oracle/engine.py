@@ -227,8 +227,8 @@ class OracleSasEngine:
 
     # ---- crop variant (redistribution after root growth / root loss opens the day)
     def set_crop_parameters(self, sas_params_re_rg, sas_params_re_rl):
-        if self.settings.solute == 0 or self.settings.solver != 0 or self.settings.age_statistics:
-            raise NotImplementedError("crop variant: anion / nitrate solutes, deterministic solver, no age statistics")
+        if self.settings.solute == 0 or self.settings.solver != 0:
+            raise NotImplementedError("crop variant: anion / nitrate solutes, deterministic solver")
         self._crop_sp = [np.ascontiguousarray(a, dtype=np.float64).reshape(self.n, 8) for a in (sas_params_re_rg, sas_params_re_rl)]
         self._crop_out = np.zeros((6, self.n))
         self._crop_re = None

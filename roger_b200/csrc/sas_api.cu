@@ -634,9 +634,8 @@ int roger_sas_set_parameters(roger_sas* h, const double* mask_catch, const doubl
 
 int roger_sas_set_crop_parameters(roger_sas* h, const double* sas_params_re_rg, const double* sas_params_re_rl) {
     if (!h || !sas_params_re_rg || !sas_params_re_rl) return fail(ROGER_EINVAL, "roger_sas_set_crop_parameters: bad argument");
-    if (h->st.solute == 0 || h->st.solver != 0 || h->st.age_statistics)
-        return fail(ROGER_ENOTSUP, "roger_sas_set_crop_parameters: the crop variant runs anion / nitrate solutes with the deterministic solver "
-                                   "and without age statistics");
+    if (h->st.solute == 0 || h->st.solver != 0)
+        return fail(ROGER_ENOTSUP, "roger_sas_set_crop_parameters: the crop variant runs anion / nitrate solutes with the deterministic solver");
     CU(cudaSetDevice(h->device));
     const int64_t C = h->C;
     std::vector<double> rows((size_t)2 * 8 * (size_t)C), t;

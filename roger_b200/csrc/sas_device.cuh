@@ -1228,7 +1228,7 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
     }
     FluxStats fs_evap, fs_transp, fs_qss;
     double C_transp_v = 0, C_q_ss_v = 0, C_inf1 = 0, C_inf2 = 0, C_inf3 = 0;
-    if (!STATS && crop.re) {  // svat_crop_transport_model_deterministic (transport.py:1042-1051): redistribution opens the day
+    if (crop.re) {  // svat_crop_transport_model_deterministic (transport.py:1042-1051): redistribution opens the day
         // crop.py:2461-2558 (root growth: subsoil -> root zone), :2729-2828 (root loss: root zone -> subsoil): the flux is limited to the
         // water the source layer holds, the solute leaves with partition coefficient 1
         auto redistribute = [&](int src, int dst, double re_in, const double* sp, int k_re, int k_C, int k_M) {

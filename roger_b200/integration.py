@@ -532,9 +532,9 @@ class CudaTransportDriver:
         for flag in ("enable_groundwater", "enable_routing_1D", "enable_routing_2D", "enable_virtualtracer"):
             if getattr(st, flag, False):
                 raise NotImplementedError(f"offline transport with settings.{flag} is outside the CUDA hot path (DESIGN.md section 7)")
-        if self.crop and (not self.anion or self.euler or stats or self.lbc):
-            raise NotImplementedError("settings.enable_crop_phenology: anion / nitrate transport with the deterministic solver, without age "
-                                      "statistics and without the groundwater boundary")
+        if self.crop and (not self.anion or self.euler or self.lbc):
+            raise NotImplementedError("settings.enable_crop_phenology: anion / nitrate transport with the deterministic solver, without "
+                                      "the groundwater boundary")
         if self.lbc and self.euler:
             raise NotImplementedError("settings.enable_groundwater_boundary runs with the deterministic solver")
         if self.nitrate and self.euler:

@@ -66,6 +66,14 @@ CASES = {
     "sas_bromide_crop": dict(shape=(2, 2), ndays=16, ages=40, doy=100, solute="bromide", crop=True,
                              sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0),
                                       re_rg=(3, 0.7, 1.6), re_rl=(1,))),
+    # the crop variant with age statistics and balance errors (numerics.py:445-467: the water balance of the crop variant;
+    # :642-715: the bromide / nitrate solute balances do not exclude the crop model)
+    "sas_bromide_crop_stats": dict(shape=(2, 2), ndays=14, ages=40, doy=100, solute="bromide", crop=True, age_statistics=True,
+                                   sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0),
+                                            re_rg=(6, 0.5), re_rl=(6, 10.0))),
+    "sas_nitrate_crop_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=100, solute="nitrate", crop=True, age_statistics=True,
+                                   sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0),
+                                            re_rg=(3, 0.7, 1.6), re_rl=(6, 10.0))),
     # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
     "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
                          sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),

@@ -75,25 +75,29 @@ def test_oracle_reproduces_reference_nitrate_age_statistics_bit_for_bit():
 
 # ---- crop variant of the offline model: redistribution after root growth / root loss opens the day ----------------------------
 def crop_model_from_fixture(fx, engine_cls, engine_kwargs=None):
-    """fixtures sas_nitrate_crop / sas_bromide_crop (settings.enable_crop_phenology, svat_crop_transport_model_deterministic)"""
+    """fixtures sas_nitrate_crop / sas_bromide_crop (settings.enable_crop_phenology, svat_crop_transport_model_deterministic) and
+    their *_stats siblings (settings.enable_age_statistics on top)"""
     C, A = int(fx["nx"]) * int(fx["ny"]), int(fx["ages"])
+    stats = "rec_dC_num_error" in fx
     daily = {k[3:]: fx[k] for k in fx if k.startswith("in_")}
     spec = {p: fx["sas_" + p] for p in sas.PROCESSES + ["re_rg", "re_rl"]}
     anion = dict(alpha_transp=fx["par_alpha_transp"], alpha_q=fx["par_alpha_q"], lu_id=fx["par_lu_id"], S_sat_rz=fx["par_S_sat_rz"])
     if int(fx["solute"]) == 2:
         params = {k: fx["par_" + k] for k in nitrate.PARAMS + ["phi_soil_temp", "damp_soil_temp"]}
         m = nitrate.NitrateModel(engine_cls, C, A, daily, spec, params, anion, nitt=int(fx["ndays"]) + 1, pi=3.14159265358979323846264338327950588,
-                                 substeps=int(fx["substeps"]), store_tt=True, engine_kwargs=engine_kwargs, crop=True)
+                                 substeps=int(fx["substeps"]), store_tt=True, engine_kwargs=engine_kwargs, crop=True, age_statistics=stats)
         m.setup()
         for k, name in enumerate(nitrate.STATE):
             m.engine.upload_state_index(k, fx["init_" + name])
         m.temp_soil_given = np.concatenate([fx["rec_temp_soil"][:1], fx["rec_temp_soil"]])
     else:
         m = sas.SasModel(engine_cls, C, A, daily, spec, substeps=int(fx["substeps"]), store_tt=True, solute=sas.ANION, anion_parameters=anion,
-                         engine_kwargs=engine_kwargs, crop=True)
+                         engine_kwargs=engine_kwargs, crop=True, age_statistics=stats)
         m.setup()
         for k in sas.STATE:
             m.engine.upload_state(k, fx["init_" + k])
+    if stats:
+        m.engine.set_balance_reference(fx["init_C_s"])
     return m
 
 
@@ -108,13 +112,15 @@ def crop_snapshot(m, fx):
         snap[k] = o[k]
     for p in sas.PROCESSES:
         snap["tt_" + p] = m.tt(p)
+    if "rec_dC_num_error" in fx:
+        snap.update({k: v for k, v in m.statistics().items() if k != "sanity_ok"})
     return snap
 
 
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("case", ["sas_nitrate_crop", "sas_bromide_crop"])
+@pytest.mark.parametrize("case", ["sas_nitrate_crop", "sas_bromide_crop", "sas_nitrate_crop_stats", "sas_bromide_crop_stats"])
 def test_oracle_reproduces_reference_crop_variant_bit_for_bit(case):
     lib().sas_oracle_set_pow(0)
     fx = u.load_case(case)
