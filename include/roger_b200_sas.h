@@ -89,7 +89,10 @@ typedef struct roger_sas_settings {
                                1: conservative anion (bromide / chloride: msa holds bin solute MASS, the *_transport_anion_kernel
                                   family of the reference; the RSO_C_iso_* result planes then hold the solute masses M_*);
                                2: nitrate = the anion transport plus the soil nitrogen cycle (two more age-ranked arrays Nmin_rz,
-                                  Nmin_ss: state 4 and 5 of roger_sas_upload_state); deterministic solver */
+                                  Nmin_ss: state 4 and 5 of roger_sas_upload_state); deterministic solver;
+                               3: virtual tracer (settings.enable_virtualtracer): the anion transport whose soil evaporation carries the
+                                  solute with partition coefficient 1 (evapotranspiration.py:723-791: RSO_C_evap_soil, and M_evap_soil in
+                                  RSO_C_iso_evap_soil) and whose solute balance counts it (numerics.py:517-549); deterministic solver */
     int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day
                                (svat_transport_model_euler, transport.py:2063-2413; statistics / balance errors are those of the day's
                                last Euler step, as the reference's output shows them -- isotope and anion branch alike);
@@ -134,7 +137,7 @@ int roger_sas_download_nitrate_outputs(roger_sas *h, double *host);
  * roger/core/transport.py:1042-1087): every day then opens with crop.calculate_redistribution_transport (roger/core/crop.py:2829-2867,
  * anion kernels :2461-2558 and :2729-2828) -- water and solute move from the subsoil to the root zone after root growth (re_rg) and
  * back after root loss (re_rl), each a SAS-controlled withdrawal with its own parameter row (vs.sas_params_re_rg / _re_rl,
- * n_cells * 8 doubles each, same row layout as roger_sas_set_parameters).  Anion and nitrate solutes, deterministic solver, no age
+ * n_cells * 8 doubles each, same row layout as roger_sas_set_parameters).  Anion, nitrate and virtual-tracer solutes, deterministic solver, with or without age
  * statistics (ROGER_ENOTSUP otherwise).  The day's fluxes vs.re_rg, vs.re_rl (n_cells doubles each, host; an input of the offline
  * model, read from the SVAT-CROP output by the reference's setups) must be set before every roger_sas_step*. */
 int roger_sas_set_crop_parameters(roger_sas *h, const double *sas_params_re_rg, const double *sas_params_re_rl);

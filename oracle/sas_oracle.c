@@ -497,6 +497,9 @@ void sas_oracle_set_sanity_bounds(const double *S_sat_rz, const double *S_sat_ss
  * :622-679 ageing.
  * ================================================================================================================ */
 static const double *g_anion[4] = {NULL, NULL, NULL, NULL}; /* alpha_transp, alpha_q, lu_id, S_sat_rz */
+/* settings.solute == 3, the virtual tracer: the soil evaporation carries the solute with partition coefficient 1
+ * (evapotranspiration.py:723-791) and the solute balance counts it (numerics.py:517-549) */
+static int g_tracer = 0;
 void sas_oracle_set_anion_parameters(const double *alpha_transp, const double *alpha_q, const double *lu_id, const double *S_sat_rz)
 {
     g_anion[0] = alpha_transp; g_anion[1] = alpha_q; g_anion[2] = lu_id; g_anion[3] = S_sat_rz;
@@ -754,12 +757,21 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
     O(RSO_C_iso_inf_pf_rz) = O(RSO_C_inf_pf_rz) * F(RSF_inf_pf_rz) * m;    /* M_inf_pf_rz  */
     s_rz[0] += F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) * m;
     ms_rz[0] += O(RSO_C_iso_inf_mat_rz) + O(RSO_C_iso_inf_pf_rz) * m;
-    /* soil evaporation: water only */
+    /* soil evaporation: water only (evapotranspiration.py:620-651); the virtual tracer leaves with it (:723-791, alpha = 1 without mask) */
     anion_tt(c, s_rz, F(RSF_evap_soil), SP(RSP_evap_soil), m, tt, w2);
-    update_sa(A, s_rz, tt, F(RSF_evap_soil), m);
+    if (g_tracer) {
+        anion_mtt(A, s_rz, tt, F(RSF_evap_soil), ms_rz, 1.0, m, mtt);
+        const double M = np_sum(mtt, A);
+        O(RSO_C_evap_soil) = ((F(RSF_evap_soil) > 0) ? M / F(RSF_evap_soil) : 0) * m;
+        O(RSO_C_iso_evap_soil) = M * m; /* M_evap_soil */
+        update_sa(A, s_rz, tt, F(RSF_evap_soil), m);
+        for (int j = 0; j < A; j++) ms_rz[j] += -mtt[j] * m;
+    } else {
+        update_sa(A, s_rz, tt, F(RSF_evap_soil), m);
+        O(RSO_C_evap_soil) = 0;
+        O(RSO_C_iso_evap_soil) = 0;
+    }
     keep_tt(TTO(RSP_evap_soil), tt, A);
-    O(RSO_C_evap_soil) = 0;
-    O(RSO_C_iso_evap_soil) = 0;
     /* transpiration */
     {
         anion_tt(c, s_rz, F(RSF_transp), SP(RSP_transp), m, tt, w2);
@@ -878,6 +890,11 @@ static void anion_day_cell(const sas_ctx *c, int64_t C, int64_t i, double *s_rz,
                                             (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
                                              F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss)) -
                                              g_nit.out[(size_t)RNO_denit_s * (size_t)C + (size_t)i] + g_nit.out[(size_t)RNO_nit_s * (size_t)C + (size_t)i]) * 1.0);
+            else if (g_tracer) /* numerics.py:517-549: the evaporated tracer as well */
+                ST(RSS_dC_num_error) = fabs((S * O(RSO_C_s) - sum_sa_s_m1 * *bp_C) -
+                                            (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
+                                             F(RSF_inf_pf_ss) * nan0(O(RSO_C_inf_pf_ss)) - w[0] * nan0(O(RSO_C_evap_soil)) -
+                                             w[1] * nan0(O(RSO_C_transp)) - w[2] * nan0(O(RSO_C_q_ss))) * 1.0);
             else
             ST(RSS_dC_num_error) = fabs((S * O(RSO_C_s) - sum_sa_s_m1 * *bp_C) -
                                         (F(RSF_inf_mat_rz) * nan0(O(RSO_C_inf_mat_rz)) + F(RSF_inf_pf_rz) * nan0(O(RSO_C_inf_pf_rz)) +
@@ -1332,6 +1349,7 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
 {
     sas_ctx ctx = {st->ages, st->substeps, st->VSMOW_conc18O, st->d18O_min, st->d18O_max};
     const int A = ctx.A;
+    g_tracer = (st->solute == 3);
 #pragma omp parallel
     {
         double *work = (double *)malloc(sizeof(double) * (size_t)(16 * (A + 2)));
@@ -1501,6 +1519,7 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
     }
     sas_ctx ctx = {st->ages, st->substeps, st->VSMOW_conc18O, st->d18O_min, st->d18O_max};
     const int A = ctx.A;
+    g_tracer = (st->solute == 3);
 #pragma omp parallel
     {
         double *work = (double *)malloc(sizeof(double) * (size_t)(16 * (A + 2)));
@@ -1513,7 +1532,7 @@ void sas_oracle_day_stats(int64_t C, const roger_sas_settings *st, double *sa_rz
             const double m = mask[i];
             double *s_rz = sa_rz + (size_t)i * A, *s_ss = sa_ss + (size_t)i * A;
             double *ms_rz = msa_rz + (size_t)i * A, *ms_ss = msa_ss + (size_t)i * A;
-            if (st->solute == 1 || st->solute == 2) {
+            if (st->solute >= 1 && st->solute <= 3) {
                 anion_day_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, tt_out, work, tmp, stats, balance_prev, ttk, ages);
                 continue;
             }

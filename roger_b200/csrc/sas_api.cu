@@ -446,9 +446,10 @@ extern "C" {
 int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings* settings, int device) {
     if (!out || !settings || n_cells <= 0) return fail(ROGER_EINVAL, "roger_sas_create: bad argument");
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
-    if (settings->solute < 0 || settings->solute > 2) return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope), 1 (anion) or 2 (nitrate)");
-    if (settings->solute == 2 && settings->solver != 0)
-        return fail(ROGER_ENOTSUP, "roger_sas_create: nitrate runs with the deterministic solver");
+    if (settings->solute < 0 || settings->solute > 3)
+        return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope), 1 (anion), 2 (nitrate) or 3 (virtual tracer)");
+    if (settings->solute >= 2 && settings->solver != 0)
+        return fail(ROGER_ENOTSUP, "roger_sas_create: nitrate and the virtual tracer run with the deterministic solver");
     if (settings->solver < 0 || settings->solver > 2)
         return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic), 1 (Euler) or 2 (RK4)");
     if (settings->solver == 2 && settings->solute != 0)
@@ -722,9 +723,10 @@ static int step_common(roger_sas* h, const double* d_forcing) {
                                                                         ap, np_, h->crop(), nullptr, nullptr);
         h->have_nit_forcing = false;
         h->have_crop_re = false;
-    } else if (h->st.solute == 1) {
+    } else if (h->st.solute == 1 || h->st.solute == 3) {
         AnionParams ap{nullptr, nullptr, nullptr, nullptr};
         if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
+        ap.tracer = (h->st.solute == 3);
         if (h->st.age_statistics)
             k_sas_day_anion<true><<<blocks, threads, 0, h->stream>>>(h->params(), h->planes(), h->d_plan, d_forcing, h->d_mask, h->d_params,
                                                                      h->d_out, ap, h->d_stats, h->d_C_s_prev, h->crop());

@@ -1024,6 +1024,7 @@ struct AnionParams {  // per-cell planes (may be null: alpha = 1, no crops)
     const double* alpha_q;
     const double* lu_id;
     const double* S_sat_rz;
+    int tracer = 0;  // settings.solute == 3, the virtual tracer: the soil evaporation carries the solute (evapotranspiration.py:723-791)
 };
 
 // ================================================================================================================
@@ -1252,8 +1253,14 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
         s_rz[o0] = s_rz[o0] + (F(RSF_inf_mat_rz) + F(RSF_inf_pf_rz) * m);
         m_rz[o0] = m_rz[o0] + (M1 + M2 * m);
     }
-    anion_withdrawal<STATS>(cx, 0, -1, F(RSF_evap_soil), SP(RSP_evap_soil), C, m, 0.0, false, RSP_evap_soil, &fs_evap);  // water only
-    O(RSO_C_evap_soil) = 0; O(RSO_C_iso_evap_soil) = 0;
+    double C_evap_v = 0;
+    {   // soil evaporation: water only (evapotranspiration.py:620-651); the virtual tracer leaves with it, partition coefficient 1 (:723-791)
+        const bool vt = ap.tracer != 0;
+        const double M = anion_withdrawal<STATS>(cx, 0, -1, F(RSF_evap_soil), SP(RSP_evap_soil), C, m, vt ? 1.0 : 0.0, vt, RSP_evap_soil, &fs_evap);
+        C_evap_v = vt ? ((F(RSF_evap_soil) > 0) ? M / F(RSF_evap_soil) : 0) * m : 0.0;
+        O(RSO_C_evap_soil) = C_evap_v;
+        O(RSO_C_iso_evap_soil) = vt ? M * m : 0.0;
+    }
     {   // transpiration: crop nutrient uptake stops above 80 % saturation (evapotranspiration.py:931-938)
         const double lu = ap.lu_id ? ap.lu_id[i] : 0.0;
         bool crop_wet = false;
@@ -1347,6 +1354,10 @@ __device__ __forceinline__ void anion_day(const CellCtx& cx, const double* __res
                                             (F(RSF_inf_mat_rz) * nan0(C_inf1) + F(RSF_inf_pf_rz) * nan0(C_inf2) + F(RSF_inf_pf_ss) * nan0(C_inf3) -
                                              fs_transp.wsum * nan0(C_transp_v) - fs_qss.wsum * nan0(C_q_ss_v) -
                                              nitrate->out[(int64_t)RNO_denit_s * C + i] + nitrate->out[(int64_t)RNO_nit_s * C + i]) * 1.0);
+            else if (ap.tracer)  // numerics.py:517-549: the evaporated tracer as well
+                ST(RSS_dC_num_error) = fabs((sums[5] * C_s - sum_sa_s_m1 * Cp) -
+                                            (F(RSF_inf_mat_rz) * nan0(C_inf1) + F(RSF_inf_pf_rz) * nan0(C_inf2) + F(RSF_inf_pf_ss) * nan0(C_inf3) -
+                                             fs_evap.wsum * nan0(C_evap_v) - fs_transp.wsum * nan0(C_transp_v) - fs_qss.wsum * nan0(C_q_ss_v)) * 1.0);
             else
                 ST(RSS_dC_num_error) = fabs((sums[5] * C_s - sum_sa_s_m1 * Cp) -
                                             (F(RSF_inf_mat_rz) * nan0(C_inf1) + F(RSF_inf_pf_rz) * nan0(C_inf2) + F(RSF_inf_pf_ss) * nan0(C_inf3) -

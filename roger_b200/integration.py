@@ -513,9 +513,12 @@ class CudaTransportDriver:
         vs, st = self.state.variables, self.state.settings
         iso18, iso2 = bool(getattr(st, "enable_oxygen18", False)), bool(getattr(st, "enable_deuterium", False))
         self.nitrate = bool(getattr(st, "enable_nitrate", False))
-        self.anion = bool(getattr(st, "enable_bromide", False)) or bool(getattr(st, "enable_chloride", False)) or self.nitrate
+        # the virtual tracer is the anion model whose soil evaporation carries the solute (evapotranspiration.py:1014-1016)
+        self.tracer = bool(getattr(st, "enable_virtualtracer", False))
+        self.anion = bool(getattr(st, "enable_bromide", False)) or bool(getattr(st, "enable_chloride", False)) or self.nitrate or self.tracer
         if not getattr(st, "enable_offline_transport", False) or not (iso18 or iso2 or self.anion):
-            raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium / bromide / chloride / nitrate transport models")
+            raise ValueError("CudaTransportDriver drives the offline oxygen-18 / deuterium / bromide / chloride / nitrate / virtual-tracer "
+                             "transport models")
         solver = getattr(st, "sas_solver", None)
         if solver not in ("deterministic", "Euler", "RK4"):
             raise NotImplementedError(f"sas_solver = {solver!r}: 'deterministic', 'Euler' and 'RK4' run on the device")
@@ -529,7 +532,7 @@ class CudaTransportDriver:
         # (capillary_rise.py:590-611), and the reference then computes no balance errors (numerics.py:423-428, :1380-1387)
         self.crop = bool(getattr(st, "enable_crop_phenology", False))
         self.lbc = bool(getattr(st, "enable_groundwater_boundary", False))
-        for flag in ("enable_groundwater", "enable_routing_1D", "enable_routing_2D", "enable_virtualtracer"):
+        for flag in ("enable_groundwater", "enable_routing_1D", "enable_routing_2D"):
             if getattr(st, flag, False):
                 raise NotImplementedError(f"offline transport with settings.{flag} is outside the CUDA hot path (DESIGN.md section 7)")
         if self.crop and (not self.anion or self.euler or self.lbc):
@@ -537,8 +540,8 @@ class CudaTransportDriver:
                                       "the groundwater boundary")
         if self.lbc and self.euler:
             raise NotImplementedError("settings.enable_groundwater_boundary runs with the deterministic solver")
-        if self.nitrate and self.euler:
-            raise NotImplementedError("nitrate runs with the deterministic solver")
+        if (self.nitrate or self.tracer) and self.euler:
+            raise NotImplementedError("nitrate and the virtual tracer run with the deterministic solver")
 
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
         self.C = self.nx * self.ny
@@ -547,7 +550,7 @@ class CudaTransportDriver:
         # deuterium runs the same kernels with its own standard ratio and plausibility window (transport.py:315-340)
         vsmow, dmin, dmax = (st.VSMOW_conc2H, st.d2H_min, st.d2H_max) if iso2 else (st.VSMOW_conc18O, st.d18O_min, st.d18O_max)
         s = sas.SasSettings(self.A, int(st.sas_solver_substeps), float(vsmow), float(dmin), float(dmax), int(bool(store_tt)), int(self.stats),
-                            2 if self.nitrate else (sas.ANION if self.anion else sas.ISOTOPE),
+                            2 if self.nitrate else (sas.VIRTUALTRACER if self.tracer else (sas.ANION if self.anion else sas.ISOTOPE)),
                             {"deterministic": sas.DETERMINISTIC, "Euler": sas.EULER, "RK4": sas.RK4}[solver])
         self.settings = s
         self.engine = engine_cls(self.C, s, **(engine_kwargs or {}))

@@ -32,6 +32,7 @@ class SasSettings(C.Structure):
 
 
 ISOTOPE, ANION = 0, 1
+VIRTUALTRACER = 3  # roger_sas_settings.solute: the anion model whose soil evaporation carries the tracer (settings.enable_virtualtracer)
 DETERMINISTIC, EULER, RK4 = 0, 1, 2  # settings.sas_solver of the reference (roger/settings.py); RK4: isotope branch
 
 
@@ -95,6 +96,8 @@ class SasModel:
         # anion transport (roger/models/svat_bromide): dict alpha_transp, alpha_q, lu_id, S_sat_rz of n_cells values each
         self.anion_parameters = anion_parameters
         self.settings = default_settings(ages, substeps, store_tt, age_statistics, solute, solver)
+        if self.solute == VIRTUALTRACER:  # the host side is the anion model's; the engine's settings carry the 3
+            self.solute = ANION
         self.engine = engine_cls(self.C, self.settings, **(engine_kwargs or {}))
         self.mask = np.ones(self.C) if mask is None else np.asarray(mask, dtype=np.float64)
         self.sas_params = sas_parameter_block(self.C, sas_spec)

@@ -74,6 +74,13 @@ CASES = {
     "sas_nitrate_crop_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=100, solute="nitrate", crop=True, age_statistics=True,
                                    sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.25), transp=(6, 0.5), q_rz=(6, 2.0), q_ss=(6, 3.0),
                                             re_rg=(3, 0.7, 1.6), re_rl=(6, 10.0))),
+    # virtual tracer (settings.enable_virtualtracer): the anion model whose soil evaporation carries the tracer with partition
+    # coefficient 1 (evapotranspiration.py:723-791); its own solute balance (numerics.py:517-549); with and without the crop variant
+    "sas_virtualtracer": dict(shape=(2, 3), ndays=22, ages=50, doy=100, solute="virtualtracer", age_statistics=True,
+                              sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
+    "sas_virtualtracer_crop": dict(shape=(2, 2), ndays=16, ages=40, doy=100, solute="virtualtracer", crop=True,
+                                   sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0),
+                                            re_rg=(6, 0.5), re_rl=(6, 10.0))),
     # mixed families: uniform, Kumaraswamy, exponential, storage-dependent power, dirac
     "sas_families": dict(shape=(2, 3), ndays=20, ages=45, doy=130,
                          sas=dict(evap_soil=(1,), cpr_rz=(51, 2.0), transp=(3, 0.7, 1.6), q_rz=(61, 0.0, 0.0, 0.5, 2.0, 60.0, 160.0), q_ss=(35, 0.0, 0.0, 0.4, 1.5, 150.0, 700.0))),
@@ -130,7 +137,7 @@ def build(name):
         ciso = rng.uniform(-12, -5, (nx, ny, ndays + 1))
     ciso[:, :, 0] = np.nan
     case["C_ISO_IN"] = ciso
-    if c.get("solute") in ("bromide", "nitrate"):
+    if c.get("solute") in ("bromide", "nitrate", "virtualtracer"):
         # a bromide pulse dissolved in the rain of days 2..4 (mg/l), nothing afterwards
         cin = np.zeros((nx, ny, ndays + 1))
         wet = np.flatnonzero(case["PREC"][0, 0, 1:] > 0) + 1
@@ -190,8 +197,9 @@ SIMD_KEEP = ["sa_rz", "sa_ss", "C_rz", "C_iso_transp", "C_iso_q_ss"]
 def run(name, simd_out=None):
     case = build(name)
     nitrate = case.get("solute") == "nitrate"
-    bromide = case.get("solute") in ("bromide", "nitrate")
-    Setup = rh.make_nitrate_setup(case) if nitrate else (rh.make_bromide_setup(case) if bromide else rh.make_o18_setup(case))
+    tracer = case.get("solute") == "virtualtracer"
+    bromide = case.get("solute") in ("bromide", "nitrate", "virtualtracer")
+    Setup = rh.make_nitrate_setup(case) if nitrate else (rh.make_virtualtracer_setup(case) if tracer else (rh.make_bromide_setup(case) if bromide else rh.make_o18_setup(case)))
     crop = bool(case.get("crop"))
     if crop:
         Setup = rh.with_crop_redistribution(Setup, case)
@@ -211,6 +219,8 @@ def run(name, simd_out=None):
         scal_vars = ["C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz", "C_inf_mat_rz", "C_inf_pf_rz", "C_inf_pf_ss", "C_in",
                      "M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_inf_mat_rz", "M_inf_pf_rz", "M_inf_pf_ss"]
         lvl_vars = ["C_rz", "C_ss", "C_s", "M_rz", "M_ss", "M_s"]
+    if tracer:
+        scal_vars = scal_vars + ["C_evap_soil", "M_evap_soil"]
     if nitrate:
         age_vars = age_vars + ["Nmin_rz", "Nmin_ss"]
         scal_vars = scal_vars + ["nit_s", "denit_s", "min_s", "ngas_s", "nfix_s", "nh4_up"]
@@ -276,7 +286,7 @@ def run(name, simd_out=None):
     if case["sas_solver"] in ("Euler", "RK4"):
         out["solver"] = np.asarray({"Euler": 1, "RK4": 2}[case["sas_solver"]])
     if bromide:
-        out["solute"] = np.asarray(2 if nitrate else 1)
+        out["solute"] = np.asarray(2 if nitrate else (3 if tracer else 1))
         for k in ("alpha_transp", "alpha_q", "lu_id"):
             out["par_" + k] = np.asarray(case[k], dtype=np.float64).reshape(C)
     if nitrate:

@@ -598,6 +598,47 @@ def make_bromide_setup(case):
     return BromideSetup
 
 
+def make_virtualtracer_setup(case):
+    """Offline virtual-tracer transport (settings.enable_virtualtracer, examples/plot_scale/freiburg_altheim_kupferzell/svat_transport/
+    svat_transport.py:74, :385-392): the conservative-anion model in which the soil evaporation carries the tracer as well
+    (evapotranspiration.py:723-791, partition coefficient 1) and whose solute balance counts it (numerics.py:517-549).  `C_IN` is not
+    an active variable of this configuration (variables.py:5497-5512): the setup writes the day's `C_in` itself, as the example does."""
+    import_reference()
+    from roger import roger_routine
+    from roger.core.operators import update, at
+
+    Base = make_bromide_setup(case)
+
+    class VirtualTracerSetup(Base):
+        @roger_routine
+        def set_settings(self, state):
+            super().set_settings(state)
+            s = state.settings
+            s.identifier = "GOLDEN_VT"
+            s.enable_bromide = False
+            s.enable_virtualtracer = True
+
+        @roger_routine
+        def set_forcing_setup(self, state):
+            pass
+
+        @roger_routine
+        def set_forcing(self, state):
+            vs = state.variables
+            t = vs.itt
+            vs.prec = update(vs.prec, at[2:-2, 2:-2, vs.tau], case["PREC"][:, :, t])
+            for name, key in (("inf_mat_rz", "INF_MAT_RZ"), ("inf_pf_rz", "INF_PF_RZ"), ("inf_pf_ss", "INF_PF_SS"), ("transp", "TRANSP"),
+                              ("evap_soil", "EVAP_SOIL"), ("cpr_rz", "CPR_RZ"), ("q_rz", "Q_RZ"), ("q_ss", "Q_SS")):
+                setattr(vs, name, update(getattr(vs, name), at[2:-2, 2:-2], case[key][:, :, t]))
+            vs.S_rz = update(vs.S_rz, at[2:-2, 2:-2, vs.tau], case["S_RZ"][:, :, t])
+            vs.S_ss = update(vs.S_ss, at[2:-2, 2:-2, vs.tau], case["S_SS"][:, :, t])
+            vs.S_s = update(vs.S_s, at[2:-2, 2:-2, vs.tau], vs.S_rz[2:-2, 2:-2, vs.tau] + vs.S_ss[2:-2, 2:-2, vs.tau])
+            vs.C_in = update(vs.C_in, at[2:-2, 2:-2], case["C_IN"][:, :, t])
+            vs.M_in = update(vs.M_in, at[2:-2, 2:-2], vs.C_in[2:-2, 2:-2] * vs.prec[2:-2, 2:-2, vs.tau])
+
+    return VirtualTracerSetup
+
+
 def make_nitrate_setup(case):
     """Offline nitrate StorAge-selection transport with the soil nitrogen cycle: the bromide setup above with
     `settings.enable_nitrate` (transport.svat_transport_model_deterministic, roger/core/transport.py:948-991 -> nitrate.py) and the

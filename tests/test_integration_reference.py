@@ -153,7 +153,8 @@ def test_transport_driver_reproduces_reference_nitrate_step():
 
 
 @pytest.mark.parametrize("name,ndays,tight", [("sas_rk4_stats", 8, 8), ("sas_power_lbc", 5, 5), ("sas_nitrate_crop", 10, 10), ("sas_bromide_crop", 11, 4),
-                                              ("sas_nitrate_crop_stats", 10, 4), ("sas_bromide_crop_stats", 11, 4)])
+                                              ("sas_nitrate_crop_stats", 10, 4), ("sas_bromide_crop_stats", 11, 4),
+                                              ("sas_virtualtracer", 20, 4), ("sas_virtualtracer_crop", 11, 4)])
 def test_transport_driver_variants_reproduce_reference_step(name, ndays, tight):
     """RK4 solver (with age statistics); groundwater boundary (svat_lbc_transport_model_deterministic: same transport, balance errors
     left at 0); crop variant (redistribution after root growth / root loss) for nitrate and bromide.  The reference runs on NumPy's
@@ -170,7 +171,7 @@ def test_transport_driver_variants_reproduce_reference_step(name, ndays, tight):
     lib().roger_oracle_set_pow(0)
     case = mg.build(name)
     solute = case.get("solute")
-    Setup = rh.make_nitrate_setup(case) if solute == "nitrate" else (rh.make_bromide_setup(case) if solute == "bromide" else rh.make_o18_setup(case))
+    Setup = {"nitrate": rh.make_nitrate_setup, "bromide": rh.make_bromide_setup, "virtualtracer": rh.make_virtualtracer_setup}.get(solute, rh.make_o18_setup)(case)
     if case.get("crop"):
         Setup = rh.with_crop_redistribution(Setup, case)
     ref, dut = Setup(), Setup()
@@ -185,6 +186,8 @@ def test_transport_driver_variants_reproduce_reference_step(name, ndays, tight):
         names += ["M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_rz", "M_ss", "M_s"]
     if solute == "nitrate":
         names += ["Nmin_rz", "Nmin_ss", "Nmin_s", "nit_s", "denit_s", "min_s"]
+    if solute == "virtualtracer":  # settings.enable_virtualtracer: the soil evaporation carries the tracer
+        names += ["C_evap_soil", "M_evap_soil"]
     if case.get("crop"):
         names += list(sas.REDISTRIBUTION)
     if case["age_statistics"]:
@@ -206,6 +209,8 @@ def test_transport_driver_variants_reproduce_reference_step(name, ndays, tight):
             moved += float(np.asarray(b.re_rg).sum() + np.asarray(b.re_rl).sum())  # water moved between the layers
     if case.get("crop"):
         assert moved > 0
+    if name == "sas_virtualtracer":
+        assert float(np.nanmax(np.asarray(b.M_evap_soil))) > 0  # the pulse has arrived and evaporates
     if name == "sas_power_lbc":  # the reference leaves the balance errors at 0 under the groundwater boundary, and so does the driver
         assert float(np.abs(np.asarray(b.dS_num_error)).max()) == 0.0 and float(np.abs(np.asarray(a.dS_num_error)).max()) == 0.0
 

@@ -114,7 +114,7 @@ def test_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, oracle_ro
 
 
 # ---- crop variant (svat_crop_transport_model_deterministic): redistribution after root growth / root loss -----------------------
-@pytest.mark.parametrize("case", ["sas_nitrate_crop", "sas_bromide_crop", "sas_nitrate_crop_stats", "sas_bromide_crop_stats"])
+@pytest.mark.parametrize("case", ["sas_nitrate_crop", "sas_bromide_crop", "sas_nitrate_crop_stats", "sas_bromide_crop_stats", "sas_virtualtracer_crop"])
 def test_crop_variant_cuda_equals_oracle_bit_for_bit_on_fixture_inputs(case, oracle_roger_pow):
     from tests.test_nitrate_oracle_golden import crop_model_from_fixture, crop_snapshot
 
@@ -163,7 +163,8 @@ def test_crop_variant_needs_the_days_fluxes_and_rejects_other_configurations():
             _cuda()(4, sas.default_settings(8, **kw)).set_crop_parameters(rows[0], rows[1])
 
 
-@pytest.mark.parametrize("case", ["sas_nitrate", "sas_nitrate_crop", "sas_bromide_crop", "sas_nitrate_crop_stats", "sas_bromide_crop_stats"])
+@pytest.mark.parametrize("case", ["sas_nitrate", "sas_nitrate_crop", "sas_bromide_crop", "sas_nitrate_crop_stats", "sas_bromide_crop_stats",
+                                  "sas_virtualtracer_crop"])
 def test_cuda_reproduces_reference_fixture_bit_for_bit(case):
     """nitrate (anion transport + soil nitrogen cycle) and the crop variants (the *_stats ones with age statistics and balance errors) against the reference's own numbers, bit for bit on every
     day (the soil temperature, a host-side expression, is taken from the fixture as in the oracle pin)"""

@@ -91,7 +91,7 @@ def crop_model_from_fixture(fx, engine_cls, engine_kwargs=None):
             m.engine.upload_state_index(k, fx["init_" + name])
         m.temp_soil_given = np.concatenate([fx["rec_temp_soil"][:1], fx["rec_temp_soil"]])
     else:
-        m = sas.SasModel(engine_cls, C, A, daily, spec, substeps=int(fx["substeps"]), store_tt=True, solute=sas.ANION, anion_parameters=anion,
+        m = sas.SasModel(engine_cls, C, A, daily, spec, substeps=int(fx["substeps"]), store_tt=True, solute=int(fx["solute"]), anion_parameters=anion,
                          engine_kwargs=engine_kwargs, crop=True, age_statistics=stats)
         m.setup()
         for k in sas.STATE:
@@ -110,6 +110,8 @@ def crop_snapshot(m, fx):
     o = m.outputs()
     for k in ("C_rz", "C_ss", "C_s", "C_transp", "C_q_rz", "C_q_ss", "C_cpr_rz"):
         snap[k] = o[k]
+    if int(fx["solute"]) == 3:  # virtual tracer: the soil evaporation carries solute (evapotranspiration.py:723-791)
+        snap["C_evap_soil"], snap["M_evap_soil"] = o["C_evap_soil"], o["C_iso_evap_soil"]
     for p in sas.PROCESSES:
         snap["tt_" + p] = m.tt(p)
     if "rec_dC_num_error" in fx:
@@ -120,7 +122,7 @@ def crop_snapshot(m, fx):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("case", ["sas_nitrate_crop", "sas_bromide_crop", "sas_nitrate_crop_stats", "sas_bromide_crop_stats"])
+@pytest.mark.parametrize("case", ["sas_nitrate_crop", "sas_bromide_crop", "sas_nitrate_crop_stats", "sas_bromide_crop_stats", "sas_virtualtracer_crop"])
 def test_oracle_reproduces_reference_crop_variant_bit_for_bit(case):
     lib().sas_oracle_set_pow(0)
     fx = u.load_case(case)

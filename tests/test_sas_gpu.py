@@ -284,8 +284,9 @@ def test_anion_transport_against_reference_fixture():
             assert u.rel_err(snap[k], fx["rec_" + k][day]) < 1e-9, (k, day)
 
 
-@pytest.mark.parametrize("C_,A,ndays", [(300, 96, 10), (65, 513, 4), (1, 5, 6)])
-def test_anion_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, oracle_roger_pow):
+@pytest.mark.parametrize("C_,A,ndays,solute", [(300, 96, 10, 1), (65, 513, 4, 1), (1, 5, 6, 1), (300, 96, 10, 3), (40, 200, 5, 3)])
+def test_anion_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, solute, oracle_roger_pow):
+    """solute 1: conservative anion; 3: virtual tracer (the soil evaporation carries the solute, its balance error counts it)"""
     from roger_b200 import sas
 
     daily, spec = _random_case(C_, A, ndays, seed=900 + A)
@@ -296,7 +297,7 @@ def test_anion_cuda_equals_oracle_bit_for_bit_on_seeded_inputs(C_, A, ndays, ora
               S_sat_rz=daily["S_RZ"][:, 0] * rng.uniform(0.9, 2.0, C_))
     mask = np.ones(C_)
     mask[3::11] = 0.0
-    models = [sas.SasModel(e, C_, A, daily, spec, store_tt=True, mask=mask, solute=sas.ANION, anion_parameters=ap, age_statistics=(A != 513))
+    models = [sas.SasModel(e, C_, A, daily, spec, store_tt=True, mask=mask, solute=solute, anion_parameters=ap, age_statistics=(A != 513))
               for e in (_cuda(), oracle_roger_pow)]
     for m in models:
         m.setup()

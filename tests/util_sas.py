@@ -7,7 +7,7 @@ from roger_b200 import sas
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SAS_CASES = ["sas_power", "sas_power_snow", "sas_families", "sas_power_stats", "sas_power_300", "sas_power_1500"]
-ANION_CASES = ["sas_bromide"]
+ANION_CASES = ["sas_bromide", "sas_virtualtracer"]  # the latter: settings.enable_virtualtracer (the evaporation carries the tracer)
 RK4_CASES = ["sas_rk4", "sas_rk4_stats", "sas_rk4_52"]
 EULER_CASES = ["sas_euler", "sas_euler_families", "sas_euler_stats", "sas_euler_bromide", "sas_euler_52", "sas_euler_bromide_stats"]
 # gamma family (scipy.special.gammainc in the reference, roger_gamma.h here): pinned to 1e-10, not bit for bit
@@ -26,10 +26,10 @@ def model_from_fixture(fx, engine_cls, store_tt=True, engine_kwargs=None, mask=N
     spec = {p: fx["sas_" + p] for p in sas.PROCESSES}
     if age_statistics is None:
         age_statistics = "rec_dC_num_error" in fx
-    anion = "solute" in fx and int(fx["solute"]) == 1
+    anion = "solute" in fx and int(fx["solute"]) in (1, 3)
     kw = {}
     if anion:
-        kw = dict(solute=sas.ANION, anion_parameters=dict(alpha_transp=fx["par_alpha_transp"], alpha_q=fx["par_alpha_q"], lu_id=fx["par_lu_id"],
+        kw = dict(solute=int(fx["solute"]), anion_parameters=dict(alpha_transp=fx["par_alpha_transp"], alpha_q=fx["par_alpha_q"], lu_id=fx["par_lu_id"],
                                                           S_sat_rz=fx["par_S_sat_rz"]))
     if "solver" in fx:
         kw["solver"] = int(fx["solver"])
@@ -73,7 +73,7 @@ def snapshot(model):
         for p in sas.PROCESSES:
             out["tt_" + p] = model.tt(p)
     out.update(model.outputs())
-    if model.settings.solute == 1:  # anion transport: the C_iso_* result planes carry the solute masses M_*
+    if model.settings.solute in (1, 3):  # anion transport / virtual tracer: the C_iso_* result planes carry the solute masses M_*
         for k in list(out):
             if k.startswith("C_iso_"):
                 out["M_" + k[len("C_iso_"):]] = out.pop(k)
