@@ -92,7 +92,8 @@ typedef struct roger_sas_settings {
                                   Nmin_ss: state 4 and 5 of roger_sas_upload_state); deterministic solver;
                                3: virtual tracer (settings.enable_virtualtracer): the anion transport whose soil evaporation carries the
                                   solute with partition coefficient 1 (evapotranspiration.py:723-791: RSO_C_evap_soil, and M_evap_soil in
-                                  RSO_C_iso_evap_soil) and whose solute balance counts it (numerics.py:517-549); deterministic solver */
+                                  RSO_C_iso_evap_soil) and whose solute balance counts it (numerics.py:517-549); deterministic solver, and the Euler
+                                  scheme, whose anion branch it shares unchanged (transport.py:2308-2331) */
     int32_t solver;         /* 0: deterministic sub-step solver (transport.py:948-991); 1: explicit Euler with `substeps` steps per day
                                (svat_transport_model_euler, transport.py:2063-2413; statistics / balance errors are those of the day's
                                last Euler step, as the reference's output shows them -- isotope and anion branch alike);

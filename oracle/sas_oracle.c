@@ -1374,7 +1374,7 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
                     sum_sa_s_m1 = np_sum(tmp, A);
                     Cp = (ctx.substeps > 1) ? O(RSO_C_s) : balance_prev[i];
                 }
-                if (st->solute == 1) {
+                if (st->solute == 1 || st->solute == 3) { /* the virtual tracer runs the same anion branch (transport.py:2308): identical */
                     euler_substep_cell_anion(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out,
                                              tt_out ? tt_out + (size_t)i * A : ((stats && last) ? ttk : NULL), tt_out ? (size_t)C * A : (size_t)A, work);
                     storage_kernels_anion(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
@@ -1390,7 +1390,7 @@ static void euler_day(int64_t C, const roger_sas_settings *st, double *sa_rz, do
                 else euler_substep_cell(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, forcing, m, sas_params, out, (stats && last) ? ttk : NULL, (size_t)A, work);
                 storage_kernels_iso(&ctx, C, i, s_rz, s_ss, ms_rz, ms_ss, m, out, tmp);
             }
-            if (st->solute == 1) {
+            if (st->solute == 1 || st->solute == 3) {
                 if (stats) { /* age statistics (water only, transport.py:59-312) and the balance errors of the day's last Euler step:
                               * numerics.py:424-445 (water), :642-672 (bromide / chloride), both carrying settings.h */
                     const double h = 1.0 / ctx.substeps;

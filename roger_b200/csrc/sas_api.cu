@@ -448,8 +448,8 @@ int roger_sas_create(roger_sas** out, int64_t n_cells, const roger_sas_settings*
     if (settings->ages < 2 || settings->substeps < 1) return fail(ROGER_EINVAL, "roger_sas_create: ages >= 2 and substeps >= 1 required");
     if (settings->solute < 0 || settings->solute > 3)
         return fail(ROGER_EINVAL, "roger_sas_create: solute must be 0 (isotope), 1 (anion), 2 (nitrate) or 3 (virtual tracer)");
-    if (settings->solute >= 2 && settings->solver != 0)
-        return fail(ROGER_ENOTSUP, "roger_sas_create: nitrate and the virtual tracer run with the deterministic solver");
+    if (settings->solute == 2 && settings->solver != 0)
+        return fail(ROGER_ENOTSUP, "roger_sas_create: nitrate runs with the deterministic solver");
     if (settings->solver < 0 || settings->solver > 2)
         return fail(ROGER_EINVAL, "roger_sas_create: solver must be 0 (deterministic), 1 (Euler) or 2 (RK4)");
     if (settings->solver == 2 && settings->solute != 0)
@@ -683,7 +683,9 @@ static int step_common(roger_sas* h, const double* d_forcing) {
     const int blocks = (int)((h->C + threads - 1) / threads);
     if (h->st.solver != 0) {
         const int eb = (int)((h->C + ROGER_EULER_BLOCK - 1) / ROGER_EULER_BLOCK);
-        if (h->st.solute == 1) {
+        // the virtual tracer (solute 3) runs the anion branch of the Euler scheme unchanged: no solute leaves with the evaporation there
+        // (transport.py:2308-2331), so its balance error (numerics.py:517-549) subtracts w * C_evap_soil = w * 0 and keeps the anion bits
+        if (h->st.solute == 1 || h->st.solute == 3) {
             AnionParams ap{nullptr, nullptr, nullptr, nullptr};
             if (h->d_anion) ap = AnionParams{h->d_anion, h->d_anion + h->C, h->d_anion + 2 * h->C, h->d_anion + 3 * h->C};
             if (h->st.age_statistics)

@@ -540,8 +540,8 @@ class CudaTransportDriver:
                                       "the groundwater boundary")
         if self.lbc and self.euler:
             raise NotImplementedError("settings.enable_groundwater_boundary runs with the deterministic solver")
-        if (self.nitrate or self.tracer) and self.euler:
-            raise NotImplementedError("nitrate and the virtual tracer run with the deterministic solver")
+        if self.nitrate and self.euler:
+            raise NotImplementedError("nitrate runs with the deterministic solver")
 
         self.nx, self.ny, self.A = int(st.nx), int(st.ny), int(st.ages)
         self.C = self.nx * self.ny

@@ -93,6 +93,10 @@ CASES = {
                               sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
     "sas_euler_bromide_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=100, solute="bromide", sas_solver="Euler", age_statistics=True,
                                     sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
+    # the virtual tracer under the Euler scheme: the anion branch of svat_transport_model_euler (transport.py:2308-2331 -- no solute
+    # leaves with the evaporation there), the virtual tracer's own balance error (numerics.py:517-549)
+    "sas_euler_virtualtracer_stats": dict(shape=(2, 2), ndays=16, ages=40, doy=100, solute="virtualtracer", sas_solver="Euler", age_statistics=True,
+                                          sas=dict(evap_soil=(6, 0.1), cpr_rz=(6, 0.1), transp=(6, 0.3), q_rz=(6, 2.0), q_ss=(6, 3.0))),
     # Runge-Kutta solver (settings.sas_solver = "RK4")
     "sas_rk4": dict(shape=(2, 2), ndays=12, ages=40, doy=100, sas_solver="RK4",
                     sas=dict(evap_soil=(6, 0.2), cpr_rz=(6, 0.2), transp=(6, 0.5), q_rz=(6, 1.5), q_ss=(6, 1.5))),

@@ -154,7 +154,7 @@ def test_transport_driver_reproduces_reference_nitrate_step():
 
 @pytest.mark.parametrize("name,ndays,tight", [("sas_rk4_stats", 8, 8), ("sas_power_lbc", 5, 5), ("sas_nitrate_crop", 10, 10), ("sas_bromide_crop", 11, 4),
                                               ("sas_nitrate_crop_stats", 10, 4), ("sas_bromide_crop_stats", 11, 4),
-                                              ("sas_virtualtracer", 20, 4), ("sas_virtualtracer_crop", 11, 4)])
+                                              ("sas_virtualtracer", 20, 4), ("sas_virtualtracer_crop", 11, 4), ("sas_euler_virtualtracer_stats", 8, 4)])
 def test_transport_driver_variants_reproduce_reference_step(name, ndays, tight):
     """RK4 solver (with age statistics); groundwater boundary (svat_lbc_transport_model_deterministic: same transport, balance errors
     left at 0); crop variant (redistribution after root growth / root loss) for nitrate and bromide.  The reference runs on NumPy's

@@ -9,7 +9,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SAS_CASES = ["sas_power", "sas_power_snow", "sas_families", "sas_power_stats", "sas_power_300", "sas_power_1500"]
 ANION_CASES = ["sas_bromide", "sas_virtualtracer"]  # the latter: settings.enable_virtualtracer (the evaporation carries the tracer)
 RK4_CASES = ["sas_rk4", "sas_rk4_stats", "sas_rk4_52"]
-EULER_CASES = ["sas_euler", "sas_euler_families", "sas_euler_stats", "sas_euler_bromide", "sas_euler_52", "sas_euler_bromide_stats"]
+EULER_CASES = ["sas_euler", "sas_euler_families", "sas_euler_stats", "sas_euler_bromide", "sas_euler_52", "sas_euler_bromide_stats", "sas_euler_virtualtracer_stats"]
 # gamma family (scipy.special.gammainc in the reference, roger_gamma.h here): pinned to 1e-10, not bit for bit
 GAMMA_CASES = ["sas_gamma52"]
 
