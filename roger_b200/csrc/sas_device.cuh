@@ -510,6 +510,19 @@ struct PowPassConst {
     double S, rS, y, flux, h, fh, rfh;
 };
 
+// Experiment ROGER_SAS_COLD_OUTLINE=1: the two practically never-taken slow paths of the pass (a quotient outside the exact range of
+// div_by()) as calls instead of inline IEEE division sequences / the general pow (a third of the loop body).  Same bits.  Measured:
+// 88.1 -> 86.7 ms per day on tools/sas_timing.py (all cells alike, no empty bins), but 555 -> 622 ms per day on the BENCH workload
+// (empty bins, heterogeneous cells: gpurun_out/r3v_sas.log, r3w_bench_sas.json) -- not shipped.
+#ifndef ROGER_SAS_COLD_OUTLINE
+#define ROGER_SAS_COLD_OUTLINE 0
+#endif
+__device__ __noinline__ double pow_pass_cold_pow(double SA, double S, double y, const roger_pow_tables tabs) {
+    ROGER_IS_SHARED(tabs.log_tab); ROGER_IS_SHARED(tabs.exp_tab);
+    return roger_pow(SA / S, y, tabs);
+}
+__device__ __noinline__ double pow_pass_cold_div(double a, double b) { return a / b; }
+
 // N consecutive bins whose san / TTn values are already in registers (xb, tb)
 template <int N, bool FIRST>
 __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarry& c, const roger_pow_tables tabs, const double* xb,
@@ -533,7 +546,11 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
         const double xr = div_by(SA, k.S, k.rS);
         // outside `easy` the core runs on whatever bits xr has (arithmetic and a masked table index only) and its result is replaced
         double p = roger_pow_core(roger_pow_asu(xr), k.y, tabs);
+#if ROGER_SAS_COLD_OUTLINE
+        if (in && !easy) p = pow_pass_cold_pow(SA, k.S, k.y, tabs);
+#else
         if (in && !easy) p = roger_pow(SA / k.S, k.y, tabs);
+#endif
         om[u] = (SA > 0) ? ((SA <= k.S) ? p : 1.) : 0.;
     }
 #pragma unroll
@@ -545,7 +562,12 @@ __device__ __forceinline__ void pow_pass_bins(const PowPassConst& k, PowPassCarr
         const double q = k.flux * tti * k.h;
         const double ttqi = (q > x) ? x : q;
         // div_by() is exact for ttqi = 0 and for 2^-500 <= ttqi <= 2^500; ttqi <= flux * h * tti <= fh <= 2^500 (checked by the caller)
+#if ROGER_SAS_COLD_OUTLINE
+        if (ttqi == 0 || ttqi >= 0x1p-500) tti = div_by(ttqi, k.fh, k.rfh);
+        else tti = pow_pass_cold_div(ttqi, k.fh);
+#else
         tti = (ttqi == 0 || ttqi >= 0x1p-500) ? div_by(ttqi, k.fh, k.rfh) : ttqi / k.fh;
+#endif
         const double xn = x + -tti * k.flux * k.h;
         san_o[u * C] = xn;
         c.acc_new += xn;
