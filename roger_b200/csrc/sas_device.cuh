@@ -510,12 +510,13 @@ struct PowPassConst {
     double S, rS, y, flux, h, fh, rfh;
 };
 
-// Experiment ROGER_SAS_COLD_OUTLINE=1: the two practically never-taken slow paths of the pass (a quotient outside the exact range of
-// div_by()) as calls instead of inline IEEE division sequences / the general pow (a third of the loop body).  Same bits.  Measured:
-// 88.1 -> 86.7 ms per day on tools/sas_timing.py (all cells alike, no empty bins), but 555 -> 622 ms per day on the BENCH workload
-// (empty bins, heterogeneous cells: gpurun_out/r3v_sas.log, r3w_bench_sas.json) -- not shipped.
+// The two practically never-taken slow paths of the pass (a quotient outside the exact range of div_by()) are calls instead of inline
+// IEEE division sequences / the general pow, which made a third of the loop body.  Same bits.  Measured on the same commands
+// (gpurun_out/r3v_sas.log, r3w_bench_sas.json vs r3x_bench_sas.json): 88.1 -> 86.7 ms per day at 262 144 cells x 1000 bins (uniform
+// cells), 651.5 -> 622.5 ms per day over 48 days of the BENCH workload (1024 x 1024 cells x 1500 bins).  ROGER_SAS_COLD_OUTLINE=0
+// restores the inline form.
 #ifndef ROGER_SAS_COLD_OUTLINE
-#define ROGER_SAS_COLD_OUTLINE 0
+#define ROGER_SAS_COLD_OUTLINE 1
 #endif
 __device__ __noinline__ double pow_pass_cold_pow(double SA, double S, double y, const roger_pow_tables tabs) {
     ROGER_IS_SHARED(tabs.log_tab); ROGER_IS_SHARED(tabs.exp_tab);
