@@ -489,8 +489,16 @@ class CudaTransportDriver:
     `transport.svat_transport_model_deterministic` (core/transport.py:948-991) -- or, with `settings.sas_solver = "Euler"` / `"RK4"`,
     the day's explicit steps (`svat_transport_model_euler`, :2063-2413, `svat_transport_model_rk4`, :1138-2047, driven by :3221-3302) -- for
     every cell, and the results are written back into `vs` with both time levels as `after_substep_iso` (:3421-3520) leaves them.
-    Variants: `settings.enable_crop_phenology` (anion / nitrate: redistribution after root growth / root loss opens the day),
-    `settings.enable_groundwater_boundary` (same transport; the reference computes no balance errors then).
+    Solutes: oxygen-18 / deuterium, bromide / chloride, nitrate (`settings.enable_nitrate`: + the soil nitrogen cycle) and the virtual
+    tracer (`settings.enable_virtualtracer`: the anion model whose soil evaporation carries the tracer, evapotranspiration.py:723-791;
+    such a setup writes the day's `vs.C_in` itself -- `C_IN` is not an active variable there, variables.py:5497-5512).
+    Variants: `settings.enable_crop_phenology` (anion / nitrate / virtual tracer, with or without age statistics: redistribution after
+    root growth / root loss opens the day), `settings.enable_groundwater_boundary` (same transport; the reference computes no balance
+    errors then).  Not driven: the crop variant of the ISOTOPE models (its redistribution kernel ADDS the mixed concentration to the
+    root zone's instead of replacing it, crop.py:2406-2425 `update_add` -- concentrations double per day) and of the Euler scheme (its
+    anion branch reads `vs.q_re_rg`, a variable the reference does not declare, transport.py:3012).
+    Deviations kept on purpose: one result record per day under the Euler / RK4 schemes (the reference calls `write_output` after
+    every step of the day, transport.py:3240); the derived age-ranked arrays `SA_*`, `MSA_*`, `csa_*`, `TT_*` are not written back.
 
         model = MyOxygen18Setup(); model.setup(); model.warmup()
         driver = CudaTransportDriver(model)
