@@ -90,3 +90,39 @@ def test_two_ranks_equal_one_rank(tmp_path):
     # the partition matters: without the collective the ranks would take different time steps
     dts = np.asarray(scal1)[:, 1]
     assert len(set(dts.tolist())) > 1
+
+
+@pytest.mark.parametrize("case", ["sas_power_stats", "sas_virtualtracer"])
+def test_sas_cell_blocks_equal_the_whole_grid(case):
+    """The offline transport shards with no exchange at all: every rank steps its contiguous block of cells,
+    and the blocks put together are the whole grid bit for bit -- the reference fixture's cells, cut as `cell_block` cuts them."""
+    from oracle.engine import OracleSasEngine, lib
+    from roger_b200.parallel import cell_block
+    from tests import util_sas as u
+
+    lib().sas_oracle_set_pow(0)
+    fx = u.load_case(case)
+    C = int(fx["nx"]) * int(fx["ny"])
+    per_cell = lambda v: isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == C  # noqa: E731
+
+    def block(lo, hi):
+        sub = {}
+        for k, v in fx.items():
+            if k.startswith("rec_") or k.startswith("simd_"):
+                continue
+            sub[k] = v[lo:hi] if per_cell(v) else v
+        sub["nx"], sub["ny"] = np.asarray(hi - lo), np.asarray(1)
+        return u.model_from_fixture(sub, OracleSasEngine)
+
+    blocks = [cell_block(C, r, 2) for r in range(2)]
+    models = [block(lo, hi) for lo, hi in blocks]
+    for day in range(int(fx["ndays"])):
+        snaps = []
+        for m in models:
+            m.step()
+            snaps.append(u.snapshot(m))
+        for k in snaps[0]:
+            if "rec_" + k not in fx:
+                continue
+            got = np.concatenate([s[k] for s in snaps])
+            assert u.same(got, fx["rec_" + k][day]), (day, k)
