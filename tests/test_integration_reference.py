@@ -227,6 +227,23 @@ def test_transport_driver_refuses_what_the_reference_has_no_working_branch_for()
     m.setup()
     with pytest.raises(NotImplementedError, match="isotope branch only"):
         CudaTransportDriver(m, engine_cls=OracleSasEngine)
+    # the crop variant is driven for anion / nitrate / virtual-tracer solutes with the deterministic solver: the isotope crop model
+    # (its redistribution kernel doubles the bin concentrations per day, crop.py:2405-2425) and the Euler crop model (reads variables the
+    # reference does not declare, transport.py:3012) are refused loudly
+    case = mg.build("sas_power")
+    case["RE_RG"] = np.zeros((case["nx"], case["ny"], case["ndays"] + 1))
+    case["RE_RL"] = np.zeros((case["nx"], case["ny"], case["ndays"] + 1))
+    case["sas"] = dict(case["sas"], re_rg=np.zeros((case["nx"], case["ny"], 8)), re_rl=np.zeros((case["nx"], case["ny"], 8)))
+    m = rh.with_crop_redistribution(rh.make_o18_setup(case), case)()
+    m.setup()
+    with pytest.raises(NotImplementedError, match="enable_crop_phenology"):
+        CudaTransportDriver(m, engine_cls=OracleSasEngine)
+    case = mg.build("sas_bromide_crop")
+    case["sas_solver"] = "Euler"
+    m = rh.with_crop_redistribution(rh.make_bromide_setup(case), case)()
+    m.setup()
+    with pytest.raises(NotImplementedError, match="enable_crop_phenology"):
+        CudaTransportDriver(m, engine_cls=OracleSasEngine)
 
 
 def test_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_path):
