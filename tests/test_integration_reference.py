@@ -374,3 +374,58 @@ def test_transport_driver_writes_the_files_the_setups_diagnostics_ask_for(tmp_pa
                     got = f.variables[v][k].T
                     want_v = np.where(np.isnan(rec[v]), np.nan, rec[v])
                     assert rel_err(np.where(got == -9999, np.nan, got) if np.isnan(want_v).any() else got, want_v) < 1e-9, (name, v, k)
+
+
+@pytest.mark.parametrize("which", ["deuterium", "chloride"])
+def test_transport_driver_runs_the_sibling_solutes(which):
+    """settings.enable_deuterium runs the oxygen-18 kernels with its own standard ratio and plausibility window (transport.py:315-340:
+    VSMOW_conc2H, d2H_min / d2H_max), settings.enable_chloride the bromide kernels (the reference groups the two in every dispatch; only
+    the setup-time initial solute mass differs, soil.py:1508-1525, which is the reference's own code on both sides here)."""
+    import make_sas_golden as mg
+    import ref_harness as rh
+    from oracle.engine import OracleSasEngine, lib
+    from roger_b200 import sas
+    from roger_b200.integration import CudaTransportDriver
+    from tests.util_sas import rel_err
+
+    lib().roger_oracle_set_pow(0)
+    rh.import_reference()
+    from roger import roger_routine
+
+    if which == "deuterium":
+        case = mg.build("sas_power")
+        case["C_ISO_IN"] = 8.0 * case["C_ISO_IN"] + 10.0  # the meteoric water line
+        Base, on, off = rh.make_o18_setup(case), "enable_deuterium", "enable_oxygen18"
+    else:
+        case = mg.build("sas_bromide")
+        Base, on, off = rh.make_bromide_setup(case), "enable_chloride", "enable_bromide"
+
+    class Setup(Base):
+        @roger_routine
+        def set_settings(self, state):
+            super().set_settings(state)
+            setattr(state.settings, off, False)
+            setattr(state.settings, on, True)
+
+    ref, dut = Setup(), Setup()
+    for m in (ref, dut):
+        m.setup()
+        m.warmup()
+    driver = CudaTransportDriver(dut, engine_cls=OracleSasEngine)
+    if which == "deuterium":
+        st = dut.state.settings
+        assert driver.settings.VSMOW_conc18O == float(st.VSMOW_conc2H) and driver.settings.d18O_min == float(st.d2H_min)
+    a, b = ref.state.variables, dut.state.variables
+    meta = ref.state.var_meta
+    names = list(sas.STATE) + [n for n in sas.OUTPUTS if n in meta and meta[n].active and n != "C_evap_soil"]
+    if which == "chloride":
+        names = [n for n in names if not n.startswith("C_iso")] + ["M_transp", "M_q_rz", "M_q_ss", "M_cpr_rz", "M_rz", "M_ss", "M_s"]
+    for day in range(5):  # the days before the first rounding-decided clamp of the power-law solver (SVML `power` on the reference side)
+        ref.step(ref.state)
+        driver.step()
+        for n in names:
+            x, y = np.asarray(getattr(a, n))[2:-2, 2:-2], np.asarray(getattr(b, n))[2:-2, 2:-2]
+            lim = 1e-8 if n.startswith("C_iso") else 1e-10  # delta values amplify concentration rounding
+            assert rel_err(y, x) < lim, (day, n, rel_err(y, x))
+    if which == "deuterium":  # concentrations on deuterium's scale (VSMOW 2H/1H = 1.5576e-4), not oxygen-18's (2.0052e-3)
+        assert float(np.nanmax(np.asarray(b.C_rz)[2:-2, 2:-2])) < 1e-3 < float(sas.delta_to_conc(-10.0))
